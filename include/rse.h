@@ -1,0 +1,199 @@
+/*
+ * rse.h — C-ABI of librse.so, the B200-native retrieval core that replaces the
+ * query hot path of JWSch4fer/rag-search-engine.
+ *
+ * Plain C: opaque handle, raw pointers and sizes, int status codes, no
+ * exceptions and no torch/numpy types across the boundary.  The reference is
+ * pure Python, so the reference-side binding is a ctypes stub;
+ * each entry point names the reference interface it replaces (file:line are
+ * relative to /root/reference/rag_search_engine/).
+ *
+ * Conventions
+ *   - every function returns RSE_OK (0) or a negative RSE_ERR_* code;
+ *     rse_last_error(h) gives the message (h may be NULL for rse_create).
+ *   - "host" pointers are caller-owned CPU buffers; "dev" pointers are
+ *     caller-owned device buffers on the handle's device (the *_dev entry
+ *     points are what the torch.distributed host plumbing uses; they enqueue
+ *     on the handle's stream and do not synchronise).
+ *   - one handle = one device + one CUDA stream; calls on a handle are
+ *     synchronous unless stated and not re-entrant (the reference objects are
+ *     single-threaded too: utils/basesearch_db.py:40).
+ *   - there is NO CPU fallback: without a CUDA device rse_create fails.
+ */
+#ifndef RSE_H_
+#define RSE_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define RSE_ABI_VERSION 1
+
+#define RSE_OK 0
+#define RSE_ERR_INVALID -1     /* bad argument */
+#define RSE_ERR_CUDA -2        /* CUDA runtime error (message has the call) */
+#define RSE_ERR_STATE -3       /* e.g. query before load */
+#define RSE_ERR_UNSUPPORTED -4 /* outside documented limits */
+#define RSE_ERR_NOMEM -5
+
+/* Limits (documented in DESIGN.md §limits) */
+#define RSE_VEC0_BLOCK 1024     /* sqlite-vec default chunk_size (semantic_search.py:96-99 passes none) */
+#define RSE_MAX_KPRIME 4096     /* sqlite-vec caps k at 4096 */
+#define RSE_MAX_BM25_K 256
+#define RSE_MAX_FUSE_LIMIT 128
+#define RSE_MAX_QUERY_TOKENS 255
+#define RSE_RRF_NOT_FOUND 99999 /* hybrid_search.py:247 */
+
+/* tie_mode for the fusion entry points */
+#define RSE_TIE_REFERENCE 0 /* CPython set iteration order of the id union (hybrid_search.py:148,248) */
+#define RSE_TIE_BY_ID 1     /* deterministic by ascending id (north_star wording) */
+
+typedef struct rse_index rse_index;
+
+int rse_abi_version(void);
+
+/* Create a handle bound to CUDA device `device`.  Fails (RSE_ERR_CUDA) when no
+ * device is present.  Replaces the object construction at
+ * utils/hybrid_search.py:41-54 (one KeywordSearch + one SemanticSearch). */
+int rse_create(int32_t device, rse_index **out);
+void rse_destroy(rse_index *h);
+const char *rse_last_error(const rse_index *h);
+
+/* Use an externally owned CUDA stream (cudaStream_t as void*), e.g. torch's
+ * current stream; NULL restores the handle's own stream. */
+int rse_set_stream(rse_index *h, void *cuda_stream);
+/* Block until everything enqueued on the handle's stream has finished. */
+int rse_synchronize(rse_index *h);
+
+/* ------------------------------------------------------------------ a1: vec0 store
+ * Replaces the vec0 virtual table `chunk_embeddings` (semantic_search.py:94-101)
+ * as the thing the KNN scans.  Rows are given in vec0 PHYSICAL layout: row i of
+ * `emb` is (block pos_base/1024 + i/1024, slot i%1024); `valid[i]==0` marks an
+ * empty slot (NULL: all valid).  `rowid` (NULL: rowid = pos_base + i) is
+ * chunks.id; `movie_idx` (NULL: aggregation unavailable) is the dense index of
+ * chunks.movie_id in the caller's sorted id universe, or -1 when the JOIN at
+ * semantic_search.py:262-276 would drop the row.  pos_base must be a multiple of
+ * 1024 (row shards are aligned to vec0 blocks).  use_fma selects the aarch64
+ * (contracted) arithmetic of sqlite-vec instead of the x86-64 one.
+ * The host variant copies; the dev variant BORROWS emb_dev (caller keeps it
+ * alive) and copies the small side arrays. */
+int rse_load_embeddings(rse_index *h, const float *emb_host, int64_t n_rows, int32_t dim,
+                        const uint8_t *valid_host, const int64_t *rowid_host,
+                        const int32_t *movie_idx_host, int64_t pos_base);
+int rse_attach_embeddings_dev(rse_index *h, const float *emb_dev, int64_t n_rows, int32_t dim,
+                              const uint8_t *valid_dev, const int64_t *rowid_dev,
+                              const int32_t *movie_idx_dev, int64_t pos_base);
+int rse_set_fma(rse_index *h, int32_t use_fma);
+
+/* KNN: `embedding MATCH :q AND k = :k ... ORDER BY knn.distance`
+ * (semantic_search.py:254-279).  Q is [nq, dim] fp32.  Outputs are [nq, kprime]
+ * in vec0 emit order (distance asc, block asc, slot desc); out_count[q] <= kprime
+ * rows are valid.  out_pos / out_rowid / out_movie_idx may be NULL. */
+int rse_knn(rse_index *h, const float *q_host, int32_t nq, int32_t kprime, float *out_dist,
+            int64_t *out_pos, int64_t *out_rowid, int32_t *out_movie_idx, int32_t *out_count);
+
+/* KNN + best-chunk-per-movie aggregation = SemanticSearch.query_top_k numerics
+ * (semantic_search.py:250-317): top-kprime chunks, first row per movie, first k.
+ * Outputs [nq, k]. */
+int rse_knn_movies(rse_index *h, const float *q_host, int32_t nq, int32_t k, int32_t kprime,
+                   float *out_dist, int64_t *out_chunk_rowid, int32_t *out_movie_idx,
+                   int32_t *out_count);
+
+/* Device-pointer building blocks for the row-sharded multi-GPU path.
+ * Local top-kprime as packed candidates: cand_dev is [nq, kprime, 3] int64 =
+ * {key, rowid, movie_idx}; key = (orderable(distance) << 32) | (global_pos ^ 1023),
+ * so ascending key IS the vec0 emit order; unused tail entries have key = -1
+ * (all ones).  q_dev is [nq, dim] fp32 on the device. */
+int rse_knn_local_dev(rse_index *h, const float *q_dev, int32_t nq, int32_t kprime,
+                      int64_t *cand_dev);
+/* Merge n_lists candidate lists per query (gathered_dev is [n_lists, nq, kprime, 3],
+ * the layout all_gather produces), keep the first kprime under the key order, then
+ * aggregate per movie like rse_knn_movies.  Outputs are DEVICE buffers [nq, k]. */
+int rse_knn_merge_movies_dev(rse_index *h, const int64_t *gathered_dev, int32_t n_lists,
+                             int32_t nq, int32_t k, int32_t kprime, float *out_dist_dev,
+                             int64_t *out_chunk_rowid_dev, int32_t *out_movie_idx_dev,
+                             int32_t *out_count_dev);
+
+/* ------------------------------------------------------------------ a6: BM25 index
+ * Replaces the SQLite tables terms/postings/doclen as the thing
+ * KeywordSearch.search (keyword_search.py:180-250) scores against.
+ *   indptr[T+1], doc_idx[P] (dense doc index, ascending within a term — the
+ *   order the (term_id, doc_id) autoindex yields, :214-218), tf[P] =
+ *   len(positions) (:227-228), df[T] = len(rows) (:222; may exceed the CSR
+ *   length when postings without a doclen row were dropped, :235-236),
+ *   dl[M] = doclen.length, n_movies = COUNT(movies) (:196), avgdl = AVG(length)
+ *   (:197-198). */
+int rse_load_bm25(rse_index *h, const int64_t *indptr, const uint32_t *doc_idx, const uint32_t *tf,
+                  const int64_t *df, int64_t n_terms, int64_t n_postings, const uint32_t *dl,
+                  int64_t n_docs, int64_t n_movies, double avgdl);
+
+/* BM25 top-k for a batch of tokenised queries.  tok_indptr[nq+1] delimits each
+ * query's tokens in `term_rows` (CSR term row per token in query order,
+ * duplicates kept, -1 = unknown term, skipped: keyword_search.py:205-210).
+ * Outputs [nq, k]: scores (fp64, bit-exact reference arithmetic :224,:241-244),
+ * dense doc indices, and per-query counts.  Order = sorted(..., reverse=True)
+ * with dict-insertion tie order (:250). */
+int rse_bm25(rse_index *h, const int32_t *tok_indptr, const int32_t *term_rows, int32_t nq,
+             int32_t k, double k1, double b, double *out_score, int32_t *out_doc_idx,
+             int32_t *out_count);
+
+/* ------------------------------------------------------------------ a8-a10: fusion
+ * ids are the caller's document ids (movies.id).  Inputs [nq, limit] with
+ * per-query counts; BM25 lists are score-descending, semantic lists
+ * distance-ascending (what the retrievers return).  Outputs [nq, limit].
+ * weighted: hybrid_search.py:117-180 (min_max_norm utils.py:182-191,
+ *           alpha*b + (1-alpha)*s :163).
+ * rrf:      hybrid_search.py:217-272,379 (0-based ranks, NOT_FOUND=99999 :247,
+ *           1/(k+r_b) + 1/(k+r_s) :255); out ranks are -1 for None. */
+int rse_fuse_weighted(rse_index *h, int32_t nq, int32_t limit, double alpha, int32_t tie_mode,
+                      const int64_t *bm25_id, const double *bm25_score, const int32_t *bm25_count,
+                      const int64_t *sem_id, const float *sem_dist, const int32_t *sem_count,
+                      int64_t *out_id, double *out_bm25, double *out_sem, double *out_score,
+                      int32_t *out_count);
+int rse_fuse_rrf(rse_index *h, int32_t nq, int32_t limit, double k, int32_t tie_mode,
+                 const int64_t *bm25_id, const double *bm25_score, const int32_t *bm25_count,
+                 const int64_t *sem_id, const float *sem_dist, const int32_t *sem_count,
+                 int64_t *out_id, double *out_score, int32_t *out_bm25_rank, int32_t *out_sem_rank,
+                 int32_t *out_count);
+
+/* ------------------------------------------------------------------ hybrid, end to end
+ * HybridSearch.rrf_search / weighted_search numerics for a batch (hybrid_search.py:91-180,
+ * 183-272): BM25(k=limit) + KNN(k=limit, kprime=max(limit*knn_multiplier, limit),
+ * semantic_search.py:251) + fusion, all on the device, one host round trip.
+ * doc_ids[n_docs] / movie_ids[n_movies_uni] map dense indices to movies.id (set with
+ * rse_set_id_tables).  mode: 0 = rrf (param = k), 1 = weighted (param = alpha).
+ * Outputs [nq, limit]; out_a/out_b = (bm25_rank, sem_rank) as doubles for rrf
+ * (-1 = None) or (bm25_norm, sem_norm) for weighted. */
+int rse_set_id_tables(rse_index *h, const int64_t *doc_ids, int64_t n_docs, const int64_t *movie_ids,
+                      int64_t n_movie_ids);
+int rse_hybrid(rse_index *h, int32_t mode, double param, int32_t tie_mode, int32_t limit,
+               int32_t knn_multiplier, int32_t nq, const float *q_host, const int32_t *tok_indptr,
+               const int32_t *term_rows, double k1, double b, int64_t *out_id, double *out_score,
+               double *out_a, double *out_b, int32_t *out_count);
+
+/* ------------------------------------------------------------------ introspection
+ * Counters since the last rse_stats_reset: kernels launched by this library,
+ * device ms of the last call per stage (CUDA events on the handle's stream). */
+typedef struct rse_stats {
+  int64_t kernel_launches;
+  int64_t knn_scan_launches;
+  double last_knn_scan_ms;   /* sum of scan-kernel time in the last knn call */
+  double last_knn_total_ms;  /* scan + select + aggregate */
+  double last_bm25_ms;
+  double last_fuse_ms;
+  int64_t emb_rows;
+  int32_t emb_dim;
+  int64_t bm25_postings;
+  int64_t bm25_docs;
+} rse_stats;
+int rse_get_stats(rse_index *h, rse_stats *out);
+int rse_stats_reset(rse_index *h);
+/* Enable per-stage CUDA-event timing (adds event records + a sync per call). */
+int rse_set_timing(rse_index *h, int32_t enabled);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* RSE_H_ */

@@ -1,0 +1,237 @@
+// knn_scan.cuh — K1: exact vec0-cosine scan of the chunk-embedding matrix.
+//
+// Replaces the per-row `distance_cosine_float` loop that sqlite-vec runs inside
+// `embedding MATCH :q AND k = :k` (reference call site
+// rag_search_engine/utils/semantic_search.py:254-261).
+//
+// The kernel does not approximate: every row's distance is computed with the
+// reference's own association — ONE sequential fp32 accumulator over the 384
+// products (separate multiply and add, or fused when the index was loaded in
+// aarch64 mode), double sqrt/mul/div/sub tail, narrowed to f32 — so the f32
+// distance of every row is bit-identical to the oracle and no shortlist/guard
+// band is needed for the streaming path.
+//
+// B200 mapping (HBM-bound, 1536 B/row):
+//   * one warp = one 32-row tile, LANE-PER-ROW (the only mapping that keeps the
+//     reference's summation order); rows are staged in shared memory by the TMA
+//     engine as 32 bulk copies (cp.async.bulk, one 1536 B row per lane) landing
+//     on a row stride of 1552 B (≡16 mod 128), which makes the lane-per-row
+//     128-bit LDS conflict-free;
+//   * 4 warps per CTA, one 49.7 KB stage each (199 KB of the 227 KB), one CTA
+//     per SM, persistent over tiles; a warp re-arms its stage as soon as its
+//     last LDS retired, so the other three stages are in flight while it does
+//     the 384-step dependent add chain — ≥100 KB in flight per SM, well above
+//     the ~35 KB latency×bandwidth product per SM;
+//   * up to QB=8 queries share one pass over the corpus (query vectors in
+//     shared memory, read as broadcast LDS.128), which is what the hybrid batch
+//     path uses: FP32 issue, not HBM, becomes the limit only above QB≈4.
+#pragma once
+#include "common.cuh"
+
+namespace rse {
+
+constexpr int kScanD = 384;
+constexpr int kScanRowStride = 388;                     // floats: 1552 B ≡ 16 (mod 128)
+constexpr int kScanTileRows = 32;
+constexpr int kScanWarps = 4;
+constexpr int kScanStageBytes = kScanTileRows * kScanRowStride * 4;   // 49,664
+constexpr int kScanMaxQB = 8;
+
+__host__ __device__ constexpr int scan_smem_bytes(int qb) {
+  return kScanWarps * kScanStageBytes + qb * kScanD * 4 + kScanWarps * 8 + 16;
+}
+
+// ---------------------------------------------------------------- PTX helpers
+__device__ __forceinline__ uint32_t smem_u32(const void* p) {
+  return static_cast<uint32_t>(__cvta_generic_to_shared(p));
+}
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes)
+               : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "WAIT_LOOP:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra WAIT_DONE;\n"
+      "bra WAIT_LOOP;\n"
+      "WAIT_DONE:\n"
+      "}\n" ::"r"(smem_u32(bar)), "r"(parity)
+      : "memory");
+}
+// TMA bulk copy global -> shared, completion signalled on an mbarrier.
+__device__ __forceinline__ void bulk_g2s(void* dst_smem, const void* src_gmem, uint32_t bytes, uint64_t* bar) {
+  asm volatile(
+      "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+          smem_u32(dst_smem)),
+      "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar))
+      : "memory");
+}
+
+template <bool FMA>
+__device__ __forceinline__ float mac(float acc, float a, float b) {
+  if (FMA) return __fmaf_rn(a, b, acc);
+  return __fadd_rn(acc, __fmul_rn(a, b));   // never contracted
+}
+
+// vec0 tail: 1 - dot / (sqrt((double)aMag) * sqrt((double)bMag)), narrowed to f32.
+__device__ __forceinline__ float cosine_tail(float dot, double sa, double sb) {
+  double den = __dmul_rn(sa, sb);
+  double d = __dsub_rn(1.0, __ddiv_rn(static_cast<double>(dot), den));
+  return __double2float_rn(d);
+}
+
+// ---------------------------------------------------------------- query prep
+// sb[j] = sqrt((double) Σ q_i^2) with the sequential fp32 sum (the reference
+// recomputes bMag for every row; it is row-independent).
+template <bool FMA>
+__global__ void knn_query_prep_kernel(const float* __restrict__ q, int nq, int dim, double* __restrict__ sb) {
+  int j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= nq) return;
+  const float* v = q + static_cast<int64_t>(j) * dim;
+  float m = 0.0f;
+  for (int i = 0; i < dim; ++i) m = mac<FMA>(m, v[i], v[i]);
+  sb[j] = sqrt(static_cast<double>(m));
+}
+
+// amag[row] = Σ a_i^2 (sequential fp32), -1 for empty vec0 slots.  Load time only.
+template <bool FMA>
+__global__ void knn_row_sqmag_kernel(const float* __restrict__ emb, int64_t n_rows, int dim,
+                                     const uint8_t* __restrict__ valid, float* __restrict__ amag) {
+  int64_t r = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (r >= n_rows) return;
+  if (valid && !valid[r]) { amag[r] = -1.0f; return; }
+  const float* v = emb + r * dim;
+  float m = 0.0f;
+  if ((dim & 3) == 0) {
+    const float4* v4 = reinterpret_cast<const float4*>(v);
+    for (int i = 0; i < dim / 4; ++i) {
+      float4 a = v4[i];
+      m = mac<FMA>(m, a.x, a.x); m = mac<FMA>(m, a.y, a.y);
+      m = mac<FMA>(m, a.z, a.z); m = mac<FMA>(m, a.w, a.w);
+    }
+  } else {
+    for (int i = 0; i < dim; ++i) m = mac<FMA>(m, v[i], v[i]);
+  }
+  amag[r] = m;
+}
+
+// ---------------------------------------------------------------- K1 fast path (dim = 384)
+template <int QB, bool FMA>
+__global__ void __launch_bounds__(kScanWarps * 32, 1)
+knn_scan384_kernel(const float* __restrict__ emb, const float* __restrict__ amag, int64_t n_rows,
+                   const float* __restrict__ q, const double* __restrict__ sb, int nq,
+                   float* __restrict__ dist, int64_t ld) {
+  extern __shared__ __align__(128) unsigned char smem[];
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  float* stage = reinterpret_cast<float*>(smem + warp * kScanStageBytes);
+  float* qs = reinterpret_cast<float*>(smem + kScanWarps * kScanStageBytes);
+  uint64_t* bar = reinterpret_cast<uint64_t*>(smem + kScanWarps * kScanStageBytes + QB * kScanD * 4) + warp;
+
+  // queries -> smem (zero-fill unused slots so the unrolled QB loop stays finite)
+  for (int i = threadIdx.x; i < QB * kScanD; i += blockDim.x)
+    qs[i] = (i / kScanD < nq) ? q[i] : 0.0f;
+  if (lane == 0) mbar_init(bar, 1);
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  __syncthreads();
+
+  const int64_t n_tiles = (n_rows + kScanTileRows - 1) / kScanTileRows;
+  const int64_t tstride = static_cast<int64_t>(gridDim.x) * kScanWarps;
+  int64_t tile = static_cast<int64_t>(blockIdx.x) * kScanWarps + warp;
+  uint32_t parity = 0;
+
+  auto issue = [&](int64_t t) {
+    const int64_t row0 = t * kScanTileRows;
+    const int64_t rem = n_rows - row0;
+    const int nvalid = rem < kScanTileRows ? static_cast<int>(rem) : kScanTileRows;
+    if (lane == 0) mbar_arrive_expect_tx(bar, static_cast<uint32_t>(nvalid) * (kScanD * 4));
+    __syncwarp();
+    if (lane < nvalid)
+      bulk_g2s(stage + lane * kScanRowStride, emb + (row0 + lane) * kScanD, kScanD * 4, bar);
+  };
+
+  if (tile < n_tiles) issue(tile);
+
+  double sbr[QB];
+#pragma unroll
+  for (int j = 0; j < QB; ++j) sbr[j] = (j < nq) ? sb[j] : 1.0;
+
+  const float4* rowp = reinterpret_cast<const float4*>(stage + lane * kScanRowStride);
+  const float4* qp = reinterpret_cast<const float4*>(qs);
+
+  for (; tile < n_tiles; tile += tstride) {
+    const int64_t row = tile * kScanTileRows + lane;
+    const bool in_range = row < n_rows;
+    const float am = in_range ? __ldg(amag + row) : -1.0f;   // issued before the wait
+
+    mbar_wait(bar, parity);
+    parity ^= 1u;
+
+    float acc[QB];
+#pragma unroll
+    for (int j = 0; j < QB; ++j) acc[j] = 0.0f;
+
+#pragma unroll 4
+    for (int c = 0; c < kScanD / 4; ++c) {
+      const float4 a = rowp[c];
+#pragma unroll
+      for (int j = 0; j < QB; ++j) {
+        const float4 b = qp[j * (kScanD / 4) + c];
+        acc[j] = mac<FMA>(acc[j], a.x, b.x);
+        acc[j] = mac<FMA>(acc[j], a.y, b.y);
+        acc[j] = mac<FMA>(acc[j], a.z, b.z);
+        acc[j] = mac<FMA>(acc[j], a.w, b.w);
+      }
+    }
+    __syncwarp();   // every lane's LDS of this stage has retired (values consumed above)
+    if (tile + tstride < n_tiles) issue(tile + tstride);
+
+    if (in_range) {
+      if (am >= 0.0f) {
+        const double sa = sqrt(static_cast<double>(am));
+#pragma unroll
+        for (int j = 0; j < QB; ++j)
+          if (j < nq) dist[j * ld + row] = cosine_tail(acc[j], sa, sbr[j]);
+      } else {
+#pragma unroll
+        for (int j = 0; j < QB; ++j)
+          if (j < nq) dist[j * ld + row] = __uint_as_float(0x7FFFFFFFu);   // empty slot → okey 0xFFFFFFFF
+      }
+    }
+  }
+}
+
+// ---------------------------------------------------------------- K1 generic path (any dim)
+// Same arithmetic, lane-per-row straight from global memory.  Used for
+// dim != 384 (e.g. the reference's own unit test uses dim = 4,
+// tests/test_semantic_search.py:34-44); not a performance path.
+template <bool FMA>
+__global__ void knn_scan_generic_kernel(const float* __restrict__ emb, const float* __restrict__ amag,
+                                        int64_t n_rows, int dim, const float* __restrict__ q,
+                                        const double* __restrict__ sb, int nq, float* __restrict__ dist,
+                                        int64_t ld) {
+  int64_t row = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (row >= n_rows) return;
+  const float am = amag[row];
+  const float* a = emb + row * dim;
+  for (int j = 0; j < nq; ++j) {
+    float v;
+    if (am < 0.0f) {
+      v = __uint_as_float(0x7FFFFFFFu);
+    } else {
+      const float* b = q + static_cast<int64_t>(j) * dim;
+      float acc = 0.0f;
+      for (int i = 0; i < dim; ++i) acc = mac<FMA>(acc, a[i], __ldg(b + i));
+      v = cosine_tail(acc, sqrt(static_cast<double>(am)), sb[j]);
+    }
+    dist[j * ld + row] = v;
+  }
+}
+
+}  // namespace rse

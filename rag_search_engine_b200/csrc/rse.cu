@@ -1,0 +1,876 @@
+// rse.cu — the C-ABI of librse.so (see include/rse.h).  Host-side orchestration of
+// the sm_100a kernels; no torch, no CPU fallback.
+#include "../../include/rse.h"
+
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "bm25.cuh"
+#include "common.cuh"
+#include "fusion.cuh"
+#include "knn_scan.cuh"
+#include "select.cuh"
+
+using namespace rse;
+
+namespace {
+
+thread_local std::string g_create_error;
+
+struct DevBuf {
+  void* p = nullptr;
+  size_t bytes = 0;
+};
+
+}  // namespace
+
+struct rse_index {
+  int device = 0;
+  int sm_count = 148;
+  cudaStream_t own_stream = nullptr;
+  cudaStream_t stream = nullptr;
+  std::string err;
+  bool fma = false;
+  bool timing = false;
+  cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
+
+  // ---- a1: embeddings (vec0 physical layout)
+  const float* emb = nullptr;
+  float* emb_owned = nullptr;
+  int64_t n_rows = 0;
+  int dim = 0;
+  uint64_t pos_base = 0;
+  float* amag = nullptr;
+  int64_t* rowid = nullptr;
+  int32_t* movie_idx = nullptr;
+
+  // ---- knn scratch (grow-only)
+  DevBuf q_dev, sb, sel, hist, selkeys, cand, dist, o_dist, o_pos, o_rowid, o_movie, o_count;
+  int64_t dist_ld = 0;
+
+  // ---- a6: BM25
+  int64_t n_terms = 0, n_postings = 0, n_docs = 0, n_movies = 0;
+  double avgdl = 0.0;
+  int nr = 0;
+  int64_t* indptr = nullptr;
+  uint2* post = nullptr;
+  uint32_t* dl = nullptr;
+  uint32_t* roff = nullptr;
+  double* normk = nullptr;
+  double normk_k1 = NAN, normk_b = NAN;
+  std::vector<int64_t> df_host;
+  DevBuf b_tokptr, b_terms, b_idf, b_chi, b_clo, b_ccnt, b_score, b_doc, b_count;
+
+  // ---- fusion scratch + id tables
+  DevBuf f_bid, f_bsc, f_bcnt, f_sid, f_sds, f_scnt, f_oid, f_osc, f_oa, f_ob, f_ocnt;
+  long long* doc_ids = nullptr;
+  int64_t n_doc_ids = 0;
+  long long* movie_ids = nullptr;
+  int64_t n_movie_ids = 0;
+
+  rse_stats stats{};
+};
+
+namespace {
+
+int fail(rse_index* h, int code, const std::string& msg) {
+  if (h) h->err = msg; else g_create_error = msg;
+  return code;
+}
+
+#define CK(call)                                                                              \
+  do {                                                                                        \
+    cudaError_t e__ = (call);                                                                 \
+    if (e__ != cudaSuccess)                                                                   \
+      return fail(h, RSE_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(e__));      \
+  } while (0)
+
+#define LAUNCHED(h)                                                                           \
+  do {                                                                                        \
+    (h)->stats.kernel_launches++;                                                             \
+    cudaError_t e__ = cudaGetLastError();                                                     \
+    if (e__ != cudaSuccess)                                                                   \
+      return fail(h, RSE_ERR_CUDA, std::string("kernel launch: ") + cudaGetErrorString(e__)); \
+  } while (0)
+
+int ensure(rse_index* h, DevBuf& b, size_t bytes) {
+  if (bytes <= b.bytes) return RSE_OK;
+  if (b.p) CK(cudaFree(b.p));
+  b.p = nullptr; b.bytes = 0;
+  size_t want = bytes + bytes / 4 + 256;
+  CK(cudaMalloc(&b.p, want));
+  b.bytes = want;
+  return RSE_OK;
+}
+#define ENSURE(buf, bytes)                         \
+  do {                                             \
+    int rc__ = ensure(h, (buf), (bytes));          \
+    if (rc__ != RSE_OK) return rc__;               \
+  } while (0)
+
+void free_buf(DevBuf& b) {
+  if (b.p) cudaFree(b.p);
+  b.p = nullptr; b.bytes = 0;
+}
+
+template <typename T>
+void free_ptr(T*& p) {
+  if (p) cudaFree(p);
+  p = nullptr;
+}
+
+void release_embeddings(rse_index* h) {
+  free_ptr(h->emb_owned);
+  h->emb = nullptr;
+  free_ptr(h->amag);
+  free_ptr(h->rowid);
+  free_ptr(h->movie_idx);
+  h->n_rows = 0; h->dim = 0;
+}
+
+void release_bm25(rse_index* h) {
+  free_ptr(h->indptr); free_ptr(h->post); free_ptr(h->dl); free_ptr(h->roff); free_ptr(h->normk);
+  h->df_host.clear();
+  h->n_terms = h->n_postings = h->n_docs = h->n_movies = 0;
+  h->normk_k1 = NAN; h->normk_b = NAN;
+}
+
+// ------------------------------------------------------------------ scan launch
+template <int QB, bool FMA>
+int launch_scan384(rse_index* h, const float* q, const double* sb, int nq, float* dist) {
+  static bool attr_set = false;
+  const int smem = scan_smem_bytes(QB);
+  if (!attr_set) {
+    CK(cudaFuncSetAttribute(knn_scan384_kernel<QB, FMA>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    attr_set = true;
+  }
+  const int64_t n_tiles = (h->n_rows + kScanTileRows - 1) / kScanTileRows;
+  int grid = static_cast<int>(std::min<int64_t>(h->sm_count, (n_tiles + kScanWarps - 1) / kScanWarps));
+  if (grid < 1) grid = 1;
+  knn_scan384_kernel<QB, FMA><<<grid, kScanWarps * 32, smem, h->stream>>>(h->emb, h->amag, h->n_rows, q, sb, nq,
+                                                                         dist, h->dist_ld);
+  LAUNCHED(h);
+  h->stats.knn_scan_launches++;
+  return RSE_OK;
+}
+
+template <bool FMA>
+int launch_scan(rse_index* h, const float* q, const double* sb, int nq, float* dist) {
+  if (h->dim == kScanD) {
+    if (nq <= 1) return launch_scan384<1, FMA>(h, q, sb, nq, dist);
+    if (nq <= 2) return launch_scan384<2, FMA>(h, q, sb, nq, dist);
+    if (nq <= 4) return launch_scan384<4, FMA>(h, q, sb, nq, dist);
+    return launch_scan384<8, FMA>(h, q, sb, nq, dist);
+  }
+  const int threads = 128;
+  const int grid = static_cast<int>((h->n_rows + threads - 1) / threads);
+  knn_scan_generic_kernel<FMA><<<grid, threads, 0, h->stream>>>(h->emb, h->amag, h->n_rows, h->dim, q, sb, nq,
+                                                                dist, h->dist_ld);
+  LAUNCHED(h);
+  h->stats.knn_scan_launches++;
+  return RSE_OK;
+}
+
+// Local top-kprime for nq device-resident queries → packed candidates (device).
+int knn_local(rse_index* h, const float* q_dev, int nq, int kprime, long long* cand_dev) {
+  if (!h->emb) return fail(h, RSE_ERR_STATE, "rse_knn: no embeddings loaded");
+  if (nq <= 0) return RSE_OK;
+  if (kprime < 1 || kprime > RSE_MAX_KPRIME)
+    return fail(h, RSE_ERR_UNSUPPORTED, "rse_knn: kprime must be in [1, 4096] (sqlite-vec caps k at 4096)");
+  const int QB = kScanMaxQB;
+  ENSURE(h->sb, sizeof(double) * nq);
+  ENSURE(h->sel, sizeof(SelState) * nq);
+  if (h->hist.bytes < sizeof(unsigned int) * kSelBins * QB) {
+    ENSURE(h->hist, sizeof(unsigned int) * kSelBins * QB);
+    CK(cudaMemsetAsync(h->hist.p, 0, h->hist.bytes, h->stream));
+  }
+  ENSURE(h->selkeys, sizeof(unsigned long long) * static_cast<size_t>(nq) * kprime);
+  ENSURE(h->dist, sizeof(float) * static_cast<size_t>(QB) * h->dist_ld);
+
+  double* sb = static_cast<double*>(h->sb.p);
+  SelState* sel = static_cast<SelState*>(h->sel.p);
+  unsigned int* hist = static_cast<unsigned int*>(h->hist.p);
+  unsigned long long* selkeys = static_cast<unsigned long long*>(h->selkeys.p);
+  float* dist = static_cast<float*>(h->dist.p);
+
+  if (h->fma) knn_query_prep_kernel<true><<<(nq + 127) / 128, 128, 0, h->stream>>>(q_dev, nq, h->dim, sb);
+  else knn_query_prep_kernel<false><<<(nq + 127) / 128, 128, 0, h->stream>>>(q_dev, nq, h->dim, sb);
+  LAUNCHED(h);
+  select_init_kernel<<<(nq + 127) / 128, 128, 0, h->stream>>>(sel, nq, static_cast<unsigned int>(kprime));
+  LAUNCHED(h);
+
+  static const int shifts[6] = {53, 42, 32, 21, 10, 0};
+  static const int widths[6] = {11, 11, 10, 11, 11, 10};
+  int sel_blocks = static_cast<int>(std::min<int64_t>((h->n_rows + 4095) / 4096, h->sm_count * 2));
+  if (sel_blocks < 1) sel_blocks = 1;
+
+  for (int g0 = 0; g0 < nq; g0 += QB) {
+    const int ng = std::min(QB, nq - g0);
+    if (h->timing) CK(cudaEventRecord(h->ev[0], h->stream));
+    int rc = h->fma ? launch_scan<true>(h, q_dev + static_cast<int64_t>(g0) * h->dim, sb + g0, ng, dist)
+                    : launch_scan<false>(h, q_dev + static_cast<int64_t>(g0) * h->dim, sb + g0, ng, dist);
+    if (rc != RSE_OK) return rc;
+    if (h->timing) {
+      CK(cudaEventRecord(h->ev[1], h->stream));
+      CK(cudaEventSynchronize(h->ev[1]));
+      float ms = 0.f;
+      CK(cudaEventElapsedTime(&ms, h->ev[0], h->ev[1]));
+      h->stats.last_knn_scan_ms += ms;
+    }
+    dim3 grid(sel_blocks, ng);
+    for (int p = 0; p < 6; ++p) {
+      select_pass_kernel<<<grid, kSelThreads, 0, h->stream>>>(dist, h->dist_ld, h->n_rows, h->pos_base, sel + g0, hist,
+                                                              shifts[p], widths[p]);
+      LAUNCHED(h);
+    }
+    select_collect_kernel<<<grid, kSelThreads, 0, h->stream>>>(dist, h->dist_ld, h->n_rows, h->pos_base, sel + g0,
+                                                               selkeys + static_cast<int64_t>(g0) * kprime, kprime);
+    LAUNCHED(h);
+  }
+  const int kp2 = next_pow2(kprime);
+  const size_t fsmem = static_cast<size_t>(kp2) * 12;
+  if (fsmem > 48 * 1024) {
+    static bool set = false;
+    if (!set) {
+      CK(cudaFuncSetAttribute(select_finish_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
+      set = true;
+    }
+  }
+  select_finish_kernel<<<nq, kSelThreads, fsmem, h->stream>>>(selkeys, sel, kprime, kp2, h->pos_base, h->rowid,
+                                                             h->movie_idx, cand_dev);
+  LAUNCHED(h);
+  return RSE_OK;
+}
+
+int aggregate(rse_index* h, const long long* cand, int nq, int k, int kprime, float* o_dist, long long* o_rowid,
+              int* o_movie, int* o_count) {
+  const size_t smem = static_cast<size_t>(kprime) * 8;
+  knn_aggregate_kernel<<<nq, kSelThreads, smem, h->stream>>>(cand, nq, kprime, k, o_dist, o_rowid, o_movie, o_count);
+  LAUNCHED(h);
+  return RSE_OK;
+}
+
+int upload_queries(rse_index* h, const float* q_host, int nq) {
+  ENSURE(h->q_dev, sizeof(float) * static_cast<size_t>(nq) * h->dim);
+  CK(cudaMemcpyAsync(h->q_dev.p, q_host, sizeof(float) * static_cast<size_t>(nq) * h->dim, cudaMemcpyHostToDevice,
+                     h->stream));
+  return RSE_OK;
+}
+
+int finish_embeddings(rse_index* h, const uint8_t* valid_dev) {
+  CK(cudaMalloc(&h->amag, sizeof(float) * std::max<int64_t>(h->n_rows, 1)));
+  if (h->n_rows > 0) {
+    const int threads = 128;
+    const int grid = static_cast<int>((h->n_rows + threads - 1) / threads);
+    if (h->fma) knn_row_sqmag_kernel<true><<<grid, threads, 0, h->stream>>>(h->emb, h->n_rows, h->dim, valid_dev, h->amag);
+    else knn_row_sqmag_kernel<false><<<grid, threads, 0, h->stream>>>(h->emb, h->n_rows, h->dim, valid_dev, h->amag);
+    LAUNCHED(h);
+  }
+  h->dist_ld = ((h->n_rows + 31) / 32) * 32;
+  if (h->dist_ld < 32) h->dist_ld = 32;
+  CK(cudaStreamSynchronize(h->stream));
+  h->stats.emb_rows = h->n_rows;
+  h->stats.emb_dim = h->dim;
+  return RSE_OK;
+}
+
+int check_emb_args(rse_index* h, const float* emb, int64_t n_rows, int32_t dim, int64_t pos_base) {
+  if (!h) return RSE_ERR_INVALID;
+  if ((!emb && n_rows > 0) || n_rows < 0 || dim < 1 || dim > 65536)
+    return fail(h, RSE_ERR_INVALID, "rse_load_embeddings: bad emb/n_rows/dim");
+  if (pos_base < 0 || (pos_base % RSE_VEC0_BLOCK) != 0)
+    return fail(h, RSE_ERR_INVALID, "rse_load_embeddings: pos_base must be a non-negative multiple of 1024");
+  if (static_cast<uint64_t>(pos_base) + static_cast<uint64_t>(n_rows) >= 0xFFFFFFFFull)
+    return fail(h, RSE_ERR_UNSUPPORTED, "rse_load_embeddings: global position must fit 32 bits");
+  return RSE_OK;
+}
+
+}  // namespace
+
+// =================================================================== C-ABI
+extern "C" {
+
+int rse_abi_version(void) { return RSE_ABI_VERSION; }
+
+const char* rse_last_error(const rse_index* h) { return h ? h->err.c_str() : g_create_error.c_str(); }
+
+int rse_create(int32_t device, rse_index** out) {
+  rse_index* h = nullptr;
+  if (!out) return fail(nullptr, RSE_ERR_INVALID, "rse_create: out is NULL");
+  *out = nullptr;
+  int n = 0;
+  cudaError_t e = cudaGetDeviceCount(&n);
+  if (e != cudaSuccess || n <= 0)
+    return fail(nullptr, RSE_ERR_CUDA,
+                std::string("rse_create: no CUDA device (") + cudaGetErrorString(e) + "); librse has no CPU fallback");
+  if (device < 0 || device >= n) return fail(nullptr, RSE_ERR_INVALID, "rse_create: device ordinal out of range");
+  e = cudaSetDevice(device);
+  if (e != cudaSuccess) return fail(nullptr, RSE_ERR_CUDA, std::string("cudaSetDevice: ") + cudaGetErrorString(e));
+  cudaDeviceProp prop;
+  e = cudaGetDeviceProperties(&prop, device);
+  if (e != cudaSuccess) return fail(nullptr, RSE_ERR_CUDA, std::string("cudaGetDeviceProperties: ") + cudaGetErrorString(e));
+  if (prop.major != 10)
+    return fail(nullptr, RSE_ERR_UNSUPPORTED, "rse_create: librse is built for sm_100a (B200) only");
+  h = new rse_index();
+  h->device = device;
+  h->sm_count = prop.multiProcessorCount;
+  e = cudaStreamCreateWithFlags(&h->own_stream, cudaStreamNonBlocking);
+  if (e != cudaSuccess) {
+    delete h;
+    return fail(nullptr, RSE_ERR_CUDA, std::string("cudaStreamCreate: ") + cudaGetErrorString(e));
+  }
+  h->stream = h->own_stream;
+  for (auto& ev : h->ev) cudaEventCreate(&ev);
+  *out = h;
+  return RSE_OK;
+}
+
+void rse_destroy(rse_index* h) {
+  if (!h) return;
+  cudaSetDevice(h->device);
+  cudaStreamSynchronize(h->stream);
+  release_embeddings(h);
+  release_bm25(h);
+  for (DevBuf* b : {&h->q_dev, &h->sb, &h->sel, &h->hist, &h->selkeys, &h->cand, &h->dist, &h->o_dist, &h->o_pos,
+                    &h->o_rowid, &h->o_movie, &h->o_count, &h->b_tokptr, &h->b_terms, &h->b_idf, &h->b_chi, &h->b_clo,
+                    &h->b_ccnt, &h->b_score, &h->b_doc, &h->b_count, &h->f_bid, &h->f_bsc, &h->f_bcnt, &h->f_sid,
+                    &h->f_sds, &h->f_scnt, &h->f_oid, &h->f_osc, &h->f_oa, &h->f_ob, &h->f_ocnt})
+    free_buf(*b);
+  free_ptr(h->doc_ids);
+  free_ptr(h->movie_ids);
+  for (auto& ev : h->ev) if (ev) cudaEventDestroy(ev);
+  if (h->own_stream) cudaStreamDestroy(h->own_stream);
+  delete h;
+}
+
+int rse_set_stream(rse_index* h, void* s) {
+  if (!h) return RSE_ERR_INVALID;
+  CK(cudaStreamSynchronize(h->stream));
+  h->stream = s ? static_cast<cudaStream_t>(s) : h->own_stream;
+  return RSE_OK;
+}
+
+int rse_synchronize(rse_index* h) {
+  if (!h) return RSE_ERR_INVALID;
+  CK(cudaSetDevice(h->device));
+  CK(cudaStreamSynchronize(h->stream));
+  return RSE_OK;
+}
+
+int rse_set_fma(rse_index* h, int32_t use_fma) {
+  if (!h) return RSE_ERR_INVALID;
+  if (h->emb) return fail(h, RSE_ERR_STATE, "rse_set_fma: set before loading embeddings");
+  h->fma = use_fma != 0;
+  return RSE_OK;
+}
+
+int rse_set_timing(rse_index* h, int32_t enabled) {
+  if (!h) return RSE_ERR_INVALID;
+  h->timing = enabled != 0;
+  return RSE_OK;
+}
+
+int rse_get_stats(rse_index* h, rse_stats* out) {
+  if (!h || !out) return RSE_ERR_INVALID;
+  *out = h->stats;
+  return RSE_OK;
+}
+
+int rse_stats_reset(rse_index* h) {
+  if (!h) return RSE_ERR_INVALID;
+  const int64_t rows = h->stats.emb_rows, post = h->stats.bm25_postings, docs = h->stats.bm25_docs;
+  const int dim = h->stats.emb_dim;
+  h->stats = rse_stats{};
+  h->stats.emb_rows = rows; h->stats.emb_dim = dim; h->stats.bm25_postings = post; h->stats.bm25_docs = docs;
+  return RSE_OK;
+}
+
+// ------------------------------------------------------------------ embeddings
+int rse_load_embeddings(rse_index* h, const float* emb_host, int64_t n_rows, int32_t dim, const uint8_t* valid_host,
+                        const int64_t* rowid_host, const int32_t* movie_idx_host, int64_t pos_base) {
+  int rc = check_emb_args(h, emb_host, n_rows, dim, pos_base);
+  if (rc != RSE_OK) return rc;
+  CK(cudaSetDevice(h->device));
+  release_embeddings(h);
+  const size_t bytes = sizeof(float) * static_cast<size_t>(std::max<int64_t>(n_rows, 1)) * dim;
+  CK(cudaMalloc(&h->emb_owned, bytes));
+  if (n_rows > 0)
+    CK(cudaMemcpyAsync(h->emb_owned, emb_host, sizeof(float) * static_cast<size_t>(n_rows) * dim,
+                       cudaMemcpyHostToDevice, h->stream));
+  h->emb = h->emb_owned;
+  h->n_rows = n_rows; h->dim = dim; h->pos_base = static_cast<uint64_t>(pos_base);
+  uint8_t* valid_dev = nullptr;
+  if (valid_host && n_rows > 0) {
+    CK(cudaMalloc(&valid_dev, n_rows));
+    CK(cudaMemcpyAsync(valid_dev, valid_host, n_rows, cudaMemcpyHostToDevice, h->stream));
+  }
+  if (rowid_host && n_rows > 0) {
+    CK(cudaMalloc(&h->rowid, sizeof(int64_t) * n_rows));
+    CK(cudaMemcpyAsync(h->rowid, rowid_host, sizeof(int64_t) * n_rows, cudaMemcpyHostToDevice, h->stream));
+  }
+  if (movie_idx_host && n_rows > 0) {
+    CK(cudaMalloc(&h->movie_idx, sizeof(int32_t) * n_rows));
+    CK(cudaMemcpyAsync(h->movie_idx, movie_idx_host, sizeof(int32_t) * n_rows, cudaMemcpyHostToDevice, h->stream));
+  }
+  rc = finish_embeddings(h, valid_dev);
+  if (valid_dev) cudaFree(valid_dev);
+  return rc;
+}
+
+int rse_attach_embeddings_dev(rse_index* h, const float* emb_dev, int64_t n_rows, int32_t dim,
+                              const uint8_t* valid_dev, const int64_t* rowid_dev, const int32_t* movie_idx_dev,
+                              int64_t pos_base) {
+  int rc = check_emb_args(h, emb_dev, n_rows, dim, pos_base);
+  if (rc != RSE_OK) return rc;
+  if ((reinterpret_cast<uintptr_t>(emb_dev) & 15u) != 0)
+    return fail(h, RSE_ERR_INVALID, "rse_attach_embeddings_dev: emb_dev must be 16-byte aligned");
+  CK(cudaSetDevice(h->device));
+  release_embeddings(h);
+  h->emb = emb_dev;
+  h->n_rows = n_rows; h->dim = dim; h->pos_base = static_cast<uint64_t>(pos_base);
+  if (rowid_dev && n_rows > 0) {
+    CK(cudaMalloc(&h->rowid, sizeof(int64_t) * n_rows));
+    CK(cudaMemcpyAsync(h->rowid, rowid_dev, sizeof(int64_t) * n_rows, cudaMemcpyDeviceToDevice, h->stream));
+  }
+  if (movie_idx_dev && n_rows > 0) {
+    CK(cudaMalloc(&h->movie_idx, sizeof(int32_t) * n_rows));
+    CK(cudaMemcpyAsync(h->movie_idx, movie_idx_dev, sizeof(int32_t) * n_rows, cudaMemcpyDeviceToDevice, h->stream));
+  }
+  return finish_embeddings(h, valid_dev);
+}
+
+int rse_knn_local_dev(rse_index* h, const float* q_dev, int32_t nq, int32_t kprime, int64_t* cand_dev) {
+  if (!h) return RSE_ERR_INVALID;
+  if (!q_dev || !cand_dev || nq < 0) return fail(h, RSE_ERR_INVALID, "rse_knn_local_dev: bad arguments");
+  CK(cudaSetDevice(h->device));
+  return knn_local(h, q_dev, nq, kprime, reinterpret_cast<long long*>(cand_dev));
+}
+
+int rse_knn(rse_index* h, const float* q_host, int32_t nq, int32_t kprime, float* out_dist, int64_t* out_pos,
+            int64_t* out_rowid, int32_t* out_movie_idx, int32_t* out_count) {
+  if (!h) return RSE_ERR_INVALID;
+  if (nq < 0 || (nq > 0 && (!q_host || !out_dist || !out_count)))
+    return fail(h, RSE_ERR_INVALID, "rse_knn: bad arguments");
+  if (!h->emb) return fail(h, RSE_ERR_STATE, "rse_knn: no embeddings loaded");
+  if (nq == 0) return RSE_OK;
+  CK(cudaSetDevice(h->device));
+  h->stats.last_knn_scan_ms = 0.0;
+  if (h->timing) CK(cudaEventRecord(h->ev[2], h->stream));
+  int rc = upload_queries(h, q_host, nq);
+  if (rc != RSE_OK) return rc;
+  const size_t n = static_cast<size_t>(nq) * kprime;
+  ENSURE(h->cand, sizeof(long long) * n * 3);
+  ENSURE(h->o_dist, sizeof(float) * n);
+  ENSURE(h->o_pos, sizeof(long long) * n);
+  ENSURE(h->o_rowid, sizeof(long long) * n);
+  ENSURE(h->o_movie, sizeof(int) * n);
+  ENSURE(h->o_count, sizeof(int) * nq);
+  rc = knn_local(h, static_cast<const float*>(h->q_dev.p), nq, kprime, static_cast<long long*>(h->cand.p));
+  if (rc != RSE_OK) return rc;
+  knn_unpack_kernel<<<nq, 128, 0, h->stream>>>(static_cast<const long long*>(h->cand.p), nq, kprime,
+                                               static_cast<float*>(h->o_dist.p), static_cast<long long*>(h->o_pos.p),
+                                               static_cast<long long*>(h->o_rowid.p), static_cast<int*>(h->o_movie.p),
+                                               static_cast<int*>(h->o_count.p));
+  LAUNCHED(h);
+  CK(cudaMemcpyAsync(out_dist, h->o_dist.p, sizeof(float) * n, cudaMemcpyDeviceToHost, h->stream));
+  if (out_pos) CK(cudaMemcpyAsync(out_pos, h->o_pos.p, sizeof(long long) * n, cudaMemcpyDeviceToHost, h->stream));
+  if (out_rowid) CK(cudaMemcpyAsync(out_rowid, h->o_rowid.p, sizeof(long long) * n, cudaMemcpyDeviceToHost, h->stream));
+  if (out_movie_idx) CK(cudaMemcpyAsync(out_movie_idx, h->o_movie.p, sizeof(int) * n, cudaMemcpyDeviceToHost, h->stream));
+  CK(cudaMemcpyAsync(out_count, h->o_count.p, sizeof(int) * nq, cudaMemcpyDeviceToHost, h->stream));
+  if (h->timing) CK(cudaEventRecord(h->ev[3], h->stream));
+  CK(cudaStreamSynchronize(h->stream));
+  if (h->timing) {
+    float ms = 0.f;
+    CK(cudaEventElapsedTime(&ms, h->ev[2], h->ev[3]));
+    h->stats.last_knn_total_ms = ms;
+  }
+  return RSE_OK;
+}
+
+int rse_knn_movies(rse_index* h, const float* q_host, int32_t nq, int32_t k, int32_t kprime, float* out_dist,
+                   int64_t* out_chunk_rowid, int32_t* out_movie_idx, int32_t* out_count) {
+  if (!h) return RSE_ERR_INVALID;
+  if (nq < 0 || k < 1 || (nq > 0 && (!q_host || !out_dist || !out_chunk_rowid || !out_movie_idx || !out_count)))
+    return fail(h, RSE_ERR_INVALID, "rse_knn_movies: bad arguments");
+  if (!h->emb) return fail(h, RSE_ERR_STATE, "rse_knn_movies: no embeddings loaded");
+  if (!h->movie_idx) return fail(h, RSE_ERR_STATE, "rse_knn_movies: embeddings were loaded without movie_idx");
+  if (nq == 0) return RSE_OK;
+  CK(cudaSetDevice(h->device));
+  h->stats.last_knn_scan_ms = 0.0;
+  if (h->timing) CK(cudaEventRecord(h->ev[2], h->stream));
+  int rc = upload_queries(h, q_host, nq);
+  if (rc != RSE_OK) return rc;
+  const size_t n = static_cast<size_t>(nq) * k;
+  ENSURE(h->cand, sizeof(long long) * static_cast<size_t>(nq) * kprime * 3);
+  ENSURE(h->o_dist, sizeof(float) * n);
+  ENSURE(h->o_rowid, sizeof(long long) * n);
+  ENSURE(h->o_movie, sizeof(int) * n);
+  ENSURE(h->o_count, sizeof(int) * nq);
+  rc = knn_local(h, static_cast<const float*>(h->q_dev.p), nq, kprime, static_cast<long long*>(h->cand.p));
+  if (rc != RSE_OK) return rc;
+  rc = aggregate(h, static_cast<const long long*>(h->cand.p), nq, k, kprime, static_cast<float*>(h->o_dist.p),
+                 static_cast<long long*>(h->o_rowid.p), static_cast<int*>(h->o_movie.p),
+                 static_cast<int*>(h->o_count.p));
+  if (rc != RSE_OK) return rc;
+  CK(cudaMemcpyAsync(out_dist, h->o_dist.p, sizeof(float) * n, cudaMemcpyDeviceToHost, h->stream));
+  CK(cudaMemcpyAsync(out_chunk_rowid, h->o_rowid.p, sizeof(long long) * n, cudaMemcpyDeviceToHost, h->stream));
+  CK(cudaMemcpyAsync(out_movie_idx, h->o_movie.p, sizeof(int) * n, cudaMemcpyDeviceToHost, h->stream));
+  CK(cudaMemcpyAsync(out_count, h->o_count.p, sizeof(int) * nq, cudaMemcpyDeviceToHost, h->stream));
+  if (h->timing) CK(cudaEventRecord(h->ev[3], h->stream));
+  CK(cudaStreamSynchronize(h->stream));
+  if (h->timing) {
+    float ms = 0.f;
+    CK(cudaEventElapsedTime(&ms, h->ev[2], h->ev[3]));
+    h->stats.last_knn_total_ms = ms;
+  }
+  return RSE_OK;
+}
+
+int rse_knn_merge_movies_dev(rse_index* h, const int64_t* gathered_dev, int32_t n_lists, int32_t nq, int32_t k,
+                             int32_t kprime, float* out_dist_dev, int64_t* out_chunk_rowid_dev,
+                             int32_t* out_movie_idx_dev, int32_t* out_count_dev) {
+  if (!h) return RSE_ERR_INVALID;
+  if (!gathered_dev || n_lists < 1 || nq < 0 || k < 1 || kprime < 1 || !out_dist_dev || !out_chunk_rowid_dev ||
+      !out_movie_idx_dev || !out_count_dev)
+    return fail(h, RSE_ERR_INVALID, "rse_knn_merge_movies_dev: bad arguments");
+  if (nq == 0) return RSE_OK;
+  CK(cudaSetDevice(h->device));
+  const int n2 = next_pow2(n_lists * kprime);
+  const size_t smem = static_cast<size_t>(n2) * 12;
+  if (smem > 200 * 1024)
+    return fail(h, RSE_ERR_UNSUPPORTED, "rse_knn_merge_movies_dev: n_lists*kprime too large for the merge kernel");
+  if (smem > 48 * 1024) CK(cudaFuncSetAttribute(knn_merge_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+  ENSURE(h->cand, sizeof(long long) * static_cast<size_t>(nq) * kprime * 3);
+  knn_merge_kernel<<<nq, kSelThreads, smem, h->stream>>>(reinterpret_cast<const long long*>(gathered_dev), n_lists, nq,
+                                                         kprime, n2, static_cast<long long*>(h->cand.p));
+  LAUNCHED(h);
+  return aggregate(h, static_cast<const long long*>(h->cand.p), nq, k, kprime, out_dist_dev,
+                   reinterpret_cast<long long*>(out_chunk_rowid_dev), out_movie_idx_dev, out_count_dev);
+}
+
+// ------------------------------------------------------------------ BM25
+int rse_load_bm25(rse_index* h, const int64_t* indptr, const uint32_t* doc_idx, const uint32_t* tf, const int64_t* df,
+                  int64_t n_terms, int64_t n_postings, const uint32_t* dl, int64_t n_docs, int64_t n_movies,
+                  double avgdl) {
+  if (!h) return RSE_ERR_INVALID;
+  if (n_terms < 0 || n_postings < 0 || n_docs < 0 || !indptr || (n_postings > 0 && (!doc_idx || !tf)) ||
+      (n_terms > 0 && !df) || (n_docs > 0 && !dl))
+    return fail(h, RSE_ERR_INVALID, "rse_load_bm25: bad arguments");
+  if (n_docs >= 0xFFFFFFFFll || n_postings >= (1ll << 40))
+    return fail(h, RSE_ERR_UNSUPPORTED, "rse_load_bm25: index too large");
+  if (indptr[0] != 0 || indptr[n_terms] != n_postings)
+    return fail(h, RSE_ERR_INVALID, "rse_load_bm25: indptr must start at 0 and end at n_postings");
+  CK(cudaSetDevice(h->device));
+  release_bm25(h);
+  h->n_terms = n_terms; h->n_postings = n_postings; h->n_docs = n_docs; h->n_movies = n_movies; h->avgdl = avgdl;
+  h->nr = static_cast<int>((n_docs + kBmRange - 1) / kBmRange);
+  if (h->nr < 1) h->nr = 1;
+  if (h->nr > 2048) return fail(h, RSE_ERR_UNSUPPORTED, "rse_load_bm25: more than 16.7M documents");
+  h->df_host.assign(df, df + n_terms);
+
+  CK(cudaMalloc(&h->indptr, sizeof(int64_t) * (n_terms + 1)));
+  CK(cudaMemcpyAsync(h->indptr, indptr, sizeof(int64_t) * (n_terms + 1), cudaMemcpyHostToDevice, h->stream));
+  CK(cudaMalloc(&h->post, sizeof(uint2) * std::max<int64_t>(n_postings, 1)));
+  if (n_postings > 0) {
+    // strided 2D copies interleave (doc, tf) into uint2 without a host temporary
+    CK(cudaMemcpy2DAsync(reinterpret_cast<char*>(h->post), sizeof(uint2), doc_idx, sizeof(uint32_t), sizeof(uint32_t),
+                         n_postings, cudaMemcpyHostToDevice, h->stream));
+    CK(cudaMemcpy2DAsync(reinterpret_cast<char*>(h->post) + 4, sizeof(uint2), tf, sizeof(uint32_t), sizeof(uint32_t),
+                         n_postings, cudaMemcpyHostToDevice, h->stream));
+  }
+  CK(cudaMalloc(&h->dl, sizeof(uint32_t) * std::max<int64_t>(n_docs, 1)));
+  if (n_docs > 0) CK(cudaMemcpyAsync(h->dl, dl, sizeof(uint32_t) * n_docs, cudaMemcpyHostToDevice, h->stream));
+  CK(cudaMalloc(&h->normk, sizeof(double) * std::max<int64_t>(n_docs, 1)));
+  const int64_t roff_n = std::max<int64_t>(n_terms, 1) * (h->nr + 1);
+  CK(cudaMalloc(&h->roff, sizeof(uint32_t) * roff_n));
+  if (n_terms > 0) {
+    const int threads = 256;
+    const int64_t total = n_terms * (h->nr + 1);
+    const int64_t grid = (total + threads - 1) / threads;
+    if (grid > 0x7FFFFFFFll) return fail(h, RSE_ERR_UNSUPPORTED, "rse_load_bm25: range table too large");
+    bm25_range_offsets_by_term_kernel<<<static_cast<unsigned int>(grid), threads, 0, h->stream>>>(
+        h->indptr, h->post, n_terms, h->nr, h->roff);
+    LAUNCHED(h);
+  }
+  CK(cudaStreamSynchronize(h->stream));
+  h->stats.bm25_postings = n_postings;
+  h->stats.bm25_docs = n_docs;
+  static bool attr = false;
+  if (!attr) {
+    CK(cudaFuncSetAttribute(bm25_score_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kBmRange * 9));
+    attr = true;
+  }
+  return RSE_OK;
+}
+
+namespace {
+
+// tokens → device (with host-computed idf, keyword_search.py:224); results stay on the device
+// in h->b_score / b_doc / b_count ([nq][k]).
+int bm25_device(rse_index* h, const int32_t* tok_indptr, const int32_t* term_rows, int nq, int k, double k1, double b) {
+  if (!h->indptr) return fail(h, RSE_ERR_STATE, "rse_bm25: no BM25 index loaded");
+  if (k < 1 || k > RSE_MAX_BM25_K) return fail(h, RSE_ERR_UNSUPPORTED, "rse_bm25: k must be in [1, 256]");
+  const int64_t ntok = tok_indptr[nq];
+  if (tok_indptr[0] != 0 || ntok < 0) return fail(h, RSE_ERR_INVALID, "rse_bm25: bad tok_indptr");
+  std::vector<double> idf(static_cast<size_t>(std::max<int64_t>(ntok, 1)), 0.0);
+  std::vector<int32_t> terms(static_cast<size_t>(std::max<int64_t>(ntok, 1)), -1);
+  const bool dead = (h->n_docs == 0) || !(h->avgdl != 0.0);   // avgdl None/0 → [] (:199-200)
+  for (int q = 0; q < nq; ++q) {
+    const int n = tok_indptr[q + 1] - tok_indptr[q];
+    if (n < 0) return fail(h, RSE_ERR_INVALID, "rse_bm25: tok_indptr not monotone");
+    if (n > RSE_MAX_QUERY_TOKENS) return fail(h, RSE_ERR_UNSUPPORTED, "rse_bm25: more than 255 tokens in a query");
+    for (int t = tok_indptr[q]; t < tok_indptr[q + 1]; ++t) {
+      const int32_t term = term_rows[t];
+      if (term >= h->n_terms) return fail(h, RSE_ERR_INVALID, "rse_bm25: term row out of range");
+      if (term < 0 || dead) continue;
+      const int64_t df = h->df_host[term];
+      if (df <= 0) continue;                                   // `if not rows: continue` (:219-220)
+      terms[t] = term;
+      const double N = static_cast<double>(h->n_movies - df);  // int arithmetic first, as Python does
+      idf[t] = std::log((N + 0.5) / (static_cast<double>(df) + 0.5) + 1.0);
+    }
+  }
+  ENSURE(h->b_tokptr, sizeof(int32_t) * (nq + 1));
+  ENSURE(h->b_terms, sizeof(int32_t) * std::max<int64_t>(ntok, 1));
+  ENSURE(h->b_idf, sizeof(double) * std::max<int64_t>(ntok, 1));
+  ENSURE(h->b_score, sizeof(double) * static_cast<size_t>(nq) * k);
+  ENSURE(h->b_doc, sizeof(int) * static_cast<size_t>(nq) * k);
+  ENSURE(h->b_count, sizeof(int) * nq);
+  CK(cudaMemcpyAsync(h->b_tokptr.p, tok_indptr, sizeof(int32_t) * (nq + 1), cudaMemcpyHostToDevice, h->stream));
+  if (ntok > 0) {
+    CK(cudaMemcpyAsync(h->b_terms.p, terms.data(), sizeof(int32_t) * ntok, cudaMemcpyHostToDevice, h->stream));
+    CK(cudaMemcpyAsync(h->b_idf.p, idf.data(), sizeof(double) * ntok, cudaMemcpyHostToDevice, h->stream));
+  }
+  if (!(h->normk_k1 == k1 && h->normk_b == b) && h->n_docs > 0) {
+    const int threads = 256;
+    bm25_norm_kernel<<<static_cast<unsigned int>((h->n_docs + threads - 1) / threads), threads, 0, h->stream>>>(
+        h->dl, h->n_docs, k1, b, h->avgdl, h->normk);
+    LAUNCHED(h);
+    h->normk_k1 = k1; h->normk_b = b;
+  }
+  const int chunk = 4096;
+  const size_t per_q = static_cast<size_t>(h->nr) * k;
+  ENSURE(h->b_chi, sizeof(unsigned long long) * per_q * std::min(nq, chunk));
+  ENSURE(h->b_clo, sizeof(unsigned long long) * per_q * std::min(nq, chunk));
+  ENSURE(h->b_ccnt, sizeof(int) * static_cast<size_t>(h->nr) * std::min(nq, chunk));
+  const double k1p1 = k1 + 1.0;
+  for (int q0 = 0; q0 < nq; q0 += chunk) {
+    const int nc = std::min(chunk, nq - q0);
+    // candidate buffers are indexed by absolute q inside the kernels → offset the base pointers
+    unsigned long long* chi = static_cast<unsigned long long*>(h->b_chi.p) - static_cast<int64_t>(q0) * per_q;
+    unsigned long long* clo = static_cast<unsigned long long*>(h->b_clo.p) - static_cast<int64_t>(q0) * per_q;
+    int* ccnt = static_cast<int*>(h->b_ccnt.p) - static_cast<int64_t>(q0) * h->nr;
+    dim3 grid(h->nr, nc);
+    bm25_score_kernel<<<grid, kBmThreads, kBmRange * 9, h->stream>>>(
+        h->indptr, h->post, h->roff, h->normk, h->nr, h->n_docs, static_cast<const int32_t*>(h->b_tokptr.p),
+        static_cast<const int32_t*>(h->b_terms.p), static_cast<const double*>(h->b_idf.p), q0, k, k1p1, chi, clo, ccnt);
+    LAUNCHED(h);
+    bm25_merge_kernel<<<nc, kBmThreads, 0, h->stream>>>(chi, clo, ccnt, h->nr, q0, k, static_cast<double*>(h->b_score.p),
+                                                        static_cast<int*>(h->b_doc.p), static_cast<int*>(h->b_count.p));
+    LAUNCHED(h);
+  }
+  return RSE_OK;
+}
+
+}  // namespace
+
+int rse_bm25(rse_index* h, const int32_t* tok_indptr, const int32_t* term_rows, int32_t nq, int32_t k, double k1,
+             double b, double* out_score, int32_t* out_doc_idx, int32_t* out_count) {
+  if (!h) return RSE_ERR_INVALID;
+  if (nq < 0 || !tok_indptr || (nq > 0 && (!out_score || !out_doc_idx || !out_count)))
+    return fail(h, RSE_ERR_INVALID, "rse_bm25: bad arguments");
+  if (nq == 0) return RSE_OK;
+  if (tok_indptr[nq] > 0 && !term_rows) return fail(h, RSE_ERR_INVALID, "rse_bm25: term_rows is NULL");
+  CK(cudaSetDevice(h->device));
+  if (h->timing) CK(cudaEventRecord(h->ev[2], h->stream));
+  int rc = bm25_device(h, tok_indptr, term_rows, nq, k, k1, b);
+  if (rc != RSE_OK) return rc;
+  const size_t n = static_cast<size_t>(nq) * k;
+  CK(cudaMemcpyAsync(out_score, h->b_score.p, sizeof(double) * n, cudaMemcpyDeviceToHost, h->stream));
+  CK(cudaMemcpyAsync(out_doc_idx, h->b_doc.p, sizeof(int) * n, cudaMemcpyDeviceToHost, h->stream));
+  CK(cudaMemcpyAsync(out_count, h->b_count.p, sizeof(int) * nq, cudaMemcpyDeviceToHost, h->stream));
+  if (h->timing) CK(cudaEventRecord(h->ev[3], h->stream));
+  CK(cudaStreamSynchronize(h->stream));
+  if (h->timing) {
+    float ms = 0.f;
+    CK(cudaEventElapsedTime(&ms, h->ev[2], h->ev[3]));
+    h->stats.last_bm25_ms = ms;
+  }
+  return RSE_OK;
+}
+
+// ------------------------------------------------------------------ fusion
+namespace {
+
+int fuse_launch(rse_index* h, int mode, double param, int tie_mode, int nq, int limit, const FuseIn& in,
+                long long* o_id, double* o_sc, double* o_a, double* o_b, int* o_cnt) {
+  if (limit < 1 || limit > RSE_MAX_FUSE_LIMIT) return fail(h, RSE_ERR_UNSUPPORTED, "fusion: limit must be in [1, 128]");
+  if (tie_mode != RSE_TIE_REFERENCE && tie_mode != RSE_TIE_BY_ID) return fail(h, RSE_ERR_INVALID, "fusion: bad tie_mode");
+  const size_t smem = fuse_smem_bytes(limit);
+  static size_t attr_smem = 0;
+  if (smem > 48 * 1024 && smem > attr_smem) {
+    CK(cudaFuncSetAttribute(fuse_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+    attr_smem = smem;
+  }
+  fuse_kernel<<<nq, 32, smem, h->stream>>>(in, nq, limit, mode, param, tie_mode, o_id, o_sc, o_a, o_b, o_cnt);
+  LAUNCHED(h);
+  return RSE_OK;
+}
+
+int fuse_host(rse_index* h, int mode, double param, int tie_mode, int nq, int limit, const int64_t* bm25_id,
+              const double* bm25_score, const int32_t* bm25_count, const int64_t* sem_id, const float* sem_dist,
+              const int32_t* sem_count, int64_t* out_id, double* out_score, double* out_a, double* out_b,
+              int32_t* out_count) {
+  if (nq < 0 || (nq > 0 && (!bm25_id || !bm25_score || !bm25_count || !sem_id || !sem_dist || !sem_count || !out_id ||
+                            !out_score || !out_a || !out_b || !out_count)))
+    return fail(h, RSE_ERR_INVALID, "fusion: bad arguments");
+  if (nq == 0) return RSE_OK;
+  if (limit < 1 || limit > RSE_MAX_FUSE_LIMIT) return fail(h, RSE_ERR_UNSUPPORTED, "fusion: limit must be in [1, 128]");
+  CK(cudaSetDevice(h->device));
+  const size_t n = static_cast<size_t>(nq) * limit;
+  ENSURE(h->f_bid, 8 * n); ENSURE(h->f_bsc, 8 * n); ENSURE(h->f_bcnt, 4 * static_cast<size_t>(nq));
+  ENSURE(h->f_sid, 8 * n); ENSURE(h->f_sds, 4 * n); ENSURE(h->f_scnt, 4 * static_cast<size_t>(nq));
+  ENSURE(h->f_oid, 8 * n); ENSURE(h->f_osc, 8 * n); ENSURE(h->f_oa, 8 * n); ENSURE(h->f_ob, 8 * n);
+  ENSURE(h->f_ocnt, 4 * static_cast<size_t>(nq));
+  if (h->timing) CK(cudaEventRecord(h->ev[2], h->stream));
+  CK(cudaMemcpyAsync(h->f_bid.p, bm25_id, 8 * n, cudaMemcpyHostToDevice, h->stream));
+  CK(cudaMemcpyAsync(h->f_bsc.p, bm25_score, 8 * n, cudaMemcpyHostToDevice, h->stream));
+  CK(cudaMemcpyAsync(h->f_bcnt.p, bm25_count, 4 * static_cast<size_t>(nq), cudaMemcpyHostToDevice, h->stream));
+  CK(cudaMemcpyAsync(h->f_sid.p, sem_id, 8 * n, cudaMemcpyHostToDevice, h->stream));
+  CK(cudaMemcpyAsync(h->f_sds.p, sem_dist, 4 * n, cudaMemcpyHostToDevice, h->stream));
+  CK(cudaMemcpyAsync(h->f_scnt.p, sem_count, 4 * static_cast<size_t>(nq), cudaMemcpyHostToDevice, h->stream));
+  FuseIn in{static_cast<const long long*>(h->f_bid.p), static_cast<const double*>(h->f_bsc.p),
+            static_cast<const int*>(h->f_bcnt.p),      static_cast<const long long*>(h->f_sid.p),
+            static_cast<const float*>(h->f_sds.p),     static_cast<const int*>(h->f_scnt.p)};
+  int rc = fuse_launch(h, mode, param, tie_mode, nq, limit, in, static_cast<long long*>(h->f_oid.p),
+                       static_cast<double*>(h->f_osc.p), static_cast<double*>(h->f_oa.p),
+                       static_cast<double*>(h->f_ob.p), static_cast<int*>(h->f_ocnt.p));
+  if (rc != RSE_OK) return rc;
+  CK(cudaMemcpyAsync(out_id, h->f_oid.p, 8 * n, cudaMemcpyDeviceToHost, h->stream));
+  CK(cudaMemcpyAsync(out_score, h->f_osc.p, 8 * n, cudaMemcpyDeviceToHost, h->stream));
+  CK(cudaMemcpyAsync(out_a, h->f_oa.p, 8 * n, cudaMemcpyDeviceToHost, h->stream));
+  CK(cudaMemcpyAsync(out_b, h->f_ob.p, 8 * n, cudaMemcpyDeviceToHost, h->stream));
+  CK(cudaMemcpyAsync(out_count, h->f_ocnt.p, 4 * static_cast<size_t>(nq), cudaMemcpyDeviceToHost, h->stream));
+  if (h->timing) CK(cudaEventRecord(h->ev[3], h->stream));
+  CK(cudaStreamSynchronize(h->stream));
+  if (h->timing) {
+    float ms = 0.f;
+    CK(cudaEventElapsedTime(&ms, h->ev[2], h->ev[3]));
+    h->stats.last_fuse_ms = ms;
+  }
+  return RSE_OK;
+}
+
+}  // namespace
+
+int rse_fuse_weighted(rse_index* h, int32_t nq, int32_t limit, double alpha, int32_t tie_mode, const int64_t* bm25_id,
+                      const double* bm25_score, const int32_t* bm25_count, const int64_t* sem_id, const float* sem_dist,
+                      const int32_t* sem_count, int64_t* out_id, double* out_bm25, double* out_sem, double* out_score,
+                      int32_t* out_count) {
+  if (!h) return RSE_ERR_INVALID;
+  return fuse_host(h, 1, alpha, tie_mode, nq, limit, bm25_id, bm25_score, bm25_count, sem_id, sem_dist, sem_count,
+                   out_id, out_score, out_bm25, out_sem, out_count);
+}
+
+int rse_fuse_rrf(rse_index* h, int32_t nq, int32_t limit, double k, int32_t tie_mode, const int64_t* bm25_id,
+                 const double* bm25_score, const int32_t* bm25_count, const int64_t* sem_id, const float* sem_dist,
+                 const int32_t* sem_count, int64_t* out_id, double* out_score, int32_t* out_bm25_rank,
+                 int32_t* out_sem_rank, int32_t* out_count) {
+  if (!h) return RSE_ERR_INVALID;
+  if (nq > 0 && (!out_bm25_rank || !out_sem_rank)) return fail(h, RSE_ERR_INVALID, "rse_fuse_rrf: bad arguments");
+  const size_t n = static_cast<size_t>(std::max(nq, 0)) * std::max(limit, 0);
+  std::vector<double> a(std::max<size_t>(n, 1)), b(std::max<size_t>(n, 1));
+  int rc = fuse_host(h, 0, k, tie_mode, nq, limit, bm25_id, bm25_score, bm25_count, sem_id, sem_dist, sem_count, out_id,
+                     out_score, a.data(), b.data(), out_count);
+  if (rc != RSE_OK) return rc;
+  for (size_t i = 0; i < n; ++i) {
+    out_bm25_rank[i] = static_cast<int32_t>(a[i]);
+    out_sem_rank[i] = static_cast<int32_t>(b[i]);
+  }
+  return RSE_OK;
+}
+
+// ------------------------------------------------------------------ hybrid
+int rse_set_id_tables(rse_index* h, const int64_t* doc_ids, int64_t n_docs, const int64_t* movie_ids,
+                      int64_t n_movie_ids) {
+  if (!h) return RSE_ERR_INVALID;
+  if (n_docs < 0 || n_movie_ids < 0 || (n_docs > 0 && !doc_ids) || (n_movie_ids > 0 && !movie_ids))
+    return fail(h, RSE_ERR_INVALID, "rse_set_id_tables: bad arguments");
+  CK(cudaSetDevice(h->device));
+  free_ptr(h->doc_ids); free_ptr(h->movie_ids);
+  CK(cudaMalloc(&h->doc_ids, 8 * std::max<int64_t>(n_docs, 1)));
+  CK(cudaMalloc(&h->movie_ids, 8 * std::max<int64_t>(n_movie_ids, 1)));
+  if (n_docs) CK(cudaMemcpyAsync(h->doc_ids, doc_ids, 8 * n_docs, cudaMemcpyHostToDevice, h->stream));
+  if (n_movie_ids) CK(cudaMemcpyAsync(h->movie_ids, movie_ids, 8 * n_movie_ids, cudaMemcpyHostToDevice, h->stream));
+  CK(cudaStreamSynchronize(h->stream));
+  h->n_doc_ids = n_docs; h->n_movie_ids = n_movie_ids;
+  return RSE_OK;
+}
+
+int rse_hybrid(rse_index* h, int32_t mode, double param, int32_t tie_mode, int32_t limit, int32_t knn_multiplier,
+               int32_t nq, const float* q_host, const int32_t* tok_indptr, const int32_t* term_rows, double k1,
+               double b, int64_t* out_id, double* out_score, double* out_a, double* out_b, int32_t* out_count) {
+  if (!h) return RSE_ERR_INVALID;
+  if (nq < 0 || (nq > 0 && (!q_host || !tok_indptr || !out_id || !out_score || !out_a || !out_b || !out_count)))
+    return fail(h, RSE_ERR_INVALID, "rse_hybrid: bad arguments");
+  if (mode != 0 && mode != 1) return fail(h, RSE_ERR_INVALID, "rse_hybrid: mode must be 0 (rrf) or 1 (weighted)");
+  if (limit < 1 || limit > RSE_MAX_FUSE_LIMIT) return fail(h, RSE_ERR_UNSUPPORTED, "rse_hybrid: limit must be in [1, 128]");
+  if (!h->emb || !h->movie_idx || !h->indptr || !h->doc_ids || !h->movie_ids)
+    return fail(h, RSE_ERR_STATE, "rse_hybrid: needs embeddings (with movie_idx), a BM25 index and id tables");
+  if (nq == 0) return RSE_OK;
+  CK(cudaSetDevice(h->device));
+  const int kprime = std::max(limit * knn_multiplier, limit);   // semantic_search.py:251
+  if (kprime > RSE_MAX_KPRIME) return fail(h, RSE_ERR_UNSUPPORTED, "rse_hybrid: limit*knn_multiplier exceeds 4096");
+  h->stats.last_knn_scan_ms = 0.0;
+
+  // BM25 (k = limit, hybrid_search.py:70)
+  int rc = bm25_device(h, tok_indptr, term_rows, nq, limit, k1, b);
+  if (rc != RSE_OK) return rc;
+  // KNN + aggregation (k = limit, hybrid_search.py:88)
+  rc = upload_queries(h, q_host, nq);
+  if (rc != RSE_OK) return rc;
+  const size_t n = static_cast<size_t>(nq) * limit;
+  ENSURE(h->cand, sizeof(long long) * static_cast<size_t>(nq) * kprime * 3);
+  ENSURE(h->o_dist, sizeof(float) * n);
+  ENSURE(h->o_rowid, sizeof(long long) * n);
+  ENSURE(h->o_movie, sizeof(int) * n);
+  ENSURE(h->o_count, sizeof(int) * nq);
+  rc = knn_local(h, static_cast<const float*>(h->q_dev.p), nq, kprime, static_cast<long long*>(h->cand.p));
+  if (rc != RSE_OK) return rc;
+  rc = aggregate(h, static_cast<const long long*>(h->cand.p), nq, limit, kprime, static_cast<float*>(h->o_dist.p),
+                 static_cast<long long*>(h->o_rowid.p), static_cast<int*>(h->o_movie.p), static_cast<int*>(h->o_count.p));
+  if (rc != RSE_OK) return rc;
+  // dense index → movies.id
+  ENSURE(h->f_bid, 8 * n); ENSURE(h->f_sid, 8 * n);
+  ENSURE(h->f_oid, 8 * n); ENSURE(h->f_osc, 8 * n); ENSURE(h->f_oa, 8 * n); ENSURE(h->f_ob, 8 * n);
+  ENSURE(h->f_ocnt, 4 * static_cast<size_t>(nq));
+  const unsigned int gblocks = static_cast<unsigned int>((n + 255) / 256);
+  gather_ids_kernel<<<gblocks, 256, 0, h->stream>>>(static_cast<const int*>(h->b_doc.p), static_cast<int64_t>(n),
+                                                    h->doc_ids, h->n_doc_ids, static_cast<long long*>(h->f_bid.p));
+  LAUNCHED(h);
+  gather_ids_kernel<<<gblocks, 256, 0, h->stream>>>(static_cast<const int*>(h->o_movie.p), static_cast<int64_t>(n),
+                                                    h->movie_ids, h->n_movie_ids, static_cast<long long*>(h->f_sid.p));
+  LAUNCHED(h);
+  FuseIn in{static_cast<const long long*>(h->f_bid.p), static_cast<const double*>(h->b_score.p),
+            static_cast<const int*>(h->b_count.p),     static_cast<const long long*>(h->f_sid.p),
+            static_cast<const float*>(h->o_dist.p),    static_cast<const int*>(h->o_count.p)};
+  rc = fuse_launch(h, mode, param, tie_mode, nq, limit, in, static_cast<long long*>(h->f_oid.p),
+                   static_cast<double*>(h->f_osc.p), static_cast<double*>(h->f_oa.p), static_cast<double*>(h->f_ob.p),
+                   static_cast<int*>(h->f_ocnt.p));
+  if (rc != RSE_OK) return rc;
+  CK(cudaMemcpyAsync(out_id, h->f_oid.p, 8 * n, cudaMemcpyDeviceToHost, h->stream));
+  CK(cudaMemcpyAsync(out_score, h->f_osc.p, 8 * n, cudaMemcpyDeviceToHost, h->stream));
+  CK(cudaMemcpyAsync(out_a, h->f_oa.p, 8 * n, cudaMemcpyDeviceToHost, h->stream));
+  CK(cudaMemcpyAsync(out_b, h->f_ob.p, 8 * n, cudaMemcpyDeviceToHost, h->stream));
+  CK(cudaMemcpyAsync(out_count, h->f_ocnt.p, 4 * static_cast<size_t>(nq), cudaMemcpyDeviceToHost, h->stream));
+  CK(cudaStreamSynchronize(h->stream));
+  return RSE_OK;
+}
+
+}  // extern "C"
