@@ -1,0 +1,366 @@
+#!/usr/bin/env python
+"""bench.py — hybrid queries/sec (RRF, top-10) on the movies_600k-shaped synthetic corpus.
+
+    python bench.py --gpus N --steps K --warmup W            # this repo (librse on the B200)
+    python bench.py --impl reference --gpus N --steps K ...   # the reference's CPU path (oracle port)
+
+A "step" = one batch of hybrid queries through the whole hot path
+(BM25 top-10 + exact vec0 KNN top-100 + best-chunk-per-movie + RRF fusion).
+  value : whole-job queries/s with the query batch already resident in HBM
+          (rse_hybrid_stage once, then K × rse_hybrid_run), CUDA events, max over ranks.
+  e2e   : the same metric through the host-buffer C-ABI call (rse_hybrid): H2D of the
+          query vectors/tokens from pinned memory and D2H of the results inside the timed region.
+N > 1   : strong scaling — the same corpus row-sharded over N ranks (vec0-block aligned), one
+          all_gather of the local top-K' candidates per step, BM25/fusion split by query slice.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import time
+from pathlib import Path
+
+ROOT = Path(__file__).resolve().parent
+if str(ROOT) not in sys.path:
+    sys.path.insert(0, str(ROOT))
+
+import numpy as np  # noqa: E402
+
+ROW_BYTES = 384 * 4 + 4          # algorithmic bytes per chunk row per pass: 1536 B vector + 4 B |a|^2
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--movies", type=int, default=600_000)
+    ap.add_argument("--vocab", type=int, default=1_000_000)
+    ap.add_argument("--batch", type=int, default=256, help="hybrid queries per step")
+    ap.add_argument("--limit", type=int, default=10)
+    ap.add_argument("--mode", default="rrf", choices=["rrf", "weighted"])
+    ap.add_argument("--cpu-sample", type=int, default=0, help="queries in the cpu_baseline sample (0 = 2 x cores)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    return ap.parse_args()
+
+
+# ----------------------------------------------------------------------------- clocks
+class ClockSampler:
+    FIELDS = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+              "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+              "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int):
+        self.gpu = gpu_index
+        self.proc = None
+        self.path = Path(os.environ.get("TMPDIR", "/tmp")) / f"rse_clocks_{os.getpid()}.csv"
+
+    def start(self):
+        try:
+            self.fh = open(self.path, "w")
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu), f"--query-gpu={self.FIELDS}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"], stdout=self.fh,
+                                         stderr=subprocess.DEVNULL)
+        except Exception:
+            self.proc = None
+
+    def stop(self) -> dict:
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        if self.proc is None:
+            return out
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        self.fh.close()
+        sm, mx, reasons = [], [], set()
+        for line in self.path.read_text().splitlines():
+            p = [x.strip() for x in line.split(",")]
+            if len(p) < 8:
+                continue
+            try:
+                sm.append(float(p[0])); mx.append(float(p[1]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), p[4:8]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        if sm:
+            out.update(sm_mhz=statistics.median(sm), sm_max_mhz=max(mx), reasons=sorted(reasons), samples=len(sm))
+        try:
+            self.path.unlink()
+        except Exception:
+            pass
+        return out
+
+
+# ----------------------------------------------------------------------------- workload
+def build_workload(args, device: str):
+    """Seeded S-600k corpus + query batch (identical on every rank and in both arms)."""
+    import torch
+    from rag_search_engine_b200 import synth
+    t0 = time.time()
+    se = synth.synth_embeddings(args.movies, seed=1234, device=device)
+    bm = synth.synth_bm25(args.movies, args.vocab, seed=1234, device=device)
+    tok_indptr, terms = synth.synth_token_queries(bm, args.batch, seed=99)
+    Q = synth.synth_query_vectors(se.emb, args.batch, seed=99)
+    if device != "cpu":
+        torch.cuda.synchronize()
+    info = {"chunks": int(se.emb.shape[0]), "dim": int(se.emb.shape[1]), "movies": args.movies,
+            "postings": int(len(bm.doc_idx)), "terms": int(len(bm.df)), "build_s": round(time.time() - t0, 1)}
+    return se, bm, tok_indptr, terms, Q, info
+
+
+def postings_touched(bm, tok_indptr, terms) -> int:
+    t = terms[terms >= 0]
+    return int(bm.df[t].sum())
+
+
+def config_dict(args, info, world):
+    return {"workload": "configs[3]: movies_600k-shaped synthetic (S-600k), hybrid rrf_search k=60 limit=10 "
+                        "(BM25 top-10 + exact vec0 KNN top-100 + per-movie best chunk + RRF), Gemini disabled",
+            "mode": args.mode, "limit": args.limit, "knn_kprime": max(args.limit * 10, args.limit),
+            "queries_per_step": args.batch, "movies": info["movies"], "chunks": info["chunks"], "dim": info["dim"],
+            "bm25_postings": info["postings"], "bm25_terms": info["terms"],
+            "l2": "inputs larger than L2 (7.4 GB embedding stream per 8-query pass vs 126 MB L2); no flush",
+            "parallelism": f"row-shard x{world} + all_gather(top-K') + query-slice BM25/fusion" if world > 1 else "1 GPU"}
+
+
+# ----------------------------------------------------------------------------- CPU baseline (oracle port)
+def cpu_hybrid_sample(se_emb_host, movie_of, bm, ids, Q, tok_indptr, terms, limit, mode, sample, threads):
+    """The reference's CPU path restated (oracle/): literal vec0 scan + aggregation, BM25, fusion."""
+    import oracle
+    from oracle import pyref
+    os.environ["OMP_NUM_THREADS"] = str(threads)
+    nq = sample
+    tp = tok_indptr[: nq + 1].astype(np.int32)
+    tr = terms[: tp[-1]]
+    t0 = time.perf_counter()
+    kd, krow, kc = oracle.knn_movies_batch(se_emb_host, Q[:nq], movie_of, limit, max(limit * 10, limit), literal=True)
+    osc, odc, ocnt = oracle.bm25_batch(bm.indptr, bm.doc_idx, bm.tf, bm.df, bm.dl, bm.n_movies, bm.avgdl, tp, tr, limit)
+    out = []
+    for qi in range(nq):
+        bmh = [(int(ids[odc[qi, j]]), float(osc[qi, j])) for j in range(ocnt[qi])]
+        semh = [(int(ids[movie_of[krow[qi, j]]]), float(kd[qi, j])) for j in range(kc[qi])]
+        out.append(pyref.rrf_fuse(bmh, semh, 60, limit) if mode == "rrf" else pyref.weighted_fuse(bmh, semh, 0.5, limit))
+    dt = time.perf_counter() - t0
+    return nq / dt, dt, out
+
+
+def run_reference(args, rank, world):
+    """--impl reference: the reference's CPU implementation of the path on the box's host cores.
+    The reference is Python + un-vendored sqlite-vec and cannot travel to the GPU box, so this
+    times the oracle port (oracle/oracle.c: literal vec0 scan; BM25 over CSR; fusion in Python)."""
+    if rank != 0:
+        return
+    import torch
+    dev = "cuda" if torch.cuda.is_available() else "cpu"   # data generation only
+    se, bm, tok_indptr, terms, Q, info = build_workload(args, dev)
+    emb_host = se.emb.cpu().numpy()
+    movie_of = se.movie_of_chunk.cpu().numpy().astype(np.int64)
+    Qh = Q.cpu().numpy()
+    del se.emb
+    cores = os.cpu_count() or 1
+    sample = min(args.batch, args.cpu_sample or cores)
+    import oracle
+    oracle.build()
+    times = []
+    for step in range(args.warmup + args.steps):
+        off = (step * sample) % max(1, args.batch - sample + 1)
+        tp = (tok_indptr[off: off + sample + 1] - tok_indptr[off]).astype(np.int32)
+        tr = terms[tok_indptr[off]: tok_indptr[off + sample]]
+        qps, dt, _ = cpu_hybrid_sample(emb_host, movie_of, bm, se.movie_ids, Qh[off: off + sample], tp, tr, args.limit,
+                                       args.mode, sample, cores)
+        if step >= args.warmup:
+            times.append(dt)
+    total = sum(times)
+    value = sample * len(times) / total
+    line = {"impl": "reference", "metric": "hybrid queries/sec", "value": value, "unit": "queries/s",
+            "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * total / len(times),
+            "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32 scan + f64 tail/BM25/fusion",
+            "data": "synthetic", "config": config_dict(args, info, 1),
+            "cpu_baseline": {"value": value, "unit": "queries/s", "cores": cores, "kind": "port",
+                             "sample": f"{sample} hybrid queries per step over the full S-600k corpus "
+                                       f"(OpenMP over queries, each query a single-threaded literal vec0 scan)"},
+            "e2e": {"value": value, "unit": "queries/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line), flush=True)
+
+
+# ----------------------------------------------------------------------------- B200 arm
+def run_b200(args, rank, world, local_rank):
+    import torch
+    import torch.distributed as dist
+    from rag_search_engine_b200 import _lib, sharded
+
+    torch.cuda.set_device(local_rank)
+    device = torch.device("cuda", local_rank)
+    se, bm, tok_indptr, terms, Q, info = build_workload(args, f"cuda:{local_rank}")
+    C = info["chunks"]
+    bounds = sharded.shard_bounds(C, world)
+    lo, hi = bounds[rank], bounds[rank + 1]
+    idx = _lib.Index(local_rank)
+    stream = torch.cuda.current_stream(device)
+    idx.set_stream(stream.cuda_stream)
+    shard = se.emb[lo:hi]
+    mo = se.movie_of_chunk[lo:hi].contiguous()
+    idx.attach_embeddings_dev(shard.data_ptr(), hi - lo, info["dim"], movie_idx_ptr=mo.data_ptr(), pos_base=lo,
+                              keepalive=(se, shard, mo))
+    idx.load_bm25(bm.indptr, bm.doc_idx, bm.tf, bm.df, bm.dl, bm.n_movies, bm.avgdl)
+    idx.set_id_tables(se.movie_ids, se.movie_ids)
+    mode = 0 if args.mode == "rrf" else 1
+    param = 60.0 if mode == 0 else 0.5
+    limit, nq = args.limit, args.batch
+    Qh = torch.empty((nq, info["dim"]), dtype=torch.float32, pin_memory=True)
+    Qh.copy_(Q.cpu())
+    Qn = Qh.numpy()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+
+    if world > 1:
+        backend = sharded.LibrseShardBackend(idx, Qn, tok_indptr, terms, device)
+        sh = sharded.ShardedHybrid(backend, nq)
+        Qd = Q.to(device).contiguous()
+        step_fn = lambda: sh.step(Qd, mode, param, limit)        # noqa: E731
+    else:
+        idx.hybrid_stage(Qn, tok_indptr, terms)
+        step_fn = lambda: idx.hybrid_run(mode, param, limit)     # noqa: E731
+
+    for _ in range(max(args.warmup, 3)):
+        step_fn()
+    torch.cuda.synchronize(); barrier()
+
+    # ---- timed region: K steps, inputs resident in HBM
+    idx.set_timing(True)
+    idx.stats_reset()
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize(); barrier()
+    e0.record(stream)
+    for _ in range(args.steps):
+        step_fn()
+    e1.record(stream)
+    torch.cuda.synchronize(); barrier()
+    ms = e0.elapsed_time(e1)
+    clocks = sampler.stop()
+    st = idx.stats()
+    idx.set_timing(False)
+    launches = int(st.kernel_launches)
+    scan_ms = st.scan_ms_total / max(1, st.scan_launches_timed)
+    scan_share = st.scan_ms_total / ms if ms > 0 else None
+    if world > 1:
+        t = torch.tensor([ms], dtype=torch.float64, device=device)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+    value = nq * args.steps / (ms / 1e3)
+
+    # ---- e2e: host buffers through the C-ABI call, copies inside the timed region
+    e2e = None
+    if not args.no_e2e and world == 1:
+        for _ in range(2):
+            idx.hybrid(mode, param, limit, Qn, tok_indptr, terms)
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        e0.record(stream)
+        for _ in range(args.steps):
+            res = idx.hybrid(mode, param, limit, Qn, tok_indptr, terms)
+        e1.record(stream)
+        torch.cuda.synchronize()
+        wall = time.perf_counter() - t0
+        ntok = int(tok_indptr[-1])
+        h2d = Qn.nbytes + (nq + 1) * 4 + ntok * (4 + 8)
+        d2h = nq * limit * (8 + 8 + 8 + 8) + nq * 4
+        e2e = {"value": nq * args.steps / wall, "unit": "queries/s", "h2d_bytes_per_step": int(h2d),
+               "d2h_bytes_per_step": int(d2h), "device_ms_per_step": e0.elapsed_time(e1) / args.steps,
+               "wall_ms_per_step": 1e3 * wall / args.steps}
+    elif world > 1:
+        # sharded e2e: stage (H2D of this rank's slice + the batch's query vectors) + step + D2H of the fused batch
+        torch.cuda.synchronize(); barrier()
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            backend.stage_slice(sh.lo, sh.hi)
+            Qd2 = Qh.to(device, non_blocking=True)
+            r = sh.step(Qd2, mode, param, limit)
+            _ = r.ids.cpu(), r.score.cpu(), r.count.cpu()
+        torch.cuda.synchronize(); barrier()
+        wall = time.perf_counter() - t0
+        t = torch.tensor([wall], dtype=torch.float64, device=device)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        wall = float(t.item())
+        e2e = {"value": nq * args.steps / wall, "unit": "queries/s", "h2d_bytes_per_step": int(Qn.nbytes),
+               "d2h_bytes_per_step": int(nq * limit * 16 + nq * 4), "wall_ms_per_step": 1e3 * wall / args.steps}
+
+    if rank != 0:
+        return
+    peaks = {}
+    pk = ROOT / "MEASURED_PEAKS.json"
+    if pk.exists():
+        peaks = json.loads(pk.read_text())
+    peak = float(peaks.get("hbm_gbs", 6650.0))
+    rows_local = hi - lo
+    alg_bytes = rows_local * ROW_BYTES
+    achieved = alg_bytes / (scan_ms * 1e-3) / 1e9 if scan_ms > 0 else None
+    roofline = {"bound": "hbm", "kernel": "knn_scan384_kernel<QB=8> (one pass over the shard serves 8 queries)",
+                "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": (achieved / peak) if achieved else None,
+                "peak_source": "MEASURED_PEAKS.json hbm_gbs (of measured)" if peaks else "fallback 6650 GB/s (of fallback)",
+                "traffic": None, "algorithmic_bytes_per_launch": alg_bytes, "avg_launch_ms": scan_ms,
+                "scan_launches": int(st.scan_launches_timed), "scan_share_of_step": scan_share}
+
+    line = {"metric": "hybrid queries/sec", "value": value, "unit": "queries/s", "n_gpus": world, "steps": args.steps,
+            "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps, "higher_is_better": True,
+            "scaling": "strong", "vs_baseline": None, "dtype": "f32 scan + f64 tail/BM25/fusion", "data": "synthetic",
+            "config": config_dict(args, info, world), "roofline": roofline, "clocks": clocks, "e2e": e2e,
+            "gpu_launches": launches, "postings_touched_per_step": postings_touched(bm, tok_indptr, terms)}
+
+    if world == 1 and not args.no_cpu_baseline:
+        cores = os.cpu_count() or 1
+        sample = min(nq, args.cpu_sample or 2 * cores)
+        emb_host = se.emb.cpu().numpy()
+        movie_of = se.movie_of_chunk.cpu().numpy().astype(np.int64)
+        qps, dt, cpu_out = cpu_hybrid_sample(emb_host, movie_of, bm, se.movie_ids, Qn, tok_indptr, terms, limit, args.mode,
+                                             sample, cores)
+        # the sample doubles as a full-size parity check of the GPU results
+        oid, osc, oa, ob, oc = res if e2e and world == 1 else idx.hybrid(mode, param, limit, Qn, tok_indptr, terms)
+        ok = all([int(x) for x in oid[q, :oc[q]]] == [r["id"] for r in cpu_out[q]] and
+                 [float(x) for x in osc[q, :oc[q]]] == [r["score"] for r in cpu_out[q]] for q in range(sample))
+        line["cpu_baseline"] = {"value": qps, "unit": "queries/s", "cores": cores, "kind": "port",
+                                "sample": f"{sample} hybrid queries of the same batch over the full corpus, "
+                                          f"{dt:.1f} s (OpenMP over queries; literal vec0 scan per query)",
+                                "gpu_matches_cpu_on_sample": bool(ok)}
+    print(json.dumps(line), flush=True)
+    idx.close()
+
+
+def main():
+    args = parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+        return
+    if world > 1:
+        import torch
+        import torch.distributed as dist
+        torch.cuda.set_device(local_rank)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    try:
+        run_b200(args, rank, world, local_rank)
+    finally:
+        if world > 1:
+            import torch.distributed as dist
+            dist.barrier()
+            dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

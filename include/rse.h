@@ -172,6 +172,26 @@ int rse_hybrid(rse_index *h, int32_t mode, double param, int32_t tie_mode, int32
                int32_t knn_multiplier, int32_t nq, const float *q_host, const int32_t *tok_indptr,
                const int32_t *term_rows, double k1, double b, int64_t *out_id, double *out_score,
                double *out_a, double *out_b, int32_t *out_count);
+/* The same call split in three, for callers that keep a query batch resident in HBM
+ * (rse_hybrid == stage + run + fetch):
+ *   stage: upload query vectors + tokens (+ host-computed idf, keyword_search.py:224);
+ *   run:   BM25 + KNN + aggregation + fusion on the staged batch; asynchronous on the
+ *          handle's stream, results stay on the device; may be repeated;
+ *   fetch: copy the [nq, limit] results to the host and synchronise. */
+int rse_hybrid_stage(rse_index *h, int32_t nq, const float *q_host, const int32_t *tok_indptr,
+                     const int32_t *term_rows);
+int rse_hybrid_run(rse_index *h, int32_t mode, double param, int32_t tie_mode, int32_t limit,
+                   int32_t knn_multiplier, double k1, double b);
+/* Row-sharded variant of `run`: the KNN stage is replaced by the merge of
+ * n_lists gathered candidate lists ([n_lists, nq, kprime, 3] from rse_knn_local_dev on every
+ * shard + all_gather); the staged batch is this rank's query slice.  Outputs are DEVICE
+ * buffers [nq, limit] (they feed the final all_gather).  Asynchronous on the handle's stream. */
+int rse_hybrid_run_merged_dev(rse_index *h, int32_t mode, double param, int32_t tie_mode, int32_t limit,
+                              int32_t knn_multiplier, double k1, double b, const int64_t *gathered_dev,
+                              int32_t n_lists, int64_t *out_id_dev, double *out_score_dev,
+                              double *out_a_dev, double *out_b_dev, int32_t *out_count_dev);
+int rse_hybrid_fetch(rse_index *h, int32_t limit, int64_t *out_id, double *out_score, double *out_a,
+                     double *out_b, int32_t *out_count);
 
 /* ------------------------------------------------------------------ introspection
  * Counters since the last rse_stats_reset: kernels launched by this library,
@@ -179,8 +199,9 @@ int rse_hybrid(rse_index *h, int32_t mode, double param, int32_t tie_mode, int32
 typedef struct rse_stats {
   int64_t kernel_launches;
   int64_t knn_scan_launches;
-  double last_knn_scan_ms;   /* sum of scan-kernel time in the last knn call */
-  double last_knn_total_ms;  /* scan + select + aggregate */
+  double scan_ms_total;        /* Σ device time of the K1 scan launches (event pairs, resolved in rse_get_stats) */
+  int64_t scan_launches_timed; /* how many scan launches that sum covers */
+  double last_knn_total_ms;    /* last rse_knn / rse_knn_movies call, H2D → D2H */
   double last_bm25_ms;
   double last_fuse_ms;
   int64_t emb_rows;
@@ -190,7 +211,7 @@ typedef struct rse_stats {
 } rse_stats;
 int rse_get_stats(rse_index *h, rse_stats *out);
 int rse_stats_reset(rse_index *h);
-/* Enable per-stage CUDA-event timing (adds event records + a sync per call). */
+/* Enable CUDA-event timing: an event pair around every scan launch (no extra syncs). */
 int rse_set_timing(rse_index *h, int32_t enabled);
 
 #ifdef __cplusplus

@@ -34,7 +34,8 @@ class RseStats(ctypes.Structure):
     _fields_ = [
         ("kernel_launches", c_int64),
         ("knn_scan_launches", c_int64),
-        ("last_knn_scan_ms", c_double),
+        ("scan_ms_total", c_double),
+        ("scan_launches_timed", c_int64),
         ("last_knn_total_ms", c_double),
         ("last_bm25_ms", c_double),
         ("last_fuse_ms", c_double),
@@ -81,6 +82,12 @@ _SIGNATURES = {
     "rse_hybrid": (ctypes.c_int, [c_void_p, c_int32, c_double, c_int32, c_int32, c_int32, c_int32, POINTER(c_float),
                                   POINTER(c_int32), POINTER(c_int32), c_double, c_double, POINTER(c_int64),
                                   POINTER(c_double), POINTER(c_double), POINTER(c_double), POINTER(c_int32)]),
+    "rse_hybrid_stage": (ctypes.c_int, [c_void_p, c_int32, c_void_p, c_void_p, c_void_p]),
+    "rse_hybrid_run": (ctypes.c_int, [c_void_p, c_int32, c_double, c_int32, c_int32, c_int32, c_double, c_double]),
+    "rse_hybrid_run_merged_dev": (ctypes.c_int, [c_void_p, c_int32, c_double, c_int32, c_int32, c_int32, c_double,
+                                                 c_double, c_void_p, c_int32, c_void_p, c_void_p, c_void_p, c_void_p,
+                                                 c_void_p]),
+    "rse_hybrid_fetch": (ctypes.c_int, [c_void_p, c_int32, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
     "rse_get_stats": (ctypes.c_int, [c_void_p, POINTER(RseStats)]),
     "rse_stats_reset": (ctypes.c_int, [c_void_p]),
     "rse_set_timing": (ctypes.c_int, [c_void_p, c_int32]),
@@ -318,3 +325,41 @@ class Index:
                                        _ptr(osc, c_double), _ptr(oa, c_double), _ptr(ob, c_double),
                                        _ptr(oc, c_int32)))
         return oid, osc, oa, ob, oc
+
+    # split form (inputs resident in HBM between run() calls); pointers are raw host addresses
+    def hybrid_stage(self, Q, tok_indptr, term_rows):
+        Q = _c(Q, np.float32).reshape(-1, self.dim)
+        tok_indptr = _c(tok_indptr, np.int32)
+        term_rows = _c(term_rows, np.int32)
+        if term_rows.size == 0:
+            term_rows = np.zeros(1, np.int32)
+        self._check(self._L.rse_hybrid_stage(self._h, Q.shape[0], c_void_p(Q.ctypes.data),
+                                             c_void_p(tok_indptr.ctypes.data), c_void_p(term_rows.ctypes.data)))
+        self._staged_nq = Q.shape[0]
+
+    def hybrid_run(self, mode: int, param: float, limit: int, knn_multiplier: int = 10, k1: float = 1.5,
+                   b: float = 0.75, tie_mode: int = TIE_REFERENCE):
+        self._check(self._L.rse_hybrid_run(self._h, int(mode), float(param), int(tie_mode), int(limit),
+                                           int(knn_multiplier), float(k1), float(b)))
+
+    def hybrid_fetch(self, limit: int):
+        nq = self._staged_nq
+        oid = np.zeros((nq, limit), np.int64)
+        osc = np.zeros((nq, limit), np.float64)
+        oa = np.zeros((nq, limit), np.float64)
+        ob = np.zeros((nq, limit), np.float64)
+        oc = np.zeros(nq, np.int32)
+        self._check(self._L.rse_hybrid_fetch(self._h, int(limit), c_void_p(oid.ctypes.data), c_void_p(osc.ctypes.data),
+                                             c_void_p(oa.ctypes.data), c_void_p(ob.ctypes.data),
+                                             c_void_p(oc.ctypes.data)))
+        return oid, osc, oa, ob, oc
+
+    def hybrid_run_merged_dev(self, mode: int, param: float, limit: int, gathered_ptr: int, n_lists: int,
+                              out_id_ptr: int, out_score_ptr: int, out_a_ptr: int, out_b_ptr: int, out_count_ptr: int,
+                              knn_multiplier: int = 10, k1: float = 1.5, b: float = 0.75,
+                              tie_mode: int = TIE_REFERENCE):
+        self._check(self._L.rse_hybrid_run_merged_dev(self._h, int(mode), float(param), int(tie_mode), int(limit),
+                                                      int(knn_multiplier), float(k1), float(b),
+                                                      c_void_p(gathered_ptr), int(n_lists), c_void_p(out_id_ptr),
+                                                      c_void_p(out_score_ptr), c_void_p(out_a_ptr),
+                                                      c_void_p(out_b_ptr), c_void_p(out_count_ptr)))

@@ -39,6 +39,12 @@ struct rse_index {
   bool fma = false;
   bool timing = false;
   cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
+  // scan-kernel timing: event pairs recorded around every scan launch without
+  // synchronising; resolved lazily in rse_get_stats (after the caller's sync).
+  std::vector<cudaEvent_t> scan_ev;   // 2 per timed launch
+  size_t scan_ev_used = 0;
+  // staged hybrid query batch (rse_hybrid_stage)
+  int staged_nq = 0;
 
   // ---- a1: embeddings (vec0 physical layout)
   const float* emb = nullptr;
@@ -212,24 +218,29 @@ int knn_local(rse_index* h, const float* q_dev, int nq, int kprime, long long* c
 
   for (int g0 = 0; g0 < nq; g0 += QB) {
     const int ng = std::min(QB, nq - g0);
-    if (h->timing) CK(cudaEventRecord(h->ev[0], h->stream));
+    cudaEvent_t e0 = nullptr, e1 = nullptr;
+    if (h->timing && h->scan_ev_used + 2 <= (1u << 16)) {
+      while (h->scan_ev.size() < h->scan_ev_used + 2) {
+        cudaEvent_t e;
+        CK(cudaEventCreate(&e));
+        h->scan_ev.push_back(e);
+      }
+      e0 = h->scan_ev[h->scan_ev_used];
+      e1 = h->scan_ev[h->scan_ev_used + 1];
+      h->scan_ev_used += 2;
+      CK(cudaEventRecord(e0, h->stream));
+    }
     int rc = h->fma ? launch_scan<true>(h, q_dev + static_cast<int64_t>(g0) * h->dim, sb + g0, ng, dist)
                     : launch_scan<false>(h, q_dev + static_cast<int64_t>(g0) * h->dim, sb + g0, ng, dist);
     if (rc != RSE_OK) return rc;
-    if (h->timing) {
-      CK(cudaEventRecord(h->ev[1], h->stream));
-      CK(cudaEventSynchronize(h->ev[1]));
-      float ms = 0.f;
-      CK(cudaEventElapsedTime(&ms, h->ev[0], h->ev[1]));
-      h->stats.last_knn_scan_ms += ms;
-    }
+    if (e1) CK(cudaEventRecord(e1, h->stream));
     dim3 grid(sel_blocks, ng);
     for (int p = 0; p < 6; ++p) {
-      select_pass_kernel<<<grid, kSelThreads, 0, h->stream>>>(dist, h->dist_ld, h->n_rows, h->pos_base, sel + g0, hist,
+      select_pass_kernel<<<grid, kSelThreads, 0, h->stream>>>(reinterpret_cast<const uint32_t*>(dist), h->dist_ld, h->n_rows, h->pos_base, sel + g0, hist,
                                                               shifts[p], widths[p]);
       LAUNCHED(h);
     }
-    select_collect_kernel<<<grid, kSelThreads, 0, h->stream>>>(dist, h->dist_ld, h->n_rows, h->pos_base, sel + g0,
+    select_collect_kernel<<<grid, kSelThreads, 0, h->stream>>>(reinterpret_cast<const uint32_t*>(dist), h->dist_ld, h->n_rows, h->pos_base, sel + g0,
                                                                selkeys + static_cast<int64_t>(g0) * kprime, kprime);
     LAUNCHED(h);
   }
@@ -345,6 +356,7 @@ void rse_destroy(rse_index* h) {
   free_ptr(h->doc_ids);
   free_ptr(h->movie_ids);
   for (auto& ev : h->ev) if (ev) cudaEventDestroy(ev);
+  for (auto& ev : h->scan_ev) cudaEventDestroy(ev);
   if (h->own_stream) cudaStreamDestroy(h->own_stream);
   delete h;
 }
@@ -378,6 +390,17 @@ int rse_set_timing(rse_index* h, int32_t enabled) {
 
 int rse_get_stats(rse_index* h, rse_stats* out) {
   if (!h || !out) return RSE_ERR_INVALID;
+  // resolve pending scan event pairs (the caller has synchronised; if not, do it)
+  if (h->scan_ev_used) {
+    CK(cudaStreamSynchronize(h->stream));
+    for (size_t i = 0; i + 1 < h->scan_ev_used; i += 2) {
+      float ms = 0.f;
+      CK(cudaEventElapsedTime(&ms, h->scan_ev[i], h->scan_ev[i + 1]));
+      h->stats.scan_ms_total += ms;
+      h->stats.scan_launches_timed++;
+    }
+    h->scan_ev_used = 0;
+  }
   *out = h->stats;
   return RSE_OK;
 }
@@ -387,6 +410,7 @@ int rse_stats_reset(rse_index* h) {
   const int64_t rows = h->stats.emb_rows, post = h->stats.bm25_postings, docs = h->stats.bm25_docs;
   const int dim = h->stats.emb_dim;
   h->stats = rse_stats{};
+  h->scan_ev_used = 0;
   h->stats.emb_rows = rows; h->stats.emb_dim = dim; h->stats.bm25_postings = post; h->stats.bm25_docs = docs;
   return RSE_OK;
 }
@@ -460,7 +484,6 @@ int rse_knn(rse_index* h, const float* q_host, int32_t nq, int32_t kprime, float
   if (!h->emb) return fail(h, RSE_ERR_STATE, "rse_knn: no embeddings loaded");
   if (nq == 0) return RSE_OK;
   CK(cudaSetDevice(h->device));
-  h->stats.last_knn_scan_ms = 0.0;
   if (h->timing) CK(cudaEventRecord(h->ev[2], h->stream));
   int rc = upload_queries(h, q_host, nq);
   if (rc != RSE_OK) return rc;
@@ -502,7 +525,6 @@ int rse_knn_movies(rse_index* h, const float* q_host, int32_t nq, int32_t k, int
   if (!h->movie_idx) return fail(h, RSE_ERR_STATE, "rse_knn_movies: embeddings were loaded without movie_idx");
   if (nq == 0) return RSE_OK;
   CK(cudaSetDevice(h->device));
-  h->stats.last_knn_scan_ms = 0.0;
   if (h->timing) CK(cudaEventRecord(h->ev[2], h->stream));
   int rc = upload_queries(h, q_host, nq);
   if (rc != RSE_OK) return rc;
@@ -611,11 +633,9 @@ int rse_load_bm25(rse_index* h, const int64_t* indptr, const uint32_t* doc_idx, 
 
 namespace {
 
-// tokens → device (with host-computed idf, keyword_search.py:224); results stay on the device
-// in h->b_score / b_doc / b_count ([nq][k]).
-int bm25_device(rse_index* h, const int32_t* tok_indptr, const int32_t* term_rows, int nq, int k, double k1, double b) {
+// tokens → device, with host-computed idf (keyword_search.py:224, same libm `log` as CPython).
+int bm25_stage(rse_index* h, const int32_t* tok_indptr, const int32_t* term_rows, int nq) {
   if (!h->indptr) return fail(h, RSE_ERR_STATE, "rse_bm25: no BM25 index loaded");
-  if (k < 1 || k > RSE_MAX_BM25_K) return fail(h, RSE_ERR_UNSUPPORTED, "rse_bm25: k must be in [1, 256]");
   const int64_t ntok = tok_indptr[nq];
   if (tok_indptr[0] != 0 || ntok < 0) return fail(h, RSE_ERR_INVALID, "rse_bm25: bad tok_indptr");
   std::vector<double> idf(static_cast<size_t>(std::max<int64_t>(ntok, 1)), 0.0);
@@ -639,14 +659,24 @@ int bm25_device(rse_index* h, const int32_t* tok_indptr, const int32_t* term_row
   ENSURE(h->b_tokptr, sizeof(int32_t) * (nq + 1));
   ENSURE(h->b_terms, sizeof(int32_t) * std::max<int64_t>(ntok, 1));
   ENSURE(h->b_idf, sizeof(double) * std::max<int64_t>(ntok, 1));
-  ENSURE(h->b_score, sizeof(double) * static_cast<size_t>(nq) * k);
-  ENSURE(h->b_doc, sizeof(int) * static_cast<size_t>(nq) * k);
-  ENSURE(h->b_count, sizeof(int) * nq);
+  // pageable staging vectors die at return → synchronous copies here
   CK(cudaMemcpyAsync(h->b_tokptr.p, tok_indptr, sizeof(int32_t) * (nq + 1), cudaMemcpyHostToDevice, h->stream));
   if (ntok > 0) {
     CK(cudaMemcpyAsync(h->b_terms.p, terms.data(), sizeof(int32_t) * ntok, cudaMemcpyHostToDevice, h->stream));
     CK(cudaMemcpyAsync(h->b_idf.p, idf.data(), sizeof(double) * ntok, cudaMemcpyHostToDevice, h->stream));
   }
+  CK(cudaStreamSynchronize(h->stream));
+  return RSE_OK;
+}
+
+// scoring + top-k on the staged tokens; results stay on the device in
+// h->b_score / b_doc / b_count ([nq][k]).
+int bm25_run(rse_index* h, int nq, int k, double k1, double b) {
+  if (!h->indptr) return fail(h, RSE_ERR_STATE, "rse_bm25: no BM25 index loaded");
+  if (k < 1 || k > RSE_MAX_BM25_K) return fail(h, RSE_ERR_UNSUPPORTED, "rse_bm25: k must be in [1, 256]");
+  ENSURE(h->b_score, sizeof(double) * static_cast<size_t>(nq) * k);
+  ENSURE(h->b_doc, sizeof(int) * static_cast<size_t>(nq) * k);
+  ENSURE(h->b_count, sizeof(int) * nq);
   if (!(h->normk_k1 == k1 && h->normk_b == b) && h->n_docs > 0) {
     const int threads = 256;
     bm25_norm_kernel<<<static_cast<unsigned int>((h->n_docs + threads - 1) / threads), threads, 0, h->stream>>>(
@@ -676,6 +706,13 @@ int bm25_device(rse_index* h, const int32_t* tok_indptr, const int32_t* term_row
     LAUNCHED(h);
   }
   return RSE_OK;
+}
+
+int bm25_device(rse_index* h, const int32_t* tok_indptr, const int32_t* term_rows, int nq, int k, double k1, double b) {
+  if (k < 1 || k > RSE_MAX_BM25_K) return fail(h, RSE_ERR_UNSUPPORTED, "rse_bm25: k must be in [1, 256]");
+  int rc = bm25_stage(h, tok_indptr, term_rows, nq);
+  if (rc != RSE_OK) return rc;
+  return bm25_run(h, nq, k, k1, b);
 }
 
 }  // namespace
@@ -813,43 +850,67 @@ int rse_set_id_tables(rse_index* h, const int64_t* doc_ids, int64_t n_docs, cons
   return RSE_OK;
 }
 
-int rse_hybrid(rse_index* h, int32_t mode, double param, int32_t tie_mode, int32_t limit, int32_t knn_multiplier,
-               int32_t nq, const float* q_host, const int32_t* tok_indptr, const int32_t* term_rows, double k1,
-               double b, int64_t* out_id, double* out_score, double* out_a, double* out_b, int32_t* out_count) {
+int rse_hybrid_stage(rse_index* h, int32_t nq, const float* q_host, const int32_t* tok_indptr,
+                     const int32_t* term_rows) {
   if (!h) return RSE_ERR_INVALID;
-  if (nq < 0 || (nq > 0 && (!q_host || !tok_indptr || !out_id || !out_score || !out_a || !out_b || !out_count)))
-    return fail(h, RSE_ERR_INVALID, "rse_hybrid: bad arguments");
-  if (mode != 0 && mode != 1) return fail(h, RSE_ERR_INVALID, "rse_hybrid: mode must be 0 (rrf) or 1 (weighted)");
-  if (limit < 1 || limit > RSE_MAX_FUSE_LIMIT) return fail(h, RSE_ERR_UNSUPPORTED, "rse_hybrid: limit must be in [1, 128]");
+  if (nq < 0 || (nq > 0 && (!q_host || !tok_indptr))) return fail(h, RSE_ERR_INVALID, "rse_hybrid_stage: bad arguments");
   if (!h->emb || !h->movie_idx || !h->indptr || !h->doc_ids || !h->movie_ids)
     return fail(h, RSE_ERR_STATE, "rse_hybrid: needs embeddings (with movie_idx), a BM25 index and id tables");
+  h->staged_nq = 0;
   if (nq == 0) return RSE_OK;
+  if (tok_indptr[nq] > 0 && !term_rows) return fail(h, RSE_ERR_INVALID, "rse_hybrid_stage: term_rows is NULL");
+  CK(cudaSetDevice(h->device));
+  int rc = bm25_stage(h, tok_indptr, term_rows, nq);
+  if (rc != RSE_OK) return rc;
+  rc = upload_queries(h, q_host, nq);
+  if (rc != RSE_OK) return rc;
+  h->staged_nq = nq;
+  return RSE_OK;
+}
+
+namespace {
+
+// BM25 + (local KNN | merge of gathered shard candidates) + aggregation + fusion on the staged batch.
+// Outputs go to the given device buffers ([nq, limit]).
+int hybrid_run_impl(rse_index* h, int mode, double param, int tie_mode, int limit, int knn_multiplier, double k1,
+                    double b, const long long* gathered, int n_lists, long long* o_id, double* o_sc, double* o_a,
+                    double* o_b, int* o_cnt) {
+  const int nq = h->staged_nq;
+  if (nq <= 0) return fail(h, RSE_ERR_STATE, "rse_hybrid_run: nothing staged");
+  if (mode != 0 && mode != 1) return fail(h, RSE_ERR_INVALID, "rse_hybrid: mode must be 0 (rrf) or 1 (weighted)");
+  if (limit < 1 || limit > RSE_MAX_FUSE_LIMIT) return fail(h, RSE_ERR_UNSUPPORTED, "rse_hybrid: limit must be in [1, 128]");
+  if (knn_multiplier < 0) return fail(h, RSE_ERR_INVALID, "rse_hybrid: knn_multiplier < 0");
   CK(cudaSetDevice(h->device));
   const int kprime = std::max(limit * knn_multiplier, limit);   // semantic_search.py:251
   if (kprime > RSE_MAX_KPRIME) return fail(h, RSE_ERR_UNSUPPORTED, "rse_hybrid: limit*knn_multiplier exceeds 4096");
-  h->stats.last_knn_scan_ms = 0.0;
-
   // BM25 (k = limit, hybrid_search.py:70)
-  int rc = bm25_device(h, tok_indptr, term_rows, nq, limit, k1, b);
+  int rc = bm25_run(h, nq, limit, k1, b);
   if (rc != RSE_OK) return rc;
   // KNN + aggregation (k = limit, hybrid_search.py:88)
-  rc = upload_queries(h, q_host, nq);
-  if (rc != RSE_OK) return rc;
   const size_t n = static_cast<size_t>(nq) * limit;
   ENSURE(h->cand, sizeof(long long) * static_cast<size_t>(nq) * kprime * 3);
   ENSURE(h->o_dist, sizeof(float) * n);
   ENSURE(h->o_rowid, sizeof(long long) * n);
   ENSURE(h->o_movie, sizeof(int) * n);
   ENSURE(h->o_count, sizeof(int) * nq);
-  rc = knn_local(h, static_cast<const float*>(h->q_dev.p), nq, kprime, static_cast<long long*>(h->cand.p));
-  if (rc != RSE_OK) return rc;
+  if (gathered) {
+    const int n2 = next_pow2(n_lists * kprime);
+    const size_t smem = static_cast<size_t>(n2) * 12;
+    if (smem > 200 * 1024)
+      return fail(h, RSE_ERR_UNSUPPORTED, "rse_hybrid_run_merged_dev: n_lists*kprime too large for the merge kernel");
+    if (smem > 48 * 1024) CK(cudaFuncSetAttribute(knn_merge_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    knn_merge_kernel<<<nq, kSelThreads, smem, h->stream>>>(gathered, n_lists, nq, kprime, n2,
+                                                           static_cast<long long*>(h->cand.p));
+    LAUNCHED(h);
+  } else {
+    rc = knn_local(h, static_cast<const float*>(h->q_dev.p), nq, kprime, static_cast<long long*>(h->cand.p));
+    if (rc != RSE_OK) return rc;
+  }
   rc = aggregate(h, static_cast<const long long*>(h->cand.p), nq, limit, kprime, static_cast<float*>(h->o_dist.p),
                  static_cast<long long*>(h->o_rowid.p), static_cast<int*>(h->o_movie.p), static_cast<int*>(h->o_count.p));
   if (rc != RSE_OK) return rc;
   // dense index → movies.id
   ENSURE(h->f_bid, 8 * n); ENSURE(h->f_sid, 8 * n);
-  ENSURE(h->f_oid, 8 * n); ENSURE(h->f_osc, 8 * n); ENSURE(h->f_oa, 8 * n); ENSURE(h->f_ob, 8 * n);
-  ENSURE(h->f_ocnt, 4 * static_cast<size_t>(nq));
   const unsigned int gblocks = static_cast<unsigned int>((n + 255) / 256);
   gather_ids_kernel<<<gblocks, 256, 0, h->stream>>>(static_cast<const int*>(h->b_doc.p), static_cast<int64_t>(n),
                                                     h->doc_ids, h->n_doc_ids, static_cast<long long*>(h->f_bid.p));
@@ -860,10 +921,44 @@ int rse_hybrid(rse_index* h, int32_t mode, double param, int32_t tie_mode, int32
   FuseIn in{static_cast<const long long*>(h->f_bid.p), static_cast<const double*>(h->b_score.p),
             static_cast<const int*>(h->b_count.p),     static_cast<const long long*>(h->f_sid.p),
             static_cast<const float*>(h->o_dist.p),    static_cast<const int*>(h->o_count.p)};
-  rc = fuse_launch(h, mode, param, tie_mode, nq, limit, in, static_cast<long long*>(h->f_oid.p),
-                   static_cast<double*>(h->f_osc.p), static_cast<double*>(h->f_oa.p), static_cast<double*>(h->f_ob.p),
-                   static_cast<int*>(h->f_ocnt.p));
-  if (rc != RSE_OK) return rc;
+  return fuse_launch(h, mode, param, tie_mode, nq, limit, in, o_id, o_sc, o_a, o_b, o_cnt);
+}
+
+}  // namespace
+
+int rse_hybrid_run(rse_index* h, int32_t mode, double param, int32_t tie_mode, int32_t limit, int32_t knn_multiplier,
+                   double k1, double b) {
+  if (!h) return RSE_ERR_INVALID;
+  const int nq = h->staged_nq;
+  if (nq <= 0) return fail(h, RSE_ERR_STATE, "rse_hybrid_run: nothing staged");
+  if (limit < 1 || limit > RSE_MAX_FUSE_LIMIT) return fail(h, RSE_ERR_UNSUPPORTED, "rse_hybrid: limit must be in [1, 128]");
+  const size_t n = static_cast<size_t>(nq) * limit;
+  ENSURE(h->f_oid, 8 * n); ENSURE(h->f_osc, 8 * n); ENSURE(h->f_oa, 8 * n); ENSURE(h->f_ob, 8 * n);
+  ENSURE(h->f_ocnt, 4 * static_cast<size_t>(nq));
+  return hybrid_run_impl(h, mode, param, tie_mode, limit, knn_multiplier, k1, b, nullptr, 0,
+                         static_cast<long long*>(h->f_oid.p), static_cast<double*>(h->f_osc.p),
+                         static_cast<double*>(h->f_oa.p), static_cast<double*>(h->f_ob.p), static_cast<int*>(h->f_ocnt.p));
+}
+
+int rse_hybrid_run_merged_dev(rse_index* h, int32_t mode, double param, int32_t tie_mode, int32_t limit,
+                              int32_t knn_multiplier, double k1, double b, const int64_t* gathered_dev,
+                              int32_t n_lists, int64_t* out_id_dev, double* out_score_dev, double* out_a_dev,
+                              double* out_b_dev, int32_t* out_count_dev) {
+  if (!h) return RSE_ERR_INVALID;
+  if (!gathered_dev || n_lists < 1 || !out_id_dev || !out_score_dev || !out_a_dev || !out_b_dev || !out_count_dev)
+    return fail(h, RSE_ERR_INVALID, "rse_hybrid_run_merged_dev: bad arguments");
+  return hybrid_run_impl(h, mode, param, tie_mode, limit, knn_multiplier, k1, b,
+                         reinterpret_cast<const long long*>(gathered_dev), n_lists,
+                         reinterpret_cast<long long*>(out_id_dev), out_score_dev, out_a_dev, out_b_dev, out_count_dev);
+}
+
+int rse_hybrid_fetch(rse_index* h, int32_t limit, int64_t* out_id, double* out_score, double* out_a, double* out_b,
+                     int32_t* out_count) {
+  if (!h) return RSE_ERR_INVALID;
+  const int nq = h->staged_nq;
+  if (nq <= 0) return fail(h, RSE_ERR_STATE, "rse_hybrid_fetch: nothing staged");
+  if (!out_id || !out_score || !out_a || !out_b || !out_count) return fail(h, RSE_ERR_INVALID, "rse_hybrid_fetch: bad arguments");
+  const size_t n = static_cast<size_t>(nq) * limit;
   CK(cudaMemcpyAsync(out_id, h->f_oid.p, 8 * n, cudaMemcpyDeviceToHost, h->stream));
   CK(cudaMemcpyAsync(out_score, h->f_osc.p, 8 * n, cudaMemcpyDeviceToHost, h->stream));
   CK(cudaMemcpyAsync(out_a, h->f_oa.p, 8 * n, cudaMemcpyDeviceToHost, h->stream));
@@ -871,6 +966,20 @@ int rse_hybrid(rse_index* h, int32_t mode, double param, int32_t tie_mode, int32
   CK(cudaMemcpyAsync(out_count, h->f_ocnt.p, 4 * static_cast<size_t>(nq), cudaMemcpyDeviceToHost, h->stream));
   CK(cudaStreamSynchronize(h->stream));
   return RSE_OK;
+}
+
+int rse_hybrid(rse_index* h, int32_t mode, double param, int32_t tie_mode, int32_t limit, int32_t knn_multiplier,
+               int32_t nq, const float* q_host, const int32_t* tok_indptr, const int32_t* term_rows, double k1,
+               double b, int64_t* out_id, double* out_score, double* out_a, double* out_b, int32_t* out_count) {
+  if (!h) return RSE_ERR_INVALID;
+  if (nq < 0 || (nq > 0 && (!out_id || !out_score || !out_a || !out_b || !out_count)))
+    return fail(h, RSE_ERR_INVALID, "rse_hybrid: bad arguments");
+  if (nq == 0) return RSE_OK;
+  int rc = rse_hybrid_stage(h, nq, q_host, tok_indptr, term_rows);
+  if (rc != RSE_OK) return rc;
+  rc = rse_hybrid_run(h, mode, param, tie_mode, limit, knn_multiplier, k1, b);
+  if (rc != RSE_OK) return rc;
+  return rse_hybrid_fetch(h, limit, out_id, out_score, out_a, out_b, out_count);
 }
 
 }  // extern "C"

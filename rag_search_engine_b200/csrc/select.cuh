@@ -45,7 +45,7 @@ __global__ void select_init_kernel(SelState* st, int nq, unsigned int kprime) {
 // `need`-th smallest key and refines the state.  `hist` is [nq][kSelBins], zero on
 // entry and left zero on exit.
 __global__ void __launch_bounds__(kSelThreads)
-select_pass_kernel(const float* __restrict__ dist, int64_t ld, int64_t n_rows, uint64_t pos_base,
+select_pass_kernel(const uint32_t* __restrict__ dist, int64_t ld, int64_t n_rows, uint64_t pos_base,
                    SelState* __restrict__ st, unsigned int* __restrict__ hist, int shift, int bits) {
   const int q = blockIdx.y;
   __shared__ unsigned int h[kSelBins];
@@ -57,11 +57,12 @@ select_pass_kernel(const float* __restrict__ dist, int64_t ld, int64_t n_rows, u
   __syncthreads();
 
   const unsigned int dmask = (1u << bits) - 1u;
-  const float* d = dist + static_cast<int64_t>(q) * ld;
+  const uint32_t* d = dist + static_cast<int64_t>(q) * ld;   // raw f32 bits: integer-typed so the
+  // compiler cannot lower the sign-bit OR to a NaN-canonicalising FADD (it did)
   unsigned int run_digit = 0xFFFFFFFFu, run_cnt = 0u;
   for (int64_t row = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; row < n_rows;
        row += static_cast<int64_t>(gridDim.x) * blockDim.x) {
-    const uint32_t okey = f32_orderable(__float_as_uint(__ldcg(d + row)));
+    const uint32_t okey = f32_orderable(__ldcg(d + row));
     if (okey == kInvalidOKey) continue;
     const uint64_t key = knn_key(okey, pos_base + static_cast<uint64_t>(row));
     if ((key & s.mask) != s.prefix) continue;
@@ -139,14 +140,15 @@ select_pass_kernel(const float* __restrict__ dist, int64_t ld, int64_t n_rows, u
 
 // Gather the selected keys: everything whose resolved bits are <= the threshold prefix.
 __global__ void __launch_bounds__(kSelThreads)
-select_collect_kernel(const float* __restrict__ dist, int64_t ld, int64_t n_rows, uint64_t pos_base,
+select_collect_kernel(const uint32_t* __restrict__ dist, int64_t ld, int64_t n_rows, uint64_t pos_base,
                       SelState* __restrict__ st, unsigned long long* __restrict__ out_keys, int kprime) {
   const int q = blockIdx.y;
   const unsigned long long prefix = st[q].prefix, mask = st[q].mask;
-  const float* d = dist + static_cast<int64_t>(q) * ld;
+  const uint32_t* d = dist + static_cast<int64_t>(q) * ld;   // raw f32 bits: integer-typed so the
+  // compiler cannot lower the sign-bit OR to a NaN-canonicalising FADD (it did)
   for (int64_t row = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; row < n_rows;
        row += static_cast<int64_t>(gridDim.x) * blockDim.x) {
-    const uint32_t okey = f32_orderable(__float_as_uint(__ldcg(d + row)));
+    const uint32_t okey = f32_orderable(__ldcg(d + row));
     if (okey == kInvalidOKey) continue;
     const uint64_t key = knn_key(okey, pos_base + static_cast<uint64_t>(row));
     if ((key & mask) <= prefix) {

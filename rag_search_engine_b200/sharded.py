@@ -1,0 +1,164 @@
+"""Row-sharded hybrid search over the GPUs of one box.
+
+One process per GPU (``torch.distributed``; NCCL over NVLink on the B200 box, gloo in the
+CPU tests).  The chunk-embedding matrix is cut by row into contiguous shards aligned to
+1024-row vec0 blocks, so the emit-order key (distance, block asc, slot desc) is computable
+from the global row alone.  Per step:
+
+  1. every rank scans ITS shard for ALL queries of the batch → local top-K' candidates
+     packed as int64 triples {key, rowid, movie_idx} (``rse_knn_local_dev``);
+  2. ONE ``all_gather`` of nq·K'·24 B per rank — the path's only real exchange step;
+  3. each rank owns a contiguous slice of the query batch: it merges the gathered lists of
+     its slice under the same key, aggregates per movie AFTER the merge (the reference
+     aggregates over the global top-K', semantic_search.py:285-317), runs BM25 for the
+     slice on its replica of the postings and fuses (``rse_hybrid_run_merged_dev``);
+  4. the fused [slice, limit] results are all-gathered so every rank holds the batch.
+
+The compute is behind a tiny backend protocol so the plumbing (shard bounds, query
+slices, gather layout, result assembly) is testable on CPU with gloo; the product
+backend is librse on the rank's GPU — there is no CPU compute path in this package.
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass
+from typing import Protocol, Tuple
+
+import torch
+import torch.distributed as dist
+
+VEC0_BLOCK = 1024
+
+
+def shard_bounds(n_rows: int, world: int) -> list[int]:
+    """Contiguous row ranges aligned to vec0 blocks: bounds[r] .. bounds[r+1]."""
+    n_blocks = (n_rows + VEC0_BLOCK - 1) // VEC0_BLOCK
+    per, rem = divmod(n_blocks, world)
+    bounds = [0]
+    for r in range(world):
+        nb = per + (1 if r < rem else 0)
+        bounds.append(min(n_rows, bounds[-1] + nb * VEC0_BLOCK))
+    bounds[-1] = n_rows
+    return bounds
+
+
+def query_slices(nq: int, world: int) -> list[int]:
+    per, rem = divmod(nq, world)
+    out = [0]
+    for r in range(world):
+        out.append(out[-1] + per + (1 if r < rem else 0))
+    return out
+
+
+class ShardBackend(Protocol):
+    device: torch.device
+
+    def knn_local(self, q_all: torch.Tensor, kprime: int) -> torch.Tensor:
+        """[nq, dim] → packed candidates [nq, kprime, 3] int64 on ``device``."""
+
+    def stage_slice(self, lo: int, hi: int) -> None:
+        """Make queries lo..hi (tokens) the staged batch."""
+
+    def fuse_merged(self, gathered_slice: torch.Tensor, mode: int, param: float, limit: int,
+                    knn_multiplier: int) -> Tuple[torch.Tensor, ...]:
+        """[world, nslice, kprime, 3] → (id i64, score f64, a f64, b f64 [nslice, limit], count i32 [nslice])."""
+
+
+@dataclass
+class HybridBatchResult:
+    ids: torch.Tensor      # [nq, limit] int64
+    score: torch.Tensor    # [nq, limit] float64
+    a: torch.Tensor        # rrf: bm25_rank (-1 = None) / weighted: bm25_norm
+    b: torch.Tensor        # rrf: sem_rank / weighted: sem_norm
+    count: torch.Tensor    # [nq] int32
+
+
+class ShardedHybrid:
+    """The multi-GPU hybrid step.  ``group`` is a torch.distributed process group (None = default)."""
+
+    def __init__(self, backend: ShardBackend, nq: int, group=None):
+        self.backend = backend
+        self.group = group
+        self.world = dist.get_world_size(group) if dist.is_initialized() else 1
+        self.rank = dist.get_rank(group) if dist.is_initialized() else 0
+        self.nq = nq
+        self.slices = query_slices(nq, self.world)
+        self.lo, self.hi = self.slices[self.rank], self.slices[self.rank + 1]
+        self.max_slice = max(self.slices[r + 1] - self.slices[r] for r in range(self.world))
+        backend.stage_slice(self.lo, self.hi)
+
+    def step(self, q_all: torch.Tensor, mode: int, param: float, limit: int, knn_multiplier: int = 10) -> HybridBatchResult:
+        kprime = max(limit * knn_multiplier, limit)
+        dev = self.backend.device
+        cand = self.backend.knn_local(q_all, kprime)                                   # [nq, kp, 3]
+        if self.world > 1:
+            gathered = torch.empty((self.world,) + tuple(cand.shape), dtype=cand.dtype, device=dev)
+            dist.all_gather_into_tensor(gathered, cand, group=self.group)              # the exchange step
+        else:
+            gathered = cand.unsqueeze(0)
+        ns = self.hi - self.lo
+        pad = self.max_slice
+        out_id = torch.full((pad, limit), -1, dtype=torch.int64, device=dev)
+        out_sc = torch.zeros((pad, limit), dtype=torch.float64, device=dev)
+        out_a = torch.full((pad, limit), -1.0, dtype=torch.float64, device=dev)
+        out_b = torch.full((pad, limit), -1.0, dtype=torch.float64, device=dev)
+        out_c = torch.zeros((pad,), dtype=torch.int32, device=dev)
+        if ns > 0:
+            mine = gathered[:, self.lo:self.hi].contiguous()
+            i, s, a, b, c = self.backend.fuse_merged(mine, mode, param, limit, knn_multiplier)
+            out_id[:ns], out_sc[:ns], out_a[:ns], out_b[:ns], out_c[:ns] = i, s, a, b, c
+        if self.world == 1:
+            return HybridBatchResult(out_id[:ns], out_sc[:ns], out_a[:ns], out_b[:ns], out_c[:ns])
+        # assemble the batch on every rank (small: nq·limit·32 B)
+        packed = torch.cat([out_id.view(torch.float64), out_sc, out_a, out_b], dim=1)  # [pad, 4*limit] f64 bits
+        allp = torch.empty((self.world,) + tuple(packed.shape), dtype=packed.dtype, device=dev)
+        allc = torch.empty((self.world, pad), dtype=torch.int32, device=dev)
+        dist.all_gather_into_tensor(allp, packed, group=self.group)
+        dist.all_gather_into_tensor(allc, out_c, group=self.group)
+        rows = [allp[r, : self.slices[r + 1] - self.slices[r]] for r in range(self.world)]
+        cnts = [allc[r, : self.slices[r + 1] - self.slices[r]] for r in range(self.world)]
+        full = torch.cat(rows, 0)
+        L = limit
+        return HybridBatchResult(full[:, :L].contiguous().view(torch.int64), full[:, L:2 * L], full[:, 2 * L:3 * L],
+                                 full[:, 3 * L:4 * L], torch.cat(cnts, 0))
+
+
+class LibrseShardBackend:
+    """Product backend: this rank's librse handle on its GPU, sharing torch's current stream."""
+
+    def __init__(self, index, q_host, tok_indptr, term_rows, device: torch.device, k1: float = 1.5, b: float = 0.75,
+                 tie_mode: int = 0):
+        import numpy as np
+        self.index = index
+        self.device = device
+        self.q_host = np.ascontiguousarray(q_host, np.float32)
+        self.tok_indptr = np.ascontiguousarray(tok_indptr, np.int32)
+        self.term_rows = np.ascontiguousarray(term_rows, np.int32)
+        self.k1, self.b, self.tie_mode = k1, b, tie_mode
+        index.set_stream(torch.cuda.current_stream(device).cuda_stream)
+
+    def knn_local(self, q_all: torch.Tensor, kprime: int) -> torch.Tensor:
+        nq = q_all.shape[0]
+        cand = torch.empty((nq, kprime, 3), dtype=torch.int64, device=self.device)
+        self.index.knn_local_dev(q_all.data_ptr(), nq, kprime, cand.data_ptr())
+        return cand
+
+    def stage_slice(self, lo: int, hi: int) -> None:
+        import numpy as np
+        if hi <= lo:
+            return
+        t0, t1 = int(self.tok_indptr[lo]), int(self.tok_indptr[hi])
+        ptr = (self.tok_indptr[lo:hi + 1] - t0).astype(np.int32)
+        self.index.hybrid_stage(self.q_host[lo:hi], ptr, self.term_rows[t0:t1])
+
+    def fuse_merged(self, gathered_slice, mode, param, limit, knn_multiplier):
+        ns = gathered_slice.shape[1]
+        dev = self.device
+        oid = torch.empty((ns, limit), dtype=torch.int64, device=dev)
+        osc = torch.empty((ns, limit), dtype=torch.float64, device=dev)
+        oa = torch.empty((ns, limit), dtype=torch.float64, device=dev)
+        ob = torch.empty((ns, limit), dtype=torch.float64, device=dev)
+        oc = torch.empty((ns,), dtype=torch.int32, device=dev)
+        self.index.hybrid_run_merged_dev(mode, param, limit, gathered_slice.data_ptr(), gathered_slice.shape[0],
+                                         oid.data_ptr(), osc.data_ptr(), oa.data_ptr(), ob.data_ptr(), oc.data_ptr(),
+                                         knn_multiplier=knn_multiplier, k1=self.k1, b=self.b, tie_mode=self.tie_mode)
+        return oid, osc, oa, ob, oc
