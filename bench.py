@@ -299,6 +299,22 @@ def run_b200(args, rank, world, local_rank):
         e2e = {"value": nq * args.steps / wall, "unit": "queries/s", "h2d_bytes_per_step": int(Qn.nbytes),
                "d2h_bytes_per_step": int(nq * limit * 16 + nq * 4), "wall_ms_per_step": 1e3 * wall / args.steps}
 
+    # ---- batch-1 KNN (north_star: batch-1 kNN as a fraction of HBM peak): scan<QB=1> alone + whole call
+    knn1 = None
+    if world == 1:
+        kp = max(limit * 10, limit)
+        for _ in range(3):
+            idx.knn_movies(Qn[:1], limit, kp)
+        idx.set_timing(True); idx.stats_reset()
+        reps = 20
+        t0 = time.perf_counter()
+        for i in range(reps):
+            idx.knn_movies(Qn[i % nq: i % nq + 1], limit, kp)
+        wall1 = (time.perf_counter() - t0) / reps
+        s1 = idx.stats(); idx.set_timing(False)
+        sm1 = s1.scan_ms_total / max(1, s1.scan_launches_timed)
+        knn1 = {"scan_ms": sm1, "call_ms_host_buffers": 1e3 * wall1, "launches_per_query": s1.kernel_launches / reps}
+
     if rank != 0:
         return
     peaks = {}
@@ -315,11 +331,14 @@ def run_b200(args, rank, world, local_rank):
                 "traffic": None, "algorithmic_bytes_per_launch": alg_bytes, "avg_launch_ms": scan_ms,
                 "scan_launches": int(st.scan_launches_timed), "scan_share_of_step": scan_share}
 
+    if knn1:
+        g1 = alg_bytes / (knn1["scan_ms"] * 1e-3) / 1e9
+        knn1.update(achieved_gbs=g1, frac_of_measured_peak=g1 / peak, queries_per_s=1e3 / knn1["call_ms_host_buffers"])
     line = {"metric": "hybrid queries/sec", "value": value, "unit": "queries/s", "n_gpus": world, "steps": args.steps,
             "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps, "higher_is_better": True,
             "scaling": "strong", "vs_baseline": None, "dtype": "f32 scan + f64 tail/BM25/fusion", "data": "synthetic",
             "config": config_dict(args, info, world), "roofline": roofline, "clocks": clocks, "e2e": e2e,
-            "gpu_launches": launches, "postings_touched_per_step": postings_touched(bm, tok_indptr, terms)}
+            "gpu_launches": launches, "knn_batch1": knn1, "postings_touched_per_step": postings_touched(bm, tok_indptr, terms)}
 
     if world == 1 and not args.no_cpu_baseline:
         cores = os.cpu_count() or 1

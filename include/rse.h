@@ -61,9 +61,11 @@ int rse_create(int32_t device, rse_index **out);
 void rse_destroy(rse_index *h);
 const char *rse_last_error(const rse_index *h);
 
-/* Use an externally owned CUDA stream (cudaStream_t as void*), e.g. torch's
- * current stream; NULL restores the handle's own stream. */
+/* Use an externally owned CUDA stream (cudaStream_t as void*), e.g. torch's current
+ * stream.  NULL is the legacy default stream (what torch uses by default), NOT "unset";
+ * rse_use_own_stream goes back to the handle's private non-blocking stream. */
 int rse_set_stream(rse_index *h, void *cuda_stream);
+int rse_use_own_stream(rse_index *h);
 /* Block until everything enqueued on the handle's stream has finished. */
 int rse_synchronize(rse_index *h);
 
@@ -142,19 +144,21 @@ int rse_bm25(rse_index *h, const int32_t *tok_indptr, const int32_t *term_rows, 
 /* ------------------------------------------------------------------ a8-a10: fusion
  * ids are the caller's document ids (movies.id).  Inputs [nq, limit] with
  * per-query counts; BM25 lists are score-descending, semantic lists
- * distance-ascending (what the retrievers return).  Outputs [nq, limit].
+ * distance-ascending (what the retrievers return).  Distances are doubles: the
+ * reference does float(hit["distance"]) on whatever the plugged-in retriever
+ * returns (hybrid_search.py:134); vec0 distances are f32 values widened.  Outputs [nq, limit].
  * weighted: hybrid_search.py:117-180 (min_max_norm utils.py:182-191,
  *           alpha*b + (1-alpha)*s :163).
  * rrf:      hybrid_search.py:217-272,379 (0-based ranks, NOT_FOUND=99999 :247,
  *           1/(k+r_b) + 1/(k+r_s) :255); out ranks are -1 for None. */
 int rse_fuse_weighted(rse_index *h, int32_t nq, int32_t limit, double alpha, int32_t tie_mode,
                       const int64_t *bm25_id, const double *bm25_score, const int32_t *bm25_count,
-                      const int64_t *sem_id, const float *sem_dist, const int32_t *sem_count,
+                      const int64_t *sem_id, const double *sem_dist, const int32_t *sem_count,
                       int64_t *out_id, double *out_bm25, double *out_sem, double *out_score,
                       int32_t *out_count);
 int rse_fuse_rrf(rse_index *h, int32_t nq, int32_t limit, double k, int32_t tie_mode,
                  const int64_t *bm25_id, const double *bm25_score, const int32_t *bm25_count,
-                 const int64_t *sem_id, const float *sem_dist, const int32_t *sem_count,
+                 const int64_t *sem_id, const double *sem_dist, const int32_t *sem_count,
                  int64_t *out_id, double *out_score, int32_t *out_bm25_rank, int32_t *out_sem_rank,
                  int32_t *out_count);
 

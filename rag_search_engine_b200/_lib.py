@@ -52,6 +52,7 @@ _SIGNATURES = {
     "rse_destroy": (None, [c_void_p]),
     "rse_last_error": (c_char_p, [c_void_p]),
     "rse_set_stream": (ctypes.c_int, [c_void_p, c_void_p]),
+    "rse_use_own_stream": (ctypes.c_int, [c_void_p]),
     "rse_synchronize": (ctypes.c_int, [c_void_p]),
     "rse_load_embeddings": (ctypes.c_int, [c_void_p, POINTER(c_float), c_int64, c_int32, POINTER(c_uint8),
                                            POINTER(c_int64), POINTER(c_int32), c_int64]),
@@ -71,11 +72,11 @@ _SIGNATURES = {
     "rse_bm25": (ctypes.c_int, [c_void_p, POINTER(c_int32), POINTER(c_int32), c_int32, c_int32, c_double, c_double,
                                 POINTER(c_double), POINTER(c_int32), POINTER(c_int32)]),
     "rse_fuse_weighted": (ctypes.c_int, [c_void_p, c_int32, c_int32, c_double, c_int32, POINTER(c_int64),
-                                         POINTER(c_double), POINTER(c_int32), POINTER(c_int64), POINTER(c_float),
+                                         POINTER(c_double), POINTER(c_int32), POINTER(c_int64), POINTER(c_double),
                                          POINTER(c_int32), POINTER(c_int64), POINTER(c_double), POINTER(c_double),
                                          POINTER(c_double), POINTER(c_int32)]),
     "rse_fuse_rrf": (ctypes.c_int, [c_void_p, c_int32, c_int32, c_double, c_int32, POINTER(c_int64),
-                                    POINTER(c_double), POINTER(c_int32), POINTER(c_int64), POINTER(c_float),
+                                    POINTER(c_double), POINTER(c_int32), POINTER(c_int64), POINTER(c_double),
                                     POINTER(c_int32), POINTER(c_int64), POINTER(c_double), POINTER(c_int32),
                                     POINTER(c_int32), POINTER(c_int32)]),
     "rse_set_id_tables": (ctypes.c_int, [c_void_p, POINTER(c_int64), c_int64, POINTER(c_int64), c_int64]),
@@ -157,8 +158,12 @@ class Index:
         except Exception:
             pass
 
-    def set_stream(self, cuda_stream_ptr: int | None):
-        self._check(self._L.rse_set_stream(self._h, c_void_p(cuda_stream_ptr or 0)))
+    def set_stream(self, cuda_stream_ptr: int):
+        """cuda_stream_ptr = cudaStream_t as int; 0 is the legacy default stream (torch's default)."""
+        self._check(self._L.rse_set_stream(self._h, c_void_p(int(cuda_stream_ptr))))
+
+    def use_own_stream(self):
+        self._check(self._L.rse_use_own_stream(self._h))
 
     def synchronize(self):
         self._check(self._L.rse_synchronize(self._h))
@@ -262,7 +267,7 @@ class Index:
         bm25_id = _c(bm25_id, np.int64).reshape(-1, limit)
         nq = bm25_id.shape[0]
         return (nq, bm25_id, _c(bm25_score, np.float64).reshape(nq, limit), _c(bm25_count, np.int32).reshape(nq),
-                _c(sem_id, np.int64).reshape(nq, limit), _c(sem_dist, np.float32).reshape(nq, limit),
+                _c(sem_id, np.int64).reshape(nq, limit), _c(sem_dist, np.float64).reshape(nq, limit),
                 _c(sem_count, np.int32).reshape(nq))
 
     def fuse_weighted(self, limit, alpha, bm25_id, bm25_score, bm25_count, sem_id, sem_dist, sem_count,
@@ -276,7 +281,7 @@ class Index:
         oc = np.zeros(nq, np.int32)
         self._check(self._L.rse_fuse_weighted(self._h, nq, int(limit), float(alpha), int(tie_mode),
                                               _ptr(bid, c_int64), _ptr(bsc, c_double), _ptr(bc, c_int32),
-                                              _ptr(sid, c_int64), _ptr(sds, c_float), _ptr(scn, c_int32),
+                                              _ptr(sid, c_int64), _ptr(sds, c_double), _ptr(scn, c_int32),
                                               _ptr(oid, c_int64), _ptr(ob, c_double), _ptr(osem, c_double),
                                               _ptr(osc, c_double), _ptr(oc, c_int32)))
         return oid, ob, osem, osc, oc
@@ -292,7 +297,7 @@ class Index:
         oc = np.zeros(nq, np.int32)
         self._check(self._L.rse_fuse_rrf(self._h, nq, int(limit), float(k), int(tie_mode), _ptr(bid, c_int64),
                                          _ptr(bsc, c_double), _ptr(bc, c_int32), _ptr(sid, c_int64),
-                                         _ptr(sds, c_float), _ptr(scn, c_int32), _ptr(oid, c_int64),
+                                         _ptr(sds, c_double), _ptr(scn, c_int32), _ptr(oid, c_int64),
                                          _ptr(osc, c_double), _ptr(orb, c_int32), _ptr(ors, c_int32),
                                          _ptr(oc, c_int32)))
         return oid, osc, orb, ors, oc

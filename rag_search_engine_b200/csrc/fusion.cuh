@@ -30,6 +30,7 @@ __host__ __device__ inline size_t fuse_smem_bytes(int limit) {
 struct FuseIn {
   const long long* bm25_id; const double* bm25_score; const int* bm25_count;   // [nq][limit]
   const long long* sem_id; const float* sem_dist; const int* sem_count;         // [nq][limit]
+  const double* sem_dist64;   // when non-NULL used instead of sem_dist (Python floats from a plugged-in retriever)
 };
 
 // mode 0 = rrf (param = k), mode 1 = weighted (param = alpha)
@@ -57,7 +58,9 @@ fuse_kernel(FuseIn in, int nq, int limit, int mode, double param, int tie_mode, 
   const long long* bid = in.bm25_id + static_cast<int64_t>(q) * limit;
   const double* bsc = in.bm25_score + static_cast<int64_t>(q) * limit;
   const long long* sid = in.sem_id + static_cast<int64_t>(q) * limit;
-  const float* sds = in.sem_dist + static_cast<int64_t>(q) * limit;
+  const float* sds32 = in.sem_dist ? in.sem_dist + static_cast<int64_t>(q) * limit : nullptr;
+  const double* sds64 = in.sem_dist64 ? in.sem_dist64 + static_cast<int64_t>(q) * limit : nullptr;
+  auto sem_d = [&](int i) -> double { return sds64 ? sds64[i] : static_cast<double>(sds32[i]); };   // float(hit["distance"])
   int nb = in.bm25_count[q]; if (nb > limit) nb = limit; if (nb < 0) nb = 0;
   int ns = in.sem_count[q];  if (ns > limit) ns = limit; if (ns < 0) ns = 0;
 
@@ -96,8 +99,8 @@ fuse_kernel(FuseIn in, int nq, int limit, int mode, double param, int tie_mode, 
   if (mode == 1) {
     if (nb > 0) { bmin = bmax = bsc[0]; for (int i = 1; i < nb; ++i) { double v = bsc[i]; if (v < bmin) bmin = v; if (v > bmax) bmax = v; } }
     if (ns > 0) {
-      smin = smax = __dsub_rn(1.0, static_cast<double>(sds[0]));
-      for (int i = 1; i < ns; ++i) { double v = __dsub_rn(1.0, static_cast<double>(sds[i])); if (v < smin) smin = v; if (v > smax) smax = v; }
+      smin = smax = __dsub_rn(1.0, sem_d(0));
+      for (int i = 1; i < ns; ++i) { double v = __dsub_rn(1.0, sem_d(i)); if (v < smin) smin = v; if (v > smax) smax = v; }
     }
   }
 
@@ -118,7 +121,7 @@ fuse_kernel(FuseIn in, int nq, int limit, int mode, double param, int tie_mode, 
       a = 0.0; b = 0.0;                                          // :160-161 missing side → 0.0
       if (rb >= 0) a = (bmin == bmax) ? 1.0 : __ddiv_rn(__dsub_rn(bsc[rb], bmin), __dsub_rn(bmax, bmin));
       if (rs >= 0) {
-        const double sim = __dsub_rn(1.0, static_cast<double>(sds[rs]));                     // :134
+        const double sim = __dsub_rn(1.0, sem_d(rs));                     // :134
         b = (smin == smax) ? 1.0 : __ddiv_rn(__dsub_rn(sim, smin), __dsub_rn(smax, smin));
       }
       s = __dadd_rn(__dmul_rn(param, a), __dmul_rn(__dsub_rn(1.0, param), b));               // :163

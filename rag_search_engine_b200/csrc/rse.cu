@@ -364,7 +364,14 @@ void rse_destroy(rse_index* h) {
 int rse_set_stream(rse_index* h, void* s) {
   if (!h) return RSE_ERR_INVALID;
   CK(cudaStreamSynchronize(h->stream));
-  h->stream = s ? static_cast<cudaStream_t>(s) : h->own_stream;
+  h->stream = static_cast<cudaStream_t>(s);   // 0 is a real stream: the legacy default stream (torch's default)
+  return RSE_OK;
+}
+
+int rse_use_own_stream(rse_index* h) {
+  if (!h) return RSE_ERR_INVALID;
+  CK(cudaStreamSynchronize(h->stream));
+  h->stream = h->own_stream;
   return RSE_OK;
 }
 
@@ -761,7 +768,7 @@ int fuse_launch(rse_index* h, int mode, double param, int tie_mode, int nq, int 
 }
 
 int fuse_host(rse_index* h, int mode, double param, int tie_mode, int nq, int limit, const int64_t* bm25_id,
-              const double* bm25_score, const int32_t* bm25_count, const int64_t* sem_id, const float* sem_dist,
+              const double* bm25_score, const int32_t* bm25_count, const int64_t* sem_id, const double* sem_dist,
               const int32_t* sem_count, int64_t* out_id, double* out_score, double* out_a, double* out_b,
               int32_t* out_count) {
   if (nq < 0 || (nq > 0 && (!bm25_id || !bm25_score || !bm25_count || !sem_id || !sem_dist || !sem_count || !out_id ||
@@ -772,7 +779,7 @@ int fuse_host(rse_index* h, int mode, double param, int tie_mode, int nq, int li
   CK(cudaSetDevice(h->device));
   const size_t n = static_cast<size_t>(nq) * limit;
   ENSURE(h->f_bid, 8 * n); ENSURE(h->f_bsc, 8 * n); ENSURE(h->f_bcnt, 4 * static_cast<size_t>(nq));
-  ENSURE(h->f_sid, 8 * n); ENSURE(h->f_sds, 4 * n); ENSURE(h->f_scnt, 4 * static_cast<size_t>(nq));
+  ENSURE(h->f_sid, 8 * n); ENSURE(h->f_sds, 8 * n); ENSURE(h->f_scnt, 4 * static_cast<size_t>(nq));
   ENSURE(h->f_oid, 8 * n); ENSURE(h->f_osc, 8 * n); ENSURE(h->f_oa, 8 * n); ENSURE(h->f_ob, 8 * n);
   ENSURE(h->f_ocnt, 4 * static_cast<size_t>(nq));
   if (h->timing) CK(cudaEventRecord(h->ev[2], h->stream));
@@ -780,11 +787,12 @@ int fuse_host(rse_index* h, int mode, double param, int tie_mode, int nq, int li
   CK(cudaMemcpyAsync(h->f_bsc.p, bm25_score, 8 * n, cudaMemcpyHostToDevice, h->stream));
   CK(cudaMemcpyAsync(h->f_bcnt.p, bm25_count, 4 * static_cast<size_t>(nq), cudaMemcpyHostToDevice, h->stream));
   CK(cudaMemcpyAsync(h->f_sid.p, sem_id, 8 * n, cudaMemcpyHostToDevice, h->stream));
-  CK(cudaMemcpyAsync(h->f_sds.p, sem_dist, 4 * n, cudaMemcpyHostToDevice, h->stream));
+  CK(cudaMemcpyAsync(h->f_sds.p, sem_dist, 8 * n, cudaMemcpyHostToDevice, h->stream));
   CK(cudaMemcpyAsync(h->f_scnt.p, sem_count, 4 * static_cast<size_t>(nq), cudaMemcpyHostToDevice, h->stream));
   FuseIn in{static_cast<const long long*>(h->f_bid.p), static_cast<const double*>(h->f_bsc.p),
             static_cast<const int*>(h->f_bcnt.p),      static_cast<const long long*>(h->f_sid.p),
-            static_cast<const float*>(h->f_sds.p),     static_cast<const int*>(h->f_scnt.p)};
+            nullptr,                                   static_cast<const int*>(h->f_scnt.p),
+            static_cast<const double*>(h->f_sds.p)};
   int rc = fuse_launch(h, mode, param, tie_mode, nq, limit, in, static_cast<long long*>(h->f_oid.p),
                        static_cast<double*>(h->f_osc.p), static_cast<double*>(h->f_oa.p),
                        static_cast<double*>(h->f_ob.p), static_cast<int*>(h->f_ocnt.p));
@@ -807,7 +815,7 @@ int fuse_host(rse_index* h, int mode, double param, int tie_mode, int nq, int li
 }  // namespace
 
 int rse_fuse_weighted(rse_index* h, int32_t nq, int32_t limit, double alpha, int32_t tie_mode, const int64_t* bm25_id,
-                      const double* bm25_score, const int32_t* bm25_count, const int64_t* sem_id, const float* sem_dist,
+                      const double* bm25_score, const int32_t* bm25_count, const int64_t* sem_id, const double* sem_dist,
                       const int32_t* sem_count, int64_t* out_id, double* out_bm25, double* out_sem, double* out_score,
                       int32_t* out_count) {
   if (!h) return RSE_ERR_INVALID;
@@ -816,7 +824,7 @@ int rse_fuse_weighted(rse_index* h, int32_t nq, int32_t limit, double alpha, int
 }
 
 int rse_fuse_rrf(rse_index* h, int32_t nq, int32_t limit, double k, int32_t tie_mode, const int64_t* bm25_id,
-                 const double* bm25_score, const int32_t* bm25_count, const int64_t* sem_id, const float* sem_dist,
+                 const double* bm25_score, const int32_t* bm25_count, const int64_t* sem_id, const double* sem_dist,
                  const int32_t* sem_count, int64_t* out_id, double* out_score, int32_t* out_bm25_rank,
                  int32_t* out_sem_rank, int32_t* out_count) {
   if (!h) return RSE_ERR_INVALID;
@@ -920,7 +928,7 @@ int hybrid_run_impl(rse_index* h, int mode, double param, int tie_mode, int limi
   LAUNCHED(h);
   FuseIn in{static_cast<const long long*>(h->f_bid.p), static_cast<const double*>(h->b_score.p),
             static_cast<const int*>(h->b_count.p),     static_cast<const long long*>(h->f_sid.p),
-            static_cast<const float*>(h->o_dist.p),    static_cast<const int*>(h->o_count.p)};
+            static_cast<const float*>(h->o_dist.p),    static_cast<const int*>(h->o_count.p), nullptr};
   return fuse_launch(h, mode, param, tie_mode, nq, limit, in, o_id, o_sc, o_a, o_b, o_cnt);
 }
 

@@ -233,12 +233,12 @@ def _run_fusion_cases(idx, cases):
     for (limit, alpha_hex, _), cs in by_limit.items():
         nq = len(cs)
         bid = np.full((nq, limit), -1, np.int64); bsc = np.zeros((nq, limit)); bc = np.zeros(nq, np.int32)
-        sid = np.full((nq, limit), -1, np.int64); sds = np.zeros((nq, limit), np.float32); scn = np.zeros(nq, np.int32)
+        sid = np.full((nq, limit), -1, np.int64); sds = np.zeros((nq, limit), np.float64); scn = np.zeros(nq, np.int32)
         for i, c in enumerate(cs):
             for j, (d, s) in enumerate(c["bm25"]):
                 bid[i, j] = d; bsc[i, j] = float.fromhex(s)
             for j, (d, s) in enumerate(c["sem"]):
-                sid[i, j] = d; sds[i, j] = np.float32(float.fromhex(s))
+                sid[i, j] = d; sds[i, j] = float.fromhex(s)
             bc[i] = len(c["bm25"]); scn[i] = len(c["sem"])
         alpha = float.fromhex(alpha_hex)
         oid, ob, osem, osc, oc = idx.fuse_weighted(limit, alpha, bid, bsc, bc, sid, sds, scn)
@@ -286,7 +286,7 @@ def test_fusion_random_against_pyref_incl_max_limit(fresh_index):
 def test_fusion_tie_by_id_mode(fresh_index):
     from rag_search_engine_b200 import _lib
     bid = np.array([[912345, 17]], np.int64); bsc = np.array([[9.5, 7.25]]); bc = np.array([2], np.int32)
-    sid = np.array([[5, 700000]], np.int64); sds = np.array([[0.2, 0.3]], np.float32); scn = np.array([2], np.int32)
+    sid = np.array([[5, 700000]], np.int64); sds = np.array([[0.2, 0.3]], np.float64); scn = np.array([2], np.int32)
     rid, rsc, rb, rs, rc = fresh_index.fuse_rrf(2, 60, bid, bsc, bc, sid, sds, scn, tie_mode=_lib.TIE_BY_ID)
     assert rid[0].tolist() == [5, 912345]            # rank-0 tie resolved by ascending id
     rid, *_ = fresh_index.fuse_rrf(2, 60, bid, bsc, bc, sid, sds, scn, tie_mode=_lib.TIE_REFERENCE)
