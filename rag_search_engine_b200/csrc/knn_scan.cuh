@@ -22,9 +22,18 @@
 //     last LDS retired, so the other three stages are in flight while it does
 //     the 384-step dependent add chain — ≥100 KB in flight per SM, well above
 //     the ~35 KB latency×bandwidth product per SM;
-//   * up to QB=8 queries share one pass over the corpus (query vectors in
+//   * up to QB=16 queries share one pass over the corpus (query vectors in
 //     shared memory, read as broadcast LDS.128), which is what the hybrid batch
-//     path uses: FP32 issue, not HBM, becomes the limit only above QB≈4.
+//     path uses.  For QB >= 2 the arithmetic is PACKED: two queries per
+//     instruction with Blackwell's f32x2 FMA pipe (FFMA2).  ptxas contracts
+//     mul.rn.f32x2 + add.rn.f32x2 into one FFMA2 even under --fmad=false, which
+//     would change the reference's unfused rounding, so the unfused step is
+//     written as p = fma2(a, b, -0.0); acc = fma2(p, 1.0, acc) with -0.0 / 1.0
+//     passed as kernel arguments (unknown to ptxas, held in uniform registers):
+//     each fma2 then rounds exactly once on an exact product / sum, i.e.
+//     rn(a*b) and rn(p+acc) — bit-identical to FMUL + FADD at half the
+//     FMA-pipe cycles (r01 ncu: the scalar QB=8 kernel sat at 88 % of the
+//     3-register FMA-pipe rate).
 #pragma once
 #include "common.cuh"
 
@@ -35,7 +44,7 @@ constexpr int kScanRowStride = 388;                     // floats: 1552 B ≡ 16
 constexpr int kScanTileRows = 32;
 constexpr int kScanWarps = 4;
 constexpr int kScanStageBytes = kScanTileRows * kScanRowStride * 4;   // 49,664
-constexpr int kScanMaxQB = 8;
+constexpr int kScanMaxQB = 16;
 
 __host__ __device__ constexpr int scan_smem_bytes(int qb) {
   return kScanWarps * kScanStageBytes + qb * kScanD * 4 + kScanWarps * 8 + 16;
@@ -77,6 +86,24 @@ template <bool FMA>
 __device__ __forceinline__ float mac(float acc, float a, float b) {
   if (FMA) return __fmaf_rn(a, b, acc);
   return __fadd_rn(acc, __fmul_rn(a, b));   // never contracted
+}
+
+// ---- packed (two queries per instruction) arithmetic
+__device__ __forceinline__ unsigned long long fma2(unsigned long long a, unsigned long long b, unsigned long long c) {
+  unsigned long long r;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c));
+  return r;
+}
+__device__ __forceinline__ unsigned long long dup2(float a) {
+  unsigned long long r;
+  asm("mov.b64 %0, {%1, %1};" : "=l"(r) : "f"(a));
+  return r;
+}
+template <bool FMA>
+__device__ __forceinline__ unsigned long long mac2(unsigned long long acc, unsigned long long a2, unsigned long long b2,
+                                                   unsigned long long negz2, unsigned long long one2) {
+  if (FMA) return fma2(a2, b2, acc);
+  return fma2(fma2(a2, b2, negz2), one2, acc);   // rn(rn(a*b) + acc): the unfused reference step, never contracted
 }
 
 // vec0 tail: 1 - dot / (sqrt((double)aMag) * sqrt((double)bMag)), narrowed to f32.
@@ -126,7 +153,7 @@ template <int QB, bool FMA>
 __global__ void __launch_bounds__(kScanWarps * 32, 1)
 knn_scan384_kernel(const float* __restrict__ emb, const float* __restrict__ amag, int64_t n_rows,
                    const float* __restrict__ q, const double* __restrict__ sb, int nq,
-                   float* __restrict__ dist, int64_t ld) {
+                   float* __restrict__ dist, int64_t ld, unsigned long long negz2, unsigned long long one2) {
   extern __shared__ __align__(128) unsigned char smem[];
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -134,9 +161,15 @@ knn_scan384_kernel(const float* __restrict__ emb, const float* __restrict__ amag
   float* qs = reinterpret_cast<float*>(smem + kScanWarps * kScanStageBytes);
   uint64_t* bar = reinterpret_cast<uint64_t*>(smem + kScanWarps * kScanStageBytes + QB * kScanD * 4) + warp;
 
-  // queries -> smem (zero-fill unused slots so the unrolled QB loop stays finite)
-  for (int i = threadIdx.x; i < QB * kScanD; i += blockDim.x)
-    qs[i] = (i / kScanD < nq) ? q[i] : 0.0f;
+  // queries -> smem (zero-fill unused slots so the unrolled QB loop stays finite).
+  // QB == 1: plain [384].  QB >= 2: pair-interleaved, qs[(jp*384 + i)*2 + {0,1}] = q[2jp + {0,1}][i],
+  // so one LDS.128 yields {q0[i], q1[i], q0[i+1], q1[i+1]} = two packed operands.
+  for (int i = threadIdx.x; i < QB * kScanD; i += blockDim.x) {
+    int j, e;
+    if (QB == 1) { j = 0; e = i; }
+    else { const int jp = i / (2 * kScanD); const int r = i - jp * 2 * kScanD; e = r >> 1; j = 2 * jp + (r & 1); }
+    qs[i] = (j < nq) ? q[j * kScanD + e] : 0.0f;
+  }
   if (lane == 0) mbar_init(bar, 1);
   asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   __syncthreads();
@@ -174,19 +207,41 @@ knn_scan384_kernel(const float* __restrict__ emb, const float* __restrict__ amag
     parity ^= 1u;
 
     float acc[QB];
-#pragma unroll
-    for (int j = 0; j < QB; ++j) acc[j] = 0.0f;
-
+    if constexpr (QB == 1) {
+      acc[0] = 0.0f;
 #pragma unroll 4
-    for (int c = 0; c < kScanD / 4; ++c) {
-      const float4 a = rowp[c];
+      for (int c = 0; c < kScanD / 4; ++c) {
+        const float4 a = rowp[c];
+        const float4 b = qp[c];
+        acc[0] = mac<FMA>(acc[0], a.x, b.x);
+        acc[0] = mac<FMA>(acc[0], a.y, b.y);
+        acc[0] = mac<FMA>(acc[0], a.z, b.z);
+        acc[0] = mac<FMA>(acc[0], a.w, b.w);
+      }
+    } else {
+      constexpr int NP = QB / 2;
+      unsigned long long acc2[NP];
 #pragma unroll
-      for (int j = 0; j < QB; ++j) {
-        const float4 b = qp[j * (kScanD / 4) + c];
-        acc[j] = mac<FMA>(acc[j], a.x, b.x);
-        acc[j] = mac<FMA>(acc[j], a.y, b.y);
-        acc[j] = mac<FMA>(acc[j], a.z, b.z);
-        acc[j] = mac<FMA>(acc[j], a.w, b.w);
+      for (int jp = 0; jp < NP; ++jp) acc2[jp] = 0ull;                 // {+0.0f, +0.0f}
+      const ulonglong2* qp2 = reinterpret_cast<const ulonglong2*>(qs);  // [NP][192]
+#pragma unroll 2
+      for (int c = 0; c < kScanD / 4; ++c) {
+        const float4 a = rowp[c];
+        const unsigned long long ax = dup2(a.x), ay = dup2(a.y), az = dup2(a.z), aw = dup2(a.w);
+#pragma unroll
+        for (int jp = 0; jp < NP; ++jp) {
+          const ulonglong2 b01 = qp2[jp * (kScanD / 2) + 2 * c];
+          const ulonglong2 b23 = qp2[jp * (kScanD / 2) + 2 * c + 1];
+          acc2[jp] = mac2<FMA>(acc2[jp], ax, b01.x, negz2, one2);
+          acc2[jp] = mac2<FMA>(acc2[jp], ay, b01.y, negz2, one2);
+          acc2[jp] = mac2<FMA>(acc2[jp], az, b23.x, negz2, one2);
+          acc2[jp] = mac2<FMA>(acc2[jp], aw, b23.y, negz2, one2);
+        }
+      }
+#pragma unroll
+      for (int jp = 0; jp < NP; ++jp) {
+        acc[2 * jp] = __uint_as_float(static_cast<unsigned int>(acc2[jp]));
+        acc[2 * jp + 1] = __uint_as_float(static_cast<unsigned int>(acc2[jp] >> 32));
       }
     }
     __syncwarp();   // every lane's LDS of this stage has retired (values consumed above)

@@ -159,8 +159,10 @@ int launch_scan384(rse_index* h, const float* q, const double* sb, int nq, float
   const int64_t n_tiles = (h->n_rows + kScanTileRows - 1) / kScanTileRows;
   int grid = static_cast<int>(std::min<int64_t>(h->sm_count, (n_tiles + kScanWarps - 1) / kScanWarps));
   if (grid < 1) grid = 1;
+  // -0.0f / 1.0f pairs for the packed unfused step: run-time values on purpose (see knn_scan.cuh)
+  const unsigned long long negz2 = 0x8000000080000000ull, one2 = 0x3F8000003F800000ull;
   knn_scan384_kernel<QB, FMA><<<grid, kScanWarps * 32, smem, h->stream>>>(h->emb, h->amag, h->n_rows, q, sb, nq,
-                                                                         dist, h->dist_ld);
+                                                                         dist, h->dist_ld, negz2, one2);
   LAUNCHED(h);
   h->stats.knn_scan_launches++;
   return RSE_OK;
@@ -172,7 +174,8 @@ int launch_scan(rse_index* h, const float* q, const double* sb, int nq, float* d
     if (nq <= 1) return launch_scan384<1, FMA>(h, q, sb, nq, dist);
     if (nq <= 2) return launch_scan384<2, FMA>(h, q, sb, nq, dist);
     if (nq <= 4) return launch_scan384<4, FMA>(h, q, sb, nq, dist);
-    return launch_scan384<8, FMA>(h, q, sb, nq, dist);
+    if (nq <= 8) return launch_scan384<8, FMA>(h, q, sb, nq, dist);
+    return launch_scan384<16, FMA>(h, q, sb, nq, dist);
   }
   const int threads = 128;
   const int grid = static_cast<int>((h->n_rows + threads - 1) / threads);

@@ -60,12 +60,11 @@ select_pass_kernel(const uint32_t* __restrict__ dist, int64_t ld, int64_t n_rows
   const uint32_t* d = dist + static_cast<int64_t>(q) * ld;   // raw f32 bits: integer-typed so the
   // compiler cannot lower the sign-bit OR to a NaN-canonicalising FADD (it did)
   unsigned int run_digit = 0xFFFFFFFFu, run_cnt = 0u;
-  for (int64_t row = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; row < n_rows;
-       row += static_cast<int64_t>(gridDim.x) * blockDim.x) {
-    const uint32_t okey = f32_orderable(__ldcg(d + row));
-    if (okey == kInvalidOKey) continue;
+  auto visit = [&](uint32_t bits32, int64_t row) {
+    const uint32_t okey = f32_orderable(bits32);
+    if (okey == kInvalidOKey) return;
     const uint64_t key = knn_key(okey, pos_base + static_cast<uint64_t>(row));
-    if ((key & s.mask) != s.prefix) continue;
+    if ((key & s.mask) != s.prefix) return;
     const unsigned int digit = static_cast<unsigned int>(key >> shift) & dmask;
     if (digit == run_digit) {
       ++run_cnt;
@@ -73,6 +72,26 @@ select_pass_kernel(const uint32_t* __restrict__ dist, int64_t ld, int64_t n_rows
       if (run_cnt) atomicAdd(&h[run_digit], run_cnt);
       run_digit = digit; run_cnt = 1u;
     }
+  };
+  // 128-bit loads, two in flight per thread (ld is a multiple of 32 rows, so d is 16 B aligned)
+  const int64_t n4 = n_rows >> 2;
+  const uint4* d4 = reinterpret_cast<const uint4*>(d);
+  const int64_t gstride = static_cast<int64_t>(gridDim.x) * blockDim.x;
+  int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  for (; i + gstride < n4; i += 2 * gstride) {
+    const uint4 v0 = __ldcg(d4 + i);
+    const uint4 v1 = __ldcg(d4 + i + gstride);
+    visit(v0.x, 4 * i); visit(v0.y, 4 * i + 1); visit(v0.z, 4 * i + 2); visit(v0.w, 4 * i + 3);
+    const int64_t i1 = i + gstride;
+    visit(v1.x, 4 * i1); visit(v1.y, 4 * i1 + 1); visit(v1.z, 4 * i1 + 2); visit(v1.w, 4 * i1 + 3);
+  }
+  if (i < n4) {
+    const uint4 v0 = __ldcg(d4 + i);
+    visit(v0.x, 4 * i); visit(v0.y, 4 * i + 1); visit(v0.z, 4 * i + 2); visit(v0.w, 4 * i + 3);
+  }
+  if (blockIdx.x == 0 && threadIdx.x < (n_rows & 3)) {
+    const int64_t row = (n4 << 2) + threadIdx.x;
+    visit(__ldcg(d + row), row);
   }
   if (run_cnt) atomicAdd(&h[run_digit], run_cnt);
   __syncthreads();
@@ -144,17 +163,34 @@ select_collect_kernel(const uint32_t* __restrict__ dist, int64_t ld, int64_t n_r
                       SelState* __restrict__ st, unsigned long long* __restrict__ out_keys, int kprime) {
   const int q = blockIdx.y;
   const unsigned long long prefix = st[q].prefix, mask = st[q].mask;
-  const uint32_t* d = dist + static_cast<int64_t>(q) * ld;   // raw f32 bits: integer-typed so the
-  // compiler cannot lower the sign-bit OR to a NaN-canonicalising FADD (it did)
-  for (int64_t row = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; row < n_rows;
-       row += static_cast<int64_t>(gridDim.x) * blockDim.x) {
-    const uint32_t okey = f32_orderable(__ldcg(d + row));
-    if (okey == kInvalidOKey) continue;
+  const uint32_t* d = dist + static_cast<int64_t>(q) * ld;
+  auto visit = [&](uint32_t bits32, int64_t row) {
+    const uint32_t okey = f32_orderable(bits32);
+    if (okey == kInvalidOKey) return;
     const uint64_t key = knn_key(okey, pos_base + static_cast<uint64_t>(row));
     if ((key & mask) <= prefix) {
       unsigned int slot = atomicAdd(&st[q].out_count, 1u);
       if (slot < static_cast<unsigned int>(kprime)) out_keys[static_cast<int64_t>(q) * kprime + slot] = key;
     }
+  };
+  const int64_t n4 = n_rows >> 2;
+  const uint4* d4 = reinterpret_cast<const uint4*>(d);
+  const int64_t gstride = static_cast<int64_t>(gridDim.x) * blockDim.x;
+  int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  for (; i + gstride < n4; i += 2 * gstride) {
+    const uint4 v0 = __ldcg(d4 + i);
+    const uint4 v1 = __ldcg(d4 + i + gstride);
+    visit(v0.x, 4 * i); visit(v0.y, 4 * i + 1); visit(v0.z, 4 * i + 2); visit(v0.w, 4 * i + 3);
+    const int64_t i1 = i + gstride;
+    visit(v1.x, 4 * i1); visit(v1.y, 4 * i1 + 1); visit(v1.z, 4 * i1 + 2); visit(v1.w, 4 * i1 + 3);
+  }
+  if (i < n4) {
+    const uint4 v0 = __ldcg(d4 + i);
+    visit(v0.x, 4 * i); visit(v0.y, 4 * i + 1); visit(v0.z, 4 * i + 2); visit(v0.w, 4 * i + 3);
+  }
+  if (blockIdx.x == 0 && threadIdx.x < (n_rows & 3)) {
+    const int64_t row = (n4 << 2) + threadIdx.x;
+    visit(__ldcg(d + row), row);
   }
 }
 

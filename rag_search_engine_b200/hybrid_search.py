@@ -1,0 +1,193 @@
+"""HybridSearch — drop-in for rag_search_engine.utils.hybrid_search.HybridSearch with the
+fusion step (and, through the retrievers, BM25 + KNN) on the B200.
+
+The seam is the reference's own (hybrid_search.py:41-54, :70, :88): the two retrievers are
+looked up by MODULE-GLOBAL name at construction time, only ``.search(query, k=)``,
+``.query_top_k(query_text=, k=)`` and ``.close()`` are called on them, and the reference's unit
+tests swap them with ``monkeypatch.setattr(module, "KeywordSearch", Dummy)``
+(tests/test_hybrid_search.py:73-76) — which works on this module too.  Whatever the retrievers
+return is fused by ``rse_fuse_weighted`` / ``rse_fuse_rrf`` (min-max / RRF arithmetic and the
+CPython-set tie order reproduced on the device).  When both retrievers are the GPU ones,
+``*_batch`` runs the whole pipeline on the device in one call (``rse_hybrid``).
+"""
+from __future__ import annotations
+
+import logging
+import time
+from pathlib import Path
+from typing import Any, Dict, List, Optional, Sequence
+
+import numpy as np
+
+from . import _lib, runtime
+from .keyword_search import DEFAULT_DB_PATH, KeywordSearch
+from .semantic_search import SemanticSearch
+
+logger = logging.getLogger(__name__)
+
+
+class HybridSearch:
+    def __init__(self, docs_path: Path | str | None = None, db_path: Path | str | None = None, *, force: bool = False,
+                 max_chunk_size: int = 3, overlap: int = 1, device: int = 0, tie_mode: str = "reference",
+                 **retriever_kwargs) -> None:
+        self.db_path = Path(db_path) if db_path else Path(DEFAULT_DB_PATH)
+        self.device = device
+        self.tie_mode = {"reference": _lib.TIE_REFERENCE, "id": _lib.TIE_BY_ID}[tie_mode]
+        kw_extra = {k: v for k, v in retriever_kwargs.items() if k in ("tokenizer",)}
+        sem_extra = {k: v for k, v in retriever_kwargs.items() if k in ("encoder",)}
+        if KeywordSearch.__module__.startswith(__package__):
+            kw_extra["device"] = device
+        if SemanticSearch.__module__.startswith(__package__):
+            sem_extra["device"] = device
+        # module-global lookup, exactly like hybrid_search.py:41-54
+        self.keyword = KeywordSearch(docs_path=docs_path, db_path=self.db_path, force=force, **kw_extra)
+        self.semantic = SemanticSearch(docs_path=docs_path, db_path=self.db_path, max_chunk_size=max_chunk_size,
+                                       overlap=overlap, force=force, **sem_extra)
+        self._index = runtime.acquire(self.db_path, device)      # fusion kernels (+ shared with GPU retrievers)
+        self._closed = False
+
+    # ---------------- wrappers (hybrid_search.py:57-88) ---------------- #
+    def _bm25_search(self, query: str, limit: int) -> List[Dict[str, Any]]:
+        return self.keyword.search(query, k=limit)
+
+    def _semantic_search(self, query: str, limit: int) -> List[Dict[str, Any]]:
+        return self.semantic.query_top_k(query_text=query, k=limit)
+
+    # ---------------- fusion on the device ---------------- #
+    def _fuse_inputs(self, bm25_hits, sem_hits, limit):
+        L = max(1, min(limit, _lib.RSE_MAX_FUSE_LIMIT))
+        if limit > _lib.RSE_MAX_FUSE_LIMIT:
+            raise ValueError(f"limit {limit} exceeds the fusion kernel's limit of {_lib.RSE_MAX_FUSE_LIMIT}")
+        # the retrievers are asked for k=limit; a plugged-in retriever may return more — the reference
+        # would fuse all of them, so size the device call to what actually came back
+        L = max(L, len(bm25_hits), len(sem_hits))
+        if L > _lib.RSE_MAX_FUSE_LIMIT:
+            raise ValueError("retriever returned more hits than the fusion kernel supports (128)")
+        bid = np.full((1, L), -1, np.int64); bsc = np.zeros((1, L)); sid = np.full((1, L), -1, np.int64)
+        sds = np.zeros((1, L))
+        for j, h in enumerate(bm25_hits):
+            bid[0, j] = int(h["id"]); bsc[0, j] = float(h["score"])
+        for j, h in enumerate(sem_hits):
+            sid[0, j] = int(h["movie_id"]); sds[0, j] = float(h["distance"])
+        return L, bid, bsc, np.array([len(bm25_hits)], np.int32), sid, sds, np.array([len(sem_hits)], np.int32)
+
+    # ---------------- weighted (hybrid_search.py:91-180) ---------------- #
+    def weighted_search(self, query: str, alpha: float, limit: int = 5) -> List[Dict[str, Any]]:
+        bm25_hits = self._bm25_search(query=query, limit=limit)
+        sem_hits = self._semantic_search(query=query, limit=limit)
+        if not bm25_hits and not sem_hits:
+            return []
+        L, bid, bsc, bc, sid, sds, sc = self._fuse_inputs(bm25_hits, sem_hits, limit)
+        oid, ob, osem, osc, oc = self._index.fuse_weighted(L, alpha, bid, bsc, bc, sid, sds, sc, tie_mode=self.tie_mode)
+        bm25_by_id = {int(h["id"]): h for h in bm25_hits}
+        sem_by_id = {int(h["movie_id"]): h for h in sem_hits}
+        results = []
+        for j in range(min(int(oc[0]), limit)):
+            doc_id = int(oid[0, j])
+            b, s = bm25_by_id.get(doc_id, {}), sem_by_id.get(doc_id, {})
+            results.append({"id": doc_id,
+                            "title": b.get("title") or s.get("title") or "<unknown>",          # :155
+                            "description": b.get("description") or s.get("description") or "",  # :156-158
+                            "bm25": float(ob[0, j]), "semantic": float(osem[0, j]), "score": float(osc[0, j])})
+        return results
+
+    # ---------------- RRF (hybrid_search.py:183-379) ---------------- #
+    def rrf_search(self, query: str, k: int = 60, limit: int = 10, rerank_method: str | None = None) -> List[Dict[str, Any]]:
+        logger.debug("RRF search starting: query=%r, k=%s, limit=%d, rerank_method=%r", query, k, limit, rerank_method)
+        bm25_hits = sorted(self._bm25_search(query=query, limit=limit), key=lambda h: h["score"], reverse=True)   # :220-224
+        sem_hits = sorted(self._semantic_search(query=query, limit=limit), key=lambda h: h["distance"])          # :235-238
+        results: List[Dict[str, Any]] = []
+        if bm25_hits or sem_hits:
+            # the reference sorts the FULL union before any truncation (rerankers see all of it)
+            L, bid, bsc, bc, sid, sds, sc = self._fuse_inputs(bm25_hits, sem_hits, limit)
+            n_union = len({int(h["id"]) for h in bm25_hits} | {int(h["movie_id"]) for h in sem_hits})
+            Lout = max(L, min(n_union, _lib.RSE_MAX_FUSE_LIMIT))
+            if Lout != L:
+                pad = lambda a, fill: np.concatenate([a, np.full((1, Lout - L), fill, a.dtype)], 1)  # noqa: E731
+                bid, bsc, sid, sds = pad(bid, -1), pad(bsc, 0.0), pad(sid, -1), pad(sds, 0.0)
+            if n_union > _lib.RSE_MAX_FUSE_LIMIT:
+                raise ValueError("union of retriever hits exceeds the fusion kernel's limit (128)")
+            oid, osc, orb, ors, oc = self._index.fuse_rrf(Lout, k, bid, bsc, bc, sid, sds, sc, tie_mode=self.tie_mode)
+            bm25_meta = {int(h["id"]): h for h in bm25_hits}
+            sem_meta = {int(h["movie_id"]): h for h in sem_hits}
+            for j in range(int(oc[0])):
+                doc_id = int(oid[0, j])
+                meta = bm25_meta.get(doc_id) or sem_meta.get(doc_id) or {}                 # :257
+                results.append({"id": doc_id, "title": meta.get("title", "<unknown>"),
+                                "description": meta.get("description", ""), "score": float(osc[0, j]),
+                                "bm25_rank": None if orb[0, j] < 0 else int(orb[0, j]),
+                                "sem_rank": None if ors[0, j] < 0 else int(ors[0, j])})
+        logger.debug("RRF base results (pre-rerank, top %d): %s", len(results), results)
+
+        # ---- rerank branches run on the host on top of the GPU results (out of scope) ----
+        if rerank_method == "cross_encoder":                                               # :279-312
+            from sentence_transformers import CrossEncoder  # type: ignore
+            pairs = []
+            for idx, doc in enumerate(results, start=1):
+                doc["rrf_rank"] = idx
+                pairs.append([query, f"{doc.get('title', '')} - {doc.get('document') or doc.get('description', '')}"])
+            if pairs:
+                scores = CrossEncoder("cross-encoder/ms-marco-TinyBERT-L2-v2").predict(pairs)
+                for doc, score in zip(results, scores):
+                    doc["cross_encoder_score"] = float(score)
+                results.sort(key=lambda d: (d.get("cross_encoder_score", 0.0), d["score"]), reverse=True)
+            return results[:limit]
+        if rerank_method in ("individual", "batch"):                                       # :315-367
+            from rag_search_engine.llm.gemini import Gemini  # type: ignore  (network LLM: reference package)
+            gi = Gemini()
+            if rerank_method == "individual":
+                for idx, doc in enumerate(results):
+                    if idx > 0:
+                        time.sleep(3)
+                    doc["rerank_score"] = gi.rerank_document(query, doc, rerank_method)
+                results.sort(key=lambda r: (r.get("rerank_score", 0.0), r["score"]), reverse=True)
+            else:
+                ranked_ids = gi.rerank_batch(query, results, rerank_method)
+                rank_map = {doc_id: idx for idx, doc_id in enumerate(ranked_ids, start=1)}
+                for doc in results:
+                    doc["rerank_rank"] = rank_map.get(doc["id"])
+                results.sort(key=lambda r: (r.get("rerank_rank") is None, r.get("rerank_rank") or 1e9))
+            return results[:limit]
+        if rerank_method is not None:                                                      # :370-373
+            logger.warning("Unknown rerank_method=%r, using base RRF only", rerank_method)
+        return results[:limit]                                                             # :379
+
+    # ---------------- fully on-device batch path ---------------- #
+    def _gpu_retrievers(self) -> bool:
+        return isinstance(self.keyword, KeywordSearch) and isinstance(self.semantic, SemanticSearch) and \
+            type(self.keyword).__module__.startswith(__package__) and type(self.semantic).__module__.startswith(__package__)
+
+    def _hybrid_batch(self, mode, param, token_lists, query_vecs, limit, knn_multiplier, k1, b):
+        if not self._gpu_retrievers():
+            raise RuntimeError("*_batch needs the GPU KeywordSearch and SemanticSearch of this package")
+        kw, sem = self.keyword, self.semantic
+        reg = runtime.parts(self.db_path, self.device)
+        if "ids" not in reg:
+            self._index.set_id_tables(kw._arr.doc_ids, sem._arr.movie_ids)
+            reg["ids"] = True
+        tok_indptr, rows = kw._term_rows(token_lists)
+        return self._index.hybrid(mode, param, limit, query_vecs, tok_indptr, rows, knn_multiplier=knn_multiplier,
+                                  k1=k1, b=b, tie_mode=self.tie_mode)
+
+    def rrf_search_batch(self, token_lists: Sequence[Sequence[str]], query_vecs, k=60, limit: int = 10,
+                         knn_multiplier: int = 10, k1: float = 1.5, b: float = 0.75):
+        """[{id, score, bm25_rank, sem_rank}] per query; BM25 + KNN + aggregation + RRF in one device call."""
+        oid, osc, oa, ob, oc = self._hybrid_batch(0, float(k), token_lists, query_vecs, limit, knn_multiplier, k1, b)
+        return [[{"id": int(oid[q, j]), "score": float(osc[q, j]),
+                  "bm25_rank": None if oa[q, j] < 0 else int(oa[q, j]),
+                  "sem_rank": None if ob[q, j] < 0 else int(ob[q, j])} for j in range(oc[q])]
+                for q in range(len(token_lists))]
+
+    def weighted_search_batch(self, token_lists: Sequence[Sequence[str]], query_vecs, alpha: float, limit: int = 5,
+                              knn_multiplier: int = 10, k1: float = 1.5, b: float = 0.75):
+        oid, osc, oa, ob, oc = self._hybrid_batch(1, float(alpha), token_lists, query_vecs, limit, knn_multiplier, k1, b)
+        return [[{"id": int(oid[q, j]), "bm25": float(oa[q, j]), "semantic": float(ob[q, j]),
+                  "score": float(osc[q, j])} for j in range(oc[q])] for q in range(len(token_lists))]
+
+    # ---------------- cleanup (hybrid_search.py:382-384) ---------------- #
+    def close(self) -> None:
+        self.keyword.close()
+        self.semantic.close()
+        if not self._closed:
+            self._closed = True
+            runtime.release(self.db_path, self.device)

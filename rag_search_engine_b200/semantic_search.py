@@ -1,0 +1,182 @@
+"""SemanticSearch — drop-in for rag_search_engine.utils.semantic_search.SemanticSearch whose
+``query_top_k`` runs the vec0 KNN + best-chunk-per-movie aggregation on the B200.
+
+Same constructor, method names, return dicts and error behaviour as the reference
+(semantic_search.py:36-65, :211-340, :375-395).  The chunk embeddings are read once from the
+vec0 shadow tables of the reference-built SQLite file (store.export_embeddings) and kept in HBM;
+chunk text / titles for the ≤k hits still come from SQLite (:262-279, :321-328).
+"""
+from __future__ import annotations
+
+import sqlite3
+from pathlib import Path
+from typing import Any, Dict, List, Optional
+
+import numpy as np
+
+from . import runtime, store
+from .keyword_search import DEFAULT_DB_PATH
+from .textutil import chunk_text
+
+
+def _default_encoder():
+    try:
+        from sentence_transformers import SentenceTransformer  # type: ignore
+    except Exception:
+        return None
+    return SentenceTransformer("all-MiniLM-L6-v2")              # semantic_search.py:45
+
+
+class SemanticSearch:
+    def __init__(self, docs_path: Path | str | None = None, db_path: Path | str | None = None,
+                 max_chunk_size: int = 3, overlap: int = 1, force: bool = False, *, encoder=None,
+                 device: int = 0) -> None:
+        self.model = encoder if encoder is not None else _default_encoder()
+        self.max_chunk_size = max_chunk_size
+        self.overlap = overlap
+        self.db_path = Path(db_path) if db_path else Path(DEFAULT_DB_PATH)
+        self.db_path.parent.mkdir(parents=True, exist_ok=True)
+        self.docs_path = Path(docs_path) if docs_path else None
+        self.device = device
+        if self.docs_path is not None:
+            self._build(force)
+        self.conn = sqlite3.connect(self.db_path)
+        self.conn.execute("PRAGMA journal_mode=WAL")
+        self.conn.execute("PRAGMA synchronous=NORMAL")
+        self._index = runtime.acquire(self.db_path, device)
+        self._closed = False
+        self._load()
+        self.embedding_dim = (self.model.get_sentence_embedding_dimension() if self.model is not None
+                              else self._arr.dim)
+
+    # ------------------------------------------------------------------ build (stays on SQLite)
+    def _build(self, force: bool) -> None:
+        """Chunking + embedding + vec0 insert are NOT accelerated: use the reference's
+        build when it is importable, else freeze embeddings with the given encoder into the same
+        tables (store.write_reference_db)."""
+        try:
+            from rag_search_engine.utils.semantic_search import SemanticSearch as RefSS  # type: ignore
+            ref = RefSS(docs_path=self.docs_path, db_path=self.db_path, max_chunk_size=self.max_chunk_size,
+                        overlap=self.overlap, force=force)
+            ref.close()
+            return
+        except ImportError:
+            pass
+        if self.model is None:
+            raise RuntimeError("SemanticSearch build needs an encoder (sentence-transformers is not installed): "
+                               "pass encoder=<object with .encode(texts)>")
+        import json
+        data = json.loads(Path(self.docs_path).read_text(encoding="utf-8"))["movies"]
+        conn = sqlite3.connect(self.db_path)
+        try:
+            store._init_schema(conn)
+            cur = conn.cursor()
+            (n_movies,) = cur.execute("SELECT COUNT(*) FROM movies").fetchone()
+            if n_movies != len(data):
+                cur.execute("DELETE FROM movies")
+                cur.executemany("INSERT INTO movies(id, title, description) VALUES (?, ?, ?)",
+                                [(int(d["id"]), d["title"], d["description"]) for d in data])
+                conn.commit()
+            (n_chunks,) = cur.execute("SELECT COUNT(*) FROM chunks").fetchone()
+            params = cur.execute("SELECT DISTINCT max_chunk_size, overlap FROM chunks").fetchall()
+            in_sync = (n_chunks > 0 and len(params) == 1 and params[0] == (self.max_chunk_size, self.overlap)
+                       and store._table_exists(conn, f"{store.VEC_TABLE}_chunks"))          # :145-154
+            if force or not in_sync:
+                movies = cur.execute("SELECT id, title, description FROM movies ORDER BY id").fetchall()
+                rows, texts = store.plan_chunks(movies, self.max_chunk_size, self.overlap)
+                cur.execute("DELETE FROM chunks")
+                cur.executemany("INSERT INTO chunks(id, movie_id, chunk_index, max_chunk_size, overlap) "
+                                "VALUES (?,?,?,?,?)", rows)
+                emb = np.asarray(self.model.encode(texts), np.float32)
+                store.write_vec0_shadow(conn, np.array([r[0] for r in rows], np.int64), emb)
+                conn.commit()
+        finally:
+            conn.close()
+
+    def _load(self) -> None:
+        reg = runtime.parts(self.db_path, self.device)
+        if "emb" not in reg:
+            arr = store.export_embeddings(self.conn)
+            if arr.emb.shape[0] > 0:
+                self._index.load_embeddings(arr.emb, valid=arr.valid, rowid=arr.rowid, movie_idx=arr.movie_idx)
+            reg["emb"] = arr
+        self._arr: store.EmbArrays = reg["emb"]
+
+    # ------------------------------------------------------------------ BaseSearchDB helpers
+    def count_movies(self) -> int:
+        (count,) = self.conn.execute("SELECT COUNT(*) FROM movies").fetchone()
+        return count
+
+    def close(self) -> None:
+        if not self._closed:
+            self._closed = True
+            self.conn.close()
+            runtime.release(self.db_path, self.device)
+
+    @classmethod
+    def build_from_docs(cls, docs_path, db_path=None, force: bool = False, **kw) -> "SemanticSearch":
+        return cls(docs_path=docs_path, db_path=db_path, force=force, **kw)
+
+    @classmethod
+    def open_existing(cls, db_path=None, **kw) -> "SemanticSearch":
+        return cls(docs_path=None, db_path=db_path, **kw)
+
+    # ------------------------------------------------------------------ embeddings (semantic_search.py:211-222)
+    def generate_embedding(self, text):
+        texts = [text] if isinstance(text, str) else text
+        if any(len(t.strip()) == 0 for t in texts):
+            raise ValueError("cannot embed empty text")
+        if self.model is None:
+            raise RuntimeError("no query encoder (sentence-transformers is not installed): pass encoder=... "
+                               "or call query_top_k_vec with frozen query vectors")
+        return np.asarray(self.model.encode(texts), dtype=np.float32)
+
+    # ------------------------------------------------------------------ query
+    def query_top_k_vec(self, query_vecs, k: int = 5, knn_multiplier: int = 10) -> List[List[Dict[str, Any]]]:
+        """Batch entry point on frozen query vectors [B, dim] → one reference-shaped result list per query."""
+        Q = np.ascontiguousarray(query_vecs, np.float32).reshape(-1, self._arr.dim if self._arr.dim else 1)
+        if self._arr.emb.shape[0] == 0:
+            return [[] for _ in range(Q.shape[0])]
+        internal_k = max(k * knn_multiplier, k)                 # semantic_search.py:251
+        dist, rowid, movie, cnt = self._index.knn_movies(Q, k, internal_k)
+        out = []
+        cur = self.conn.cursor()
+        for q in range(Q.shape[0]):
+            hits = []
+            for j in range(cnt[q]):
+                cid = int(rowid[q, j])
+                movie_id = int(self._arr.movie_ids[movie[q, j]])
+                ci, mcs, ov = cur.execute("SELECT chunk_index, max_chunk_size, overlap FROM chunks WHERE id = ?",
+                                          (cid,)).fetchone()
+                title, desc = cur.execute("SELECT title, description FROM movies WHERE id = ?", (movie_id,)).fetchone()
+                hits.append({"chunk_id": cid, "distance": float(dist[q, j]),
+                             "chunk": chunk_text(title, desc, int(ci), int(mcs), int(ov)),
+                             "movie_id": movie_id, "title": title, "description": desc})
+            out.append(hits)
+        return out
+
+    def query_top_k(self, query_text: str, k: int = 5, knn_multiplier: int = 10) -> List[Dict[str, Any]]:
+        """semantic_search.py:225-340."""
+        query_vec = self.generate_embedding(query_text)[0]
+        return self.query_top_k_vec(query_vec[None, :], k=k, knn_multiplier=knn_multiplier)[0]
+
+    def _reconstruct_chunk_text(self, title, description, chunk_index, max_chunk_size, overlap) -> str:
+        return chunk_text(title, description, chunk_index, max_chunk_size, overlap)
+
+    # ------------------------------------------------------------------ verify (semantic_search.py:368-395)
+    def verify_model(self) -> None:
+        print(f"Model loaded: {self.model}")
+        print(f"Max sequence length: {getattr(self.model, 'max_seq_length', None)}")
+        print(f"Embedding dim: {self.embedding_dim}")
+
+    def verify_db(self) -> None:
+        cur = self.conn.cursor()
+        (movie_count,) = cur.execute("SELECT COUNT(*) FROM movies").fetchone()
+        (chunk_count,) = cur.execute("SELECT COUNT(*) FROM chunks").fetchone()
+        vec_count = int(self._arr.valid.sum()) if self._arr.valid is not None else int(self._arr.emb.shape[0])
+        print(f"Vector DB path: {self.db_path}")
+        print("sqlite-vec version: (not loaded: vec0 shadow tables read directly; KNN runs in librse on the GPU)")
+        print(f"Movies count:            {movie_count}")
+        print(f"Chunks table count:      {chunk_count}")
+        print(f"Embeddings (vec0) count: {vec_count}")
+        print(f"Embedding dim:           {self.embedding_dim}")

@@ -1,0 +1,258 @@
+"""Load-time exporter: reference SQLite file → the arrays librse keeps in HBM.
+
+SQLite stays the build/storage layer (north_star); this module only READS a database that
+the reference built (``rag-search build``) with the stdlib ``sqlite3`` — no sqlite-vec
+extension needed, because vec0 keeps its data in ordinary shadow tables:
+
+  chunk_embeddings_chunks(chunk_id, size, validity BLOB, rowids BLOB)
+  chunk_embeddings_vector_chunks00(rowid = chunk_id, vectors BLOB)      
+
+and the keyword index lives in terms / postings / doclen
+(rag_search_engine/utils/keyword_search.py:43-78).  It also contains the writer for those
+same tables (``write_reference_db``), used to freeze synthetic corpora / precomputed
+embeddings to disk in the reference's on-disk format where the reference's own build
+(spaCy + sentence-transformers + sqlite-vec) is not installable.
+"""
+from __future__ import annotations
+
+import json
+import sqlite3
+from dataclasses import dataclass, field
+from pathlib import Path
+from typing import Callable, Dict, List, Optional, Sequence
+
+import numpy as np
+
+from .textutil import Tokenizer, sentence_chunks
+
+VEC0_BLOCK = 1024
+TITLE_END_TOKEN = "[TITLE_END]"        # keyword_search.py:24
+VEC_TABLE = "chunk_embeddings"         # semantic_search.py:94
+
+
+# ----------------------------------------------------------------------------- BM25 export
+@dataclass
+class Bm25Arrays:
+    indptr: np.ndarray          # [T+1] int64
+    doc_idx: np.ndarray         # [P] uint32 dense index into doc_ids, ascending within a term
+    tf: np.ndarray              # [P] uint32 = len(positions)
+    df: np.ndarray              # [T] int64 = len(rows) as the reference counts it (:222)
+    dl: np.ndarray              # [M] uint32
+    doc_ids: np.ndarray         # [M] int64 ascending (doclen.doc_id)
+    n_movies: int               # COUNT(*) FROM movies (:196)
+    avgdl: float                # AVG(length) FROM doclen (:197-198); 0.0 when the table is empty
+    term_row: Dict[str, int] = field(default_factory=dict)
+
+
+def export_bm25(conn: sqlite3.Connection) -> Bm25Arrays:
+    cur = conn.cursor()
+    (n_movies,) = cur.execute("SELECT COUNT(*) FROM movies").fetchone()
+    rows = cur.execute("SELECT doc_id, length FROM doclen ORDER BY doc_id").fetchall()
+    doc_ids = np.array([r[0] for r in rows], np.int64)
+    dl = np.array([r[1] for r in rows], np.uint32)
+    (avgdl,) = cur.execute("SELECT AVG(length) FROM doclen").fetchone()
+    terms = cur.execute("SELECT id, term FROM terms ORDER BY id").fetchall()
+    term_ids = np.array([t[0] for t in terms], np.int64)
+    term_row = {t[1]: i for i, t in enumerate(terms)}
+    T = len(terms)
+    # postings in (term_id, doc_id) order = the autoindex order the reference reads them in (:214-218)
+    t_list: List[np.ndarray] = []
+    d_list: List[np.ndarray] = []
+    f_list: List[np.ndarray] = []
+    cur.execute("SELECT term_id, doc_id, json_array_length(positions) FROM postings ORDER BY term_id, doc_id")
+    while True:
+        chunk = cur.fetchmany(1 << 18)
+        if not chunk:
+            break
+        a = np.array(chunk, np.int64).reshape(-1, 3)
+        t_list.append(a[:, 0]); d_list.append(a[:, 1]); f_list.append(a[:, 2])
+    if t_list:
+        pt = np.concatenate(t_list); pd = np.concatenate(d_list); pf = np.concatenate(f_list)
+    else:
+        pt = pd = pf = np.zeros(0, np.int64)
+    trow = np.searchsorted(term_ids, pt)
+    known_t = (trow < T)
+    known_t[known_t] &= term_ids[trow[known_t]] == pt[known_t]
+    trow, pd, pf = trow[known_t], pd[known_t], pf[known_t]
+    df = np.bincount(trow, minlength=T).astype(np.int64)                 # len(rows), before the doclen filter
+    didx = np.searchsorted(doc_ids, pd)
+    has_dl = didx < len(doc_ids)
+    has_dl[has_dl] &= doc_ids[didx[has_dl]] == pd[has_dl]                # `if not dl_row: continue` (:235-236)
+    trow, didx, pf = trow[has_dl], didx[has_dl], pf[has_dl]
+    indptr = np.zeros(T + 1, np.int64)
+    np.cumsum(np.bincount(trow, minlength=T), out=indptr[1:])
+    return Bm25Arrays(indptr=indptr, doc_idx=didx.astype(np.uint32), tf=pf.astype(np.uint32), df=df, dl=dl,
+                      doc_ids=doc_ids, n_movies=int(n_movies), avgdl=float(avgdl) if avgdl else 0.0,
+                      term_row=term_row)
+
+
+# ----------------------------------------------------------------------------- vec0 export
+@dataclass
+class EmbArrays:
+    emb: np.ndarray                     # [n_phys, dim] float32, vec0 physical layout (block*1024 + slot)
+    valid: Optional[np.ndarray]         # [n_phys] uint8, None = all valid
+    rowid: np.ndarray                   # [n_phys] int64 (chunks.id)
+    movie_idx: np.ndarray               # [n_phys] int32 dense index into movie_ids, -1 = dropped by the JOINs
+    movie_ids: np.ndarray               # [Mm] int64 ascending (movies.id)
+    dim: int
+
+
+def _table_exists(conn: sqlite3.Connection, name: str) -> bool:
+    return conn.execute("SELECT 1 FROM sqlite_master WHERE name = ?", (name,)).fetchone() is not None
+
+
+def export_embeddings(conn: sqlite3.Connection, table: str = VEC_TABLE) -> EmbArrays:
+    """Read the vec0 shadow tables in vec0's own scan order (chunk_id ascending, slot ascending)."""
+    if not _table_exists(conn, f"{table}_chunks") or not _table_exists(conn, f"{table}_vector_chunks00"):
+        raise RuntimeError(f"{table}: vec0 shadow tables not found — was the DB built by `rag-search build`?")
+    cur = conn.cursor()
+    movie_ids = np.array([r[0] for r in cur.execute("SELECT id FROM movies ORDER BY id")], np.int64)
+    chunk_movie = dict(cur.execute("SELECT id, movie_id FROM chunks").fetchall())
+    blocks = cur.execute(
+        f"SELECT c.chunk_id, c.size, c.validity, c.rowids, v.vectors FROM {table}_chunks c "
+        f"JOIN {table}_vector_chunks00 v ON v.rowid = c.chunk_id ORDER BY c.chunk_id").fetchall()
+    embs, valids, rowids = [], [], []
+    dim = None
+    for _cid, size, validity, rowid_blob, vectors in blocks:
+        if size != VEC0_BLOCK:
+            raise RuntimeError(f"vec0 chunk_size {size} != 1024 (the reference never sets chunk_size)")
+        v = np.unpackbits(np.frombuffer(validity, np.uint8), bitorder="little")[:size]
+        if not v.any():
+            continue                                    # a block without live rows never yields a candidate
+        vec = np.frombuffer(vectors, np.float32)
+        d = vec.size // size
+        if dim is None:
+            dim = d
+        elif d != dim:
+            raise RuntimeError("inconsistent vector dimension across vec0 blocks")
+        embs.append(vec.reshape(size, d))
+        valids.append(v.astype(np.uint8))
+        rowids.append(np.frombuffer(rowid_blob, np.int64)[:size])
+    if not embs:
+        return EmbArrays(np.zeros((0, 1), np.float32), None, np.zeros(0, np.int64), np.zeros(0, np.int32), movie_ids, 0)
+    emb = np.ascontiguousarray(np.concatenate(embs, 0))
+    valid = np.concatenate(valids)
+    rowid = np.concatenate(rowids).astype(np.int64)
+    # trailing empty slots of the last block carry no information
+    last = int(np.nonzero(valid)[0][-1]) + 1
+    emb, valid, rowid = emb[:last], valid[:last], rowid[:last]
+    mv = np.array([chunk_movie.get(int(r), None) if ok else None for r, ok in zip(rowid, valid)], object)
+    movie_idx = np.full(len(rowid), -1, np.int32)
+    have = np.array([m is not None for m in mv])
+    if have.any():
+        mids = np.array([int(m) for m in mv[have]], np.int64)
+        pos = np.searchsorted(movie_ids, mids)
+        ok = pos < len(movie_ids)
+        ok[ok] &= movie_ids[pos[ok]] == mids[ok]
+        tmp = np.where(ok, pos, -1).astype(np.int32)
+        movie_idx[np.nonzero(have)[0]] = tmp
+    return EmbArrays(emb=emb, valid=None if valid.all() else valid, rowid=rowid, movie_idx=movie_idx,
+                     movie_ids=movie_ids, dim=int(dim))
+
+
+# ----------------------------------------------------------------------------- writer (reference on-disk format)
+def _init_schema(conn: sqlite3.Connection) -> None:
+    cur = conn.cursor()
+    cur.execute("CREATE TABLE IF NOT EXISTS movies (id INTEGER PRIMARY KEY, title TEXT NOT NULL, description TEXT NOT NULL)")
+    cur.execute("CREATE TABLE IF NOT EXISTS terms (id INTEGER PRIMARY KEY, term TEXT UNIQUE NOT NULL)")
+    cur.execute("CREATE TABLE IF NOT EXISTS postings (term_id INTEGER NOT NULL, doc_id INTEGER NOT NULL, "
+                "positions TEXT NOT NULL, PRIMARY KEY (term_id, doc_id))")
+    cur.execute("CREATE TABLE IF NOT EXISTS doclen (doc_id INTEGER PRIMARY KEY, length INTEGER NOT NULL)")
+    cur.execute("CREATE TABLE IF NOT EXISTS chunks (id INTEGER PRIMARY KEY, movie_id INTEGER NOT NULL, "
+                "chunk_index INTEGER NOT NULL, max_chunk_size INTEGER NOT NULL, overlap INTEGER NOT NULL)")
+    conn.commit()
+
+
+def write_keyword_index(conn: sqlite3.Connection, docs: Sequence[dict], tokenizer: Tokenizer) -> None:
+    """The tables KeywordSearch._rebuild_index fills (keyword_search.py:102-177): tokens =
+    title + ["[TITLE_END]"] + body (:132), doclen counts the sentinel (:133), positions JSON (:169)."""
+    cur = conn.cursor()
+    cur.execute("DELETE FROM postings"); cur.execute("DELETE FROM terms"); cur.execute("DELETE FROM doclen")
+    t_toks = tokenizer([d["title"] for d in docs])
+    b_toks = tokenizer([d["description"] for d in docs])
+    term_id: Dict[str, int] = {}
+    post_rows, dl_rows = [], []
+    for d, tt, bt in zip(docs, t_toks, b_toks):
+        doc_id = int(d["id"])
+        toks = list(tt) + [TITLE_END_TOKEN] + list(bt)
+        dl_rows.append((doc_id, len(toks)))
+        positions: Dict[str, List[int]] = {}
+        for pos, tok in enumerate(toks):
+            positions.setdefault(tok, []).append(pos)
+        for tok, ps in positions.items():
+            tid = term_id.setdefault(tok, len(term_id) + 1)
+            post_rows.append((tid, doc_id, json.dumps(ps)))
+    cur.executemany("INSERT INTO terms(id, term) VALUES (?, ?)", [(i, t) for t, i in term_id.items()])
+    cur.executemany("INSERT INTO doclen(doc_id, length) VALUES (?, ?)", dl_rows)
+    cur.executemany("INSERT INTO postings(term_id, doc_id, positions) VALUES (?, ?, ?)", post_rows)
+    conn.commit()
+
+
+def plan_chunks(movies: Sequence[tuple], max_chunk_size: int, overlap: int):
+    """semantic_search.py:164-188: movies ORDER BY id, chunk ids 0,1,2,… contiguous per movie,
+    title first, description windows joined without a separator.  Returns (rows, texts)."""
+    rows, texts = [], []
+    cid = 0
+    for movie_id, title, description in movies:
+        rows.append((cid, int(movie_id), 0, max_chunk_size, overlap)); texts.append(title); cid += 1
+        for li, sent in enumerate(sentence_chunks(description, max_chunk_size, overlap), start=1):
+            rows.append((cid, int(movie_id), li, max_chunk_size, overlap)); texts.append("".join(sent)); cid += 1
+    return rows, texts
+
+
+def write_vec0_shadow(conn: sqlite3.Connection, rowids: np.ndarray, emb: np.ndarray, table: str = VEC_TABLE) -> None:
+    """Store vectors exactly where vec0 would after inserting ``rowids`` in order into an empty
+    table: block i // 1024, slot i % 1024."""
+    cur = conn.cursor()
+    cur.execute(f"DROP TABLE IF EXISTS {table}_chunks")
+    cur.execute(f"DROP TABLE IF EXISTS {table}_vector_chunks00")
+    cur.execute(f"DROP TABLE IF EXISTS {table}_rowids")
+    cur.execute(f"CREATE TABLE {table}_chunks (chunk_id INTEGER PRIMARY KEY AUTOINCREMENT, size INTEGER NOT NULL, "
+                f"validity BLOB NOT NULL, rowids BLOB NOT NULL)")
+    cur.execute(f"CREATE TABLE {table}_vector_chunks00 (rowid INTEGER PRIMARY KEY, vectors BLOB NOT NULL)")
+    cur.execute(f"CREATE TABLE {table}_rowids (rowid INTEGER PRIMARY KEY AUTOINCREMENT, id, chunk_id INTEGER, "
+                f"chunk_offset INTEGER)")
+    emb = np.ascontiguousarray(emb, np.float32)
+    n, dim = emb.shape
+    for b0 in range(0, n, VEC0_BLOCK):
+        b1 = min(n, b0 + VEC0_BLOCK)
+        cnt = b1 - b0
+        vec = np.zeros((VEC0_BLOCK, dim), np.float32); vec[:cnt] = emb[b0:b1]
+        rid = np.zeros(VEC0_BLOCK, np.int64); rid[:cnt] = rowids[b0:b1]
+        bits = np.zeros(VEC0_BLOCK, np.uint8); bits[:cnt] = 1
+        chunk_id = b0 // VEC0_BLOCK + 1
+        cur.execute(f"INSERT INTO {table}_chunks(chunk_id, size, validity, rowids) VALUES (?, ?, ?, ?)",
+                    (chunk_id, VEC0_BLOCK, np.packbits(bits, bitorder="little").tobytes(), rid.tobytes()))
+        cur.execute(f"INSERT INTO {table}_vector_chunks00(rowid, vectors) VALUES (?, ?)", (chunk_id, vec.tobytes()))
+        cur.executemany(f"INSERT INTO {table}_rowids(rowid, id, chunk_id, chunk_offset) VALUES (?, NULL, ?, ?)",
+                        [(int(rowids[i]), chunk_id, i - b0) for i in range(b0, b1)])
+    conn.commit()
+
+
+def write_reference_db(db_path, docs: Sequence[dict], tokenizer: Tokenizer,
+                       embed: Optional[Callable[[List[str]], np.ndarray]] = None, max_chunk_size: int = 3,
+                       overlap: int = 1) -> Path:
+    """Create a database in the reference's on-disk format from ``docs`` = [{id,title,description}].
+    ``embed(texts) -> [n, dim] float32`` freezes the chunk embeddings (None: keyword tables only)."""
+    db_path = Path(db_path)
+    db_path.parent.mkdir(parents=True, exist_ok=True)
+    conn = sqlite3.connect(db_path)
+    try:
+        _init_schema(conn)
+        cur = conn.cursor()
+        cur.execute("DELETE FROM movies")
+        cur.executemany("INSERT INTO movies(id, title, description) VALUES (?, ?, ?)",
+                        [(int(d["id"]), d["title"], d["description"]) for d in docs])
+        conn.commit()
+        write_keyword_index(conn, docs, tokenizer)
+        if embed is not None:
+            movies = cur.execute("SELECT id, title, description FROM movies ORDER BY id").fetchall()
+            rows, texts = plan_chunks(movies, max_chunk_size, overlap)
+            cur.execute("DELETE FROM chunks")
+            cur.executemany("INSERT INTO chunks(id, movie_id, chunk_index, max_chunk_size, overlap) VALUES (?,?,?,?,?)", rows)
+            emb = np.asarray(embed(texts), np.float32)
+            write_vec0_shadow(conn, np.array([r[0] for r in rows], np.int64), emb)
+        conn.commit()
+    finally:
+        conn.close()
+    return db_path
