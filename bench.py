@@ -129,7 +129,7 @@ def config_dict(args, info, world):
             "mode": args.mode, "limit": args.limit, "knn_kprime": max(args.limit * 10, args.limit),
             "queries_per_step": args.batch, "movies": info["movies"], "chunks": info["chunks"], "dim": info["dim"],
             "bm25_postings": info["postings"], "bm25_terms": info["terms"],
-            "l2": "inputs larger than L2 (7.4 GB embedding stream per 8-query pass vs 126 MB L2); no flush",
+            "l2": "inputs larger than L2 (7.4 GB embedding stream per 16-query pass vs 126 MB L2); no flush",
             "parallelism": f"row-shard x{world} + all_gather(top-K') + query-slice BM25/fusion" if world > 1 else "1 GPU"}
 
 
@@ -325,7 +325,9 @@ def run_b200(args, rank, world, local_rank):
     rows_local = hi - lo
     alg_bytes = rows_local * ROW_BYTES
     achieved = alg_bytes / (scan_ms * 1e-3) / 1e9 if scan_ms > 0 else None
-    roofline = {"bound": "hbm", "kernel": "knn_scan384_kernel<QB=8> (one pass over the shard serves 8 queries)",
+    qb = 16 if nq >= 9 else (8 if nq >= 5 else (4 if nq >= 3 else nq))
+    roofline = {"bound": "hbm", "kernel": f"knn_scan384_kernel<QB={qb}> (one pass over the shard serves {qb} queries; "
+                                          f"FFMA2-pipe-bound above QB=4, HBM-bound at QB=1: see knn_batch1)",
                 "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": (achieved / peak) if achieved else None,
                 "peak_source": "MEASURED_PEAKS.json hbm_gbs (of measured)" if peaks else "fallback 6650 GB/s (of fallback)",
                 "traffic": None, "algorithmic_bytes_per_launch": alg_bytes, "avg_launch_ms": scan_ms,

@@ -30,13 +30,17 @@ VEC0_BLOCK = 1024
 
 
 def shard_bounds(n_rows: int, world: int) -> list[int]:
-    """Contiguous row ranges aligned to vec0 blocks: bounds[r] .. bounds[r+1]."""
+    """Contiguous row ranges aligned to vec0 blocks: rank r owns bounds[r] .. bounds[r+1].
+    Every interior bound is a multiple of 1024 (the library requires an aligned pos_base);
+    the trailing partial block belongs to the last non-empty range."""
     n_blocks = (n_rows + VEC0_BLOCK - 1) // VEC0_BLOCK
     per, rem = divmod(n_blocks, world)
+    floor_rows = (n_rows // VEC0_BLOCK) * VEC0_BLOCK
     bounds = [0]
+    blocks = 0
     for r in range(world):
-        nb = per + (1 if r < rem else 0)
-        bounds.append(min(n_rows, bounds[-1] + nb * VEC0_BLOCK))
+        blocks += per + (1 if r < rem else 0)
+        bounds.append(min(blocks * VEC0_BLOCK, floor_rows))
     bounds[-1] = n_rows
     return bounds
 
@@ -91,8 +95,10 @@ class ShardedHybrid:
         dev = self.backend.device
         cand = self.backend.knn_local(q_all, kprime)                                   # [nq, kp, 3]
         if self.world > 1:
-            gathered = torch.empty((self.world,) + tuple(cand.shape), dtype=cand.dtype, device=dev)
-            dist.all_gather_into_tensor(gathered, cand, group=self.group)              # the exchange step
+            # flat [world*nq, kp, 3] output (the layout every backend accepts), viewed as [world, nq, kp, 3]
+            flat = torch.empty((self.world * cand.shape[0],) + tuple(cand.shape[1:]), dtype=cand.dtype, device=dev)
+            dist.all_gather_into_tensor(flat, cand, group=self.group)                  # the exchange step
+            gathered = flat.view((self.world,) + tuple(cand.shape))
         else:
             gathered = cand.unsqueeze(0)
         ns = self.hi - self.lo
@@ -110,10 +116,12 @@ class ShardedHybrid:
             return HybridBatchResult(out_id[:ns], out_sc[:ns], out_a[:ns], out_b[:ns], out_c[:ns])
         # assemble the batch on every rank (small: nq·limit·32 B)
         packed = torch.cat([out_id.view(torch.float64), out_sc, out_a, out_b], dim=1)  # [pad, 4*limit] f64 bits
-        allp = torch.empty((self.world,) + tuple(packed.shape), dtype=packed.dtype, device=dev)
-        allc = torch.empty((self.world, pad), dtype=torch.int32, device=dev)
+        allp = torch.empty((self.world * pad, packed.shape[1]), dtype=packed.dtype, device=dev)
+        allc = torch.empty((self.world * pad,), dtype=torch.int32, device=dev)
         dist.all_gather_into_tensor(allp, packed, group=self.group)
         dist.all_gather_into_tensor(allc, out_c, group=self.group)
+        allp = allp.view(self.world, pad, packed.shape[1])
+        allc = allc.view(self.world, pad)
         rows = [allp[r, : self.slices[r + 1] - self.slices[r]] for r in range(self.world)]
         cnts = [allc[r, : self.slices[r + 1] - self.slices[r]] for r in range(self.world)]
         full = torch.cat(rows, 0)

@@ -1,0 +1,210 @@
+"""CPU tests of the host side: C-ABI library loads and exports every symbol include/rse.h declares
+(no compute), the SQLite exporter/writer round trip, the text helpers against the reference's own
+functions, the CPython-set emulation against the real set, and the oracle-stays-out-of-the-product rule."""
+import ctypes
+import random
+import re
+import sqlite3
+import subprocess
+from pathlib import Path
+
+import numpy as np
+import pytest
+
+from oracle import ref_import
+from helpers.corpus import build_postings, to_csr
+
+ROOT = Path(__file__).resolve().parents[1]
+
+
+# ----------------------------------------------------------------------------- C-ABI surface
+def test_library_exports_every_declared_symbol():
+    from rag_search_engine_b200 import _lib
+    header = (ROOT / "include" / "rse.h").read_text()
+    declared = set(re.findall(r"^\s*(?:int|void|const char \*)\s*\*?(rse_[a-z0-9_]+)\(", header, re.M))
+    assert len(declared) >= 25
+    L = _lib.load_library()                                   # dlopen works without a GPU
+    for name in declared:
+        assert hasattr(L, name), f"{name} declared in rse.h but not exported by librse.so"
+    assert declared == set(_lib.EXPORTED_SYMBOLS), declared ^ set(_lib.EXPORTED_SYMBOLS)
+    assert L.rse_abi_version() == 1
+
+
+def test_no_cpu_fallback_without_gpu():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    from rag_search_engine_b200 import _lib
+    with pytest.raises(_lib.RseError) as e:
+        _lib.Index(0)
+    assert "no CPU fallback" in str(e.value) or "CUDA" in str(e.value)
+
+
+def test_product_never_touches_the_oracle():
+    """Only tests/, __graft_entry__.smoke() and bench.py's baseline legs may import oracle/."""
+    for p in (ROOT / "rag_search_engine_b200").rglob("*"):
+        if p.suffix in (".py", ".cu", ".cuh", ".h"):
+            txt = p.read_text()
+            assert not re.search(r"^\s*(from|import)\s+oracle\b", txt, re.M), p
+            assert "liboracle" not in txt and "oracle/" not in txt.replace("oracle/make_golden", ""), p
+
+
+# ----------------------------------------------------------------------------- CPython set emulation
+@pytest.fixture(scope="module")
+def pyset_shim(tmp_path_factory):
+    so = tmp_path_factory.mktemp("shim") / "pyset_shim.so"
+    subprocess.run(["g++", "-O2", "-shared", "-fPIC", "-o", str(so), str(ROOT / "tests" / "helpers" / "pyset_shim.cpp")],
+                   check=True)
+    return ctypes.CDLL(str(so))
+
+
+def test_pyset_emulation_matches_cpython(pyset_shim):
+    P = ctypes.POINTER(ctypes.c_int64)
+
+    def emu(a, b):
+        A, B = np.array(a, np.int64), np.array(b, np.int64)
+        out = np.zeros(len(a) + len(b) + 1, np.int64)
+        n = pyset_shim.pyset_shim_union(A.ctypes.data_as(P), len(a), B.ctypes.data_as(P), len(b), out.ctypes.data_as(P))
+        return out[:n].tolist()
+
+    def real(a, b):
+        da, db = {x: None for x in a}, {x: None for x in b}
+        return list(set(da.keys()) | set(db.keys()))          # hybrid_search.py:148, :248
+
+    assert emu([9], [2]) == [9, 2] and emu([16, 3], [8, 1]) == [16, 8, 3, 1]
+    rnd = random.Random(1)
+    for _ in range(20000):
+        na, nb = rnd.randint(0, rnd.choice([3, 10, 40, 128])), rnd.randint(0, rnd.choice([3, 10, 40, 128]))
+        space = rnd.choice([16, 64, 1000, 10**6, 10**9, 2**40, 2**62])
+        lo = -space if rnd.random() < 0.1 else 0
+        a = list(dict.fromkeys(rnd.randrange(lo, space) for _ in range(na)))
+        b = list(dict.fromkeys((rnd.choice(a) if a and rnd.random() < 0.3 else rnd.randrange(lo, space))
+                               for _ in range(nb)))
+        assert emu(a, b) == real(a, b), (a, b)
+
+
+# ----------------------------------------------------------------------------- text helpers
+def test_window_chunks_known_shapes():
+    from rag_search_engine_b200.textutil import chunk_text, sentence_chunks, window_chunks
+    # rag_search_engine/tests/test_utils.py:100-109
+    ch = sentence_chunks("Sentence one. Sentence two! Sentence three?", 2, 1)
+    assert ch == [["Sentence one.", "Sentence two!"], ["Sentence two!", "Sentence three?"]]
+    # S sentences → 1 if S<=3 else 1+ceil((S-3)/2) chunks at (3, 1)
+    for S in range(1, 12):
+        text = " ".join(f"s{i}." for i in range(S))
+        assert len(sentence_chunks(text, 3, 1)) == (1 if S <= 3 else 1 + -(-(S - 3) // 2))
+    assert window_chunks(list("abcdefg"), 3, 0) == [list("abc"), list("def"), ["g"]]
+    assert chunk_text("T", "A. B. C. D.", 0, 3, 1) == "T"
+    assert chunk_text("T", "A. B. C. D.", 2, 3, 1) == "C.D."          # joined without separator (:182)
+    assert chunk_text("T", "A. B.", 5, 3, 1) == "A. B."                # out of range → description
+
+
+@pytest.mark.skipif(not ref_import.available(), reason="reference checkout not present (GPU box)")
+def test_text_helpers_match_reference():
+    _, _, ref_utils = ref_import.load()
+    from rag_search_engine_b200.textutil import sentence_chunks, window_chunks
+    rnd = random.Random(4)
+    for _ in range(400):
+        n = rnd.randint(0, 14)
+        items = [f"w{i}" for i in range(n)]
+        cs, ov = rnd.randint(1, 5), rnd.randint(0, 6)
+        assert window_chunks(items, cs, ov) == ref_utils.chunk(list(items), cs, ov)
+        text = " ".join(rnd.choice(["Alpha beta.", "What now?", "Go!", "no stop", "x. "]) for _ in range(n))
+        assert sentence_chunks(text, cs, ov) == ref_utils.semantic_chunk(text, cs, ov)
+
+
+# ----------------------------------------------------------------------------- SQLite exporter / writer
+def _docs(seed=3, n=60):
+    from oracle.make_golden import make_corpus
+    docs, words, weights = make_corpus(seed, n, 30)
+    for d in docs:                                            # sentence structure for the chunker
+        d["description"] = ". ".join(d["description"].split()[i] for i in range(min(7, len(d["description"].split())))) + "."
+    return docs, words, weights
+
+
+def test_export_bm25_round_trip_matches_reference_layout(tmp_path):
+    from rag_search_engine_b200 import store
+    from rag_search_engine_b200.textutil import whitespace_tokenizer
+    docs, _, _ = _docs()
+    db = store.write_reference_db(tmp_path / "m.db", docs, whitespace_tokenizer)
+    conn = sqlite3.connect(db)
+    arr = store.export_bm25(conn)
+    postings, doclen = build_postings(docs)
+    csr = to_csr(postings, doclen)
+    assert arr.n_movies == len(docs) and arr.avgdl == csr["avgdl"]
+    assert (arr.doc_ids == csr["doc_ids"]).all() and (arr.dl == csr["dl"]).all()
+    for term, row in csr["row"].items():
+        r = arr.term_row[term]
+        a = slice(arr.indptr[r], arr.indptr[r + 1]); b = slice(csr["indptr"][row], csr["indptr"][row + 1])
+        assert (arr.doc_idx[a] == csr["doc"][b]).all() and (arr.tf[a] == csr["tf"][b]).all()
+        assert arr.df[r] == csr["df"][row]
+    # a posting whose doc has no doclen row is counted in df (:222) but dropped from the CSR (:235-236)
+    tid = conn.execute("SELECT id FROM terms LIMIT 1").fetchone()[0]
+    conn.execute("INSERT INTO postings(term_id, doc_id, positions) VALUES (?, ?, ?)", (tid, 10**9, "[0, 1]"))
+    conn.commit()
+    arr2 = store.export_bm25(conn)
+    r = [v for k, v in arr2.term_row.items()][0]
+    assert arr2.df.sum() == arr.df.sum() + 1 and len(arr2.doc_idx) == len(arr.doc_idx)
+    conn.close()
+
+
+@pytest.mark.skipif(not ref_import.available(), reason="reference checkout not present (GPU box)")
+def test_writer_produces_the_tables_the_reference_build_produces(tmp_path):
+    import json
+    from rag_search_engine_b200 import store
+    from rag_search_engine_b200.textutil import whitespace_tokenizer
+    ref_kw, _, _ = ref_import.load()
+    docs, _, _ = _docs(5, 40)
+    p = tmp_path / "movies.json"
+    p.write_text(json.dumps({"movies": docs}))
+    ks = ref_kw.KeywordSearch.build_from_docs(docs_path=p, db_path=tmp_path / "ref.db", force=True)
+    ks.close()
+    store.write_reference_db(tmp_path / "ours.db", docs, whitespace_tokenizer)
+    a = store.export_bm25(sqlite3.connect(tmp_path / "ref.db"))
+    b = store.export_bm25(sqlite3.connect(tmp_path / "ours.db"))
+    assert a.n_movies == b.n_movies and a.avgdl == b.avgdl and (a.dl == b.dl).all() and (a.doc_ids == b.doc_ids).all()
+    assert set(a.term_row) == set(b.term_row)
+    for t in a.term_row:
+        ra, rb = a.term_row[t], b.term_row[t]
+        sa, sb = slice(a.indptr[ra], a.indptr[ra + 1]), slice(b.indptr[rb], b.indptr[rb + 1])
+        assert (a.doc_idx[sa] == b.doc_idx[sb]).all() and (a.tf[sa] == b.tf[sb]).all()
+
+
+def test_export_embeddings_physical_layout(tmp_path):
+    from rag_search_engine_b200 import store
+    from rag_search_engine_b200.textutil import whitespace_tokenizer
+    docs, _, _ = _docs(7, 300)                                # > 1024 chunks → 2+ vec0 blocks
+    rng = np.random.default_rng(0)
+
+    def embed(texts):
+        return rng.standard_normal((len(texts), 16)).astype(np.float32)
+
+    db = store.write_reference_db(tmp_path / "v.db", docs, whitespace_tokenizer, embed=embed)
+    conn = sqlite3.connect(db)
+    arr = store.export_embeddings(conn)
+    n_chunks = conn.execute("SELECT COUNT(*) FROM chunks").fetchone()[0]
+    assert arr.emb.shape == (n_chunks, 16) and arr.valid is None and n_chunks > 1024
+    assert (arr.rowid == np.arange(n_chunks)).all()           # fresh build: rowid i at position i (:164-206)
+    movie_of = dict(conn.execute("SELECT id, movie_id FROM chunks").fetchall())
+    assert [int(arr.movie_ids[m]) for m in arr.movie_idx] == [movie_of[i] for i in range(n_chunks)]
+    # punch holes (what a DELETE leaves behind) and orphan a chunk: export must flag them
+    blob = conn.execute("SELECT validity FROM chunk_embeddings_chunks WHERE chunk_id = 1").fetchone()[0]
+    bits = np.unpackbits(np.frombuffer(blob, np.uint8), bitorder="little"); bits[[5, 77]] = 0
+    conn.execute("UPDATE chunk_embeddings_chunks SET validity = ? WHERE chunk_id = 1",
+                 (np.packbits(bits, bitorder="little").tobytes(),))
+    conn.execute("DELETE FROM chunks WHERE id = 9")
+    conn.commit()
+    arr2 = store.export_embeddings(conn)
+    assert arr2.valid is not None and arr2.valid[5] == 0 and arr2.valid[77] == 0 and arr2.valid.sum() == n_chunks - 2
+    assert arr2.movie_idx[9] == -1 and arr2.movie_idx[5] == -1
+    conn.close()
+
+
+def test_shard_bounds_and_query_slices():
+    from rag_search_engine_b200.sharded import query_slices, shard_bounds
+    for n in (1, 1023, 1024, 1025, 4_799_462, 100_000_000):
+        for w in (1, 2, 3, 4, 8):
+            b = shard_bounds(n, w)
+            assert b[0] == 0 and b[-1] == n and len(b) == w + 1
+            assert all(x % 1024 == 0 for x in b[:-1]) and all(b[i] <= b[i + 1] for i in range(w))
+    assert query_slices(10, 4) == [0, 3, 6, 8, 10] and query_slices(2, 4) == [0, 1, 2, 2, 2]

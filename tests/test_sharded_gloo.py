@@ -1,0 +1,132 @@
+"""CPU, world_size 2, gloo: the N>1 host plumbing of rag_search_engine_b200.sharded (shard bounds,
+query slices, the candidate all_gather layout, per-slice merge+fuse, result assembly) with an
+oracle-backed stand-in for the per-rank librse calls.  The same ShardedHybrid object drives the
+real backend on the GPUs (bench.py --gpus N; tests/test_gpu_parity.py emulates the shards on one GPU)."""
+import os
+import socket
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+import oracle
+from oracle import pyref
+
+N_MOVIES, LIMIT, NQ = 500, 5, 7
+
+
+def _free_port():
+    s = socket.socket(); s.bind(("127.0.0.1", 0)); p = s.getsockname()[1]; s.close(); return p
+
+
+def _workload():
+    from rag_search_engine_b200 import synth
+    se = synth.synth_embeddings(N_MOVIES, seed=3, dim=32, device="cpu")
+    bm = synth.synth_bm25(N_MOVIES, 300, seed=3, mean_len=20, sd_len=6)
+    tok_indptr, terms = synth.synth_token_queries(bm, NQ, seed=4)
+    Q = synth.synth_query_vectors(se.emb, NQ, seed=4).numpy()
+    return se, bm, tok_indptr, terms, Q
+
+
+def _key(dist_f32, pos):
+    b = np.float32(dist_f32).view(np.uint32).astype(np.uint64)
+    ok = np.where(b & np.uint64(0x80000000), ~b & np.uint64(0xFFFFFFFF), b | np.uint64(0x80000000))
+    return ((ok << np.uint64(32)) | np.uint64(int(pos) ^ 1023)).astype(np.uint64).view(np.int64)
+
+
+class OracleBackend:
+    """Test stand-in for LibrseShardBackend: same protocol, CPU oracle inside."""
+
+    def __init__(self, se, bm, tok_indptr, terms, lo, hi):
+        self.device = torch.device("cpu")
+        self.emb = se.emb.numpy()[lo:hi]; self.movie_of = se.movie_of_chunk.numpy(); self.lo = lo
+        self.ids = se.movie_ids; self.bm = bm; self.tok_indptr = tok_indptr; self.terms = terms
+
+    def knn_local(self, q_all, kprime):
+        out = np.full((q_all.shape[0], kprime, 3), -1, np.int64)
+        for qi, q in enumerate(q_all.numpy()):
+            if len(self.emb) == 0:
+                continue
+            d, rows = oracle.vec0_knn(self.emb, q, kprime, pos=np.arange(self.lo, self.lo + len(self.emb), dtype=np.int64))
+            for j, (dd, r) in enumerate(zip(d, rows)):
+                g = self.lo + int(r)
+                out[qi, j] = (_key(dd, g), g, self.movie_of[g])
+        return torch.from_numpy(out)
+
+    def stage_slice(self, lo, hi):
+        self.slice = (lo, hi)
+
+    def fuse_merged(self, gathered, mode, param, limit, knn_multiplier):
+        lo, hi = self.slice
+        kp = max(limit * knn_multiplier, limit)
+        g = gathered.numpy()
+        ns = g.shape[1]
+        oid = np.full((ns, limit), -1, np.int64); osc = np.zeros((ns, limit)); oa = np.full((ns, limit), -1.0)
+        ob = np.full((ns, limit), -1.0); oc = np.zeros(ns, np.int32)
+        for s in range(ns):
+            cand = g[:, s].reshape(-1, 3)
+            cand = cand[cand[:, 0] != -1]
+            cand = cand[np.argsort(cand[:, 0].view(np.uint64), kind="stable")][:kp]
+            dist_bits = (cand[:, 0].view(np.uint64) >> np.uint64(32)).astype(np.uint32)
+            dd = np.where(dist_bits & 0x80000000, dist_bits & 0x7FFFFFFF, ~dist_bits).astype(np.uint32).view(np.float32)
+            sem = pyref.aggregate_movies([(int(c[1]), float(x), int(c[2])) for c, x in zip(cand, dd)], limit)
+            q = lo + s
+            tp = self.tok_indptr[q:q + 2] - self.tok_indptr[q]
+            sc, dc, cnt = oracle.bm25_batch(self.bm.indptr, self.bm.doc_idx, self.bm.tf, self.bm.df, self.bm.dl,
+                                            self.bm.n_movies, self.bm.avgdl, tp.astype(np.int32),
+                                            self.terms[self.tok_indptr[q]:self.tok_indptr[q + 1]], limit)
+            bmh = [(int(self.ids[dc[0, j]]), float(sc[0, j])) for j in range(cnt[0])]
+            semh = [(int(self.ids[m]), d) for _, d, m in sem]
+            res = pyref.rrf_fuse(bmh, semh, param, limit)
+            for j, r in enumerate(res):
+                oid[s, j] = r["id"]; osc[s, j] = r["score"]
+                oa[s, j] = -1 if r["bm25_rank"] is None else r["bm25_rank"]
+                ob[s, j] = -1 if r["sem_rank"] is None else r["sem_rank"]
+            oc[s] = len(res)
+        return tuple(torch.from_numpy(x) for x in (oid, osc, oa, ob, oc))
+
+
+def _worker(rank, world, port, out_q):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from rag_search_engine_b200 import sharded
+        se, bm, tok_indptr, terms, Q = _workload()
+        bounds = sharded.shard_bounds(se.emb.shape[0], world)
+        be = OracleBackend(se, bm, tok_indptr, terms, bounds[rank], bounds[rank + 1])
+        sh = sharded.ShardedHybrid(be, NQ)
+        r = sh.step(torch.from_numpy(Q), 0, 60.0, LIMIT)
+        out_q.put((rank, r.ids.numpy().copy(), r.score.numpy().copy(), r.count.numpy().copy()))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.timeout(300)
+def test_sharded_hybrid_two_ranks_gloo_equals_single_process():
+    world = 2
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    got = [q.get(timeout=240) for _ in range(world)]
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    # single-process ground truth
+    se, bm, tok_indptr, terms, Q = _workload()
+    emb, movie_of, ids = se.emb.numpy(), se.movie_of_chunk.numpy(), se.movie_ids
+    kd, krow, kc = oracle.knn_movies_batch(emb, Q, movie_of, LIMIT, LIMIT * 10)
+    sc, dc, cnt = oracle.bm25_batch(bm.indptr, bm.doc_idx, bm.tf, bm.df, bm.dl, bm.n_movies, bm.avgdl, tok_indptr, terms, LIMIT)
+    for rank, gid, gsc, gc in got:                       # every rank holds the whole fused batch
+        assert gid.shape == (NQ, LIMIT)
+        for qi in range(NQ):
+            bmh = [(int(ids[dc[qi, j]]), float(sc[qi, j])) for j in range(cnt[qi])]
+            semh = [(int(ids[movie_of[krow[qi, j]]]), float(kd[qi, j])) for j in range(kc[qi])]
+            want = pyref.rrf_fuse(bmh, semh, 60.0, LIMIT)
+            assert gc[qi] == len(want)
+            assert gid[qi, :gc[qi]].tolist() == [w["id"] for w in want]
+            assert gsc[qi, :gc[qi]].tolist() == [w["score"] for w in want]
