@@ -88,6 +88,10 @@ int rse_attach_embeddings_dev(rse_index *h, const float *emb_dev, int64_t n_rows
                               const uint8_t *valid_dev, const int64_t *rowid_dev,
                               const int32_t *movie_idx_dev, int64_t pos_base);
 int rse_set_fma(rse_index *h, int32_t use_fma);
+/* K4, the tcgen05 TF32 path for large query batches (probe → filter → EXACT re-score, results
+ * identical to the streaming scan): 0 = auto (batches of ≥ 48 queries on ≥ 256 k rows, dim 384),
+ * 1 = never, 2 = whenever the shape allows it. */
+int rse_set_tc_mode(rse_index *h, int32_t mode);
 
 /* KNN: `embedding MATCH :q AND k = :k ... ORDER BY knn.distance`
  * (semantic_search.py:254-279).  Q is [nq, dim] fp32.  Outputs are [nq, kprime]
@@ -212,6 +216,9 @@ typedef struct rse_stats {
   int32_t emb_dim;
   int64_t bm25_postings;
   int64_t bm25_docs;
+  int64_t tc_filter_launches;   /* K4 tensor-core filter passes (each serves ≤ 256 queries) */
+  int64_t tc_queries;           /* queries answered through K4 */
+  int64_t tc_fallback_queries;  /* of those, re-run through the exact scan (survivor overflow) */
 } rse_stats;
 int rse_get_stats(rse_index *h, rse_stats *out);
 int rse_stats_reset(rse_index *h);

@@ -43,6 +43,9 @@ class RseStats(ctypes.Structure):
         ("emb_dim", c_int32),
         ("bm25_postings", c_int64),
         ("bm25_docs", c_int64),
+        ("tc_filter_launches", c_int64),
+        ("tc_queries", c_int64),
+        ("tc_fallback_queries", c_int64),
     ]
 
 
@@ -59,6 +62,7 @@ _SIGNATURES = {
     "rse_attach_embeddings_dev": (ctypes.c_int, [c_void_p, c_void_p, c_int64, c_int32, c_void_p, c_void_p,
                                                  c_void_p, c_int64]),
     "rse_set_fma": (ctypes.c_int, [c_void_p, c_int32]),
+    "rse_set_tc_mode": (ctypes.c_int, [c_void_p, c_int32]),
     "rse_knn": (ctypes.c_int, [c_void_p, POINTER(c_float), c_int32, c_int32, POINTER(c_float), POINTER(c_int64),
                                POINTER(c_int64), POINTER(c_int32), POINTER(c_int32)]),
     "rse_knn_movies": (ctypes.c_int, [c_void_p, POINTER(c_float), c_int32, c_int32, c_int32, POINTER(c_float),
@@ -170,6 +174,10 @@ class Index:
 
     def set_timing(self, on: bool):
         self._check(self._L.rse_set_timing(self._h, int(bool(on))))
+
+    def set_tc_mode(self, mode: int):
+        """0 = auto, 1 = exact scan only, 2 = tensor-core path whenever the shape allows it."""
+        self._check(self._L.rse_set_tc_mode(self._h, int(mode)))
 
     def set_fma(self, on: bool):
         self._check(self._L.rse_set_fma(self._h, int(bool(on))))

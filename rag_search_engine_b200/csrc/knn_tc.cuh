@@ -1,0 +1,387 @@
+// knn_tc.cuh — K4: tensor-core path for LARGE query batches, with exact re-score.
+//
+// Same reference computation as K1 (vec0 cosine KNN, semantic_search.py:254-261); this path
+// exists because the exact lane-per-row scan is FP32-pipe-bound beyond ~16 queries per pass.
+// It NEVER decides a result on approximate numbers:
+//
+//   1. probe   : TF32 tcgen05 GEMM over a strided sample of 128-row tiles, epilogue stores the
+//                approximate distances d~ of the sample; the existing radix select gives each
+//                query the K'-th smallest sample d~ (tau_s).
+//   2. filter  : the same GEMM over ALL rows; epilogue keeps row r for query q iff
+//                  cos~(q, r) >= 1 - tau_s - 2*eps,
+//                where eps bounds |d~ - d_exact| (TF32 operand truncation, eps = 2.5e-3 > 2^-9;
+//                see DESIGN.md §5).  Every row of the exact top-K' passes:
+//                  d_K' <= (K'-th exact d in the sample) <= tau_s + eps, and d~ <= d + eps.
+//   3. re-score: the survivors are gathered by TMA and re-computed with the EXACT sequential
+//                fp32 arithmetic of K1 (same code path: mac<FMA>, cosine_tail), keyed with the
+//                vec0 emit-order key.
+//   4. finish  : per query, sort the exact keys, keep K' → the same packed candidates K1+K2 emit.
+//   A query whose survivor list overflows is flagged and re-run through K1/K2 by the host.
+//
+// GEMM mapping: D[128 rows x 256 queries] per tile, K = 384 in 12 k-blocks of 32 floats (one
+// 128-byte swizzle atom).  Warp-specialised: warp 0 = TMA producer (cp.async.bulk.tensor, 4-stage
+// mbarrier ring, 48 KB/stage: 16 KB of rows + 32 KB of queries), warp 1 = single-thread
+// tcgen05.mma.kind::tf32 issuer (UMMA 128x256x8, accumulators in TMEM, double-buffered:
+// 2 x 256 columns), warps 2-5 = epilogue (tcgen05.ld 32x32b, one TMEM lane = one row per thread).
+// Persistent, one CTA per SM.
+#pragma once
+#include <cuda.h>
+
+#include "common.cuh"
+#include "knn_scan.cuh"
+
+namespace rse {
+
+constexpr int kTcBM = 128;
+constexpr int kTcBN = 256;
+constexpr int kTcBK = 32;
+constexpr int kTcStages = 4;
+constexpr int kTcKBlocks = kScanD / kTcBK;                 // 12
+constexpr int kTcStageA = kTcBM * kTcBK * 4;               // 16,384
+constexpr int kTcStageB = kTcBN * kTcBK * 4;               // 32,768
+constexpr int kTcStageBytes = kTcStageA + kTcStageB;       // 49,152
+constexpr int kTcThreads = 192;                            // 6 warps
+constexpr int kTcSmemBytes = kTcStages * kTcStageBytes + 2 * kTcBN * 4 + 16 * 8 + 16 + 1024;
+constexpr float kTcEps = 2.5e-3f;                          // bound on |d~ - d| (see header)
+constexpr int kTcCandCap = 8192;                           // survivors kept per query
+
+// UMMA instruction descriptor, kind::tf32, D=f32, A/B K-major, M=128, N=256
+constexpr uint32_t kTcIdesc = (1u << 4) | (2u << 7) | (2u << 10) | ((kTcBN >> 3) << 17) | ((kTcBM >> 4) << 24);
+
+// ---------------------------------------------------------------- PTX wrappers
+__device__ __forceinline__ void tma_load_2d(void* smem_dst, const CUtensorMap* tmap, int c0, int c1, uint64_t* bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::
+          "r"(smem_u32(smem_dst)),
+      "l"(tmap), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
+               : "memory");
+}
+__device__ __forceinline__ void tc_mma_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
+                                            uint32_t accumulate) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "setp.ne.b32 p, %4, 0;\n"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n"
+      "}\n" ::"r"(tmem_d),
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+// K-major, SWIZZLE_128B shared-memory matrix descriptor (rows of 128 B, 8-row groups of 1024 B)
+__device__ __forceinline__ uint64_t tc_smem_desc(uint32_t smem_addr) {
+  uint64_t d = 0;
+  d |= static_cast<uint64_t>((smem_addr & 0x3FFFFu) >> 4);          // start address, bits [0,14)
+  d |= static_cast<uint64_t>(1) << 16;                              // LBO (unused for swizzled K-major) = 1
+  d |= static_cast<uint64_t>(1024 >> 4) << 32;                      // SBO = 1024 B
+  d |= static_cast<uint64_t>(1) << 46;                              // descriptor version (sm_100)
+  d |= static_cast<uint64_t>(2) << 61;                              // SWIZZLE_128B
+  return d;
+}
+__device__ __forceinline__ void tc_ld32(uint32_t taddr, uint32_t (&v)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];\n"
+      "tcgen05.wait::ld.sync.aligned;\n"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+        "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]),
+        "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]),
+        "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+      : "r"(taddr)
+      : "memory");
+}
+
+// ---------------------------------------------------------------- per-query constants
+// inv_sb[q] = 1/||q|| (f32); used by the probe epilogue to turn cos~ into d~.
+__global__ void tc_query_consts_kernel(const double* __restrict__ sb, int nq, float* __restrict__ inv_sb) {
+  int q = blockIdx.x * blockDim.x + threadIdx.x;
+  if (q >= kTcBN) return;
+  inv_sb[q] = (q < nq && sb[q] > 0.0) ? static_cast<float>(1.0 / sb[q]) : 0.0f;
+}
+
+// thr[q] = (1 - tau_s - 2 eps) * ||q||   (compared against dot~ / ||a||), +inf for padding columns
+// or when the sample gave no bound.  tau_s = K'-th smallest sample d~ from the radix-select state:
+// resolved bits of the prefix, unresolved low bits set (an upper bound of the bucket).
+__global__ void tc_threshold_kernel(const SelState* __restrict__ st, const double* __restrict__ sb, int nq,
+                                    unsigned int kprime, float* __restrict__ thr) {
+  int q = blockIdx.x * blockDim.x + threadIdx.x;
+  if (q >= kTcBN) return;
+  float t = __int_as_float(0x7F800000);   // +inf → nothing passes
+  if (q < nq) {
+    const SelState s = st[q];
+    const unsigned long long hi_mask = s.mask >> 32, hi_pref = s.prefix >> 32;
+    if (s.mask == 0ull) {
+      t = -__int_as_float(0x7F800000);    // fewer than K' sample rows: keep everything (host avoids this case)
+    } else {
+      const uint32_t okey = static_cast<uint32_t>(hi_pref | (~hi_mask & 0xFFFFFFFFull));
+      const float tau = __uint_as_float(f32_from_orderable(okey));
+      const float cut = 1.0f - tau - 2.0f * kTcEps - 1e-6f;
+      t = cut * static_cast<float>(sb[q]);
+      if (cut < 0.0f) t = cut * static_cast<float>(sb[q]) * 1.0001f - 1e-30f;
+    }
+  }
+  thr[q] = t;
+}
+
+// ---------------------------------------------------------------- the GEMM
+// MODE 0 (probe) : tiles t = 0..n_tiles-1 map to row tile t*tile_stride; d~ stored to
+//                  dist[q*ld + t*128 + r] (empty vec0 slots get the invalid sentinel).
+// MODE 1 (filter): all row tiles; survivors appended to cand_rows[q*cap + slot] (local row).
+template <int MODE>
+__global__ void __launch_bounds__(kTcThreads, 1)
+knn_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_q,
+              const float* __restrict__ amag, int64_t n_rows, int64_t n_tiles, int64_t tile_stride, int nq,
+              const float* __restrict__ thr, const float* __restrict__ inv_sb, uint32_t* __restrict__ dist,
+              int64_t ld, uint32_t* __restrict__ cand_rows, unsigned int* __restrict__ cand_count, int cap) {
+  extern __shared__ unsigned char smem_raw[];
+  const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  unsigned char* smem = smem_raw + (base - smem_u32(smem_raw));
+  float* s_thr = reinterpret_cast<float*>(smem + kTcStages * kTcStageBytes);
+  float* s_isb = s_thr + kTcBN;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(s_isb + kTcBN);
+  uint64_t* full = bars;                       // [kTcStages]
+  uint64_t* empty = bars + kTcStages;          // [kTcStages]
+  uint64_t* tfull = bars + 2 * kTcStages;      // [2]
+  uint64_t* tempty = bars + 2 * kTcStages + 2; // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * kTcStages + 4);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  for (int i = threadIdx.x; i < kTcBN; i += blockDim.x) {
+    s_thr[i] = (MODE == 1) ? thr[i] : 0.0f;
+    s_isb[i] = (MODE == 0) ? inv_sb[i] : 0.0f;
+  }
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < kTcStages; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
+    for (int b = 0; b < 2; ++b) { mbar_init(&tfull[b], 1); mbar_init(&tempty[b], 4); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 0) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
+                 "r"(512u)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    if (lane == 0) {
+      asm volatile("prefetch.tensormap [%0];" ::"l"(&tmap_a) : "memory");
+      asm volatile("prefetch.tensormap [%0];" ::"l"(&tmap_q) : "memory");
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int64_t t = blockIdx.x; t < n_tiles; t += gridDim.x) {
+        const int row0 = static_cast<int>(t * tile_stride * kTcBM);
+        for (int kb = 0; kb < kTcKBlocks; ++kb) {
+          mbar_wait(&empty[stage], phase ^ 1u);
+          mbar_arrive_expect_tx(&full[stage], kTcStageBytes);
+          unsigned char* sa = smem + stage * kTcStageBytes;
+          tma_load_2d(sa, &tmap_a, kb * kTcBK, row0, &full[stage]);
+          tma_load_2d(sa + kTcStageA, &tmap_q, kb * kTcBK, 0, &full[stage]);
+          if (++stage == kTcStages) { stage = 0; phase ^= 1u; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer =====================
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      int it = 0;
+      for (int64_t t = blockIdx.x; t < n_tiles; t += gridDim.x, ++it) {
+        const int buf = it & 1;
+        const uint32_t use = static_cast<uint32_t>(it >> 1);
+        mbar_wait(&tempty[buf], (use & 1u) ^ 1u);         // epilogue drained this accumulator
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(buf * kTcBN);
+        for (int kb = 0; kb < kTcKBlocks; ++kb) {
+          mbar_wait(&full[stage], phase);
+          tc_fence_after();
+          const uint32_t a_addr = base + stage * kTcStageBytes;
+          const uint64_t adesc = tc_smem_desc(a_addr);
+          const uint64_t bdesc = tc_smem_desc(a_addr + kTcStageA);
+#pragma unroll
+          for (int k = 0; k < kTcBK / 8; ++k) {
+            // advance 8 tf32 = 32 B inside the swizzle atom: +2 in the (>>4) start-address field
+            tc_mma_tf32(d_tmem, adesc + static_cast<uint64_t>(2 * k), bdesc + static_cast<uint64_t>(2 * k), kTcIdesc,
+                        (kb | k) != 0 ? 1u : 0u);
+          }
+          tc_commit(&empty[stage]);                       // smem slot free once these MMAs retire
+          if (++stage == kTcStages) { stage = 0; phase ^= 1u; }
+        }
+        tc_commit(&tfull[buf]);                           // accumulator complete
+      }
+    }
+  } else {
+    // ===================== epilogue (warps 2..5) =====================
+    const int quarter = warp & 3;                         // TMEM lanes [32*quarter, +32) belong to this warp
+    int it = 0;
+    for (int64_t t = blockIdx.x; t < n_tiles; t += gridDim.x, ++it) {
+      const int buf = it & 1;
+      const uint32_t use = static_cast<uint32_t>(it >> 1);
+      const int64_t row = t * tile_stride * kTcBM + quarter * 32 + lane;
+      const bool in_range = row < n_rows;
+      const float am = in_range ? __ldg(amag + row) : -1.0f;
+      const bool valid = am > 0.0f;
+      const float inv_sa = valid ? rsqrtf(am) : 0.0f;
+      mbar_wait(&tfull[buf], use & 1u);
+      tc_fence_after();
+      const uint32_t taddr0 = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + static_cast<uint32_t>(buf * kTcBN);
+      const int ncol = (MODE == 0) ? ((nq + 31) & ~31) : kTcBN;
+      for (int c0 = 0; c0 < ncol; c0 += 32) {
+        uint32_t v[32];
+        tc_ld32(taddr0 + static_cast<uint32_t>(c0), v);
+        if (MODE == 0) {
+          const int64_t orow = t * kTcBM + quarter * 32 + lane;
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            const int q = c0 + j;
+            if (q < nq) {
+              uint32_t bits = 0x7FFFFFFFu;                // invalid sentinel (empty slot / past the end)
+              if (valid) bits = __float_as_uint(1.0f - __uint_as_float(v[j]) * inv_sa * s_isb[q]);
+              dist[static_cast<int64_t>(q) * ld + orow] = bits;
+            }
+          }
+        } else {
+          if (valid) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+              const float s = __uint_as_float(v[j]) * inv_sa;
+              if (s >= s_thr[c0 + j]) {
+                const int q = c0 + j;
+                const unsigned int slot = atomicAdd(&cand_count[q], 1u);
+                if (slot < static_cast<unsigned int>(cap))
+                  cand_rows[static_cast<int64_t>(q) * cap + slot] = static_cast<uint32_t>(row);
+              }
+            }
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tempty[buf]);
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
+  }
+}
+
+// ---------------------------------------------------------------- exact re-score of the survivors
+// One warp = 32 survivors of ONE query, lane-per-row like K1: TMA-gathers the rows into the padded
+// stage, runs the reference's sequential sum, emits the vec0 emit-order key.  grid = (ceil(cap/128), nq).
+template <bool FMA>
+__global__ void __launch_bounds__(kScanWarps * 32, 1)
+knn_rescore_kernel(const float* __restrict__ emb, const float* __restrict__ amag, const float* __restrict__ q,
+                   const double* __restrict__ sb, const uint32_t* __restrict__ cand_rows,
+                   const unsigned int* __restrict__ cand_count, int cap, uint64_t pos_base,
+                   unsigned long long* __restrict__ cand_keys) {
+  extern __shared__ __align__(128) unsigned char smem[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int qi = blockIdx.y;
+  unsigned int n = cand_count[qi];
+  if (n > static_cast<unsigned int>(cap)) n = cap;
+  const unsigned int i0 = (blockIdx.x * kScanWarps + warp) * 32;
+  float* qs = reinterpret_cast<float*>(smem + kScanWarps * kScanStageBytes);
+  uint64_t* bar = reinterpret_cast<uint64_t*>(smem + kScanWarps * kScanStageBytes + kScanD * 4) + warp;
+  if (blockIdx.x * kScanWarps * 32 >= n) return;           // whole CTA idle (uniform)
+  for (int i = threadIdx.x; i < kScanD; i += blockDim.x) qs[i] = q[static_cast<int64_t>(qi) * kScanD + i];
+  if (lane == 0) mbar_init(bar, 1);
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  __syncthreads();
+  if (i0 >= n) return;
+  float* stage = reinterpret_cast<float*>(smem + warp * kScanStageBytes);
+  const unsigned int nvalid = (n - i0 < 32u) ? (n - i0) : 32u;
+  const bool have = lane < static_cast<int>(nvalid);
+  const uint32_t row = have ? cand_rows[static_cast<int64_t>(qi) * cap + i0 + lane] : 0u;
+  if (lane == 0) mbar_arrive_expect_tx(bar, nvalid * (kScanD * 4));
+  __syncwarp();
+  if (have) bulk_g2s(stage + lane * kScanRowStride, emb + static_cast<int64_t>(row) * kScanD, kScanD * 4, bar);
+  const float am = have ? __ldg(amag + row) : 1.0f;
+  mbar_wait(bar, 0);
+  const float4* rowp = reinterpret_cast<const float4*>(stage + lane * kScanRowStride);
+  const float4* qp = reinterpret_cast<const float4*>(qs);
+  float acc = 0.0f;
+#pragma unroll 4
+  for (int c = 0; c < kScanD / 4; ++c) {
+    const float4 a = rowp[c];
+    const float4 b = qp[c];
+    acc = mac<FMA>(acc, a.x, b.x);
+    acc = mac<FMA>(acc, a.y, b.y);
+    acc = mac<FMA>(acc, a.z, b.z);
+    acc = mac<FMA>(acc, a.w, b.w);
+  }
+  if (have) {
+    const float d = cosine_tail(acc, sqrt(static_cast<double>(am)), sb[qi]);
+    cand_keys[static_cast<int64_t>(qi) * cap + i0 + lane] =
+        knn_key(f32_orderable(__float_as_uint(d)), pos_base + static_cast<uint64_t>(row));
+  }
+}
+
+// ---------------------------------------------------------------- finish: sort exact keys, keep K'
+// One CTA per query; smem = cap2 * 8 bytes.  Queries whose survivor list overflowed get
+// status[q] = 1 and an empty result (the host re-runs them through the exact scan).
+__global__ void __launch_bounds__(kSelThreads)
+knn_cand_finish_kernel(const unsigned long long* __restrict__ cand_keys, const unsigned int* __restrict__ cand_count,
+                       int cap, int kprime, uint64_t pos_base, const int64_t* __restrict__ rowid,
+                       const int32_t* __restrict__ movie_idx, long long* __restrict__ cand, int* __restrict__ status) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  unsigned long long* keys = reinterpret_cast<unsigned long long*>(smem_raw);
+  const int q = blockIdx.x;
+  const unsigned int cnt = cand_count[q];
+  const bool overflow = cnt > static_cast<unsigned int>(cap);
+  const int n = overflow ? 0 : static_cast<int>(cnt);
+  if (threadIdx.x == 0) status[q] = overflow ? 1 : 0;
+  int n2 = 1;
+  while (n2 < n) n2 <<= 1;
+  if (n2 < 2) n2 = 2;
+  for (int i = threadIdx.x; i < n2; i += blockDim.x)
+    keys[i] = (i < n) ? cand_keys[static_cast<int64_t>(q) * cap + i] : ~0ull;
+  // keys-only bitonic sort
+  for (int size = 2; size <= n2; size <<= 1) {
+    for (int stride = size >> 1; stride > 0; stride >>= 1) {
+      __syncthreads();
+      for (int t = threadIdx.x; t < (n2 >> 1); t += blockDim.x) {
+        const int lo = 2 * t - (t & (stride - 1));
+        const int hi = lo + stride;
+        const bool up = ((lo & size) == 0);
+        const unsigned long long a = keys[lo], b = keys[hi];
+        if ((a > b) == up) { keys[lo] = b; keys[hi] = a; }
+      }
+    }
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < kprime; i += blockDim.x) {
+    long long* c = cand + (static_cast<int64_t>(q) * kprime + i) * 3;
+    if (i < n) {
+      const uint64_t key = keys[i];
+      const uint64_t pos = knn_key_pos(key);
+      const int64_t local = static_cast<int64_t>(pos - pos_base);
+      c[0] = static_cast<long long>(key);
+      c[1] = rowid ? rowid[local] : static_cast<long long>(pos);
+      c[2] = movie_idx ? movie_idx[local] : -1;
+    } else {
+      c[0] = -1ll; c[1] = -1ll; c[2] = -1ll;
+    }
+  }
+}
+
+}  // namespace rse

@@ -16,6 +16,7 @@
 #include "fusion.cuh"
 #include "knn_scan.cuh"
 #include "select.cuh"
+#include "knn_tc.cuh"
 
 using namespace rse;
 
@@ -45,6 +46,13 @@ struct rse_index {
   size_t scan_ev_used = 0;
   // staged hybrid query batch (rse_hybrid_stage)
   int staged_nq = 0;
+  // K4 tensor-core path
+  int tc_mode = 0;                 // 0 auto, 1 off (exact scan only), 2 force on
+  CUtensorMap tmap_a{};            // [n_rows][384] f32, box {32, 128}, SWIZZLE_128B
+  bool tmap_a_ok = false;
+  CUtensorMap tmap_q{};            // [256][384]
+  bool tmap_q_ok = false;
+  DevBuf tc_q, tc_thr, tc_isb, tc_rows, tc_cnt, tc_keys, tc_status;
 
   // ---- a1: embeddings (vec0 physical layout)
   const float* emb = nullptr;
@@ -138,6 +146,7 @@ void release_embeddings(rse_index* h) {
   free_ptr(h->rowid);
   free_ptr(h->movie_idx);
   h->n_rows = 0; h->dim = 0;
+  h->tmap_a_ok = false;
 }
 
 void release_bm25(rse_index* h) {
@@ -186,39 +195,22 @@ int launch_scan(rse_index* h, const float* q, const double* sb, int nq, float* d
   return RSE_OK;
 }
 
-// Local top-kprime for nq device-resident queries → packed candidates (device).
-int knn_local(rse_index* h, const float* q_dev, int nq, int kprime, long long* cand_dev) {
-  if (!h->emb) return fail(h, RSE_ERR_STATE, "rse_knn: no embeddings loaded");
-  if (nq <= 0) return RSE_OK;
-  if (kprime < 1 || kprime > RSE_MAX_KPRIME)
-    return fail(h, RSE_ERR_UNSUPPORTED, "rse_knn: kprime must be in [1, 4096] (sqlite-vec caps k at 4096)");
+// ---- exact path (K1 + K2 + K3) for queries [0, nq) whose |q| factors sb[] are ready
+int knn_exact_groups(rse_index* h, const float* q_dev, const double* sb, int nq, int kprime, long long* cand_dev) {
   const int QB = kScanMaxQB;
-  ENSURE(h->sb, sizeof(double) * nq);
-  ENSURE(h->sel, sizeof(SelState) * nq);
-  if (h->hist.bytes < sizeof(unsigned int) * kSelBins * QB) {
-    ENSURE(h->hist, sizeof(unsigned int) * kSelBins * QB);
-    CK(cudaMemsetAsync(h->hist.p, 0, h->hist.bytes, h->stream));
-  }
+  ENSURE(h->sel, sizeof(SelState) * std::max(nq, kTcBN));
   ENSURE(h->selkeys, sizeof(unsigned long long) * static_cast<size_t>(nq) * kprime);
   ENSURE(h->dist, sizeof(float) * static_cast<size_t>(QB) * h->dist_ld);
-
-  double* sb = static_cast<double*>(h->sb.p);
   SelState* sel = static_cast<SelState*>(h->sel.p);
   unsigned int* hist = static_cast<unsigned int*>(h->hist.p);
   unsigned long long* selkeys = static_cast<unsigned long long*>(h->selkeys.p);
   float* dist = static_cast<float*>(h->dist.p);
-
-  if (h->fma) knn_query_prep_kernel<true><<<(nq + 127) / 128, 128, 0, h->stream>>>(q_dev, nq, h->dim, sb);
-  else knn_query_prep_kernel<false><<<(nq + 127) / 128, 128, 0, h->stream>>>(q_dev, nq, h->dim, sb);
-  LAUNCHED(h);
   select_init_kernel<<<(nq + 127) / 128, 128, 0, h->stream>>>(sel, nq, static_cast<unsigned int>(kprime));
   LAUNCHED(h);
-
   static const int shifts[6] = {53, 42, 32, 21, 10, 0};
   static const int widths[6] = {11, 11, 10, 11, 11, 10};
   int sel_blocks = static_cast<int>(std::min<int64_t>((h->n_rows + 4095) / 4096, h->sm_count * 2));
   if (sel_blocks < 1) sel_blocks = 1;
-
   for (int g0 = 0; g0 < nq; g0 += QB) {
     const int ng = std::min(QB, nq - g0);
     cudaEvent_t e0 = nullptr, e1 = nullptr;
@@ -249,16 +241,200 @@ int knn_local(rse_index* h, const float* q_dev, int nq, int kprime, long long* c
   }
   const int kp2 = next_pow2(kprime);
   const size_t fsmem = static_cast<size_t>(kp2) * 12;
-  if (fsmem > 48 * 1024) {
-    static bool set = false;
-    if (!set) {
-      CK(cudaFuncSetAttribute(select_finish_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
-      set = true;
-    }
-  }
+  if (fsmem > 48 * 1024) CK(cudaFuncSetAttribute(select_finish_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
   select_finish_kernel<<<nq, kSelThreads, fsmem, h->stream>>>(selkeys, sel, kprime, kp2, h->pos_base, h->rowid,
                                                              h->movie_idx, cand_dev);
   LAUNCHED(h);
+  return RSE_OK;
+}
+
+// ---- K4: tensor-core path for one block of ≤ 256 queries (see knn_tc.cuh)
+typedef CUresult (*PFN_tmapEncodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                        const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                        CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+int make_tmap(rse_index* h, CUtensorMap* out, const float* base, int64_t rows, int box_rows) {
+  static PFN_tmapEncodeTiled fn = nullptr;
+  if (!fn) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    CK(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres));
+    if (!p || qres != cudaDriverEntryPointSuccess) return fail(h, RSE_ERR_CUDA, "cuTensorMapEncodeTiled unavailable");
+    fn = reinterpret_cast<PFN_tmapEncodeTiled>(p);
+  }
+  const cuuint64_t gdim[2] = {static_cast<cuuint64_t>(kScanD), static_cast<cuuint64_t>(rows)};
+  const cuuint64_t gstr[1] = {static_cast<cuuint64_t>(kScanD) * 4};
+  const cuuint32_t box[2] = {static_cast<cuuint32_t>(kTcBK), static_cast<cuuint32_t>(box_rows)};
+  const cuuint32_t estr[2] = {1, 1};
+  CUresult r = fn(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(base), gdim, gstr, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return fail(h, RSE_ERR_CUDA, "cuTensorMapEncodeTiled failed: " + std::to_string(static_cast<int>(r)));
+  return RSE_OK;
+}
+
+bool tc_eligible(const rse_index* h, int nq, int kprime) {
+  if (h->tc_mode == 1 || h->dim != kScanD) return false;
+  const int64_t n_tiles = (h->n_rows + kTcBM - 1) / kTcBM;
+  if (n_tiles * kTcBM < 8ll * kprime || h->n_rows < 1024) return false;   // the probe needs a usable sample
+  if (kprime * 4 > kTcCandCap) return false;
+  if (h->tc_mode == 2) return true;
+  return nq >= 48 && h->n_rows >= 262144;
+}
+
+int knn_tc_block(rse_index* h, const float* q_dev, const double* sb, int nqb, int kprime, long long* cand_dev,
+                 int* status_dev) {
+  static bool attrs = false;
+  if (!attrs) {
+    CK(cudaFuncSetAttribute(knn_tc_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, kTcSmemBytes));
+    CK(cudaFuncSetAttribute(knn_tc_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, kTcSmemBytes));
+    CK(cudaFuncSetAttribute(knn_rescore_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, scan_smem_bytes(1)));
+    CK(cudaFuncSetAttribute(knn_rescore_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, scan_smem_bytes(1)));
+    CK(cudaFuncSetAttribute(knn_cand_finish_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kTcCandCap * 8));
+    attrs = true;
+  }
+  if (!h->tmap_a_ok) {
+    int rc = make_tmap(h, &h->tmap_a, h->emb, h->n_rows, kTcBM);
+    if (rc != RSE_OK) return rc;
+    h->tmap_a_ok = true;
+  }
+  ENSURE(h->tc_q, sizeof(float) * kTcBN * kScanD);
+  if (!h->tmap_q_ok) {
+    int rc = make_tmap(h, &h->tmap_q, static_cast<const float*>(h->tc_q.p), kTcBN, kTcBN);
+    if (rc != RSE_OK) return rc;
+    h->tmap_q_ok = true;
+  }
+  ENSURE(h->tc_thr, sizeof(float) * kTcBN);
+  ENSURE(h->tc_isb, sizeof(float) * kTcBN);
+  ENSURE(h->tc_rows, sizeof(uint32_t) * static_cast<size_t>(kTcBN) * kTcCandCap);
+  ENSURE(h->tc_keys, sizeof(unsigned long long) * static_cast<size_t>(kTcBN) * kTcCandCap);
+  ENSURE(h->tc_cnt, sizeof(unsigned int) * kTcBN);
+  ENSURE(h->sel, sizeof(SelState) * kTcBN);
+
+  const int64_t n_tiles = (h->n_rows + kTcBM - 1) / kTcBM;
+  const int64_t target = static_cast<int64_t>(h->sm_count) * 8;               // ≈1184 sample tiles ≈ 150 k rows
+  int64_t tile_stride = std::max<int64_t>(1, n_tiles / target);
+  int64_t n_probe = (n_tiles + tile_stride - 1) / tile_stride;
+  while (n_probe * kTcBM < 8ll * kprime && tile_stride > 1) { tile_stride /= 2; n_probe = (n_tiles + tile_stride - 1) / tile_stride; }
+  const int64_t ld_probe = n_probe * kTcBM;
+  ENSURE(h->dist, std::max(sizeof(float) * static_cast<size_t>(kScanMaxQB) * h->dist_ld,
+                           sizeof(uint32_t) * static_cast<size_t>(nqb) * ld_probe));
+  uint32_t* dist = static_cast<uint32_t*>(h->dist.p);
+  SelState* sel = static_cast<SelState*>(h->sel.p);
+  unsigned int* hist = static_cast<unsigned int*>(h->hist.p);
+  float* tcq = static_cast<float*>(h->tc_q.p);
+
+  CK(cudaMemsetAsync(tcq, 0, sizeof(float) * kTcBN * kScanD, h->stream));
+  CK(cudaMemcpyAsync(tcq, q_dev, sizeof(float) * static_cast<size_t>(nqb) * kScanD, cudaMemcpyDeviceToDevice, h->stream));
+  tc_query_consts_kernel<<<2, 128, 0, h->stream>>>(sb, nqb, static_cast<float*>(h->tc_isb.p));
+  LAUNCHED(h);
+
+  // 1. probe: approximate distances of a strided sample of tiles → K'-th smallest per query
+  const int grid_p = static_cast<int>(std::min<int64_t>(h->sm_count, n_probe));
+  knn_tc_kernel<0><<<grid_p, kTcThreads, kTcSmemBytes, h->stream>>>(
+      h->tmap_a, h->tmap_q, h->amag, h->n_rows, n_probe, tile_stride, nqb, nullptr,
+      static_cast<const float*>(h->tc_isb.p), dist, ld_probe, nullptr, nullptr, 0);
+  LAUNCHED(h);
+  select_init_kernel<<<(nqb + 127) / 128, 128, 0, h->stream>>>(sel, nqb, static_cast<unsigned int>(kprime));
+  LAUNCHED(h);
+  {
+    int blocks = static_cast<int>(std::min<int64_t>((ld_probe + 4095) / 4096, h->sm_count));
+    if (blocks < 1) blocks = 1;
+    dim3 grid(blocks, nqb);
+    static const int shifts[3] = {53, 42, 32};
+    static const int widths[3] = {11, 11, 10};
+    for (int p = 0; p < 3; ++p) {
+      select_pass_kernel<<<grid, kSelThreads, 0, h->stream>>>(dist, ld_probe, ld_probe, 0ull, sel, hist, shifts[p], widths[p]);
+      LAUNCHED(h);
+    }
+  }
+  tc_threshold_kernel<<<2, 128, 0, h->stream>>>(sel, sb, nqb, static_cast<unsigned int>(kprime), static_cast<float*>(h->tc_thr.p));
+  LAUNCHED(h);
+
+  // 2. filter pass over all rows
+  CK(cudaMemsetAsync(h->tc_cnt.p, 0, sizeof(unsigned int) * kTcBN, h->stream));
+  const int grid_f = static_cast<int>(std::min<int64_t>(h->sm_count, n_tiles));
+  cudaEvent_t e0 = nullptr, e1 = nullptr;
+  if (h->timing && h->scan_ev_used + 2 <= (1u << 16)) {
+    while (h->scan_ev.size() < h->scan_ev_used + 2) {
+      cudaEvent_t e;
+      CK(cudaEventCreate(&e));
+      h->scan_ev.push_back(e);
+    }
+    e0 = h->scan_ev[h->scan_ev_used];
+    e1 = h->scan_ev[h->scan_ev_used + 1];
+    h->scan_ev_used += 2;
+    CK(cudaEventRecord(e0, h->stream));
+  }
+  knn_tc_kernel<1><<<grid_f, kTcThreads, kTcSmemBytes, h->stream>>>(
+      h->tmap_a, h->tmap_q, h->amag, h->n_rows, n_tiles, 1, nqb, static_cast<const float*>(h->tc_thr.p), nullptr,
+      nullptr, 0, static_cast<uint32_t*>(h->tc_rows.p), static_cast<unsigned int*>(h->tc_cnt.p), kTcCandCap);
+  LAUNCHED(h);
+  if (e1) CK(cudaEventRecord(e1, h->stream));
+  h->stats.knn_scan_launches++;
+  h->stats.tc_filter_launches++;
+
+  // 3. exact re-score of the survivors, 4. per-query finish
+  dim3 grid_r((kTcCandCap + kScanWarps * 32 - 1) / (kScanWarps * 32), nqb);
+  if (h->fma)
+    knn_rescore_kernel<true><<<grid_r, kScanWarps * 32, scan_smem_bytes(1), h->stream>>>(
+        h->emb, h->amag, q_dev, sb, static_cast<const uint32_t*>(h->tc_rows.p),
+        static_cast<const unsigned int*>(h->tc_cnt.p), kTcCandCap, h->pos_base,
+        static_cast<unsigned long long*>(h->tc_keys.p));
+  else
+    knn_rescore_kernel<false><<<grid_r, kScanWarps * 32, scan_smem_bytes(1), h->stream>>>(
+        h->emb, h->amag, q_dev, sb, static_cast<const uint32_t*>(h->tc_rows.p),
+        static_cast<const unsigned int*>(h->tc_cnt.p), kTcCandCap, h->pos_base,
+        static_cast<unsigned long long*>(h->tc_keys.p));
+  LAUNCHED(h);
+  knn_cand_finish_kernel<<<nqb, kSelThreads, kTcCandCap * 8, h->stream>>>(
+      static_cast<const unsigned long long*>(h->tc_keys.p), static_cast<const unsigned int*>(h->tc_cnt.p), kTcCandCap,
+      kprime, h->pos_base, h->rowid, h->movie_idx, cand_dev, status_dev);
+  LAUNCHED(h);
+  return RSE_OK;
+}
+
+// Local top-kprime for nq device-resident queries → packed candidates (device).
+int knn_local(rse_index* h, const float* q_dev, int nq, int kprime, long long* cand_dev) {
+  if (!h->emb) return fail(h, RSE_ERR_STATE, "rse_knn: no embeddings loaded");
+  if (nq <= 0) return RSE_OK;
+  if (kprime < 1 || kprime > RSE_MAX_KPRIME)
+    return fail(h, RSE_ERR_UNSUPPORTED, "rse_knn: kprime must be in [1, 4096] (sqlite-vec caps k at 4096)");
+  ENSURE(h->sb, sizeof(double) * nq);
+  if (h->hist.bytes < sizeof(unsigned int) * kSelBins * kTcBN) {
+    ENSURE(h->hist, sizeof(unsigned int) * kSelBins * kTcBN);
+    CK(cudaMemsetAsync(h->hist.p, 0, h->hist.bytes, h->stream));
+  }
+  double* sb = static_cast<double*>(h->sb.p);
+  if (h->fma) knn_query_prep_kernel<true><<<(nq + 127) / 128, 128, 0, h->stream>>>(q_dev, nq, h->dim, sb);
+  else knn_query_prep_kernel<false><<<(nq + 127) / 128, 128, 0, h->stream>>>(q_dev, nq, h->dim, sb);
+  LAUNCHED(h);
+
+  if (!tc_eligible(h, nq, kprime)) return knn_exact_groups(h, q_dev, sb, nq, kprime, cand_dev);
+
+  // ---- tensor-core path in blocks of 256 queries, exact fallback for overflowed queries
+  ENSURE(h->tc_status, sizeof(int) * nq);
+  int* status = static_cast<int*>(h->tc_status.p);
+  for (int b0 = 0; b0 < nq; b0 += kTcBN) {
+    const int nqb = std::min(kTcBN, nq - b0);
+    int rc = knn_tc_block(h, q_dev + static_cast<int64_t>(b0) * h->dim, sb + b0, nqb, kprime,
+                          cand_dev + static_cast<int64_t>(b0) * kprime * 3, status + b0);
+    if (rc != RSE_OK) return rc;
+  }
+  h->stats.tc_queries += nq;
+  std::vector<int> st(nq);
+  CK(cudaMemcpyAsync(st.data(), status, sizeof(int) * nq, cudaMemcpyDeviceToHost, h->stream));
+  CK(cudaStreamSynchronize(h->stream));
+  for (int q = 0; q < nq;) {
+    if (!st[q]) { ++q; continue; }
+    int e = q;
+    while (e < nq && st[e] && e - q < kScanMaxQB) ++e;          // contiguous run of overflowed queries
+    h->stats.tc_fallback_queries += e - q;
+    int rc = knn_exact_groups(h, q_dev + static_cast<int64_t>(q) * h->dim, sb + q, e - q, kprime,
+                              cand_dev + static_cast<int64_t>(q) * kprime * 3);
+    if (rc != RSE_OK) return rc;
+    q = e;
+  }
   return RSE_OK;
 }
 
@@ -354,7 +530,8 @@ void rse_destroy(rse_index* h) {
   for (DevBuf* b : {&h->q_dev, &h->sb, &h->sel, &h->hist, &h->selkeys, &h->cand, &h->dist, &h->o_dist, &h->o_pos,
                     &h->o_rowid, &h->o_movie, &h->o_count, &h->b_tokptr, &h->b_terms, &h->b_idf, &h->b_chi, &h->b_clo,
                     &h->b_ccnt, &h->b_score, &h->b_doc, &h->b_count, &h->f_bid, &h->f_bsc, &h->f_bcnt, &h->f_sid,
-                    &h->f_sds, &h->f_scnt, &h->f_oid, &h->f_osc, &h->f_oa, &h->f_ob, &h->f_ocnt})
+                    &h->f_sds, &h->f_scnt, &h->f_oid, &h->f_osc, &h->f_oa, &h->f_ob, &h->f_ocnt, &h->tc_q, &h->tc_thr, &h->tc_isb,
+                    &h->tc_rows, &h->tc_cnt, &h->tc_keys, &h->tc_status})
     free_buf(*b);
   free_ptr(h->doc_ids);
   free_ptr(h->movie_ids);
@@ -389,6 +566,13 @@ int rse_set_fma(rse_index* h, int32_t use_fma) {
   if (!h) return RSE_ERR_INVALID;
   if (h->emb) return fail(h, RSE_ERR_STATE, "rse_set_fma: set before loading embeddings");
   h->fma = use_fma != 0;
+  return RSE_OK;
+}
+
+int rse_set_tc_mode(rse_index* h, int32_t mode) {
+  if (!h) return RSE_ERR_INVALID;
+  if (mode < 0 || mode > 2) return fail(h, RSE_ERR_INVALID, "rse_set_tc_mode: mode must be 0 (auto), 1 (off) or 2 (on)");
+  h->tc_mode = mode;
   return RSE_OK;
 }
 

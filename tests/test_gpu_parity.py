@@ -359,3 +359,67 @@ def test_sharded_merge_equals_single_index():
     assert (od.cpu().numpy().view(np.uint32) == wd.view(np.uint32)).all()
     for h in handles:
         h.close()
+
+
+# ----------------------------------------------------------------------------- K4 tensor-core path
+@pytest.mark.parametrize("n,nq,kprime", [(40_000, 70, 100), (9_000, 256, 50), (33_000, 300, 100), (5_000, 5, 10)])
+def test_tensor_core_path_equals_exact_scan_and_oracle(n, nq, kprime):
+    """K4 (TF32 tcgen05 probe/filter + exact re-score) must return exactly what the exact scan returns:
+    same rows, same order, bit-identical distances — including duplicate rows (ties) and non-unit norms."""
+    from rag_search_engine_b200 import _lib
+    rng = np.random.default_rng(n + nq)
+    centers = unit_rows(rng, 50, 384)
+    emb = centers[rng.integers(0, 50, n)] + 0.5 * unit_rows(rng, n, 384)          # clustered → dense near-neighbour bands
+    emb *= rng.uniform(0.7, 1.4, (n, 1)).astype(np.float32)                        # non-unit norms
+    emb = inject_ties(rng, emb.astype(np.float32), n // 25)
+    Q = (centers[rng.integers(0, 50, nq)] + 0.3 * unit_rows(rng, nq, 384)).astype(np.float32)
+    Q[0] = emb[7]
+    movie_of = (np.arange(n) // 6).astype(np.int32)
+    res = {}
+    for mode in (1, 2):
+        idx = _lib.Index(0)
+        try:
+            idx.set_tc_mode(mode)
+            idx.load_embeddings(emb, movie_idx=movie_of)
+            res[mode] = idx.knn(Q, kprime) + idx.knn_movies(Q, 10, kprime)
+            st = idx.stats()
+            if mode == 2:
+                assert st.tc_queries == 2 * nq and st.tc_filter_launches >= 2, "tensor-core path did not run"
+                assert st.tc_fallback_queries <= nq // 4
+            else:
+                assert st.tc_queries == 0
+        finally:
+            idx.close()
+    for a, b in zip(res[1], res[2]):
+        assert a.dtype == b.dtype and (a.view(np.uint8) == b.view(np.uint8)).all()
+    dist, pos = res[2][0], res[2][1]
+    for qi in (0, nq // 2, nq - 1):
+        od, orow = oracle.vec0_knn(emb, Q[qi], kprime, literal=False)
+        assert pos[qi].tolist() == orow.tolist()
+        assert dist[qi].view(np.uint32).tolist() == od.view(np.uint32).tolist()
+
+
+def test_tensor_core_path_overflow_falls_back_to_exact():
+    """Thousands of identical rows tie at the threshold → the survivor list overflows → the query is
+    re-run through the exact scan and still matches."""
+    from rag_search_engine_b200 import _lib
+    rng = np.random.default_rng(77)
+    n = 30_000
+    emb = unit_rows(rng, n, 384)
+    emb[5000:17000] = emb[5000]                                   # 12 000 copies of one vector
+    Q = unit_rows(rng, 64, 384)
+    Q[3] = emb[5000] + 0.01 * unit_rows(rng, 1, 384)[0]
+    out = {}
+    for mode in (1, 2):
+        idx = _lib.Index(0)
+        try:
+            idx.set_tc_mode(mode)
+            idx.load_embeddings(emb)
+            out[mode] = idx.knn(Q, 100)
+            if mode == 2:
+                assert idx.stats().tc_fallback_queries >= 1
+        finally:
+            idx.close()
+    for a, b in zip(out[1], out[2]):
+        assert (a.view(np.uint8) == b.view(np.uint8)).all()
+    assert (out[2][1][3] >= 5000).all() and (out[2][1][3] < 17000).all()
