@@ -326,12 +326,17 @@ def run_b200(args, rank, world, local_rank):
     alg_bytes = rows_local * ROW_BYTES
     achieved = alg_bytes / (scan_ms * 1e-3) / 1e9 if scan_ms > 0 else None
     qb = 16 if nq >= 9 else (8 if nq >= 5 else (4 if nq >= 3 else nq))
-    roofline = {"bound": "hbm", "kernel": f"knn_scan384_kernel<QB={qb}> (one pass over the shard serves {qb} queries; "
-                                          f"FFMA2-pipe-bound above QB=4, HBM-bound at QB=1: see knn_batch1)",
+    tc_used = int(st.tc_filter_launches) > 0
+    kname = ("knn_tc_kernel<filter> (tcgen05 TF32 128x256x8, TMA 4-stage, one pass over the shard serves 256 queries; "
+             "survivors re-scored exactly)") if tc_used else (
+        f"knn_scan384_kernel<QB={qb}> (one pass over the shard serves {qb} queries; FFMA2-pipe-bound above QB=4, "
+        f"HBM-bound at QB=1: see knn_batch1)")
+    roofline = {"bound": "hbm", "kernel": kname,
                 "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": (achieved / peak) if achieved else None,
                 "peak_source": "MEASURED_PEAKS.json hbm_gbs (of measured)" if peaks else "fallback 6650 GB/s (of fallback)",
                 "traffic": None, "algorithmic_bytes_per_launch": alg_bytes, "avg_launch_ms": scan_ms,
-                "scan_launches": int(st.scan_launches_timed), "scan_share_of_step": scan_share}
+                "scan_launches": int(st.scan_launches_timed), "scan_share_of_step": scan_share,
+                "tc_queries": int(st.tc_queries), "tc_fallback_queries": int(st.tc_fallback_queries)}
 
     if knn1:
         g1 = alg_bytes / (knn1["scan_ms"] * 1e-3) / 1e9

@@ -13,9 +13,9 @@
 // idf (:224) is computed on the host with the same libm `log` CPython uses.
 //
 // B200 mapping (HBM/L2 gather bound, 8 B/posting + 8 B gathered norm):
-//   * documents are cut into ranges of kBmRange = 8192; one CTA owns one
-//     (query, range) pair with the range's fp64 accumulators (64 KB) and
-//     first-token bytes (8 KB) in shared memory — 3 CTAs/SM;
+//   * documents are cut into ranges of kBmRange = 7168; one CTA owns one
+//     (query, range) pair with the range's fp64 accumulators (56 KB) and
+//     first-token bytes (7 KB) in shared memory — 3 CTAs/SM;
 //   * a per-term range-offset table built at load time gives each CTA its slice
 //     of every posting list without searching; slices are read as coalesced
 //     8-byte (doc, tf) pairs;
@@ -29,10 +29,11 @@
 
 namespace rse {
 
-constexpr int kBmRange = 8192;
+constexpr int kBmRange = 7168;   // 7 x 1024: 63 KB of accumulators + first-token bytes → 3 CTAs per SM
 constexpr int kBmThreads = 256;
 constexpr int kBmMaxTokens = 255;
 constexpr int kBmDocsPerThread = kBmRange / kBmThreads;   // 32
+constexpr unsigned int kBmCandCap = 192;                    // survivors of the threshold pass kept in smem
 
 struct Key128 {
   unsigned long long hi;   // ~orderable(score): ascending hi == descending score
@@ -121,12 +122,18 @@ bm25_score_kernel(const int64_t* __restrict__ indptr, const uint2* __restrict__ 
   extern __shared__ __align__(16) unsigned char smem_raw[];
   double* acc = reinterpret_cast<double*>(smem_raw);                       // [kBmRange]
   unsigned char* first = reinterpret_cast<unsigned char*>(acc + kBmRange); // [kBmRange]
-  __shared__ long long s_lo[kBmMaxTokens + 1];
-  __shared__ unsigned int s_n[kBmMaxTokens + 1];
-  __shared__ double s_idf[kBmMaxTokens + 1];
+  // token tables (scoring phase) and selection scratch (afterwards) share one buffer
+  constexpr int kTokBytes = (kBmMaxTokens + 1) * (8 + 8 + 4);
+  constexpr int kSelBytes = (256 + static_cast<int>(kBmCandCap)) * static_cast<int>(sizeof(Key128));
+  __shared__ __align__(16) unsigned char s_cand_mem[kTokBytes > kSelBytes ? kTokBytes : kSelBytes];
+  long long* s_lo = reinterpret_cast<long long*>(s_cand_mem);
+  double* s_idf = reinterpret_cast<double*>(s_cand_mem + (kBmMaxTokens + 1) * 8);
+  unsigned int* s_n = reinterpret_cast<unsigned int*>(s_cand_mem + (kBmMaxTokens + 1) * 16);
   __shared__ Key128 s_k[kBmThreads / 32];
   __shared__ int s_w[kBmThreads / 32];
   __shared__ unsigned int s_total;
+  __shared__ unsigned int s_ncand;
+  __shared__ Key128 s_tau;
 
   const int r = blockIdx.x;
   const int q = q0 + blockIdx.y;
@@ -155,7 +162,12 @@ bm25_score_kernel(const int64_t* __restrict__ indptr, const uint2* __restrict__ 
     return;
   }
 
-  for (int i = threadIdx.x; i < kBmRange; i += blockDim.x) { acc[i] = 0.0; first[i] = 0xFF; }
+  {
+    uint4* a4 = reinterpret_cast<uint4*>(acc);                 // 64 KB of +0.0
+    for (int i = threadIdx.x; i < kBmRange / 2; i += blockDim.x) a4[i] = make_uint4(0u, 0u, 0u, 0u);
+    uint4* f4 = reinterpret_cast<uint4*>(first);               // 8 KB of 0xFF
+    for (int i = threadIdx.x; i < kBmRange / 16; i += blockDim.x) f4[i] = make_uint4(~0u, ~0u, ~0u, ~0u);
+  }
   __syncthreads();
 
   const uint32_t doc_base = static_cast<uint32_t>(r) * kBmRange;
@@ -177,13 +189,109 @@ bm25_score_kernel(const int64_t* __restrict__ indptr, const uint2* __restrict__ 
     __syncthreads();
   }
 
-  // ---- K7 (range part): k rounds of block arg-min over per-thread cached bests.
+  __syncthreads();   // the token tables are dead from here on: their storage becomes selection scratch
+
+  // ---- K7 (range part): the range's top-k under (score desc, first token asc, doc asc).
   auto make_key = [&](int l) -> Key128 {
     Key128 kk;
     kk.hi = ~f64_orderable(static_cast<uint64_t>(__double_as_longlong(acc[l])));
     kk.lo = (static_cast<unsigned long long>(first[l]) << 32) | (doc_base + static_cast<uint32_t>(l));
     return kk;
   };
+  if (k <= 32) {
+    // Fast path.  (1) every thread finds the best of its 32 documents; (2) each warp sorts its 32
+    // thread-bests with shuffles; (3) warp 0 merges the 8 sorted lists to the k-th best overall — a
+    // valid threshold because the thread-bests are distinct documents; (4) one collect pass keeps the
+    // documents at least that good (≥ k of them, usually barely more); (5) rank counting orders them.
+    Key128 mine = key_inf();
+#pragma unroll 4
+    for (int i = 0; i < kBmDocsPerThread; ++i) {
+      const int l = threadIdx.x + i * kBmThreads;
+      if (first[l] == 0xFF) continue;
+      const Key128 kk = make_key(l);
+      if (key_less(kk, mine)) mine = kk;
+    }
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    // warp bitonic sort, ascending (best first)
+#pragma unroll
+    for (int size = 2; size <= 32; size <<= 1) {
+#pragma unroll
+      for (int stride = size >> 1; stride > 0; stride >>= 1) {
+        Key128 o;
+        o.hi = __shfl_xor_sync(0xFFFFFFFFu, mine.hi, stride);
+        o.lo = __shfl_xor_sync(0xFFFFFFFFu, mine.lo, stride);
+        const bool up = ((lane & size) == 0);
+        const bool lower = ((lane & stride) == 0);
+        const bool take_min = (up == lower);
+        const bool o_less = key_less(o, mine);
+        if (take_min ? o_less : !o_less) mine = o;
+      }
+    }
+    Key128* s_wb = reinterpret_cast<Key128*>(s_cand_mem);        // [8][32]
+    s_wb[warp * 32 + lane] = mine;
+    __syncthreads();
+    if (warp == 0) {
+      // 8-way merge: lane w < 8 owns list w
+      int head = 0;
+      Key128 cur = (lane < kBmThreads / 32) ? s_wb[lane * 32] : key_inf();
+      Key128 tau = key_inf();
+      for (int round = 0; round < k; ++round) {
+        Key128 best = cur;
+        int who = lane;
+#pragma unroll
+        for (int off = 4; off > 0; off >>= 1) {
+          Key128 o;
+          o.hi = __shfl_xor_sync(0xFFFFFFFFu, best.hi, off);
+          o.lo = __shfl_xor_sync(0xFFFFFFFFu, best.lo, off);
+          const int ow = __shfl_xor_sync(0xFFFFFFFFu, who, off);
+          if (key_less(o, best)) { best = o; who = ow; }
+        }
+        best.hi = __shfl_sync(0xFFFFFFFFu, best.hi, 0);
+        best.lo = __shfl_sync(0xFFFFFFFFu, best.lo, 0);
+        who = __shfl_sync(0xFFFFFFFFu, who, 0);
+        tau = best;
+        if (best.hi == ~0ull && best.lo == ~0ull) break;         // fewer than k touched documents
+        if (lane == who) {
+          ++head;
+          cur = (head < 32) ? s_wb[lane * 32 + head] : key_inf();
+        }
+      }
+      if (lane == 0) { s_tau = tau; s_ncand = 0u; }
+    }
+    __syncthreads();
+    const Key128 tau = s_tau;
+    Key128* s_cand = reinterpret_cast<Key128*>(s_cand_mem) + 256;  // [kBmCandCap], after the warp lists
+#pragma unroll 4
+    for (int i = 0; i < kBmDocsPerThread; ++i) {
+      const int l = threadIdx.x + i * kBmThreads;
+      if (first[l] == 0xFF) continue;
+      const Key128 kk = make_key(l);
+      if (!key_less(tau, kk)) {                                  // kk <= tau
+        const unsigned int slot = atomicAdd(&s_ncand, 1u);
+        if (slot < kBmCandCap) s_cand[slot] = kk;
+      }
+    }
+    __syncthreads();
+    const unsigned int nc = s_ncand;
+    if (nc <= kBmCandCap) {
+      const int emitted = static_cast<int>(nc) < k ? static_cast<int>(nc) : k;
+      if (threadIdx.x < nc) {
+        const Key128 me = s_cand[threadIdx.x];
+        int rank = 0;
+        for (unsigned int j = 0; j < nc; ++j) rank += key_less(s_cand[j], me) ? 1 : 0;
+        if (rank < k) {
+          cand_hi[cbase * k + rank] = me.hi;
+          cand_lo[cbase * k + rank] = me.lo;
+        }
+      }
+      if (threadIdx.x == 0) cand_cnt[cbase] = emitted;
+      return;
+    }
+    // survivor overflow (mass ties at the threshold): fall through to the general path
+    __syncthreads();
+  }
+
+  // General path (k > 32, or overflow): k rounds of block arg-min over per-thread cached bests.
   auto scan_best = [&](const Key128& after, bool have_after) -> Key128 {
     Key128 best = key_inf();
 #pragma unroll 4
