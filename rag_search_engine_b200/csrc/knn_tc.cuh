@@ -19,10 +19,14 @@
 //   A query whose survivor list overflows is flagged and re-run through K1/K2 by the host.
 //
 // GEMM mapping: D[128 rows x 256 queries] per tile, K = 384 in 12 k-blocks of 32 floats (one
-// 128-byte swizzle atom).  Warp-specialised: warp 0 = TMA producer (cp.async.bulk.tensor, 4-stage
-// mbarrier ring, 48 KB/stage: 16 KB of rows + 32 KB of queries), warp 1 = single-thread
-// tcgen05.mma.kind::tf32 issuer (UMMA 128x256x8, accumulators in TMEM, double-buffered:
-// 2 x 256 columns), warps 2-5 = epilogue (tcgen05.ld 32x32b, one TMEM lane = one row per thread).
+// 128-byte swizzle atom).  The 393 KB query block cannot stay in shared memory, so it streams from
+// L2 with the rows; to halve that re-streaming a CTA works on a PAIR of row tiles per query
+// k-block (r01 ncu: with one tile per k-block the kernel moved 22.1 GB through TMA per pass, 3x the
+// rows, and sat at the TMA fill rate, ~8.3 TB/s).  Warp-specialised: warp 0 = TMA producer
+// (cp.async.bulk.tensor, 3-stage mbarrier ring, 64 KB/stage: 2 x 16 KB of rows + 32 KB of queries),
+// warp 1 = single-thread tcgen05.mma.kind::tf32 issuer (UMMA 128x256x8, the two accumulators fill
+// the 512 TMEM columns), warps 2-5 = epilogue (tcgen05.ld 32x32b, one TMEM lane = one row per
+// thread; the producer keeps prefetching the next pair during the epilogue).
 // Persistent, one CTA per SM.
 #pragma once
 #include <cuda.h>
@@ -35,11 +39,11 @@ namespace rse {
 constexpr int kTcBM = 128;
 constexpr int kTcBN = 256;
 constexpr int kTcBK = 32;
-constexpr int kTcStages = 4;
+constexpr int kTcStages = 3;
 constexpr int kTcKBlocks = kScanD / kTcBK;                 // 12
-constexpr int kTcStageA = kTcBM * kTcBK * 4;               // 16,384
-constexpr int kTcStageB = kTcBN * kTcBK * 4;               // 32,768
-constexpr int kTcStageBytes = kTcStageA + kTcStageB;       // 49,152
+constexpr int kTcStageA = kTcBM * kTcBK * 4;               // 16,384 (one 128-row tile, one k-block)
+constexpr int kTcStageB = kTcBN * kTcBK * 4;               // 32,768 (256 queries, one k-block)
+constexpr int kTcStageBytes = 2 * kTcStageA + kTcStageB;   // 65,536: TWO row tiles share one query k-block
 constexpr int kTcThreads = 192;                            // 6 warps
 constexpr int kTcSmemBytes = kTcStages * kTcStageBytes + 2 * kTcBN * 4 + 16 * 8 + 16 + 1024;
 constexpr float kTcEps = 2.5e-3f;                          // bound on |d~ - d| (see header)
@@ -177,6 +181,7 @@ knn_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant_
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
+  const int64_t n_pairs = (n_tiles + 1) / 2;
   if (warp == 0) {
     // ===================== TMA producer =====================
     if (lane == 0) {
@@ -184,14 +189,18 @@ knn_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant_
       asm volatile("prefetch.tensormap [%0];" ::"l"(&tmap_q) : "memory");
       int stage = 0;
       uint32_t phase = 0;
-      for (int64_t t = blockIdx.x; t < n_tiles; t += gridDim.x) {
-        const int row0 = static_cast<int>(t * tile_stride * kTcBM);
+      for (int64_t p = blockIdx.x; p < n_pairs; p += gridDim.x) {
+        const int64_t t0 = 2 * p, t1 = 2 * p + 1;
+        const int row0 = static_cast<int>(t0 * tile_stride * kTcBM);
+        // an odd tail has no second tile: point it past the end (TMA zero-fills out-of-bounds rows)
+        const int row1 = (t1 < n_tiles) ? static_cast<int>(t1 * tile_stride * kTcBM) : static_cast<int>(n_rows);
         for (int kb = 0; kb < kTcKBlocks; ++kb) {
           mbar_wait(&empty[stage], phase ^ 1u);
           mbar_arrive_expect_tx(&full[stage], kTcStageBytes);
           unsigned char* sa = smem + stage * kTcStageBytes;
           tma_load_2d(sa, &tmap_a, kb * kTcBK, row0, &full[stage]);
-          tma_load_2d(sa + kTcStageA, &tmap_q, kb * kTcBK, 0, &full[stage]);
+          tma_load_2d(sa + kTcStageA, &tmap_a, kb * kTcBK, row1, &full[stage]);
+          tma_load_2d(sa + 2 * kTcStageA, &tmap_q, kb * kTcBK, 0, &full[stage]);
           if (++stage == kTcStages) { stage = 0; phase ^= 1u; }
         }
       }
@@ -201,79 +210,94 @@ knn_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant_
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
-      int it = 0;
-      for (int64_t t = blockIdx.x; t < n_tiles; t += gridDim.x, ++it) {
-        const int buf = it & 1;
-        const uint32_t use = static_cast<uint32_t>(it >> 1);
-        mbar_wait(&tempty[buf], (use & 1u) ^ 1u);         // epilogue drained this accumulator
+      uint32_t it = 0;
+      for (int64_t p = blockIdx.x; p < n_pairs; p += gridDim.x, ++it) {
+        mbar_wait(&tempty[0], (it & 1u) ^ 1u);            // epilogue drained both accumulators
         tc_fence_after();
-        const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(buf * kTcBN);
         for (int kb = 0; kb < kTcKBlocks; ++kb) {
           mbar_wait(&full[stage], phase);
           tc_fence_after();
           const uint32_t a_addr = base + stage * kTcStageBytes;
-          const uint64_t adesc = tc_smem_desc(a_addr);
-          const uint64_t bdesc = tc_smem_desc(a_addr + kTcStageA);
+          const uint64_t adesc0 = tc_smem_desc(a_addr);
+          const uint64_t adesc1 = tc_smem_desc(a_addr + kTcStageA);
+          const uint64_t bdesc = tc_smem_desc(a_addr + 2 * kTcStageA);
 #pragma unroll
           for (int k = 0; k < kTcBK / 8; ++k) {
             // advance 8 tf32 = 32 B inside the swizzle atom: +2 in the (>>4) start-address field
-            tc_mma_tf32(d_tmem, adesc + static_cast<uint64_t>(2 * k), bdesc + static_cast<uint64_t>(2 * k), kTcIdesc,
-                        (kb | k) != 0 ? 1u : 0u);
+            const uint32_t accum = (kb | k) != 0 ? 1u : 0u;
+            tc_mma_tf32(tmem_base, adesc0 + static_cast<uint64_t>(2 * k), bdesc + static_cast<uint64_t>(2 * k), kTcIdesc, accum);
+            tc_mma_tf32(tmem_base + kTcBN, adesc1 + static_cast<uint64_t>(2 * k), bdesc + static_cast<uint64_t>(2 * k), kTcIdesc, accum);
           }
           tc_commit(&empty[stage]);                       // smem slot free once these MMAs retire
           if (++stage == kTcStages) { stage = 0; phase ^= 1u; }
         }
-        tc_commit(&tfull[buf]);                           // accumulator complete
+        tc_commit(&tfull[0]);                             // both accumulators complete
       }
     }
   } else {
     // ===================== epilogue (warps 2..5) =====================
     const int quarter = warp & 3;                         // TMEM lanes [32*quarter, +32) belong to this warp
-    int it = 0;
-    for (int64_t t = blockIdx.x; t < n_tiles; t += gridDim.x, ++it) {
-      const int buf = it & 1;
-      const uint32_t use = static_cast<uint32_t>(it >> 1);
-      const int64_t row = t * tile_stride * kTcBM + quarter * 32 + lane;
-      const bool in_range = row < n_rows;
-      const float am = in_range ? __ldg(amag + row) : -1.0f;
-      const bool valid = am > 0.0f;
-      const float inv_sa = valid ? rsqrtf(am) : 0.0f;
-      mbar_wait(&tfull[buf], use & 1u);
-      tc_fence_after();
-      const uint32_t taddr0 = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + static_cast<uint32_t>(buf * kTcBN);
-      const int ncol = (MODE == 0) ? ((nq + 31) & ~31) : kTcBN;
-      for (int c0 = 0; c0 < ncol; c0 += 32) {
-        uint32_t v[32];
-        tc_ld32(taddr0 + static_cast<uint32_t>(c0), v);
-        if (MODE == 0) {
-          const int64_t orow = t * kTcBM + quarter * 32 + lane;
+    uint32_t it = 0;
+    for (int64_t p = blockIdx.x; p < n_pairs; p += gridDim.x, ++it) {
+      float amv[2];
 #pragma unroll
-          for (int j = 0; j < 32; ++j) {
-            const int q = c0 + j;
-            if (q < nq) {
-              uint32_t bits = 0x7FFFFFFFu;                // invalid sentinel (empty slot / past the end)
-              if (valid) bits = __float_as_uint(1.0f - __uint_as_float(v[j]) * inv_sa * s_isb[q]);
-              dist[static_cast<int64_t>(q) * ld + orow] = bits;
-            }
-          }
-        } else {
-          if (valid) {
+      for (int buf = 0; buf < 2; ++buf) {
+        const int64_t t = 2 * p + buf;
+        const int64_t row = t * tile_stride * kTcBM + quarter * 32 + lane;
+        amv[buf] = (t < n_tiles && row < n_rows) ? __ldg(amag + row) : -1.0f;
+      }
+      mbar_wait(&tfull[0], it & 1u);
+      tc_fence_after();
+#pragma unroll
+      for (int buf = 0; buf < 2; ++buf) {
+        const int64_t t = 2 * p + buf;
+        if (t >= n_tiles) continue;
+        const int64_t row = t * tile_stride * kTcBM + quarter * 32 + lane;
+        const float am = amv[buf];
+        const bool valid = am > 0.0f;
+        const float inv_sa = valid ? rsqrtf(am) : 0.0f;
+        const uint32_t taddr0 = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + static_cast<uint32_t>(buf * kTcBN);
+        const int ncol = (MODE == 0) ? ((nq + 31) & ~31) : kTcBN;
+        for (int c0 = 0; c0 < ncol; c0 += 32) {
+          uint32_t v[32];
+          tc_ld32(taddr0 + static_cast<uint32_t>(c0), v);
+          if (MODE == 0) {
+            const int64_t orow = t * kTcBM + quarter * 32 + lane;
 #pragma unroll
             for (int j = 0; j < 32; ++j) {
-              const float s = __uint_as_float(v[j]) * inv_sa;
-              if (s >= s_thr[c0 + j]) {
-                const int q = c0 + j;
-                const unsigned int slot = atomicAdd(&cand_count[q], 1u);
-                if (slot < static_cast<unsigned int>(cap))
-                  cand_rows[static_cast<int64_t>(q) * cap + slot] = static_cast<uint32_t>(row);
+              const int q = c0 + j;
+              if (q < nq) {
+                uint32_t bits = 0x7FFFFFFFu;              // invalid sentinel (empty slot / past the end)
+                if (valid) bits = __float_as_uint(1.0f - __uint_as_float(v[j]) * inv_sa * s_isb[q]);
+                dist[static_cast<int64_t>(q) * ld + orow] = bits;
               }
+            }
+          } else {
+            // branch-free compare of 32 columns → bitmask; survivors are rare (≈K'·C/S of C rows)
+            const float4* th4 = reinterpret_cast<const float4*>(s_thr + c0);
+            uint32_t mask = 0u;
+#pragma unroll
+            for (int j4 = 0; j4 < 8; ++j4) {
+              const float4 th = th4[j4];
+              mask |= (__uint_as_float(v[4 * j4 + 0]) * inv_sa >= th.x) ? (1u << (4 * j4 + 0)) : 0u;
+              mask |= (__uint_as_float(v[4 * j4 + 1]) * inv_sa >= th.y) ? (1u << (4 * j4 + 1)) : 0u;
+              mask |= (__uint_as_float(v[4 * j4 + 2]) * inv_sa >= th.z) ? (1u << (4 * j4 + 2)) : 0u;
+              mask |= (__uint_as_float(v[4 * j4 + 3]) * inv_sa >= th.w) ? (1u << (4 * j4 + 3)) : 0u;
+            }
+            if (!valid) mask = 0u;
+            while (mask) {
+              const int q = c0 + __ffs(mask) - 1;
+              mask &= mask - 1u;
+              const unsigned int slot = atomicAdd(&cand_count[q], 1u);
+              if (slot < static_cast<unsigned int>(cap))
+                cand_rows[static_cast<int64_t>(q) * cap + slot] = static_cast<uint32_t>(row);
             }
           }
         }
       }
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(&tempty[buf]);
+      if (lane == 0) mbar_arrive(&tempty[0]);
     }
   }
 

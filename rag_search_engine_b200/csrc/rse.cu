@@ -330,7 +330,7 @@ int knn_tc_block(rse_index* h, const float* q_dev, const double* sb, int nqb, in
   LAUNCHED(h);
 
   // 1. probe: approximate distances of a strided sample of tiles → K'-th smallest per query
-  const int grid_p = static_cast<int>(std::min<int64_t>(h->sm_count, n_probe));
+  const int grid_p = static_cast<int>(std::min<int64_t>(h->sm_count, (n_probe + 1) / 2));
   knn_tc_kernel<0><<<grid_p, kTcThreads, kTcSmemBytes, h->stream>>>(
       h->tmap_a, h->tmap_q, h->amag, h->n_rows, n_probe, tile_stride, nqb, nullptr,
       static_cast<const float*>(h->tc_isb.p), dist, ld_probe, nullptr, nullptr, 0);
@@ -353,7 +353,7 @@ int knn_tc_block(rse_index* h, const float* q_dev, const double* sb, int nqb, in
 
   // 2. filter pass over all rows
   CK(cudaMemsetAsync(h->tc_cnt.p, 0, sizeof(unsigned int) * kTcBN, h->stream));
-  const int grid_f = static_cast<int>(std::min<int64_t>(h->sm_count, n_tiles));
+  const int grid_f = static_cast<int>(std::min<int64_t>(h->sm_count, (n_tiles + 1) / 2));
   cudaEvent_t e0 = nullptr, e1 = nullptr;
   if (h->timing && h->scan_ev_used + 2 <= (1u << 16)) {
     while (h->scan_ev.size() < h->scan_ev_used + 2) {
