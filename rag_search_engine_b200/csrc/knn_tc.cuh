@@ -12,11 +12,13 @@
 //                where eps bounds |d~ - d_exact| (TF32 operand truncation, eps = 2.5e-3 > 2^-9;
 //                see DESIGN.md §5).  Every row of the exact top-K' passes:
 //                  d_K' <= (K'-th exact d in the sample) <= tau_s + eps, and d~ <= d + eps.
-//   3. re-score: the survivors are gathered by TMA and re-computed with the EXACT sequential
-//                fp32 arithmetic of K1 (same code path: mac<FMA>, cosine_tail), keyed with the
-//                vec0 emit-order key.
-//   4. finish  : per query, sort the exact keys, keep K' → the same packed candidates K1+K2 emit.
-//   A query whose survivor list overflows is flagged and re-run through K1/K2 by the host.
+//   3. refine  : per query, s_K = the K'-th largest approximate value among the survivors (exact,
+//                since all rows above the filter bound survived); only rows within 2*eps of s_K
+//                stay (K' plus a thin band instead of K'·C/S rows).
+//   4. re-score: those rows are re-computed with the EXACT sequential fp32 arithmetic of K1 (same
+//                code: mac<FMA>, cosine_tail), keyed with the vec0 emit-order key, sorted, and the
+//                first K' emitted → the same packed candidates K1+K2 emit.
+//   A query whose survivor / refined list overflows is flagged and re-run through K1/K2 by the host.
 //
 // GEMM mapping: D[128 rows x 256 queries] per tile, K = 384 in 12 k-blocks of 32 floats (one
 // 128-byte swizzle atom).  The 393 KB query block cannot stay in shared memory, so it streams from
@@ -139,13 +141,13 @@ __global__ void tc_threshold_kernel(const SelState* __restrict__ st, const doubl
 // ---------------------------------------------------------------- the GEMM
 // MODE 0 (probe) : tiles t = 0..n_tiles-1 map to row tile t*tile_stride; d~ stored to
 //                  dist[q*ld + t*128 + r] (empty vec0 slots get the invalid sentinel).
-// MODE 1 (filter): all row tiles; survivors appended to cand_rows[q*cap + slot] (local row).
+// MODE 1 (filter): all row tiles; survivors appended to cand_pairs[q*cap + slot] = {local row, dot~/|a|}.
 template <int MODE>
 __global__ void __launch_bounds__(kTcThreads, 1)
 knn_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_q,
               const float* __restrict__ amag, int64_t n_rows, int64_t n_tiles, int64_t tile_stride, int nq,
               const float* __restrict__ thr, const float* __restrict__ inv_sb, uint32_t* __restrict__ dist,
-              int64_t ld, uint32_t* __restrict__ cand_rows, unsigned int* __restrict__ cand_count, int cap) {
+              int64_t ld, uint2* __restrict__ cand_pairs, unsigned int* __restrict__ cand_count, int cap) {
   extern __shared__ unsigned char smem_raw[];
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   unsigned char* smem = smem_raw + (base - smem_u32(smem_raw));
@@ -286,11 +288,17 @@ knn_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant_
             }
             if (!valid) mask = 0u;
             while (mask) {
-              const int q = c0 + __ffs(mask) - 1;
+              const int j = __ffs(mask) - 1;
+              const int q = c0 + j;
               mask &= mask - 1u;
               const unsigned int slot = atomicAdd(&cand_count[q], 1u);
-              if (slot < static_cast<unsigned int>(cap))
-                cand_rows[static_cast<int64_t>(q) * cap + slot] = static_cast<uint32_t>(row);
+              if (slot < static_cast<unsigned int>(cap)) {
+                // (row, dot~/|a|): the second-level refinement ranks survivors by this value
+                float sv = 0.0f;
+#pragma unroll
+                for (int jj = 0; jj < 32; ++jj) if (jj == j) sv = __uint_as_float(v[jj]) * inv_sa;
+                cand_pairs[static_cast<int64_t>(q) * cap + slot] = make_uint2(static_cast<uint32_t>(row), __float_as_uint(sv));
+              }
             }
           }
         }
@@ -309,81 +317,127 @@ knn_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant_
   }
 }
 
-// ---------------------------------------------------------------- exact re-score of the survivors
-// One warp = 32 survivors of ONE query, lane-per-row like K1: TMA-gathers the rows into the padded
-// stage, runs the reference's sequential sum, emits the vec0 emit-order key.  grid = (ceil(cap/128), nq).
-template <bool FMA>
-__global__ void __launch_bounds__(kScanWarps * 32, 1)
-knn_rescore_kernel(const float* __restrict__ emb, const float* __restrict__ amag, const float* __restrict__ q,
-                   const double* __restrict__ sb, const uint32_t* __restrict__ cand_rows,
-                   const unsigned int* __restrict__ cand_count, int cap, uint64_t pos_base,
-                   unsigned long long* __restrict__ cand_keys) {
-  extern __shared__ __align__(128) unsigned char smem[];
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int qi = blockIdx.y;
-  unsigned int n = cand_count[qi];
-  if (n > static_cast<unsigned int>(cap)) n = cap;
-  const unsigned int i0 = (blockIdx.x * kScanWarps + warp) * 32;
-  float* qs = reinterpret_cast<float*>(smem + kScanWarps * kScanStageBytes);
-  uint64_t* bar = reinterpret_cast<uint64_t*>(smem + kScanWarps * kScanStageBytes + kScanD * 4) + warp;
-  if (blockIdx.x * kScanWarps * 32 >= n) return;           // whole CTA idle (uniform)
-  for (int i = threadIdx.x; i < kScanD; i += blockDim.x) qs[i] = q[static_cast<int64_t>(qi) * kScanD + i];
-  if (lane == 0) mbar_init(bar, 1);
-  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-  __syncthreads();
-  if (i0 >= n) return;
-  float* stage = reinterpret_cast<float*>(smem + warp * kScanStageBytes);
-  const unsigned int nvalid = (n - i0 < 32u) ? (n - i0) : 32u;
-  const bool have = lane < static_cast<int>(nvalid);
-  const uint32_t row = have ? cand_rows[static_cast<int64_t>(qi) * cap + i0 + lane] : 0u;
-  if (lane == 0) mbar_arrive_expect_tx(bar, nvalid * (kScanD * 4));
-  __syncwarp();
-  if (have) bulk_g2s(stage + lane * kScanRowStride, emb + static_cast<int64_t>(row) * kScanD, kScanD * 4, bar);
-  const float am = have ? __ldg(amag + row) : 1.0f;
-  mbar_wait(bar, 0);
-  const float4* rowp = reinterpret_cast<const float4*>(stage + lane * kScanRowStride);
-  const float4* qp = reinterpret_cast<const float4*>(qs);
-  float acc = 0.0f;
-#pragma unroll 4
-  for (int c = 0; c < kScanD / 4; ++c) {
-    const float4 a = rowp[c];
-    const float4 b = qp[c];
-    acc = mac<FMA>(acc, a.x, b.x);
-    acc = mac<FMA>(acc, a.y, b.y);
-    acc = mac<FMA>(acc, a.z, b.z);
-    acc = mac<FMA>(acc, a.w, b.w);
-  }
-  if (have) {
-    const float d = cosine_tail(acc, sqrt(static_cast<double>(am)), sb[qi]);
-    cand_keys[static_cast<int64_t>(qi) * cap + i0 + lane] =
-        knn_key(f32_orderable(__float_as_uint(d)), pos_base + static_cast<uint64_t>(row));
-  }
-}
+// ---------------------------------------------------------------- refine + exact re-score + finish
+// One CTA per query.
+//   (a) second-level refinement on the approximate values the filter kept: with s_K = the K'-th
+//       largest dot~/|a| among the survivors (= among ALL rows, because every row above the filter
+//       threshold survived), only rows with s >= s_K - 2*eps*|q| can be in the exact top-K'
+//       (same argument as the filter bound, now with the exact K'-th approximate value);
+//   (b) those few rows (K' plus the 2*eps band) are re-computed with the EXACT sequential fp32
+//       arithmetic of K1 (mac<FMA>, cosine_tail), lane-per-row straight from global memory;
+//   (c) the exact emit-order keys are sorted and the first K' emitted as packed candidates.
+// status[q] = 1 (host re-runs the query through K1/K2) when the survivor list or the refined
+// list overflowed.  smem: cap * 8 bytes (pairs) — reused for the exact keys.
+constexpr int kTcRefineCap = 2048;                         // rows re-scored exactly per query at most
 
-// ---------------------------------------------------------------- finish: sort exact keys, keep K'
-// One CTA per query; smem = cap2 * 8 bytes.  Queries whose survivor list overflowed get
-// status[q] = 1 and an empty result (the host re-runs them through the exact scan).
-__global__ void __launch_bounds__(kSelThreads)
-knn_cand_finish_kernel(const unsigned long long* __restrict__ cand_keys, const unsigned int* __restrict__ cand_count,
-                       int cap, int kprime, uint64_t pos_base, const int64_t* __restrict__ rowid,
-                       const int32_t* __restrict__ movie_idx, long long* __restrict__ cand, int* __restrict__ status) {
+template <bool FMA>
+__global__ void __launch_bounds__(kSelThreads, 2)
+knn_refine_kernel(const float* __restrict__ emb, const float* __restrict__ amag, const float* __restrict__ q,
+                  const double* __restrict__ sb, const uint2* __restrict__ cand_pairs,
+                  const unsigned int* __restrict__ cand_count, int cap, int kprime, uint64_t pos_base,
+                  const int64_t* __restrict__ rowid, const int32_t* __restrict__ movie_idx,
+                  long long* __restrict__ cand, int* __restrict__ status) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  unsigned long long* keys = reinterpret_cast<unsigned long long*>(smem_raw);
-  const int q = blockIdx.x;
-  const unsigned int cnt = cand_count[q];
-  const bool overflow = cnt > static_cast<unsigned int>(cap);
-  const int n = overflow ? 0 : static_cast<int>(cnt);
-  if (threadIdx.x == 0) status[q] = overflow ? 1 : 0;
-  int n2 = 1;
-  while (n2 < n) n2 <<= 1;
-  if (n2 < 2) n2 = 2;
-  for (int i = threadIdx.x; i < n2; i += blockDim.x)
-    keys[i] = (i < n) ? cand_keys[static_cast<int64_t>(q) * cap + i] : ~0ull;
-  // keys-only bitonic sort
-  for (int size = 2; size <= n2; size <<= 1) {
+  uint2* pairs = reinterpret_cast<uint2*>(smem_raw);                       // [cap]
+  __shared__ float s_q[kScanD];
+  __shared__ unsigned int s_hist[256];
+  __shared__ unsigned int s_prefix, s_need, s_m;
+  __shared__ uint32_t s_rows[kTcRefineCap];
+  const int qi = blockIdx.x;
+  const unsigned int cnt = cand_count[qi];
+  long long* out = cand + static_cast<int64_t>(qi) * kprime * 3;
+  if (cnt > static_cast<unsigned int>(cap)) {                              // survivor overflow
+    if (threadIdx.x == 0) status[qi] = 1;
+    for (int i = threadIdx.x; i < kprime * 3; i += blockDim.x) out[i] = -1ll;
+    return;
+  }
+  const int n = static_cast<int>(cnt);
+  for (int i = threadIdx.x; i < n; i += blockDim.x) pairs[i] = cand_pairs[static_cast<int64_t>(qi) * cap + i];
+  for (int i = threadIdx.x; i < kScanD; i += blockDim.x) s_q[i] = q[static_cast<int64_t>(qi) * kScanD + i];
+  if (threadIdx.x == 0) { s_prefix = 0u; s_need = static_cast<unsigned int>(kprime < n ? kprime : n); s_m = 0u; }
+  __syncthreads();
+
+  // ---- (a) K'-th largest approximate value: MSD radix select (4 x 8 bits) on ~orderable(s)
+  //      (descending s == ascending ~orderable)
+  uint32_t resolved_mask = 0u;
+  if (n > kprime) {
+    for (int pass = 0; pass < 4; ++pass) {
+      const int shift = 24 - 8 * pass;
+      for (int i = threadIdx.x; i < 256; i += blockDim.x) s_hist[i] = 0u;
+      __syncthreads();
+      const uint32_t prefix = s_prefix;
+      for (int i = threadIdx.x; i < n; i += blockDim.x) {
+        const uint32_t key = ~f32_orderable(pairs[i].y);
+        if ((key & resolved_mask) == prefix) atomicAdd(&s_hist[(key >> shift) & 0xFFu], 1u);
+      }
+      __syncthreads();
+      if (threadIdx.x == 0) {
+        unsigned int need = s_need, run = 0u;
+        int d = 0;
+        for (; d < 256; ++d) {
+          if (run + s_hist[d] >= need) break;
+          run += s_hist[d];
+        }
+        s_prefix = prefix | (static_cast<uint32_t>(d) << shift);
+        s_need = need - run;
+      }
+      resolved_mask |= 0xFFu << shift;
+      __syncthreads();
+    }
+  }
+  // s_K (exact K'-th largest approximate value), cut = s_K - 2 eps |q|  (slack for f32 rounding)
+  float cut = -__int_as_float(0x7F800000);
+  if (n > kprime) {
+    const float s_k = __uint_as_float(f32_from_orderable(~s_prefix));
+    const float qn = static_cast<float>(sb[qi]);
+    cut = s_k - (2.0f * kTcEps + 1e-6f) * qn - 1e-30f;
+  }
+  for (int i = threadIdx.x; i < n; i += blockDim.x) {
+    const uint2 pr = pairs[i];
+    if (__uint_as_float(pr.y) >= cut) {
+      const unsigned int slot = atomicAdd(&s_m, 1u);
+      if (slot < kTcRefineCap) s_rows[slot] = pr.x;
+    }
+  }
+  __syncthreads();
+  const unsigned int m = s_m;
+  if (m > kTcRefineCap) {                                                  // refined list overflow (mass ties)
+    if (threadIdx.x == 0) status[qi] = 1;
+    for (int i = threadIdx.x; i < kprime * 3; i += blockDim.x) out[i] = -1ll;
+    return;
+  }
+  if (threadIdx.x == 0) status[qi] = 0;
+
+  // ---- (b) exact distances, lane-per-row from global memory (the reference's sequential sum)
+  unsigned long long* keys = reinterpret_cast<unsigned long long*>(smem_raw);   // pairs are dead
+  __syncthreads();
+  int m2 = 2;
+  while (m2 < static_cast<int>(m)) m2 <<= 1;
+  const double sbq = sb[qi];
+  for (int i = threadIdx.x; i < m2; i += blockDim.x) {
+    unsigned long long key = ~0ull;
+    if (i < static_cast<int>(m)) {
+      const uint32_t row = s_rows[i];
+      const float4* rp = reinterpret_cast<const float4*>(emb + static_cast<int64_t>(row) * kScanD);
+      float acc = 0.0f;
+#pragma unroll 8
+      for (int c = 0; c < kScanD / 4; ++c) {
+        const float4 a = __ldg(rp + c);
+        acc = mac<FMA>(acc, a.x, s_q[4 * c + 0]);
+        acc = mac<FMA>(acc, a.y, s_q[4 * c + 1]);
+        acc = mac<FMA>(acc, a.z, s_q[4 * c + 2]);
+        acc = mac<FMA>(acc, a.w, s_q[4 * c + 3]);
+      }
+      const float d = cosine_tail(acc, sqrt(static_cast<double>(__ldg(amag + row))), sbq);
+      key = knn_key(f32_orderable(__float_as_uint(d)), pos_base + static_cast<uint64_t>(row));
+    }
+    keys[i] = key;
+  }
+  // ---- (c) keys-only bitonic sort, emit the first K'
+  for (int size = 2; size <= m2; size <<= 1) {
     for (int stride = size >> 1; stride > 0; stride >>= 1) {
       __syncthreads();
-      for (int t = threadIdx.x; t < (n2 >> 1); t += blockDim.x) {
+      for (int t = threadIdx.x; t < (m2 >> 1); t += blockDim.x) {
         const int lo = 2 * t - (t & (stride - 1));
         const int hi = lo + stride;
         const bool up = ((lo & size) == 0);
@@ -394,8 +448,8 @@ knn_cand_finish_kernel(const unsigned long long* __restrict__ cand_keys, const u
   }
   __syncthreads();
   for (int i = threadIdx.x; i < kprime; i += blockDim.x) {
-    long long* c = cand + (static_cast<int64_t>(q) * kprime + i) * 3;
-    if (i < n) {
+    long long* c = out + static_cast<int64_t>(i) * 3;
+    if (i < static_cast<int>(m)) {
       const uint64_t key = keys[i];
       const uint64_t pos = knn_key_pos(key);
       const int64_t local = static_cast<int64_t>(pos - pos_base);

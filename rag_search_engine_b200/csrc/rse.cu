@@ -277,7 +277,7 @@ bool tc_eligible(const rse_index* h, int nq, int kprime) {
   if (h->tc_mode == 1 || h->dim != kScanD) return false;
   const int64_t n_tiles = (h->n_rows + kTcBM - 1) / kTcBM;
   if (n_tiles * kTcBM < 8ll * kprime || h->n_rows < 1024) return false;   // the probe needs a usable sample
-  if (kprime * 4 > kTcCandCap) return false;
+  if (kprime * 4 > kTcCandCap || kprime * 2 > kTcRefineCap) return false;
   if (h->tc_mode == 2) return true;
   return nq >= 48 && h->n_rows >= 262144;
 }
@@ -288,9 +288,8 @@ int knn_tc_block(rse_index* h, const float* q_dev, const double* sb, int nqb, in
   if (!attrs) {
     CK(cudaFuncSetAttribute(knn_tc_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, kTcSmemBytes));
     CK(cudaFuncSetAttribute(knn_tc_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, kTcSmemBytes));
-    CK(cudaFuncSetAttribute(knn_rescore_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, scan_smem_bytes(1)));
-    CK(cudaFuncSetAttribute(knn_rescore_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, scan_smem_bytes(1)));
-    CK(cudaFuncSetAttribute(knn_cand_finish_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kTcCandCap * 8));
+    CK(cudaFuncSetAttribute(knn_refine_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kTcCandCap * 8));
+    CK(cudaFuncSetAttribute(knn_refine_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kTcCandCap * 8));
     attrs = true;
   }
   if (!h->tmap_a_ok) {
@@ -306,8 +305,7 @@ int knn_tc_block(rse_index* h, const float* q_dev, const double* sb, int nqb, in
   }
   ENSURE(h->tc_thr, sizeof(float) * kTcBN);
   ENSURE(h->tc_isb, sizeof(float) * kTcBN);
-  ENSURE(h->tc_rows, sizeof(uint32_t) * static_cast<size_t>(kTcBN) * kTcCandCap);
-  ENSURE(h->tc_keys, sizeof(unsigned long long) * static_cast<size_t>(kTcBN) * kTcCandCap);
+  ENSURE(h->tc_rows, sizeof(uint2) * static_cast<size_t>(kTcBN) * kTcCandCap);
   ENSURE(h->tc_cnt, sizeof(unsigned int) * kTcBN);
   ENSURE(h->sel, sizeof(SelState) * kTcBN);
 
@@ -368,28 +366,23 @@ int knn_tc_block(rse_index* h, const float* q_dev, const double* sb, int nqb, in
   }
   knn_tc_kernel<1><<<grid_f, kTcThreads, kTcSmemBytes, h->stream>>>(
       h->tmap_a, h->tmap_q, h->amag, h->n_rows, n_tiles, 1, nqb, static_cast<const float*>(h->tc_thr.p), nullptr,
-      nullptr, 0, static_cast<uint32_t*>(h->tc_rows.p), static_cast<unsigned int*>(h->tc_cnt.p), kTcCandCap);
+      nullptr, 0, static_cast<uint2*>(h->tc_rows.p), static_cast<unsigned int*>(h->tc_cnt.p), kTcCandCap);
   LAUNCHED(h);
   if (e1) CK(cudaEventRecord(e1, h->stream));
   h->stats.knn_scan_launches++;
   h->stats.tc_filter_launches++;
 
-  // 3. exact re-score of the survivors, 4. per-query finish
-  dim3 grid_r((kTcCandCap + kScanWarps * 32 - 1) / (kScanWarps * 32), nqb);
+  // 3. refine on the approximate values, 4. exact re-score + sort + emit (one CTA per query)
   if (h->fma)
-    knn_rescore_kernel<true><<<grid_r, kScanWarps * 32, scan_smem_bytes(1), h->stream>>>(
-        h->emb, h->amag, q_dev, sb, static_cast<const uint32_t*>(h->tc_rows.p),
-        static_cast<const unsigned int*>(h->tc_cnt.p), kTcCandCap, h->pos_base,
-        static_cast<unsigned long long*>(h->tc_keys.p));
+    knn_refine_kernel<true><<<nqb, kSelThreads, kTcCandCap * 8, h->stream>>>(
+        h->emb, h->amag, q_dev, sb, static_cast<const uint2*>(h->tc_rows.p),
+        static_cast<const unsigned int*>(h->tc_cnt.p), kTcCandCap, kprime, h->pos_base, h->rowid, h->movie_idx,
+        cand_dev, status_dev);
   else
-    knn_rescore_kernel<false><<<grid_r, kScanWarps * 32, scan_smem_bytes(1), h->stream>>>(
-        h->emb, h->amag, q_dev, sb, static_cast<const uint32_t*>(h->tc_rows.p),
-        static_cast<const unsigned int*>(h->tc_cnt.p), kTcCandCap, h->pos_base,
-        static_cast<unsigned long long*>(h->tc_keys.p));
-  LAUNCHED(h);
-  knn_cand_finish_kernel<<<nqb, kSelThreads, kTcCandCap * 8, h->stream>>>(
-      static_cast<const unsigned long long*>(h->tc_keys.p), static_cast<const unsigned int*>(h->tc_cnt.p), kTcCandCap,
-      kprime, h->pos_base, h->rowid, h->movie_idx, cand_dev, status_dev);
+    knn_refine_kernel<false><<<nqb, kSelThreads, kTcCandCap * 8, h->stream>>>(
+        h->emb, h->amag, q_dev, sb, static_cast<const uint2*>(h->tc_rows.p),
+        static_cast<const unsigned int*>(h->tc_cnt.p), kTcCandCap, kprime, h->pos_base, h->rowid, h->movie_idx,
+        cand_dev, status_dev);
   LAUNCHED(h);
   return RSE_OK;
 }
