@@ -47,6 +47,11 @@ def parse_args():
     ap.add_argument("--cpu-sample", type=int, default=0, help="queries in the cpu_baseline sample (0 = 2 x cores)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-knn1", action="store_true", help="skip the batch-1 KNN micro-measurement")
+    ap.add_argument("--workload", default="hybrid600k", choices=["hybrid600k", "bm25_10k", "knn100m"],
+                    help="hybrid600k = configs[3] (the metric's configuration, default); bm25_10k = configs[1]; "
+                         "knn100m = configs[4] (12.5 M-row shard per GPU, top-100, NCCL candidate merge)")
+    ap.add_argument("--shard-rows", type=int, default=12_500_000)
     return ap.parse_args()
 
 
@@ -250,6 +255,8 @@ def run_b200(args, rank, world, local_rank):
         step_fn()
     e1.record(stream)
     torch.cuda.synchronize(); barrier()
+    sh_last = step_fn() if world > 1 else None
+    torch.cuda.synchronize(); barrier()
     ms = e0.elapsed_time(e1)
     clocks = sampler.stop()
     st = idx.stats()
@@ -301,7 +308,7 @@ def run_b200(args, rank, world, local_rank):
 
     # ---- batch-1 KNN (north_star: batch-1 kNN as a fraction of HBM peak): scan<QB=1> alone + whole call
     knn1 = None
-    if world == 1:
+    if world == 1 and not args.no_knn1:
         kp = max(limit * 10, limit)
         for _ in range(3):
             idx.knn_movies(Qn[:1], limit, kp)
@@ -315,6 +322,22 @@ def run_b200(args, rank, world, local_rank):
         sm1 = s1.scan_ms_total / max(1, s1.scan_launches_timed)
         knn1 = {"scan_ms": sm1, "call_ms_host_buffers": 1e3 * wall1, "launches_per_query": s1.kernel_launches / reps}
 
+    sharded_ok = None
+    if world > 1 and rank == 0:
+        # rank 0 generated the whole corpus: check the sharded result against a single-handle run
+        chk = _lib.Index(local_rank)
+        chk.set_stream(stream.cuda_stream)
+        mo_full = se.movie_of_chunk.contiguous()
+        chk.attach_embeddings_dev(se.emb.data_ptr(), C, info["dim"], movie_idx_ptr=mo_full.data_ptr(), keepalive=(se, mo_full))
+        chk.load_bm25(bm.indptr, bm.doc_idx, bm.tf, bm.df, bm.dl, bm.n_movies, bm.avgdl)
+        chk.set_id_tables(se.movie_ids, se.movie_ids)
+        oid, osc, oa, ob, oc = chk.hybrid(mode, param, limit, Qn, tok_indptr, terms)
+        r = sh_last
+        sharded_ok = bool((r.ids.cpu().numpy() == oid).all() and (r.score.cpu().numpy() == osc).all() and
+                          (r.count.cpu().numpy() == oc).all())
+        chk.close()
+    if world > 1:
+        dist.barrier()
     if rank != 0:
         return
     peaks = {}
@@ -345,7 +368,7 @@ def run_b200(args, rank, world, local_rank):
             "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps, "higher_is_better": True,
             "scaling": "strong", "vs_baseline": None, "dtype": "f32 scan + f64 tail/BM25/fusion", "data": "synthetic",
             "config": config_dict(args, info, world), "roofline": roofline, "clocks": clocks, "e2e": e2e,
-            "gpu_launches": launches, "knn_batch1": knn1, "postings_touched_per_step": postings_touched(bm, tok_indptr, terms)}
+            "gpu_launches": launches, "sharded_matches_single_gpu": sharded_ok, "knn_batch1": knn1, "postings_touched_per_step": postings_touched(bm, tok_indptr, terms)}
 
     if world == 1 and not args.no_cpu_baseline:
         cores = os.cpu_count() or 1
@@ -366,6 +389,139 @@ def run_b200(args, rank, world, local_rank):
     idx.close()
 
 
+def run_bm25_10k(args, local_rank):
+    """configs[1]: key_search BM25 top-10, 10k-query batch over the GPU CSR postings (host-buffer call)."""
+    import torch
+    from rag_search_engine_b200 import _lib, synth
+    torch.cuda.set_device(local_rank)
+    bm = synth.synth_bm25(args.movies, args.vocab, seed=1234, device=f"cuda:{local_rank}")
+    nq = 10_000
+    tok_indptr, terms = synth.synth_token_queries(bm, nq, seed=99)
+    idx = _lib.Index(local_rank)
+    idx.load_bm25(bm.indptr, bm.doc_idx, bm.tf, bm.df, bm.dl, bm.n_movies, bm.avgdl)
+    for _ in range(max(args.warmup, 3)):
+        sc, dc, cnt = idx.bm25(tok_indptr, terms, 10)
+    idx.stats_reset()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        sc, dc, cnt = idx.bm25(tok_indptr, terms, 10)
+    wall = (time.perf_counter() - t0) / args.steps
+    launches = int(idx.stats().kernel_launches)
+    touched = postings_touched(bm, tok_indptr, terms)
+    import oracle
+    cores = os.cpu_count() or 1
+    os.environ["OMP_NUM_THREADS"] = str(cores)
+    ns = 512
+    tp = tok_indptr[: ns + 1].astype(np.int32)
+    t0 = time.perf_counter()
+    osc, odc, ocnt = oracle.bm25_batch(bm.indptr, bm.doc_idx, bm.tf, bm.df, bm.dl, bm.n_movies, bm.avgdl, tp, terms[: tp[-1]], 10)
+    cpu_dt = time.perf_counter() - t0
+    ok = bool((odc == dc[:ns]).all() and (osc.view(np.uint64) == sc[:ns].view(np.uint64)).all() and (ocnt == cnt[:ns]).all())
+    peak = 6546.6
+    pk = ROOT / "MEASURED_PEAKS.json"
+    if pk.exists():
+        peak = float(json.loads(pk.read_text()).get("hbm_gbs", peak))
+    ach = touched * 12 / wall / 1e9
+    print(json.dumps({"metric": "BM25 top-10 queries/sec (10k-query batch)", "value": nq / wall, "unit": "queries/s",
+                      "n_gpus": 1, "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": 1e3 * wall,
+                      "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+                      "config": {"workload": "configs[1]: movies_600k-shaped BM25 index, 10k-query batch, top-10",
+                                 "docs": args.movies, "postings": int(len(bm.doc_idx)), "postings_touched": touched},
+                      "roofline": {"bound": "hbm", "kernel": "bm25_score_kernel", "achieved": ach, "peak": peak, "unit": "GB/s",
+                                   "frac": ach / peak, "traffic": None,
+                                   "note": "12 B per touched posting over the whole host-buffer call (H2D/D2H included)"},
+                      "e2e": {"value": nq / wall, "unit": "queries/s", "h2d_bytes_per_step": int(terms.nbytes * 3 + tok_indptr.nbytes),
+                              "d2h_bytes_per_step": int(sc.nbytes + dc.nbytes + cnt.nbytes)},
+                      "gpu_launches": launches,
+                      "cpu_baseline": {"value": ns / cpu_dt, "unit": "queries/s", "cores": cores, "kind": "port",
+                                       "sample": f"first {ns} queries of the batch (oracle.c BM25 over CSR, OpenMP)",
+                                       "gpu_matches_cpu_on_sample": ok}}), flush=True)
+    idx.close()
+
+
+def run_knn100m(args, rank, world, local_rank):
+    """configs[4]: synthetic 100M x 384 corpus as 12.5 M-row shards (one per GPU), top-100 with the NCCL
+    candidate merge.  Weak scaling: every rank always scans a full shard."""
+    import torch
+    import torch.distributed as dist
+    from rag_search_engine_b200 import _lib
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    rows = (args.shard_rows // 1024) * 1024
+    g = torch.Generator(device=dev).manual_seed(1234 + rank)
+    emb = torch.empty((rows, 384), dtype=torch.float32, device=dev)
+    for s0 in range(0, rows, 1 << 20):
+        e0_ = min(rows, s0 + (1 << 20))
+        x = torch.randn((e0_ - s0, 384), generator=g, device=dev)
+        emb[s0:e0_] = x / x.norm(dim=1, keepdim=True)
+    base = rank * rows
+    movie = (torch.arange(rows, device=dev, dtype=torch.int64) + base).to(torch.int32)
+    idx = _lib.Index(local_rank)
+    stream = torch.cuda.current_stream(dev)
+    idx.set_stream(stream.cuda_stream)
+    idx.attach_embeddings_dev(emb.data_ptr(), rows, 384, movie_idx_ptr=movie.data_ptr(), pos_base=base, keepalive=(emb, movie))
+    nq, kp = args.batch, 100
+    gq = torch.Generator(device=dev).manual_seed(99)
+    Q = torch.randn((nq, 384), generator=gq, device=dev)
+    Q /= Q.norm(dim=1, keepdim=True)
+    if rank == 0:
+        Q[: min(8, nq)] = emb[torch.arange(min(8, nq), device=dev) * 1000 + 5]       # known self-hits
+    if world > 1:
+        dist.broadcast(Q, 0)
+    cand = torch.empty((nq, kp, 3), dtype=torch.int64, device=dev)
+    flat = torch.empty((world * nq, kp, 3), dtype=torch.int64, device=dev)
+    od = torch.empty((nq, kp), dtype=torch.float32, device=dev); orow = torch.empty((nq, kp), dtype=torch.int64, device=dev)
+    om = torch.empty((nq, kp), dtype=torch.int32, device=dev); oc = torch.empty((nq,), dtype=torch.int32, device=dev)
+
+    def step():
+        idx.knn_local_dev(Q.data_ptr(), nq, kp, cand.data_ptr())
+        if world > 1:
+            dist.all_gather_into_tensor(flat, cand)
+            idx.knn_merge_movies_dev(flat.data_ptr(), world, nq, kp, kp, od.data_ptr(), orow.data_ptr(), om.data_ptr(), oc.data_ptr())
+        else:
+            idx.knn_merge_movies_dev(cand.data_ptr(), 1, nq, kp, kp, od.data_ptr(), orow.data_ptr(), om.data_ptr(), oc.data_ptr())
+
+    for _ in range(max(args.warmup, 3)):
+        step()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    idx.set_timing(True); idx.stats_reset()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
+    for _ in range(args.steps):
+        step()
+    e1.record(stream)
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1)
+    st = idx.stats()
+    if world > 1:
+        t = torch.tensor([ms], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+    if rank != 0:
+        return
+    ok = bool((od[: min(8, nq), 0] <= 1e-6).all().item() and (oc == kp).all().item())
+    peak = 6546.6
+    pk = ROOT / "MEASURED_PEAKS.json"
+    if pk.exists():
+        peak = float(json.loads(pk.read_text()).get("hbm_gbs", peak))
+    scan_ms = st.scan_ms_total / max(1, st.scan_launches_timed)
+    ach = rows * ROW_BYTES / (scan_ms * 1e-3) / 1e9
+    print(json.dumps({"metric": "kNN top-100 queries/sec x corpus chunks (row-sharded, NCCL candidate merge)",
+                      "value": nq * args.steps / (ms / 1e3) * world * rows, "unit": "query-chunks/s",
+                      "queries_per_s": nq * args.steps / (ms / 1e3), "n_gpus": world, "steps": args.steps,
+                      "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps, "higher_is_better": True,
+                      "scaling": "weak", "vs_baseline": None, "dtype": "tf32 filter + f32 exact re-score", "data": "synthetic",
+                      "config": {"workload": "configs[4]: synthetic 100M x 384 fp32 (12.5 M-row shard per GPU), top-100",
+                                 "rows_per_gpu": rows, "total_rows": rows * world, "queries_per_step": nq},
+                      "roofline": {"bound": "hbm", "kernel": "knn_tc_kernel<filter>" if st.tc_filter_launches else "knn_scan384_kernel",
+                                   "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": None,
+                                   "avg_launch_ms": scan_ms},
+                      "self_hits_found_and_full_k": ok, "gpu_launches": int(st.kernel_launches)}), flush=True)
+    idx.close()
+
+
 def main():
     args = parse_args()
     rank = int(os.environ.get("RANK", "0"))
@@ -380,7 +536,13 @@ def main():
         torch.cuda.set_device(local_rank)
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     try:
-        run_b200(args, rank, world, local_rank)
+        if args.workload == "bm25_10k":
+            if rank == 0:
+                run_bm25_10k(args, local_rank)
+        elif args.workload == "knn100m":
+            run_knn100m(args, rank, world, local_rank)
+        else:
+            run_b200(args, rank, world, local_rank)
     finally:
         if world > 1:
             import torch.distributed as dist

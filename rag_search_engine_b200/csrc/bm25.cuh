@@ -176,15 +176,31 @@ bm25_score_kernel(const int64_t* __restrict__ indptr, const uint2* __restrict__ 
     if (n == 0u) continue;            // uniform across the CTA
     const uint2* p = post + s_lo[t];
     const double idf = s_idf[t];
-    for (unsigned int i = threadIdx.x; i < n; i += blockDim.x) {
-      const uint2 e = __ldg(p + i);
-      const double nk = __ldg(normk + e.x);
-      const double tfd = static_cast<double>(e.y);
-      const double denom = __dadd_rn(tfd, nk);
-      const double add = __dmul_rn(idf, __ddiv_rn(__dmul_rn(tfd, k1p1), denom));
-      const uint32_t l = e.x - doc_base;
-      if (first[l] == 0xFF) first[l] = static_cast<unsigned char>(t);
-      acc[l] = __dadd_rn(acc[l], add);          // first touch is 0.0 + add
+    // 4 postings per thread per trip: all posting loads first, then all norm gathers, then the
+    // arithmetic — two dependent global loads per posting otherwise leave the warp on the long
+    // scoreboard (r01 ncu).  A document occurs once per list, so the 4 smem updates never alias.
+    for (unsigned int i0 = threadIdx.x; i0 < n; i0 += 4 * kBmThreads) {
+      uint2 e[4];
+      double nk[4];
+      bool ok[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const unsigned int i = i0 + j * kBmThreads;
+        ok[j] = i < n;
+        e[j] = ok[j] ? __ldg(p + i) : make_uint2(doc_base, 1u);
+      }
+#pragma unroll
+      for (int j = 0; j < 4; ++j) nk[j] = ok[j] ? __ldg(normk + e[j].x) : 1.0;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        if (!ok[j]) continue;
+        const double tfd = static_cast<double>(e[j].y);
+        const double denom = __dadd_rn(tfd, nk[j]);
+        const double add = __dmul_rn(idf, __ddiv_rn(__dmul_rn(tfd, k1p1), denom));
+        const uint32_t l = e[j].x - doc_base;
+        if (first[l] == 0xFF) first[l] = static_cast<unsigned char>(t);
+        acc[l] = __dadd_rn(acc[l], add);          // first touch is 0.0 + add
+      }
     }
     __syncthreads();
   }
