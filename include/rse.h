@@ -111,7 +111,9 @@ int rse_knn_movies(rse_index *h, const float *q_host, int32_t nq, int32_t k, int
  * Local top-kprime as packed candidates: cand_dev is [nq, kprime, 3] int64 =
  * {key, rowid, movie_idx}; key = (orderable(distance) << 32) | (global_pos ^ 1023),
  * so ascending key IS the vec0 emit order; unused tail entries have key = -1
- * (all ones).  q_dev is [nq, dim] fp32 on the device. */
+ * (all ones).  q_dev is [nq, dim] fp32 on the device.  Asynchronous on the handle's stream when
+ * the exact scan serves the batch; the tensor-core path (rse_set_tc_mode) synchronises once to
+ * read its per-query overflow flags. */
 int rse_knn_local_dev(rse_index *h, const float *q_dev, int32_t nq, int32_t kprime,
                       int64_t *cand_dev);
 /* Merge n_lists candidate lists per query (gathered_dev is [n_lists, nq, kprime, 3],

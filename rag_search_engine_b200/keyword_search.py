@@ -79,7 +79,7 @@ class KeywordSearch:
     def _load(self) -> None:
         reg = runtime.parts(self.db_path, self.device)
         if "bm25" not in reg:
-            arr = store.export_bm25(self.conn)
+            arr = store.load_or_export(self.conn, self.db_path, "bm25")
             self._index.load_bm25(arr.indptr, arr.doc_idx, arr.tf, arr.df, arr.dl, arr.n_movies, arr.avgdl)
             reg["bm25"] = arr
         self._arr: store.Bm25Arrays = reg["bm25"]

@@ -96,7 +96,7 @@ class SemanticSearch:
     def _load(self) -> None:
         reg = runtime.parts(self.db_path, self.device)
         if "emb" not in reg:
-            arr = store.export_embeddings(self.conn)
+            arr = store.load_or_export(self.conn, self.db_path, "emb")
             if arr.emb.shape[0] > 0:
                 self._index.load_embeddings(arr.emb, valid=arr.valid, rowid=arr.rowid, movie_idx=arr.movie_idx)
             reg["emb"] = arr

@@ -150,6 +150,65 @@ def export_embeddings(conn: sqlite3.Connection, table: str = VEC_TABLE) -> EmbAr
                      movie_ids=movie_ids, dim=int(dim))
 
 
+# ----------------------------------------------------------------------------- frozen sidecar
+SIDECAR_VERSION = 1
+
+
+def _db_fingerprint(conn: sqlite3.Connection, db_path) -> dict:
+    """What the reference's own sync-or-skip checks look at (basesearch_db.py:81-92,
+    keyword_search.py:87-100, semantic_search.py:145-154) plus the file's size and mtime."""
+    p = Path(db_path)
+    st = p.stat()
+    cur = conn.cursor()
+    counts = {}
+    for t in ("movies", "terms", "postings", "doclen", "chunks", f"{VEC_TABLE}_chunks"):
+        counts[t] = cur.execute(f"SELECT COUNT(*) FROM {t}").fetchone()[0] if _table_exists(conn, t) else -1
+    wal = Path(str(p) + "-wal")
+    return {"version": SIDECAR_VERSION, "size": st.st_size, "mtime_ns": st.st_mtime_ns,
+            "wal_size": wal.stat().st_size if wal.exists() else 0, "counts": counts}
+
+
+def sidecar_path(db_path, part: str) -> Path:
+    return Path(str(db_path) + f".rse-{part}.npz")
+
+
+def load_or_export(conn: sqlite3.Connection, db_path, part: str, use_cache: bool = True):
+    """part = 'bm25' | 'emb'.  Exports once and keeps an .npz next to the database; a later open
+    whose fingerprint matches loads the arrays without touching the big tables."""
+    exporter = {"bm25": export_bm25, "emb": export_embeddings}[part]
+    if not use_cache:
+        return exporter(conn)
+    fp = json.dumps(_db_fingerprint(conn, db_path), sort_keys=True)
+    sc = sidecar_path(db_path, part)
+    if sc.exists():
+        try:
+            with np.load(sc, allow_pickle=False) as z:
+                if str(z["fingerprint"]) == fp:
+                    if part == "bm25":
+                        terms = z["terms"].tolist()
+                        return Bm25Arrays(indptr=z["indptr"], doc_idx=z["doc_idx"], tf=z["tf"], df=z["df"], dl=z["dl"],
+                                          doc_ids=z["doc_ids"], n_movies=int(z["n_movies"]), avgdl=float(z["avgdl"]),
+                                          term_row={t: i for i, t in enumerate(terms)})
+                    valid = z["valid"] if int(z["has_valid"]) else None
+                    return EmbArrays(emb=z["emb"], valid=valid, rowid=z["rowid"], movie_idx=z["movie_idx"],
+                                     movie_ids=z["movie_ids"], dim=int(z["dim"]))
+        except Exception:
+            pass                                      # unreadable / stale sidecar → re-export
+    arr = exporter(conn)
+    try:
+        if part == "bm25":
+            terms = np.array([t for t, _ in sorted(arr.term_row.items(), key=lambda kv: kv[1])], dtype=np.str_)
+            np.savez(sc, fingerprint=np.str_(fp), indptr=arr.indptr, doc_idx=arr.doc_idx, tf=arr.tf, df=arr.df, dl=arr.dl,
+                     doc_ids=arr.doc_ids, n_movies=np.int64(arr.n_movies), avgdl=np.float64(arr.avgdl), terms=terms)
+        else:
+            np.savez(sc, fingerprint=np.str_(fp), emb=arr.emb, has_valid=np.int64(arr.valid is not None),
+                     valid=arr.valid if arr.valid is not None else np.zeros(0, np.uint8), rowid=arr.rowid,
+                     movie_idx=arr.movie_idx, movie_ids=arr.movie_ids, dim=np.int64(arr.dim))
+    except OSError:
+        pass                                          # read-only location: just skip the cache
+    return arr
+
+
 # ----------------------------------------------------------------------------- writer (reference on-disk format)
 def _init_schema(conn: sqlite3.Connection) -> None:
     cur = conn.cursor()

@@ -423,3 +423,35 @@ def test_tensor_core_path_overflow_falls_back_to_exact():
     for a, b in zip(out[1], out[2]):
         assert (a.view(np.uint8) == b.view(np.uint8)).all()
     assert (out[2][1][3] >= 5000).all() and (out[2][1][3] < 17000).all()
+
+
+def test_hybrid_large_batch_takes_tensor_core_path_and_matches_oracle(fresh_index):
+    """≥ 262 144 rows and ≥ 48 queries → the hybrid call routes its KNN through K4 automatically; the
+    fused lists must still equal the oracle pipeline bit for bit."""
+    from rag_search_engine_b200 import synth
+    n_movies = 36_000
+    se = synth.synth_embeddings(n_movies, seed=6, device="cuda")
+    assert se.emb.shape[0] >= 262_144
+    bm = synth.synth_bm25(n_movies, 20_000, seed=6, mean_len=40, sd_len=12, device="cuda")
+    nq, limit = 64, 10
+    tok_indptr, terms = synth.synth_token_queries(bm, nq, seed=12)
+    Q = synth.synth_query_vectors(se.emb, nq, seed=12).cpu().numpy()
+    ids = se.movie_ids
+    fresh_index.attach_embeddings_dev(se.emb.data_ptr(), se.emb.shape[0], 384, movie_idx_ptr=se.movie_of_chunk.data_ptr(),
+                                      keepalive=se)
+    fresh_index.load_bm25(bm.indptr, bm.doc_idx, bm.tf, bm.df, bm.dl, bm.n_movies, bm.avgdl)
+    fresh_index.set_id_tables(ids, ids)
+    oid, sc, a, b, cnt = fresh_index.hybrid(0, 60.0, limit, Q, tok_indptr, terms)
+    st = fresh_index.stats()
+    assert st.tc_queries == nq and st.tc_filter_launches == 1
+    emb = se.emb.cpu().numpy(); movie_of = se.movie_of_chunk.cpu().numpy()
+    sel = [0, 7, 31, 63]
+    kd, krow, kc = oracle.knn_movies_batch(emb, Q[sel], movie_of, limit, limit * 10, literal=False)
+    osc, odc, ocnt = oracle.bm25_batch(bm.indptr, bm.doc_idx, bm.tf, bm.df, bm.dl, bm.n_movies, bm.avgdl, tok_indptr,
+                                       terms, limit)
+    for i, qi in enumerate(sel):
+        bmh = [(int(ids[odc[qi, j]]), float(osc[qi, j])) for j in range(ocnt[qi])]
+        semh = [(int(ids[movie_of[krow[i, j]]]), float(kd[i, j])) for j in range(kc[i])]
+        want = pyref.rrf_fuse(bmh, semh, 60.0, limit)
+        got = [(int(oid[qi, j]), float(sc[qi, j])) for j in range(cnt[qi])]
+        assert got == [(x["id"], x["score"]) for x in want]

@@ -208,3 +208,28 @@ def test_shard_bounds_and_query_slices():
             assert b[0] == 0 and b[-1] == n and len(b) == w + 1
             assert all(x % 1024 == 0 for x in b[:-1]) and all(b[i] <= b[i + 1] for i in range(w))
     assert query_slices(10, 4) == [0, 3, 6, 8, 10] and query_slices(2, 4) == [0, 1, 2, 2, 2]
+
+
+def test_sidecar_cache_round_trip_and_invalidation(tmp_path):
+    from rag_search_engine_b200 import store
+    from rag_search_engine_b200.textutil import whitespace_tokenizer
+    docs, _, _ = _docs(9, 80)
+    rng = np.random.default_rng(1)
+    db = store.write_reference_db(tmp_path / "s.db", docs, whitespace_tokenizer,
+                                  embed=lambda texts: rng.standard_normal((len(texts), 8)).astype(np.float32))
+    conn = sqlite3.connect(db)
+    a = store.load_or_export(conn, db, "bm25")
+    e = store.load_or_export(conn, db, "emb")
+    assert store.sidecar_path(db, "bm25").exists() and store.sidecar_path(db, "emb").exists()
+    a2 = store.load_or_export(conn, db, "bm25")          # served from the sidecar
+    e2 = store.load_or_export(conn, db, "emb")
+    for f in ("indptr", "doc_idx", "tf", "df", "dl", "doc_ids"):
+        assert (getattr(a, f) == getattr(a2, f)).all()
+    assert a.term_row == a2.term_row and a.avgdl == a2.avgdl and a.n_movies == a2.n_movies
+    assert (e.emb == e2.emb).all() and (e.rowid == e2.rowid).all() and (e.movie_idx == e2.movie_idx).all() and e2.valid is None
+    # a change in the database invalidates the sidecar
+    conn.execute("INSERT INTO movies(id, title, description) VALUES (999999, 'x', 'y')")
+    conn.commit()
+    a3 = store.load_or_export(conn, db, "bm25")
+    assert a3.n_movies == a.n_movies + 1
+    conn.close()
