@@ -310,9 +310,10 @@ int knn_tc_block(rse_index* h, const float* q_dev, const double* sb, int nqb, in
   ENSURE(h->sel, sizeof(SelState) * kTcBN);
 
   const int64_t n_tiles = (h->n_rows + kTcBM - 1) / kTcBM;
-  const int64_t target = static_cast<int64_t>(h->sm_count) * 8;               // ≈1184 sample tiles ≈ 150 k rows
-  // expected survivors per query ≈ K' * tile_stride (+ the 2*eps band): keep that under a third of the cap
-  int64_t tile_stride = std::max<int64_t>(1, std::min<int64_t>(n_tiles / target, kTcCandCap / (3ll * kprime)));
+  // Probe sample: every tile_stride-th 128-row tile.  Expected survivors per query ≈ K' * tile_stride
+  // (+ the 2*eps band), so the stride is as large as a third of the survivor cap allows, while the
+  // sample keeps at least 64 tiles (and 8 K' rows) so its K'-th value is a meaningful bound.
+  int64_t tile_stride = std::max<int64_t>(1, std::min<int64_t>(kTcCandCap / (3ll * kprime), n_tiles / 64));
   int64_t n_probe = (n_tiles + tile_stride - 1) / tile_stride;
   while (n_probe * kTcBM < 8ll * kprime && tile_stride > 1) { tile_stride /= 2; n_probe = (n_tiles + tile_stride - 1) / tile_stride; }
   const int64_t ld_probe = n_probe * kTcBM;

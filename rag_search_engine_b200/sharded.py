@@ -63,7 +63,7 @@ class ShardBackend(Protocol):
         """Make queries lo..hi (tokens) the staged batch."""
 
     def fuse_merged(self, gathered_slice: torch.Tensor, mode: int, param: float, limit: int,
-                    knn_multiplier: int) -> Tuple[torch.Tensor, ...]:
+                    knn_multiplier: int, out=None) -> Tuple[torch.Tensor, ...]:
         """[world, nslice, kprime, 3] → (id i64, score f64, a f64, b f64 [nslice, limit], count i32 [nslice])."""
 
 
@@ -90,44 +90,45 @@ class ShardedHybrid:
         self.max_slice = max(self.slices[r + 1] - self.slices[r] for r in range(self.world))
         backend.stage_slice(self.lo, self.hi)
 
+    def _buffers(self, nq_all: int, kprime: int, limit: int, dev):
+        key = (nq_all, kprime, limit)
+        if getattr(self, "_buf_key", None) != key:
+            pad = self.max_slice
+            self._flat = torch.empty((self.world * nq_all, kprime, 3), dtype=torch.int64, device=dev)
+            self._mine = torch.empty((self.world, max(self.hi - self.lo, 1), kprime, 3), dtype=torch.int64, device=dev)
+            # one packed result block per rank: planes id(bits) / score / a / b / count, each [pad, limit] f64
+            self._pack = torch.zeros((5, pad, limit), dtype=torch.float64, device=dev)
+            self._allp = torch.empty((self.world * 5, pad, limit), dtype=torch.float64, device=dev)
+            self._cnt = torch.zeros((pad,), dtype=torch.int32, device=dev)
+            self._buf_key = key
+        return self._flat, self._mine, self._pack, self._allp, self._cnt
+
     def step(self, q_all: torch.Tensor, mode: int, param: float, limit: int, knn_multiplier: int = 10) -> HybridBatchResult:
         kprime = max(limit * knn_multiplier, limit)
         dev = self.backend.device
         cand = self.backend.knn_local(q_all, kprime)                                   # [nq, kp, 3]
-        if self.world > 1:
-            # flat [world*nq, kp, 3] output (the layout every backend accepts), viewed as [world, nq, kp, 3]
-            flat = torch.empty((self.world * cand.shape[0],) + tuple(cand.shape[1:]), dtype=cand.dtype, device=dev)
-            dist.all_gather_into_tensor(flat, cand, group=self.group)                  # the exchange step
-            gathered = flat.view((self.world,) + tuple(cand.shape))
-        else:
-            gathered = cand.unsqueeze(0)
         ns = self.hi - self.lo
-        pad = self.max_slice
-        out_id = torch.full((pad, limit), -1, dtype=torch.int64, device=dev)
-        out_sc = torch.zeros((pad, limit), dtype=torch.float64, device=dev)
-        out_a = torch.full((pad, limit), -1.0, dtype=torch.float64, device=dev)
-        out_b = torch.full((pad, limit), -1.0, dtype=torch.float64, device=dev)
-        out_c = torch.zeros((pad,), dtype=torch.int32, device=dev)
-        if ns > 0:
-            mine = gathered[:, self.lo:self.hi].contiguous()
-            i, s, a, b, c = self.backend.fuse_merged(mine, mode, param, limit, knn_multiplier)
-            out_id[:ns], out_sc[:ns], out_a[:ns], out_b[:ns], out_c[:ns] = i, s, a, b, c
         if self.world == 1:
-            return HybridBatchResult(out_id[:ns], out_sc[:ns], out_a[:ns], out_b[:ns], out_c[:ns])
-        # assemble the batch on every rank (small: nq·limit·32 B)
-        packed = torch.cat([out_id.view(torch.float64), out_sc, out_a, out_b], dim=1)  # [pad, 4*limit] f64 bits
-        allp = torch.empty((self.world * pad, packed.shape[1]), dtype=packed.dtype, device=dev)
-        allc = torch.empty((self.world * pad,), dtype=torch.int32, device=dev)
-        dist.all_gather_into_tensor(allp, packed, group=self.group)
-        dist.all_gather_into_tensor(allc, out_c, group=self.group)
-        allp = allp.view(self.world, pad, packed.shape[1])
-        allc = allc.view(self.world, pad)
-        rows = [allp[r, : self.slices[r + 1] - self.slices[r]] for r in range(self.world)]
-        cnts = [allc[r, : self.slices[r + 1] - self.slices[r]] for r in range(self.world)]
-        full = torch.cat(rows, 0)
-        L = limit
-        return HybridBatchResult(full[:, :L].contiguous().view(torch.int64), full[:, L:2 * L], full[:, 2 * L:3 * L],
-                                 full[:, 3 * L:4 * L], torch.cat(cnts, 0))
+            i, s, a, b, c = self.backend.fuse_merged(cand.unsqueeze(0), mode, param, limit, knn_multiplier)
+            return HybridBatchResult(i, s, a, b, c)
+        flat, mine, pack, allp, cnt = self._buffers(cand.shape[0], kprime, limit, dev)
+        dist.all_gather_into_tensor(flat, cand, group=self.group)                      # the exchange step
+        gathered = flat.view((self.world,) + tuple(cand.shape))
+        if ns > 0:
+            mine.copy_(gathered[:, self.lo:self.hi])                                   # this rank's query slice, contiguous
+            i, s, a, b, c = self.backend.fuse_merged(mine, mode, param, limit, knn_multiplier,
+                                                     out=(pack[0, :ns].view(torch.int64), pack[1, :ns], pack[2, :ns],
+                                                          pack[3, :ns], cnt[:ns]))
+            pack[4, :ns, 0] = cnt[:ns].to(torch.float64)
+        # assemble the batch on every rank (small: nq·limit·40 B): ONE all_gather of the packed block
+        dist.all_gather_into_tensor(allp, pack, group=self.group)
+        allv = allp.view(self.world, 5, self.max_slice, limit)
+        if self.nq % self.world == 0:
+            full = allv.permute(1, 0, 2, 3).reshape(5, self.nq, limit)
+        else:
+            full = torch.cat([allv[r, :, : self.slices[r + 1] - self.slices[r]] for r in range(self.world)], 1)
+        return HybridBatchResult(full[0].contiguous().view(torch.int64), full[1], full[2], full[3],
+                                 full[4, :, 0].to(torch.int32))
 
 
 class LibrseShardBackend:
@@ -158,14 +159,16 @@ class LibrseShardBackend:
         ptr = (self.tok_indptr[lo:hi + 1] - t0).astype(np.int32)
         self.index.hybrid_stage(self.q_host[lo:hi], ptr, self.term_rows[t0:t1])
 
-    def fuse_merged(self, gathered_slice, mode, param, limit, knn_multiplier):
+    def fuse_merged(self, gathered_slice, mode, param, limit, knn_multiplier, out=None):
         ns = gathered_slice.shape[1]
         dev = self.device
-        oid = torch.empty((ns, limit), dtype=torch.int64, device=dev)
-        osc = torch.empty((ns, limit), dtype=torch.float64, device=dev)
-        oa = torch.empty((ns, limit), dtype=torch.float64, device=dev)
-        ob = torch.empty((ns, limit), dtype=torch.float64, device=dev)
-        oc = torch.empty((ns,), dtype=torch.int32, device=dev)
+        if out is None:
+            out = (torch.empty((ns, limit), dtype=torch.int64, device=dev),
+                   torch.empty((ns, limit), dtype=torch.float64, device=dev),
+                   torch.empty((ns, limit), dtype=torch.float64, device=dev),
+                   torch.empty((ns, limit), dtype=torch.float64, device=dev),
+                   torch.empty((ns,), dtype=torch.int32, device=dev))
+        oid, osc, oa, ob, oc = out
         self.index.hybrid_run_merged_dev(mode, param, limit, gathered_slice.data_ptr(), gathered_slice.shape[0],
                                          oid.data_ptr(), osc.data_ptr(), oa.data_ptr(), ob.data_ptr(), oc.data_ptr(),
                                          knn_multiplier=knn_multiplier, k1=self.k1, b=self.b, tie_mode=self.tie_mode)

@@ -58,7 +58,7 @@ class OracleBackend:
     def stage_slice(self, lo, hi):
         self.slice = (lo, hi)
 
-    def fuse_merged(self, gathered, mode, param, limit, knn_multiplier):
+    def fuse_merged(self, gathered, mode, param, limit, knn_multiplier, out=None):
         lo, hi = self.slice
         kp = max(limit * knn_multiplier, limit)
         g = gathered.numpy()
@@ -85,7 +85,12 @@ class OracleBackend:
                 oa[s, j] = -1 if r["bm25_rank"] is None else r["bm25_rank"]
                 ob[s, j] = -1 if r["sem_rank"] is None else r["sem_rank"]
             oc[s] = len(res)
-        return tuple(torch.from_numpy(x) for x in (oid, osc, oa, ob, oc))
+        res = tuple(torch.from_numpy(x) for x in (oid, osc, oa, ob, oc))
+        if out is not None:
+            for dst, src in zip(out, res):
+                dst.copy_(src)
+            return out
+        return res
 
 
 def _worker(rank, world, port, out_q):
