@@ -52,6 +52,7 @@ def parse_args():
                     help="hybrid600k = configs[3] (the metric's configuration, default); bm25_10k = configs[1]; "
                          "knn100m = configs[4] (12.5 M-row shard per GPU, top-100, NCCL candidate merge)")
     ap.add_argument("--shard-rows", type=int, default=12_500_000)
+    ap.add_argument("--tc-mode", type=int, default=-1, help="rse_set_tc_mode override (see include/rse.h); -1 = library default")
     return ap.parse_args()
 
 
@@ -211,6 +212,8 @@ def run_b200(args, rank, world, local_rank):
     bounds = sharded.shard_bounds(C, world)
     lo, hi = bounds[rank], bounds[rank + 1]
     idx = _lib.Index(local_rank)
+    if args.tc_mode >= 0:
+        idx.set_tc_mode(args.tc_mode)
     stream = torch.cuda.current_stream(device)
     idx.set_stream(stream.cuda_stream)
     shard = se.emb[lo:hi]
@@ -457,6 +460,8 @@ def run_knn100m(args, rank, world, local_rank):
     base = rank * rows
     movie = (torch.arange(rows, device=dev, dtype=torch.int64) + base).to(torch.int32)
     idx = _lib.Index(local_rank)
+    if args.tc_mode >= 0:
+        idx.set_tc_mode(args.tc_mode)
     stream = torch.cuda.current_stream(dev)
     idx.set_stream(stream.cuda_stream)
     idx.attach_embeddings_dev(emb.data_ptr(), rows, 384, movie_idx_ptr=movie.data_ptr(), pos_base=base, keepalive=(emb, movie))

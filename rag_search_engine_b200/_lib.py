@@ -176,7 +176,8 @@ class Index:
         self._check(self._L.rse_set_timing(self._h, int(bool(on))))
 
     def set_tc_mode(self, mode: int):
-        """0 = auto, 1 = exact scan only, 2 = tensor-core path whenever the shape allows it."""
+        """0 = auto, 1 = exact scan only, 2 = tensor-core path whenever the shape allows it;
+        3 / 4 = like 0 / 2 with the TMEM-resident-queries (cta_group::2) filter kernel."""
         self._check(self._L.rse_set_tc_mode(self._h, int(mode)))
 
     def set_fma(self, on: bool):

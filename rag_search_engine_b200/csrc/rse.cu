@@ -17,6 +17,7 @@
 #include "knn_scan.cuh"
 #include "select.cuh"
 #include "knn_tc.cuh"
+#include "knn_tc2.cuh"
 
 using namespace rse;
 
@@ -52,6 +53,9 @@ struct rse_index {
   bool tmap_a_ok = false;
   CUtensorMap tmap_q{};            // [256][384]
   bool tmap_q_ok = false;
+  CUtensorMap tmap_b2{};           // [n_rows][384] f32, box {32, 64}: the half-tile the TMEM-resident kernel loads
+  bool tmap_b2_ok = false;
+  int tc_filter_kind = 0;          // 0 = knn_tc_kernel<1> (queries streamed), 1 = knn_tc2_filter_kernel (queries in TMEM)
   DevBuf tc_q, tc_thr, tc_isb, tc_rows, tc_cnt, tc_keys, tc_status;
 
   // ---- a1: embeddings (vec0 physical layout)
@@ -147,6 +151,7 @@ void release_embeddings(rse_index* h) {
   free_ptr(h->movie_idx);
   h->n_rows = 0; h->dim = 0;
   h->tmap_a_ok = false;
+  h->tmap_b2_ok = false;
 }
 
 void release_bm25(rse_index* h) {
@@ -366,10 +371,29 @@ int knn_tc_block(rse_index* h, const float* q_dev, const double* sb, int nqb, in
     h->scan_ev_used += 2;
     CK(cudaEventRecord(e0, h->stream));
   }
+  if (h->tc_filter_kind == 1) {
+    static bool attr2 = false;
+    if (!attr2) {
+      CK(cudaFuncSetAttribute(knn_tc2_filter_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kT2SmemBytes));
+      attr2 = true;
+    }
+    if (!h->tmap_b2_ok) {
+      int rc = make_tmap(h, &h->tmap_b2, h->emb, h->n_rows, kT2HalfRows);
+      if (rc != RSE_OK) return rc;
+      h->tmap_b2_ok = true;
+    }
+    const int64_t n_tiles2 = (h->n_rows + kT2TileRows - 1) / kT2TileRows;
+    const int n_clusters = static_cast<int>(std::min<int64_t>(h->sm_count / 2, n_tiles2));
+    knn_tc2_filter_kernel<<<2 * n_clusters, kT2Threads, kT2SmemBytes, h->stream>>>(
+        h->tmap_b2, tcq, h->amag, h->n_rows, n_tiles2, static_cast<const float*>(h->tc_thr.p),
+        static_cast<uint2*>(h->tc_rows.p), static_cast<unsigned int*>(h->tc_cnt.p), kTcCandCap);
+    LAUNCHED(h);
+  } else {
   knn_tc_kernel<1><<<grid_f, kTcThreads, kTcSmemBytes, h->stream>>>(
       h->tmap_a, h->tmap_q, h->amag, h->n_rows, n_tiles, 1, nqb, static_cast<const float*>(h->tc_thr.p), nullptr,
       nullptr, 0, static_cast<uint2*>(h->tc_rows.p), static_cast<unsigned int*>(h->tc_cnt.p), kTcCandCap);
   LAUNCHED(h);
+  }
   if (e1) CK(cudaEventRecord(e1, h->stream));
   h->stats.knn_scan_launches++;
   h->stats.tc_filter_launches++;
@@ -566,8 +590,10 @@ int rse_set_fma(rse_index* h, int32_t use_fma) {
 
 int rse_set_tc_mode(rse_index* h, int32_t mode) {
   if (!h) return RSE_ERR_INVALID;
-  if (mode < 0 || mode > 2) return fail(h, RSE_ERR_INVALID, "rse_set_tc_mode: mode must be 0 (auto), 1 (off) or 2 (on)");
-  h->tc_mode = mode;
+  if (mode < 0 || mode > 4) return fail(h, RSE_ERR_INVALID, "rse_set_tc_mode: mode must be 0..4");
+  // 3 / 4 = like 0 / 2 but the filter pass uses the TMEM-resident-queries kernel (cta_group::2)
+  h->tc_filter_kind = (mode >= 3) ? 1 : 0;
+  h->tc_mode = (mode == 3) ? 0 : (mode == 4 ? 2 : mode);
   return RSE_OK;
 }
 
