@@ -31,6 +31,28 @@ if str(ROOT) not in sys.path:
 import numpy as np  # noqa: E402
 
 ROW_BYTES = 384 * 4 + 4          # algorithmic bytes per chunk row per pass: 1536 B vector + 4 B |a|^2
+ROW_BYTES_SHADOW = 384 * 2       # the fp16-shadow filter pass (knn_tc3) streams 768 B per row and nothing else
+
+
+def tc_kind(args):
+    """Which K4 kernel rse_set_tc_mode selects (include/rse.h)."""
+    m = getattr(args, "tc_mode", -1)
+    return "f16-shadow" if m in (-1, 0, 2) else ("tf32-tmem" if m in (3, 4) else "tf32-streamed")
+
+
+def scan_kernel_desc(args, tc_used, qb):
+    if not tc_used:
+        return (f"knn_scan384_kernel<QB={qb}> (one pass over the shard serves {qb} queries; FFMA2-pipe-bound above QB=4, "
+                f"HBM-bound at QB=1: see knn_batch1)"), ROW_BYTES
+    k = tc_kind(args)
+    if k == "f16-shadow":
+        return ("knn_tc3_kernel<filter> (tcgen05 kind::f16 256x256x16 cta_group::2 over the fp16 normalised shadow, "
+                "queries resident in shared memory, TMA 8-stage; one pass serves 256 queries; survivors re-scored "
+                "exactly in fp32)"), ROW_BYTES_SHADOW
+    if k == "tf32-tmem":
+        return "knn_tc2_filter_kernel (tcgen05 TF32 cta_group::2, queries resident in TMEM)", ROW_BYTES
+    return ("knn_tc_kernel<filter> (tcgen05 TF32 128x256x8, TMA 3-stage, queries streamed from L2; one pass over the "
+            "shard serves 256 queries; survivors re-scored exactly)"), ROW_BYTES
 
 
 def parse_args():
@@ -349,14 +371,11 @@ def run_b200(args, rank, world, local_rank):
         peaks = json.loads(pk.read_text())
     peak = float(peaks.get("hbm_gbs", 6650.0))
     rows_local = hi - lo
-    alg_bytes = rows_local * ROW_BYTES
-    achieved = alg_bytes / (scan_ms * 1e-3) / 1e9 if scan_ms > 0 else None
     qb = 16 if nq >= 9 else (8 if nq >= 5 else (4 if nq >= 3 else nq))
     tc_used = int(st.tc_filter_launches) > 0
-    kname = ("knn_tc_kernel<filter> (tcgen05 TF32 128x256x8, TMA 4-stage, one pass over the shard serves 256 queries; "
-             "survivors re-scored exactly)") if tc_used else (
-        f"knn_scan384_kernel<QB={qb}> (one pass over the shard serves {qb} queries; FFMA2-pipe-bound above QB=4, "
-        f"HBM-bound at QB=1: see knn_batch1)")
+    kname, row_bytes = scan_kernel_desc(args, tc_used, qb)
+    alg_bytes = rows_local * row_bytes
+    achieved = alg_bytes / (scan_ms * 1e-3) / 1e9 if scan_ms > 0 else None
     roofline = {"bound": "hbm", "kernel": kname,
                 "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": (achieved / peak) if achieved else None,
                 "peak_source": "MEASURED_PEAKS.json hbm_gbs (of measured)" if peaks else "fallback 6650 GB/s (of fallback)",
@@ -365,7 +384,7 @@ def run_b200(args, rank, world, local_rank):
                 "tc_queries": int(st.tc_queries), "tc_fallback_queries": int(st.tc_fallback_queries)}
 
     if knn1:
-        g1 = alg_bytes / (knn1["scan_ms"] * 1e-3) / 1e9
+        g1 = rows_local * ROW_BYTES / (knn1["scan_ms"] * 1e-3) / 1e9
         knn1.update(achieved_gbs=g1, frac_of_measured_peak=g1 / peak, queries_per_s=1e3 / knn1["call_ms_host_buffers"])
     line = {"metric": "hybrid queries/sec", "value": value, "unit": "queries/s", "n_gpus": world, "steps": args.steps,
             "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps, "higher_is_better": True,
@@ -512,15 +531,16 @@ def run_knn100m(args, rank, world, local_rank):
     if pk.exists():
         peak = float(json.loads(pk.read_text()).get("hbm_gbs", peak))
     scan_ms = st.scan_ms_total / max(1, st.scan_launches_timed)
-    ach = rows * ROW_BYTES / (scan_ms * 1e-3) / 1e9
+    kname, row_bytes = scan_kernel_desc(args, int(st.tc_filter_launches) > 0, 16)
+    ach = rows * row_bytes / (scan_ms * 1e-3) / 1e9
     print(json.dumps({"metric": "kNN top-100 queries/sec x corpus chunks (row-sharded, NCCL candidate merge)",
                       "value": nq * args.steps / (ms / 1e3) * world * rows, "unit": "query-chunks/s",
                       "queries_per_s": nq * args.steps / (ms / 1e3), "n_gpus": world, "steps": args.steps,
                       "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps, "higher_is_better": True,
-                      "scaling": "weak", "vs_baseline": None, "dtype": "tf32 filter + f32 exact re-score", "data": "synthetic",
+                      "scaling": "weak", "vs_baseline": None, "dtype": f"{tc_kind(args)} filter + f32 exact re-score", "data": "synthetic",
                       "config": {"workload": "configs[4]: synthetic 100M x 384 fp32 (12.5 M-row shard per GPU), top-100",
                                  "rows_per_gpu": rows, "total_rows": rows * world, "queries_per_step": nq},
-                      "roofline": {"bound": "hbm", "kernel": "knn_tc_kernel<filter>" if st.tc_filter_launches else "knn_scan384_kernel",
+                      "roofline": {"bound": "hbm", "kernel": kname, "algorithmic_bytes_per_launch": rows * row_bytes,
                                    "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": None,
                                    "avg_launch_ms": scan_ms},
                       "self_hits_found_and_full_k": ok, "gpu_launches": int(st.kernel_launches)}), flush=True)

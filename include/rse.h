@@ -90,8 +90,10 @@ int rse_attach_embeddings_dev(rse_index *h, const float *emb_dev, int64_t n_rows
 int rse_set_fma(rse_index *h, int32_t use_fma);
 /* K4, the tcgen05 TF32 path for large query batches (probe → filter → EXACT re-score, results
  * identical to the streaming scan): 0 = auto (batches of ≥ 48 queries on ≥ 256 k rows, dim 384),
- * 1 = never, 2 = whenever the shape allows it; 3 / 4 = like 0 / 2 but the filter pass keeps the
- * queries resident in tensor memory (cta_group::2 kernel, knn_tc2.cuh). */
+ * 1 = never, 2 = whenever the shape allows it.  0 / 2 run the probe/filter GEMM over an fp16
+ * normalised shadow of the corpus (knn_tc3.cuh; built once, +768 B per row of device memory);
+ * 3 / 4 = like 0 / 2 with the TF32 kernel that keeps the queries in tensor memory (knn_tc2.cuh),
+ * 5 / 6 = like 0 / 2 with the TF32 kernel that streams the queries (knn_tc.cuh). */
 int rse_set_tc_mode(rse_index *h, int32_t mode);
 
 /* KNN: `embedding MATCH :q AND k = :k ... ORDER BY knn.distance`

@@ -176,8 +176,9 @@ class Index:
         self._check(self._L.rse_set_timing(self._h, int(bool(on))))
 
     def set_tc_mode(self, mode: int):
-        """0 = auto, 1 = exact scan only, 2 = tensor-core path whenever the shape allows it;
-        3 / 4 = like 0 / 2 with the TMEM-resident-queries (cta_group::2) filter kernel."""
+        """0 = auto, 1 = exact scan only, 2 = tensor-core path whenever the shape allows it (fp16-shadow
+        kernel); 3 / 4 = like 0 / 2 with the TF32 TMEM-resident-queries kernel; 5 / 6 = like 0 / 2 with
+        the TF32 streamed-queries kernel.  Results are identical in every mode."""
         self._check(self._L.rse_set_tc_mode(self._h, int(mode)))
 
     def set_fma(self, on: bool):

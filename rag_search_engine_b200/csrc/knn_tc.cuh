@@ -327,7 +327,10 @@ knn_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant_
 //       arithmetic of K1 (mac<FMA>, cosine_tail), lane-per-row straight from global memory;
 //   (c) the exact emit-order keys are sorted and the first K' emitted as packed candidates.
 // status[q] = 1 (host re-runs the query through K1/K2) when the survivor list or the refined
-// list overflowed.  smem: cap * 8 bytes (pairs) — reused for the exact keys.
+// list overflowed, or fewer than K' rows survived (a corpus/query the bound does not cover: fewer
+// than K' valid rows, zero or non-finite query norm).  `normalized`: the survivor values are cos~
+// (knn_tc3, unit-norm operands) instead of dot~/|a| (knn_tc / knn_tc2), so the band is not scaled by |q|.
+// smem: cap * 8 bytes (pairs) — reused for the exact keys.
 constexpr int kTcRefineCap = 2048;                         // rows re-scored exactly per query at most
 
 template <bool FMA>
@@ -336,7 +339,7 @@ knn_refine_kernel(const float* __restrict__ emb, const float* __restrict__ amag,
                   const double* __restrict__ sb, const uint2* __restrict__ cand_pairs,
                   const unsigned int* __restrict__ cand_count, int cap, int kprime, uint64_t pos_base,
                   const int64_t* __restrict__ rowid, const int32_t* __restrict__ movie_idx,
-                  long long* __restrict__ cand, int* __restrict__ status) {
+                  long long* __restrict__ cand, int* __restrict__ status, int normalized) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   uint2* pairs = reinterpret_cast<uint2*>(smem_raw);                       // [cap]
   __shared__ float s_q[kScanD];
@@ -352,7 +355,13 @@ knn_refine_kernel(const float* __restrict__ emb, const float* __restrict__ amag,
     return;
   }
   const int n = static_cast<int>(cnt);
-  for (int i = threadIdx.x; i < n; i += blockDim.x) pairs[i] = cand_pairs[static_cast<int64_t>(qi) * cap + i];
+  // survivors that are empty vec0 slots (knn_tc3 does not look at |a|^2 in its epilogue) get value -inf:
+  // they can neither be the K'-th largest (unless fewer than K' valid rows survived → exact scan) nor pass the cut
+  for (int i = threadIdx.x; i < n; i += blockDim.x) {
+    uint2 pr = cand_pairs[static_cast<int64_t>(qi) * cap + i];
+    if (!(__ldg(amag + pr.x) > 0.0f)) pr.y = 0xFF800000u;
+    pairs[i] = pr;
+  }
   for (int i = threadIdx.x; i < kScanD; i += blockDim.x) s_q[i] = q[static_cast<int64_t>(qi) * kScanD + i];
   if (threadIdx.x == 0) { s_prefix = 0u; s_need = static_cast<unsigned int>(kprime < n ? kprime : n); s_m = 0u; }
   __syncthreads();
@@ -389,19 +398,19 @@ knn_refine_kernel(const float* __restrict__ emb, const float* __restrict__ amag,
   float cut = -__int_as_float(0x7F800000);
   if (n > kprime) {
     const float s_k = __uint_as_float(f32_from_orderable(~s_prefix));
-    const float qn = static_cast<float>(sb[qi]);
+    const float qn = normalized ? 1.0f : static_cast<float>(sb[qi]);
     cut = s_k - (2.0f * kTcEps + 1e-6f) * qn - 1e-30f;
   }
   for (int i = threadIdx.x; i < n; i += blockDim.x) {
     const uint2 pr = pairs[i];
-    if (__uint_as_float(pr.y) >= cut) {
+    if (__uint_as_float(pr.y) >= cut && pr.y != 0xFF800000u) {
       const unsigned int slot = atomicAdd(&s_m, 1u);
       if (slot < kTcRefineCap) s_rows[slot] = pr.x;
     }
   }
   __syncthreads();
   const unsigned int m = s_m;
-  if (m > kTcRefineCap) {                                                  // refined list overflow (mass ties)
+  if (m > kTcRefineCap || m < static_cast<unsigned int>(kprime)) {         // refined list overflow (mass ties) / too few rows
     if (threadIdx.x == 0) status[qi] = 1;
     for (int i = threadIdx.x; i < kprime * 3; i += blockDim.x) out[i] = -1ll;
     return;

@@ -18,6 +18,7 @@
 #include "select.cuh"
 #include "knn_tc.cuh"
 #include "knn_tc2.cuh"
+#include "knn_tc3.cuh"
 
 using namespace rse;
 
@@ -55,8 +56,15 @@ struct rse_index {
   bool tmap_q_ok = false;
   CUtensorMap tmap_b2{};           // [n_rows][384] f32, box {32, 64}: the half-tile the TMEM-resident kernel loads
   bool tmap_b2_ok = false;
-  int tc_filter_kind = 0;          // 0 = knn_tc_kernel<1> (queries streamed), 1 = knn_tc2_filter_kernel (queries in TMEM)
+  int tc_filter_kind = 2;          // 2 = knn_tc3_kernel (fp16 normalised shadow, queries resident in shared memory; default),
+                                   // 0 = knn_tc_kernel<1> (TF32, queries streamed), 1 = knn_tc2_filter_kernel (TF32, queries in TMEM)
   DevBuf tc_q, tc_thr, tc_isb, tc_rows, tc_cnt, tc_keys, tc_status;
+  // fp16 normalised shadow of the corpus for knn_tc3 (built lazily at the first tensor-core batch)
+  DevBuf tc_shadow, tc_q16;
+  int shadow_state = 0;            // 0 = not built, 1 = usable, -1 = corpus has non-finite norms: exact scan only
+  CUtensorMap tmap_a16{};          // [n_rows][384] f16, box {64, 128}, SWIZZLE_128B
+  CUtensorMap tmap_q16{};          // [256][384] f16, box {64, 128}
+  bool tmap_q16_ok = false;
 
   // ---- a1: embeddings (vec0 physical layout)
   const float* emb = nullptr;
@@ -152,6 +160,8 @@ void release_embeddings(rse_index* h) {
   h->n_rows = 0; h->dim = 0;
   h->tmap_a_ok = false;
   h->tmap_b2_ok = false;
+  free_buf(h->tc_shadow);
+  h->shadow_state = 0;
 }
 
 void release_bm25(rse_index* h) {
@@ -258,7 +268,14 @@ typedef CUresult (*PFN_tmapEncodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuin
                                         const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
                                         CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 
+int make_tmap_any(rse_index* h, CUtensorMap* out, const void* base, int64_t rows, int box_rows, int elem_bytes);
+
 int make_tmap(rse_index* h, CUtensorMap* out, const float* base, int64_t rows, int box_rows) {
+  return make_tmap_any(h, out, base, rows, box_rows, 4);
+}
+
+// [rows][384] row-major matrix of f32 (elem_bytes 4) or f16 (2); box = one 128-byte swizzle atom x box_rows
+int make_tmap_any(rse_index* h, CUtensorMap* out, const void* base, int64_t rows, int box_rows, int elem_bytes) {
   static PFN_tmapEncodeTiled fn = nullptr;
   if (!fn) {
     void* p = nullptr;
@@ -268,14 +285,161 @@ int make_tmap(rse_index* h, CUtensorMap* out, const float* base, int64_t rows, i
     fn = reinterpret_cast<PFN_tmapEncodeTiled>(p);
   }
   const cuuint64_t gdim[2] = {static_cast<cuuint64_t>(kScanD), static_cast<cuuint64_t>(rows)};
-  const cuuint64_t gstr[1] = {static_cast<cuuint64_t>(kScanD) * 4};
-  const cuuint32_t box[2] = {static_cast<cuuint32_t>(kTcBK), static_cast<cuuint32_t>(box_rows)};
+  const cuuint64_t gstr[1] = {static_cast<cuuint64_t>(kScanD) * elem_bytes};
+  const cuuint32_t box[2] = {static_cast<cuuint32_t>(128 / elem_bytes), static_cast<cuuint32_t>(box_rows)};
   const cuuint32_t estr[2] = {1, 1};
-  CUresult r = fn(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(base), gdim, gstr, box, estr,
+  CUresult r = fn(out, elem_bytes == 4 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2,
+                  const_cast<void*>(base), gdim, gstr, box, estr,
                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) return fail(h, RSE_ERR_CUDA, "cuTensorMapEncodeTiled failed: " + std::to_string(static_cast<int>(r)));
   return RSE_OK;
+}
+
+// refine + exact re-score + emit for one block of queries whose survivors are in tc_rows / tc_cnt
+int knn_tc_refine(rse_index* h, const float* q_dev, const double* sb, int nqb, int kprime, long long* cand_dev,
+                  int* status_dev, int normalized) {
+  static bool attrs = false;
+  if (!attrs) {
+    CK(cudaFuncSetAttribute(knn_refine_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kTcCandCap * 8));
+    CK(cudaFuncSetAttribute(knn_refine_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kTcCandCap * 8));
+    attrs = true;
+  }
+  if (h->fma)
+    knn_refine_kernel<true><<<nqb, kSelThreads, kTcCandCap * 8, h->stream>>>(
+        h->emb, h->amag, q_dev, sb, static_cast<const uint2*>(h->tc_rows.p),
+        static_cast<const unsigned int*>(h->tc_cnt.p), kTcCandCap, kprime, h->pos_base, h->rowid, h->movie_idx,
+        cand_dev, status_dev, normalized);
+  else
+    knn_refine_kernel<false><<<nqb, kSelThreads, kTcCandCap * 8, h->stream>>>(
+        h->emb, h->amag, q_dev, sb, static_cast<const uint2*>(h->tc_rows.p),
+        static_cast<const unsigned int*>(h->tc_cnt.p), kTcCandCap, kprime, h->pos_base, h->rowid, h->movie_idx,
+        cand_dev, status_dev, normalized);
+  LAUNCHED(h);
+  return RSE_OK;
+}
+
+// record a CUDA-event pair around the dominant kernel of a pass (resolved lazily in rse_get_stats)
+int scan_event(rse_index* h, cudaEvent_t* out) {
+  *out = nullptr;
+  if (!h->timing || h->scan_ev_used + 1 > (1u << 16)) return RSE_OK;
+  while (h->scan_ev.size() < h->scan_ev_used + 1) {
+    cudaEvent_t e;
+    CK(cudaEventCreate(&e));
+    h->scan_ev.push_back(e);
+  }
+  *out = h->scan_ev[h->scan_ev_used++];
+  CK(cudaEventRecord(*out, h->stream));
+  return RSE_OK;
+}
+
+// Build the fp16 normalised shadow (knn_tc3.cuh) once per corpus.  Returns RSE_OK with shadow_state = -1
+// when the corpus holds rows whose squared norm is not finite (the error bound needs a finite norm).
+int ensure_shadow(rse_index* h) {
+  if (h->shadow_state != 0) return RSE_OK;
+  ENSURE(h->tc_shadow, sizeof(__half) * static_cast<size_t>(h->n_rows) * kScanD + 16);
+  ENSURE(h->tc_cnt, sizeof(unsigned int) * kTcBN);
+  unsigned int* bad = static_cast<unsigned int*>(h->tc_cnt.p);
+  CK(cudaMemsetAsync(bad, 0, sizeof(unsigned int), h->stream));
+  const int grid = h->sm_count * 8;
+  tc3_shadow_kernel<<<grid, 256, 0, h->stream>>>(h->emb, h->amag, h->n_rows, static_cast<__half*>(h->tc_shadow.p), bad);
+  LAUNCHED(h);
+  unsigned int nbad = 0;
+  CK(cudaMemcpyAsync(&nbad, bad, sizeof(unsigned int), cudaMemcpyDeviceToHost, h->stream));
+  CK(cudaStreamSynchronize(h->stream));
+  if (nbad) {
+    free_buf(h->tc_shadow);
+    h->shadow_state = -1;
+    return RSE_OK;
+  }
+  int rc = make_tmap_any(h, &h->tmap_a16, h->tc_shadow.p, h->n_rows, kT3HalfRows, 2);
+  if (rc != RSE_OK) return rc;
+  h->shadow_state = 1;
+  return RSE_OK;
+}
+
+// ---- K4 over the fp16 shadow (knn_tc3.cuh) for one block of ≤ 256 queries
+int knn_tc3_block(rse_index* h, const float* q_dev, const double* sb, int nqb, int kprime, long long* cand_dev,
+                  int* status_dev) {
+  static bool attrs = false;
+  if (!attrs) {
+    CK(cudaFuncSetAttribute(knn_tc3_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, kT3SmemBytes));
+    CK(cudaFuncSetAttribute(knn_tc3_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, kT3SmemBytes));
+    attrs = true;
+  }
+  ENSURE(h->tc_q16, sizeof(__half) * kTcBN * kScanD);
+  if (!h->tmap_q16_ok) {
+    int rc = make_tmap_any(h, &h->tmap_q16, h->tc_q16.p, kTcBN, kT3HalfRows, 2);
+    if (rc != RSE_OK) return rc;
+    h->tmap_q16_ok = true;
+  }
+  ENSURE(h->tc_thr, sizeof(float) * kTcBN);
+  ENSURE(h->tc_rows, sizeof(uint2) * static_cast<size_t>(kTcBN) * kTcCandCap);
+  ENSURE(h->tc_cnt, sizeof(unsigned int) * kTcBN);
+  ENSURE(h->sel, sizeof(SelState) * kTcBN);
+
+  const int64_t n_tiles = (h->n_rows + kT3TileRows - 1) / kT3TileRows;
+  const int max_clusters = std::max(1, h->sm_count / 2);
+  // Probe sample: every tile_stride-th 256-row tile.  Expected survivors per query ≈ K' * tile_stride
+  // (+ the 2*eps band), so the stride is as large as a third of the survivor cap allows, while the
+  // sample keeps at least 64 tiles (and 8 K' rows) so its K'-th value is a meaningful bound.
+  int64_t tile_stride = std::max<int64_t>(1, std::min<int64_t>(kTcCandCap / (3ll * kprime), n_tiles / 64));
+  int64_t n_probe = (n_tiles + tile_stride - 1) / tile_stride;
+  while (n_probe * kT3TileRows < 8ll * kprime && tile_stride > 1) { tile_stride /= 2; n_probe = (n_tiles + tile_stride - 1) / tile_stride; }
+  const int64_t ld_probe = n_probe * kT3TileRows;
+  ENSURE(h->dist, std::max(sizeof(float) * static_cast<size_t>(kScanMaxQB) * h->dist_ld,
+                           sizeof(uint32_t) * static_cast<size_t>(nqb) * ld_probe));
+  uint32_t* dist = static_cast<uint32_t*>(h->dist.p);
+  SelState* sel = static_cast<SelState*>(h->sel.p);
+  unsigned int* hist = static_cast<unsigned int*>(h->hist.p);
+  __half* q16 = static_cast<__half*>(h->tc_q16.p);
+  float* thr = static_cast<float*>(h->tc_thr.p);
+
+  tc3_query_prep_kernel<<<kTcBN, kScanD / 4, 0, h->stream>>>(q_dev, sb, nqb, q16);
+  LAUNCHED(h);
+
+  // 1. probe: approximate distances of a strided sample of tiles → K'-th smallest per query
+  const int grid_p = 2 * static_cast<int>(std::min<int64_t>(max_clusters, n_probe));
+  knn_tc3_kernel<0><<<grid_p, kT3Threads, kT3SmemBytes, h->stream>>>(
+      h->tmap_a16, h->tmap_q16, n_probe, tile_stride, nqb, nullptr, dist, ld_probe, nullptr, nullptr, 0);
+  LAUNCHED(h);
+  select_init_kernel<<<(nqb + 127) / 128, 128, 0, h->stream>>>(sel, nqb, static_cast<unsigned int>(kprime));
+  LAUNCHED(h);
+  {
+    int blocks = static_cast<int>(std::min<int64_t>((ld_probe + 4095) / 4096, h->sm_count));
+    if (blocks < 1) blocks = 1;
+    dim3 grid(blocks, nqb);
+    static const int shifts[3] = {53, 42, 32};
+    static const int widths[3] = {11, 11, 10};
+    for (int p = 0; p < 3; ++p) {
+      select_pass_kernel<<<grid, kSelThreads, 0, h->stream>>>(dist, ld_probe, ld_probe, 0ull, sel, hist, shifts[p], widths[p]);
+      LAUNCHED(h);
+    }
+  }
+  tc3_threshold_kernel<<<2, 128, 0, h->stream>>>(sel, sb, nqb, thr);
+  LAUNCHED(h);
+
+  // 2. filter pass over all rows
+  CK(cudaMemsetAsync(h->tc_cnt.p, 0, sizeof(unsigned int) * kTcBN, h->stream));
+  const int grid_f = 2 * static_cast<int>(std::min<int64_t>(max_clusters, n_tiles));
+  cudaEvent_t e0 = nullptr, e1 = nullptr;
+  if (h->timing && h->scan_ev_used + 2 <= (1u << 16)) {
+    int rc = scan_event(h, &e0);
+    if (rc != RSE_OK) return rc;
+  }
+  knn_tc3_kernel<1><<<grid_f, kT3Threads, kT3SmemBytes, h->stream>>>(
+      h->tmap_a16, h->tmap_q16, n_tiles, 1, nqb, thr, nullptr, 0, static_cast<uint2*>(h->tc_rows.p),
+      static_cast<unsigned int*>(h->tc_cnt.p), kTcCandCap);
+  LAUNCHED(h);
+  if (e0) {
+    int rc = scan_event(h, &e1);
+    if (rc != RSE_OK) return rc;
+  }
+  h->stats.knn_scan_launches++;
+  h->stats.tc_filter_launches++;
+
+  // 3. refine on the approximate values, 4. exact re-score + sort + emit (one CTA per query)
+  return knn_tc_refine(h, q_dev, sb, nqb, kprime, cand_dev, status_dev, 1);
 }
 
 bool tc_eligible(const rse_index* h, int nq, int kprime) {
@@ -293,8 +457,6 @@ int knn_tc_block(rse_index* h, const float* q_dev, const double* sb, int nqb, in
   if (!attrs) {
     CK(cudaFuncSetAttribute(knn_tc_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, kTcSmemBytes));
     CK(cudaFuncSetAttribute(knn_tc_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, kTcSmemBytes));
-    CK(cudaFuncSetAttribute(knn_refine_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kTcCandCap * 8));
-    CK(cudaFuncSetAttribute(knn_refine_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kTcCandCap * 8));
     attrs = true;
   }
   if (!h->tmap_a_ok) {
@@ -399,18 +561,7 @@ int knn_tc_block(rse_index* h, const float* q_dev, const double* sb, int nqb, in
   h->stats.tc_filter_launches++;
 
   // 3. refine on the approximate values, 4. exact re-score + sort + emit (one CTA per query)
-  if (h->fma)
-    knn_refine_kernel<true><<<nqb, kSelThreads, kTcCandCap * 8, h->stream>>>(
-        h->emb, h->amag, q_dev, sb, static_cast<const uint2*>(h->tc_rows.p),
-        static_cast<const unsigned int*>(h->tc_cnt.p), kTcCandCap, kprime, h->pos_base, h->rowid, h->movie_idx,
-        cand_dev, status_dev);
-  else
-    knn_refine_kernel<false><<<nqb, kSelThreads, kTcCandCap * 8, h->stream>>>(
-        h->emb, h->amag, q_dev, sb, static_cast<const uint2*>(h->tc_rows.p),
-        static_cast<const unsigned int*>(h->tc_cnt.p), kTcCandCap, kprime, h->pos_base, h->rowid, h->movie_idx,
-        cand_dev, status_dev);
-  LAUNCHED(h);
-  return RSE_OK;
+  return knn_tc_refine(h, q_dev, sb, nqb, kprime, cand_dev, status_dev, 0);
 }
 
 // Local top-kprime for nq device-resident queries → packed candidates (device).
@@ -434,9 +585,17 @@ int knn_local(rse_index* h, const float* q_dev, int nq, int kprime, long long* c
   // ---- tensor-core path in blocks of 256 queries, exact fallback for overflowed queries
   ENSURE(h->tc_status, sizeof(int) * nq);
   int* status = static_cast<int*>(h->tc_status.p);
+  bool use_shadow = h->tc_filter_kind == 2;
+  if (use_shadow) {
+    int rc = ensure_shadow(h);
+    if (rc != RSE_OK) return rc;
+    if (h->shadow_state < 0) return knn_exact_groups(h, q_dev, sb, nq, kprime, cand_dev);
+  }
   for (int b0 = 0; b0 < nq; b0 += kTcBN) {
     const int nqb = std::min(kTcBN, nq - b0);
-    int rc = knn_tc_block(h, q_dev + static_cast<int64_t>(b0) * h->dim, sb + b0, nqb, kprime,
+    int rc = use_shadow ? knn_tc3_block(h, q_dev + static_cast<int64_t>(b0) * h->dim, sb + b0, nqb, kprime,
+                                        cand_dev + static_cast<int64_t>(b0) * kprime * 3, status + b0)
+                        : knn_tc_block(h, q_dev + static_cast<int64_t>(b0) * h->dim, sb + b0, nqb, kprime,
                           cand_dev + static_cast<int64_t>(b0) * kprime * 3, status + b0);
     if (rc != RSE_OK) return rc;
   }
@@ -590,10 +749,11 @@ int rse_set_fma(rse_index* h, int32_t use_fma) {
 
 int rse_set_tc_mode(rse_index* h, int32_t mode) {
   if (!h) return RSE_ERR_INVALID;
-  if (mode < 0 || mode > 4) return fail(h, RSE_ERR_INVALID, "rse_set_tc_mode: mode must be 0..4");
-  // 3 / 4 = like 0 / 2 but the filter pass uses the TMEM-resident-queries kernel (cta_group::2)
-  h->tc_filter_kind = (mode >= 3) ? 1 : 0;
-  h->tc_mode = (mode == 3) ? 0 : (mode == 4 ? 2 : mode);
+  if (mode < 0 || mode > 6) return fail(h, RSE_ERR_INVALID, "rse_set_tc_mode: mode must be 0..6");
+  // 0 / 2: fp16-shadow kernel (knn_tc3); 3 / 4: TF32, queries resident in TMEM (knn_tc2);
+  // 5 / 6: TF32, queries streamed (knn_tc) — auto / forced respectively
+  h->tc_filter_kind = (mode >= 5) ? 0 : (mode >= 3 ? 1 : 2);
+  h->tc_mode = (mode == 3 || mode == 5) ? 0 : ((mode == 4 || mode == 6) ? 2 : mode);
   return RSE_OK;
 }
 

@@ -364,8 +364,9 @@ def test_sharded_merge_equals_single_index():
 # ----------------------------------------------------------------------------- K4 tensor-core path
 @pytest.mark.parametrize("n,nq,kprime", [(40_000, 70, 100), (9_000, 256, 50), (33_000, 300, 100), (5_000, 5, 10)])
 def test_tensor_core_path_equals_exact_scan_and_oracle(n, nq, kprime):
-    """K4 (TF32 tcgen05 probe/filter + exact re-score) must return exactly what the exact scan returns:
-    same rows, same order, bit-identical distances — including duplicate rows (ties) and non-unit norms."""
+    """K4 (tcgen05 probe/filter + exact re-score) must return exactly what the exact scan returns:
+    same rows, same order, bit-identical distances — including duplicate rows (ties) and non-unit norms.
+    Mode 2 = fp16-shadow kernel (the default), 4 = TF32 with queries in TMEM, 6 = TF32 with streamed queries."""
     from rag_search_engine_b200 import _lib
     rng = np.random.default_rng(n + nq)
     centers = unit_rows(rng, 50, 384)
@@ -376,22 +377,23 @@ def test_tensor_core_path_equals_exact_scan_and_oracle(n, nq, kprime):
     Q[0] = emb[7]
     movie_of = (np.arange(n) // 6).astype(np.int32)
     res = {}
-    for mode in (1, 2):
+    for mode in (1, 2, 4, 6):
         idx = _lib.Index(0)
         try:
             idx.set_tc_mode(mode)
             idx.load_embeddings(emb, movie_idx=movie_of)
             res[mode] = idx.knn(Q, kprime) + idx.knn_movies(Q, 10, kprime)
             st = idx.stats()
-            if mode == 2:
+            if mode != 1:
                 assert st.tc_queries == 2 * nq and st.tc_filter_launches >= 2, "tensor-core path did not run"
                 assert st.tc_fallback_queries <= nq // 4
             else:
                 assert st.tc_queries == 0
         finally:
             idx.close()
-    for a, b in zip(res[1], res[2]):
-        assert a.dtype == b.dtype and (a.view(np.uint8) == b.view(np.uint8)).all()
+    for mode in (2, 4, 6):
+        for a, b in zip(res[1], res[mode]):
+            assert a.dtype == b.dtype and (a.view(np.uint8) == b.view(np.uint8)).all(), f"tc_mode {mode}"
     dist, pos = res[2][0], res[2][1]
     for qi in (0, nq // 2, nq - 1):
         od, orow = oracle.vec0_knn(emb, Q[qi], kprime, literal=False)
@@ -410,6 +412,42 @@ def test_tensor_core_path_overflow_falls_back_to_exact():
     Q = unit_rows(rng, 64, 384)
     Q[3] = emb[5000] + 0.01 * unit_rows(rng, 1, 384)[0]
     out = {}
+    for mode in (1, 2, 6):
+        idx = _lib.Index(0)
+        try:
+            idx.set_tc_mode(mode)
+            idx.load_embeddings(emb)
+            out[mode] = idx.knn(Q, 100)
+            if mode != 1:
+                assert idx.stats().tc_fallback_queries >= 1
+        finally:
+            idx.close()
+    for mode in (2, 6):
+        for a, b in zip(out[1], out[mode]):
+            assert (a.view(np.uint8) == b.view(np.uint8)).all()
+    assert (out[2][1][3] >= 5000).all() and (out[2][1][3] < 17000).all()
+
+
+@pytest.mark.parametrize("zero_rows", [False, True])
+def test_tensor_core_path_degenerate_rows_and_queries(zero_rows):
+    """Zero-norm query, empty vec0 slots past the end of a tile, tiny / huge norms and a wide dynamic range
+    inside rows: the fp16-shadow filter must never lose a row of the exact top-K' (the zero-norm query is
+    handed to the exact scan).  With zero-norm ROWS in the corpus the exact distance is NaN, which the
+    filter bound cannot cover: the index must stay on the exact scan altogether."""
+    from rag_search_engine_b200 import _lib
+    rng = np.random.default_rng(5)
+    n = 20_000
+    emb = unit_rows(rng, n, 384)
+    emb[::7] *= np.float32(1e-3)                                  # tiny norms
+    emb[1::11] *= np.float32(3e4)                                 # huge norms (fp16 could not hold these unscaled)
+    emb[2::13, :200] *= np.float32(1e-6)                          # components far below the fp16 normal range
+    if zero_rows:
+        emb[500:520] = 0.0
+    Q = unit_rows(rng, 64, 384)
+    Q[1] = 0.0                                                    # zero-norm query
+    Q[2] = emb[1] * np.float32(1e-4)
+    Q[3] = emb[2] + np.float32(1e-3) * unit_rows(rng, 1, 384)[0]
+    out = {}
     for mode in (1, 2):
         idx = _lib.Index(0)
         try:
@@ -417,12 +455,15 @@ def test_tensor_core_path_overflow_falls_back_to_exact():
             idx.load_embeddings(emb)
             out[mode] = idx.knn(Q, 100)
             if mode == 2:
-                assert idx.stats().tc_fallback_queries >= 1
+                st = idx.stats()
+                if zero_rows:
+                    assert st.tc_queries == 0 and st.tc_filter_launches == 0
+                else:
+                    assert st.tc_queries == 64 and 1 <= st.tc_fallback_queries <= 8
         finally:
             idx.close()
     for a, b in zip(out[1], out[2]):
         assert (a.view(np.uint8) == b.view(np.uint8)).all()
-    assert (out[2][1][3] >= 5000).all() and (out[2][1][3] < 17000).all()
 
 
 def test_hybrid_large_batch_takes_tensor_core_path_and_matches_oracle(fresh_index):
