@@ -96,15 +96,14 @@ __device__ __forceinline__ float fmax3(float a, float b, float c) {
   asm("max.f32 %0, %1, %2, %3;" : "=f"(d) : "f"(a), "f"(b), "f"(c));
   return d;
 }
-// max of a thread's 32 accumulator columns: 16 instructions, depth 4
-__device__ __forceinline__ float t3_max32(const uint32_t (&v)[32]) {
-  float m[10];
-#pragma unroll
-  for (int i = 0; i < 10; ++i)
-    m[i] = fmax3(__uint_as_float(v[3 * i]), __uint_as_float(v[3 * i + 1]), __uint_as_float(v[3 * i + 2]));
-  const float a = fmax3(m[0], m[1], m[2]), b = fmax3(m[3], m[4], m[5]), c = fmax3(m[6], m[7], m[8]);
-  const float d = fmax3(m[9], __uint_as_float(v[30]), __uint_as_float(v[31]));
-  return fmaxf(fmax3(a, b, c), d);
+// remote mbarrier arrive without the cluster-scope release fence of mbar_arrive_remote (knn_tc2.cuh): the
+// epilogue's TMEM reads are ordered by tcgen05.fence::before_thread_sync, nothing else is published.
+// (r01 ncu: the .release.cluster form lowered to MEMBAR.ALL.GPU + ERRBAR + CGAERRBAR, 9 % of the stall
+// samples of the peer CTA's epilogue.)
+__device__ __forceinline__ void mbar_arrive_remote_relaxed(uint64_t* local_bar, uint32_t target_rank) {
+  uint32_t raddr;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(raddr) : "r"(smem_u32(local_bar)), "r"(target_rank));
+  asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(raddr) : "memory");
 }
 
 // Per-warp survivor queue in shared memory (filter epilogue).
@@ -130,7 +129,7 @@ __device__ __forceinline__ void t3_flush(const T3Queue& qu, int lane, uint2* __r
   __syncwarp();
 }
 // one survivor → the warp's queue (straight to global memory if the queue is full); kept out of line:
-// it is called from 32 unrolled sites and must not bloat the hot loop's instruction footprint
+// it is called from 32 sites per chunk and must not bloat the hot loop's instruction footprint
 __device__ __noinline__ void t3_push(uint32_t* qrow, uint32_t* qcount, uint32_t row, uint32_t val, uint32_t q,
                                      uint2* __restrict__ cand_pairs, unsigned int* __restrict__ cand_count, int cap) {
   const uint32_t pos = atomicAdd(qcount, 1u);
@@ -138,6 +137,74 @@ __device__ __noinline__ void t3_push(uint32_t* qrow, uint32_t* qcount, uint32_t 
     qrow[pos] = row; qrow[kT3QueueCap + pos] = val; qrow[2 * kT3QueueCap + pos] = q;
   } else {
     t3_emit(cand_pairs, cand_count, cap, q, row, val);
+  }
+}
+
+// One thread (= one query), 32 accumulator columns (= 32 rows): max tree (16 instructions, depth 4) and one
+// compare; only when the maximum reaches the threshold is the tree walked back down to the element(s)
+// that did (≈ 10 compares for one survivor instead of 32).  Returns whether anything was pushed.
+struct T3Sink {
+  uint32_t* qrow; uint32_t* qcount; uint32_t q; uint2* cand_pairs; unsigned int* cand_count; int cap;
+  __device__ __forceinline__ void push(uint32_t row, uint32_t val) const {
+    t3_push(qrow, qcount, row, val, q, cand_pairs, cand_count, cap);
+  }
+};
+__device__ __forceinline__ bool t3_scan32(const uint32_t* v, float thr, uint32_t row0, const T3Sink& sink) {
+  float m[10];
+#pragma unroll
+  for (int i = 0; i < 10; ++i)
+    m[i] = fmax3(__uint_as_float(v[3 * i]), __uint_as_float(v[3 * i + 1]), __uint_as_float(v[3 * i + 2]));
+  float g[4];
+  g[0] = fmax3(m[0], m[1], m[2]); g[1] = fmax3(m[3], m[4], m[5]); g[2] = fmax3(m[6], m[7], m[8]);
+  g[3] = fmax3(m[9], __uint_as_float(v[30]), __uint_as_float(v[31]));
+  if (!(fmaxf(fmax3(g[0], g[1], g[2]), g[3]) >= thr)) return false;
+#pragma unroll
+  for (int gi = 0; gi < 4; ++gi) {
+    if (g[gi] >= thr) {
+#pragma unroll
+      for (int ti = 3 * gi; ti < 3 * gi + 3 && ti < 10; ++ti) {
+        if (m[ti] >= thr) {
+#pragma unroll
+          for (int j = 3 * ti; j < 3 * ti + 3; ++j)
+            if (__uint_as_float(v[j]) >= thr) sink.push(row0 + static_cast<uint32_t>(j), v[j]);
+        }
+      }
+      if (gi == 3) {
+        if (__uint_as_float(v[30]) >= thr) sink.push(row0 + 30u, v[30]);
+        if (__uint_as_float(v[31]) >= thr) sink.push(row0 + 31u, v[31]);
+      }
+    }
+  }
+  return true;
+}
+
+// four back-to-back 32-column loads (128 accumulator columns of this thread's lane), one wait
+__device__ __forceinline__ void tc_ld128(uint32_t taddr, uint32_t (&v)[128]) {
+#pragma unroll
+  for (int c = 0; c < 4; ++c) {
+    uint32_t* w = v + 32 * c;
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];\n"
+        : "=r"(w[0]), "=r"(w[1]), "=r"(w[2]), "=r"(w[3]), "=r"(w[4]), "=r"(w[5]), "=r"(w[6]), "=r"(w[7]), "=r"(w[8]),
+          "=r"(w[9]), "=r"(w[10]), "=r"(w[11]), "=r"(w[12]), "=r"(w[13]), "=r"(w[14]), "=r"(w[15]), "=r"(w[16]),
+          "=r"(w[17]), "=r"(w[18]), "=r"(w[19]), "=r"(w[20]), "=r"(w[21]), "=r"(w[22]), "=r"(w[23]), "=r"(w[24]),
+          "=r"(w[25]), "=r"(w[26]), "=r"(w[27]), "=r"(w[28]), "=r"(w[29]), "=r"(w[30]), "=r"(w[31])
+        : "r"(taddr + static_cast<uint32_t>(32 * c))
+        : "memory");
+  }
+  // the wait names every destination register so that no use can be scheduled above it
+#pragma unroll
+  for (int c = 0; c < 4; ++c) {
+    uint32_t* w = v + 32 * c;
+    asm volatile("tcgen05.wait::ld.sync.aligned;\n"
+                 : "+r"(w[0]), "+r"(w[1]), "+r"(w[2]), "+r"(w[3]), "+r"(w[4]), "+r"(w[5]), "+r"(w[6]), "+r"(w[7]),
+                   "+r"(w[8]), "+r"(w[9]), "+r"(w[10]), "+r"(w[11]), "+r"(w[12]), "+r"(w[13]), "+r"(w[14]), "+r"(w[15]),
+                   "+r"(w[16]), "+r"(w[17]), "+r"(w[18]), "+r"(w[19]), "+r"(w[20]), "+r"(w[21]), "+r"(w[22]), "+r"(w[23]),
+                   "+r"(w[24]), "+r"(w[25]), "+r"(w[26]), "+r"(w[27]), "+r"(w[28]), "+r"(w[29]), "+r"(w[30]), "+r"(w[31])
+                 :
+                 : "memory");
   }
 }
 
@@ -333,6 +400,7 @@ knn_tc3_kernel(const __grid_constant__ CUtensorMap tmap_rows, const __grid_const
     uint32_t* qcount = s_queue + kT3EpiWarps * 3 * kT3QueueCap + ew;
     T3Queue qu;
     qu.row = qrow; qu.val = qrow + kT3QueueCap; qu.qid = qrow + 2 * kT3QueueCap; qu.count = qcount;
+    const T3Sink sink{qrow, qcount, static_cast<uint32_t>(qi), cand_pairs, cand_count, cap};
     uint32_t it = 0;
     for (int64_t t = cluster_id; t < n_tiles; t += n_clusters, ++it) {
       const uint32_t buf = it & 1u, use = it >> 1;
@@ -361,20 +429,11 @@ knn_tc3_kernel(const __grid_constant__ CUtensorMap tmap_rows, const __grid_const
         }
       } else {
         const uint32_t row_base = static_cast<uint32_t>(t * kT3TileRows + col_half * 128);
-        bool pushed = false;
-#pragma unroll 1
-        for (int c0 = 0; c0 < 128; c0 += 32) {
-          uint32_t v[32];
-          tc_ld32(taddr0 + static_cast<uint32_t>(c0), v);
-          if (t3_max32(v) >= my_thr) {             // rare per lane: ≈ K'·stride + band survivors per query per pass
-            pushed = true;
+        uint32_t v[128];
+        tc_ld128(taddr0, v);
+        bool pushed = false;                       // rare per lane: ≈ K'·stride + band survivors per query per pass
 #pragma unroll
-            for (int j = 0; j < 32; ++j)
-              if (__uint_as_float(v[j]) >= my_thr)
-                t3_push(qrow, qcount, row_base + static_cast<uint32_t>(c0 + j), v[j], static_cast<uint32_t>(qi), cand_pairs,
-                        cand_count, cap);
-          }
-        }
+        for (int c = 0; c < 4; ++c) pushed |= t3_scan32(v + 32 * c, my_thr, row_base + static_cast<uint32_t>(32 * c), sink);
         if (__any_sync(0xFFFFFFFFu, pushed)) {
           __syncwarp();
           if (*qcount >= static_cast<uint32_t>(kT3QueueFlush)) t3_flush(qu, lane, cand_pairs, cand_count, cap);
@@ -383,7 +442,7 @@ knn_tc3_kernel(const __grid_constant__ CUtensorMap tmap_rows, const __grid_const
       tc_fence_before();
       __syncwarp();
       if (lane == 0) {
-        if (leader) mbar_arrive(&tempty[buf]); else mbar_arrive_remote(&tempty[buf], 0u);
+        if (leader) mbar_arrive(&tempty[buf]); else mbar_arrive_remote_relaxed(&tempty[buf], 0u);
       }
     }
     if (MODE == 1) t3_flush(qu, lane, cand_pairs, cand_count, cap);
