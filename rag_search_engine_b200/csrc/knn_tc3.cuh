@@ -28,8 +28,9 @@
 //   a register and "does any of these 32 rows survive" is a 3-input-max tree + one compare: 17
 //   instructions per 32 elements (the first version had lane = row, read the 256 thresholds from shared
 //   memory and chained 32 dependent FSETPs on one warp per scheduler: 2.0 ms per pass, issue-latency-bound).
-//   warp 0   : TMA producer — 7-stage ring of 16 KB k-blocks (128 rows x 64 halves, SWIZZLE_128B); the
-//              loads of BOTH CTAs complete on the leader's mbarrier (cp.async.bulk.tensor...cta_group::2)
+//   warp 0   : TMA producer — 7-stage ring of 16 KB k-blocks (128 rows x 64 halves, SWIZZLE_128B), each
+//              one contiguous block of the tiled shadow (tc3_shadow_kernel); the loads of BOTH CTAs
+//              complete on the leader's mbarrier (cp.async.bulk.tensor...cta_group::2)
 //   warp 1   : leader CTA only — single-thread tcgen05.mma issuer; tcgen05.commit multicast frees the
 //              stage / publishes the accumulator in both CTAs
 //   warps 2-9: epilogue, two warps per TMEM lane quarter (128 columns each) so every scheduler has two
@@ -209,10 +210,19 @@ __device__ __forceinline__ void tc_ld128(uint32_t taddr, uint32_t (&v)[128]) {
 }
 
 // ---------------------------------------------------------------- shadow / query preparation
-// One warp per row: shadow[r] = fp16_rn(a[r] / ||a_r||) with ||a_r|| = sqrt(amag[r]) (the same sequential
+// One warp per row: shadow row r = fp16_rn(a[r] / ||a_r||) with ||a_r|| = sqrt(amag[r]) (the same sequential
 // fp32 sum K1 uses).  Empty vec0 slots (amag < 0) become zero rows.  A zero or non-finite amag makes
 // the exact distance NaN, which the bound cannot cover: such rows are counted in *bad and the host
 // keeps the whole index on the exact scan (MiniLM embeddings are unit-norm; this is a guard).
+//
+// Layout: the shadow is private to the probe/filter GEMM, so it is stored the way the GEMM consumes it —
+// [row / 128][k-block 0..5][row % 128][64 halves]: every pipeline stage (128 rows x one 128-byte k-block)
+// is ONE contiguous 16 KB block of HBM.  (A row-major shadow made each stage 128 separate 128-byte
+// pieces 768 B apart; the filter pass then stalled on TMA data at 4.5 TB/s, r01 ncu.)  The buffer is
+// padded with zero rows to a multiple of 256 rows.
+__device__ __forceinline__ int64_t t3_shadow_offset(int64_t row, int kb) {      // in halves
+  return (((row >> 7) * kT3KBlocks + kb) * kT3HalfRows + (row & 127)) * kT3BK;
+}
 __global__ void __launch_bounds__(256)
 tc3_shadow_kernel(const float* __restrict__ emb, const float* __restrict__ amag, int64_t n_rows,
                   __half* __restrict__ shadow, unsigned int* __restrict__ bad) {
@@ -225,16 +235,17 @@ tc3_shadow_kernel(const float* __restrict__ emb, const float* __restrict__ amag,
     if (am > 0.0f && am < __int_as_float(0x7F800000)) inv = static_cast<float>(1.0 / sqrt(static_cast<double>(am)));
     else if (!(am < 0.0f) && lane == 0) atomicAdd(bad, 1u);            // 0, +inf or NaN
     const float4* src = reinterpret_cast<const float4*>(emb + r * kScanD);
-    uint2* dst = reinterpret_cast<uint2*>(shadow + r * kScanD);
 #pragma unroll
     for (int j = 0; j < kScanD / 128; ++j) {
-      const float4 f = __ldg(src + j * 32 + lane);
+      const int f4 = j * 32 + lane;                                     // float4 index inside the row: 0..95
+      const float4 f = __ldg(src + f4);
       const __half2 lo = __floats2half2_rn(__fmul_rn(f.x, inv), __fmul_rn(f.y, inv));
       const __half2 hi = __floats2half2_rn(__fmul_rn(f.z, inv), __fmul_rn(f.w, inv));
       uint2 o;
       o.x = *reinterpret_cast<const uint32_t*>(&lo);
       o.y = *reinterpret_cast<const uint32_t*>(&hi);
-      dst[j * 32 + lane] = o;
+      const int kb = f4 >> 4, within = f4 & 15;                         // 16 float4 (= 64 halves) per k-block
+      reinterpret_cast<uint2*>(shadow + t3_shadow_offset(r, kb))[within] = o;
     }
   }
 }
@@ -347,14 +358,19 @@ knn_tc3_kernel(const __grid_constant__ CUtensorMap tmap_rows, const __grid_const
         tma_load_2d_2sm(smem + kb * kT3StageBytes, &tmap_q, kb * kT3BK, static_cast<int>(rank) * kT3HalfRows, lq);
       int stage = 0;
       uint32_t phase = 0;
-      for (int64_t t = cluster_id; t < n_tiles; t += n_clusters) {
-        const int row0 = static_cast<int>(t * tile_stride * kT3TileRows + rank * kT3HalfRows);
-        for (int kb = 0; kb < kT3KBlocks; ++kb) {
-          mbar_wait(&empty[stage], phase ^ 1u);
-          if (leader) mbar_arrive_expect_tx(&full[stage], 2 * kT3StageBytes);
-          tma_load_2d_2sm(ring + stage * kT3StageBytes, &tmap_rows, kb * kT3BK, row0, map_to_rank(&full[stage], 0u));
-          if (++stage == kT3Stages) { stage = 0; phase ^= 1u; }
-        }
+      // (An L2 prefetch 6-18 stages ahead of the fill — cp.async.bulk.prefetch.tensor — changed nothing:
+      // with every MMA but one per stage removed the same ring streams at 7.4 TB/s; the pass is bound by
+      // the tensor pipe + TMEM reads, not by the fill.  r01 experiments)
+      const int64_t my_tiles = (n_tiles - cluster_id + n_clusters - 1) / n_clusters;
+      const int64_t my_stages = my_tiles * kT3KBlocks;
+      for (int64_t g = 0; g < my_stages; ++g) {
+        // my 128 rows of the tile = 6 contiguous 16 KB blocks of the tiled shadow (one per k-block)
+        const int64_t t = cluster_id + (g / kT3KBlocks) * n_clusters;
+        const int line = static_cast<int>(((t * tile_stride * 2 + rank) * kT3KBlocks + g % kT3KBlocks) * kT3HalfRows);
+        mbar_wait(&empty[stage], phase ^ 1u);
+        if (leader) mbar_arrive_expect_tx(&full[stage], 2 * kT3StageBytes);
+        tma_load_2d_2sm(ring + stage * kT3StageBytes, &tmap_rows, 0, line, map_to_rank(&full[stage], 0u));
+        if (++stage == kT3Stages) { stage = 0; phase ^= 1u; }
       }
     }
     __syncwarp();                                  // reconverge before the aligned cluster barrier below

@@ -296,6 +296,27 @@ int make_tmap_any(rse_index* h, CUtensorMap* out, const void* base, int64_t rows
   return RSE_OK;
 }
 
+// [lines][64] f16 array of contiguous 128-byte lines, box {64, box_lines}, SWIZZLE_128B
+int make_tmap_lines(rse_index* h, CUtensorMap* out, const void* base, int64_t lines, int box_lines) {
+  PFN_tmapEncodeTiled fn = nullptr;
+  {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    CK(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres));
+    if (!p || qres != cudaDriverEntryPointSuccess) return fail(h, RSE_ERR_CUDA, "cuTensorMapEncodeTiled unavailable");
+    fn = reinterpret_cast<PFN_tmapEncodeTiled>(p);
+  }
+  const cuuint64_t gdim[2] = {64, static_cast<cuuint64_t>(lines)};
+  const cuuint64_t gstr[1] = {128};
+  const cuuint32_t box[2] = {64, static_cast<cuuint32_t>(box_lines)};
+  const cuuint32_t estr[2] = {1, 1};
+  CUresult r = fn(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<void*>(base), gdim, gstr, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return fail(h, RSE_ERR_CUDA, "cuTensorMapEncodeTiled (lines) failed: " + std::to_string(static_cast<int>(r)));
+  return RSE_OK;
+}
+
 // refine + exact re-score + emit for one block of queries whose survivors are in tc_rows / tc_cnt
 int knn_tc_refine(rse_index* h, const float* q_dev, const double* sb, int nqb, int kprime, long long* cand_dev,
                   int* status_dev, int normalized) {
@@ -337,8 +358,15 @@ int scan_event(rse_index* h, cudaEvent_t* out) {
 // when the corpus holds rows whose squared norm is not finite (the error bound needs a finite norm).
 int ensure_shadow(rse_index* h) {
   if (h->shadow_state != 0) return RSE_OK;
-  ENSURE(h->tc_shadow, sizeof(__half) * static_cast<size_t>(h->n_rows) * kScanD + 16);
+  const int64_t n_pad = (h->n_rows + kT3TileRows - 1) / kT3TileRows * kT3TileRows;     // zero rows up to a whole tile
+  const size_t shadow_bytes = sizeof(__half) * static_cast<size_t>(n_pad) * kScanD;
+  ENSURE(h->tc_shadow, shadow_bytes);
   ENSURE(h->tc_cnt, sizeof(unsigned int) * kTcBN);
+  {
+    // the last (partial) tile pair: zero it before the rows that exist are written
+    const size_t tail0 = sizeof(__half) * static_cast<size_t>(n_pad - kT3TileRows) * kScanD;
+    CK(cudaMemsetAsync(static_cast<char*>(h->tc_shadow.p) + tail0, 0, shadow_bytes - tail0, h->stream));
+  }
   unsigned int* bad = static_cast<unsigned int*>(h->tc_cnt.p);
   CK(cudaMemsetAsync(bad, 0, sizeof(unsigned int), h->stream));
   const int grid = h->sm_count * 8;
@@ -352,7 +380,8 @@ int ensure_shadow(rse_index* h) {
     h->shadow_state = -1;
     return RSE_OK;
   }
-  int rc = make_tmap_any(h, &h->tmap_a16, h->tc_shadow.p, h->n_rows, kT3HalfRows, 2);
+  // the tiled shadow as a 2-D array of 128-byte lines: [n_pad * 6 lines][64 halves], box = 128 lines = one stage
+  int rc = make_tmap_lines(h, &h->tmap_a16, h->tc_shadow.p, n_pad * kT3KBlocks, kT3HalfRows);
   if (rc != RSE_OK) return rc;
   h->shadow_state = 1;
   return RSE_OK;
