@@ -118,7 +118,9 @@ bm25_score_kernel(const int64_t* __restrict__ indptr, const uint2* __restrict__ 
                   int64_t n_docs, const int32_t* __restrict__ tok_indptr, const int32_t* __restrict__ term_rows,
                   const double* __restrict__ tok_idf, int q0, int k, double k1p1,
                   unsigned long long* __restrict__ cand_hi, unsigned long long* __restrict__ cand_lo,
-                  int* __restrict__ cand_cnt) {
+                  int* __restrict__ cand_cnt, const int* __restrict__ only_flagged) {
+  // second launch after bm25_stream_kernel: only the queries it flagged are (re-)scored here
+  if (only_flagged && only_flagged[q0 + blockIdx.y] == 0) return;
   extern __shared__ __align__(16) unsigned char smem_raw[];
   double* acc = reinterpret_cast<double*>(smem_raw);                       // [kBmRange]
   unsigned char* first = reinterpret_cast<unsigned char*>(acc + kBmRange); // [kBmRange]
@@ -336,15 +338,256 @@ bm25_score_kernel(const int64_t* __restrict__ indptr, const uint2* __restrict__ 
   if (threadIdx.x == 0) cand_cnt[cbase] = emitted;
 }
 
+// ---------------------------------------------------------------------------------------------
+// K6' + K7': streaming BM25 (the default path for k <= 32 and <= 16 query tokens).
+//
+// r01 ncu of bm25_score_kernel: 21.5 k CTAs (one per 7168-document range and query), each paying a
+// chain of dependent global loads for its token slices, a gathered norm per posting, a 64 KB clear and
+// a full top-k (thread bests, 8 warp sorts, a serial 8-way merge, a collect pass) for ~3.6 k postings
+// of real work: 0.9 ms per 256-query step, 36 k cycles per CTA.  Here
+//   * the per-posting weight w = tf*(k1+1)/(tf + k1*(1-b+b*dl/avgdl)) — keyword_search.py:241-242 up to
+//     the multiplication by idf, in the reference's association — is precomputed per (k1, b) next to
+//     the document index (16 B postings), so a posting costs one coalesced 16 B load, DMUL, DADD and
+//     a shared-memory update: no gather, no division at query time;
+//   * one CTA owns a QUERY and a GROUP of consecutive ranges; the range offsets of its tokens are read
+//     once into shared memory, the accumulator array is reused range after range (cleared by the scan
+//     that reads it);
+//   * top-k is a running threshold: the first non-empty range establishes theta = k-th largest of the
+//     256 per-thread maxima (distinct documents, so a valid lower bound of the k-th best score); every
+//     later range only collects documents with score >= theta (a handful), and theta is tightened
+//     whenever the candidate list is compacted.  Ties are resolved at the very end, for the <= k + ties
+//     finalists only: the first query token whose posting list holds the document is found by binary
+//     search instead of being tracked per posting.
+// The emitted per-group lists have the format of bm25_score_kernel's per-range lists and go through the
+// same bm25_merge_kernel.  A query the kernel cannot finish (more than 16 tokens, candidate overflow
+// from mass ties) is flagged in status[] and re-scored by bm25_score_kernel — no host round trip.
+struct __align__(16) Post16 {
+  uint32_t doc;
+  uint32_t tf;
+  double w;        // tf*(k1+1) / (tf + normk[doc])
+};
+
+constexpr int kBsMaxTok = 16;
+constexpr int kBsMaxRpg = 128;                    // ranges per group (bounds the offset table in shared memory)
+constexpr unsigned int kBsCandCap = 256;
+constexpr unsigned int kBsCompactAt = 128;
+constexpr int kBsFinalCap = 64;                   // finalists (k + ties) ranked exactly
+
+__global__ void bm25_weight_kernel(const uint2* __restrict__ post, const double* __restrict__ normk, int64_t n,
+                                   double k1p1, Post16* __restrict__ out) {
+  const int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const uint2 e = post[i];
+  const double tfd = static_cast<double>(e.y);
+  Post16 o;
+  o.doc = e.x; o.tf = e.y;
+  o.w = __ddiv_rn(__dmul_rn(tfd, k1p1), __dadd_rn(tfd, normk[e.x]));
+  out[i] = o;
+}
+
+constexpr int bs_smem_bytes() {
+  return kBmRange * 8 + kBsMaxTok * (kBsMaxRpg + 1) * 4 + 2 * static_cast<int>(kBsCandCap) * 16;
+}
+
+__global__ void __launch_bounds__(kBmThreads, 3)
+bm25_stream_kernel(const int64_t* __restrict__ indptr, const Post16* __restrict__ post, const uint32_t* __restrict__ roff,
+                   int nr, const int32_t* __restrict__ tok_indptr, const int32_t* __restrict__ term_rows,
+                   const double* __restrict__ tok_idf, int q0, int k, int rpg, int ng,
+                   unsigned long long* __restrict__ cand_hi, unsigned long long* __restrict__ cand_lo,
+                   int* __restrict__ cand_cnt, int* __restrict__ status) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  double* acc = reinterpret_cast<double*>(smem_raw);                                   // [kBmRange]
+  uint32_t* s_off = reinterpret_cast<uint32_t*>(acc + kBmRange);                       // [kBsMaxTok][rpg + 1]
+  double2* s_cand0 = reinterpret_cast<double2*>(s_off + kBsMaxTok * (kBsMaxRpg + 1));  // {score, doc as double bits}
+  double2* s_cand1 = s_cand0 + kBsCandCap;
+  __shared__ long long s_base[kBsMaxTok];
+  __shared__ double s_idf[kBsMaxTok];
+  __shared__ int s_term[kBsMaxTok];
+  __shared__ unsigned int s_ncand, s_nkept;
+  __shared__ unsigned long long s_theta_bits, s_min_bits;
+
+  const int g = blockIdx.x;
+  const int q = q0 + blockIdx.y;
+  const int t0 = tok_indptr[q], ntok = tok_indptr[q + 1] - t0;
+  const int64_t cbase = static_cast<int64_t>(q) * ng + g;
+  if (ntok > kBsMaxTok) {                                 // uniform: the whole query goes to the general kernel
+    if (threadIdx.x == 0) { cand_cnt[cbase] = 0; if (g == 0) status[q] = 1; }
+    return;
+  }
+  const int r0 = g * rpg, r1 = min(nr, r0 + rpg);
+  const int nrg = r1 - r0;
+  if (threadIdx.x < ntok) {
+    const int term = term_rows[t0 + threadIdx.x];
+    s_term[threadIdx.x] = term;
+    s_base[threadIdx.x] = term >= 0 ? indptr[term] : 0;
+    s_idf[threadIdx.x] = tok_idf[t0 + threadIdx.x];
+  }
+  if (threadIdx.x == 0) { s_ncand = 0u; s_theta_bits = 0ull; }
+  __syncthreads();
+  for (int i = threadIdx.x; i < ntok * (nrg + 1); i += blockDim.x) {
+    const int t = i / (nrg + 1), j = i - t * (nrg + 1);
+    const int term = s_term[t];
+    s_off[t * (kBsMaxRpg + 1) + j] = term >= 0 ? roff[static_cast<int64_t>(term) * (nr + 1) + r0 + j] : 0u;
+  }
+  {
+    uint4* a4 = reinterpret_cast<uint4*>(acc);
+    for (int i = threadIdx.x; i < kBmRange / 2; i += blockDim.x) a4[i] = make_uint4(0u, 0u, 0u, 0u);
+  }
+  __syncthreads();
+
+  double2* cand = s_cand0;
+  double2* cand_alt = s_cand1;
+  double theta = 0.0;                                     // 0 = not established: every touched document qualifies
+  bool established = false;
+
+  // keep the documents that fewer than k others beat on score (ties at the boundary stay), tighten theta
+  auto compact = [&]() {
+    const unsigned int n = s_ncand;                       // uniform (read after a barrier)
+    if (n < static_cast<unsigned int>(k)) return;
+    if (threadIdx.x == 0) { s_nkept = 0u; s_min_bits = ~0ull; }
+    __syncthreads();
+    if (threadIdx.x < n) {
+      const double2 me = cand[threadIdx.x];
+      unsigned int greater = 0u;
+      for (unsigned int j = 0; j < n; ++j) greater += cand[j].x > me.x ? 1u : 0u;
+      if (greater < static_cast<unsigned int>(k)) {
+        cand_alt[atomicAdd(&s_nkept, 1u)] = me;
+        atomicMin(&s_min_bits, static_cast<unsigned long long>(__double_as_longlong(me.x)));   // scores are > 0: bit order = value order
+      }
+    }
+    __syncthreads();
+    double2* tmp = cand; cand = cand_alt; cand_alt = tmp;
+    theta = __longlong_as_double(static_cast<long long>(s_min_bits));
+    established = true;
+    __syncthreads();
+    if (threadIdx.x == 0) s_ncand = s_nkept;
+    __syncthreads();
+  };
+
+  for (int r = r0; r < r1; ++r) {
+    const int j = r - r0;
+    unsigned int total = 0u;
+    for (int t = 0; t < ntok; ++t) total += s_off[t * (kBsMaxRpg + 1) + j + 1] - s_off[t * (kBsMaxRpg + 1) + j];
+    if (total == 0u) continue;                            // uniform
+    const uint32_t doc_base = static_cast<uint32_t>(r) * kBmRange;
+    for (int t = 0; t < ntok; ++t) {
+      const uint32_t a = s_off[t * (kBsMaxRpg + 1) + j];
+      const unsigned int n = s_off[t * (kBsMaxRpg + 1) + j + 1] - a;
+      if (n == 0u) continue;                              // uniform
+      const Post16* p = post + s_base[t] + a;
+      const double idf = s_idf[t];
+      for (unsigned int i0 = threadIdx.x; i0 < n; i0 += 4 * kBmThreads) {
+        uint4 e[4];
+        bool ok[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const unsigned int i = i0 + u * kBmThreads;
+          ok[u] = i < n;
+          e[u] = ok[u] ? __ldg(reinterpret_cast<const uint4*>(p + i)) : make_uint4(doc_base, 0u, 0u, 0u);
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          if (!ok[u]) continue;
+          const double w = __hiloint2double(static_cast<int>(e[u].w), static_cast<int>(e[u].z));
+          const uint32_t l = e[u].x - doc_base;
+          acc[l] = __dadd_rn(acc[l], __dmul_rn(idf, w));  // first touch is 0.0 + add (keyword_search.py:244)
+        }
+      }
+      __syncthreads();
+    }
+    if (!established) {
+      // theta = k-th largest of the per-thread maxima (distinct documents)
+      unsigned long long* s_tmax = reinterpret_cast<unsigned long long*>(cand_alt);   // [256]: the spare candidate buffer
+      double mx = 0.0;
+#pragma unroll 4
+      for (int i = 0; i < kBmDocsPerThread; ++i) mx = fmax(mx, acc[threadIdx.x + i * kBmThreads]);
+      s_tmax[threadIdx.x] = static_cast<unsigned long long>(__double_as_longlong(mx));
+      __syncthreads();
+      const unsigned long long mine = s_tmax[threadIdx.x];
+      int rank = 0;
+      for (int t = 0; t < kBmThreads; ++t) {
+        const unsigned long long o = s_tmax[t];
+        rank += (o > mine || (o == mine && t < static_cast<int>(threadIdx.x))) ? 1 : 0;
+      }
+      if (rank == k - 1) s_theta_bits = mine;             // 0 when fewer than k threads saw a document
+      __syncthreads();
+      const unsigned long long tb = s_theta_bits;
+      if (tb != 0ull) { theta = __longlong_as_double(static_cast<long long>(tb)); established = true; }
+    }
+    // scan + clear: collect the documents at or above theta
+#pragma unroll 4
+    for (int i = 0; i < kBmDocsPerThread; ++i) {
+      const int l = threadIdx.x + i * kBmThreads;
+      const double s = acc[l];
+      if (s != 0.0) {
+        acc[l] = 0.0;
+        if (s >= theta) {
+          const unsigned int slot = atomicAdd(&s_ncand, 1u);
+          if (slot < kBsCandCap) cand[slot] = make_double2(s, __longlong_as_double(static_cast<long long>(doc_base + l)));
+        }
+      }
+    }
+    __syncthreads();
+    if (s_ncand > kBsCandCap) {                           // uniform: mass ties → the general kernel re-scores the query
+      if (threadIdx.x == 0) { status[q] = 1; cand_cnt[cbase] = 0; }
+      return;
+    }
+    if (s_ncand >= kBsCompactAt) compact();
+  }
+  compact();
+  const unsigned int n = s_ncand;
+  if (n > static_cast<unsigned int>(kBsFinalCap)) {
+    if (threadIdx.x == 0) { status[q] = 1; cand_cnt[cbase] = 0; }
+    return;
+  }
+  // finalists: first query token whose posting list holds the document, then the exact key order
+  Key128* s_keys = reinterpret_cast<Key128*>(cand_alt);
+  if (threadIdx.x < n) {
+    const double2 me = cand[threadIdx.x];
+    const uint32_t doc = static_cast<uint32_t>(__double_as_longlong(me.y));
+    const int r = static_cast<int>(doc / kBmRange);
+    unsigned int first = 0xFFu;
+    for (int t = 0; t < ntok && first == 0xFFu; ++t) {
+      const uint32_t a = s_off[t * (kBsMaxRpg + 1) + (r - r0)], b = s_off[t * (kBsMaxRpg + 1) + (r - r0) + 1];
+      const Post16* p = post + s_base[t];
+      uint32_t lo = a, hi = b;
+      while (lo < hi) {
+        const uint32_t mid = (lo + hi) >> 1;
+        if (__ldg(&p[mid].doc) < doc) lo = mid + 1; else hi = mid;
+      }
+      if (lo < b && __ldg(&p[lo].doc) == doc) first = static_cast<unsigned int>(t);
+    }
+    Key128 kk;
+    kk.hi = ~f64_orderable(static_cast<uint64_t>(__double_as_longlong(me.x)));
+    kk.lo = (static_cast<unsigned long long>(first) << 32) | doc;
+    s_keys[threadIdx.x] = kk;
+  }
+  __syncthreads();
+  if (threadIdx.x < n) {
+    const Key128 me = s_keys[threadIdx.x];
+    int rank = 0;
+    for (unsigned int j = 0; j < n; ++j) rank += key_less(s_keys[j], me) ? 1 : 0;
+    if (rank < k) {
+      cand_hi[cbase * k + rank] = me.hi;
+      cand_lo[cbase * k + rank] = me.lo;
+    }
+  }
+  if (threadIdx.x == 0) cand_cnt[cbase] = static_cast<int>(n) < k ? static_cast<int>(n) : k;
+}
+
 // K7 (query part): k-way merge of the per-range sorted candidate lists.
 // One CTA per query; thread j owns ranges j, j+blockDim, ...
 __global__ void __launch_bounds__(kBmThreads)
 bm25_merge_kernel(const unsigned long long* __restrict__ cand_hi, const unsigned long long* __restrict__ cand_lo,
                   const int* __restrict__ cand_cnt, int nr, int q0, int k, double* __restrict__ out_score,
-                  int* __restrict__ out_doc, int* __restrict__ out_count) {
+                  int* __restrict__ out_doc, int* __restrict__ out_count,
+                  const unsigned long long* __restrict__ alt_hi, const unsigned long long* __restrict__ alt_lo,
+                  const int* __restrict__ alt_cnt, int alt_nr, const int* __restrict__ use_alt) {
   __shared__ Key128 s_k[kBmThreads / 32];
   __shared__ int s_w[kBmThreads / 32];
   const int q = q0 + blockIdx.x;
+  // the streaming kernel's per-group lists unless it flagged the query (then the general kernel's per-range lists)
+  if (use_alt && use_alt[q] == 0) { cand_hi = alt_hi; cand_lo = alt_lo; cand_cnt = alt_cnt; nr = alt_nr; }
   // per-thread heads (a thread may own several ranges when nr > blockDim; it keeps
   // the best head among them and re-scans its ranges after winning)
   constexpr int kMaxOwn = 8;                 // nr <= 2048 ranges = 16.7 M docs

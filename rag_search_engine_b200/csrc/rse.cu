@@ -90,6 +90,9 @@ struct rse_index {
   uint32_t* roff = nullptr;
   double* normk = nullptr;
   double normk_k1 = NAN, normk_b = NAN;
+  Post16* post16 = nullptr;        // {doc, tf, w}: postings with the (k1, b)-dependent weight precomputed (bm25_stream_kernel)
+  double w_k1 = NAN, w_b = NAN;
+  DevBuf b_shi, b_slo, b_scnt, b_status;
   std::vector<int64_t> df_host;
   DevBuf b_tokptr, b_terms, b_idf, b_chi, b_clo, b_ccnt, b_score, b_doc, b_count;
 
@@ -165,7 +168,8 @@ void release_embeddings(rse_index* h) {
 }
 
 void release_bm25(rse_index* h) {
-  free_ptr(h->indptr); free_ptr(h->post); free_ptr(h->dl); free_ptr(h->roff); free_ptr(h->normk);
+  free_ptr(h->indptr); free_ptr(h->post); free_ptr(h->dl); free_ptr(h->roff); free_ptr(h->normk); free_ptr(h->post16);
+  h->w_k1 = NAN; h->w_b = NAN;
   h->df_host.clear();
   h->n_terms = h->n_postings = h->n_docs = h->n_movies = 0;
   h->normk_k1 = NAN; h->normk_b = NAN;
@@ -738,7 +742,8 @@ void rse_destroy(rse_index* h) {
                     &h->o_rowid, &h->o_movie, &h->o_count, &h->b_tokptr, &h->b_terms, &h->b_idf, &h->b_chi, &h->b_clo,
                     &h->b_ccnt, &h->b_score, &h->b_doc, &h->b_count, &h->f_bid, &h->f_bsc, &h->f_bcnt, &h->f_sid,
                     &h->f_sds, &h->f_scnt, &h->f_oid, &h->f_osc, &h->f_oa, &h->f_ob, &h->f_ocnt, &h->tc_q, &h->tc_thr, &h->tc_isb,
-                    &h->tc_rows, &h->tc_cnt, &h->tc_keys, &h->tc_status})
+                    &h->tc_rows, &h->tc_cnt, &h->tc_keys, &h->tc_status, &h->tc_q16, &h->b_shi, &h->b_slo, &h->b_scnt,
+                    &h->b_status})
     free_buf(*b);
   free_ptr(h->doc_ids);
   free_ptr(h->movie_ids);
@@ -1030,6 +1035,7 @@ int rse_load_bm25(rse_index* h, const int64_t* indptr, const uint32_t* doc_idx, 
   static bool attr = false;
   if (!attr) {
     CK(cudaFuncSetAttribute(bm25_score_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kBmRange * 9));
+    CK(cudaFuncSetAttribute(bm25_stream_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bs_smem_bytes()));
     attr = true;
   }
   return RSE_OK;
@@ -1094,19 +1100,64 @@ int bm25_run(rse_index* h, int nq, int k, double k1, double b) {
   ENSURE(h->b_clo, sizeof(unsigned long long) * per_q * std::min(nq, chunk));
   ENSURE(h->b_ccnt, sizeof(int) * static_cast<size_t>(h->nr) * std::min(nq, chunk));
   const double k1p1 = k1 + 1.0;
+
+  // streaming path (bm25_stream_kernel): k <= 32; needs the weighted postings of this (k1, b)
+  const bool stream = k <= 32 && h->n_postings > 0;
+  int ng = 1, rpg = h->nr;
+  if (stream) {
+    if (!(h->w_k1 == k1 && h->w_b == b)) {
+      if (!h->post16) CK(cudaMalloc(&h->post16, sizeof(Post16) * static_cast<size_t>(h->n_postings)));
+      const int threads = 256;
+      bm25_weight_kernel<<<static_cast<unsigned int>((h->n_postings + threads - 1) / threads), threads, 0, h->stream>>>(
+          h->post, h->normk, h->n_postings, k1p1, h->post16);
+      LAUNCHED(h);
+      h->w_k1 = k1; h->w_b = b;
+    }
+    // one CTA per (query, group of consecutive ranges): enough groups to fill the machine twice over
+    const int want = 6 * h->sm_count;
+    ng = std::max(1, std::min(h->nr, (want + std::min(nq, chunk) - 1) / std::min(nq, chunk)));
+    rpg = (h->nr + ng - 1) / ng;
+    if (rpg > kBsMaxRpg) rpg = kBsMaxRpg;
+    ng = (h->nr + rpg - 1) / rpg;
+    const size_t per_qs = static_cast<size_t>(ng) * k;
+    ENSURE(h->b_shi, sizeof(unsigned long long) * per_qs * std::min(nq, chunk));
+    ENSURE(h->b_slo, sizeof(unsigned long long) * per_qs * std::min(nq, chunk));
+    ENSURE(h->b_scnt, sizeof(int) * static_cast<size_t>(ng) * std::min(nq, chunk));
+    ENSURE(h->b_status, sizeof(int) * nq);
+    CK(cudaMemsetAsync(h->b_status.p, 0, sizeof(int) * nq, h->stream));
+  }
   for (int q0 = 0; q0 < nq; q0 += chunk) {
     const int nc = std::min(chunk, nq - q0);
     // candidate buffers are indexed by absolute q inside the kernels → offset the base pointers
     unsigned long long* chi = static_cast<unsigned long long*>(h->b_chi.p) - static_cast<int64_t>(q0) * per_q;
     unsigned long long* clo = static_cast<unsigned long long*>(h->b_clo.p) - static_cast<int64_t>(q0) * per_q;
     int* ccnt = static_cast<int*>(h->b_ccnt.p) - static_cast<int64_t>(q0) * h->nr;
+    unsigned long long* shi = nullptr;
+    unsigned long long* slo = nullptr;
+    int* scnt = nullptr;
+    int* status = nullptr;
+    if (stream) {
+      const size_t per_qs = static_cast<size_t>(ng) * k;
+      shi = static_cast<unsigned long long*>(h->b_shi.p) - static_cast<int64_t>(q0) * per_qs;
+      slo = static_cast<unsigned long long*>(h->b_slo.p) - static_cast<int64_t>(q0) * per_qs;
+      scnt = static_cast<int*>(h->b_scnt.p) - static_cast<int64_t>(q0) * ng;
+      status = static_cast<int*>(h->b_status.p);
+      dim3 sgrid(ng, nc);
+      bm25_stream_kernel<<<sgrid, kBmThreads, bs_smem_bytes(), h->stream>>>(
+          h->indptr, h->post16, h->roff, h->nr, static_cast<const int32_t*>(h->b_tokptr.p),
+          static_cast<const int32_t*>(h->b_terms.p), static_cast<const double*>(h->b_idf.p), q0, k, rpg, ng, shi, slo, scnt,
+          status);
+      LAUNCHED(h);
+    }
+    // general kernel: every query when the streaming path does not apply, else only the flagged ones
     dim3 grid(h->nr, nc);
     bm25_score_kernel<<<grid, kBmThreads, kBmRange * 9, h->stream>>>(
         h->indptr, h->post, h->roff, h->normk, h->nr, h->n_docs, static_cast<const int32_t*>(h->b_tokptr.p),
-        static_cast<const int32_t*>(h->b_terms.p), static_cast<const double*>(h->b_idf.p), q0, k, k1p1, chi, clo, ccnt);
+        static_cast<const int32_t*>(h->b_terms.p), static_cast<const double*>(h->b_idf.p), q0, k, k1p1, chi, clo, ccnt, status);
     LAUNCHED(h);
     bm25_merge_kernel<<<nc, kBmThreads, 0, h->stream>>>(chi, clo, ccnt, h->nr, q0, k, static_cast<double*>(h->b_score.p),
-                                                        static_cast<int*>(h->b_doc.p), static_cast<int*>(h->b_count.p));
+                                                        static_cast<int*>(h->b_doc.p), static_cast<int*>(h->b_count.p),
+                                                        shi, slo, scnt, ng, status);
     LAUNCHED(h);
   }
   return RSE_OK;

@@ -206,6 +206,50 @@ def test_bm25_large_synthetic_matches_c_oracle(fresh_index):
         assert (sc.view(np.uint64) == osc.view(np.uint64)).all()
 
 
+def test_bm25_streaming_kernel_fallbacks_and_ties(fresh_index):
+    """The streaming BM25 kernel hands a query to the general kernel when it has more than 16 tokens or when
+    a mass tie overflows its candidate list; small tie groups are resolved inside it (first query token whose
+    postings hold the document, then doc).  Everything must equal the C oracle bit for bit."""
+    rng = np.random.default_rng(11)
+    n_docs, vocab = 40_000, 400
+    # documents: 12 000 byte-identical ones (mass tie), groups of 3 identical ones (small ties), the rest random
+    docs = []
+    for d in range(n_docs):
+        if d % 3 == 0 and d < 36_000:
+            toks = [1, 2, 3, 3]
+        elif d % 3 == 1 and d < 36_000:
+            base = (d // 30) % 50
+            toks = [10 + base, 11 + base, 200 + (d // 30) % 7]
+        else:
+            toks = rng.integers(0, vocab, rng.integers(3, 12)).tolist()
+        docs.append(toks)
+    indptr = [0]; doc_idx = []; tf = []
+    by_term = [dict() for _ in range(vocab)]
+    for d, toks in enumerate(docs):
+        for t in toks:
+            by_term[t][d] = by_term[t].get(d, 0) + 1
+    for t in range(vocab):
+        for d in sorted(by_term[t]):
+            doc_idx.append(d); tf.append(by_term[t][d])
+        indptr.append(len(doc_idx))
+    indptr = np.array(indptr, np.int64); doc_idx = np.array(doc_idx, np.uint32); tf = np.array(tf, np.uint32)
+    df = np.diff(indptr).astype(np.int64)
+    dl = np.array([len(t) + 1 for t in docs], np.uint32)
+    avgdl = float(dl.sum()) / n_docs
+    queries = [[1, 3], [3, 2, 1, 3], [10, 11, 200], [12, 13, 201, 12], list(range(5, 25)), [7], [399, 1, 50],
+               [203, 30, 31], list(range(100, 117)), [2]]
+    queries += [rng.integers(0, vocab, rng.integers(1, 7)).tolist() for _ in range(40)]
+    tok_indptr = np.cumsum([0] + [len(q) for q in queries]).astype(np.int32)
+    terms = np.array([t for q in queries for t in q], np.int32)
+    fresh_index.load_bm25(indptr, doc_idx, tf, df, dl, n_docs, avgdl)
+    for k in (10, 3, 32):
+        sc, dc, cnt = fresh_index.bm25(tok_indptr, terms, k)
+        osc, odc, ocnt = oracle.bm25_batch(indptr, doc_idx, tf, df, dl, n_docs, avgdl, tok_indptr, terms, k)
+        assert cnt.tolist() == ocnt.tolist()
+        assert (dc == odc).all()
+        assert (sc.view(np.uint64) == osc.view(np.uint64)).all()
+
+
 def test_bm25_edge_cases(fresh_index):
     postings, doclen = build_postings([{"id": 5, "title": "a b", "description": "c a"},
                                        {"id": 9, "title": "a", "description": ""}])
