@@ -367,6 +367,9 @@ struct __align__(16) Post16 {
   double w;        // tf*(k1+1) / (tf + normk[doc])
 };
 
+constexpr int kBsThreads = 512;                   // 16 warps x 3 CTAs per SM: the kernel is issue-latency-bound, TLP is what it needs
+constexpr int kBsPerTrip = 2;                     // postings per thread per trip
+constexpr int kBsDocsPerThread = kBmRange / kBsThreads;   // 14
 constexpr int kBsMaxTok = 16;
 constexpr int kBsMaxRpg = 128;                    // ranges per group (bounds the offset table in shared memory)
 constexpr unsigned int kBsCandCap = 256;
@@ -389,7 +392,7 @@ constexpr int bs_smem_bytes() {
   return kBmRange * 8 + kBsMaxTok * (kBsMaxRpg + 1) * 4 + 2 * static_cast<int>(kBsCandCap) * 16;
 }
 
-__global__ void __launch_bounds__(kBmThreads, 3)
+__global__ void __launch_bounds__(kBsThreads, 3)
 bm25_stream_kernel(const int64_t* __restrict__ indptr, const Post16* __restrict__ post, const uint32_t* __restrict__ roff,
                    int nr, const int32_t* __restrict__ tok_indptr, const int32_t* __restrict__ term_rows,
                    const double* __restrict__ tok_idf, int q0, int k, int rpg, int ng,
@@ -404,7 +407,8 @@ bm25_stream_kernel(const int64_t* __restrict__ indptr, const Post16* __restrict_
   __shared__ double s_idf[kBsMaxTok];
   __shared__ int s_term[kBsMaxTok];
   __shared__ unsigned int s_ncand, s_nkept;
-  __shared__ unsigned long long s_theta_bits, s_min_bits;
+  __shared__ unsigned long long s_min_bits;
+  __shared__ unsigned long long s_tw[kBsThreads / 32];
 
   const int g = blockIdx.x;
   const int q = q0 + blockIdx.y;
@@ -422,7 +426,7 @@ bm25_stream_kernel(const int64_t* __restrict__ indptr, const Post16* __restrict_
     s_base[threadIdx.x] = term >= 0 ? indptr[term] : 0;
     s_idf[threadIdx.x] = tok_idf[t0 + threadIdx.x];
   }
-  if (threadIdx.x == 0) { s_ncand = 0u; s_theta_bits = 0ull; }
+  if (threadIdx.x == 0) s_ncand = 0u;
   __syncthreads();
   for (int i = threadIdx.x; i < ntok * (nrg + 1); i += blockDim.x) {
     const int t = i / (nrg + 1), j = i - t * (nrg + 1);
@@ -476,17 +480,17 @@ bm25_stream_kernel(const int64_t* __restrict__ indptr, const Post16* __restrict_
       if (n == 0u) continue;                              // uniform
       const Post16* p = post + s_base[t] + a;
       const double idf = s_idf[t];
-      for (unsigned int i0 = threadIdx.x; i0 < n; i0 += 4 * kBmThreads) {
-        uint4 e[4];
-        bool ok[4];
+      for (unsigned int i0 = threadIdx.x; i0 < n; i0 += kBsPerTrip * kBsThreads) {
+        uint4 e[kBsPerTrip];
+        bool ok[kBsPerTrip];
 #pragma unroll
-        for (int u = 0; u < 4; ++u) {
-          const unsigned int i = i0 + u * kBmThreads;
+        for (int u = 0; u < kBsPerTrip; ++u) {
+          const unsigned int i = i0 + u * kBsThreads;
           ok[u] = i < n;
           e[u] = ok[u] ? __ldg(reinterpret_cast<const uint4*>(p + i)) : make_uint4(doc_base, 0u, 0u, 0u);
         }
 #pragma unroll
-        for (int u = 0; u < 4; ++u) {
+        for (int u = 0; u < kBsPerTrip; ++u) {
           if (!ok[u]) continue;
           const double w = __hiloint2double(static_cast<int>(e[u].w), static_cast<int>(e[u].z));
           const uint32_t l = e[u].x - doc_base;
@@ -496,28 +500,42 @@ bm25_stream_kernel(const int64_t* __restrict__ indptr, const Post16* __restrict_
       __syncthreads();
     }
     if (!established) {
-      // theta = k-th largest of the per-thread maxima (distinct documents)
-      unsigned long long* s_tmax = reinterpret_cast<unsigned long long*>(cand_alt);   // [256]: the spare candidate buffer
+      // theta = k-th largest of the 512 per-thread maxima (distinct documents, so a lower bound of the k-th
+      // best score): rank inside each warp by shuffles, then among the warps' k best
       double mx = 0.0;
-#pragma unroll 4
-      for (int i = 0; i < kBmDocsPerThread; ++i) mx = fmax(mx, acc[threadIdx.x + i * kBmThreads]);
-      s_tmax[threadIdx.x] = static_cast<unsigned long long>(__double_as_longlong(mx));
-      __syncthreads();
-      const unsigned long long mine = s_tmax[threadIdx.x];
+#pragma unroll 2
+      for (int i = 0; i < kBsDocsPerThread; ++i) mx = fmax(mx, acc[threadIdx.x + i * kBsThreads]);
+      const unsigned long long mine = static_cast<unsigned long long>(__double_as_longlong(mx));
+      const int lane = threadIdx.x & 31;
       int rank = 0;
-      for (int t = 0; t < kBmThreads; ++t) {
-        const unsigned long long o = s_tmax[t];
-        rank += (o > mine || (o == mine && t < static_cast<int>(threadIdx.x))) ? 1 : 0;
+#pragma unroll 8
+      for (int o = 0; o < 32; ++o) {
+        const unsigned long long v = __shfl_sync(0xFFFFFFFFu, mine, o);
+        rank += (v > mine || (v == mine && o < lane)) ? 1 : 0;
       }
-      if (rank == k - 1) s_theta_bits = mine;             // 0 when fewer than k threads saw a document
+      // the k best lane maxima of every warp → 16 k values whose k-th largest is the k-th largest of all 512
+      unsigned long long* s_top = reinterpret_cast<unsigned long long*>(cand_alt);   // [16][k], k <= 32: 4 KB
+      if (rank < k) s_top[(threadIdx.x >> 5) * k + rank] = mine;
+      if (threadIdx.x == 0) s_tw[0] = 0ull;
       __syncthreads();
-      const unsigned long long tb = s_theta_bits;
+      const int nv = (kBsThreads / 32) * k;
+      if (static_cast<int>(threadIdx.x) < nv) {
+        const unsigned long long me = s_top[threadIdx.x];
+        int r2 = 0;
+        for (int j = 0; j < nv; ++j) {
+          const unsigned long long o = s_top[j];
+          r2 += (o > me || (o == me && j < static_cast<int>(threadIdx.x))) ? 1 : 0;
+        }
+        if (r2 == k - 1) s_tw[0] = me;                     // 0 when fewer than k threads saw a document
+      }
+      __syncthreads();
+      const unsigned long long tb = s_tw[0];
       if (tb != 0ull) { theta = __longlong_as_double(static_cast<long long>(tb)); established = true; }
     }
     // scan + clear: collect the documents at or above theta
 #pragma unroll 4
-    for (int i = 0; i < kBmDocsPerThread; ++i) {
-      const int l = threadIdx.x + i * kBmThreads;
+    for (int i = 0; i < kBsDocsPerThread; ++i) {
+      const int l = threadIdx.x + i * kBsThreads;
       const double s = acc[l];
       if (s != 0.0) {
         acc[l] = 0.0;
