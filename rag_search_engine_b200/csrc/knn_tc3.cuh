@@ -52,6 +52,7 @@ constexpr int kT3BK = 64;                                 // halves per k-block:
 constexpr int kT3KBlocks = kScanD / kT3BK;                // 6
 constexpr int kT3StageBytes = kT3HalfRows * kT3BK * 2;    // 16,384
 constexpr int kT3Stages = 7;                              // 112 KB of rows in flight per SM
+constexpr int kT3ProbeTop = 8;                            // MODE 2: sample values kept per thread
 constexpr int kT3QueueCap = 128;                          // per-warp survivor queue (entries of 12 B)
 constexpr int kT3QueueFlush = 32;                         // flushed to global memory once this full
 constexpr int kT3QBytes = kT3KBlocks * kT3StageBytes;     // 98,304: this CTA's 128 queries
@@ -139,6 +140,17 @@ __device__ __noinline__ void t3_push(uint32_t* qrow, uint32_t* qcount, uint32_t 
   } else {
     t3_emit(cand_pairs, cand_count, cap, q, row, val);
   }
+}
+
+// max of a thread's 32 accumulator columns: 16 instructions, depth 4
+__device__ __forceinline__ float t3_max32(const uint32_t* v) {
+  float m[10];
+#pragma unroll
+  for (int i = 0; i < 10; ++i)
+    m[i] = fmax3(__uint_as_float(v[3 * i]), __uint_as_float(v[3 * i + 1]), __uint_as_float(v[3 * i + 2]));
+  const float a = fmax3(m[0], m[1], m[2]), b = fmax3(m[3], m[4], m[5]), c = fmax3(m[6], m[7], m[8]);
+  const float d = fmax3(m[9], __uint_as_float(v[30]), __uint_as_float(v[31]));
+  return fmaxf(fmax3(a, b, c), d);
 }
 
 // One thread (= one query), 32 accumulator columns (= 32 rows): max tree (16 instructions, depth 4) and one
@@ -297,6 +309,13 @@ __global__ void tc3_threshold_kernel(const SelState* __restrict__ st, const doub
 //                  dist[q*ld + t*256 + r].  Empty slots / rows past the end are zero rows of the shadow:
 //                  they read d~ = 1, which can only matter when tau_s >= 1 - 2 eps — and then the query is
 //                  handed to the exact scan anyway (tc3_threshold_kernel).
+// MODE 2 (probe, K' <= 256): same tiles as MODE 0, but nothing dense is stored: every epilogue thread keeps the
+//                  8 largest cos~ of the (query, rows) pairs it sees in registers and writes them at the end —
+//                  dist[q*ld + (cluster*2 + half)*8 + i], ld = n_clusters*16.  The K'-th smallest d~ of that
+//                  union is the K'-th smallest of a SUBSET of the sample: still an upper bound of the K'-th
+//                  exact distance (+eps), and equal to the dense answer unless one thread holds more than 8 of
+//                  the sample's best K' (148 threads share them).  The dense probe wrote 182 MB per 256-query
+//                  batch and its three radix-select passes cost 0.19 ms; this one writes 1.2 MB.
 // MODE 1 (filter): all tiles; survivors appended to cand_pairs[q*cap + slot] = {local row, cos~}.  thr > 0
 //                  for every query (or +inf), so zero rows never survive.
 // grid = 2 * n_clusters (<= 148), cluster = 2.
@@ -417,6 +436,9 @@ knn_tc3_kernel(const __grid_constant__ CUtensorMap tmap_rows, const __grid_const
     T3Queue qu;
     qu.row = qrow; qu.val = qrow + kT3QueueCap; qu.qid = qrow + 2 * kT3QueueCap; qu.count = qcount;
     const T3Sink sink{qrow, qcount, static_cast<uint32_t>(qi), cand_pairs, cand_count, cap};
+    float top[kT3ProbeTop];
+#pragma unroll
+    for (int i = 0; i < kT3ProbeTop; ++i) top[i] = -3.0f;                    // below any cosine
     uint32_t it = 0;
     for (int64_t t = cluster_id; t < n_tiles; t += n_clusters, ++it) {
       const uint32_t buf = it & 1u, use = it >> 1;
@@ -443,6 +465,27 @@ knn_tc3_kernel(const __grid_constant__ CUtensorMap tmap_rows, const __grid_const
             }
           }
         }
+      } else if (MODE == 2) {
+        // running top-8 of this thread's share of the sample (registers, sorted descending)
+        uint32_t v[128];
+        tc_ld128(taddr0, v);
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          if (t3_max32(v + 32 * c) > top[kT3ProbeTop - 1]) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+              const float x = __uint_as_float(v[32 * c + j]);
+              if (x > top[kT3ProbeTop - 1]) {
+                top[kT3ProbeTop - 1] = x;
+#pragma unroll
+                for (int i = kT3ProbeTop - 1; i > 0; --i) {
+                  const float hi = fmaxf(top[i - 1], top[i]), lo = fminf(top[i - 1], top[i]);
+                  top[i - 1] = hi; top[i] = lo;
+                }
+              }
+            }
+          }
+        }
       } else {
         const uint32_t row_base = static_cast<uint32_t>(t * kT3TileRows + col_half * 128);
         uint32_t v[128];
@@ -462,6 +505,13 @@ knn_tc3_kernel(const __grid_constant__ CUtensorMap tmap_rows, const __grid_const
       }
     }
     if (MODE == 1) t3_flush(qu, lane, cand_pairs, cand_count, cap);
+    if (MODE == 2 && qi < nq) {
+      // d~ of this thread's best 8 sample rows; unused slots carry the invalid sentinel
+      uint32_t* o = dist + static_cast<int64_t>(qi) * ld + (cluster_id * 2 + col_half) * kT3ProbeTop;
+#pragma unroll
+      for (int i = 0; i < kT3ProbeTop; ++i)
+        o[i] = top[i] > -2.0f ? __float_as_uint(1.0f - top[i]) : 0x7FFFFFFFu;
+    }
   }
 
   tc_fence_before();

@@ -398,6 +398,7 @@ int knn_tc3_block(rse_index* h, const float* q_dev, const double* sb, int nqb, i
   if (!attrs) {
     CK(cudaFuncSetAttribute(knn_tc3_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, kT3SmemBytes));
     CK(cudaFuncSetAttribute(knn_tc3_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, kT3SmemBytes));
+    CK(cudaFuncSetAttribute(knn_tc3_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, kT3SmemBytes));
     attrs = true;
   }
   ENSURE(h->tc_q16, sizeof(__half) * kTcBN * kScanD);
@@ -432,20 +433,29 @@ int knn_tc3_block(rse_index* h, const float* q_dev, const double* sb, int nqb, i
   LAUNCHED(h);
 
   // 1. probe: approximate distances of a strided sample of tiles → K'-th smallest per query
-  const int grid_p = 2 * static_cast<int>(std::min<int64_t>(max_clusters, n_probe));
-  knn_tc3_kernel<0><<<grid_p, kT3Threads, kT3SmemBytes, h->stream>>>(
-      h->tmap_a16, h->tmap_q16, n_probe, tile_stride, nqb, nullptr, dist, ld_probe, nullptr, nullptr, 0);
+  const int probe_clusters = static_cast<int>(std::min<int64_t>(max_clusters, n_probe));
+  const int grid_p = 2 * probe_clusters;
+  const bool sparse_probe = kprime <= 256 && static_cast<int64_t>(probe_clusters) * 2 * kT3ProbeTop >= 4ll * kprime;
+  int64_t ld_sel = ld_probe;
+  if (sparse_probe) {
+    ld_sel = static_cast<int64_t>(probe_clusters) * 2 * kT3ProbeTop;
+    knn_tc3_kernel<2><<<grid_p, kT3Threads, kT3SmemBytes, h->stream>>>(
+        h->tmap_a16, h->tmap_q16, n_probe, tile_stride, nqb, nullptr, dist, ld_sel, nullptr, nullptr, 0);
+  } else {
+    knn_tc3_kernel<0><<<grid_p, kT3Threads, kT3SmemBytes, h->stream>>>(
+        h->tmap_a16, h->tmap_q16, n_probe, tile_stride, nqb, nullptr, dist, ld_probe, nullptr, nullptr, 0);
+  }
   LAUNCHED(h);
   select_init_kernel<<<(nqb + 127) / 128, 128, 0, h->stream>>>(sel, nqb, static_cast<unsigned int>(kprime));
   LAUNCHED(h);
   {
-    int blocks = static_cast<int>(std::min<int64_t>((ld_probe + 4095) / 4096, h->sm_count));
+    int blocks = static_cast<int>(std::min<int64_t>((ld_sel + 4095) / 4096, h->sm_count));
     if (blocks < 1) blocks = 1;
     dim3 grid(blocks, nqb);
     static const int shifts[3] = {53, 42, 32};
     static const int widths[3] = {11, 11, 10};
     for (int p = 0; p < 3; ++p) {
-      select_pass_kernel<<<grid, kSelThreads, 0, h->stream>>>(dist, ld_probe, ld_probe, 0ull, sel, hist, shifts[p], widths[p]);
+      select_pass_kernel<<<grid, kSelThreads, 0, h->stream>>>(dist, ld_sel, ld_sel, 0ull, sel, hist, shifts[p], widths[p]);
       LAUNCHED(h);
     }
   }
