@@ -58,7 +58,7 @@ def scan_kernel_desc(args, tc_used, qb):
 def parse_args():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--steps", type=int, default=100)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--movies", type=int, default=600_000)
@@ -80,6 +80,9 @@ def parse_args():
 
 # ----------------------------------------------------------------------------- clocks
 class ClockSampler:
+    """SM clock + throttle reasons sampled DURING the timed region.  The timed region of the default run is tens
+    of milliseconds, far below nvidia-smi's loop granularity, so NVML is polled from a thread every ~1 ms
+    (nvidia-smi -lms is the fallback when the NVML binding is missing)."""
     FIELDS = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
               "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
               "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
@@ -87,19 +90,68 @@ class ClockSampler:
     def __init__(self, gpu_index: int):
         self.gpu = gpu_index
         self.proc = None
+        self.thread = None
+        self.stop_flag = False
+        self.sm, self.reasons = [], set()
+        self.sm_max = None
         self.path = Path(os.environ.get("TMPDIR", "/tmp")) / f"rse_clocks_{os.getpid()}.csv"
+
+    def _poll(self, nv, handle):
+        names = {"hw_slowdown": getattr(nv, "nvmlClocksEventReasonHwSlowdown", 0x8),
+                 "hw_thermal_slowdown": getattr(nv, "nvmlClocksEventReasonHwThermalSlowdown", 0x40),
+                 "sw_thermal_slowdown": getattr(nv, "nvmlClocksEventReasonSwThermalSlowdown", 0x20),
+                 "sw_power_cap": getattr(nv, "nvmlClocksEventReasonSwPowerCap", 0x4)}
+        get_reasons = getattr(nv, "nvmlDeviceGetCurrentClocksEventReasons", None) or \
+            getattr(nv, "nvmlDeviceGetCurrentClocksThrottleReasons")
+        while not self.stop_flag:
+            try:
+                self.sm.append(float(nv.nvmlDeviceGetClockInfo(handle, nv.NVML_CLOCK_SM)))
+                mask = int(get_reasons(handle))
+                for k, bit in names.items():
+                    if mask & bit:
+                        self.reasons.add(k)
+            except Exception:
+                pass
+            time.sleep(0.001)
 
     def start(self):
         try:
+            import pynvml as nv
+            import threading
+            nv.nvmlInit()
+            # CUDA_VISIBLE_DEVICES may renumber devices: address the GPU by the PCI bus id torch reports
+            handle = None
+            try:
+                import torch
+                bus = torch.cuda.get_device_properties(self.gpu).pci_bus_id
+                dom = torch.cuda.get_device_properties(self.gpu).pci_domain_id
+                dev = torch.cuda.get_device_properties(self.gpu).pci_device_id
+                handle = nv.nvmlDeviceGetHandleByPciBusId(f"{dom:08x}:{bus:02x}:{dev:02x}.0".encode())
+            except Exception:
+                handle = nv.nvmlDeviceGetHandleByIndex(self.gpu)
+            self.sm_max = float(nv.nvmlDeviceGetMaxClockInfo(handle, nv.NVML_CLOCK_SM))
+            self.thread = threading.Thread(target=self._poll, args=(nv, handle), daemon=True)
+            self.thread.start()
+            return
+        except Exception:
+            self.thread = None
+        try:
             self.fh = open(self.path, "w")
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu), f"--query-gpu={self.FIELDS}",
-                                          "--format=csv,noheader,nounits", "-lms", "100"], stdout=self.fh,
+                                          "--format=csv,noheader,nounits", "-lms", "20"], stdout=self.fh,
                                          stderr=subprocess.DEVNULL)
         except Exception:
             self.proc = None
 
     def stop(self) -> dict:
         out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        if self.thread is not None:
+            self.stop_flag = True
+            self.thread.join(timeout=2)
+            if self.sm:
+                out.update(sm_mhz=statistics.median(self.sm), sm_max_mhz=self.sm_max, reasons=sorted(self.reasons),
+                           samples=len(self.sm), source="nvml, 1 ms poll")
+            return out
         if self.proc is None:
             return out
         self.proc.terminate()
@@ -121,7 +173,8 @@ class ClockSampler:
                 if v.lower().startswith("active"):
                     reasons.add(name)
         if sm:
-            out.update(sm_mhz=statistics.median(sm), sm_max_mhz=max(mx), reasons=sorted(reasons), samples=len(sm))
+            out.update(sm_mhz=statistics.median(sm), sm_max_mhz=max(mx), reasons=sorted(reasons), samples=len(sm),
+                       source="nvidia-smi -lms 20")
         try:
             self.path.unlink()
         except Exception:
@@ -157,7 +210,8 @@ def config_dict(args, info, world):
             "mode": args.mode, "limit": args.limit, "knn_kprime": max(args.limit * 10, args.limit),
             "queries_per_step": args.batch, "movies": info["movies"], "chunks": info["chunks"], "dim": info["dim"],
             "bm25_postings": info["postings"], "bm25_terms": info["terms"],
-            "l2": "inputs larger than L2 (7.4 GB embedding stream per 16-query pass vs 126 MB L2); no flush",
+            "l2": "inputs larger than L2: every step streams the 3.7 GB fp16 shadow of the corpus (one pass per 256 "
+                  "queries) and ~1.3 GB of postings against a 126 MB L2; no flush",
             "parallelism": f"row-shard x{world} + all_gather(top-K') + query-slice BM25/fusion" if world > 1 else "1 GPU"}
 
 
@@ -212,7 +266,7 @@ def run_reference(args, rank, world):
     value = sample * len(times) / total
     line = {"impl": "reference", "metric": "hybrid queries/sec", "value": value, "unit": "queries/s",
             "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * total / len(times),
-            "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32 scan + f64 tail/BM25/fusion",
+            "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f16 tensor-core filter + exact f32 re-score (f64 tail), f64 BM25/fusion",
             "data": "synthetic", "config": config_dict(args, info, 1),
             "cpu_baseline": {"value": value, "unit": "queries/s", "cores": cores, "kind": "port",
                              "sample": f"{sample} hybrid queries per step over the full S-600k corpus "
@@ -280,10 +334,10 @@ def run_b200(args, rank, world, local_rank):
         step_fn()
     e1.record(stream)
     torch.cuda.synchronize(); barrier()
+    clocks = sampler.stop()
     sh_last = step_fn() if world > 1 else None
     torch.cuda.synchronize(); barrier()
     ms = e0.elapsed_time(e1)
-    clocks = sampler.stop()
     st = idx.stats()
     idx.set_timing(False)
     launches = int(st.kernel_launches)
@@ -375,20 +429,48 @@ def run_b200(args, rank, world, local_rank):
     tc_used = int(st.tc_filter_launches) > 0
     kname, row_bytes = scan_kernel_desc(args, tc_used, qb)
     alg_bytes = rows_local * row_bytes
-    achieved = alg_bytes / (scan_ms * 1e-3) / 1e9 if scan_ms > 0 else None
-    roofline = {"bound": "hbm", "kernel": kname,
-                "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": (achieved / peak) if achieved else None,
-                "peak_source": "MEASURED_PEAKS.json hbm_gbs (of measured)" if peaks else "fallback 6650 GB/s (of fallback)",
-                "traffic": None, "algorithmic_bytes_per_launch": alg_bytes, "avg_launch_ms": scan_ms,
-                "scan_launches": int(st.scan_launches_timed), "scan_share_of_step": scan_share,
-                "tc_queries": int(st.tc_queries), "tc_fallback_queries": int(st.tc_fallback_queries)}
+    # DRAM bytes per launch of the dominant kernel, from the committed ncu --set full capture (profiles/): only
+    # quoted when this run has the shard size that was profiled
+    traffic = None
+    tj = ROOT / "profiles" / "r01_dominant_kernel_traffic.json"
+    if tj.exists():
+        t = json.loads(tj.read_text())
+        if t.get("rows") == rows_local and t.get("tc_kind") == (tc_kind(args) if tc_used else "scan"):
+            traffic = t.get("dram_bytes_read", 0) + t.get("dram_bytes_write", 0)
+    hbm_achieved = alg_bytes / (scan_ms * 1e-3) / 1e9 if scan_ms > 0 else None
+    psrc = "MEASURED_PEAKS.json" if peaks else "fallback"
+    if tc_used:
+        # The batched filter pass is bound by the tensor pipe (+ TMEM reads), not by the stream: with the MMAs
+        # removed the same kernel streams the shadow at 7.4 TB/s (0.50 ms), with the TMEM loads removed it takes
+        # 0.65 ms = 1.45 PFLOP/s.  Algorithmic work: 2*384 flop per (row, query) pair.
+        q_per_pass = min(nq, 256)
+        flops = 2.0 * 384 * rows_local * q_per_pass
+        tpeak = float(peaks.get("bf16_tflops_sustained", 1400.0))
+        tach = flops / (scan_ms * 1e-3) / 1e12 if scan_ms > 0 else None
+        roofline = {"bound": "tensor", "kernel": kname, "achieved": tach, "peak": tpeak, "unit": "TFLOP/s",
+                    "frac": (tach / tpeak) if tach else None,
+                    "peak_source": f"{psrc} bf16_tflops_sustained (kernel timed inside the step; f16 and bf16 share the "
+                                   f"tensor rate; burst figure {peaks.get('bf16_tflops')})",
+                    "traffic": traffic, "algorithmic_flops_per_launch": flops, "queries_per_pass": q_per_pass,
+                    "avg_launch_ms": scan_ms,
+                    "hbm": {"achieved": hbm_achieved, "peak": peak, "unit": "GB/s",
+                            "frac": (hbm_achieved / peak) if hbm_achieved else None,
+                            "algorithmic_bytes_per_launch": alg_bytes, "bytes_per_row": row_bytes},
+                    "scan_launches": int(st.scan_launches_timed), "scan_share_of_step": scan_share,
+                    "tc_queries": int(st.tc_queries), "tc_fallback_queries": int(st.tc_fallback_queries)}
+    else:
+        roofline = {"bound": "hbm", "kernel": kname,
+                    "achieved": hbm_achieved, "peak": peak, "unit": "GB/s", "frac": (hbm_achieved / peak) if hbm_achieved else None,
+                    "peak_source": f"{psrc} hbm_gbs", "traffic": traffic, "algorithmic_bytes_per_launch": alg_bytes,
+                    "avg_launch_ms": scan_ms, "scan_launches": int(st.scan_launches_timed), "scan_share_of_step": scan_share,
+                    "tc_queries": int(st.tc_queries), "tc_fallback_queries": int(st.tc_fallback_queries)}
 
     if knn1:
         g1 = rows_local * ROW_BYTES / (knn1["scan_ms"] * 1e-3) / 1e9
         knn1.update(achieved_gbs=g1, frac_of_measured_peak=g1 / peak, queries_per_s=1e3 / knn1["call_ms_host_buffers"])
     line = {"metric": "hybrid queries/sec", "value": value, "unit": "queries/s", "n_gpus": world, "steps": args.steps,
             "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps, "higher_is_better": True,
-            "scaling": "strong", "vs_baseline": None, "dtype": "f32 scan + f64 tail/BM25/fusion", "data": "synthetic",
+            "scaling": "strong", "vs_baseline": None, "dtype": "f16 tensor-core filter + exact f32 re-score (f64 tail), f64 BM25/fusion", "data": "synthetic",
             "config": config_dict(args, info, world), "roofline": roofline, "clocks": clocks, "e2e": e2e,
             "gpu_launches": launches, "sharded_matches_single_gpu": sharded_ok, "knn_batch1": knn1, "postings_touched_per_step": postings_touched(bm, tok_indptr, terms)}
 
