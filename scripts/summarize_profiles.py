@@ -29,6 +29,8 @@ def launches(tag, path):
     tot, cnt = collections.defaultdict(float), collections.Counter()
     for row in csv.DictReader(lines):
         name = row["Kernel Name"].split("(")[0]
+        if "rse::" not in name:
+            continue          # torch kernels that generate the synthetic corpus are not part of the step
         try:
             v = float(row["Metric Value"].replace(",", ""))
         except ValueError:
@@ -40,8 +42,20 @@ def launches(tag, path):
            f"# source: {Path(path).name}; {sum(cnt.values())} launches, {T/1e6:.1f} ms total", ""]
     for k, v in sorted(tot.items(), key=lambda x: -x[1])[:25]:
         out.append(f"{v/T*100:6.2f}%  n={cnt[k]:5d}  avg={v/cnt[k]/1e3:10.1f} us  {k[:110]}")
+    # the kernels of ONE step (between the last two fuse_kernel launches), in launch order
+    rows = [r for r in csv.DictReader(lines)]
+    names = [r["Kernel Name"].split("(")[0] for r in rows]
+    fuse = [i for i, n in enumerate(names) if "fuse_kernel" in n]
+    if len(fuse) >= 2:
+        out += ["", "# one step (launch order):"]
+        tot = 0.0
+        for i in range(fuse[-2] + 1, fuse[-1] + 1):
+            v = float(rows[i]["Metric Value"].replace(",", "")) * {"us": 1e3, "ms": 1e6, "s": 1e9}.get(rows[i]["Metric Unit"], 1.0)
+            tot += v
+            out.append(f"{v/1e3:10.1f} us  {names[i][:100]}")
+        out.append(f"{tot/1e3:10.1f} us  total")
     (ROOT / "profiles" / f"{tag}_launches_summary.txt").write_text("\n".join(out) + "\n")
-    print("\n".join(out[:14]))
+    print("\n".join(out))
 
 
 def full(tag, rep):
@@ -58,6 +72,21 @@ def full(tag, rep):
         out.append("")
     name = Path(rep).stem
     (ROOT / "profiles" / f"{name}_metrics.txt").write_text("\n".join(out) + "\n")
+    # DRAM traffic per launch of the dominant kernel (bench.py quotes it as roofline.traffic)
+    import json
+    for row in data:
+        kn = row[hdr.index("Kernel Name")]
+        if "knn_tc3_kernel<1>" in kn or "knn_tc3_kernel<(int)1>" in kn:
+            def val(m):
+                i = hdr.index(m)
+                return float(row[i].replace(",", "")) * {"Gbyte": 1e9, "Mbyte": 1e6, "Kbyte": 1e3, "byte": 1}.get(units[i], 1)
+            grid = row[hdr.index("Grid Size")] if "Grid Size" in hdr else ""
+            (ROOT / "profiles" / "r01_dominant_kernel_traffic.json").write_text(json.dumps({
+                "kernel": "knn_tc3_kernel<1> (filter)", "tc_kind": "f16-shadow", "rows": 4799462, "source": Path(rep).name,
+                "dram_bytes_read": val("dram__bytes_read.sum"), "dram_bytes_write": val("dram__bytes_write.sum"),
+                "gpu_time_ms_under_ncu": val("gpu__time_duration.sum") / 1e6 if units[hdr.index("gpu__time_duration.sum")] == "ns" else None,
+                "grid": grid}, indent=1) + "\n")
+            break
     print("\n".join(out[:40]))
 
 
