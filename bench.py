@@ -74,6 +74,15 @@ def parse_args():
                     help="hybrid600k = configs[3] (the metric's configuration, default); bm25_10k = configs[1]; "
                          "knn100m = configs[4] (12.5 M-row shard per GPU, top-100, NCCL candidate merge)")
     ap.add_argument("--shard-rows", type=int, default=12_500_000)
+    ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
+                    help="N > 1: weak = --batch queries per GPU per step (global batch = batch x N; every rank scans its "
+                         "row shard for all of them, so per-GPU work is constant); strong = the same --batch split over N")
+    ap.add_argument("--parallelism", default="auto", choices=["auto", "replicate", "rowshard"],
+                    help="N > 1: replicate = every GPU holds the corpus and serves its own slice of the query batch (hybrid "
+                         "queries are independent units: no data-path collective); rowshard = the corpus is cut by row, "
+                         "local top-K' + one all_gather + merge (what a corpus that does not fit one GPU needs: "
+                         "--workload knn100m always uses it).  auto = replicate when corpus + shadow fit in 1/3 of HBM; "
+                         "the JSON line then carries a shorter rowshard measurement of the same batch as well")
     ap.add_argument("--tc-mode", type=int, default=-1, help="rse_set_tc_mode override (see include/rse.h); -1 = library default")
     return ap.parse_args()
 
@@ -204,15 +213,18 @@ def postings_touched(bm, tok_indptr, terms) -> int:
     return int(bm.df[t].sum())
 
 
-def config_dict(args, info, world):
+def config_dict(args, info, world, par="replicate"):
     return {"workload": "configs[3]: movies_600k-shaped synthetic (S-600k), hybrid rrf_search k=60 limit=10 "
                         "(BM25 top-10 + exact vec0 KNN top-100 + per-movie best chunk + RRF), Gemini disabled",
             "mode": args.mode, "limit": args.limit, "knn_kprime": max(args.limit * 10, args.limit),
-            "queries_per_step": args.batch, "movies": info["movies"], "chunks": info["chunks"], "dim": info["dim"],
+            "queries_per_step": args.batch, "queries_per_gpu_per_step": args.batch // max(1, world) if getattr(args, "scaling", "weak") == "weak" else None,
+            "movies": info["movies"], "chunks": info["chunks"], "dim": info["dim"],
             "bm25_postings": info["postings"], "bm25_terms": info["terms"],
             "l2": "inputs larger than L2: every step streams the 3.7 GB fp16 shadow of the corpus (one pass per 256 "
                   "queries) and ~1.3 GB of postings against a 126 MB L2; no flush",
-            "parallelism": f"row-shard x{world} + all_gather(top-K') + query-slice BM25/fusion" if world > 1 else "1 GPU"}
+            "parallelism": ("1 GPU" if world == 1 else
+                            (f"row-shard x{world} + all_gather(top-K') + query-slice BM25/fusion" if par == "rowshard" else
+                             f"corpus replicated x{world}, query batch split by rank, no data-path collective"))}
 
 
 # ----------------------------------------------------------------------------- CPU baseline (oracle port)
@@ -254,7 +266,11 @@ def run_reference(args, rank, world):
     import oracle
     oracle.build()
     times = []
+    budget_s = 150.0          # the whole arm must end within a few minutes whatever --steps says
+    t_start = time.perf_counter()
     for step in range(args.warmup + args.steps):
+        if step > args.warmup + 1 and time.perf_counter() - t_start > budget_s:
+            break
         off = (step * sample) % max(1, args.batch - sample + 1)
         tp = (tok_indptr[off: off + sample + 1] - tok_indptr[off]).astype(np.int32)
         tr = terms[tok_indptr[off]: tok_indptr[off + sample]]
@@ -265,14 +281,71 @@ def run_reference(args, rank, world):
     total = sum(times)
     value = sample * len(times) / total
     line = {"impl": "reference", "metric": "hybrid queries/sec", "value": value, "unit": "queries/s",
-            "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * total / len(times),
-            "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f16 tensor-core filter + exact f32 re-score (f64 tail), f64 BM25/fusion",
+            "n_gpus": args.gpus, "steps": len(times), "steps_requested": args.steps, "warmup": args.warmup,
+            "ms_per_step": 1e3 * total / len(times),
+            "higher_is_better": True, "scaling": "replicas only (CPU path, rank 0)", "vs_baseline": None,
+            "dtype": "f32 sequential scan + f64 tail/BM25/fusion (the reference's arithmetic)",
             "data": "synthetic", "config": config_dict(args, info, 1),
             "cpu_baseline": {"value": value, "unit": "queries/s", "cores": cores, "kind": "port",
                              "sample": f"{sample} hybrid queries per step over the full S-600k corpus "
                                        f"(OpenMP over queries, each query a single-threaded literal vec0 scan)"},
             "e2e": {"value": value, "unit": "queries/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line), flush=True)
+
+
+def measure_rowshard(args, rank, world, local_rank, se, bm, tok_indptr, terms, Q, Qn, info, mode, param, limit, steps):
+    """The same global batch through the ROW-SHARDED path (north_star: local top-K' per shard + one NCCL all_gather
+    + merge; sharded.py): device-timed steps with the batch resident, max over ranks, checked against one handle."""
+    import torch
+    import torch.distributed as dist
+    from rag_search_engine_b200 import _lib, sharded
+    device = torch.device("cuda", local_rank)
+    C, nq = info["chunks"], Qn.shape[0]
+    bounds = sharded.shard_bounds(C, world)
+    lo, hi = bounds[rank], bounds[rank + 1]
+    idx = _lib.Index(local_rank)
+    if args.tc_mode >= 0:
+        idx.set_tc_mode(args.tc_mode)
+    stream = torch.cuda.current_stream(device)
+    idx.set_stream(stream.cuda_stream)
+    shard = se.emb[lo:hi]
+    mo = se.movie_of_chunk[lo:hi].contiguous()
+    idx.attach_embeddings_dev(shard.data_ptr(), hi - lo, info["dim"], movie_idx_ptr=mo.data_ptr(), pos_base=lo,
+                              keepalive=(se, shard, mo))
+    idx.load_bm25(bm.indptr, bm.doc_idx, bm.tf, bm.df, bm.dl, bm.n_movies, bm.avgdl)
+    idx.set_id_tables(se.movie_ids, se.movie_ids)
+    backend = sharded.LibrseShardBackend(idx, Qn, tok_indptr, terms, device)
+    sh = sharded.ShardedHybrid(backend, nq)
+    Qd = Q.to(device).contiguous()
+    for _ in range(3):
+        sh.step(Qd, mode, param, limit)
+    torch.cuda.synchronize(); dist.barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
+    for _ in range(steps):
+        r = sh.step(Qd, mode, param, limit)
+    e1.record(stream)
+    torch.cuda.synchronize(); dist.barrier()
+    t = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=device)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms = float(t.item())
+    ok = None
+    if rank == 0:
+        chk = _lib.Index(local_rank)
+        chk.set_stream(stream.cuda_stream)
+        mo_full = se.movie_of_chunk.contiguous()
+        chk.attach_embeddings_dev(se.emb.data_ptr(), C, info["dim"], movie_idx_ptr=mo_full.data_ptr(), keepalive=(se, mo_full))
+        chk.load_bm25(bm.indptr, bm.doc_idx, bm.tf, bm.df, bm.dl, bm.n_movies, bm.avgdl)
+        chk.set_id_tables(se.movie_ids, se.movie_ids)
+        oid, osc, oa, ob, oc = chk.hybrid(mode, param, limit, Qn, tok_indptr, terms)
+        ok = bool((r.ids.cpu().numpy() == oid).all() and (r.score.cpu().numpy() == osc).all() and
+                  (r.count.cpu().numpy() == oc).all())
+        chk.close()
+    idx.close()
+    dist.barrier()
+    return {"value": nq * steps / (ms / 1e3), "unit": "queries/s", "ms_per_step": ms / steps, "steps": steps,
+            "queries_per_step": nq, "parallelism": f"row-shard x{world} + all_gather(top-K') + query-slice BM25/fusion",
+            "sharded_matches_single_gpu": ok}
 
 
 # ----------------------------------------------------------------------------- B200 arm
@@ -283,10 +356,18 @@ def run_b200(args, rank, world, local_rank):
 
     torch.cuda.set_device(local_rank)
     device = torch.device("cuda", local_rank)
+    per_gpu_batch = args.batch
+    if world > 1 and args.scaling == "weak":
+        args.batch = args.batch * world          # global batch; every rank scans its shard for all of it
     se, bm, tok_indptr, terms, Q, info = build_workload(args, f"cuda:{local_rank}")
     C = info["chunks"]
-    bounds = sharded.shard_bounds(C, world)
-    lo, hi = bounds[rank], bounds[rank + 1]
+    par = args.parallelism
+    if par == "auto":
+        fits = C * info["dim"] * 6 < torch.cuda.get_device_properties(device).total_memory / 3
+        par = "replicate" if fits else "rowshard"
+    rowshard = world > 1 and par == "rowshard"
+    bounds = sharded.shard_bounds(C, world) if rowshard else [0] + [C] * world
+    lo, hi = (bounds[rank], bounds[rank + 1]) if rowshard else (0, C)
     idx = _lib.Index(local_rank)
     if args.tc_mode >= 0:
         idx.set_tc_mode(args.tc_mode)
@@ -304,18 +385,25 @@ def run_b200(args, rank, world, local_rank):
     Qh = torch.empty((nq, info["dim"]), dtype=torch.float32, pin_memory=True)
     Qh.copy_(Q.cpu())
     Qn = Qh.numpy()
+    # replicate: this rank's slice of the global batch (the whole batch when N = 1)
+    qs = sharded.query_slices(nq, world)
+    qlo, qhi = (qs[rank], qs[rank + 1]) if (world > 1 and not rowshard) else (0, nq)
+    Qn_loc = Qn[qlo:qhi]
+    tp_loc = (tok_indptr[qlo:qhi + 1] - tok_indptr[qlo]).astype(np.int32)
+    tr_loc = terms[tok_indptr[qlo]:tok_indptr[qhi]]
+    nq_loc = qhi - qlo
 
     def barrier():
         if world > 1:
             dist.barrier()
 
-    if world > 1:
+    if rowshard:
         backend = sharded.LibrseShardBackend(idx, Qn, tok_indptr, terms, device)
         sh = sharded.ShardedHybrid(backend, nq)
         Qd = Q.to(device).contiguous()
         step_fn = lambda: sh.step(Qd, mode, param, limit)        # noqa: E731
     else:
-        idx.hybrid_stage(Qn, tok_indptr, terms)
+        idx.hybrid_stage(Qn_loc, tp_loc, tr_loc)
         step_fn = lambda: idx.hybrid_run(mode, param, limit)     # noqa: E731
 
     for _ in range(max(args.warmup, 3)):
@@ -335,7 +423,7 @@ def run_b200(args, rank, world, local_rank):
     e1.record(stream)
     torch.cuda.synchronize(); barrier()
     clocks = sampler.stop()
-    sh_last = step_fn() if world > 1 else None
+    sh_last = step_fn() if rowshard else None
     torch.cuda.synchronize(); barrier()
     ms = e0.elapsed_time(e1)
     st = idx.stats()
@@ -351,24 +439,30 @@ def run_b200(args, rank, world, local_rank):
 
     # ---- e2e: host buffers through the C-ABI call, copies inside the timed region
     e2e = None
-    if not args.no_e2e and world == 1:
+    res = None
+    if not args.no_e2e and not rowshard:
+        # every rank: its slice of the batch through the host-buffer call (H2D of queries + tokens, D2H of results)
         for _ in range(2):
-            idx.hybrid(mode, param, limit, Qn, tok_indptr, terms)
-        torch.cuda.synchronize()
+            idx.hybrid(mode, param, limit, Qn_loc, tp_loc, tr_loc)
+        torch.cuda.synchronize(); barrier()
         t0 = time.perf_counter()
         e0.record(stream)
         for _ in range(args.steps):
-            res = idx.hybrid(mode, param, limit, Qn, tok_indptr, terms)
+            res = idx.hybrid(mode, param, limit, Qn_loc, tp_loc, tr_loc)
         e1.record(stream)
         torch.cuda.synchronize()
         wall = time.perf_counter() - t0
+        if world > 1:
+            t = torch.tensor([wall], dtype=torch.float64, device=device)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            wall = float(t.item())
         ntok = int(tok_indptr[-1])
-        h2d = Qn.nbytes + (nq + 1) * 4 + ntok * (4 + 8)
+        h2d = Qn.nbytes + (nq + world) * 4 + ntok * (4 + 8)
         d2h = nq * limit * (8 + 8 + 8 + 8) + nq * 4
         e2e = {"value": nq * args.steps / wall, "unit": "queries/s", "h2d_bytes_per_step": int(h2d),
                "d2h_bytes_per_step": int(d2h), "device_ms_per_step": e0.elapsed_time(e1) / args.steps,
                "wall_ms_per_step": 1e3 * wall / args.steps}
-    elif world > 1:
+    elif rowshard and not args.no_e2e:
         # sharded e2e: stage (H2D of this rank's slice + the batch's query vectors) + step + D2H of the fused batch
         torch.cuda.synchronize(); barrier()
         t0 = time.perf_counter()
@@ -402,19 +496,38 @@ def run_b200(args, rank, world, local_rank):
         knn1 = {"scan_ms": sm1, "call_ms_host_buffers": 1e3 * wall1, "launches_per_query": s1.kernel_launches / reps}
 
     sharded_ok = None
-    if world > 1 and rank == 0:
-        # rank 0 generated the whole corpus: check the sharded result against a single-handle run
-        chk = _lib.Index(local_rank)
-        chk.set_stream(stream.cuda_stream)
-        mo_full = se.movie_of_chunk.contiguous()
-        chk.attach_embeddings_dev(se.emb.data_ptr(), C, info["dim"], movie_idx_ptr=mo_full.data_ptr(), keepalive=(se, mo_full))
-        chk.load_bm25(bm.indptr, bm.doc_idx, bm.tf, bm.df, bm.dl, bm.n_movies, bm.avgdl)
-        chk.set_id_tables(se.movie_ids, se.movie_ids)
-        oid, osc, oa, ob, oc = chk.hybrid(mode, param, limit, Qn, tok_indptr, terms)
-        r = sh_last
-        sharded_ok = bool((r.ids.cpu().numpy() == oid).all() and (r.score.cpu().numpy() == osc).all() and
-                          (r.count.cpu().numpy() == oc).all())
-        chk.close()
+    replicas_ok = None
+    rowshard_extra = None
+    if world > 1:
+        # rank 0 generated the whole corpus: check the N-GPU result against a single-handle run of the whole batch
+        if rowshard:
+            got = (sh_last.ids.cpu().numpy(), sh_last.score.cpu().numpy(), sh_last.count.cpu().numpy())
+        else:
+            mine = res if res is not None else idx.hybrid(mode, param, limit, Qn_loc, tp_loc, tr_loc)
+            parts = [None] * world
+            dist.all_gather_object(parts, (mine[0], mine[1], mine[4]))
+            got = tuple(np.concatenate([p[i] for p in parts]) for i in range(3))
+        if rank == 0:
+            if rowshard:
+                chk = _lib.Index(local_rank)
+                chk.set_stream(stream.cuda_stream)
+                mo_full = se.movie_of_chunk.contiguous()
+                chk.attach_embeddings_dev(se.emb.data_ptr(), C, info["dim"], movie_idx_ptr=mo_full.data_ptr(),
+                                          keepalive=(se, mo_full))
+                chk.load_bm25(bm.indptr, bm.doc_idx, bm.tf, bm.df, bm.dl, bm.n_movies, bm.avgdl)
+                chk.set_id_tables(se.movie_ids, se.movie_ids)
+            else:
+                chk = idx
+            oid, osc, oa, ob, oc = chk.hybrid(mode, param, limit, Qn, tok_indptr, terms)
+            ok = bool((got[0] == oid).all() and (got[1] == osc).all() and (got[2] == oc).all())
+            if rowshard:
+                sharded_ok = ok
+                chk.close()
+            else:
+                replicas_ok = ok
+        if not rowshard and args.parallelism == "auto":
+            rowshard_extra = measure_rowshard(args, rank, world, local_rank, se, bm, tok_indptr, terms, Q, Qn, info, mode,
+                                              param, limit, min(args.steps, 30))
     if world > 1:
         dist.barrier()
     if rank != 0:
@@ -443,7 +556,7 @@ def run_b200(args, rank, world, local_rank):
         # The batched filter pass is bound by the tensor pipe (+ TMEM reads), not by the stream: with the MMAs
         # removed the same kernel streams the shadow at 7.4 TB/s (0.50 ms), with the TMEM loads removed it takes
         # 0.65 ms = 1.45 PFLOP/s.  Algorithmic work: 2*384 flop per (row, query) pair.
-        q_per_pass = min(nq, 256)
+        q_per_pass = min(nq if rowshard else nq_loc, 256)
         flops = 2.0 * 384 * rows_local * q_per_pass
         tpeak = float(peaks.get("bf16_tflops_sustained", 1400.0))
         tach = flops / (scan_ms * 1e-3) / 1e12 if scan_ms > 0 else None
@@ -470,9 +583,11 @@ def run_b200(args, rank, world, local_rank):
         knn1.update(achieved_gbs=g1, frac_of_measured_peak=g1 / peak, queries_per_s=1e3 / knn1["call_ms_host_buffers"])
     line = {"metric": "hybrid queries/sec", "value": value, "unit": "queries/s", "n_gpus": world, "steps": args.steps,
             "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps, "higher_is_better": True,
-            "scaling": "strong", "vs_baseline": None, "dtype": "f16 tensor-core filter + exact f32 re-score (f64 tail), f64 BM25/fusion", "data": "synthetic",
-            "config": config_dict(args, info, world), "roofline": roofline, "clocks": clocks, "e2e": e2e,
-            "gpu_launches": launches, "sharded_matches_single_gpu": sharded_ok, "knn_batch1": knn1, "postings_touched_per_step": postings_touched(bm, tok_indptr, terms)}
+            "scaling": (args.scaling if world > 1 else "weak"), "vs_baseline": None,
+            "dtype": "f16 tensor-core filter + exact f32 re-score (f64 tail), f64 BM25/fusion", "data": "synthetic",
+            "config": config_dict(args, info, world, par), "roofline": roofline, "clocks": clocks, "e2e": e2e,
+            "gpu_launches": launches, "sharded_matches_single_gpu": sharded_ok, "replicas_match_single_gpu": replicas_ok,
+            "rowshard": rowshard_extra, "knn_batch1": knn1, "postings_touched_per_step": postings_touched(bm, tok_indptr, terms)}
 
     if world == 1 and not args.no_cpu_baseline:
         cores = os.cpu_count() or 1
