@@ -112,15 +112,13 @@ __device__ __forceinline__ Key128 block_argmin(Key128 mine, Key128* s_k, int* s_
 
 // K6: one CTA per (range, query).
 //   cand_hi/lo: [nq][nr][k]; cand_cnt: [nq][nr]
-__global__ void __launch_bounds__(kBmThreads)
-bm25_score_kernel(const int64_t* __restrict__ indptr, const uint2* __restrict__ post,
-                  const uint32_t* __restrict__ roff, const double* __restrict__ normk, int nr,
-                  int64_t n_docs, const int32_t* __restrict__ tok_indptr, const int32_t* __restrict__ term_rows,
-                  const double* __restrict__ tok_idf, int q0, int k, double k1p1,
-                  unsigned long long* __restrict__ cand_hi, unsigned long long* __restrict__ cand_lo,
-                  int* __restrict__ cand_cnt, const int* __restrict__ only_flagged) {
-  // second launch after bm25_stream_kernel: only the queries it flagged are (re-)scored here
-  if (only_flagged && only_flagged[q0 + blockIdx.y] == 0) return;
+__device__ __forceinline__ void
+bm25_score_one(const int64_t* __restrict__ indptr, const uint2* __restrict__ post,
+               const uint32_t* __restrict__ roff, const double* __restrict__ normk, int nr,
+               int64_t n_docs, const int32_t* __restrict__ tok_indptr, const int32_t* __restrict__ term_rows,
+               const double* __restrict__ tok_idf, int q, int k, double k1p1,
+               unsigned long long* __restrict__ cand_hi, unsigned long long* __restrict__ cand_lo,
+               int* __restrict__ cand_cnt) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   double* acc = reinterpret_cast<double*>(smem_raw);                       // [kBmRange]
   unsigned char* first = reinterpret_cast<unsigned char*>(acc + kBmRange); // [kBmRange]
@@ -138,11 +136,11 @@ bm25_score_kernel(const int64_t* __restrict__ indptr, const uint2* __restrict__ 
   __shared__ Key128 s_tau;
 
   const int r = blockIdx.x;
-  const int q = q0 + blockIdx.y;
   const int t0 = tok_indptr[q], t1 = tok_indptr[q + 1];
   const int ntok = t1 - t0;
   const int64_t cbase = (static_cast<int64_t>(q) * nr + r);
 
+  __syncthreads();                                        // a previous query of this CTA may still be reading the scratch
   if (threadIdx.x == 0) s_total = 0u;
   __syncthreads();
   for (int t = threadIdx.x; t < ntok; t += blockDim.x) {
@@ -336,6 +334,41 @@ bm25_score_kernel(const int64_t* __restrict__ indptr, const uint2* __restrict__ 
     ++emitted;
   }
   if (threadIdx.x == 0) cand_cnt[cbase] = emitted;
+}
+
+// flagged == nullptr: grid (nr, nq), CTA (r, j) scores query q0 + j.
+// flagged != nullptr (second launch after bm25_stream_kernel): grid (nr, few); the CTAs walk the compacted list of
+// the queries the streaming path flagged (flagged[0] = count, flagged[1..] = query indices) — usually empty, so
+// the launch costs a few microseconds instead of one early-exit CTA per (range, query).
+__global__ void __launch_bounds__(kBmThreads)
+bm25_score_kernel(const int64_t* __restrict__ indptr, const uint2* __restrict__ post,
+                  const uint32_t* __restrict__ roff, const double* __restrict__ normk, int nr,
+                  int64_t n_docs, const int32_t* __restrict__ tok_indptr, const int32_t* __restrict__ term_rows,
+                  const double* __restrict__ tok_idf, int q0, int k, double k1p1,
+                  unsigned long long* __restrict__ cand_hi, unsigned long long* __restrict__ cand_lo,
+                  int* __restrict__ cand_cnt, const int* __restrict__ flagged) {
+  if (!flagged) {
+    bm25_score_one(indptr, post, roff, normk, nr, n_docs, tok_indptr, term_rows, tok_idf, q0 + blockIdx.y, k, k1p1, cand_hi,
+                   cand_lo, cand_cnt);
+    return;
+  }
+  const int n = flagged[0];
+  for (int j = blockIdx.y; j < n; j += gridDim.y)
+    bm25_score_one(indptr, post, roff, normk, nr, n_docs, tok_indptr, term_rows, tok_idf, flagged[1 + j], k, k1p1, cand_hi,
+                   cand_lo, cand_cnt);
+}
+
+// flagged[0] = number of queries in [q0, q0 + nc) with status != 0, flagged[1..] = those queries (ascending)
+__global__ void bm25_flag_compact_kernel(const int* __restrict__ status, int q0, int nc, int* __restrict__ flagged) {
+  __shared__ int s_n;
+  if (threadIdx.x == 0) s_n = 0;
+  __syncthreads();
+  for (int base = 0; base < nc; base += blockDim.x) {      // one CTA; order inside the list does not matter
+    const int j = base + threadIdx.x;
+    if (j < nc && status[q0 + j] != 0) flagged[1 + atomicAdd(&s_n, 1)] = q0 + j;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) flagged[0] = s_n;
 }
 
 // ---------------------------------------------------------------------------------------------

@@ -118,12 +118,27 @@ __device__ __forceinline__ float cosine_tail(float dot, double sa, double sb) {
 // recomputes bMag for every row; it is row-independent).
 template <bool FMA>
 __global__ void knn_query_prep_kernel(const float* __restrict__ q, int nq, int dim, double* __restrict__ sb) {
-  int j = blockIdx.x * blockDim.x + threadIdx.x;
+  // one warp per query: the row is fetched coalesced into shared memory, then ONE lane adds the squares in
+  // index order (the reference's single sequential accumulator).  A thread-per-query loop over global memory
+  // took 29 us for 256 queries (384 dependent scalar loads each).
+  constexpr int kMaxStaged = 1024;
+  __shared__ float s_v[4][kMaxStaged];
+  const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int j = blockIdx.x * 4 + w;
   if (j >= nq) return;
   const float* v = q + static_cast<int64_t>(j) * dim;
   float m = 0.0f;
-  for (int i = 0; i < dim; ++i) m = mac<FMA>(m, v[i], v[i]);
-  sb[j] = sqrt(static_cast<double>(m));
+  if (dim <= kMaxStaged) {
+    for (int i = lane; i < dim; i += 32) s_v[w][i] = v[i];
+    __syncwarp();
+    if (lane == 0) {
+#pragma unroll 8
+      for (int i = 0; i < dim; ++i) m = mac<FMA>(m, s_v[w][i], s_v[w][i]);
+    }
+  } else if (lane == 0) {
+    for (int i = 0; i < dim; ++i) m = mac<FMA>(m, v[i], v[i]);
+  }
+  if (lane == 0) sb[j] = sqrt(static_cast<double>(m));
 }
 
 // amag[row] = Σ a_i^2 (sequential fp32), -1 for empty vec0 slots.  Load time only.

@@ -304,6 +304,61 @@ __global__ void tc3_threshold_kernel(const SelState* __restrict__ st, const doub
   thr[q] = t;
 }
 
+// Sparse probe → thresholds in one launch: one CTA per query finds the K'-th smallest of its <= 2048 probe
+// values (MSD radix select, 4 x 8 bits, in shared memory) and writes thr[q] like tc3_threshold_kernel.
+// (select_init + three select passes + the threshold kernel were five launches and 35 us for 1184 values.)
+constexpr int kT3SelMax = 2048;
+__global__ void __launch_bounds__(256)
+tc3_probe_threshold_kernel(const uint32_t* __restrict__ dist, int64_t ld, int nq, int kprime,
+                           const double* __restrict__ sb, float* __restrict__ thr) {
+  __shared__ uint32_t s_key[kT3SelMax];
+  __shared__ unsigned int s_hist[256];
+  __shared__ unsigned int s_prefix, s_need, s_fail;
+  const int q = blockIdx.x;
+  const float inf = __int_as_float(0x7F800000);
+  if (q >= nq || !(sb[q] > 0.0 && sb[q] < 1e300)) {
+    if (threadIdx.x == 0) thr[q] = inf;
+    return;
+  }
+  const int n = static_cast<int>(ld);
+  for (int i = threadIdx.x; i < n; i += blockDim.x) s_key[i] = f32_orderable(dist[static_cast<int64_t>(q) * ld + i]);
+  if (threadIdx.x == 0) { s_prefix = 0u; s_need = static_cast<unsigned int>(kprime); s_fail = n < kprime ? 1u : 0u; }
+  __syncthreads();
+  uint32_t resolved = 0u;
+  for (int pass = 0; pass < 4 && s_fail == 0u; ++pass) {
+    const int shift = 24 - 8 * pass;
+    s_hist[threadIdx.x] = 0u;
+    __syncthreads();
+    const uint32_t prefix = s_prefix;
+    for (int i = threadIdx.x; i < n; i += blockDim.x) {
+      const uint32_t key = s_key[i];
+      if ((key & resolved) == prefix) atomicAdd(&s_hist[(key >> shift) & 0xFFu], 1u);
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      unsigned int need = s_need, run = 0u;
+      int d = 0;
+      for (; d < 256; ++d) {
+        if (run + s_hist[d] >= need) break;
+        run += s_hist[d];
+      }
+      s_prefix = prefix | (static_cast<uint32_t>(d & 0xFF) << shift);
+      s_need = need - run;
+    }
+    resolved |= 0xFFu << shift;
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) {
+    float t = inf;
+    if (s_fail == 0u) {
+      const float tau = __uint_as_float(f32_from_orderable(s_prefix));   // K'-th smallest d~ (NaN if it is a sentinel)
+      const float cut = 1.0f - tau - 2.0f * kTcEps - 1e-6f;
+      if (cut > 1e-6f) t = cut;
+    }
+    thr[q] = t;
+  }
+}
+
 // ---------------------------------------------------------------- the GEMM
 // MODE 0 (probe) : tiles t = 0..n_tiles-1 map to the 256-row tile t*tile_stride; d~ = 1 - cos~ is stored to
 //                  dist[q*ld + t*256 + r].  Empty slots / rows past the end are zero rows of the shadow:

@@ -92,7 +92,7 @@ struct rse_index {
   double normk_k1 = NAN, normk_b = NAN;
   Post16* post16 = nullptr;        // {doc, tf, w}: postings with the (k1, b)-dependent weight precomputed (bm25_stream_kernel)
   double w_k1 = NAN, w_b = NAN;
-  DevBuf b_shi, b_slo, b_scnt, b_status;
+  DevBuf b_shi, b_slo, b_scnt, b_status, b_flagged;
   std::vector<int64_t> df_host;
   DevBuf b_tokptr, b_terms, b_idf, b_chi, b_clo, b_ccnt, b_score, b_doc, b_count;
 
@@ -446,9 +446,12 @@ int knn_tc3_block(rse_index* h, const float* q_dev, const double* sb, int nqb, i
         h->tmap_a16, h->tmap_q16, n_probe, tile_stride, nqb, nullptr, dist, ld_probe, nullptr, nullptr, 0);
   }
   LAUNCHED(h);
-  select_init_kernel<<<(nqb + 127) / 128, 128, 0, h->stream>>>(sel, nqb, static_cast<unsigned int>(kprime));
-  LAUNCHED(h);
-  {
+  if (sparse_probe && ld_sel <= kT3SelMax) {
+    tc3_probe_threshold_kernel<<<kTcBN, 256, 0, h->stream>>>(dist, ld_sel, nqb, kprime, sb, thr);
+    LAUNCHED(h);
+  } else {
+    select_init_kernel<<<(nqb + 127) / 128, 128, 0, h->stream>>>(sel, nqb, static_cast<unsigned int>(kprime));
+    LAUNCHED(h);
     int blocks = static_cast<int>(std::min<int64_t>((ld_sel + 4095) / 4096, h->sm_count));
     if (blocks < 1) blocks = 1;
     dim3 grid(blocks, nqb);
@@ -458,9 +461,9 @@ int knn_tc3_block(rse_index* h, const float* q_dev, const double* sb, int nqb, i
       select_pass_kernel<<<grid, kSelThreads, 0, h->stream>>>(dist, ld_sel, ld_sel, 0ull, sel, hist, shifts[p], widths[p]);
       LAUNCHED(h);
     }
+    tc3_threshold_kernel<<<2, 128, 0, h->stream>>>(sel, sb, nqb, thr);
+    LAUNCHED(h);
   }
-  tc3_threshold_kernel<<<2, 128, 0, h->stream>>>(sel, sb, nqb, thr);
-  LAUNCHED(h);
 
   // 2. filter pass over all rows
   CK(cudaMemsetAsync(h->tc_cnt.p, 0, sizeof(unsigned int) * kTcBN, h->stream));
@@ -619,8 +622,8 @@ int knn_local(rse_index* h, const float* q_dev, int nq, int kprime, long long* c
     CK(cudaMemsetAsync(h->hist.p, 0, h->hist.bytes, h->stream));
   }
   double* sb = static_cast<double*>(h->sb.p);
-  if (h->fma) knn_query_prep_kernel<true><<<(nq + 127) / 128, 128, 0, h->stream>>>(q_dev, nq, h->dim, sb);
-  else knn_query_prep_kernel<false><<<(nq + 127) / 128, 128, 0, h->stream>>>(q_dev, nq, h->dim, sb);
+  if (h->fma) knn_query_prep_kernel<true><<<(nq + 3) / 4, 128, 0, h->stream>>>(q_dev, nq, h->dim, sb);
+  else knn_query_prep_kernel<false><<<(nq + 3) / 4, 128, 0, h->stream>>>(q_dev, nq, h->dim, sb);
   LAUNCHED(h);
 
   if (!tc_eligible(h, nq, kprime)) return knn_exact_groups(h, q_dev, sb, nq, kprime, cand_dev);
@@ -753,7 +756,7 @@ void rse_destroy(rse_index* h) {
                     &h->b_ccnt, &h->b_score, &h->b_doc, &h->b_count, &h->f_bid, &h->f_bsc, &h->f_bcnt, &h->f_sid,
                     &h->f_sds, &h->f_scnt, &h->f_oid, &h->f_osc, &h->f_oa, &h->f_ob, &h->f_ocnt, &h->tc_q, &h->tc_thr, &h->tc_isb,
                     &h->tc_rows, &h->tc_cnt, &h->tc_keys, &h->tc_status, &h->tc_q16, &h->b_shi, &h->b_slo, &h->b_scnt,
-                    &h->b_status})
+                    &h->b_status, &h->b_flagged})
     free_buf(*b);
   free_ptr(h->doc_ids);
   free_ptr(h->movie_ids);
@@ -1145,6 +1148,7 @@ int bm25_run(rse_index* h, int nq, int k, double k1, double b) {
     ENSURE(h->b_slo, sizeof(unsigned long long) * per_qs * std::min(nq, chunk));
     ENSURE(h->b_scnt, sizeof(int) * static_cast<size_t>(ng) * std::min(nq, chunk));
     ENSURE(h->b_status, sizeof(int) * nq);
+    ENSURE(h->b_flagged, sizeof(int) * (std::min(nq, chunk) + 1));
     CK(cudaMemsetAsync(h->b_status.p, 0, sizeof(int) * nq, h->stream));
   }
   for (int q0 = 0; q0 < nq; q0 += chunk) {
@@ -1171,10 +1175,17 @@ int bm25_run(rse_index* h, int nq, int k, double k1, double b) {
       LAUNCHED(h);
     }
     // general kernel: every query when the streaming path does not apply, else only the flagged ones
-    dim3 grid(h->nr, nc);
+    // (compacted on the device; the launch is then a small grid that usually finds an empty list)
+    int* flagged = nullptr;
+    if (stream) {
+      flagged = static_cast<int*>(h->b_flagged.p);
+      bm25_flag_compact_kernel<<<1, 256, 0, h->stream>>>(status, q0, nc, flagged);
+      LAUNCHED(h);
+    }
+    dim3 grid(h->nr, stream ? std::min(nc, 16) : nc);
     bm25_score_kernel<<<grid, kBmThreads, kBmRange * 9, h->stream>>>(
         h->indptr, h->post, h->roff, h->normk, h->nr, h->n_docs, static_cast<const int32_t*>(h->b_tokptr.p),
-        static_cast<const int32_t*>(h->b_terms.p), static_cast<const double*>(h->b_idf.p), q0, k, k1p1, chi, clo, ccnt, status);
+        static_cast<const int32_t*>(h->b_terms.p), static_cast<const double*>(h->b_idf.p), q0, k, k1p1, chi, clo, ccnt, flagged);
     LAUNCHED(h);
     bm25_merge_kernel<<<nc, kBmThreads, 0, h->stream>>>(chi, clo, ccnt, h->nr, q0, k, static_cast<double*>(h->b_score.p),
                                                         static_cast<int*>(h->b_doc.p), static_cast<int*>(h->b_count.p),
