@@ -96,6 +96,12 @@ int rse_set_fma(rse_index *h, int32_t use_fma);
  * 5 / 6 = like 0 / 2 with the TF32 kernel that streams the queries (knn_tc.cuh). */
 int rse_set_tc_mode(rse_index *h, int32_t mode);
 
+/* Which BM25 kernels serve rse_bm25 / rse_hybrid for k <= 32 (results are bit-identical in every mode):
+ * 0 = fixed-point streaming kernel + exact re-score of the finalists (default), 1 = streaming kernel that
+ * keeps the reference's summation order with one barrier per (range, token) slice, 2 = general kernel only
+ * (one CTA per range and query; what k > 32, > 16 tokens and flagged queries always use). */
+int rse_set_bm25_mode(rse_index *h, int32_t mode);
+
 /* KNN: `embedding MATCH :q AND k = :k ... ORDER BY knn.distance`
  * (semantic_search.py:254-279).  Q is [nq, dim] fp32.  Outputs are [nq, kprime]
  * in vec0 emit order (distance asc, block asc, slot desc); out_count[q] <= kprime

@@ -63,6 +63,7 @@ _SIGNATURES = {
                                                  c_void_p, c_int64]),
     "rse_set_fma": (ctypes.c_int, [c_void_p, c_int32]),
     "rse_set_tc_mode": (ctypes.c_int, [c_void_p, c_int32]),
+    "rse_set_bm25_mode": (ctypes.c_int, [c_void_p, c_int32]),
     "rse_knn": (ctypes.c_int, [c_void_p, POINTER(c_float), c_int32, c_int32, POINTER(c_float), POINTER(c_int64),
                                POINTER(c_int64), POINTER(c_int32), POINTER(c_int32)]),
     "rse_knn_movies": (ctypes.c_int, [c_void_p, POINTER(c_float), c_int32, c_int32, c_int32, POINTER(c_float),
@@ -180,6 +181,11 @@ class Index:
         kernel); 3 / 4 = like 0 / 2 with the TF32 TMEM-resident-queries kernel; 5 / 6 = like 0 / 2 with
         the TF32 streamed-queries kernel.  Results are identical in every mode."""
         self._check(self._L.rse_set_tc_mode(self._h, int(mode)))
+
+    def set_bm25_mode(self, mode: int):
+        """0 = fixed-point streaming BM25 + exact re-score of the finalists (default), 1 = exact-order streaming
+        kernel, 2 = general kernel only.  Results are identical in every mode."""
+        self._check(self._L.rse_set_bm25_mode(self._h, int(mode)))
 
     def set_fma(self, on: bool):
         self._check(self._L.rse_set_fma(self._h, int(bool(on))))

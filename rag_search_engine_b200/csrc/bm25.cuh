@@ -407,6 +407,7 @@ constexpr int kBsMaxTok = 16;
 constexpr int kBsMaxRpg = 128;                    // ranges per group (bounds the offset table in shared memory)
 constexpr unsigned int kBsCandCap = 256;
 constexpr unsigned int kBsCompactAt = 128;
+constexpr int kBsMaxGroups = 32;                  // groups per query bm25_fx_finish_kernel merges
 constexpr unsigned int kBsRangeCap = 256;         // documents that may cross theta inside one range
 constexpr int kBsFinalCap = 64;                   // finalists (k + ties) ranked exactly
 
@@ -655,6 +656,356 @@ bm25_stream_kernel(const int64_t* __restrict__ indptr, const Post16* __restrict_
   if (threadIdx.x == 0) cand_cnt[cbase] = static_cast<int>(n) < k ? static_cast<int>(n) : k;
 }
 
+// ---------------------------------------------------------------------------------------------
+// K6'' + K7'': fixed-point streaming BM25 — selection on an order-free sum, exact re-score of the finalists.
+//
+// bm25_stream_kernel keeps the reference's summation order with a CTA barrier after every (range, token) slice;
+// the median slice holds ~150 postings, so its 16 warps mostly wait at barriers (r01 ncu: barrier 8.7 + long
+// scoreboard 5.9 stall cycles per issue, 0.43 ms per 256-query step whatever is done about load latency).
+// The order only matters for the low bits of a sum.  This kernel accumulates idf*w in 32-bit FIXED POINT with
+// native shared-memory integer atomics (ATOMS.ADD; 64-bit and double shared atomics are CAS loops on sm_100).  The
+// scale is the largest power of two that keeps (k1+1)*log(N+2)*16 below 2^31 (2^21 for the default k1: steps of
+// 4.8e-7).  The sum is exact in that format, independent of the order, and within 8 units (each of <= 16 terms is
+// rounded once, <= 0.5 unit) of the reference's double sum times the scale — so all the
+// token slices of a range are cut into 32-posting items that the warps take round robin with NO barrier between
+// tokens.  Everything decided on these sums carries a margin of kFxMargin units; the finalists (k plus whatever
+// lies within the margin of the k-th) are RE-SCORED in bm25_fx_finish_kernel with the reference's own
+// expression in query-token order — one thread per (document, token) finds the posting by binary search — which
+// also yields the reference's tie key (first token holding the document).  Scores, order and ties are therefore
+// bit-identical to the general kernel; queries it cannot finish are flagged for it exactly like before.
+constexpr unsigned int kFxMargin = 40u;               // > 2 x (8 units of accumulated rounding + the double sum's own)
+constexpr int kFxFinalCap = 48;
+constexpr int kFxRescoreCap = 96;
+
+__host__ __device__ constexpr int fx_smem_bytes(int rpg) {
+  return kBmRange * 4 + ((kBsMaxTok * (rpg + 1) * 4 + 15) & ~15) + 2 * static_cast<int>(kBsCandCap) * 8;
+}
+
+// fin: [nq][ng][kFxFinalCap] {fixed-point sum, doc}; fin_cnt: [nq][ng]
+__global__ void __launch_bounds__(kBsThreads, 3)
+bm25_fx_kernel(const int64_t* __restrict__ indptr, const Post16* __restrict__ post, const uint32_t* __restrict__ roff,
+               int nr, const int32_t* __restrict__ tok_indptr, const int32_t* __restrict__ term_rows,
+               const double* __restrict__ tok_idf, double scale, int q0, int k, int rpg, int ng,
+               uint2* __restrict__ fin, int* __restrict__ fin_cnt, int* __restrict__ status) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  uint32_t* acc = reinterpret_cast<uint32_t*>(smem_raw);                               // [kBmRange] fixed-point sums
+  uint32_t* s_off = acc + kBmRange;                                                    // [kBsMaxTok][rpg + 1]
+  const int ostride = rpg + 1;
+  uint2* s_cand0 = reinterpret_cast<uint2*>(smem_raw + kBmRange * 4 + ((kBsMaxTok * ostride * 4 + 15) & ~15));
+  uint2* s_cand1 = s_cand0 + kBsCandCap;                                               // {sum, doc}
+  __shared__ long long s_base[kBsMaxTok];
+  __shared__ double s_idfx[kBsMaxTok];                                                 // idf * scale (exact: a power of two)
+  __shared__ int s_term[kBsMaxTok];
+  __shared__ unsigned int s_pre[kBsMaxTok + 1];
+  __shared__ unsigned int s_ncand, s_nkept, s_nrc;
+  __shared__ unsigned int s_min, s_tw;
+  __shared__ unsigned short s_rc[kBsRangeCap];
+  __shared__ unsigned char s_itok[kBsMaxTok * (kBmRange / 32)];                        // token of every item of the range
+
+  const int g = blockIdx.x;
+  const int q = q0 + blockIdx.y;
+  const int t0 = tok_indptr[q], ntok = tok_indptr[q + 1] - t0;
+  const int64_t cbase = static_cast<int64_t>(q) * ng + g;
+  if (ntok > kBsMaxTok) {                                 // uniform: the whole query goes to the general kernel
+    if (threadIdx.x == 0) { fin_cnt[cbase] = 0; if (g == 0) status[q] = 1; }
+    return;
+  }
+  const int r0 = g * rpg, r1 = min(nr, r0 + rpg);
+  const int nrg = r1 - r0;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  if (threadIdx.x < ntok) {
+    const int term = term_rows[t0 + threadIdx.x];
+    s_term[threadIdx.x] = term;
+    s_base[threadIdx.x] = term >= 0 ? indptr[term] : 0;
+    s_idfx[threadIdx.x] = tok_idf[t0 + threadIdx.x] * scale;
+  }
+  if (threadIdx.x == 0) { s_ncand = 0u; s_nrc = 0u; }
+  __syncthreads();
+  for (int i = threadIdx.x; i < ntok * (nrg + 1); i += blockDim.x) {
+    const int t = i / (nrg + 1), j = i - t * (nrg + 1);
+    const int term = s_term[t];
+    s_off[t * ostride + j] = term >= 0 ? roff[static_cast<int64_t>(term) * (nr + 1) + r0 + j] : 0u;
+  }
+  {
+    uint4* a4 = reinterpret_cast<uint4*>(acc);
+    for (int i = threadIdx.x; i < kBmRange / 4; i += blockDim.x) a4[i] = make_uint4(0u, 0u, 0u, 0u);
+  }
+  __syncthreads();
+
+  uint2* cand = s_cand0;
+  uint2* cand_alt = s_cand1;
+  unsigned int theta = 0u;                        // 0 = not established: every touched document qualifies
+  bool established = false;
+
+  // keep the documents that fewer than k others beat beyond the margin; new theta = (smallest kept sum) - margin:
+  // a later document below it has k documents above it by more than the margin, i.e. k exactly greater scores
+  auto compact = [&]() {
+    const unsigned int n = s_ncand;                       // uniform (read after a barrier)
+    if (n < static_cast<unsigned int>(k)) return;
+    if (threadIdx.x == 0) { s_nkept = 0u; s_min = ~0u; }
+    __syncthreads();
+    if (threadIdx.x < n) {
+      const uint2 me = cand[threadIdx.x];
+      const unsigned int bar = me.x + kFxMargin;
+      unsigned int greater = 0u;
+      for (unsigned int j = 0; j < n; ++j) greater += cand[j].x > bar ? 1u : 0u;
+      if (greater < static_cast<unsigned int>(k)) {
+        cand_alt[atomicAdd(&s_nkept, 1u)] = me;
+        atomicMin(&s_min, me.x);
+      }
+    }
+    __syncthreads();
+    uint2* tmp = cand; cand = cand_alt; cand_alt = tmp;
+    const unsigned int mn = s_min;
+    theta = mn > kFxMargin ? mn - kFxMargin : 1u;
+    established = true;
+    __syncthreads();
+    if (threadIdx.x == 0) s_ncand = s_nkept;
+    __syncthreads();
+  };
+
+  for (int r = r0; r < r1; ++r) {
+    const int jr = r - r0;
+    // items of this range: slice t contributes ceil(n_t / 32) items of 32 postings (one per lane)
+    if (warp == 0) {
+      unsigned int c = 0u;
+      if (lane < ntok) c = (s_off[lane * ostride + jr + 1] - s_off[lane * ostride + jr] + 31u) >> 5;
+      unsigned int incl = c;
+#pragma unroll
+      for (int off = 1; off < 32; off <<= 1) {
+        const unsigned int o = __shfl_up_sync(0xFFFFFFFFu, incl, off);
+        if (lane >= off) incl += o;
+      }
+      if (lane < ntok) s_pre[lane] = incl - c;
+      if (lane == ntok - 1 || (ntok == 0 && lane == 0)) s_pre[ntok] = ntok ? incl : 0u;
+    }
+    __syncthreads();
+    const unsigned int n_items = s_pre[ntok];
+    if (n_items == 0u) continue;                          // uniform; the next iteration's barrier protects s_pre
+    const uint32_t doc_base = static_cast<uint32_t>(r) * kBmRange;
+    const unsigned int cross = established ? theta : ~0u;
+    // item → token table, one THREAD per item (a warp-uniform search per item was half of the kernel's instructions)
+    for (unsigned int i = threadIdx.x; i < n_items; i += kBsThreads) {
+      int t = 0;
+      while (t + 1 < ntok && s_pre[t + 1] <= i) ++t;
+      s_itok[i] = static_cast<unsigned char>(t);
+    }
+    __syncthreads();
+
+    auto item_load = [&](unsigned int item, uint4& e, double& idfx) {
+      e = make_uint4(0xFFFFFFFFu, 0u, 0u, 0u);
+      idfx = 0.0;
+      if (item >= n_items) return;
+      const int t = s_itok[item];
+      idfx = s_idfx[t];
+      const uint32_t a = s_off[t * ostride + jr];
+      const unsigned int n = s_off[t * ostride + jr + 1] - a;
+      const unsigned int i = (item - s_pre[t]) * 32u + lane;
+      if (i < n) e = __ldg(reinterpret_cast<const uint4*>(post + s_base[t] + a + i));
+    };
+    auto item_apply = [&](const uint4& e, double idfx) {
+      if (e.x == 0xFFFFFFFFu) return;
+      const double w = __hiloint2double(static_cast<int>(e.w), static_cast<int>(e.z));
+      const unsigned int add = __double2uint_rn(__dmul_rn(idfx, w));
+      const uint32_t l = e.x - doc_base;
+      const unsigned int old = atomicAdd(&acc[l], add);
+      if (old < cross && old + add >= cross) {            // just reached theta (sums only grow): note the document once
+        const unsigned int slot = atomicAdd(&s_nrc, 1u);
+        if (slot < kBsRangeCap) s_rc[slot] = static_cast<unsigned short>(l);
+      }
+    };
+    {
+      // two loads in flight per lane, buffers alternate by name
+      constexpr unsigned int kW = kBsThreads / 32;
+      uint4 e0, e1;
+      double f0, f1;
+      unsigned int it = warp;
+      item_load(it, e0, f0);
+      while (it < n_items) {
+        item_load(it + kW, e1, f1); item_apply(e0, f0); it += kW;
+        if (it >= n_items) break;
+        item_load(it + kW, e0, f0); item_apply(e1, f1); it += kW;
+      }
+    }
+    __syncthreads();
+
+    if (established) {
+      // the noted documents now hold their final sums
+      const unsigned int nrc = s_nrc;
+      if (nrc > kBsRangeCap) {                            // uniform
+        if (threadIdx.x == 0) { status[q] = 1; fin_cnt[cbase] = 0; }
+        return;
+      }
+      if (threadIdx.x < nrc) {
+        const uint32_t l = s_rc[threadIdx.x];
+        const unsigned int slot = atomicAdd(&s_ncand, 1u);
+        if (slot < kBsCandCap) cand[slot] = make_uint2(acc[l], doc_base + l);
+      }
+      __syncthreads();
+      uint4* a4 = reinterpret_cast<uint4*>(acc);
+      for (int i = threadIdx.x; i < kBmRange / 4; i += kBsThreads) a4[i] = make_uint4(0u, 0u, 0u, 0u);
+      if (threadIdx.x == 0) s_nrc = 0u;
+    } else {
+      // theta = (k-th largest of the warps' best thread maxima) - margin: maxima of distinct threads are distinct
+      // documents, so k of them at or above it bound the k-th best exact score from below
+      unsigned int mine = 0u;
+#pragma unroll 2
+      for (int i = 0; i < kBsDocsPerThread; ++i) mine = max(mine, acc[threadIdx.x + i * kBsThreads]);
+      const int m = (k + kBsThreads / 32 - 1) / (kBsThreads / 32);        // 1 or 2
+      unsigned int* s_top = reinterpret_cast<unsigned int*>(cand_alt);
+      for (int round = 0; round < m; ++round) {
+        unsigned int wm = mine;
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) wm = max(wm, __shfl_xor_sync(0xFFFFFFFFu, wm, off));
+        const unsigned int holders = __ballot_sync(0xFFFFFFFFu, mine == wm);
+        if (lane == __ffs(holders) - 1) { s_top[warp * m + round] = wm; mine = 0u; }
+      }
+      if (threadIdx.x == 0) s_tw = 0u;
+      __syncthreads();
+      const int nv = (kBsThreads / 32) * m;                                // 16 or 32
+      if (static_cast<int>(threadIdx.x) < nv) {
+        const unsigned int me = s_top[threadIdx.x];
+        int r2 = 0;
+        for (int jj = 0; jj < nv; ++jj) {
+          const unsigned int o = s_top[jj];
+          r2 += (o > me || (o == me && jj < static_cast<int>(threadIdx.x))) ? 1 : 0;
+        }
+        if (r2 == k - 1) s_tw = me;                        // 0 when fewer than k threads saw a document
+      }
+      __syncthreads();
+      const unsigned int tb = s_tw;
+      if (tb != 0u) { theta = tb > kFxMargin ? tb - kFxMargin : 1u; established = true; }
+      // scan + clear: collect the documents at or above theta
+#pragma unroll 2
+      for (int i = 0; i < kBsDocsPerThread; ++i) {
+        const int l = threadIdx.x + i * kBsThreads;
+        const unsigned int sc = acc[l];
+        if (sc != 0u) {
+          acc[l] = 0u;
+          if (sc >= theta) {
+            const unsigned int slot = atomicAdd(&s_ncand, 1u);
+            if (slot < kBsCandCap) cand[slot] = make_uint2(sc, doc_base + l);
+          }
+        }
+      }
+    }
+    __syncthreads();
+    if (s_ncand > kBsCandCap) {                           // uniform: mass ties → the general kernel re-scores the query
+      if (threadIdx.x == 0) { status[q] = 1; fin_cnt[cbase] = 0; }
+      return;
+    }
+    if (s_ncand >= kBsCompactAt) compact();
+  }
+  __syncthreads();
+  compact();
+  const unsigned int n = s_ncand;
+  if (n > static_cast<unsigned int>(kFxFinalCap)) {
+    if (threadIdx.x == 0) { status[q] = 1; fin_cnt[cbase] = 0; }
+    return;
+  }
+  if (threadIdx.x < n) fin[cbase * kFxFinalCap + threadIdx.x] = cand[threadIdx.x];
+  if (threadIdx.x == 0) fin_cnt[cbase] = static_cast<int>(n);
+}
+
+// K7'': one CTA per query bm25_fx_kernel finished (see the header above).
+__global__ void __launch_bounds__(kBmThreads)
+bm25_fx_finish_kernel(const uint2* __restrict__ fin, const int* __restrict__ fin_cnt, int ng, int* __restrict__ status,
+                      const int64_t* __restrict__ indptr, const Post16* __restrict__ post,
+                      const uint32_t* __restrict__ roff, int nr, const int32_t* __restrict__ tok_indptr,
+                      const int32_t* __restrict__ term_rows, const double* __restrict__ tok_idf, int q0, int k,
+                      double* __restrict__ out_score, int* __restrict__ out_doc, int* __restrict__ out_count) {
+  __shared__ uint2 s_c[kBsMaxGroups * kFxFinalCap];       // 12 KB: the groups' candidates {sum, doc}
+  __shared__ double s_w[kFxRescoreCap][kBsMaxTok];        // 12 KB: weight of (document, token), 0 = not in the list
+  __shared__ uint32_t s_doc[kFxRescoreCap];
+  __shared__ Key128 s_key[kFxRescoreCap];
+  __shared__ unsigned int s_n, s_m;
+  const int q = q0 + blockIdx.x;
+  if (status[q] != 0) return;                             // the general path owns this query
+  const int t0 = tok_indptr[q], ntok = tok_indptr[q + 1] - t0;
+  if (threadIdx.x == 0) { s_n = 0u; s_m = 0u; }
+  __syncthreads();
+  for (int g = 0; g < ng; ++g) {
+    const int64_t cb = static_cast<int64_t>(q) * ng + g;
+    const int c = fin_cnt[cb];
+    if (static_cast<int>(threadIdx.x) < c) s_c[atomicAdd(&s_n, 1u)] = fin[cb * kFxFinalCap + threadIdx.x];
+  }
+  __syncthreads();
+  const unsigned int n = s_n;
+  // documents that fewer than k others beat beyond the margin: the exact top-k is among them
+  for (unsigned int e = threadIdx.x; e < n; e += blockDim.x) {
+    const uint2 me = s_c[e];
+    const unsigned int bar = me.x + kFxMargin;
+    unsigned int greater = 0u;
+    for (unsigned int j = 0; j < n; ++j) greater += s_c[j].x > bar ? 1u : 0u;
+    if (greater < static_cast<unsigned int>(k)) {
+      const unsigned int slot = atomicAdd(&s_m, 1u);
+      if (slot < static_cast<unsigned int>(kFxRescoreCap)) s_doc[slot] = me.y;
+    }
+  }
+  __syncthreads();
+  if (s_m > static_cast<unsigned int>(kFxRescoreCap)) {   // a near-tie group at the k-th score larger than the cap:
+    if (threadIdx.x == 0) status[q] = 1;                  // the general kernels run after this one and pick the query up
+    return;
+  }
+  const unsigned int m = s_m;
+  // exact re-score, step 1: the posting of every (document, token) pair
+  for (unsigned int pidx = threadIdx.x; pidx < m * static_cast<unsigned int>(ntok); pidx += blockDim.x) {
+    const unsigned int d = pidx / ntok;
+    const int t = static_cast<int>(pidx - d * ntok);
+    const uint32_t doc = s_doc[d];
+    const int term = term_rows[t0 + t];
+    double w = 0.0;
+    if (term >= 0) {
+      const uint32_t* ro = roff + static_cast<int64_t>(term) * (nr + 1) + static_cast<int>(doc / kBmRange);
+      const uint32_t a = ro[0], b = ro[1];
+      const Post16* p = post + indptr[term];
+      uint32_t lo = a, hi = b;
+      while (lo < hi) {
+        const uint32_t mid = (lo + hi) >> 1;
+        if (__ldg(&p[mid].doc) < doc) lo = mid + 1; else hi = mid;
+      }
+      if (lo < b && __ldg(&p[lo].doc) == doc) w = __ldg(&p[lo].w);
+    }
+    s_w[d][t] = w;
+  }
+  __syncthreads();
+  // step 2: the reference's sum in query-token order (keyword_search.py:241-244) and the tie key
+  if (threadIdx.x < m) {
+    double score = 0.0;
+    unsigned int first = 0xFFu;
+    for (int t = 0; t < ntok; ++t) {
+      const double w = s_w[threadIdx.x][t];
+      if (w != 0.0) {
+        score = __dadd_rn(score, __dmul_rn(tok_idf[t0 + t], w));
+        if (first == 0xFFu) first = static_cast<unsigned int>(t);
+      }
+    }
+    Key128 kk;
+    kk.hi = ~f64_orderable(static_cast<uint64_t>(__double_as_longlong(score)));
+    kk.lo = (static_cast<unsigned long long>(first) << 32) | s_doc[threadIdx.x];
+    s_key[threadIdx.x] = kk;
+  }
+  __syncthreads();
+  if (threadIdx.x < m) {
+    const Key128 me = s_key[threadIdx.x];
+    int rank = 0;
+    for (unsigned int j = 0; j < m; ++j) rank += key_less(s_key[j], me) ? 1 : 0;
+    if (rank < k) {
+      const int64_t o = static_cast<int64_t>(q) * k + rank;
+      const uint64_t ob = ~me.hi;
+      const uint64_t bits = (ob & 0x8000000000000000ull) ? (ob & 0x7FFFFFFFFFFFFFFFull) : ~ob;
+      out_score[o] = __longlong_as_double(static_cast<long long>(bits));
+      out_doc[o] = static_cast<int>(static_cast<uint32_t>(me.lo));
+    }
+  }
+  const int emitted = static_cast<int>(m) < k ? static_cast<int>(m) : k;
+  if (threadIdx.x == 0) out_count[q] = emitted;
+  for (int i = emitted + threadIdx.x; i < k; i += blockDim.x) {
+    out_score[static_cast<int64_t>(q) * k + i] = 0.0;
+    out_doc[static_cast<int64_t>(q) * k + i] = -1;
+  }
+}
+
 // K7 (query part): k-way merge of the per-range sorted candidate lists.
 // One CTA per query; thread j owns ranges j, j+blockDim, ...
 __global__ void __launch_bounds__(kBmThreads)
@@ -667,7 +1018,10 @@ bm25_merge_kernel(const unsigned long long* __restrict__ cand_hi, const unsigned
   __shared__ int s_w[kBmThreads / 32];
   const int q = q0 + blockIdx.x;
   // the streaming kernel's per-group lists unless it flagged the query (then the general kernel's per-range lists)
-  if (use_alt && use_alt[q] == 0) { cand_hi = alt_hi; cand_lo = alt_lo; cand_cnt = alt_cnt; nr = alt_nr; }
+  if (use_alt && use_alt[q] == 0) {
+    if (!alt_hi) return;                                  // bm25_fx_finish_kernel already wrote this query's results
+    cand_hi = alt_hi; cand_lo = alt_lo; cand_cnt = alt_cnt; nr = alt_nr;
+  }
   // per-thread heads (a thread may own several ranges when nr > blockDim; it keeps
   // the best head among them and re-scans its ranges after winning)
   constexpr int kMaxOwn = 8;                 // nr <= 2048 ranges = 16.7 M docs

@@ -331,6 +331,30 @@ knn_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant_
 // than K' valid rows, zero or non-finite query norm).  `normalized`: the survivor values are cos~
 // (knn_tc3, unit-norm operands) instead of dot~/|a| (knn_tc / knn_tc2), so the band is not scaled by |q|.
 // smem: cap * 8 bytes (pairs) — reused for the exact keys.
+// 256 threads, 256 histogram bins (one per thread): the digit d with  sum(hist[0..d-1]) < need <= sum(hist[0..d]).
+// The thread that owns d writes *out_digit = d and *out_before = sum(hist[0..d-1]); *out_digit stays 256 when
+// the histogram holds fewer than `need` entries.  s_warp: 8 words of scratch.  Ends with a barrier.
+__device__ __forceinline__ void block_pick_digit(const unsigned int* s_hist, unsigned int need, unsigned int* s_warp,
+                                                 unsigned int* out_digit, unsigned int* out_before) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const unsigned int c = s_hist[threadIdx.x];
+  unsigned int incl = c;
+#pragma unroll
+  for (int off = 1; off < 32; off <<= 1) {
+    const unsigned int o = __shfl_up_sync(0xFFFFFFFFu, incl, off);
+    if (lane >= off) incl += o;
+  }
+  if (lane == 31) s_warp[warp] = incl;
+  if (threadIdx.x == 0) *out_digit = 256u;
+  __syncthreads();
+  unsigned int base = 0u;
+#pragma unroll
+  for (int w = 0; w < 8; ++w) base += (w < warp) ? s_warp[w] : 0u;
+  incl += base;
+  if (incl >= need && incl - c < need) { *out_digit = threadIdx.x; *out_before = incl - c; }
+  __syncthreads();
+}
+
 constexpr int kTcRefineCap = 2048;                         // rows re-scored exactly per query at most
 
 template <bool FMA>
@@ -344,7 +368,8 @@ knn_refine_kernel(const float* __restrict__ emb, const float* __restrict__ amag,
   uint2* pairs = reinterpret_cast<uint2*>(smem_raw);                       // [cap]
   __shared__ float s_q[kScanD];
   __shared__ unsigned int s_hist[256];
-  __shared__ unsigned int s_prefix, s_need, s_m;
+  __shared__ unsigned int s_prefix, s_need, s_m, s_digit, s_before;
+  __shared__ unsigned int s_warp[8];
   __shared__ uint32_t s_rows[kTcRefineCap];
   const int qi = blockIdx.x;
   const unsigned int cnt = cand_count[qi];
@@ -355,13 +380,9 @@ knn_refine_kernel(const float* __restrict__ emb, const float* __restrict__ amag,
     return;
   }
   const int n = static_cast<int>(cnt);
-  // survivors that are empty vec0 slots (knn_tc3 does not look at |a|^2 in its epilogue) get value -inf:
-  // they can neither be the K'-th largest (unless fewer than K' valid rows survived → exact scan) nor pass the cut
-  for (int i = threadIdx.x; i < n; i += blockDim.x) {
-    uint2 pr = cand_pairs[static_cast<int64_t>(qi) * cap + i];
-    if (!(__ldg(amag + pr.x) > 0.0f)) pr.y = 0xFF800000u;
-    pairs[i] = pr;
-  }
+  // (knn_tc3 never emits an empty slot or a zero row: its thresholds are positive and those rows read cos~ = 0;
+  //  knn_tc / knn_tc2 check |a|^2 in their epilogues)
+  for (int i = threadIdx.x; i < n; i += blockDim.x) pairs[i] = cand_pairs[static_cast<int64_t>(qi) * cap + i];
   for (int i = threadIdx.x; i < kScanD; i += blockDim.x) s_q[i] = q[static_cast<int64_t>(qi) * kScanD + i];
   if (threadIdx.x == 0) { s_prefix = 0u; s_need = static_cast<unsigned int>(kprime < n ? kprime : n); s_m = 0u; }
   __syncthreads();
@@ -380,15 +401,10 @@ knn_refine_kernel(const float* __restrict__ emb, const float* __restrict__ amag,
         if ((key & resolved_mask) == prefix) atomicAdd(&s_hist[(key >> shift) & 0xFFu], 1u);
       }
       __syncthreads();
+      block_pick_digit(s_hist, s_need, s_warp, &s_digit, &s_before);     // a thread-0 loop over the bins cost 10 % of the kernel
       if (threadIdx.x == 0) {
-        unsigned int need = s_need, run = 0u;
-        int d = 0;
-        for (; d < 256; ++d) {
-          if (run + s_hist[d] >= need) break;
-          run += s_hist[d];
-        }
-        s_prefix = prefix | (static_cast<uint32_t>(d) << shift);
-        s_need = need - run;
+        s_prefix = prefix | ((s_digit & 0xFFu) << shift);
+        s_need = s_need - s_before;
       }
       resolved_mask |= 0xFFu << shift;
       __syncthreads();

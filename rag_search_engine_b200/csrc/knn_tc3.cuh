@@ -313,7 +313,8 @@ tc3_probe_threshold_kernel(const uint32_t* __restrict__ dist, int64_t ld, int nq
                            const double* __restrict__ sb, float* __restrict__ thr) {
   __shared__ uint32_t s_key[kT3SelMax];
   __shared__ unsigned int s_hist[256];
-  __shared__ unsigned int s_prefix, s_need, s_fail;
+  __shared__ unsigned int s_prefix, s_need, s_fail, s_digit, s_before;
+  __shared__ unsigned int s_warp[8];
   const int q = blockIdx.x;
   const float inf = __int_as_float(0x7F800000);
   if (q >= nq || !(sb[q] > 0.0 && sb[q] < 1e300)) {
@@ -335,15 +336,10 @@ tc3_probe_threshold_kernel(const uint32_t* __restrict__ dist, int64_t ld, int nq
       if ((key & resolved) == prefix) atomicAdd(&s_hist[(key >> shift) & 0xFFu], 1u);
     }
     __syncthreads();
+    block_pick_digit(s_hist, s_need, s_warp, &s_digit, &s_before);
     if (threadIdx.x == 0) {
-      unsigned int need = s_need, run = 0u;
-      int d = 0;
-      for (; d < 256; ++d) {
-        if (run + s_hist[d] >= need) break;
-        run += s_hist[d];
-      }
-      s_prefix = prefix | (static_cast<uint32_t>(d & 0xFF) << shift);
-      s_need = need - run;
+      s_prefix = prefix | ((s_digit & 0xFFu) << shift);
+      s_need = s_need - s_before;
     }
     resolved |= 0xFFu << shift;
     __syncthreads();

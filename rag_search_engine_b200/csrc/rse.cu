@@ -93,6 +93,7 @@ struct rse_index {
   Post16* post16 = nullptr;        // {doc, tf, w}: postings with the (k1, b)-dependent weight precomputed (bm25_stream_kernel)
   double w_k1 = NAN, w_b = NAN;
   DevBuf b_shi, b_slo, b_scnt, b_status, b_flagged;
+  int bm25_mode = 0;               // 0 = fixed-point streaming kernel (default), 1 = exact-order streaming kernel, 2 = general kernel only
   std::vector<int64_t> df_host;
   DevBuf b_tokptr, b_terms, b_idf, b_chi, b_clo, b_ccnt, b_score, b_doc, b_count;
 
@@ -804,6 +805,13 @@ int rse_set_tc_mode(rse_index* h, int32_t mode) {
   return RSE_OK;
 }
 
+int rse_set_bm25_mode(rse_index* h, int32_t mode) {
+  if (!h) return RSE_ERR_INVALID;
+  if (mode < 0 || mode > 2) return fail(h, RSE_ERR_INVALID, "rse_set_bm25_mode: mode must be 0..2");
+  h->bm25_mode = mode;
+  return RSE_OK;
+}
+
 int rse_set_timing(rse_index* h, int32_t enabled) {
   if (!h) return RSE_ERR_INVALID;
   h->timing = enabled != 0;
@@ -1049,6 +1057,7 @@ int rse_load_bm25(rse_index* h, const int64_t* indptr, const uint32_t* doc_idx, 
   if (!attr) {
     CK(cudaFuncSetAttribute(bm25_score_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kBmRange * 9));
     CK(cudaFuncSetAttribute(bm25_stream_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bs_smem_bytes()));
+    CK(cudaFuncSetAttribute(bm25_fx_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, fx_smem_bytes(kBsMaxRpg)));
     attr = true;
   }
   return RSE_OK;
@@ -1115,7 +1124,17 @@ int bm25_run(rse_index* h, int nq, int k, double k1, double b) {
   const double k1p1 = k1 + 1.0;
 
   // streaming path (bm25_stream_kernel): k <= 32; needs the weighted postings of this (k1, b)
-  const bool stream = k <= 32 && h->n_postings > 0;
+  const bool stream = k <= 32 && h->n_postings > 0 && h->bm25_mode != 2;
+  // fixed-point sums must stay below 2^31: idf <= log(N + 2), w < k1 + 1, <= 16 tokens; the scale is the largest
+  // power of two that allows (2^21 for the default k1), and the path needs at least 2^12
+  double fx_scale = 0.0;
+  if (stream && h->bm25_mode == 0 && k1 >= 0.0) {
+    const double max_sum = (k1 + 1.0) * std::log(static_cast<double>(h->n_movies) + 2.0) * 16.0 + 1.0;
+    int e = 0;
+    std::frexp(max_sum, &e);                               // max_sum < 2^e
+    if (31 - e >= 12) fx_scale = std::ldexp(1.0, 31 - e);
+  }
+  const bool fx = fx_scale > 0.0;
   int ng = 1, rpg = h->nr;
   if (stream) {
     if (!(h->w_k1 == k1 && h->w_b == b)) {
@@ -1131,19 +1150,21 @@ int bm25_run(rse_index* h, int nq, int k, double k1, double b) {
     // the kernel ran at 30 % occupancy)
     {
       const int nqc = std::min(nq, chunk);
-      const double conc = 3.0 * h->sm_count;
+      const double conc = (fx ? 4.0 : 3.0) * h->sm_count;   // resident CTAs: the fixed-point kernel fits 4 per SM
       const int g_lo = std::max(1, static_cast<int>((4.0 * conc + nqc - 1) / nqc));
       double best_eff = -1.0;
       for (int cand = g_lo; cand <= g_lo + 10; ++cand) {
         int c_rpg = (h->nr + std::min(cand, h->nr) - 1) / std::min(cand, h->nr);
         if (c_rpg > kBsMaxRpg) c_rpg = kBsMaxRpg;
         const int c_ng = (h->nr + c_rpg - 1) / c_rpg;
+        if (fx && c_ng > kBsMaxGroups && best_eff >= 0.0) continue;
         const double waves = nqc * static_cast<double>(c_ng) / conc;
         const double eff = waves / std::ceil(waves);
         if (eff > best_eff + 1e-9) { best_eff = eff; ng = c_ng; rpg = c_rpg; }
       }
     }
-    const size_t per_qs = static_cast<size_t>(ng) * k;
+    if (fx && ng > kBsMaxGroups) { rpg = (h->nr + kBsMaxGroups - 1) / kBsMaxGroups; ng = (h->nr + rpg - 1) / rpg; }
+    const size_t per_qs = static_cast<size_t>(ng) * std::max(k, 2 * kFxFinalCap);
     ENSURE(h->b_shi, sizeof(unsigned long long) * per_qs * std::min(nq, chunk));
     ENSURE(h->b_slo, sizeof(unsigned long long) * per_qs * std::min(nq, chunk));
     ENSURE(h->b_scnt, sizeof(int) * static_cast<size_t>(ng) * std::min(nq, chunk));
@@ -1161,8 +1182,23 @@ int bm25_run(rse_index* h, int nq, int k, double k1, double b) {
     unsigned long long* slo = nullptr;
     int* scnt = nullptr;
     int* status = nullptr;
-    if (stream) {
-      const size_t per_qs = static_cast<size_t>(ng) * k;
+    if (fx) {
+      uint2* fin = static_cast<uint2*>(h->b_shi.p) - static_cast<int64_t>(q0) * ng * kFxFinalCap;
+      int* fcnt = static_cast<int*>(h->b_scnt.p) - static_cast<int64_t>(q0) * ng;
+      status = static_cast<int*>(h->b_status.p);
+      dim3 sgrid(ng, nc);
+      bm25_fx_kernel<<<sgrid, kBsThreads, fx_smem_bytes(rpg), h->stream>>>(
+          h->indptr, h->post16, h->roff, h->nr, static_cast<const int32_t*>(h->b_tokptr.p),
+          static_cast<const int32_t*>(h->b_terms.p), static_cast<const double*>(h->b_idf.p), fx_scale, q0, k, rpg, ng, fin,
+          fcnt, status);
+      LAUNCHED(h);
+      bm25_fx_finish_kernel<<<nc, kBmThreads, 0, h->stream>>>(
+          fin, fcnt, ng, status, h->indptr, h->post16, h->roff, h->nr, static_cast<const int32_t*>(h->b_tokptr.p),
+          static_cast<const int32_t*>(h->b_terms.p), static_cast<const double*>(h->b_idf.p), q0, k,
+          static_cast<double*>(h->b_score.p), static_cast<int*>(h->b_doc.p), static_cast<int*>(h->b_count.p));
+      LAUNCHED(h);
+    } else if (stream) {
+      const size_t per_qs = static_cast<size_t>(ng) * std::max(k, 2 * kFxFinalCap);
       shi = static_cast<unsigned long long*>(h->b_shi.p) - static_cast<int64_t>(q0) * per_qs;
       slo = static_cast<unsigned long long*>(h->b_slo.p) - static_cast<int64_t>(q0) * per_qs;
       scnt = static_cast<int*>(h->b_scnt.p) - static_cast<int64_t>(q0) * ng;

@@ -206,7 +206,8 @@ def test_bm25_large_synthetic_matches_c_oracle(fresh_index):
         assert (sc.view(np.uint64) == osc.view(np.uint64)).all()
 
 
-def test_bm25_streaming_kernel_fallbacks_and_ties(fresh_index):
+@pytest.mark.parametrize("mode", [0, 1])
+def test_bm25_streaming_kernel_fallbacks_and_ties(fresh_index, mode):
     """The streaming BM25 kernel hands a query to the general kernel when it has more than 16 tokens or when
     a mass tie overflows its candidate list; small tie groups are resolved inside it (first query token whose
     postings hold the document, then doc).  Everything must equal the C oracle bit for bit."""
@@ -241,10 +242,29 @@ def test_bm25_streaming_kernel_fallbacks_and_ties(fresh_index):
     queries += [rng.integers(0, vocab, rng.integers(1, 7)).tolist() for _ in range(40)]
     tok_indptr = np.cumsum([0] + [len(q) for q in queries]).astype(np.int32)
     terms = np.array([t for q in queries for t in q], np.int32)
+    fresh_index.set_bm25_mode(mode)
     fresh_index.load_bm25(indptr, doc_idx, tf, df, dl, n_docs, avgdl)
     for k in (10, 3, 32):
         sc, dc, cnt = fresh_index.bm25(tok_indptr, terms, k)
         osc, odc, ocnt = oracle.bm25_batch(indptr, doc_idx, tf, df, dl, n_docs, avgdl, tok_indptr, terms, k)
+        assert cnt.tolist() == ocnt.tolist()
+        assert (dc == odc).all()
+        assert (sc.view(np.uint64) == osc.view(np.uint64)).all()
+
+
+@pytest.mark.parametrize("mode", [0, 1, 2])
+def test_bm25_modes_agree_with_oracle(fresh_index, mode):
+    """rse_set_bm25_mode: fixed-point streaming (0), exact-order streaming (1) and the general kernel (2) must all
+    return the oracle's documents, order and scores bit for bit."""
+    from rag_search_engine_b200 import synth
+    bm = synth.synth_bm25(60_000, 8_000, seed=21, mean_len=50, sd_len=20)       # 9 doc ranges
+    tok_indptr, terms = synth.synth_token_queries(bm, 400, seed=22)
+    fresh_index.set_bm25_mode(mode)
+    fresh_index.load_bm25(bm.indptr, bm.doc_idx, bm.tf, bm.df, bm.dl, bm.n_movies, bm.avgdl)
+    for k, k1, b in [(10, 1.5, 0.75), (32, 1.2, 0.5), (5, 3.0, 1.0)]:
+        sc, dc, cnt = fresh_index.bm25(tok_indptr, terms, k, k1, b)
+        osc, odc, ocnt = oracle.bm25_batch(bm.indptr, bm.doc_idx, bm.tf, bm.df, bm.dl, bm.n_movies, bm.avgdl,
+                                           tok_indptr, terms, k, k1, b)
         assert cnt.tolist() == ocnt.tolist()
         assert (dc == odc).all()
         assert (sc.view(np.uint64) == osc.view(np.uint64)).all()
