@@ -56,6 +56,17 @@ struct rse_index {
   bool tmap_q_ok = false;
   CUtensorMap tmap_b2{};           // [n_rows][384] f32, box {32, 64}: the half-tile the TMEM-resident kernel loads
   bool tmap_b2_ok = false;
+  // pending tensor-core batch (knn_local_begin / knn_local_finish)
+  bool knn_pending = false;
+  const float* pend_q = nullptr;
+  int pend_nq = 0, pend_kprime = 0;
+  long long* pend_cand = nullptr;
+  char* pin_stage = nullptr;       // pinned staging for the token / idf upload of a hybrid or BM25 batch
+  size_t pin_stage_bytes = 0;
+  int* pin_status = nullptr;       // pinned host copy of the per-query overflow flags
+  size_t pin_status_n = 0;
+  cudaEvent_t ev_status = nullptr;
+  cudaEvent_t ev_stage = nullptr;  // the uploads out of pin_stage have completed
   int tc_filter_kind = 2;          // 2 = knn_tc3_kernel (fp16 normalised shadow, queries resident in shared memory; default),
                                    // 0 = knn_tc_kernel<1> (TF32, queries streamed), 1 = knn_tc2_filter_kernel (TF32, queries in TMEM)
   DevBuf tc_q, tc_thr, tc_isb, tc_rows, tc_cnt, tc_keys, tc_status;
@@ -611,8 +622,12 @@ int knn_tc_block(rse_index* h, const float* q_dev, const double* sb, int nqb, in
   return knn_tc_refine(h, q_dev, sb, nqb, kprime, cand_dev, status_dev, 0);
 }
 
-// Local top-kprime for nq device-resident queries → packed candidates (device).
-int knn_local(rse_index* h, const float* q_dev, int nq, int kprime, long long* cand_dev) {
+// Local top-kprime for nq device-resident queries → packed candidates (device), in two halves: _begin enqueues
+// everything and, on the tensor-core path, an asynchronous read-back of the per-query overflow flags; _finish
+// waits for that read-back only (an event, not the stream) and re-runs flagged queries through the exact scan.
+// The hybrid step enqueues its BM25 kernels between the two, so the device never idles on the host round trip.
+int knn_local_begin(rse_index* h, const float* q_dev, int nq, int kprime, long long* cand_dev) {
+  h->knn_pending = false;
   if (!h->emb) return fail(h, RSE_ERR_STATE, "rse_knn: no embeddings loaded");
   if (nq <= 0) return RSE_OK;
   if (kprime < 1 || kprime > RSE_MAX_KPRIME)
@@ -647,9 +662,29 @@ int knn_local(rse_index* h, const float* q_dev, int nq, int kprime, long long* c
     if (rc != RSE_OK) return rc;
   }
   h->stats.tc_queries += nq;
-  std::vector<int> st(nq);
-  CK(cudaMemcpyAsync(st.data(), status, sizeof(int) * nq, cudaMemcpyDeviceToHost, h->stream));
-  CK(cudaStreamSynchronize(h->stream));
+  if (h->pin_status_n < static_cast<size_t>(nq)) {
+    if (h->pin_status) CK(cudaFreeHost(h->pin_status));
+    h->pin_status = nullptr; h->pin_status_n = 0;
+    CK(cudaMallocHost(reinterpret_cast<void**>(&h->pin_status), sizeof(int) * (static_cast<size_t>(nq) + 256)));
+    h->pin_status_n = static_cast<size_t>(nq) + 256;
+  }
+  if (!h->ev_status) CK(cudaEventCreateWithFlags(&h->ev_status, cudaEventDisableTiming));
+  CK(cudaMemcpyAsync(h->pin_status, status, sizeof(int) * nq, cudaMemcpyDeviceToHost, h->stream));
+  CK(cudaEventRecord(h->ev_status, h->stream));
+  h->knn_pending = true;
+  h->pend_q = q_dev; h->pend_nq = nq; h->pend_kprime = kprime; h->pend_cand = cand_dev;
+  return RSE_OK;
+}
+
+int knn_local_finish(rse_index* h) {
+  if (!h->knn_pending) return RSE_OK;
+  h->knn_pending = false;
+  CK(cudaEventSynchronize(h->ev_status));
+  const float* q_dev = h->pend_q;
+  const int nq = h->pend_nq, kprime = h->pend_kprime;
+  long long* cand_dev = h->pend_cand;
+  const double* sb = static_cast<const double*>(h->sb.p);
+  const int* st = h->pin_status;
   for (int q = 0; q < nq;) {
     if (!st[q]) { ++q; continue; }
     int e = q;
@@ -661,6 +696,12 @@ int knn_local(rse_index* h, const float* q_dev, int nq, int kprime, long long* c
     q = e;
   }
   return RSE_OK;
+}
+
+int knn_local(rse_index* h, const float* q_dev, int nq, int kprime, long long* cand_dev) {
+  int rc = knn_local_begin(h, q_dev, nq, kprime, cand_dev);
+  if (rc != RSE_OK) return rc;
+  return knn_local_finish(h);
 }
 
 int aggregate(rse_index* h, const long long* cand, int nq, int k, int kprime, float* o_dist, long long* o_rowid,
@@ -759,6 +800,10 @@ void rse_destroy(rse_index* h) {
                     &h->tc_rows, &h->tc_cnt, &h->tc_keys, &h->tc_status, &h->tc_q16, &h->b_shi, &h->b_slo, &h->b_scnt,
                     &h->b_status, &h->b_flagged})
     free_buf(*b);
+  if (h->pin_status) cudaFreeHost(h->pin_status);
+  if (h->pin_stage) cudaFreeHost(h->pin_stage);
+  if (h->ev_status) cudaEventDestroy(h->ev_status);
+  if (h->ev_stage) cudaEventDestroy(h->ev_stage);
   free_ptr(h->doc_ids);
   free_ptr(h->movie_ids);
   for (auto& ev : h->ev) if (ev) cudaEventDestroy(ev);
@@ -1070,8 +1115,26 @@ int bm25_stage(rse_index* h, const int32_t* tok_indptr, const int32_t* term_rows
   if (!h->indptr) return fail(h, RSE_ERR_STATE, "rse_bm25: no BM25 index loaded");
   const int64_t ntok = tok_indptr[nq];
   if (tok_indptr[0] != 0 || ntok < 0) return fail(h, RSE_ERR_INVALID, "rse_bm25: bad tok_indptr");
-  std::vector<double> idf(static_cast<size_t>(std::max<int64_t>(ntok, 1)), 0.0);
-  std::vector<int32_t> terms(static_cast<size_t>(std::max<int64_t>(ntok, 1)), -1);
+  // The token table goes through a pinned staging buffer owned by the handle, so the three uploads are truly
+  // asynchronous (a pageable source makes cudaMemcpyAsync synchronise the stream first).  Every entry point that
+  // stages ends in a stream synchronisation before it returns (fetch / result copy), so the buffer is free again
+  // by the next call; a stage-only caller (rse_hybrid_stage) is covered by the synchronisation below.
+  const size_t nt = static_cast<size_t>(std::max<int64_t>(ntok, 1));
+  const size_t bytes_idf = sizeof(double) * nt, bytes_terms = sizeof(int32_t) * nt, bytes_ptr = sizeof(int32_t) * (nq + 1);
+  const size_t need = bytes_idf + ((bytes_terms + 7) & ~size_t(7)) + bytes_ptr;
+  if (!h->ev_stage) CK(cudaEventCreateWithFlags(&h->ev_stage, cudaEventDisableTiming));
+  else CK(cudaEventSynchronize(h->ev_stage));               // the previous batch's uploads are out of the buffer
+  if (h->pin_stage_bytes < need) {
+    CK(cudaStreamSynchronize(h->stream));
+    if (h->pin_stage) CK(cudaFreeHost(h->pin_stage));
+    h->pin_stage = nullptr; h->pin_stage_bytes = 0;
+    CK(cudaMallocHost(reinterpret_cast<void**>(&h->pin_stage), need + need / 2 + 4096));
+    h->pin_stage_bytes = need + need / 2 + 4096;
+  }
+  double* idf = reinterpret_cast<double*>(h->pin_stage);
+  int32_t* terms = reinterpret_cast<int32_t*>(h->pin_stage + bytes_idf);
+  int32_t* ptr = reinterpret_cast<int32_t*>(h->pin_stage + bytes_idf + ((bytes_terms + 7) & ~size_t(7)));
+  for (size_t i = 0; i < nt; ++i) { idf[i] = 0.0; terms[i] = -1; }
   const bool dead = (h->n_docs == 0) || !(h->avgdl != 0.0);   // avgdl None/0 → [] (:199-200)
   for (int q = 0; q < nq; ++q) {
     const int n = tok_indptr[q + 1] - tok_indptr[q];
@@ -1088,16 +1151,16 @@ int bm25_stage(rse_index* h, const int32_t* tok_indptr, const int32_t* term_rows
       idf[t] = std::log((N + 0.5) / (static_cast<double>(df) + 0.5) + 1.0);
     }
   }
+  std::memcpy(ptr, tok_indptr, bytes_ptr);
   ENSURE(h->b_tokptr, sizeof(int32_t) * (nq + 1));
   ENSURE(h->b_terms, sizeof(int32_t) * std::max<int64_t>(ntok, 1));
   ENSURE(h->b_idf, sizeof(double) * std::max<int64_t>(ntok, 1));
-  // pageable staging vectors die at return → synchronous copies here
-  CK(cudaMemcpyAsync(h->b_tokptr.p, tok_indptr, sizeof(int32_t) * (nq + 1), cudaMemcpyHostToDevice, h->stream));
+  CK(cudaMemcpyAsync(h->b_tokptr.p, ptr, bytes_ptr, cudaMemcpyHostToDevice, h->stream));
   if (ntok > 0) {
-    CK(cudaMemcpyAsync(h->b_terms.p, terms.data(), sizeof(int32_t) * ntok, cudaMemcpyHostToDevice, h->stream));
-    CK(cudaMemcpyAsync(h->b_idf.p, idf.data(), sizeof(double) * ntok, cudaMemcpyHostToDevice, h->stream));
+    CK(cudaMemcpyAsync(h->b_terms.p, terms, sizeof(int32_t) * ntok, cudaMemcpyHostToDevice, h->stream));
+    CK(cudaMemcpyAsync(h->b_idf.p, idf, sizeof(double) * ntok, cudaMemcpyHostToDevice, h->stream));
   }
-  CK(cudaStreamSynchronize(h->stream));
+  CK(cudaEventRecord(h->ev_stage, h->stream));
   return RSE_OK;
 }
 
@@ -1389,7 +1452,7 @@ int rse_hybrid_stage(rse_index* h, int32_t nq, const float* q_host, const int32_
   rc = upload_queries(h, q_host, nq);
   if (rc != RSE_OK) return rc;
   h->staged_nq = nq;
-  return RSE_OK;
+  return RSE_OK;                      // asynchronous: rse_hybrid_run / _fetch (or rse_synchronize) order behind it
 }
 
 namespace {
@@ -1407,10 +1470,7 @@ int hybrid_run_impl(rse_index* h, int mode, double param, int tie_mode, int limi
   CK(cudaSetDevice(h->device));
   const int kprime = std::max(limit * knn_multiplier, limit);   // semantic_search.py:251
   if (kprime > RSE_MAX_KPRIME) return fail(h, RSE_ERR_UNSUPPORTED, "rse_hybrid: limit*knn_multiplier exceeds 4096");
-  // BM25 (k = limit, hybrid_search.py:70)
-  int rc = bm25_run(h, nq, limit, k1, b);
-  if (rc != RSE_OK) return rc;
-  // KNN + aggregation (k = limit, hybrid_search.py:88)
+  int rc = RSE_OK;
   const size_t n = static_cast<size_t>(nq) * limit;
   ENSURE(h->cand, sizeof(long long) * static_cast<size_t>(nq) * kprime * 3);
   ENSURE(h->o_dist, sizeof(float) * n);
@@ -1423,11 +1483,20 @@ int hybrid_run_impl(rse_index* h, int mode, double param, int tie_mode, int limi
     if (smem > 200 * 1024)
       return fail(h, RSE_ERR_UNSUPPORTED, "rse_hybrid_run_merged_dev: n_lists*kprime too large for the merge kernel");
     if (smem > 48 * 1024) CK(cudaFuncSetAttribute(knn_merge_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    // BM25 (k = limit, hybrid_search.py:70), then the merge of the gathered KNN candidates
+    rc = bm25_run(h, nq, limit, k1, b);
+    if (rc != RSE_OK) return rc;
     knn_merge_kernel<<<nq, kSelThreads, smem, h->stream>>>(gathered, n_lists, nq, kprime, n2,
                                                            static_cast<long long*>(h->cand.p));
     LAUNCHED(h);
   } else {
-    rc = knn_local(h, static_cast<const float*>(h->q_dev.p), nq, kprime, static_cast<long long*>(h->cand.p));
+    // KNN (k = limit, hybrid_search.py:88) is enqueued first; BM25 (hybrid_search.py:70) goes in behind it while
+    // the tensor-core path's overflow flags travel back, so the host round trip costs the device nothing
+    rc = knn_local_begin(h, static_cast<const float*>(h->q_dev.p), nq, kprime, static_cast<long long*>(h->cand.p));
+    if (rc != RSE_OK) return rc;
+    rc = bm25_run(h, nq, limit, k1, b);
+    if (rc != RSE_OK) return rc;
+    rc = knn_local_finish(h);
     if (rc != RSE_OK) return rc;
   }
   rc = aggregate(h, static_cast<const long long*>(h->cand.p), nq, limit, kprime, static_cast<float*>(h->o_dist.p),
