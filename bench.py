@@ -481,6 +481,7 @@ def run_b200(args, rank, world, local_rank):
 
     # ---- batch-1 KNN (north_star: batch-1 kNN as a fraction of HBM peak): scan<QB=1> alone + whole call
     knn1 = None
+    knn1k = None
     if world == 1 and not args.no_knn1:
         kp = max(limit * 10, limit)
         for _ in range(3):
@@ -494,6 +495,22 @@ def run_b200(args, rank, world, local_rank):
         s1 = idx.stats(); idx.set_timing(False)
         sm1 = s1.scan_ms_total / max(1, s1.scan_launches_timed)
         knn1 = {"scan_ms": sm1, "call_ms_host_buffers": 1e3 * wall1, "launches_per_query": s1.kernel_launches / reps}
+        # configs[2]: batch-1024 semantic search (KNN top-K' + per-movie best chunk) through the host-buffer call
+        from rag_search_engine_b200 import synth as _synth
+        Q1k = _synth.synth_query_vectors(se.emb, 1024, seed=7).cpu().numpy()
+        for _ in range(2):
+            idx.knn_movies(Q1k, limit, kp)
+        idx.set_timing(True); idx.stats_reset()
+        reps = 5
+        t0 = time.perf_counter()
+        for _ in range(reps):
+            idx.knn_movies(Q1k, limit, kp)
+        wall1k = (time.perf_counter() - t0) / reps
+        s1k = idx.stats(); idx.set_timing(False)
+        f_ms = s1k.scan_ms_total / max(1, s1k.scan_launches_timed)
+        knn1k = {"call_ms_host_buffers": 1e3 * wall1k, "queries_per_s": 1024 / wall1k, "filter_pass_ms": f_ms,
+                 "filter_tflops": 2.0 * 384 * (hi - lo) * 256 / (f_ms * 1e-3) / 1e12 if f_ms > 0 else None,
+                 "tc_fallback_queries": int(s1k.tc_fallback_queries)}
 
     sharded_ok = None
     replicas_ok = None
@@ -587,7 +604,7 @@ def run_b200(args, rank, world, local_rank):
             "dtype": "f16 tensor-core filter + exact f32 re-score (f64 tail), f64 BM25/fusion", "data": "synthetic",
             "config": config_dict(args, info, world, par), "roofline": roofline, "clocks": clocks, "e2e": e2e,
             "gpu_launches": launches, "sharded_matches_single_gpu": sharded_ok, "replicas_match_single_gpu": replicas_ok,
-            "rowshard": rowshard_extra, "knn_batch1": knn1, "postings_touched_per_step": postings_touched(bm, tok_indptr, terms)}
+            "rowshard": rowshard_extra, "knn_batch1": knn1, "knn_batch1024": knn1k, "postings_touched_per_step": postings_touched(bm, tok_indptr, terms)}
 
     if world == 1 and not args.no_cpu_baseline:
         cores = os.cpu_count() or 1

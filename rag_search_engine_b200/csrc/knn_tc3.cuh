@@ -540,7 +540,7 @@ knn_tc3_kernel(const __grid_constant__ CUtensorMap tmap_rows, const __grid_const
       } else {
         const uint32_t row_base = static_cast<uint32_t>(t * kT3TileRows + col_half * 128);
         uint32_t v[128];
-        tc_ld128(taddr0, v);
+        tc_ld128(taddr0, v);                       // (one .x128 load instead of four .x32: same time, r01)
         bool pushed = false;                       // rare per lane: ≈ K'·stride + band survivors per query per pass
 #pragma unroll
         for (int c = 0; c < 4; ++c) pushed |= t3_scan32(v + 32 * c, my_thr, row_base + static_cast<uint32_t>(32 * c), sink);
