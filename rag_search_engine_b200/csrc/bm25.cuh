@@ -675,6 +675,7 @@ bm25_stream_kernel(const int64_t* __restrict__ indptr, const Post16* __restrict_
 // bit-identical to the general kernel; queries it cannot finish are flagged for it exactly like before.
 constexpr unsigned int kFxMargin = 40u;               // > 2 x (8 units of accumulated rounding + the double sum's own)
 constexpr int kFxFinalCap = 48;
+constexpr unsigned int kFxMaxItems = 3072;            // 32-posting items per range (98 k postings; beyond: general kernel)
 constexpr int kFxRescoreCap = 96;
 
 __host__ __device__ constexpr int fx_smem_bytes(int rpg) {
@@ -700,7 +701,7 @@ bm25_fx_kernel(const int64_t* __restrict__ indptr, const Post16* __restrict__ po
   __shared__ unsigned int s_ncand, s_nkept, s_nrc;
   __shared__ unsigned int s_min, s_tw;
   __shared__ unsigned short s_rc[kBsRangeCap];
-  __shared__ unsigned char s_itok[kBsMaxTok * (kBmRange / 32)];                        // token of every item of the range
+  __shared__ unsigned char s_itok[kFxMaxItems];                                        // token of every item of the range
 
   const int g = blockIdx.x;
   const int q = q0 + blockIdx.y;
@@ -782,6 +783,10 @@ bm25_fx_kernel(const int64_t* __restrict__ indptr, const Post16* __restrict__ po
     __syncthreads();
     const unsigned int n_items = s_pre[ntok];
     if (n_items == 0u) continue;                          // uniform; the next iteration's barrier protects s_pre
+    if (n_items > kFxMaxItems) {                          // uniform
+      if (threadIdx.x == 0) { status[q] = 1; fin_cnt[cbase] = 0; }
+      return;
+    }
     const uint32_t doc_base = static_cast<uint32_t>(r) * kBmRange;
     const unsigned int cross = established ? theta : ~0u;
     // item → token table, one THREAD per item (a warp-uniform search per item was half of the kernel's instructions)

@@ -28,7 +28,7 @@
 //   a register and "does any of these 32 rows survive" is a 3-input-max tree + one compare: 17
 //   instructions per 32 elements (the first version had lane = row, read the 256 thresholds from shared
 //   memory and chained 32 dependent FSETPs on one warp per scheduler: 2.0 ms per pass, issue-latency-bound).
-//   warp 0   : TMA producer — 7-stage ring of 16 KB k-blocks (128 rows x 64 halves, SWIZZLE_128B), each
+//   warp 0   : TMA producer — 4-stage ring of 16 KB k-blocks (128 rows x 64 halves, SWIZZLE_128B), each
 //              one contiguous block of the tiled shadow (tc3_shadow_kernel); the loads of BOTH CTAs
 //              complete on the leader's mbarrier (cp.async.bulk.tensor...cta_group::2)
 //   warp 1   : leader CTA only — single-thread tcgen05.mma issuer; tcgen05.commit multicast frees the
@@ -51,7 +51,12 @@ constexpr int kT3HalfRows = 128;                          // rows each CTA strea
 constexpr int kT3BK = 64;                                 // halves per k-block: one 128-byte swizzle atom
 constexpr int kT3KBlocks = kScanD / kT3BK;                // 6
 constexpr int kT3StageBytes = kT3HalfRows * kT3BK * 2;    // 16,384
-constexpr int kT3Stages = 7;                              // 112 KB of rows in flight per SM
+constexpr int kT3Stages = 4;                              // 64 KB of rows in flight per SM.  3..7 stages measure the same
+                                                          // (0.81-0.85 ms, r01): the pass is not fill-bound, and the
+                                                          // smaller footprint (178 KB, 120 registers) leaves room for ONE
+                                                          // BM25 CTA per SM to run underneath it (rse.cu, hybrid step).
+                                                          // Room for two (3 stages, 96 registers) was worse: the filter
+                                                          // slowed from 0.86 to 0.99 ms and the step from 1.28 to 1.40 ms
 constexpr int kT3ProbeTop = 8;                            // MODE 2: sample values kept per thread
 constexpr int kT3QueueCap = 128;                          // per-warp survivor queue (entries of 12 B)
 constexpr int kT3QueueFlush = 32;                         // flushed to global memory once this full
@@ -189,6 +194,35 @@ __device__ __forceinline__ bool t3_scan32(const uint32_t* v, float thr, uint32_t
     }
   }
   return true;
+}
+
+// two back-to-back 32-column loads, one wait (the register-lean variant of tc_ld128)
+__device__ __forceinline__ void tc_ld64(uint32_t taddr, uint32_t (&v)[64]) {
+#pragma unroll
+  for (int c = 0; c < 2; ++c) {
+    uint32_t* w = v + 32 * c;
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];\n"
+        : "=r"(w[0]), "=r"(w[1]), "=r"(w[2]), "=r"(w[3]), "=r"(w[4]), "=r"(w[5]), "=r"(w[6]), "=r"(w[7]), "=r"(w[8]),
+          "=r"(w[9]), "=r"(w[10]), "=r"(w[11]), "=r"(w[12]), "=r"(w[13]), "=r"(w[14]), "=r"(w[15]), "=r"(w[16]),
+          "=r"(w[17]), "=r"(w[18]), "=r"(w[19]), "=r"(w[20]), "=r"(w[21]), "=r"(w[22]), "=r"(w[23]), "=r"(w[24]),
+          "=r"(w[25]), "=r"(w[26]), "=r"(w[27]), "=r"(w[28]), "=r"(w[29]), "=r"(w[30]), "=r"(w[31])
+        : "r"(taddr + static_cast<uint32_t>(32 * c))
+        : "memory");
+  }
+#pragma unroll
+  for (int c = 0; c < 2; ++c) {
+    uint32_t* w = v + 32 * c;
+    asm volatile("tcgen05.wait::ld.sync.aligned;\n"
+                 : "+r"(w[0]), "+r"(w[1]), "+r"(w[2]), "+r"(w[3]), "+r"(w[4]), "+r"(w[5]), "+r"(w[6]), "+r"(w[7]),
+                   "+r"(w[8]), "+r"(w[9]), "+r"(w[10]), "+r"(w[11]), "+r"(w[12]), "+r"(w[13]), "+r"(w[14]), "+r"(w[15]),
+                   "+r"(w[16]), "+r"(w[17]), "+r"(w[18]), "+r"(w[19]), "+r"(w[20]), "+r"(w[21]), "+r"(w[22]), "+r"(w[23]),
+                   "+r"(w[24]), "+r"(w[25]), "+r"(w[26]), "+r"(w[27]), "+r"(w[28]), "+r"(w[29]), "+r"(w[30]), "+r"(w[31])
+                 :
+                 : "memory");
+  }
 }
 
 // four back-to-back 32-column loads (128 accumulator columns of this thread's lane), one wait
@@ -518,14 +552,14 @@ knn_tc3_kernel(const __grid_constant__ CUtensorMap tmap_rows, const __grid_const
         }
       } else if (MODE == 2) {
         // running top-8 of this thread's share of the sample (registers, sorted descending)
-        uint32_t v[128];
-        tc_ld128(taddr0, v);
-#pragma unroll
+#pragma unroll 1
         for (int c = 0; c < 4; ++c) {
-          if (t3_max32(v + 32 * c) > top[kT3ProbeTop - 1]) {
+          uint32_t v[32];
+          tc_ld32(taddr0 + static_cast<uint32_t>(32 * c), v);
+          if (t3_max32(v) > top[kT3ProbeTop - 1]) {
 #pragma unroll
             for (int j = 0; j < 32; ++j) {
-              const float x = __uint_as_float(v[32 * c + j]);
+              const float x = __uint_as_float(v[j]);
               if (x > top[kT3ProbeTop - 1]) {
                 top[kT3ProbeTop - 1] = x;
 #pragma unroll
@@ -539,11 +573,15 @@ knn_tc3_kernel(const __grid_constant__ CUtensorMap tmap_rows, const __grid_const
         }
       } else {
         const uint32_t row_base = static_cast<uint32_t>(t * kT3TileRows + col_half * 128);
-        uint32_t v[128];
-        tc_ld128(taddr0, v);                       // (one .x128 load instead of four .x32: same time, r01)
         bool pushed = false;                       // rare per lane: ≈ K'·stride + band survivors per query per pass
+#pragma unroll 1
+        for (int hcol = 0; hcol < 128; hcol += 64) {     // 64 columns at a time: 120 registers instead of 168, same speed
+          uint32_t v[64];
+          tc_ld64(taddr0 + static_cast<uint32_t>(hcol), v);
 #pragma unroll
-        for (int c = 0; c < 4; ++c) pushed |= t3_scan32(v + 32 * c, my_thr, row_base + static_cast<uint32_t>(32 * c), sink);
+          for (int c = 0; c < 2; ++c)
+            pushed |= t3_scan32(v + 32 * c, my_thr, row_base + static_cast<uint32_t>(hcol + 32 * c), sink);
+        }
         if (__any_sync(0xFFFFFFFFu, pushed)) {
           __syncwarp();
           if (*qcount >= static_cast<uint32_t>(kT3QueueFlush)) t3_flush(qu, lane, cand_pairs, cand_count, cap);

@@ -67,6 +67,14 @@ struct rse_index {
   size_t pin_status_n = 0;
   cudaEvent_t ev_status = nullptr;
   cudaEvent_t ev_stage = nullptr;  // the uploads out of pin_stage have completed
+  // hybrid step: BM25 runs on a second, lowest-priority stream UNDER the tensor-core filter pass (one BM25 CTA fits
+  // next to the filter's CTA on every SM); see hybrid_run_impl / knn_tc3_block
+  cudaStream_t stream_b = nullptr;
+  cudaEvent_t ev_prefilter = nullptr, ev_bm25_done = nullptr;
+  bool bm25_overlap_pending = false;
+  int ov_nq = 0, ov_limit = 0;
+  double ov_k1 = 0.0, ov_b = 0.0;
+  bool overlap_enabled = true;
   int tc_filter_kind = 2;          // 2 = knn_tc3_kernel (fp16 normalised shadow, queries resident in shared memory; default),
                                    // 0 = knn_tc_kernel<1> (TF32, queries streamed), 1 = knn_tc2_filter_kernel (TF32, queries in TMEM)
   DevBuf tc_q, tc_thr, tc_isb, tc_rows, tc_cnt, tc_keys, tc_status;
@@ -403,6 +411,30 @@ int ensure_shadow(rse_index* h) {
   return RSE_OK;
 }
 
+extern "C" int bm25_run_fwd(rse_index* h, int nq, int k, double k1, double b);   // = bm25_run (defined further down)
+
+// Enqueue the pending BM25 batch of a hybrid step on the second stream, ordered behind `after` (an event on the main
+// stream).  Called right after the filter kernel has been launched, so the filter's CTAs are placed first and BM25
+// fills what is left of every SM.
+int enqueue_bm25_overlapped(rse_index* h, cudaEvent_t after) {
+  if (!h->bm25_overlap_pending) return RSE_OK;
+  h->bm25_overlap_pending = false;
+  if (!h->stream_b) {
+    int lo = 0, hi = 0;
+    CK(cudaDeviceGetStreamPriorityRange(&lo, &hi));          // lo = numerically largest = lowest priority
+    CK(cudaStreamCreateWithPriority(&h->stream_b, cudaStreamNonBlocking, lo));
+    CK(cudaEventCreateWithFlags(&h->ev_bm25_done, cudaEventDisableTiming));
+  }
+  CK(cudaStreamWaitEvent(h->stream_b, after, 0));
+  cudaStream_t main_stream = h->stream;
+  h->stream = h->stream_b;
+  const int rc = bm25_run_fwd(h, h->ov_nq, h->ov_limit, h->ov_k1, h->ov_b);
+  h->stream = main_stream;
+  if (rc != RSE_OK) return rc;
+  CK(cudaEventRecord(h->ev_bm25_done, h->stream_b));
+  return RSE_OK;
+}
+
 // ---- K4 over the fp16 shadow (knn_tc3.cuh) for one block of ≤ 256 queries
 int knn_tc3_block(rse_index* h, const float* q_dev, const double* sb, int nqb, int kprime, long long* cand_dev,
                   int* status_dev) {
@@ -411,6 +443,9 @@ int knn_tc3_block(rse_index* h, const float* q_dev, const double* sb, int nqb, i
     CK(cudaFuncSetAttribute(knn_tc3_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, kT3SmemBytes));
     CK(cudaFuncSetAttribute(knn_tc3_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, kT3SmemBytes));
     CK(cudaFuncSetAttribute(knn_tc3_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, kT3SmemBytes));
+    // the filter shares its SMs with BM25 CTAs (hybrid step): ask for the full shared-memory carve-out, otherwise the
+    // driver picks the smallest configuration that fits the filter alone and nothing else can become resident
+    CK(cudaFuncSetAttribute(knn_tc3_kernel<1>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
     attrs = true;
   }
   ENSURE(h->tc_q16, sizeof(__half) * kTcBN * kScanD);
@@ -485,10 +520,18 @@ int knn_tc3_block(rse_index* h, const float* q_dev, const double* sb, int nqb, i
     int rc = scan_event(h, &e0);
     if (rc != RSE_OK) return rc;
   }
+  if (h->bm25_overlap_pending) {
+    if (!h->ev_prefilter) CK(cudaEventCreateWithFlags(&h->ev_prefilter, cudaEventDisableTiming));
+    CK(cudaEventRecord(h->ev_prefilter, h->stream));
+  }
   knn_tc3_kernel<1><<<grid_f, kT3Threads, kT3SmemBytes, h->stream>>>(
       h->tmap_a16, h->tmap_q16, n_tiles, 1, nqb, thr, nullptr, 0, static_cast<uint2*>(h->tc_rows.p),
       static_cast<unsigned int*>(h->tc_cnt.p), kTcCandCap);
   LAUNCHED(h);
+  {
+    int rc = enqueue_bm25_overlapped(h, h->ev_prefilter);     // no-op unless a hybrid step asked for it
+    if (rc != RSE_OK) return rc;
+  }
   if (e0) {
     int rc = scan_event(h, &e1);
     if (rc != RSE_OK) return rc;
@@ -804,6 +847,9 @@ void rse_destroy(rse_index* h) {
   if (h->pin_stage) cudaFreeHost(h->pin_stage);
   if (h->ev_status) cudaEventDestroy(h->ev_status);
   if (h->ev_stage) cudaEventDestroy(h->ev_stage);
+  if (h->ev_prefilter) cudaEventDestroy(h->ev_prefilter);
+  if (h->ev_bm25_done) cudaEventDestroy(h->ev_bm25_done);
+  if (h->stream_b) cudaStreamDestroy(h->stream_b);
   free_ptr(h->doc_ids);
   free_ptr(h->movie_ids);
   for (auto& ev : h->ev) if (ev) cudaEventDestroy(ev);
@@ -1103,6 +1149,7 @@ int rse_load_bm25(rse_index* h, const int64_t* indptr, const uint32_t* doc_idx, 
     CK(cudaFuncSetAttribute(bm25_score_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kBmRange * 9));
     CK(cudaFuncSetAttribute(bm25_stream_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bs_smem_bytes()));
     CK(cudaFuncSetAttribute(bm25_fx_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, fx_smem_bytes(kBsMaxRpg)));
+    CK(cudaFuncSetAttribute(bm25_fx_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
     attr = true;
   }
   return RSE_OK;
@@ -1303,6 +1350,12 @@ int bm25_device(rse_index* h, const int32_t* tok_indptr, const int32_t* term_row
 
 }  // namespace
 
+// internal trampoline (not part of the ABI in include/rse.h): lets the KNN code above enqueue a BM25 batch
+__attribute__((visibility("hidden"))) int bm25_run_fwd(rse_index* h, int nq, int k, double k1, double b) {
+  return bm25_run(h, nq, k, k1, b);
+}
+
+
 int rse_bm25(rse_index* h, const int32_t* tok_indptr, const int32_t* term_rows, int32_t nq, int32_t k, double k1,
              double b, double* out_score, int32_t* out_doc_idx, int32_t* out_count) {
   if (!h) return RSE_ERR_INVALID;
@@ -1492,12 +1545,22 @@ int hybrid_run_impl(rse_index* h, int mode, double param, int tie_mode, int limi
   } else {
     // KNN (k = limit, hybrid_search.py:88) is enqueued first; BM25 (hybrid_search.py:70) goes in behind it while
     // the tensor-core path's overflow flags travel back, so the host round trip costs the device nothing
+    // ... and when the KNN takes the tensor-core path, on a second stream UNDERNEATH the filter pass: the filter
+    // kernel keeps one 178 KB CTA per SM busy on the tensor pipe at ~20 % issue utilisation, and one BM25 CTA
+    // (38 KB, 512 threads) fits beside it.
+    h->bm25_overlap_pending = h->overlap_enabled;
+    h->ov_nq = nq; h->ov_limit = limit; h->ov_k1 = k1; h->ov_b = b;
     rc = knn_local_begin(h, static_cast<const float*>(h->q_dev.p), nq, kprime, static_cast<long long*>(h->cand.p));
-    if (rc != RSE_OK) return rc;
-    rc = bm25_run(h, nq, limit, k1, b);
-    if (rc != RSE_OK) return rc;
+    if (rc != RSE_OK) { h->bm25_overlap_pending = false; return rc; }
+    const bool overlapped = h->overlap_enabled && !h->bm25_overlap_pending;   // the filter launch consumed the request
+    h->bm25_overlap_pending = false;
+    if (!overlapped) {
+      rc = bm25_run(h, nq, limit, k1, b);
+      if (rc != RSE_OK) return rc;
+    }
     rc = knn_local_finish(h);
     if (rc != RSE_OK) return rc;
+    if (overlapped) CK(cudaStreamWaitEvent(h->stream, h->ev_bm25_done, 0));
   }
   rc = aggregate(h, static_cast<const long long*>(h->cand.p), nq, limit, kprime, static_cast<float*>(h->o_dist.p),
                  static_cast<long long*>(h->o_rowid.p), static_cast<int*>(h->o_movie.p), static_cast<int*>(h->o_count.p));
