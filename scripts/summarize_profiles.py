@@ -47,7 +47,8 @@ def launches(tag, path):
     names = [r["Kernel Name"].split("(")[0] for r in rows]
     fuse = [i for i, n in enumerate(names) if "fuse_kernel" in n]
     if len(fuse) >= 2:
-        out += ["", "# one step (launch order):"]
+        out += ["", "# one step (launch order; ncu serialises the launches — in a real step bm25_fx_kernel runs on a second",
+                "# stream underneath knn_tc3_kernel<1>, so the step is shorter than this sum):"]
         tot = 0.0
         for i in range(fuse[-2] + 1, fuse[-1] + 1):
             v = float(rows[i]["Metric Value"].replace(",", "")) * {"us": 1e3, "ms": 1e6, "s": 1e9}.get(rows[i]["Metric Unit"], 1.0)
