@@ -61,6 +61,11 @@ struct rse_index {
   const float* pend_q = nullptr;
   int pend_nq = 0, pend_kprime = 0;
   long long* pend_cand = nullptr;
+  DevBuf f_pack;                   // rse_hybrid_run results: id | score | a | b | count, back to back
+  size_t pack_n = 0;
+  int pack_nq = 0;
+  char* pin_out = nullptr;         // pinned landing buffer of rse_hybrid_fetch
+  size_t pin_out_bytes = 0;
   char* pin_stage = nullptr;       // pinned staging for the token / idf upload of a hybrid or BM25 batch
   size_t pin_stage_bytes = 0;
   int* pin_status = nullptr;       // pinned host copy of the per-query overflow flags
@@ -845,6 +850,8 @@ void rse_destroy(rse_index* h) {
     free_buf(*b);
   if (h->pin_status) cudaFreeHost(h->pin_status);
   if (h->pin_stage) cudaFreeHost(h->pin_stage);
+  if (h->pin_out) cudaFreeHost(h->pin_out);
+  free_buf(h->f_pack);
   if (h->ev_status) cudaEventDestroy(h->ev_status);
   if (h->ev_stage) cudaEventDestroy(h->ev_stage);
   if (h->ev_prefilter) cudaEventDestroy(h->ev_prefilter);
@@ -1589,11 +1596,15 @@ int rse_hybrid_run(rse_index* h, int32_t mode, double param, int32_t tie_mode, i
   if (nq <= 0) return fail(h, RSE_ERR_STATE, "rse_hybrid_run: nothing staged");
   if (limit < 1 || limit > RSE_MAX_FUSE_LIMIT) return fail(h, RSE_ERR_UNSUPPORTED, "rse_hybrid: limit must be in [1, 128]");
   const size_t n = static_cast<size_t>(nq) * limit;
-  ENSURE(h->f_oid, 8 * n); ENSURE(h->f_osc, 8 * n); ENSURE(h->f_oa, 8 * n); ENSURE(h->f_ob, 8 * n);
-  ENSURE(h->f_ocnt, 4 * static_cast<size_t>(nq));
+  // the five result arrays live back to back in one buffer, so rse_hybrid_fetch is ONE device-to-host copy into
+  // pinned memory (five copies into pageable caller buffers were five synchronous staging round trips)
+  ENSURE(h->f_pack, 32 * n + 4 * static_cast<size_t>(nq));
+  char* pk = static_cast<char*>(h->f_pack.p);
+  h->pack_n = n; h->pack_nq = nq;
   return hybrid_run_impl(h, mode, param, tie_mode, limit, knn_multiplier, k1, b, nullptr, 0,
-                         static_cast<long long*>(h->f_oid.p), static_cast<double*>(h->f_osc.p),
-                         static_cast<double*>(h->f_oa.p), static_cast<double*>(h->f_ob.p), static_cast<int*>(h->f_ocnt.p));
+                         reinterpret_cast<long long*>(pk), reinterpret_cast<double*>(pk + 8 * n),
+                         reinterpret_cast<double*>(pk + 16 * n), reinterpret_cast<double*>(pk + 24 * n),
+                         reinterpret_cast<int*>(pk + 32 * n));
 }
 
 int rse_hybrid_run_merged_dev(rse_index* h, int32_t mode, double param, int32_t tie_mode, int32_t limit,
@@ -1615,12 +1626,21 @@ int rse_hybrid_fetch(rse_index* h, int32_t limit, int64_t* out_id, double* out_s
   if (nq <= 0) return fail(h, RSE_ERR_STATE, "rse_hybrid_fetch: nothing staged");
   if (!out_id || !out_score || !out_a || !out_b || !out_count) return fail(h, RSE_ERR_INVALID, "rse_hybrid_fetch: bad arguments");
   const size_t n = static_cast<size_t>(nq) * limit;
-  CK(cudaMemcpyAsync(out_id, h->f_oid.p, 8 * n, cudaMemcpyDeviceToHost, h->stream));
-  CK(cudaMemcpyAsync(out_score, h->f_osc.p, 8 * n, cudaMemcpyDeviceToHost, h->stream));
-  CK(cudaMemcpyAsync(out_a, h->f_oa.p, 8 * n, cudaMemcpyDeviceToHost, h->stream));
-  CK(cudaMemcpyAsync(out_b, h->f_ob.p, 8 * n, cudaMemcpyDeviceToHost, h->stream));
-  CK(cudaMemcpyAsync(out_count, h->f_ocnt.p, 4 * static_cast<size_t>(nq), cudaMemcpyDeviceToHost, h->stream));
+  if (h->pack_n != n || h->pack_nq != nq) return fail(h, RSE_ERR_STATE, "rse_hybrid_fetch: limit differs from the last rse_hybrid_run");
+  const size_t bytes = 32 * n + 4 * static_cast<size_t>(nq);
+  if (h->pin_out_bytes < bytes) {
+    if (h->pin_out) CK(cudaFreeHost(h->pin_out));
+    h->pin_out = nullptr; h->pin_out_bytes = 0;
+    CK(cudaMallocHost(reinterpret_cast<void**>(&h->pin_out), bytes + bytes / 2));
+    h->pin_out_bytes = bytes + bytes / 2;
+  }
+  CK(cudaMemcpyAsync(h->pin_out, h->f_pack.p, bytes, cudaMemcpyDeviceToHost, h->stream));
   CK(cudaStreamSynchronize(h->stream));
+  std::memcpy(out_id, h->pin_out, 8 * n);
+  std::memcpy(out_score, h->pin_out + 8 * n, 8 * n);
+  std::memcpy(out_a, h->pin_out + 16 * n, 8 * n);
+  std::memcpy(out_b, h->pin_out + 24 * n, 8 * n);
+  std::memcpy(out_count, h->pin_out + 32 * n, 4 * static_cast<size_t>(nq));
   return RSE_OK;
 }
 
