@@ -128,6 +128,9 @@ struct rse_index {
   long long* movie_ids = nullptr;
   int64_t n_movie_ids = 0;
 
+  // cudaFuncSetAttribute is per device: remember per HANDLE which kernels were configured (a process-wide static
+  // flag would leave the second device of a multi-GPU process unconfigured)
+  uint32_t attr_mask = 0;
   rse_stats stats{};
 };
 
@@ -203,11 +206,11 @@ void release_bm25(rse_index* h) {
 // ------------------------------------------------------------------ scan launch
 template <int QB, bool FMA>
 int launch_scan384(rse_index* h, const float* q, const double* sb, int nq, float* dist) {
-  static bool attr_set = false;
   const int smem = scan_smem_bytes(QB);
-  if (!attr_set) {
+  constexpr uint32_t bit = 1u << ((QB == 1 ? 0 : QB == 2 ? 1 : QB == 4 ? 2 : QB == 8 ? 3 : 4) + (FMA ? 5 : 0));
+  if (!(h->attr_mask & bit)) {
     CK(cudaFuncSetAttribute(knn_scan384_kernel<QB, FMA>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    attr_set = true;
+    h->attr_mask |= bit;
   }
   const int64_t n_tiles = (h->n_rows + kScanTileRows - 1) / kScanTileRows;
   int grid = static_cast<int>(std::min<int64_t>(h->sm_count, (n_tiles + kScanWarps - 1) / kScanWarps));
@@ -349,11 +352,10 @@ int make_tmap_lines(rse_index* h, CUtensorMap* out, const void* base, int64_t li
 // refine + exact re-score + emit for one block of queries whose survivors are in tc_rows / tc_cnt
 int knn_tc_refine(rse_index* h, const float* q_dev, const double* sb, int nqb, int kprime, long long* cand_dev,
                   int* status_dev, int normalized) {
-  static bool attrs = false;
-  if (!attrs) {
+  if (!(h->attr_mask & (1u << 10))) {
     CK(cudaFuncSetAttribute(knn_refine_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kTcCandCap * 8));
     CK(cudaFuncSetAttribute(knn_refine_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kTcCandCap * 8));
-    attrs = true;
+    h->attr_mask |= 1u << 10;
   }
   if (h->fma)
     knn_refine_kernel<true><<<nqb, kSelThreads, kTcCandCap * 8, h->stream>>>(
@@ -443,15 +445,14 @@ int enqueue_bm25_overlapped(rse_index* h, cudaEvent_t after) {
 // ---- K4 over the fp16 shadow (knn_tc3.cuh) for one block of ≤ 256 queries
 int knn_tc3_block(rse_index* h, const float* q_dev, const double* sb, int nqb, int kprime, long long* cand_dev,
                   int* status_dev) {
-  static bool attrs = false;
-  if (!attrs) {
+  if (!(h->attr_mask & (1u << 11))) {
     CK(cudaFuncSetAttribute(knn_tc3_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, kT3SmemBytes));
     CK(cudaFuncSetAttribute(knn_tc3_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, kT3SmemBytes));
     CK(cudaFuncSetAttribute(knn_tc3_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, kT3SmemBytes));
     // the filter shares its SMs with BM25 CTAs (hybrid step): ask for the full shared-memory carve-out, otherwise the
     // driver picks the smallest configuration that fits the filter alone and nothing else can become resident
     CK(cudaFuncSetAttribute(knn_tc3_kernel<1>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
-    attrs = true;
+    h->attr_mask |= 1u << 11;
   }
   ENSURE(h->tc_q16, sizeof(__half) * kTcBN * kScanD);
   if (!h->tmap_q16_ok) {
@@ -559,11 +560,10 @@ bool tc_eligible(const rse_index* h, int nq, int kprime) {
 
 int knn_tc_block(rse_index* h, const float* q_dev, const double* sb, int nqb, int kprime, long long* cand_dev,
                  int* status_dev) {
-  static bool attrs = false;
-  if (!attrs) {
+  if (!(h->attr_mask & (1u << 12))) {
     CK(cudaFuncSetAttribute(knn_tc_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, kTcSmemBytes));
     CK(cudaFuncSetAttribute(knn_tc_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, kTcSmemBytes));
-    attrs = true;
+    h->attr_mask |= 1u << 12;
   }
   if (!h->tmap_a_ok) {
     int rc = make_tmap(h, &h->tmap_a, h->emb, h->n_rows, kTcBM);
@@ -640,10 +640,9 @@ int knn_tc_block(rse_index* h, const float* q_dev, const double* sb, int nqb, in
     CK(cudaEventRecord(e0, h->stream));
   }
   if (h->tc_filter_kind == 1) {
-    static bool attr2 = false;
-    if (!attr2) {
+    if (!(h->attr_mask & (1u << 13))) {
       CK(cudaFuncSetAttribute(knn_tc2_filter_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kT2SmemBytes));
-      attr2 = true;
+      h->attr_mask |= 1u << 13;
     }
     if (!h->tmap_b2_ok) {
       int rc = make_tmap(h, &h->tmap_b2, h->emb, h->n_rows, kT2HalfRows);
@@ -1151,13 +1150,12 @@ int rse_load_bm25(rse_index* h, const int64_t* indptr, const uint32_t* doc_idx, 
   CK(cudaStreamSynchronize(h->stream));
   h->stats.bm25_postings = n_postings;
   h->stats.bm25_docs = n_docs;
-  static bool attr = false;
-  if (!attr) {
+  if (!(h->attr_mask & (1u << 14))) {
     CK(cudaFuncSetAttribute(bm25_score_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kBmRange * 9));
     CK(cudaFuncSetAttribute(bm25_stream_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bs_smem_bytes()));
     CK(cudaFuncSetAttribute(bm25_fx_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, fx_smem_bytes(kBsMaxRpg)));
     CK(cudaFuncSetAttribute(bm25_fx_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
-    attr = true;
+    h->attr_mask |= 1u << 14;
   }
   return RSE_OK;
 }
