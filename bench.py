@@ -47,7 +47,7 @@ def scan_kernel_desc(args, tc_used, qb):
     k = tc_kind(args)
     if k == "f16-shadow":
         return ("knn_tc3_kernel<filter> (tcgen05 kind::f16 256x256x16 cta_group::2 over the fp16 normalised shadow, "
-                "queries resident in shared memory, TMA 8-stage; one pass serves 256 queries; survivors re-scored "
+                "queries resident in shared memory, TMA 4-stage ring; one pass serves 256 queries; survivors re-scored "
                 "exactly in fp32)"), ROW_BYTES_SHADOW
     if k == "tf32-tmem":
         return "knn_tc2_filter_kernel (tcgen05 TF32 cta_group::2, queries resident in TMEM)", ROW_BYTES

@@ -560,3 +560,41 @@ def test_hybrid_large_batch_takes_tensor_core_path_and_matches_oracle(fresh_inde
         want = pyref.rrf_fuse(bmh, semh, 60.0, limit)
         got = [(int(oid[qi, j]), float(sc[qi, j])) for j in range(cnt[qi])]
         assert got == [(x["id"], x["score"]) for x in want]
+
+
+# ----------------------------------------------------------------------------- full-size properties (S-600k shape)
+def test_full_size_tensor_core_path_equals_exact_scan_and_is_idempotent():
+    """At the benchmark's own size (4.8 M chunks x 384): the batched tensor-core path must return exactly what the
+    exact streaming scan returns for the same 256 queries (rows, order, distance bits), twice in a row (idempotence),
+    and every list must be sorted by the vec0 emit order (distance asc, block asc, slot desc)."""
+    import torch
+    from rag_search_engine_b200 import _lib, synth
+    se = synth.synth_embeddings(600_000, seed=1234, device="cuda")
+    n = int(se.emb.shape[0])
+    Q = synth.synth_query_vectors(se.emb, 256, seed=99).cpu().numpy()
+    out = {}
+    for mode in (1, 0):
+        idx = _lib.Index(0)
+        try:
+            idx.set_tc_mode(mode)
+            idx.attach_embeddings_dev(se.emb.data_ptr(), n, 384, movie_idx_ptr=se.movie_of_chunk.data_ptr(), keepalive=se)
+            out[mode] = idx.knn(Q, 100)
+            if mode == 0:
+                again = idx.knn(Q, 100)
+                for a, b in zip(out[0], again):
+                    assert (a.view(np.uint8) == b.view(np.uint8)).all(), "second run differs from the first"
+                st = idx.stats()
+                assert st.tc_queries == 512 and st.tc_fallback_queries == 0
+        finally:
+            idx.close()
+    for a, b in zip(out[1], out[0]):
+        assert a.dtype == b.dtype and (a.view(np.uint8) == b.view(np.uint8)).all()
+    dist, pos = out[0][0], out[0][1]
+    assert (out[0][-1] == 100).all()                                  # every query found its full K'
+    d = dist                                                          # f32 distances (may be a few ulps below 0)
+    blk, slot = pos // 1024, pos % 1024
+    ok = (d[:, 1:] > d[:, :-1]) | ((d[:, 1:] == d[:, :-1]) & ((blk[:, 1:] > blk[:, :-1]) |
+                                                              ((blk[:, 1:] == blk[:, :-1]) & (slot[:, 1:] < slot[:, :-1]))))
+    assert ok.all(), "a result list is not in vec0 emit order"
+    del se
+    torch.cuda.empty_cache()
