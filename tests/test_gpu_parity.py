@@ -598,3 +598,31 @@ def test_full_size_tensor_core_path_equals_exact_scan_and_is_idempotent():
     assert ok.all(), "a result list is not in vec0 emit order"
     del se
     torch.cuda.empty_cache()
+
+
+def test_full_size_bm25_modes_agree():
+    """At the benchmark's own size (600 k documents, 54 M postings, 256 queries touching ~78 M postings): the
+    fixed-point streaming path, the exact-order streaming path and the general kernel return identical documents,
+    order and score bits; scores are non-increasing and every hit is a real document."""
+    import torch
+    from rag_search_engine_b200 import _lib, synth
+    bm = synth.synth_bm25(600_000, 1_000_000, seed=1234, device="cuda")
+    tok_indptr, terms = synth.synth_token_queries(bm, 256, seed=99)
+    out = {}
+    for mode in (2, 1, 0):
+        idx = _lib.Index(0)
+        try:
+            idx.set_bm25_mode(mode)
+            idx.load_bm25(bm.indptr, bm.doc_idx, bm.tf, bm.df, bm.dl, bm.n_movies, bm.avgdl)
+            out[mode] = idx.bm25(tok_indptr, terms, 10)
+        finally:
+            idx.close()
+    for mode in (1, 0):
+        for a, b in zip(out[2], out[mode]):
+            assert (a.view(np.uint8) == b.view(np.uint8)).all(), f"bm25 mode {mode} differs from the general kernel"
+    sc, dc, cnt = out[0]
+    for q in range(256):
+        c = int(cnt[q])
+        assert (np.diff(sc[q, :c]) <= 0).all()
+        assert ((dc[q, :c] >= 0) & (dc[q, :c] < 600_000)).all()
+    torch.cuda.empty_cache()
