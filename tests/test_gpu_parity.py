@@ -426,7 +426,8 @@ def test_sharded_merge_equals_single_index():
 
 
 # ----------------------------------------------------------------------------- K4 tensor-core path
-@pytest.mark.parametrize("n,nq,kprime", [(40_000, 70, 100), (9_000, 256, 50), (33_000, 300, 100), (5_000, 5, 10)])
+@pytest.mark.parametrize("n,nq,kprime", [(40_000, 70, 100), (9_000, 256, 50), (33_000, 300, 100), (5_000, 5, 10),
+                                         (60_000, 64, 400)])      # K' > 256: the dense probe instead of the per-thread top-8
 def test_tensor_core_path_equals_exact_scan_and_oracle(n, nq, kprime):
     """K4 (tcgen05 probe/filter + exact re-score) must return exactly what the exact scan returns:
     same rows, same order, bit-identical distances — including duplicate rows (ties) and non-unit norms.
