@@ -701,7 +701,9 @@ bm25_fx_kernel(const int64_t* __restrict__ indptr, const Post16* __restrict__ po
   __shared__ unsigned int s_ncand, s_nkept, s_nrc;
   __shared__ unsigned int s_min, s_tw;
   __shared__ unsigned short s_rc[kBsRangeCap];
-  __shared__ unsigned char s_itok[kFxMaxItems];                                        // token of every item of the range
+  __shared__ unsigned short s_itab[kFxMaxItems];                                       // (token << 8) | chunk of every item of the range
+  __shared__ long long s_sbase[kBsMaxTok];                                             // first posting of token t's slice in this range
+  __shared__ unsigned int s_sn[kBsMaxTok];                                             // postings in that slice
 
   const int g = blockIdx.x;
   const int q = q0 + blockIdx.y;
@@ -767,7 +769,10 @@ bm25_fx_kernel(const int64_t* __restrict__ indptr, const Post16* __restrict__ po
 
   for (int r = r0; r < r1; ++r) {
     const int jr = r - r0;
-    // items of this range: slice t contributes ceil(n_t / 32) items of 32 postings (one per lane)
+    // items of this range: slice t contributes ceil(n_t / 32) items of 32 postings (one per lane).
+    // The barrier keeps warp 0 from overwriting s_pre while a slower warp still reads the previous range's item
+    // count (an empty range `continue`s without passing any other barrier).
+    __syncthreads();
     if (warp == 0) {
       unsigned int c = 0u;
       if (lane < ntok) c = (s_off[lane * ostride + jr + 1] - s_off[lane * ostride + jr] + 31u) >> 5;
@@ -782,18 +787,25 @@ bm25_fx_kernel(const int64_t* __restrict__ indptr, const Post16* __restrict__ po
     }
     __syncthreads();
     const unsigned int n_items = s_pre[ntok];
-    if (n_items == 0u) continue;                          // uniform; the next iteration's barrier protects s_pre
+    if (n_items == 0u) continue;                          // uniform
     if (n_items > kFxMaxItems) {                          // uniform
       if (threadIdx.x == 0) { status[q] = 1; fin_cnt[cbase] = 0; }
       return;
     }
     const uint32_t doc_base = static_cast<uint32_t>(r) * kBmRange;
     const unsigned int cross = established ? theta : ~0u;
-    // item → token table, one THREAD per item (a warp-uniform search per item was half of the kernel's instructions)
+    // item table, one THREAD per item: (token << 8) | chunk, so a warp fetches its item with three shared-memory
+    // loads (a warp-uniform search per item was half of the kernel's instructions, per-item offset arithmetic a
+    // fifth of what was left)
+    if (threadIdx.x < ntok) {
+      const uint32_t a = s_off[threadIdx.x * ostride + jr];
+      s_sbase[threadIdx.x] = s_base[threadIdx.x] + a;
+      s_sn[threadIdx.x] = s_off[threadIdx.x * ostride + jr + 1] - a;
+    }
     for (unsigned int i = threadIdx.x; i < n_items; i += kBsThreads) {
       int t = 0;
       while (t + 1 < ntok && s_pre[t + 1] <= i) ++t;
-      s_itok[i] = static_cast<unsigned char>(t);
+      s_itab[i] = static_cast<unsigned short>((t << 8) | (i - s_pre[t]));
     }
     __syncthreads();
 
@@ -801,12 +813,11 @@ bm25_fx_kernel(const int64_t* __restrict__ indptr, const Post16* __restrict__ po
       e = make_uint4(0xFFFFFFFFu, 0u, 0u, 0u);
       idfx = 0.0;
       if (item >= n_items) return;
-      const int t = s_itok[item];
+      const unsigned int d = s_itab[item];
+      const int t = static_cast<int>(d >> 8);
+      const unsigned int i = (d & 0xFFu) * 32u + lane;
       idfx = s_idfx[t];
-      const uint32_t a = s_off[t * ostride + jr];
-      const unsigned int n = s_off[t * ostride + jr + 1] - a;
-      const unsigned int i = (item - s_pre[t]) * 32u + lane;
-      if (i < n) e = __ldg(reinterpret_cast<const uint4*>(post + s_base[t] + a + i));
+      if (i < s_sn[t]) e = __ldg(reinterpret_cast<const uint4*>(post + s_sbase[t] + i));
     };
     auto item_apply = [&](const uint4& e, double idfx) {
       if (e.x == 0xFFFFFFFFu) return;

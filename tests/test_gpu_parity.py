@@ -627,3 +627,34 @@ def test_full_size_bm25_modes_agree():
         assert (np.diff(sc[q, :c]) <= 0).all()
         assert ((dc[q, :c] >= 0) & (dc[q, :c] < 600_000)).all()
     torch.cuda.empty_cache()
+
+
+def test_hybrid_repeated_large_batches_are_stable(fresh_index):
+    """Back-to-back hybrid batches of 1024 queries (four tensor-core blocks, BM25 on the second stream underneath the
+    filter pass) must return the same bits every time — a shared-memory race in the BM25 kernel once made this fail
+    intermittently with an illegal access."""
+    from rag_search_engine_b200 import synth
+    n_movies = 36_000
+    se = synth.synth_embeddings(n_movies, seed=6, device="cuda")
+    assert se.emb.shape[0] >= 262_144
+    bm = synth.synth_bm25(n_movies, 20_000, seed=6, mean_len=40, sd_len=12, device="cuda")
+    nq, limit = 1024, 10
+    tok_indptr, terms = synth.synth_token_queries(bm, nq, seed=13)
+    Q = synth.synth_query_vectors(se.emb, nq, seed=13).cpu().numpy()
+    ids = se.movie_ids
+    fresh_index.attach_embeddings_dev(se.emb.data_ptr(), se.emb.shape[0], 384, movie_idx_ptr=se.movie_of_chunk.data_ptr(),
+                                      keepalive=se)
+    fresh_index.load_bm25(bm.indptr, bm.doc_idx, bm.tf, bm.df, bm.dl, bm.n_movies, bm.avgdl)
+    fresh_index.set_id_tables(ids, ids)
+    ref = fresh_index.hybrid(0, 60.0, limit, Q, tok_indptr, terms)
+    assert fresh_index.stats().tc_queries == nq
+    for it in range(25):
+        got = fresh_index.hybrid(0, 60.0, limit, Q, tok_indptr, terms)
+        for a, b in zip(ref, got):
+            assert (a.view(np.uint8) == b.view(np.uint8)).all(), f"iteration {it} differs"
+    fresh_index.hybrid_stage(Q, tok_indptr, terms)
+    for it in range(25):
+        fresh_index.hybrid_run(0, 60.0, limit)
+    got = fresh_index.hybrid_fetch(limit)
+    for a, b in zip(ref, got):
+        assert (a.view(np.uint8) == b.view(np.uint8)).all()
