@@ -103,6 +103,7 @@ class ClockSampler:
         self.stop_flag = False
         self.sm, self.reasons = [], set()
         self.sm_max = None
+        self.poll_once = lambda: None
         self.path = Path(os.environ.get("TMPDIR", "/tmp")) / f"rse_clocks_{os.getpid()}.csv"
 
     def _poll(self, nv, handle):
@@ -112,7 +113,7 @@ class ClockSampler:
                  "sw_power_cap": getattr(nv, "nvmlClocksEventReasonSwPowerCap", 0x4)}
         get_reasons = getattr(nv, "nvmlDeviceGetCurrentClocksEventReasons", None) or \
             getattr(nv, "nvmlDeviceGetCurrentClocksThrottleReasons")
-        while not self.stop_flag:
+        def once():
             try:
                 self.sm.append(float(nv.nvmlDeviceGetClockInfo(handle, nv.NVML_CLOCK_SM)))
                 mask = int(get_reasons(handle))
@@ -121,6 +122,9 @@ class ClockSampler:
                         self.reasons.add(k)
             except Exception:
                 pass
+        self.poll_once = once                 # the timed loop also samples inline every few steps (the thread can starve)
+        while not self.stop_flag:
+            once()
             time.sleep(0.001)
 
     def start(self):
@@ -159,7 +163,7 @@ class ClockSampler:
             self.thread.join(timeout=2)
             if self.sm:
                 out.update(sm_mhz=statistics.median(self.sm), sm_max_mhz=self.sm_max, reasons=sorted(self.reasons),
-                           samples=len(self.sm), source="nvml, 1 ms poll")
+                           samples=len(self.sm), source="nvml: 1 ms polling thread + inline sample every 8 steps")
             return out
         if self.proc is None:
             return out
@@ -418,8 +422,10 @@ def run_b200(args, rank, world, local_rank):
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     torch.cuda.synchronize(); barrier()
     e0.record(stream)
-    for _ in range(args.steps):
+    for i in range(args.steps):
         step_fn()
+        if (i & 7) == 3:
+            sampler.poll_once()               # ~20 us of host time every 8 steps; the device queue stays fed
     e1.record(stream)
     torch.cuda.synchronize(); barrier()
     clocks = sampler.stop()
