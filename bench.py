@@ -48,7 +48,8 @@ def scan_kernel_desc(args, tc_used, qb):
     if k == "f16-shadow":
         return ("knn_tc3_kernel<filter> (tcgen05 kind::f16 256x256x16 cta_group::2 over the fp16 normalised shadow, "
                 "queries resident in shared memory, TMA 4-stage ring; one pass serves 256 queries; survivors re-scored "
-                "exactly in fp32)"), ROW_BYTES_SHADOW
+                "exactly in fp32; in the hybrid step one bm25_fx_kernel CTA per SM runs underneath it on a second "
+                "stream, which costs the pass ~8 %)"), ROW_BYTES_SHADOW
     if k == "tf32-tmem":
         return "knn_tc2_filter_kernel (tcgen05 TF32 cta_group::2, queries resident in TMEM)", ROW_BYTES
     return ("knn_tc_kernel<filter> (tcgen05 TF32 128x256x8, TMA 3-stage, queries streamed from L2; one pass over the "
