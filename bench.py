@@ -59,7 +59,7 @@ def scan_kernel_desc(args, tc_used, qb):
 def parse_args():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=100)
+    ap.add_argument("--steps", type=int, default=300)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--movies", type=int, default=600_000)
@@ -104,7 +104,6 @@ class ClockSampler:
         self.stop_flag = False
         self.sm, self.reasons = [], set()
         self.sm_max = None
-        self.poll_once = lambda: None
         self.path = Path(os.environ.get("TMPDIR", "/tmp")) / f"rse_clocks_{os.getpid()}.csv"
 
     def _poll(self, nv, handle):
@@ -123,7 +122,6 @@ class ClockSampler:
                         self.reasons.add(k)
             except Exception:
                 pass
-        self.poll_once = once                 # the timed loop also samples inline every few steps (the thread can starve)
         while not self.stop_flag:
             once()
             time.sleep(0.001)
@@ -164,7 +162,7 @@ class ClockSampler:
             self.thread.join(timeout=2)
             if self.sm:
                 out.update(sm_mhz=statistics.median(self.sm), sm_max_mhz=self.sm_max, reasons=sorted(self.reasons),
-                           samples=len(self.sm), source="nvml: 1 ms polling thread + inline sample every 8 steps")
+                           samples=len(self.sm), source="nvml polling thread (one query takes ~25 ms)")
             return out
         if self.proc is None:
             return out
@@ -423,11 +421,9 @@ def run_b200(args, rank, world, local_rank):
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     torch.cuda.synchronize(); barrier()
     e0.record(stream)
-    for i in range(args.steps):
-        step_fn()
-        if (i & 7) == 3:
-            sampler.poll_once()               # ~20 us of host time every 8 steps; the device queue stays fed
-    e1.record(stream)
+    for _ in range(args.steps):
+        step_fn()                             # (no inline NVML sampling here: one query costs the host ~25 ms and the
+    e1.record(stream)                         #  device would idle; the sampler thread polls concurrently instead)
     torch.cuda.synchronize(); barrier()
     clocks = sampler.stop()
     sh_last = step_fn() if rowshard else None
