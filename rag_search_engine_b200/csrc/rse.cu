@@ -7,6 +7,7 @@
 #include <algorithm>
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -830,6 +831,8 @@ int rse_create(int32_t device, rse_index** out) {
   }
   h->stream = h->own_stream;
   for (auto& ev : h->ev) cudaEventCreate(&ev);
+  // diagnostics: RSE_NO_OVERLAP=1 keeps the hybrid step's BM25 on the caller's stream (no second stream)
+  if (const char* ev = std::getenv("RSE_NO_OVERLAP")) h->overlap_enabled = !(ev[0] == '1');
   *out = h;
   return RSE_OK;
 }
