@@ -620,7 +620,10 @@ def run_b200(args, rank, world, local_rank):
         oid, osc, oa, ob, oc = res if e2e and world == 1 else idx.hybrid(mode, param, limit, Qn, tok_indptr, terms)
         ok = all([int(x) for x in oid[q, :oc[q]]] == [r["id"] for r in cpu_out[q]] and
                  [float(x) for x in osc[q, :oc[q]]] == [r["score"] for r in cpu_out[q]] for q in range(sample))
+        # the reference itself is single-threaded: the same port on ONE core, two queries
+        qps1, dt1, _ = cpu_hybrid_sample(emb_host, movie_of, bm, se.movie_ids, Qn, tok_indptr, terms, limit, args.mode, 2, 1)
         line["cpu_baseline"] = {"value": qps, "unit": "queries/s", "cores": cores, "kind": "port",
+                                "one_core": {"value": qps1, "unit": "queries/s", "sample": f"2 queries, {dt1:.1f} s"},
                                 "sample": f"{sample} hybrid queries of the same batch over the full corpus, "
                                           f"{dt:.1f} s (OpenMP over queries; literal vec0 scan per query)",
                                 "gpu_matches_cpu_on_sample": bool(ok)}
