@@ -235,7 +235,7 @@ def cpu_hybrid_sample(se_emb_host, movie_of, bm, ids, Q, tok_indptr, terms, limi
     """The reference's CPU path restated (oracle/): literal vec0 scan + aggregation, BM25, fusion."""
     import oracle
     from oracle import pyref
-    os.environ["OMP_NUM_THREADS"] = str(threads)
+    oracle.set_threads(threads)
     nq = sample
     tp = tok_indptr[: nq + 1].astype(np.int32)
     tr = terms[: tp[-1]]

@@ -71,12 +71,15 @@ def lib() -> ctypes.CDLL:
                                               ctypes.c_int32, ctypes.c_int32, ctypes.c_int32,
                                               ctypes.c_int, ctypes.c_int, c_f, c_i64, c_i32]
         L.oracle_num_threads.restype = ctypes.c_int
+        L.oracle_set_threads.restype = None
+        L.oracle_set_threads.argtypes = [ctypes.c_int]
         _lib = L
     return _lib
 
 
 def set_threads(n: int) -> None:
-    os.environ["OMP_NUM_THREADS"] = str(int(n))
+    os.environ["OMP_NUM_THREADS"] = str(int(n))      # for a runtime that has not started yet
+    lib().oracle_set_threads(int(n))                  # and for one that has
 
 
 def _p(a: np.ndarray, ty):

@@ -346,3 +346,12 @@ int oracle_num_threads(void) {
   return 1;
 #endif
 }
+
+/* Thread count of the following calls (OMP_NUM_THREADS is only read when the OpenMP runtime starts). */
+void oracle_set_threads(int n) {
+#ifdef _OPENMP
+  if (n > 0) omp_set_num_threads(n);
+#else
+  (void)n;
+#endif
+}
