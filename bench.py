@@ -84,6 +84,7 @@ def parse_args():
                          "local top-K' + one all_gather + merge (what a corpus that does not fit one GPU needs: "
                          "--workload knn100m always uses it).  auto = replicate when corpus + shadow fit in 1/3 of HBM; "
                          "the JSON line then carries a shorter rowshard measurement of the same batch as well")
+    ap.add_argument("--bm25-mode", type=int, default=-1, help="rse_set_bm25_mode override (see include/rse.h); -1 = library default")
     ap.add_argument("--tc-mode", type=int, default=-1, help="rse_set_tc_mode override (see include/rse.h); -1 = library default")
     return ap.parse_args()
 
@@ -374,6 +375,8 @@ def run_b200(args, rank, world, local_rank):
     idx = _lib.Index(local_rank)
     if args.tc_mode >= 0:
         idx.set_tc_mode(args.tc_mode)
+    if args.bm25_mode >= 0:
+        idx.set_bm25_mode(args.bm25_mode)
     stream = torch.cuda.current_stream(device)
     idx.set_stream(stream.cuda_stream)
     shard = se.emb[lo:hi]
