@@ -1573,18 +1573,11 @@ int hybrid_run_impl(rse_index* h, int mode, double param, int tie_mode, int limi
   rc = aggregate(h, static_cast<const long long*>(h->cand.p), nq, limit, kprime, static_cast<float*>(h->o_dist.p),
                  static_cast<long long*>(h->o_rowid.p), static_cast<int*>(h->o_movie.p), static_cast<int*>(h->o_count.p));
   if (rc != RSE_OK) return rc;
-  // dense index → movies.id
-  ENSURE(h->f_bid, 8 * n); ENSURE(h->f_sid, 8 * n);
-  const unsigned int gblocks = static_cast<unsigned int>((n + 255) / 256);
-  gather_ids_kernel<<<gblocks, 256, 0, h->stream>>>(static_cast<const int*>(h->b_doc.p), static_cast<int64_t>(n),
-                                                    h->doc_ids, h->n_doc_ids, static_cast<long long*>(h->f_bid.p));
-  LAUNCHED(h);
-  gather_ids_kernel<<<gblocks, 256, 0, h->stream>>>(static_cast<const int*>(h->o_movie.p), static_cast<int64_t>(n),
-                                                    h->movie_ids, h->n_movie_ids, static_cast<long long*>(h->f_sid.p));
-  LAUNCHED(h);
-  FuseIn in{static_cast<const long long*>(h->f_bid.p), static_cast<const double*>(h->b_score.p),
-            static_cast<const int*>(h->b_count.p),     static_cast<const long long*>(h->f_sid.p),
-            static_cast<const float*>(h->o_dist.p),    static_cast<const int*>(h->o_count.p), nullptr};
+  // dense index → movies.id happens inside the fusion kernel (two gather launches less)
+  FuseIn in{nullptr, static_cast<const double*>(h->b_score.p), static_cast<const int*>(h->b_count.p), nullptr,
+            static_cast<const float*>(h->o_dist.p), static_cast<const int*>(h->o_count.p), nullptr};
+  in.bm25_idx = static_cast<const int*>(h->b_doc.p); in.bm25_table = h->doc_ids; in.bm25_table_n = h->n_doc_ids;
+  in.sem_idx = static_cast<const int*>(h->o_movie.p); in.sem_table = h->movie_ids; in.sem_table_n = h->n_movie_ids;
   return fuse_launch(h, mode, param, tie_mode, nq, limit, in, o_id, o_sc, o_a, o_b, o_cnt);
 }
 
