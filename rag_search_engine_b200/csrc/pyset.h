@@ -39,7 +39,7 @@ constexpr int kPySetPerturbShift = 5;
 RSE_HD int64_t py_hash_int(int64_t v) {
   const uint64_t P = (1ull << 61) - 1ull;
   uint64_t mag = v < 0 ? (0ull - static_cast<uint64_t>(v)) : static_cast<uint64_t>(v);
-  uint64_t m = mag % P;
+  uint64_t m = mag < P ? mag : mag % P;        // ids are far below 2**61: skip the 64-bit division
   int64_t h = v < 0 ? -static_cast<int64_t>(m) : static_cast<int64_t>(m);
   if (h == -1) h = -2;
   return h;
