@@ -521,6 +521,19 @@ def run_b200(args, rank, world, local_rank):
     sharded_ok = None
     replicas_ok = None
     rowshard_extra = None
+    mismatch = None
+    corpora_identical = None
+    if world > 1:
+        # every rank generates the corpus on its own GPU from the same seeds: verify they really are the same bits
+        def csum(t):
+            t = t.contiguous().view(torch.int32) if t.dtype == torch.float32 else t.to(torch.int64)
+            return int(t.to(torch.int64).sum().item())
+        sig = [csum(se.emb), csum(se.movie_of_chunk), csum(torch.as_tensor(np.asarray(bm.doc_idx).astype(np.int64))),
+               csum(torch.as_tensor(np.asarray(bm.tf).astype(np.int64))), int(np.asarray(tok_indptr).sum()),
+               int(np.asarray(terms).astype(np.int64).sum()), csum(torch.as_tensor(Qn).view(torch.int32))]
+        sigs = [None] * world
+        dist.all_gather_object(sigs, sig)
+        corpora_identical = all(x == sigs[0] for x in sigs)
     if world > 1:
         # rank 0 generated the whole corpus: check the N-GPU result against a single-handle run of the whole batch
         if rowshard:
@@ -543,6 +556,15 @@ def run_b200(args, rank, world, local_rank):
                 chk = idx
             oid, osc, oa, ob, oc = chk.hybrid(mode, param, limit, Qn, tok_indptr, terms)
             ok = bool((got[0] == oid).all() and (got[1] == osc).all() and (got[2] == oc).all())
+            if not ok:
+                badq = np.nonzero((got[0] != oid).any(axis=1) | (got[1] != osc).any(axis=1) | (got[2] != oc))[0]
+                mismatch = {"queries": int(len(badq)), "first": [int(x) for x in badq[:8]],
+                            "ids_differ": int((got[0] != oid).any(axis=1).sum()),
+                            "scores_differ": int((got[1] != osc).any(axis=1).sum()),
+                            "example": {"q": int(badq[0]), "got_id": [int(x) for x in got[0][badq[0]]],
+                                        "want_id": [int(x) for x in oid[badq[0]]],
+                                        "got_score": [float(x) for x in got[1][badq[0]]],
+                                        "want_score": [float(x) for x in osc[badq[0]]]}}
             if rowshard:
                 sharded_ok = ok
                 chk.close()
@@ -609,7 +631,8 @@ def run_b200(args, rank, world, local_rank):
             "scaling": (args.scaling if world > 1 else "weak"), "vs_baseline": None,
             "dtype": "f16 tensor-core filter + exact f32 re-score (f64 tail), f64 BM25/fusion", "data": "synthetic",
             "config": config_dict(args, info, world, par), "roofline": roofline, "clocks": clocks, "e2e": e2e,
-            "gpu_launches": launches, "sharded_matches_single_gpu": sharded_ok, "replicas_match_single_gpu": replicas_ok,
+            "gpu_launches": launches, "sharded_matches_single_gpu": sharded_ok, "replicas_match_single_gpu": replicas_ok, "mismatch": mismatch,
+            "corpora_identical_across_ranks": corpora_identical,
             "rowshard": rowshard_extra, "knn_batch1": knn1, "knn_batch1024": knn1k, "postings_touched_per_step": postings_touched(bm, tok_indptr, terms)}
 
     if world == 1 and not args.no_cpu_baseline:

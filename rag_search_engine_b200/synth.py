@@ -60,16 +60,29 @@ def synth_embeddings(n_movies: int, seed: int = 1234, dim: int = 384, mean_desc_
     n_near = int(C * neardup_frac)
     if C > 1 and (n_dup or n_near):
         idx = torch.randint(0, C, (2, n_dup + n_near), generator=g)
-        src = idx[0].to(dev)
-        dst = idx[1].to(dev)
-        emb[dst[:n_dup]] = emb[src[:n_dup]]
+        col_all = torch.randint(0, dim, (n_near,), generator=g) if n_near else None
+
+        def first_occurrence(d: torch.Tensor) -> torch.Tensor:
+            """Positions of the first occurrence of every destination row.  An indexed assignment with repeated
+            destinations is nondeterministic on CUDA (whichever thread writes last wins), which made the corpus
+            differ between runs and between the GPUs of a multi-GPU bench in ~1000 rows."""
+            _, first = np.unique(d.numpy(), return_index=True)
+            return torch.from_numpy(np.sort(first))
+
+        keep = first_occurrence(idx[1, :n_dup])
+        src = idx[0, :n_dup][keep].to(dev)
+        dst = idx[1, :n_dup][keep].to(dev)
+        emb[dst] = emb[src]
         if n_near:
-            rows = emb[src[n_dup:]].clone()
-            col = torch.randint(0, dim, (n_near,), generator=g).to(dev)
-            ar = torch.arange(n_near, device=dev)
+            keep = first_occurrence(idx[1, n_dup:])
+            src = idx[0, n_dup:][keep].to(dev)
+            dst = idx[1, n_dup:][keep].to(dev)
+            col = col_all[keep].to(dev)
+            rows = emb[src].clone()
+            ar = torch.arange(rows.shape[0], device=dev)
             v = rows[ar, col]
             rows[ar, col] = torch.nextafter(v, torch.full_like(v, 2.0))
-            emb[dst[n_dup:]] = rows
+            emb[dst] = rows
     return SynthEmbeddings(emb=emb, movie_of_chunk=movie_of_chunk.to(dev), movie_ids=synth_movie_ids(n_movies, seed),
                            n_movies=n_movies)
 
