@@ -123,9 +123,10 @@ class ClockSampler:
                         self.reasons.add(k)
             except Exception:
                 pass
+        period = float(os.environ.get("RSE_CLOCK_POLL_MS", "1")) * 1e-3
         while not self.stop_flag:
             once()
-            time.sleep(0.001)
+            time.sleep(period)
 
     def start(self):
         try:

@@ -411,8 +411,9 @@ constexpr int kBsMaxGroups = 32;                  // groups per query bm25_fx_fi
 constexpr unsigned int kBsRangeCap = 256;         // documents that may cross theta inside one range
 constexpr int kBsFinalCap = 64;                   // finalists (k + ties) ranked exactly
 
+// out8 (optional): the 8-byte stream bm25_fx_kernel reads, {doc, round(w * wq_scale)} — see the K6'' header
 __global__ void bm25_weight_kernel(const uint2* __restrict__ post, const double* __restrict__ normk, int64_t n,
-                                   double k1p1, Post16* __restrict__ out) {
+                                   double k1p1, Post16* __restrict__ out, uint2* __restrict__ out8, double wq_scale) {
   const int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
   if (i >= n) return;
   const uint2 e = post[i];
@@ -421,6 +422,7 @@ __global__ void bm25_weight_kernel(const uint2* __restrict__ post, const double*
   o.doc = e.x; o.tf = e.y;
   o.w = __ddiv_rn(__dmul_rn(tfd, k1p1), __dadd_rn(tfd, normk[e.x]));
   out[i] = o;
+  if (out8) out8[i] = make_uint2(e.x, __double2uint_rn(__dmul_rn(o.w, wq_scale)));
 }
 
 constexpr int bs_smem_bytes() {
@@ -665,17 +667,20 @@ bm25_stream_kernel(const int64_t* __restrict__ indptr, const Post16* __restrict_
 // The order only matters for the low bits of a sum.  This kernel accumulates idf*w in 32-bit FIXED POINT with
 // native shared-memory integer atomics (ATOMS.ADD; 64-bit and double shared atomics are CAS loops on sm_100).  The
 // scale is the largest power of two that keeps (k1+1)*log(N+2)*16 below 2^31 (2^21 for the default k1: steps of
-// 4.8e-7).  The sum is exact in that format, independent of the order, and within 8 units (each of <= 16 terms is
-// rounded once, <= 0.5 unit) of the reference's double sum times the scale — so all the
-// token slices of a range are cut into 32-posting items that the warps take round robin with NO barrier between
-// tokens.  Everything decided on these sums carries a margin of kFxMargin units; the finalists (k plus whatever
+// 4.8e-7).  The kernel is HBM-bound on the posting stream, so it reads an 8-BYTE posting {doc, wq} instead of the
+// 16-byte {doc, tf, double w}: wq = round(w * wq_scale) with wq_scale the largest power of two keeping
+// (k1+1)*wq_scale <= 2^31, i.e. w is known to 2^-32..2^-31 absolute — 1/16 unit of the sum at most.  The sum is
+// exact in that format, independent of the order, and within 9 units (each of <= 16 terms: <= 0.5 unit from its
+// one rounding + <= 1/16 unit from wq) of the reference's double sum times the scale — so all the token slices
+// of a range are cut into 64-posting items (a lane loads one aligned 16-byte PAIR) that the warps take round
+// robin with NO barrier between tokens.  Everything decided on these sums carries a margin of kFxMargin units; the finalists (k plus whatever
 // lies within the margin of the k-th) are RE-SCORED in bm25_fx_finish_kernel with the reference's own
 // expression in query-token order — one thread per (document, token) finds the posting by binary search — which
 // also yields the reference's tie key (first token holding the document).  Scores, order and ties are therefore
 // bit-identical to the general kernel; queries it cannot finish are flagged for it exactly like before.
-constexpr unsigned int kFxMargin = 40u;               // > 2 x (8 units of accumulated rounding + the double sum's own)
+constexpr unsigned int kFxMargin = 40u;               // > 2 x (9 units of accumulated rounding + the double sum's own)
 constexpr int kFxFinalCap = 48;
-constexpr unsigned int kFxMaxItems = 3072;            // 32-posting items per range (98 k postings; beyond: general kernel)
+constexpr unsigned int kFxMaxItems = 3072;            // 64-posting items per range (196 k postings; beyond: general kernel)
 constexpr int kFxRescoreCap = 96;
 
 __host__ __device__ constexpr int fx_smem_bytes(int rpg) {
@@ -684,7 +689,7 @@ __host__ __device__ constexpr int fx_smem_bytes(int rpg) {
 
 // fin: [nq][ng][kFxFinalCap] {fixed-point sum, doc}; fin_cnt: [nq][ng]
 __global__ void __launch_bounds__(kBsThreads, 3)
-bm25_fx_kernel(const int64_t* __restrict__ indptr, const Post16* __restrict__ post, const uint32_t* __restrict__ roff,
+bm25_fx_kernel(const int64_t* __restrict__ indptr, const uint2* __restrict__ post8, const uint32_t* __restrict__ roff,
                int nr, const int32_t* __restrict__ tok_indptr, const int32_t* __restrict__ term_rows,
                const double* __restrict__ tok_idf, double scale, int q0, int k, int rpg, int ng,
                uint2* __restrict__ fin, int* __restrict__ fin_cnt, int* __restrict__ status) {
@@ -695,7 +700,7 @@ bm25_fx_kernel(const int64_t* __restrict__ indptr, const Post16* __restrict__ po
   uint2* s_cand0 = reinterpret_cast<uint2*>(smem_raw + kBmRange * 4 + ((kBsMaxTok * ostride * 4 + 15) & ~15));
   uint2* s_cand1 = s_cand0 + kBsCandCap;                                               // {sum, doc}
   __shared__ long long s_base[kBsMaxTok];
-  __shared__ double s_idfx[kBsMaxTok];                                                 // idf * scale (exact: a power of two)
+  __shared__ double s_idfx[kBsMaxTok];                                                 // idf * scale / wq_scale (exact: powers of two)
   __shared__ int s_term[kBsMaxTok];
   __shared__ unsigned int s_pre[kBsMaxTok + 1];
   __shared__ unsigned int s_ncand, s_nkept, s_nrc;
@@ -769,13 +774,18 @@ bm25_fx_kernel(const int64_t* __restrict__ indptr, const Post16* __restrict__ po
 
   for (int r = r0; r < r1; ++r) {
     const int jr = r - r0;
-    // items of this range: slice t contributes ceil(n_t / 32) items of 32 postings (one per lane).
+    // items of this range: slice t contributes items of 32 aligned posting PAIRS (one 16-byte load per lane).
     // The barrier keeps warp 0 from overwriting s_pre while a slower warp still reads the previous range's item
     // count (an empty range `continue`s without passing any other barrier).
     __syncthreads();
     if (warp == 0) {
       unsigned int c = 0u;
-      if (lane < ntok) c = (s_off[lane * ostride + jr + 1] - s_off[lane * ostride + jr] + 31u) >> 5;
+      if (lane < ntok) {
+        const uint32_t a = s_off[lane * ostride + jr];
+        const uint32_t sn = s_off[lane * ostride + jr + 1] - a;
+        const uint32_t odd = static_cast<uint32_t>((s_base[lane] + a) & 1);     // pairs start at an even posting index
+        c = sn ? (sn + odd + 63u) >> 6 : 0u;
+      }
       unsigned int incl = c;
 #pragma unroll
       for (int off = 1; off < 32; off <<= 1) {
@@ -810,25 +820,33 @@ bm25_fx_kernel(const int64_t* __restrict__ indptr, const Post16* __restrict__ po
     __syncthreads();
 
     auto item_load = [&](unsigned int item, uint4& e, double& idfx) {
-      e = make_uint4(0xFFFFFFFFu, 0u, 0u, 0u);
+      e = make_uint4(0xFFFFFFFFu, 0u, 0xFFFFFFFFu, 0u);   // {doc, wq, doc, wq}; doc = ~0: nothing to add
       idfx = 0.0;
       if (item >= n_items) return;
       const unsigned int d = s_itab[item];
       const int t = static_cast<int>(d >> 8);
-      const unsigned int i = (d & 0xFFu) * 32u + lane;
+      const long long sb = s_sbase[t], se = sb + s_sn[t];
+      const long long j0 = (sb & ~1LL) + (d & 0xFFu) * 64u + 2u * lane;
       idfx = s_idfx[t];
-      if (i < s_sn[t]) e = __ldg(reinterpret_cast<const uint4*>(post + s_sbase[t] + i));
+      if (j0 + 1 >= sb && j0 < se) {                      // the pair overlaps the slice (the stream is padded by one pair)
+        e = __ldg(reinterpret_cast<const uint4*>(post8 + j0));
+        if (j0 < sb) e.x = 0xFFFFFFFFu;
+        if (j0 + 1 >= se) e.z = 0xFFFFFFFFu;
+      }
     };
-    auto item_apply = [&](const uint4& e, double idfx) {
-      if (e.x == 0xFFFFFFFFu) return;
-      const double w = __hiloint2double(static_cast<int>(e.w), static_cast<int>(e.z));
-      const unsigned int add = __double2uint_rn(__dmul_rn(idfx, w));
-      const uint32_t l = e.x - doc_base;
+    auto apply_one = [&](uint32_t doc, uint32_t wq, double idfx) {
+      if (doc == 0xFFFFFFFFu) return;
+      const unsigned int add = __double2uint_rn(__dmul_rn(idfx, __uint2double_rn(wq)));
+      const uint32_t l = doc - doc_base;
       const unsigned int old = atomicAdd(&acc[l], add);
       if (old < cross && old + add >= cross) {            // just reached theta (sums only grow): note the document once
         const unsigned int slot = atomicAdd(&s_nrc, 1u);
         if (slot < kBsRangeCap) s_rc[slot] = static_cast<unsigned short>(l);
       }
+    };
+    auto item_apply = [&](const uint4& e, double idfx) {
+      apply_one(e.x, e.y, idfx);
+      apply_one(e.z, e.w, idfx);
     };
     {
       // two loads in flight per lane, buffers alternate by name

@@ -81,6 +81,11 @@ struct rse_index {
   int ov_nq = 0, ov_limit = 0;
   double ov_k1 = 0.0, ov_b = 0.0;
   bool overlap_enabled = true;
+  // RSE_TIMELINE=1: timed events at the stage boundaries of a hybrid step on both streams, printed (ms since the
+  // step's first event) to stderr by rse_hybrid_fetch — a development aid, off by default
+  bool timeline = false;
+  cudaEvent_t tl[8] = {};
+  bool tl_set[8] = {};
   int tc_filter_kind = 2;          // 2 = knn_tc3_kernel (fp16 normalised shadow, queries resident in shared memory; default),
                                    // 0 = knn_tc_kernel<1> (TF32, queries streamed), 1 = knn_tc2_filter_kernel (TF32, queries in TMEM)
   DevBuf tc_q, tc_thr, tc_isb, tc_rows, tc_cnt, tc_keys, tc_status;
@@ -116,6 +121,8 @@ struct rse_index {
   double* normk = nullptr;
   double normk_k1 = NAN, normk_b = NAN;
   Post16* post16 = nullptr;        // {doc, tf, w}: postings with the (k1, b)-dependent weight precomputed (bm25_stream_kernel)
+  uint2* post8 = nullptr;          // {doc, round(w * wq_scale)}: the 8-byte stream of bm25_fx_kernel (padded by one pair)
+  double wq_scale = 0.0;
   double w_k1 = NAN, w_b = NAN;
   DevBuf b_shi, b_slo, b_scnt, b_status, b_flagged;
   int bm25_mode = 0;               // 0 = fixed-point streaming kernel (default), 1 = exact-order streaming kernel, 2 = general kernel only
@@ -197,7 +204,7 @@ void release_embeddings(rse_index* h) {
 }
 
 void release_bm25(rse_index* h) {
-  free_ptr(h->indptr); free_ptr(h->post); free_ptr(h->dl); free_ptr(h->roff); free_ptr(h->normk); free_ptr(h->post16);
+  free_ptr(h->indptr); free_ptr(h->post); free_ptr(h->dl); free_ptr(h->roff); free_ptr(h->normk); free_ptr(h->post16); free_ptr(h->post8);
   h->w_k1 = NAN; h->w_b = NAN;
   h->df_host.clear();
   h->n_terms = h->n_postings = h->n_docs = h->n_movies = 0;
@@ -421,6 +428,29 @@ int ensure_shadow(rse_index* h) {
 
 extern "C" int bm25_run_fwd(rse_index* h, int nq, int k, double k1, double b);   // = bm25_run (defined further down)
 
+enum { kTlStart = 0, kTlPrefilter, kTlFilterEnd, kTlKnnEnd, kTlBm25Start, kTlBm25End, kTlStepEnd, kTlCount };
+
+void tl_mark(rse_index* h, int which, cudaStream_t s) {
+  if (!h->timeline) return;
+  if (!h->tl[which] && cudaEventCreate(&h->tl[which]) != cudaSuccess) return;
+  h->tl_set[which] = cudaEventRecord(h->tl[which], s) == cudaSuccess;
+}
+
+void tl_print(rse_index* h) {
+  if (!h->timeline || !h->tl_set[kTlStart]) return;
+  static const char* names[kTlCount] = {"start", "prefilter", "filter_end", "knn_end", "bm25_start", "bm25_end", "step_end"};
+  std::fprintf(stderr, "[rse timeline]");
+  for (int i = 1; i < kTlCount; ++i) {
+    float ms = 0.f;
+    if (h->tl_set[i] && cudaEventSynchronize(h->tl[i]) == cudaSuccess &&
+        cudaEventElapsedTime(&ms, h->tl[kTlStart], h->tl[i]) == cudaSuccess)
+      std::fprintf(stderr, " %s=%.3f", names[i], ms);
+    h->tl_set[i] = false;
+  }
+  std::fprintf(stderr, "\n");
+  h->tl_set[kTlStart] = false;
+}
+
 // Enqueue the pending BM25 batch of a hybrid step on the second stream, ordered behind `after` (an event on the main
 // stream).  Called right after the filter kernel has been launched, so the filter's CTAs are placed first and BM25
 // fills what is left of every SM.
@@ -434,11 +464,13 @@ int enqueue_bm25_overlapped(rse_index* h, cudaEvent_t after) {
     CK(cudaEventCreateWithFlags(&h->ev_bm25_done, cudaEventDisableTiming));
   }
   CK(cudaStreamWaitEvent(h->stream_b, after, 0));
+  tl_mark(h, kTlBm25Start, h->stream_b);
   cudaStream_t main_stream = h->stream;
   h->stream = h->stream_b;
   const int rc = bm25_run_fwd(h, h->ov_nq, h->ov_limit, h->ov_k1, h->ov_b);
   h->stream = main_stream;
   if (rc != RSE_OK) return rc;
+  tl_mark(h, kTlBm25End, h->stream_b);
   CK(cudaEventRecord(h->ev_bm25_done, h->stream_b));
   return RSE_OK;
 }
@@ -531,10 +563,12 @@ int knn_tc3_block(rse_index* h, const float* q_dev, const double* sb, int nqb, i
     if (!h->ev_prefilter) CK(cudaEventCreateWithFlags(&h->ev_prefilter, cudaEventDisableTiming));
     CK(cudaEventRecord(h->ev_prefilter, h->stream));
   }
+  tl_mark(h, kTlPrefilter, h->stream);
   knn_tc3_kernel<1><<<grid_f, kT3Threads, kT3SmemBytes, h->stream>>>(
       h->tmap_a16, h->tmap_q16, n_tiles, 1, nqb, thr, nullptr, 0, static_cast<uint2*>(h->tc_rows.p),
       static_cast<unsigned int*>(h->tc_cnt.p), kTcCandCap);
   LAUNCHED(h);
+  tl_mark(h, kTlFilterEnd, h->stream);
   {
     int rc = enqueue_bm25_overlapped(h, h->ev_prefilter);     // no-op unless a hybrid step asked for it
     if (rc != RSE_OK) return rc;
@@ -833,6 +867,7 @@ int rse_create(int32_t device, rse_index** out) {
   for (auto& ev : h->ev) cudaEventCreate(&ev);
   // diagnostics: RSE_NO_OVERLAP=1 keeps the hybrid step's BM25 on the caller's stream (no second stream)
   if (const char* ev = std::getenv("RSE_NO_OVERLAP")) h->overlap_enabled = !(ev[0] == '1');
+  if (const char* ev = std::getenv("RSE_TIMELINE")) h->timeline = ev[0] == '1';
   *out = h;
   return RSE_OK;
 }
@@ -856,6 +891,7 @@ void rse_destroy(rse_index* h) {
   free_buf(h->f_pack);
   if (h->ev_status) cudaEventDestroy(h->ev_status);
   if (h->ev_stage) cudaEventDestroy(h->ev_stage);
+  for (cudaEvent_t e : h->tl) if (e) cudaEventDestroy(e);
   if (h->ev_prefilter) cudaEventDestroy(h->ev_prefilter);
   if (h->ev_bm25_done) cudaEventDestroy(h->ev_bm25_done);
   if (h->stream_b) cudaStreamDestroy(h->stream_b);
@@ -1246,7 +1282,7 @@ int bm25_run(rse_index* h, int nq, int k, double k1, double b) {
   // fixed-point sums must stay below 2^31: idf <= log(N + 2), w < k1 + 1, <= 16 tokens; the scale is the largest
   // power of two that allows (2^21 for the default k1), and the path needs at least 2^12
   double fx_scale = 0.0;
-  if (stream && h->bm25_mode == 0 && k1 >= 0.0) {
+  if (stream && h->bm25_mode == 0 && k1 >= 0.0 && b >= 0.0 && b <= 1.0) {      // 0 < w <= k1 + 1 needs normk >= 0
     const double max_sum = (k1 + 1.0) * std::log(static_cast<double>(h->n_movies) + 2.0) * 16.0 + 1.0;
     int e = 0;
     std::frexp(max_sum, &e);                               // max_sum < 2^e
@@ -1257,9 +1293,17 @@ int bm25_run(rse_index* h, int nq, int k, double k1, double b) {
   if (stream) {
     if (!(h->w_k1 == k1 && h->w_b == b)) {
       if (!h->post16) CK(cudaMalloc(&h->post16, sizeof(Post16) * static_cast<size_t>(h->n_postings)));
+      // compact stream of the fixed-point kernel: wq_scale = largest power of two with (k1 + 1) * wq_scale <= 2^31
+      h->wq_scale = 0.0;
+      if (k1 >= 0.0 && b >= 0.0 && b <= 1.0 && k1p1 < 1048576.0) {
+        int e = 0;
+        const double m = std::frexp(k1p1, &e);                 // k1p1 = m * 2^e, 0.5 <= m < 1
+        h->wq_scale = std::ldexp(1.0, m == 0.5 ? 32 - e : 31 - e);
+        if (!h->post8) CK(cudaMalloc(&h->post8, sizeof(uint2) * (static_cast<size_t>(h->n_postings) + 2)));
+      }
       const int threads = 256;
       bm25_weight_kernel<<<static_cast<unsigned int>((h->n_postings + threads - 1) / threads), threads, 0, h->stream>>>(
-          h->post, h->normk, h->n_postings, k1p1, h->post16);
+          h->post, h->normk, h->n_postings, k1p1, h->post16, h->wq_scale > 0.0 ? h->post8 : nullptr, h->wq_scale);
       LAUNCHED(h);
       h->w_k1 = k1; h->w_b = b;
     }
@@ -1306,9 +1350,9 @@ int bm25_run(rse_index* h, int nq, int k, double k1, double b) {
       status = static_cast<int*>(h->b_status.p);
       dim3 sgrid(ng, nc);
       bm25_fx_kernel<<<sgrid, kBsThreads, fx_smem_bytes(rpg), h->stream>>>(
-          h->indptr, h->post16, h->roff, h->nr, static_cast<const int32_t*>(h->b_tokptr.p),
-          static_cast<const int32_t*>(h->b_terms.p), static_cast<const double*>(h->b_idf.p), fx_scale, q0, k, rpg, ng, fin,
-          fcnt, status);
+          h->indptr, h->post8, h->roff, h->nr, static_cast<const int32_t*>(h->b_tokptr.p),
+          static_cast<const int32_t*>(h->b_terms.p), static_cast<const double*>(h->b_idf.p), fx_scale / h->wq_scale, q0, k,
+          rpg, ng, fin, fcnt, status);
       LAUNCHED(h);
       bm25_fx_finish_kernel<<<nc, kBmThreads, 0, h->stream>>>(
           fin, fcnt, ng, status, h->indptr, h->post16, h->roff, h->nr, static_cast<const int32_t*>(h->b_tokptr.p),
@@ -1556,6 +1600,7 @@ int hybrid_run_impl(rse_index* h, int mode, double param, int tie_mode, int limi
     // ... and when the KNN takes the tensor-core path, on a second stream UNDERNEATH the filter pass: the filter
     // kernel keeps one 178 KB CTA per SM busy on the tensor pipe at ~20 % issue utilisation, and one BM25 CTA
     // (38 KB, 512 threads) fits beside it.
+    tl_mark(h, kTlStart, h->stream);
     h->bm25_overlap_pending = h->overlap_enabled;
     h->ov_nq = nq; h->ov_limit = limit; h->ov_k1 = k1; h->ov_b = b;
     rc = knn_local_begin(h, static_cast<const float*>(h->q_dev.p), nq, kprime, static_cast<long long*>(h->cand.p));
@@ -1563,11 +1608,14 @@ int hybrid_run_impl(rse_index* h, int mode, double param, int tie_mode, int limi
     const bool overlapped = h->overlap_enabled && !h->bm25_overlap_pending;   // the filter launch consumed the request
     h->bm25_overlap_pending = false;
     if (!overlapped) {
+      tl_mark(h, kTlBm25Start, h->stream);
       rc = bm25_run(h, nq, limit, k1, b);
       if (rc != RSE_OK) return rc;
+      tl_mark(h, kTlBm25End, h->stream);
     }
     rc = knn_local_finish(h);
     if (rc != RSE_OK) return rc;
+    tl_mark(h, kTlKnnEnd, h->stream);
     if (overlapped) CK(cudaStreamWaitEvent(h->stream, h->ev_bm25_done, 0));
   }
   rc = aggregate(h, static_cast<const long long*>(h->cand.p), nq, limit, kprime, static_cast<float*>(h->o_dist.p),
@@ -1578,7 +1626,9 @@ int hybrid_run_impl(rse_index* h, int mode, double param, int tie_mode, int limi
             static_cast<const float*>(h->o_dist.p), static_cast<const int*>(h->o_count.p), nullptr};
   in.bm25_idx = static_cast<const int*>(h->b_doc.p); in.bm25_table = h->doc_ids; in.bm25_table_n = h->n_doc_ids;
   in.sem_idx = static_cast<const int*>(h->o_movie.p); in.sem_table = h->movie_ids; in.sem_table_n = h->n_movie_ids;
-  return fuse_launch(h, mode, param, tie_mode, nq, limit, in, o_id, o_sc, o_a, o_b, o_cnt);
+  rc = fuse_launch(h, mode, param, tie_mode, nq, limit, in, o_id, o_sc, o_a, o_b, o_cnt);
+  tl_mark(h, kTlStepEnd, h->stream);
+  return rc;
 }
 
 }  // namespace
@@ -1630,6 +1680,7 @@ int rse_hybrid_fetch(rse_index* h, int32_t limit, int64_t* out_id, double* out_s
   }
   CK(cudaMemcpyAsync(h->pin_out, h->f_pack.p, bytes, cudaMemcpyDeviceToHost, h->stream));
   CK(cudaStreamSynchronize(h->stream));
+  tl_print(h);
   std::memcpy(out_id, h->pin_out, 8 * n);
   std::memcpy(out_score, h->pin_out + 8 * n, 8 * n);
   std::memcpy(out_a, h->pin_out + 16 * n, 8 * n);

@@ -261,7 +261,10 @@ def test_bm25_modes_agree_with_oracle(fresh_index, mode):
     tok_indptr, terms = synth.synth_token_queries(bm, 400, seed=22)
     fresh_index.set_bm25_mode(mode)
     fresh_index.load_bm25(bm.indptr, bm.doc_idx, bm.tf, bm.df, bm.dl, bm.n_movies, bm.avgdl)
-    for k, k1, b in [(10, 1.5, 0.75), (32, 1.2, 0.5), (5, 3.0, 1.0)]:
+    # k1 + 1 an exact power of two (1.0, 3.0, 0.0) is the edge of the 8-byte posting's weight scale; b = 0 makes
+    # every normk equal; k1 = 0 gives w == k1 + 1 for every posting; b > 1 leaves the fixed-point path
+    for k, k1, b in [(10, 1.5, 0.75), (32, 1.2, 0.5), (5, 3.0, 1.0), (10, 1.0, 0.75), (10, 0.0, 0.75), (7, 2.0, 0.0),
+                     (10, 1.5, 1.25), (10, 100.0, 0.3)]:
         sc, dc, cnt = fresh_index.bm25(tok_indptr, terms, k, k1, b)
         osc, odc, ocnt = oracle.bm25_batch(bm.indptr, bm.doc_idx, bm.tf, bm.df, bm.dl, bm.n_movies, bm.avgdl,
                                            tok_indptr, terms, k, k1, b)
