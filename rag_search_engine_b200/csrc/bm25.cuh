@@ -680,7 +680,6 @@ bm25_stream_kernel(const int64_t* __restrict__ indptr, const Post16* __restrict_
 // bit-identical to the general kernel; queries it cannot finish are flagged for it exactly like before.
 constexpr unsigned int kFxMargin = 40u;               // > 2 x (9 units of accumulated rounding + the double sum's own)
 constexpr int kFxFinalCap = 48;
-constexpr unsigned int kFxMaxItems = 3072;            // 64-posting items per range (196 k postings; beyond: general kernel)
 constexpr int kFxRescoreCap = 96;
 
 __host__ __device__ constexpr int fx_smem_bytes(int rpg) {
@@ -702,13 +701,8 @@ bm25_fx_kernel(const int64_t* __restrict__ indptr, const uint2* __restrict__ pos
   __shared__ long long s_base[kBsMaxTok];
   __shared__ double s_idfx[kBsMaxTok];                                                 // idf * scale / wq_scale (exact: powers of two)
   __shared__ int s_term[kBsMaxTok];
-  __shared__ unsigned int s_pre[kBsMaxTok + 1];
-  __shared__ unsigned int s_ncand, s_nkept, s_nrc;
+  __shared__ unsigned int s_ncand, s_nkept;
   __shared__ unsigned int s_min, s_tw;
-  __shared__ unsigned short s_rc[kBsRangeCap];
-  __shared__ unsigned short s_itab[kFxMaxItems];                                       // (token << 8) | chunk of every item of the range
-  __shared__ long long s_sbase[kBsMaxTok];                                             // first posting of token t's slice in this range
-  __shared__ unsigned int s_sn[kBsMaxTok];                                             // postings in that slice
 
   const int g = blockIdx.x;
   const int q = q0 + blockIdx.y;
@@ -727,7 +721,7 @@ bm25_fx_kernel(const int64_t* __restrict__ indptr, const uint2* __restrict__ pos
     s_base[threadIdx.x] = term >= 0 ? indptr[term] : 0;
     s_idfx[threadIdx.x] = tok_idf[t0 + threadIdx.x] * scale;
   }
-  if (threadIdx.x == 0) { s_ncand = 0u; s_nrc = 0u; }
+  if (threadIdx.x == 0) s_ncand = 0u;
   __syncthreads();
   for (int i = threadIdx.x; i < ntok * (nrg + 1); i += blockDim.x) {
     const int t = i / (nrg + 1), j = i - t * (nrg + 1);
@@ -772,85 +766,62 @@ bm25_fx_kernel(const int64_t* __restrict__ indptr, const uint2* __restrict__ pos
     __syncthreads();
   };
 
+  constexpr unsigned int kW = kBsThreads / 32;
+  constexpr int kVec = kBmRange / 4;                      // accumulators as uint4
   for (int r = r0; r < r1; ++r) {
     const int jr = r - r0;
-    // items of this range: slice t contributes items of 32 aligned posting PAIRS (one 16-byte load per lane).
-    // The barrier keeps warp 0 from overwriting s_pre while a slower warp still reads the previous range's item
-    // count (an empty range `continue`s without passing any other barrier).
-    __syncthreads();
-    if (warp == 0) {
-      unsigned int c = 0u;
-      if (lane < ntok) {
-        const uint32_t a = s_off[lane * ostride + jr];
-        const uint32_t sn = s_off[lane * ostride + jr + 1] - a;
-        const uint32_t odd = static_cast<uint32_t>((s_base[lane] + a) & 1);     // pairs start at an even posting index
-        c = sn ? (sn + odd + 63u) >> 6 : 0u;
-      }
-      unsigned int incl = c;
+    // Items of this range: slice t contributes items of 32 aligned posting PAIRS (one 16-byte load per lane).
+    // Every warp derives the same item prefix in registers (lane t owns token t): no shared item table, no
+    // barrier before the postings — the two barriers of a range are "sums complete" and "accumulators cleared".
+    long long sb = 0;
+    unsigned int sn = 0u, c = 0u;
+    if (lane < ntok) {
+      const uint32_t a = s_off[lane * ostride + jr];
+      sn = s_off[lane * ostride + jr + 1] - a;
+      sb = s_base[lane] + a;
+      c = sn ? (sn + static_cast<unsigned int>(sb & 1) + 63u) >> 6 : 0u;      // pairs start at an even posting index
+    }
+    unsigned int incl = c;
 #pragma unroll
-      for (int off = 1; off < 32; off <<= 1) {
-        const unsigned int o = __shfl_up_sync(0xFFFFFFFFu, incl, off);
-        if (lane >= off) incl += o;
-      }
-      if (lane < ntok) s_pre[lane] = incl - c;
-      if (lane == ntok - 1 || (ntok == 0 && lane == 0)) s_pre[ntok] = ntok ? incl : 0u;
+    for (int off = 1; off < 32; off <<= 1) {
+      const unsigned int o = __shfl_up_sync(0xFFFFFFFFu, incl, off);
+      if (lane >= off) incl += o;
     }
-    __syncthreads();
-    const unsigned int n_items = s_pre[ntok];
-    if (n_items == 0u) continue;                          // uniform
-    if (n_items > kFxMaxItems) {                          // uniform
-      if (threadIdx.x == 0) { status[q] = 1; fin_cnt[cbase] = 0; }
-      return;
-    }
+    const unsigned int n_items = __shfl_sync(0xFFFFFFFFu, incl, 31);
+    if (n_items == 0u) continue;                          // uniform (every warp computes the same prefix)
+    const unsigned int pre = incl - c;                    // first item of token `lane`
+    const unsigned int has = __ballot_sync(0xFFFFFFFFu, c != 0u);
     const uint32_t doc_base = static_cast<uint32_t>(r) * kBmRange;
-    const unsigned int cross = established ? theta : ~0u;
-    // item table, one THREAD per item: (token << 8) | chunk, so a warp fetches its item with three shared-memory
-    // loads (a warp-uniform search per item was half of the kernel's instructions, per-item offset arithmetic a
-    // fifth of what was left)
-    if (threadIdx.x < ntok) {
-      const uint32_t a = s_off[threadIdx.x * ostride + jr];
-      s_sbase[threadIdx.x] = s_base[threadIdx.x] + a;
-      s_sn[threadIdx.x] = s_off[threadIdx.x * ostride + jr + 1] - a;
-    }
-    for (unsigned int i = threadIdx.x; i < n_items; i += kBsThreads) {
-      int t = 0;
-      while (t + 1 < ntok && s_pre[t + 1] <= i) ++t;
-      s_itab[i] = static_cast<unsigned short>((t << 8) | (i - s_pre[t]));
-    }
-    __syncthreads();
+    const int sb_lo = static_cast<int>(static_cast<unsigned long long>(sb) & 0xFFFFFFFFull);
+    const int sb_hi = static_cast<int>(static_cast<unsigned long long>(sb) >> 32);
 
     auto item_load = [&](unsigned int item, uint4& e, double& idfx) {
       e = make_uint4(0xFFFFFFFFu, 0u, 0xFFFFFFFFu, 0u);   // {doc, wq, doc, wq}; doc = ~0: nothing to add
       idfx = 0.0;
-      if (item >= n_items) return;
-      const unsigned int d = s_itab[item];
-      const int t = static_cast<int>(d >> 8);
-      const long long sb = s_sbase[t], se = sb + s_sn[t];
-      const long long j0 = (sb & ~1LL) + (d & 0xFFu) * 64u + 2u * lane;
+      if (item >= n_items) return;                        // warp-uniform
+      // token of the item: the highest lane holding items whose first item is <= item
+      const unsigned int le = __ballot_sync(0xFFFFFFFFu, pre <= item) & has;
+      const int t = 31 - __clz(static_cast<int>(le));
+      const unsigned int chunk = item - __shfl_sync(0xFFFFFFFFu, pre, t);
+      const long long tsb = static_cast<long long>(
+          (static_cast<unsigned long long>(static_cast<unsigned int>(__shfl_sync(0xFFFFFFFFu, sb_hi, t))) << 32) |
+          static_cast<unsigned int>(__shfl_sync(0xFFFFFFFFu, sb_lo, t)));
+      const long long se = tsb + __shfl_sync(0xFFFFFFFFu, sn, t);
+      const long long j0 = (tsb & ~1LL) + chunk * 64u + 2u * lane;
       idfx = s_idfx[t];
-      if (j0 + 1 >= sb && j0 < se) {                      // the pair overlaps the slice (the stream is padded by one pair)
+      if (j0 + 1 >= tsb && j0 < se) {                     // the pair overlaps the slice (the stream is padded by one pair)
         e = __ldg(reinterpret_cast<const uint4*>(post8 + j0));
-        if (j0 < sb) e.x = 0xFFFFFFFFu;
+        if (j0 < tsb) e.x = 0xFFFFFFFFu;
         if (j0 + 1 >= se) e.z = 0xFFFFFFFFu;
       }
     };
-    auto apply_one = [&](uint32_t doc, uint32_t wq, double idfx) {
-      if (doc == 0xFFFFFFFFu) return;
-      const unsigned int add = __double2uint_rn(__dmul_rn(idfx, __uint2double_rn(wq)));
-      const uint32_t l = doc - doc_base;
-      const unsigned int old = atomicAdd(&acc[l], add);
-      if (old < cross && old + add >= cross) {            // just reached theta (sums only grow): note the document once
-        const unsigned int slot = atomicAdd(&s_nrc, 1u);
-        if (slot < kBsRangeCap) s_rc[slot] = static_cast<unsigned short>(l);
-      }
-    };
     auto item_apply = [&](const uint4& e, double idfx) {
-      apply_one(e.x, e.y, idfx);
-      apply_one(e.z, e.w, idfx);
+      // sums only grow and nothing reads them before the barrier: plain reductions, no returned value to wait for
+      if (e.x != 0xFFFFFFFFu) atomicAdd(&acc[e.x - doc_base], __double2uint_rn(__dmul_rn(idfx, __uint2double_rn(e.y))));
+      if (e.z != 0xFFFFFFFFu) atomicAdd(&acc[e.z - doc_base], __double2uint_rn(__dmul_rn(idfx, __uint2double_rn(e.w))));
     };
     {
       // two loads in flight per lane, buffers alternate by name
-      constexpr unsigned int kW = kBsThreads / 32;
       uint4 e0, e1;
       double f0, f1;
       unsigned int it = warp;
@@ -861,30 +832,17 @@ bm25_fx_kernel(const int64_t* __restrict__ indptr, const uint2* __restrict__ pos
         item_load(it + kW, e0, f0); item_apply(e1, f1); it += kW;
       }
     }
-    __syncthreads();
+    __syncthreads();                                      // the range's sums are complete
 
-    if (established) {
-      // the noted documents now hold their final sums
-      const unsigned int nrc = s_nrc;
-      if (nrc > kBsRangeCap) {                            // uniform
-        if (threadIdx.x == 0) { status[q] = 1; fin_cnt[cbase] = 0; }
-        return;
-      }
-      if (threadIdx.x < nrc) {
-        const uint32_t l = s_rc[threadIdx.x];
-        const unsigned int slot = atomicAdd(&s_ncand, 1u);
-        if (slot < kBsCandCap) cand[slot] = make_uint2(acc[l], doc_base + l);
-      }
-      __syncthreads();
-      uint4* a4 = reinterpret_cast<uint4*>(acc);
-      for (int i = threadIdx.x; i < kBmRange / 4; i += kBsThreads) a4[i] = make_uint4(0u, 0u, 0u, 0u);
-      if (threadIdx.x == 0) s_nrc = 0u;
-    } else {
+    uint4* a4 = reinterpret_cast<uint4*>(acc);
+    if (!established) {
       // theta = (k-th largest of the warps' best thread maxima) - margin: maxima of distinct threads are distinct
       // documents, so k of them at or above it bound the k-th best exact score from below
       unsigned int mine = 0u;
-#pragma unroll 2
-      for (int i = 0; i < kBsDocsPerThread; ++i) mine = max(mine, acc[threadIdx.x + i * kBsThreads]);
+      for (int v = threadIdx.x; v < kVec; v += kBsThreads) {
+        const uint4 x = a4[v];
+        mine = max(mine, max(max(x.x, x.y), max(x.z, x.w)));
+      }
       const int m = (k + kBsThreads / 32 - 1) / (kBsThreads / 32);        // 1 or 2
       unsigned int* s_top = reinterpret_cast<unsigned int*>(cand_alt);
       for (int round = 0; round < m; ++round) {
@@ -909,21 +867,27 @@ bm25_fx_kernel(const int64_t* __restrict__ indptr, const uint2* __restrict__ pos
       __syncthreads();
       const unsigned int tb = s_tw;
       if (tb != 0u) { theta = tb > kFxMargin ? tb - kFxMargin : 1u; established = true; }
-      // scan + clear: collect the documents at or above theta
-#pragma unroll 2
-      for (int i = 0; i < kBsDocsPerThread; ++i) {
-        const int l = threadIdx.x + i * kBsThreads;
-        const unsigned int sc = acc[l];
-        if (sc != 0u) {
-          acc[l] = 0u;
-          if (sc >= theta) {
+    }
+    // scan + clear: collect the documents at or above theta (theta = 0: every touched document)
+    {
+      const unsigned int bar = theta ? theta : 1u;
+      for (int v = threadIdx.x; v < kVec; v += kBsThreads) {
+        const uint4 x = a4[v];
+        if ((x.x | x.y | x.z | x.w) == 0u) continue;
+        a4[v] = make_uint4(0u, 0u, 0u, 0u);
+        const unsigned int mx = max(max(x.x, x.y), max(x.z, x.w));
+        if (mx < bar) continue;
+        const unsigned int xs[4] = {x.x, x.y, x.z, x.w};
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          if (xs[u] >= bar) {
             const unsigned int slot = atomicAdd(&s_ncand, 1u);
-            if (slot < kBsCandCap) cand[slot] = make_uint2(sc, doc_base + l);
+            if (slot < kBsCandCap) cand[slot] = make_uint2(xs[u], doc_base + static_cast<uint32_t>(v) * 4u + u);
           }
         }
       }
     }
-    __syncthreads();
+    __syncthreads();                                      // accumulators are clear, the candidate count is final
     if (s_ncand > kBsCandCap) {                           // uniform: mass ties → the general kernel re-scores the query
       if (threadIdx.x == 0) { status[q] = 1; fin_cnt[cbase] = 0; }
       return;
