@@ -687,7 +687,10 @@ __host__ __device__ constexpr int fx_smem_bytes(int rpg) {
 }
 
 // fin: [nq][ng][kFxFinalCap] {fixed-point sum, doc}; fin_cnt: [nq][ng]
-__global__ void __launch_bounds__(kBsThreads, 3)
+// 4 CTAs per SM = 32 registers per thread: that is also what lets ONE of these CTAs sit beside the tensor-core
+// filter's CTA (120 registers x 320 threads) in a hybrid step — at 40 registers the pair overflows a scheduler's
+// 16 K registers and BM25 silently waits for the filter to finish.
+__global__ void __launch_bounds__(kBsThreads, 4)
 bm25_fx_kernel(const int64_t* __restrict__ indptr, const uint2* __restrict__ post8, const uint32_t* __restrict__ roff,
                int nr, const int32_t* __restrict__ tok_indptr, const int32_t* __restrict__ term_rows,
                const double* __restrict__ tok_idf, double scale, int q0, int k, int rpg, int ng,
