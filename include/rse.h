@@ -211,6 +211,26 @@ int rse_hybrid_run_merged_dev(rse_index *h, int32_t mode, double param, int32_t 
                               double *out_a_dev, double *out_b_dev, int32_t *out_count_dev);
 int rse_hybrid_fetch(rse_index *h, int32_t limit, int64_t *out_id, double *out_score, double *out_a,
                      double *out_b, int32_t *out_count);
+/* Pipelined form of rse_hybrid for a serving loop: at most TWO batches in flight per handle.
+ *   submit : stage (host buffers -> pinned -> device, asynchronous) + run + an asynchronous copy of
+ *            the results into a pinned slot owned by the handle; returns a ticket.  It returns as
+ *            soon as the batch is ENQUEUED — it never waits for the device — so the caller submits
+ *            batch i+1 before collecting batch i and the device does not idle between batches.
+ *            Caller buffers may be reused as soon as submit returns.
+ *   collect: wait for the ticket's results and copy them out; tickets are collected in submission
+ *            order.  out_nq / out_limit (optional) report the batch's shape.  The tensor-core
+ *            path's per-query overflow flags (a mass tie at the K'-th distance; rse_hybrid waits
+ *            for them in mid-batch) are checked HERE: a batch with a flagged query is re-run
+ *            through rse_hybrid from the handle's copies of its inputs before collect returns.
+ * Results are those of rse_hybrid on the same inputs.  A third submit before a collect returns
+ * RSE_ERR_STATE.  Not to be interleaved with stage/run/fetch between a submit and its collect. */
+int rse_hybrid_submit(rse_index *h, int32_t mode, double param, int32_t tie_mode, int32_t limit,
+                      int32_t knn_multiplier, int32_t nq, const float *q_host,
+                      const int32_t *tok_indptr, const int32_t *term_rows, double k1, double b,
+                      int64_t *ticket);
+int rse_hybrid_collect(rse_index *h, int64_t ticket, int32_t *out_nq, int32_t *out_limit,
+                       int64_t *out_id, double *out_score, double *out_a, double *out_b,
+                       int32_t *out_count);
 
 /* ------------------------------------------------------------------ introspection
  * Counters since the last rse_stats_reset: kernels launched by this library,

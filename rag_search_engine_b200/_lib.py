@@ -94,6 +94,10 @@ _SIGNATURES = {
                                                  c_double, c_void_p, c_int32, c_void_p, c_void_p, c_void_p, c_void_p,
                                                  c_void_p]),
     "rse_hybrid_fetch": (ctypes.c_int, [c_void_p, c_int32, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
+    "rse_hybrid_submit": (ctypes.c_int, [c_void_p, c_int32, c_double, c_int32, c_int32, c_int32, c_int32, c_void_p,
+                                         c_void_p, c_void_p, c_double, c_double, POINTER(c_int64)]),
+    "rse_hybrid_collect": (ctypes.c_int, [c_void_p, c_int64, POINTER(c_int32), POINTER(c_int32), c_void_p, c_void_p,
+                                          c_void_p, c_void_p, c_void_p]),
     "rse_get_stats": (ctypes.c_int, [c_void_p, POINTER(RseStats)]),
     "rse_stats_reset": (ctypes.c_int, [c_void_p]),
     "rse_set_timing": (ctypes.c_int, [c_void_p, c_int32]),
@@ -144,6 +148,7 @@ class Index:
             raise RseError(rc, msg.decode() if msg else "rse_create failed")
         self.device = int(device)
         self._keepalive = []
+        self._tickets = {}
 
     # ------------------------------------------------------------------ plumbing
     def _check(self, rc: int):
@@ -373,6 +378,40 @@ class Index:
         self._check(self._L.rse_hybrid_fetch(self._h, int(limit), c_void_p(oid.ctypes.data), c_void_p(osc.ctypes.data),
                                              c_void_p(oa.ctypes.data), c_void_p(ob.ctypes.data),
                                              c_void_p(oc.ctypes.data)))
+        return oid, osc, oa, ob, oc
+
+    # pipelined form: two batches in flight (rse_hybrid_submit / rse_hybrid_collect)
+    def hybrid_submit(self, mode: int, param: float, limit: int, Q, tok_indptr, term_rows, knn_multiplier: int = 10,
+                      k1: float = 1.5, b: float = 0.75, tie_mode: int = TIE_REFERENCE) -> int:
+        Q = _c(Q, np.float32).reshape(-1, self.dim)
+        nq = Q.shape[0]
+        tok_indptr = _c(tok_indptr, np.int32)
+        term_rows = _c(term_rows, np.int32)
+        if term_rows.size == 0:
+            term_rows = np.zeros(1, np.int32)
+        if len(tok_indptr) != nq + 1:
+            raise ValueError("tok_indptr must have nq+1 entries")
+        ticket = c_int64(-1)
+        self._check(self._L.rse_hybrid_submit(self._h, int(mode), float(param), int(tie_mode), int(limit),
+                                              int(knn_multiplier), nq, c_void_p(Q.ctypes.data),
+                                              c_void_p(tok_indptr.ctypes.data), c_void_p(term_rows.ctypes.data),
+                                              float(k1), float(b), ctypes.byref(ticket)))
+        self._tickets[ticket.value] = (nq, int(limit))
+        return ticket.value
+
+    def hybrid_collect(self, ticket: int):
+        if ticket not in self._tickets:
+            raise KeyError(f"unknown ticket {ticket}")
+        nq, limit = self._tickets[ticket]
+        oid = np.zeros((nq, limit), np.int64)
+        osc = np.zeros((nq, limit), np.float64)
+        oa = np.zeros((nq, limit), np.float64)
+        ob = np.zeros((nq, limit), np.float64)
+        oc = np.zeros(nq, np.int32)
+        self._check(self._L.rse_hybrid_collect(self._h, int(ticket), None, None, c_void_p(oid.ctypes.data),
+                                               c_void_p(osc.ctypes.data), c_void_p(oa.ctypes.data),
+                                               c_void_p(ob.ctypes.data), c_void_p(oc.ctypes.data)))
+        del self._tickets[ticket]
         return oid, osc, oa, ob, oc
 
     def hybrid_run_merged_dev(self, mode: int, param: float, limit: int, gathered_ptr: int, n_lists: int,

@@ -67,6 +67,32 @@ struct rse_index {
   int pack_nq = 0;
   char* pin_out = nullptr;         // pinned landing buffer of rse_hybrid_fetch
   size_t pin_out_bytes = 0;
+  // rse_hybrid_submit / rse_hybrid_collect: two batches in flight.  Inputs of batch i+1 are staged through their
+  // own pinned buffer and uploaded in stream order behind batch i's kernels; each batch's results land in its own
+  // pinned slot (copy enqueued by submit right behind the fusion kernel, event per slot).
+  struct OutSlot {
+    char* pin = nullptr; size_t bytes = 0; cudaEvent_t ev = nullptr;
+    size_t n = 0; int nq = 0; long long ticket = -1;
+    // the tensor-core path's per-query overflow flags are NOT waited for by submit (that wait is what would keep
+    // the host one KNN stage behind the device): they land here and collect checks them; a batch with a flagged
+    // query (rare: a mass tie at the K'-th distance) is re-run through the blocking call from the copies below
+    int* pin_status = nullptr; size_t pin_status_n = 0; bool deferred = false;
+    std::vector<int32_t> tok_indptr, term_rows;
+    int mode = 0, tie_mode = 0, limit = 0, knn_multiplier = 0; double param = 0.0, k1 = 0.0, b = 0.0;
+    // the slot's own device copies of the staged inputs and of the packed results, swapped into the handle around
+    // stage + run: batch i+1's uploads (copy stream) overlap batch i's kernels, batch i's result copy (third
+    // stream) overlaps batch i+1's first kernels — the main stream carries kernels only
+    DevBuf q_dev, b_tokptr, b_terms, b_idf, f_pack;
+  } out_slot[2];
+  cudaStream_t stream_h2d = nullptr, stream_d2h = nullptr;
+  cudaEvent_t ev_fused = nullptr;
+  bool defer_status = false;       // set around the run of a submit
+  bool run_deferred = false;       // ... and whether that run left its flags unchecked
+  long long pipeline_reruns = 0;
+  long long next_ticket = 0, next_collect = 0;
+  float* pin_q[2] = {nullptr, nullptr};   // pinned staging of the query vectors, alternating with the tickets
+  size_t pin_q_bytes[2] = {0, 0};
+  cudaEvent_t ev_q[2] = {nullptr, nullptr};
   char* pin_stage = nullptr;       // pinned staging for the token / idf upload of a hybrid or BM25 batch
   size_t pin_stage_bytes = 0;
   int* pin_status = nullptr;       // pinned host copy of the per-query overflow flags
@@ -888,6 +914,16 @@ void rse_destroy(rse_index* h) {
   if (h->pin_status) cudaFreeHost(h->pin_status);
   if (h->pin_stage) cudaFreeHost(h->pin_stage);
   if (h->pin_out) cudaFreeHost(h->pin_out);
+  for (auto& sl : h->out_slot) {
+    if (sl.pin) cudaFreeHost(sl.pin);
+    if (sl.pin_status) cudaFreeHost(sl.pin_status);
+    if (sl.ev) cudaEventDestroy(sl.ev);
+    for (DevBuf* d : {&sl.q_dev, &sl.b_tokptr, &sl.b_terms, &sl.b_idf, &sl.f_pack}) if (d->p) cudaFree(d->p);
+  }
+  if (h->stream_h2d) cudaStreamDestroy(h->stream_h2d);
+  if (h->stream_d2h) cudaStreamDestroy(h->stream_d2h);
+  if (h->ev_fused) cudaEventDestroy(h->ev_fused);
+  for (int i = 0; i < 2; ++i) { if (h->pin_q[i]) cudaFreeHost(h->pin_q[i]); if (h->ev_q[i]) cudaEventDestroy(h->ev_q[i]); }
   free_buf(h->f_pack);
   if (h->ev_status) cudaEventDestroy(h->ev_status);
   if (h->ev_stage) cudaEventDestroy(h->ev_stage);
@@ -1613,8 +1649,14 @@ int hybrid_run_impl(rse_index* h, int mode, double param, int tie_mode, int limi
       if (rc != RSE_OK) return rc;
       tl_mark(h, kTlBm25End, h->stream);
     }
-    rc = knn_local_finish(h);
-    if (rc != RSE_OK) return rc;
+    h->run_deferred = false;
+    if (h->defer_status && h->knn_pending) {                  // rse_hybrid_submit: flags are checked by collect
+      h->knn_pending = false;
+      h->run_deferred = true;
+    } else {
+      rc = knn_local_finish(h);
+      if (rc != RSE_OK) return rc;
+    }
     tl_mark(h, kTlKnnEnd, h->stream);
     if (overlapped) CK(cudaStreamWaitEvent(h->stream, h->ev_bm25_done, 0));
   }
@@ -1701,6 +1743,124 @@ int rse_hybrid(rse_index* h, int32_t mode, double param, int32_t tie_mode, int32
   rc = rse_hybrid_run(h, mode, param, tie_mode, limit, knn_multiplier, k1, b);
   if (rc != RSE_OK) return rc;
   return rse_hybrid_fetch(h, limit, out_id, out_score, out_a, out_b, out_count);
+}
+
+int rse_hybrid_submit(rse_index* h, int32_t mode, double param, int32_t tie_mode, int32_t limit, int32_t knn_multiplier,
+                      int32_t nq, const float* q_host, const int32_t* tok_indptr, const int32_t* term_rows, double k1,
+                      double b, int64_t* ticket) {
+  if (!h) return RSE_ERR_INVALID;
+  if (!ticket || nq < 1 || !q_host || !tok_indptr) return fail(h, RSE_ERR_INVALID, "rse_hybrid_submit: bad arguments");
+  if (limit < 1 || limit > RSE_MAX_FUSE_LIMIT) return fail(h, RSE_ERR_UNSUPPORTED, "rse_hybrid: limit must be in [1, 128]");
+  if (h->next_ticket - h->next_collect >= 2)
+    return fail(h, RSE_ERR_STATE, "rse_hybrid_submit: two batches already in flight, collect one first");
+  CK(cudaSetDevice(h->device));
+  if (!h->stream_h2d) {
+    CK(cudaStreamCreateWithFlags(&h->stream_h2d, cudaStreamNonBlocking));
+    CK(cudaStreamCreateWithFlags(&h->stream_d2h, cudaStreamNonBlocking));
+    CK(cudaEventCreateWithFlags(&h->ev_fused, cudaEventDisableTiming));
+  }
+  const int s = static_cast<int>(h->next_ticket & 1);
+  rse_index::OutSlot& sl = h->out_slot[s];
+  // query vectors through a pinned buffer of this slot: the upload is then truly asynchronous (a pageable source
+  // makes cudaMemcpyAsync wait for the stream before it returns)
+  const size_t qbytes = sizeof(float) * static_cast<size_t>(nq) * h->dim;
+  if (!h->ev_q[s]) CK(cudaEventCreateWithFlags(&h->ev_q[s], cudaEventDisableTiming));
+  else CK(cudaEventSynchronize(h->ev_q[s]));                 // the upload two tickets ago has left the buffer
+  if (h->pin_q_bytes[s] < qbytes) {
+    if (h->pin_q[s]) CK(cudaFreeHost(h->pin_q[s]));
+    h->pin_q[s] = nullptr; h->pin_q_bytes[s] = 0;
+    CK(cudaMallocHost(reinterpret_cast<void**>(&h->pin_q[s]), qbytes + qbytes / 2));
+    h->pin_q_bytes[s] = qbytes + qbytes / 2;
+  }
+  std::memcpy(h->pin_q[s], q_host, qbytes);
+
+  // the slot's device buffers and flag buffer stand in for the handle's while this batch is staged and enqueued
+  auto swap_in_out = [&]() {
+    std::swap(h->q_dev, sl.q_dev); std::swap(h->b_tokptr, sl.b_tokptr); std::swap(h->b_terms, sl.b_terms);
+    std::swap(h->b_idf, sl.b_idf); std::swap(h->f_pack, sl.f_pack);
+    std::swap(h->pin_status, sl.pin_status); std::swap(h->pin_status_n, sl.pin_status_n);
+  };
+  swap_in_out();
+  cudaStream_t main_stream = h->stream;
+  h->stream = h->stream_h2d;                                  // uploads on the copy stream
+  int rc = rse_hybrid_stage(h, nq, h->pin_q[s], tok_indptr, term_rows);
+  h->stream = main_stream;
+  cudaError_t ce = cudaSuccess;
+  if (rc == RSE_OK) {
+    ce = cudaEventRecord(h->ev_q[s], h->stream_h2d);
+    if (ce == cudaSuccess) ce = cudaStreamWaitEvent(h->stream, h->ev_q[s], 0);
+    if (ce == cudaSuccess) {
+      h->defer_status = true;
+      rc = rse_hybrid_run(h, mode, param, tie_mode, limit, knn_multiplier, k1, b);
+      h->defer_status = false;
+    }
+  }
+  const size_t n = static_cast<size_t>(nq) * limit;
+  const size_t bytes = 32 * n + 4 * static_cast<size_t>(nq);
+  if (rc == RSE_OK && ce == cudaSuccess) {
+    if (sl.bytes < bytes) {                                   // the slot is free: its previous ticket was collected
+      if (sl.pin) cudaFreeHost(sl.pin);
+      sl.pin = nullptr; sl.bytes = 0;
+      ce = cudaMallocHost(reinterpret_cast<void**>(&sl.pin), bytes + bytes / 2);
+      if (ce == cudaSuccess) sl.bytes = bytes + bytes / 2;
+    }
+    if (ce == cudaSuccess && !sl.ev) ce = cudaEventCreateWithFlags(&sl.ev, cudaEventDisableTiming);
+    // results: third stream, behind the fusion kernel
+    if (ce == cudaSuccess) ce = cudaEventRecord(h->ev_fused, h->stream);
+    if (ce == cudaSuccess) ce = cudaStreamWaitEvent(h->stream_d2h, h->ev_fused, 0);
+    if (ce == cudaSuccess) ce = cudaMemcpyAsync(sl.pin, h->f_pack.p, bytes, cudaMemcpyDeviceToHost, h->stream_d2h);
+    if (ce == cudaSuccess) ce = cudaEventRecord(sl.ev, h->stream_d2h);
+  }
+  swap_in_out();
+  if (rc != RSE_OK) return rc;
+  if (ce != cudaSuccess) return fail(h, RSE_ERR_CUDA, std::string("rse_hybrid_submit: ") + cudaGetErrorString(ce));
+  sl.deferred = h->run_deferred;
+  if (sl.deferred) {
+    sl.tok_indptr.assign(tok_indptr, tok_indptr + nq + 1);
+    sl.term_rows.assign(term_rows, term_rows + (term_rows ? tok_indptr[nq] : 0));
+    sl.mode = mode; sl.tie_mode = tie_mode; sl.limit = limit; sl.knn_multiplier = knn_multiplier;
+    sl.param = param; sl.k1 = k1; sl.b = b;
+  }
+  sl.n = n; sl.nq = nq; sl.ticket = h->next_ticket;
+  *ticket = h->next_ticket++;
+  return RSE_OK;
+}
+
+int rse_hybrid_collect(rse_index* h, int64_t ticket, int32_t* out_nq, int32_t* out_limit, int64_t* out_id,
+                       double* out_score, double* out_a, double* out_b, int32_t* out_count) {
+  if (!h) return RSE_ERR_INVALID;
+  if (!out_id || !out_score || !out_a || !out_b || !out_count) return fail(h, RSE_ERR_INVALID, "rse_hybrid_collect: bad arguments");
+  if (ticket != h->next_collect || ticket >= h->next_ticket)
+    return fail(h, RSE_ERR_STATE, "rse_hybrid_collect: tickets are collected in submission order");
+  rse_index::OutSlot& sl = h->out_slot[ticket & 1];
+  CK(cudaEventSynchronize(sl.ev));
+  tl_print(h);
+  const size_t n = sl.n;
+  if (out_nq) *out_nq = sl.nq;
+  if (out_limit) *out_limit = sl.nq ? static_cast<int32_t>(n / sl.nq) : 0;
+  if (sl.deferred) {
+    bool flagged = false;
+    for (int q = 0; q < sl.nq && !flagged; ++q) flagged = sl.pin_status[q] != 0;
+    if (flagged) {
+      // the query vectors are still in this ticket's pinned staging buffer (the next ticket uses the other one);
+      // the blocking call handles the flagged queries through the exact scan.  The batch submitted after this one
+      // is complete and parked in its own pinned slot once the stream has drained.
+      CK(cudaStreamSynchronize(h->stream));
+      ++h->pipeline_reruns;
+      ++h->next_collect;
+      sl.deferred = false;
+      return rse_hybrid(h, sl.mode, sl.param, sl.tie_mode, sl.limit, sl.knn_multiplier, sl.nq, h->pin_q[ticket & 1],
+                        sl.tok_indptr.data(), sl.term_rows.empty() ? nullptr : sl.term_rows.data(), sl.k1, sl.b,
+                        out_id, out_score, out_a, out_b, out_count);
+    }
+  }
+  std::memcpy(out_id, sl.pin, 8 * n);
+  std::memcpy(out_score, sl.pin + 8 * n, 8 * n);
+  std::memcpy(out_a, sl.pin + 16 * n, 8 * n);
+  std::memcpy(out_b, sl.pin + 24 * n, 8 * n);
+  std::memcpy(out_count, sl.pin + 32 * n, 4 * static_cast<size_t>(sl.nq));
+  ++h->next_collect;
+  return RSE_OK;
 }
 
 }  // extern "C"

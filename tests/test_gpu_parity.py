@@ -632,6 +632,90 @@ def test_full_size_bm25_modes_agree():
     torch.cuda.empty_cache()
 
 
+def test_hybrid_pipelined_submit_collect_equals_the_blocking_call(fresh_index):
+    """rse_hybrid_submit / rse_hybrid_collect (two batches in flight): every batch returns what rse_hybrid returns on
+    the same inputs, whatever is in flight behind it; the third submit and an out-of-order collect are refused."""
+    from rag_search_engine_b200 import synth
+    n_movies = 36_000
+    se = synth.synth_embeddings(n_movies, seed=31, device="cuda")
+    bm = synth.synth_bm25(n_movies, 20_000, seed=32, mean_len=40, sd_len=12, device="cuda")
+    fresh_index.attach_embeddings_dev(se.emb.data_ptr(), se.emb.shape[0], 384, movie_idx_ptr=se.movie_of_chunk.data_ptr(),
+                                      keepalive=se)
+    fresh_index.load_bm25(bm.indptr, bm.doc_idx, bm.tf, bm.df, bm.dl, bm.n_movies, bm.avgdl)
+    fresh_index.set_id_tables(se.movie_ids, se.movie_ids)
+    batches = []
+    for i, nq in enumerate([96, 300, 17, 256, 64]):            # sizes on both sides of the tensor-core threshold
+        Q = synth.synth_query_vectors(se.emb, nq, seed=40 + i).cpu().numpy()
+        tp, tr = synth.synth_token_queries(bm, nq, seed=50 + i)
+        batches.append((Q, tp, tr, 10 if i % 2 == 0 else 5, i % 2))
+    want = [fresh_index.hybrid(mode, 60.0 if mode == 0 else 0.5, limit, Q, tp, tr) for Q, tp, tr, limit, mode in batches]
+    got, tickets = [], []
+    for Q, tp, tr, limit, mode in batches:
+        Qc, tpc, trc = Q.copy(), tp.copy(), tr.copy()
+        tickets.append(fresh_index.hybrid_submit(mode, 60.0 if mode == 0 else 0.5, limit, Qc, tpc, trc))
+        Qc[:] = 0; tpc[:] = 0; trc[:] = 0                        # caller buffers are free once submit returns
+        if len(tickets) == 2:
+            with pytest.raises(Exception):
+                fresh_index.hybrid_submit(mode, 60.0, limit, Q, tp, tr)       # a third batch in flight
+            with pytest.raises(Exception):
+                fresh_index.hybrid_collect(tickets[1])                          # out of order
+            got.append(fresh_index.hybrid_collect(tickets.pop(0)))
+    while tickets:
+        got.append(fresh_index.hybrid_collect(tickets.pop(0)))
+    assert len(got) == len(want)
+    for g, w in zip(got, want):
+        assert (g[0] == w[0]).all() and (g[4] == w[4]).all()
+        for a, b in zip(g[1:4], w[1:4]):
+            assert (a.view(np.uint64) == b.view(np.uint64)).all()
+    # the blocking call still works afterwards
+    Q, tp, tr, limit, mode = batches[0]
+    again = fresh_index.hybrid(mode, 60.0, limit, Q, tp, tr)
+    assert (again[0] == want[0][0]).all()
+
+
+def test_hybrid_pipelined_overflowed_batch_is_rerun_at_collect():
+    """submit does not wait for the tensor-core path's overflow flags; collect finds a flagged query (12 000 identical
+    rows tie at the threshold) and re-runs that batch through the blocking call — same bits as the exact path, and
+    the batch in flight behind it is not disturbed."""
+    from rag_search_engine_b200 import _lib, synth
+    rng = np.random.default_rng(78)
+    n = 30_000
+    emb = unit_rows(rng, n, 384)
+    emb[5000:17000] = emb[5000]
+    movie_of = (np.arange(n) // 3).astype(np.int32)
+    ids = (np.arange(n // 3 + 1, dtype=np.int64) * 7 + 3)
+    bm = synth.synth_bm25(len(ids), 4_000, seed=3, mean_len=30, sd_len=10)
+    Qa = unit_rows(rng, 64, 384)
+    Qa[3] = emb[5000] + 0.01 * unit_rows(rng, 1, 384)[0]         # overflows
+    Qb = unit_rows(rng, 64, 384)                                   # does not
+    tpa, tra = synth.synth_token_queries(bm, 64, seed=4)
+    tpb, trb = synth.synth_token_queries(bm, 64, seed=5)
+    out = {}
+    for mode in (1, 2):
+        idx = _lib.Index(0)
+        try:
+            idx.set_tc_mode(mode)
+            idx.load_embeddings(emb, movie_idx=movie_of)
+            idx.load_bm25(bm.indptr, bm.doc_idx, bm.tf, bm.df, bm.dl, bm.n_movies, bm.avgdl)
+            idx.set_id_tables(ids, ids)
+            if mode == 1:
+                out[1] = (idx.hybrid(0, 60.0, 10, Qa, tpa, tra), idx.hybrid(0, 60.0, 10, Qb, tpb, trb))
+            else:
+                ta = idx.hybrid_submit(0, 60.0, 10, Qa, tpa, tra)
+                tb = idx.hybrid_submit(0, 60.0, 10, Qb, tpb, trb)
+                assert idx.stats().tc_fallback_queries == 0          # nothing has been checked yet
+                ra = idx.hybrid_collect(ta)
+                assert idx.stats().tc_fallback_queries >= 1
+                rb = idx.hybrid_collect(tb)
+                out[2] = (ra, rb)
+        finally:
+            idx.close()
+    for want, got in zip(out[1], out[2]):
+        for a, b in zip(want, got):
+            assert (a.view(np.uint8) == b.view(np.uint8)).all()
+
+
+
 def test_hybrid_repeated_large_batches_are_stable(fresh_index):
     """Back-to-back hybrid batches of 1024 queries (four tensor-core blocks, BM25 on the second stream underneath the
     filter pass) must return the same bits every time — a shared-memory race in the BM25 kernel once made this fail
