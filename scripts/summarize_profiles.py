@@ -85,7 +85,8 @@ def full(tag, rep):
             (ROOT / "profiles" / "r01_dominant_kernel_traffic.json").write_text(json.dumps({
                 "kernel": "knn_tc3_kernel<1> (filter)", "tc_kind": "f16-shadow", "rows": 4799462, "source": Path(rep).name,
                 "dram_bytes_read": val("dram__bytes_read.sum"), "dram_bytes_write": val("dram__bytes_write.sum"),
-                "gpu_time_ms_under_ncu": val("gpu__time_duration.sum") / 1e6 if units[hdr.index("gpu__time_duration.sum")] == "ns" else None,
+                "gpu_time_ms_under_ncu": float(row[hdr.index("gpu__time_duration.sum")].replace(",", "")) *
+                {"ns": 1e-6, "us": 1e-3, "ms": 1.0, "s": 1e3}.get(units[hdr.index("gpu__time_duration.sum")], float("nan")),
                 "grid": grid}, indent=1) + "\n")
             break
     print("\n".join(out[:40]))
