@@ -1612,6 +1612,7 @@ int hybrid_run_impl(rse_index* h, int mode, double param, int tie_mode, int limi
   const int kprime = std::max(limit * knn_multiplier, limit);   // semantic_search.py:251
   if (kprime > RSE_MAX_KPRIME) return fail(h, RSE_ERR_UNSUPPORTED, "rse_hybrid: limit*knn_multiplier exceeds 4096");
   int rc = RSE_OK;
+  bool join_bm25 = false;
   const size_t n = static_cast<size_t>(nq) * limit;
   ENSURE(h->cand, sizeof(long long) * static_cast<size_t>(nq) * kprime * 3);
   ENSURE(h->o_dist, sizeof(float) * n);
@@ -1658,11 +1659,13 @@ int hybrid_run_impl(rse_index* h, int mode, double param, int tie_mode, int limi
       if (rc != RSE_OK) return rc;
     }
     tl_mark(h, kTlKnnEnd, h->stream);
-    if (overlapped) CK(cudaStreamWaitEvent(h->stream, h->ev_bm25_done, 0));
+    join_bm25 = overlapped;
   }
   rc = aggregate(h, static_cast<const long long*>(h->cand.p), nq, limit, kprime, static_cast<float*>(h->o_dist.p),
                  static_cast<long long*>(h->o_rowid.p), static_cast<int*>(h->o_movie.p), static_cast<int*>(h->o_count.p));
   if (rc != RSE_OK) return rc;
+  // the per-movie aggregation needs the KNN candidates only: BM25 (usually the last to finish) is joined after it
+  if (join_bm25) CK(cudaStreamWaitEvent(h->stream, h->ev_bm25_done, 0));
   // dense index → movies.id happens inside the fusion kernel (two gather launches less)
   FuseIn in{nullptr, static_cast<const double*>(h->b_score.p), static_cast<const int*>(h->b_count.p), nullptr,
             static_cast<const float*>(h->o_dist.p), static_cast<const int*>(h->o_count.p), nullptr};
