@@ -151,7 +151,7 @@ def export_embeddings(conn: sqlite3.Connection, table: str = VEC_TABLE) -> EmbAr
 
 
 # ----------------------------------------------------------------------------- frozen sidecar
-SIDECAR_VERSION = 1
+SIDECAR_VERSION = 2
 
 
 def _db_fingerprint(conn: sqlite3.Connection, db_path) -> dict:
@@ -172,9 +172,17 @@ def sidecar_path(db_path, part: str) -> Path:
     return Path(str(db_path) + f".rse-{part}.npz")
 
 
+def emb_matrix_path(db_path) -> Path:
+    """The embedding matrix of the 'emb' sidecar: a raw .npy of its own, so a later open MEMORY-MAPS it
+    (np.load(mmap_mode="r")) instead of reading gigabytes into anonymous memory — rse_load_embeddings then
+    copies to the device straight out of the page cache."""
+    return Path(str(db_path) + ".rse-emb.f32.npy")
+
+
 def load_or_export(conn: sqlite3.Connection, db_path, part: str, use_cache: bool = True):
-    """part = 'bm25' | 'emb'.  Exports once and keeps an .npz next to the database; a later open
-    whose fingerprint matches loads the arrays without touching the big tables."""
+    """part = 'bm25' | 'emb'.  Exports once and keeps an .npz next to the database (plus, for 'emb', the
+    matrix as a memory-mappable .npy); a later open whose fingerprint matches loads the arrays without
+    touching the big tables."""
     exporter = {"bm25": export_bm25, "emb": export_embeddings}[part]
     if not use_cache:
         return exporter(conn)
@@ -190,7 +198,10 @@ def load_or_export(conn: sqlite3.Connection, db_path, part: str, use_cache: bool
                                           doc_ids=z["doc_ids"], n_movies=int(z["n_movies"]), avgdl=float(z["avgdl"]),
                                           term_row={t: i for i, t in enumerate(terms)})
                     valid = z["valid"] if int(z["has_valid"]) else None
-                    return EmbArrays(emb=z["emb"], valid=valid, rowid=z["rowid"], movie_idx=z["movie_idx"],
+                    emb = np.load(emb_matrix_path(db_path), mmap_mode="r")
+                    if emb.dtype != np.float32 or list(emb.shape) != z["emb_shape"].tolist():
+                        raise ValueError("embedding matrix does not belong to this sidecar")
+                    return EmbArrays(emb=emb, valid=valid, rowid=z["rowid"], movie_idx=z["movie_idx"],
                                      movie_ids=z["movie_ids"], dim=int(z["dim"]))
         except Exception:
             pass                                      # unreadable / stale sidecar → re-export
@@ -201,7 +212,10 @@ def load_or_export(conn: sqlite3.Connection, db_path, part: str, use_cache: bool
             np.savez(sc, fingerprint=np.str_(fp), indptr=arr.indptr, doc_idx=arr.doc_idx, tf=arr.tf, df=arr.df, dl=arr.dl,
                      doc_ids=arr.doc_ids, n_movies=np.int64(arr.n_movies), avgdl=np.float64(arr.avgdl), terms=terms)
         else:
-            np.savez(sc, fingerprint=np.str_(fp), emb=arr.emb, has_valid=np.int64(arr.valid is not None),
+            # the matrix first, the .npz (which carries the fingerprint) last: it is the commit marker
+            np.save(emb_matrix_path(db_path), np.ascontiguousarray(arr.emb, dtype=np.float32))
+            np.savez(sc, fingerprint=np.str_(fp), emb_shape=np.asarray(arr.emb.shape, np.int64),
+                     has_valid=np.int64(arr.valid is not None),
                      valid=arr.valid if arr.valid is not None else np.zeros(0, np.uint8), rowid=arr.rowid,
                      movie_idx=arr.movie_idx, movie_ids=arr.movie_ids, dim=np.int64(arr.dim))
     except OSError:

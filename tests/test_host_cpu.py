@@ -227,6 +227,13 @@ def test_sidecar_cache_round_trip_and_invalidation(tmp_path):
         assert (getattr(a, f) == getattr(a2, f)).all()
     assert a.term_row == a2.term_row and a.avgdl == a2.avgdl and a.n_movies == a2.n_movies
     assert (e.emb == e2.emb).all() and (e.rowid == e2.rowid).all() and (e.movie_idx == e2.movie_idx).all() and e2.valid is None
+    # the matrix comes back memory-mapped from its own .npy, contiguous float32 (what the ctypes stub passes on as is)
+    assert isinstance(e2.emb, np.memmap) and e2.emb.dtype == np.float32 and e2.emb.flags["C_CONTIGUOUS"]
+    assert store.emb_matrix_path(db).exists()
+    # a matrix file that does not belong to the sidecar (wrong shape) is not trusted: re-export
+    np.save(store.emb_matrix_path(db), np.zeros((3, 8), np.float32))
+    e4 = store.load_or_export(conn, db, "emb")
+    assert (np.asarray(e4.emb) == np.asarray(e.emb)).all()
     # a change in the database invalidates the sidecar
     conn.execute("INSERT INTO movies(id, title, description) VALUES (999999, 'x', 'y')")
     conn.commit()
