@@ -902,6 +902,8 @@ void rse_destroy(rse_index* h) {
   if (!h) return;
   cudaSetDevice(h->device);
   cudaStreamSynchronize(h->stream);
+  for (cudaStream_t st : {h->stream_b, h->stream_h2d, h->stream_d2h})   // tickets may still be in flight
+    if (st) cudaStreamSynchronize(st);
   release_embeddings(h);
   release_bm25(h);
   for (DevBuf* b : {&h->q_dev, &h->sb, &h->sel, &h->hist, &h->selkeys, &h->cand, &h->dist, &h->o_dist, &h->o_pos,
