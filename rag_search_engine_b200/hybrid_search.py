@@ -184,6 +184,43 @@ class HybridSearch:
         return [[{"id": int(oid[q, j]), "bm25": float(oa[q, j]), "semantic": float(ob[q, j]),
                   "score": float(osc[q, j])} for j in range(oc[q])] for q in range(len(token_lists))]
 
+    def rrf_search_stream(self, batches, k=60, limit: int = 10, knn_multiplier: int = 10, k1: float = 1.5,
+                          b: float = 0.75):
+        """Serving loop over an iterable of ``(token_lists, query_vecs)`` batches: yields what ``rrf_search_batch``
+        returns for each batch, in order, while the NEXT batch is already enqueued on the device
+        (``rse_hybrid_submit`` / ``rse_hybrid_collect``, two batches in flight) — the device never waits for the host
+        to stage inputs or unpack results."""
+        if not self._gpu_retrievers():
+            raise RuntimeError("*_stream needs the GPU KeywordSearch and SemanticSearch of this package")
+        kw, sem = self.keyword, self.semantic
+        reg = runtime.parts(self.db_path, self.device)
+        if "ids" not in reg:
+            self._index.set_id_tables(kw._arr.doc_ids, sem._arr.movie_ids)
+            reg["ids"] = True
+
+        def unpack(res, nq):
+            oid, osc, oa, ob, oc = res
+            return [[{"id": int(oid[q, j]), "score": float(osc[q, j]),
+                      "bm25_rank": None if oa[q, j] < 0 else int(oa[q, j]),
+                      "sem_rank": None if ob[q, j] < 0 else int(ob[q, j])} for j in range(oc[q])] for q in range(nq)]
+
+        pending = None                                           # (ticket, nq) of the batch in flight
+        for token_lists, query_vecs in batches:
+            if len(token_lists) == 0:
+                if pending is not None:
+                    yield unpack(self._index.hybrid_collect(pending[0]), pending[1])
+                    pending = None
+                yield []
+                continue
+            tok_indptr, rows = kw._term_rows(token_lists)
+            ticket = self._index.hybrid_submit(0, float(k), limit, query_vecs, tok_indptr, rows,
+                                               knn_multiplier=knn_multiplier, k1=k1, b=b, tie_mode=self.tie_mode)
+            if pending is not None:
+                yield unpack(self._index.hybrid_collect(pending[0]), pending[1])
+            pending = (ticket, len(token_lists))
+        if pending is not None:
+            yield unpack(self._index.hybrid_collect(pending[0]), pending[1])
+
     # ---------------- cleanup (hybrid_search.py:382-384) ---------------- #
     def close(self) -> None:
         self.keyword.close()

@@ -171,6 +171,15 @@ def test_hybrid_search_matches_reference_pipeline(built):
             assert [(g["id"], g["bm25"], g["semantic"], g["score"]) for g in gwb] == \
                    [(w["id"], w["bm25"], w["semantic"], w["score"]) for w in ww]
         assert hs.rrf_search("w0", limit=5, rerank_method="nonsense") == hs.rrf_search("w0", limit=5)   # :370-373
+        # the serving loop (two batches in flight) yields, in order, what the blocking batch call returns
+        qs = ["w0 w1", built["docs"][7]["title"], "w2 w2 w9 zzz", "w60", "w3 w4 w5", "w1"]
+        batches = [([q.lower().split() for q in qs[i:i + n]], built["enc"].encode(qs[i:i + n]))
+                   for i, n in ((0, 2), (2, 1), (3, 0), (3, 3))]
+        streamed = list(hs.rrf_search_stream(iter(batches), k=60, limit=5))
+        assert len(streamed) == len(batches) and streamed[2] == []
+        for (toks, qv), got in zip(batches, streamed):
+            if toks:
+                assert got == hs.rrf_search_batch(toks, qv, k=60, limit=5)
     finally:
         hs.close()
 
