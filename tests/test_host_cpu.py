@@ -262,3 +262,64 @@ def test_synthetic_corpus_is_deterministic_and_keeps_its_tie_cases():
     # rows stay unit length (a near-duplicate differs from its source by one ulp in one component)
     norms = np.linalg.norm(a.emb.numpy().astype(np.float64), axis=1)
     assert np.abs(norms - 1.0).max() < 1e-5
+
+
+def test_rrf_search_stream_keeps_two_batches_in_flight_and_the_order(tmp_path):
+    """Host logic of HybridSearch.rrf_search_stream against a fake handle: every batch is submitted before the
+    previous one is collected (never more than two tickets outstanding), tickets are collected in submission
+    order, an empty batch drains the pipeline and yields [], results come back in the order of the batches."""
+    from pathlib import Path
+    from rag_search_engine_b200 import hybrid_search as hsm, runtime
+    from rag_search_engine_b200.keyword_search import KeywordSearch
+    from rag_search_engine_b200.semantic_search import SemanticSearch
+
+    class FakeIndex:
+        def __init__(self):
+            self.next, self.outstanding, self.log, self.max_outstanding = 0, [], [], 0
+        def set_id_tables(self, a, b):
+            self.log.append("ids")
+        def hybrid_submit(self, mode, param, limit, Q, tok_indptr, rows, **kw):
+            assert mode == 0 and param == 60.0 and len(tok_indptr) == len(Q) + 1
+            assert len(self.outstanding) < 2, "a third batch in flight"
+            t = self.next; self.next += 1
+            self.outstanding.append((t, len(Q), limit))
+            self.max_outstanding = max(self.max_outstanding, len(self.outstanding))
+            self.log.append(("submit", t))
+            return t
+        def hybrid_collect(self, ticket):
+            t, nq, limit = self.outstanding.pop(0)
+            assert t == ticket, "collected out of order"
+            self.log.append(("collect", t))
+            oid = np.full((nq, limit), 100 * t, np.int64) + np.arange(limit)
+            osc = np.tile(1.0 / (1 + np.arange(limit)), (nq, 1))
+            oa = np.tile(np.arange(limit, dtype=np.float64), (nq, 1)); oa[:, -1] = -1.0
+            ob = -np.ones((nq, limit))
+            return oid, osc, oa, ob, np.full(nq, limit - 1, np.int32)
+
+    class Arr:
+        term_row = {"a": 0, "b": 1}
+        doc_ids = np.arange(3, dtype=np.int64)
+        movie_ids = np.arange(3, dtype=np.int64)
+
+    db = tmp_path / "x.db"
+    db.touch()
+    hs = hsm.HybridSearch.__new__(hsm.HybridSearch)
+    kw = KeywordSearch.__new__(KeywordSearch); kw._arr = Arr()
+    sem = SemanticSearch.__new__(SemanticSearch); sem._arr = Arr()
+    fake = FakeIndex()
+    hs.keyword, hs.semantic, hs._index, hs.db_path, hs.device, hs.tie_mode = kw, sem, fake, Path(db), 0, 0
+    key = (str(Path(db).resolve()), 0)
+    runtime._handles[key] = [fake, 1, {}]
+    try:
+        sizes = [3, 1, 0, 2, 4]
+        batches = [([["a", "zz"]] * n, np.zeros((n, 8), np.float32)) for n in sizes]
+        out = list(hs.rrf_search_stream(iter(batches), k=60, limit=4))
+    finally:
+        del runtime._handles[key]
+    assert [len(o) for o in out] == sizes
+    assert fake.max_outstanding == 2 and not fake.outstanding
+    assert fake.log == ["ids", ("submit", 0), ("submit", 1), ("collect", 0), ("collect", 1),      # empty batch drains
+                        ("submit", 2), ("submit", 3), ("collect", 2), ("collect", 3)]
+    # batch i carries ticket i's ids, three hits per query (count = limit - 1), last rank None-able fields mapped
+    assert out[0][0][0] == {"id": 0, "score": 1.0, "bm25_rank": 0, "sem_rank": None}
+    assert [h["id"] for h in out[3][1]] == [200, 201, 202] and [h["id"] for h in out[4][0]] == [300, 301, 302]
