@@ -38,25 +38,18 @@ ROW_BYTES_SHADOW = 384 * 2       # the fp16-shadow filter pass (knn_tc3) streams
 
 
 def tc_kind(args):
-    """Which K4 kernel rse_set_tc_mode selects (include/rse.h)."""
-    m = getattr(args, "tc_mode", -1)
-    return "f16-shadow" if m in (-1, 0, 2) else ("tf32-tmem" if m in (3, 4) else "tf32-streamed")
+    """The K4 kernel (r01's two TF32 mappings were removed in r02: 2.6-3.5x slower on every measured shape)."""
+    return "f16-shadow"
 
 
 def scan_kernel_desc(args, tc_used, qb):
     if not tc_used:
         return (f"knn_scan384_kernel<QB={qb}> (one pass over the shard serves {qb} queries; FFMA2-pipe-bound above QB=4, "
                 f"HBM-bound at QB=1: see knn_batch1)"), ROW_BYTES
-    k = tc_kind(args)
-    if k == "f16-shadow":
-        return ("knn_tc3_kernel<filter> (tcgen05 kind::f16 256x256x16 cta_group::2 over the fp16 normalised shadow, "
-                "queries resident in shared memory, TMA 4-stage ring; one pass serves 256 queries; survivors re-scored "
-                "exactly in fp32; in the hybrid step one bm25_fx_kernel CTA per SM runs underneath it on a second "
-                "stream, which costs the pass ~8 %)"), ROW_BYTES_SHADOW
-    if k == "tf32-tmem":
-        return "knn_tc2_filter_kernel (tcgen05 TF32 cta_group::2, queries resident in TMEM)", ROW_BYTES
-    return ("knn_tc_kernel<filter> (tcgen05 TF32 128x256x8, TMA 3-stage, queries streamed from L2; one pass over the "
-            "shard serves 256 queries; survivors re-scored exactly)"), ROW_BYTES
+    return ("knn_tc3_kernel<filter> (tcgen05 kind::f16 256x256x16 cta_group::2 over the fp16 normalised shadow, "
+            "queries resident in shared memory, TMA 4-stage ring; one pass serves 256 queries; survivors re-scored "
+            "exactly in fp32; in the hybrid step one bm25_fx_kernel CTA per SM runs underneath it on a second "
+            "stream, which costs the pass ~8 %)"), ROW_BYTES_SHADOW
 
 
 def parse_args():

@@ -29,7 +29,7 @@
 extern "C" {
 #endif
 
-#define RSE_ABI_VERSION 1
+#define RSE_ABI_VERSION 2
 
 #define RSE_OK 0
 #define RSE_ERR_INVALID -1     /* bad argument */
@@ -88,12 +88,11 @@ int rse_attach_embeddings_dev(rse_index *h, const float *emb_dev, int64_t n_rows
                               const uint8_t *valid_dev, const int64_t *rowid_dev,
                               const int32_t *movie_idx_dev, int64_t pos_base);
 int rse_set_fma(rse_index *h, int32_t use_fma);
-/* K4, the tcgen05 TF32 path for large query batches (probe → filter → EXACT re-score, results
- * identical to the streaming scan): 0 = auto (batches of ≥ 48 queries on ≥ 256 k rows, dim 384),
- * 1 = never, 2 = whenever the shape allows it.  0 / 2 run the probe/filter GEMM over an fp16
- * normalised shadow of the corpus (knn_tc3.cuh; built once, +768 B per row of device memory);
- * 3 / 4 = like 0 / 2 with the TF32 kernel that keeps the queries in tensor memory (knn_tc2.cuh),
- * 5 / 6 = like 0 / 2 with the TF32 kernel that streams the queries (knn_tc.cuh). */
+/* K4, the tcgen05 path for query batches (probe -> filter -> EXACT re-score, results identical to the
+ * streaming scan): 0 = auto (batches of >= RSE_TC_MIN_BATCH queries on >= 256 k rows, dim 384), 1 = never,
+ * 2 = whenever the shape allows it.  The probe/filter GEMM runs over an fp16 normalised shadow of the corpus
+ * (knn_tc3.cuh; built once at the first batch that needs it, +768 B per row of device memory). */
+#define RSE_TC_MIN_BATCH 4
 int rse_set_tc_mode(rse_index *h, int32_t mode);
 
 /* Which BM25 kernels serve rse_bm25 / rse_hybrid for k <= 32 (results are bit-identical in every mode):
@@ -231,6 +230,9 @@ int rse_hybrid_submit(rse_index *h, int32_t mode, double param, int32_t tie_mode
 int rse_hybrid_collect(rse_index *h, int64_t ticket, int32_t *out_nq, int32_t *out_limit,
                        int64_t *out_id, double *out_score, double *out_a, double *out_b,
                        int32_t *out_count);
+/* Wait for and DISCARD every ticket still in flight (a consumer that stops early, an error between a
+ * submit and its collect): afterwards the handle accepts submits again.  out_dropped (optional) = how many. */
+int rse_hybrid_drain(rse_index *h, int32_t *out_dropped);
 
 /* ------------------------------------------------------------------ introspection
  * Counters since the last rse_stats_reset: kernels launched by this library,
@@ -250,6 +252,13 @@ typedef struct rse_stats {
   int64_t tc_filter_launches;   /* K4 tensor-core filter passes (each serves ≤ 256 queries) */
   int64_t tc_queries;           /* queries answered through K4 */
   int64_t tc_fallback_queries;  /* of those, re-run through the exact scan (survivor overflow) */
+  int64_t tc_second_chance_queries; /* of tc_queries, answered by the second filter pass with a tightened bound */
+  int64_t bm25_queries;           /* queries scored by the BM25 kernels */
+  int64_t bm25_fallback_queries;  /* of those, handed to the general kernel by the streaming path (device-side flag) */
+  int64_t bm25_finalists;         /* documents re-scored exactly by the fixed-point path's finish kernel */
+  int64_t bm25_candidates;        /* candidates the fixed-point kernel handed to the finish kernel */
+  int64_t h2d_bytes;              /* bytes moved host -> device by the query entry points (not the index loads) */
+  int64_t d2h_bytes;              /* bytes moved device -> host by the query entry points */
 } rse_stats;
 int rse_get_stats(rse_index *h, rse_stats *out);
 int rse_stats_reset(rse_index *h);

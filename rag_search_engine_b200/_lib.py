@@ -46,6 +46,13 @@ class RseStats(ctypes.Structure):
         ("tc_filter_launches", c_int64),
         ("tc_queries", c_int64),
         ("tc_fallback_queries", c_int64),
+        ("tc_second_chance_queries", c_int64),
+        ("bm25_queries", c_int64),
+        ("bm25_fallback_queries", c_int64),
+        ("bm25_finalists", c_int64),
+        ("bm25_candidates", c_int64),
+        ("h2d_bytes", c_int64),
+        ("d2h_bytes", c_int64),
     ]
 
 
@@ -98,6 +105,7 @@ _SIGNATURES = {
                                          c_void_p, c_void_p, c_double, c_double, POINTER(c_int64)]),
     "rse_hybrid_collect": (ctypes.c_int, [c_void_p, c_int64, POINTER(c_int32), POINTER(c_int32), c_void_p, c_void_p,
                                           c_void_p, c_void_p, c_void_p]),
+    "rse_hybrid_drain": (ctypes.c_int, [c_void_p, POINTER(c_int32)]),
     "rse_get_stats": (ctypes.c_int, [c_void_p, POINTER(RseStats)]),
     "rse_stats_reset": (ctypes.c_int, [c_void_p]),
     "rse_set_timing": (ctypes.c_int, [c_void_p, c_int32]),
@@ -182,9 +190,8 @@ class Index:
         self._check(self._L.rse_set_timing(self._h, int(bool(on))))
 
     def set_tc_mode(self, mode: int):
-        """0 = auto, 1 = exact scan only, 2 = tensor-core path whenever the shape allows it (fp16-shadow
-        kernel); 3 / 4 = like 0 / 2 with the TF32 TMEM-resident-queries kernel; 5 / 6 = like 0 / 2 with
-        the TF32 streamed-queries kernel.  Results are identical in every mode."""
+        """0 = auto (batches of >= 4 queries on >= 256 k rows), 1 = exact scan only, 2 = tensor-core path
+        whenever the shape allows it.  Results are identical in every mode."""
         self._check(self._L.rse_set_tc_mode(self._h, int(mode)))
 
     def set_bm25_mode(self, mode: int):
@@ -413,6 +420,13 @@ class Index:
                                                c_void_p(ob.ctypes.data), c_void_p(oc.ctypes.data)))
         del self._tickets[ticket]
         return oid, osc, oa, ob, oc
+
+    def hybrid_drain(self) -> int:
+        """Wait for and discard every ticket still in flight; the handle accepts submits again afterwards."""
+        n = c_int32(0)
+        self._check(self._L.rse_hybrid_drain(self._h, ctypes.byref(n)))
+        self._tickets.clear()
+        return int(n.value)
 
     def hybrid_run_merged_dev(self, mode: int, param: float, limit: int, gathered_ptr: int, n_lists: int,
                               out_id_ptr: int, out_score_ptr: int, out_a_ptr: int, out_b_ptr: int, out_count_ptr: int,

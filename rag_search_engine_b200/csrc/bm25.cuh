@@ -359,7 +359,9 @@ bm25_score_kernel(const int64_t* __restrict__ indptr, const uint2* __restrict__ 
 }
 
 // flagged[0] = number of queries in [q0, q0 + nc) with status != 0, flagged[1..] = those queries (ascending)
-__global__ void bm25_flag_compact_kernel(const int* __restrict__ status, int q0, int nc, int* __restrict__ flagged) {
+// counters (optional): [0] += the number of flagged queries — the BM25 counterpart of tc_fallback_queries
+__global__ void bm25_flag_compact_kernel(const int* __restrict__ status, int q0, int nc, int* __restrict__ flagged,
+                                         unsigned long long* __restrict__ counters) {
   __shared__ int s_n;
   if (threadIdx.x == 0) s_n = 0;
   __syncthreads();
@@ -368,7 +370,10 @@ __global__ void bm25_flag_compact_kernel(const int* __restrict__ status, int q0,
     if (j < nc && status[q0 + j] != 0) flagged[1 + atomicAdd(&s_n, 1)] = q0 + j;
   }
   __syncthreads();
-  if (threadIdx.x == 0) flagged[0] = s_n;
+  if (threadIdx.x == 0) {
+    flagged[0] = s_n;
+    if (counters && s_n) atomicAdd(&counters[0], static_cast<unsigned long long>(s_n));
+  }
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -914,7 +919,8 @@ bm25_fx_finish_kernel(const uint2* __restrict__ fin, const int* __restrict__ fin
                       const int64_t* __restrict__ indptr, const Post16* __restrict__ post,
                       const uint32_t* __restrict__ roff, int nr, const int32_t* __restrict__ tok_indptr,
                       const int32_t* __restrict__ term_rows, const double* __restrict__ tok_idf, int q0, int k,
-                      double* __restrict__ out_score, int* __restrict__ out_doc, int* __restrict__ out_count) {
+                      double* __restrict__ out_score, int* __restrict__ out_doc, int* __restrict__ out_count,
+                      unsigned long long* __restrict__ counters) {
   __shared__ uint2 s_c[kBsMaxGroups * kFxFinalCap];       // 12 KB: the groups' candidates {sum, doc}
   __shared__ double s_w[kFxRescoreCap][kBsMaxTok];        // 12 KB: weight of (document, token), 0 = not in the list
   __shared__ uint32_t s_doc[kFxRescoreCap];
@@ -949,6 +955,10 @@ bm25_fx_finish_kernel(const uint2* __restrict__ fin, const int* __restrict__ fin
     return;
   }
   const unsigned int m = s_m;
+  if (counters && threadIdx.x == 0) {                     // [1] finalists re-scored exactly, [2] candidates the groups handed over
+    atomicAdd(&counters[1], static_cast<unsigned long long>(m));
+    atomicAdd(&counters[2], static_cast<unsigned long long>(n));
+  }
   // exact re-score, step 1: the posting of every (document, token) pair
   for (unsigned int pidx = threadIdx.x; pidx < m * static_cast<unsigned int>(ntok); pidx += blockDim.x) {
     const unsigned int d = pidx / ntok;

@@ -1,0 +1,180 @@
+// knn_refine.cuh — steps 3 and 4 of K4 (knn_tc3.cuh): refine the filter's survivors on their approximate
+// values, re-score the few that remain with the reference's EXACT sequential fp32 arithmetic (the same
+// mac<FMA> / cosine_tail K1 uses; reference call site rag_search_engine/utils/semantic_search.py:254-261),
+// sort by the vec0 emit-order key and emit the packed candidates K1+K2 would emit.
+#pragma once
+#include "select.cuh"
+#include "tc_common.cuh"
+
+namespace rse {
+
+// ---------------------------------------------------------------- refine + exact re-score + finish
+// One CTA per query.
+//   (a) second-level refinement on the approximate values the filter kept: with s_K = the K'-th
+//       largest dot~/|a| among the survivors (= among ALL rows, because every row above the filter
+//       threshold survived), only rows with s >= s_K - 2*eps*|q| can be in the exact top-K'
+//       (same argument as the filter bound, now with the exact K'-th approximate value);
+//   (b) those few rows (K' plus the 2*eps band) are re-computed with the EXACT sequential fp32
+//       arithmetic of K1 (mac<FMA>, cosine_tail), lane-per-row straight from global memory;
+//   (c) the exact emit-order keys are sorted and the first K' emitted as packed candidates.
+// status[q] = 1 (host re-runs the query through K1/K2) when the survivor list or the refined
+// list overflowed, or fewer than K' rows survived (a corpus/query the bound does not cover: fewer
+// than K' valid rows, zero or non-finite query norm).  `normalized`: the survivor values are cos~
+// (knn_tc3, unit-norm operands) instead of dot~/|a| (knn_tc / knn_tc2), so the band is not scaled by |q|.
+// smem: cap * 8 bytes (pairs) — reused for the exact keys.
+// 256 threads, 256 histogram bins (one per thread): the digit d with  sum(hist[0..d-1]) < need <= sum(hist[0..d]).
+// The thread that owns d writes *out_digit = d and *out_before = sum(hist[0..d-1]); *out_digit stays 256 when
+// the histogram holds fewer than `need` entries.  s_warp: 8 words of scratch.  Ends with a barrier.
+__device__ __forceinline__ void block_pick_digit(const unsigned int* s_hist, unsigned int need, unsigned int* s_warp,
+                                                 unsigned int* out_digit, unsigned int* out_before) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const unsigned int c = s_hist[threadIdx.x];
+  unsigned int incl = c;
+#pragma unroll
+  for (int off = 1; off < 32; off <<= 1) {
+    const unsigned int o = __shfl_up_sync(0xFFFFFFFFu, incl, off);
+    if (lane >= off) incl += o;
+  }
+  if (lane == 31) s_warp[warp] = incl;
+  if (threadIdx.x == 0) *out_digit = 256u;
+  __syncthreads();
+  unsigned int base = 0u;
+#pragma unroll
+  for (int w = 0; w < 8; ++w) base += (w < warp) ? s_warp[w] : 0u;
+  incl += base;
+  if (incl >= need && incl - c < need) { *out_digit = threadIdx.x; *out_before = incl - c; }
+  __syncthreads();
+}
+
+
+template <bool FMA>
+__global__ void __launch_bounds__(kSelThreads, 2)
+knn_refine_kernel(const float* __restrict__ emb, const float* __restrict__ amag, const float* __restrict__ q,
+                  const double* __restrict__ sb, const uint2* __restrict__ cand_pairs,
+                  const unsigned int* __restrict__ cand_count, int cap, int kprime, uint64_t pos_base,
+                  const int64_t* __restrict__ rowid, const int32_t* __restrict__ movie_idx,
+                  long long* __restrict__ cand, int* __restrict__ status, int normalized) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  uint2* pairs = reinterpret_cast<uint2*>(smem_raw);                       // [cap]
+  __shared__ float s_q[kScanD];
+  __shared__ unsigned int s_hist[256];
+  __shared__ unsigned int s_prefix, s_need, s_m, s_digit, s_before;
+  __shared__ unsigned int s_warp[8];
+  __shared__ uint32_t s_rows[kTcRefineCap];
+  const int qi = blockIdx.x;
+  const unsigned int cnt = cand_count[qi];
+  long long* out = cand + static_cast<int64_t>(qi) * kprime * 3;
+  if (cnt > static_cast<unsigned int>(cap)) {                              // survivor overflow
+    if (threadIdx.x == 0) status[qi] = 1;
+    for (int i = threadIdx.x; i < kprime * 3; i += blockDim.x) out[i] = -1ll;
+    return;
+  }
+  const int n = static_cast<int>(cnt);
+  // (knn_tc3 never emits an empty slot or a zero row: its thresholds are positive and those rows read cos~ = 0;
+  //  knn_tc / knn_tc2 check |a|^2 in their epilogues)
+  for (int i = threadIdx.x; i < n; i += blockDim.x) pairs[i] = cand_pairs[static_cast<int64_t>(qi) * cap + i];
+  for (int i = threadIdx.x; i < kScanD; i += blockDim.x) s_q[i] = q[static_cast<int64_t>(qi) * kScanD + i];
+  if (threadIdx.x == 0) { s_prefix = 0u; s_need = static_cast<unsigned int>(kprime < n ? kprime : n); s_m = 0u; }
+  __syncthreads();
+
+  // ---- (a) K'-th largest approximate value: MSD radix select (4 x 8 bits) on ~orderable(s)
+  //      (descending s == ascending ~orderable)
+  uint32_t resolved_mask = 0u;
+  if (n > kprime) {
+    for (int pass = 0; pass < 4; ++pass) {
+      const int shift = 24 - 8 * pass;
+      for (int i = threadIdx.x; i < 256; i += blockDim.x) s_hist[i] = 0u;
+      __syncthreads();
+      const uint32_t prefix = s_prefix;
+      for (int i = threadIdx.x; i < n; i += blockDim.x) {
+        const uint32_t key = ~f32_orderable(pairs[i].y);
+        if ((key & resolved_mask) == prefix) atomicAdd(&s_hist[(key >> shift) & 0xFFu], 1u);
+      }
+      __syncthreads();
+      block_pick_digit(s_hist, s_need, s_warp, &s_digit, &s_before);     // a thread-0 loop over the bins cost 10 % of the kernel
+      if (threadIdx.x == 0) {
+        s_prefix = prefix | ((s_digit & 0xFFu) << shift);
+        s_need = s_need - s_before;
+      }
+      resolved_mask |= 0xFFu << shift;
+      __syncthreads();
+    }
+  }
+  // s_K (exact K'-th largest approximate value), cut = s_K - 2 eps |q|  (slack for f32 rounding)
+  float cut = -__int_as_float(0x7F800000);
+  if (n > kprime) {
+    const float s_k = __uint_as_float(f32_from_orderable(~s_prefix));
+    const float qn = normalized ? 1.0f : static_cast<float>(sb[qi]);
+    cut = s_k - (2.0f * kTcEps + 1e-6f) * qn - 1e-30f;
+  }
+  for (int i = threadIdx.x; i < n; i += blockDim.x) {
+    const uint2 pr = pairs[i];
+    if (__uint_as_float(pr.y) >= cut && pr.y != 0xFF800000u) {
+      const unsigned int slot = atomicAdd(&s_m, 1u);
+      if (slot < kTcRefineCap) s_rows[slot] = pr.x;
+    }
+  }
+  __syncthreads();
+  const unsigned int m = s_m;
+  if (m > kTcRefineCap || m < static_cast<unsigned int>(kprime)) {         // refined list overflow (mass ties) / too few rows
+    if (threadIdx.x == 0) status[qi] = 1;
+    for (int i = threadIdx.x; i < kprime * 3; i += blockDim.x) out[i] = -1ll;
+    return;
+  }
+  if (threadIdx.x == 0) status[qi] = 0;
+
+  // ---- (b) exact distances, lane-per-row from global memory (the reference's sequential sum)
+  unsigned long long* keys = reinterpret_cast<unsigned long long*>(smem_raw);   // pairs are dead
+  __syncthreads();
+  int m2 = 2;
+  while (m2 < static_cast<int>(m)) m2 <<= 1;
+  const double sbq = sb[qi];
+  for (int i = threadIdx.x; i < m2; i += blockDim.x) {
+    unsigned long long key = ~0ull;
+    if (i < static_cast<int>(m)) {
+      const uint32_t row = s_rows[i];
+      const float4* rp = reinterpret_cast<const float4*>(emb + static_cast<int64_t>(row) * kScanD);
+      float acc = 0.0f;
+#pragma unroll 8
+      for (int c = 0; c < kScanD / 4; ++c) {
+        const float4 a = __ldg(rp + c);
+        acc = mac<FMA>(acc, a.x, s_q[4 * c + 0]);
+        acc = mac<FMA>(acc, a.y, s_q[4 * c + 1]);
+        acc = mac<FMA>(acc, a.z, s_q[4 * c + 2]);
+        acc = mac<FMA>(acc, a.w, s_q[4 * c + 3]);
+      }
+      const float d = cosine_tail(acc, sqrt(static_cast<double>(__ldg(amag + row))), sbq);
+      key = knn_key(f32_orderable(__float_as_uint(d)), pos_base + static_cast<uint64_t>(row));
+    }
+    keys[i] = key;
+  }
+  // ---- (c) keys-only bitonic sort, emit the first K'
+  for (int size = 2; size <= m2; size <<= 1) {
+    for (int stride = size >> 1; stride > 0; stride >>= 1) {
+      __syncthreads();
+      for (int t = threadIdx.x; t < (m2 >> 1); t += blockDim.x) {
+        const int lo = 2 * t - (t & (stride - 1));
+        const int hi = lo + stride;
+        const bool up = ((lo & size) == 0);
+        const unsigned long long a = keys[lo], b = keys[hi];
+        if ((a > b) == up) { keys[lo] = b; keys[hi] = a; }
+      }
+    }
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < kprime; i += blockDim.x) {
+    long long* c = out + static_cast<int64_t>(i) * 3;
+    if (i < static_cast<int>(m)) {
+      const uint64_t key = keys[i];
+      const uint64_t pos = knn_key_pos(key);
+      const int64_t local = static_cast<int64_t>(pos - pos_base);
+      c[0] = static_cast<long long>(key);
+      c[1] = rowid ? rowid[local] : static_cast<long long>(pos);
+      c[2] = movie_idx ? movie_idx[local] : -1;
+    } else {
+      c[0] = -1ll; c[1] = -1ll; c[2] = -1ll;
+    }
+  }
+}
+
+}  // namespace rse

@@ -41,8 +41,7 @@
 #pragma once
 #include <cuda_fp16.h>
 
-#include "knn_tc.cuh"
-#include "knn_tc2.cuh"
+#include "knn_refine.cuh"
 
 namespace rse {
 

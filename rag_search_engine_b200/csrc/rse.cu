@@ -17,8 +17,6 @@
 #include "fusion.cuh"
 #include "knn_scan.cuh"
 #include "select.cuh"
-#include "knn_tc.cuh"
-#include "knn_tc2.cuh"
 #include "knn_tc3.cuh"
 
 using namespace rse;
@@ -51,12 +49,6 @@ struct rse_index {
   int staged_nq = 0;
   // K4 tensor-core path
   int tc_mode = 0;                 // 0 auto, 1 off (exact scan only), 2 force on
-  CUtensorMap tmap_a{};            // [n_rows][384] f32, box {32, 128}, SWIZZLE_128B
-  bool tmap_a_ok = false;
-  CUtensorMap tmap_q{};            // [256][384]
-  bool tmap_q_ok = false;
-  CUtensorMap tmap_b2{};           // [n_rows][384] f32, box {32, 64}: the half-tile the TMEM-resident kernel loads
-  bool tmap_b2_ok = false;
   // pending tensor-core batch (knn_local_begin / knn_local_finish)
   bool knn_pending = false;
   const float* pend_q = nullptr;
@@ -112,9 +104,7 @@ struct rse_index {
   bool timeline = false;
   cudaEvent_t tl[8] = {};
   bool tl_set[8] = {};
-  int tc_filter_kind = 2;          // 2 = knn_tc3_kernel (fp16 normalised shadow, queries resident in shared memory; default),
-                                   // 0 = knn_tc_kernel<1> (TF32, queries streamed), 1 = knn_tc2_filter_kernel (TF32, queries in TMEM)
-  DevBuf tc_q, tc_thr, tc_isb, tc_rows, tc_cnt, tc_keys, tc_status;
+  DevBuf tc_thr, tc_rows, tc_cnt, tc_status;
   // fp16 normalised shadow of the corpus for knn_tc3 (built lazily at the first tensor-core batch)
   DevBuf tc_shadow, tc_q16;
   int shadow_state = 0;            // 0 = not built, 1 = usable, -1 = corpus has non-finite norms: exact scan only
@@ -166,6 +156,9 @@ struct rse_index {
   // flag would leave the second device of a multi-GPU process unconfigured)
   uint32_t attr_mask = 0;
   rse_stats stats{};
+  // device-side counters read back by rse_get_stats: [0] BM25 queries handed to the general kernel, [1] BM25
+  // finalists re-scored exactly, [2] BM25 candidates merged by the finish kernel
+  unsigned long long* dev_counters = nullptr;
 };
 
 namespace {
@@ -223,8 +216,6 @@ void release_embeddings(rse_index* h) {
   free_ptr(h->rowid);
   free_ptr(h->movie_idx);
   h->n_rows = 0; h->dim = 0;
-  h->tmap_a_ok = false;
-  h->tmap_b2_ok = false;
   free_buf(h->tc_shadow);
   h->shadow_state = 0;
 }
@@ -333,12 +324,6 @@ int knn_exact_groups(rse_index* h, const float* q_dev, const double* sb, int nq,
 typedef CUresult (*PFN_tmapEncodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                                         const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
                                         CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-
-int make_tmap_any(rse_index* h, CUtensorMap* out, const void* base, int64_t rows, int box_rows, int elem_bytes);
-
-int make_tmap(rse_index* h, CUtensorMap* out, const float* base, int64_t rows, int box_rows) {
-  return make_tmap_any(h, out, base, rows, box_rows, 4);
-}
 
 // [rows][384] row-major matrix of f32 (elem_bytes 4) or f16 (2); box = one 128-byte swizzle atom x box_rows
 int make_tmap_any(rse_index* h, CUtensorMap* out, const void* base, int64_t rows, int box_rows, int elem_bytes) {
@@ -612,122 +597,10 @@ int knn_tc3_block(rse_index* h, const float* q_dev, const double* sb, int nqb, i
 
 bool tc_eligible(const rse_index* h, int nq, int kprime) {
   if (h->tc_mode == 1 || h->dim != kScanD) return false;
-  const int64_t n_tiles = (h->n_rows + kTcBM - 1) / kTcBM;
-  if (n_tiles * kTcBM < 8ll * kprime || h->n_rows < 1024) return false;   // the probe needs a usable sample
+  if (((h->n_rows + 127) / 128) * 128 < 8ll * kprime || h->n_rows < 1024) return false;   // the probe needs a usable sample
   if (kprime * 4 > kTcCandCap || kprime * 2 > kTcRefineCap) return false;
   if (h->tc_mode == 2) return true;
-  return nq >= 48 && h->n_rows >= 262144;
-}
-
-int knn_tc_block(rse_index* h, const float* q_dev, const double* sb, int nqb, int kprime, long long* cand_dev,
-                 int* status_dev) {
-  if (!(h->attr_mask & (1u << 12))) {
-    CK(cudaFuncSetAttribute(knn_tc_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, kTcSmemBytes));
-    CK(cudaFuncSetAttribute(knn_tc_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, kTcSmemBytes));
-    h->attr_mask |= 1u << 12;
-  }
-  if (!h->tmap_a_ok) {
-    int rc = make_tmap(h, &h->tmap_a, h->emb, h->n_rows, kTcBM);
-    if (rc != RSE_OK) return rc;
-    h->tmap_a_ok = true;
-  }
-  ENSURE(h->tc_q, sizeof(float) * kTcBN * kScanD);
-  if (!h->tmap_q_ok) {
-    int rc = make_tmap(h, &h->tmap_q, static_cast<const float*>(h->tc_q.p), kTcBN, kTcBN);
-    if (rc != RSE_OK) return rc;
-    h->tmap_q_ok = true;
-  }
-  ENSURE(h->tc_thr, sizeof(float) * kTcBN);
-  ENSURE(h->tc_isb, sizeof(float) * kTcBN);
-  ENSURE(h->tc_rows, sizeof(uint2) * static_cast<size_t>(kTcBN) * kTcCandCap);
-  ENSURE(h->tc_cnt, sizeof(unsigned int) * kTcBN);
-  ENSURE(h->sel, sizeof(SelState) * kTcBN);
-
-  const int64_t n_tiles = (h->n_rows + kTcBM - 1) / kTcBM;
-  // Probe sample: every tile_stride-th 128-row tile.  Expected survivors per query ≈ K' * tile_stride
-  // (+ the 2*eps band), so the stride is as large as a third of the survivor cap allows, while the
-  // sample keeps at least 64 tiles (and 8 K' rows) so its K'-th value is a meaningful bound.
-  int64_t tile_stride = std::max<int64_t>(1, std::min<int64_t>(kTcCandCap / (3ll * kprime), n_tiles / 64));
-  int64_t n_probe = (n_tiles + tile_stride - 1) / tile_stride;
-  while (n_probe * kTcBM < 8ll * kprime && tile_stride > 1) { tile_stride /= 2; n_probe = (n_tiles + tile_stride - 1) / tile_stride; }
-  const int64_t ld_probe = n_probe * kTcBM;
-  ENSURE(h->dist, std::max(sizeof(float) * static_cast<size_t>(kScanMaxQB) * h->dist_ld,
-                           sizeof(uint32_t) * static_cast<size_t>(nqb) * ld_probe));
-  uint32_t* dist = static_cast<uint32_t*>(h->dist.p);
-  SelState* sel = static_cast<SelState*>(h->sel.p);
-  unsigned int* hist = static_cast<unsigned int*>(h->hist.p);
-  float* tcq = static_cast<float*>(h->tc_q.p);
-
-  CK(cudaMemsetAsync(tcq, 0, sizeof(float) * kTcBN * kScanD, h->stream));
-  CK(cudaMemcpyAsync(tcq, q_dev, sizeof(float) * static_cast<size_t>(nqb) * kScanD, cudaMemcpyDeviceToDevice, h->stream));
-  tc_query_consts_kernel<<<2, 128, 0, h->stream>>>(sb, nqb, static_cast<float*>(h->tc_isb.p));
-  LAUNCHED(h);
-
-  // 1. probe: approximate distances of a strided sample of tiles → K'-th smallest per query
-  const int grid_p = static_cast<int>(std::min<int64_t>(h->sm_count, (n_probe + 1) / 2));
-  knn_tc_kernel<0><<<grid_p, kTcThreads, kTcSmemBytes, h->stream>>>(
-      h->tmap_a, h->tmap_q, h->amag, h->n_rows, n_probe, tile_stride, nqb, nullptr,
-      static_cast<const float*>(h->tc_isb.p), dist, ld_probe, nullptr, nullptr, 0);
-  LAUNCHED(h);
-  select_init_kernel<<<(nqb + 127) / 128, 128, 0, h->stream>>>(sel, nqb, static_cast<unsigned int>(kprime));
-  LAUNCHED(h);
-  {
-    int blocks = static_cast<int>(std::min<int64_t>((ld_probe + 4095) / 4096, h->sm_count));
-    if (blocks < 1) blocks = 1;
-    dim3 grid(blocks, nqb);
-    static const int shifts[3] = {53, 42, 32};
-    static const int widths[3] = {11, 11, 10};
-    for (int p = 0; p < 3; ++p) {
-      select_pass_kernel<<<grid, kSelThreads, 0, h->stream>>>(dist, ld_probe, ld_probe, 0ull, sel, hist, shifts[p], widths[p]);
-      LAUNCHED(h);
-    }
-  }
-  tc_threshold_kernel<<<2, 128, 0, h->stream>>>(sel, sb, nqb, static_cast<unsigned int>(kprime), static_cast<float*>(h->tc_thr.p));
-  LAUNCHED(h);
-
-  // 2. filter pass over all rows
-  CK(cudaMemsetAsync(h->tc_cnt.p, 0, sizeof(unsigned int) * kTcBN, h->stream));
-  const int grid_f = static_cast<int>(std::min<int64_t>(h->sm_count, (n_tiles + 1) / 2));
-  cudaEvent_t e0 = nullptr, e1 = nullptr;
-  if (h->timing && h->scan_ev_used + 2 <= (1u << 16)) {
-    while (h->scan_ev.size() < h->scan_ev_used + 2) {
-      cudaEvent_t e;
-      CK(cudaEventCreate(&e));
-      h->scan_ev.push_back(e);
-    }
-    e0 = h->scan_ev[h->scan_ev_used];
-    e1 = h->scan_ev[h->scan_ev_used + 1];
-    h->scan_ev_used += 2;
-    CK(cudaEventRecord(e0, h->stream));
-  }
-  if (h->tc_filter_kind == 1) {
-    if (!(h->attr_mask & (1u << 13))) {
-      CK(cudaFuncSetAttribute(knn_tc2_filter_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kT2SmemBytes));
-      h->attr_mask |= 1u << 13;
-    }
-    if (!h->tmap_b2_ok) {
-      int rc = make_tmap(h, &h->tmap_b2, h->emb, h->n_rows, kT2HalfRows);
-      if (rc != RSE_OK) return rc;
-      h->tmap_b2_ok = true;
-    }
-    const int64_t n_tiles2 = (h->n_rows + kT2TileRows - 1) / kT2TileRows;
-    const int n_clusters = static_cast<int>(std::min<int64_t>(h->sm_count / 2, n_tiles2));
-    knn_tc2_filter_kernel<<<2 * n_clusters, kT2Threads, kT2SmemBytes, h->stream>>>(
-        h->tmap_b2, tcq, h->amag, h->n_rows, n_tiles2, static_cast<const float*>(h->tc_thr.p),
-        static_cast<uint2*>(h->tc_rows.p), static_cast<unsigned int*>(h->tc_cnt.p), kTcCandCap);
-    LAUNCHED(h);
-  } else {
-  knn_tc_kernel<1><<<grid_f, kTcThreads, kTcSmemBytes, h->stream>>>(
-      h->tmap_a, h->tmap_q, h->amag, h->n_rows, n_tiles, 1, nqb, static_cast<const float*>(h->tc_thr.p), nullptr,
-      nullptr, 0, static_cast<uint2*>(h->tc_rows.p), static_cast<unsigned int*>(h->tc_cnt.p), kTcCandCap);
-  LAUNCHED(h);
-  }
-  if (e1) CK(cudaEventRecord(e1, h->stream));
-  h->stats.knn_scan_launches++;
-  h->stats.tc_filter_launches++;
-
-  // 3. refine on the approximate values, 4. exact re-score + sort + emit (one CTA per query)
-  return knn_tc_refine(h, q_dev, sb, nqb, kprime, cand_dev, status_dev, 0);
+  return nq >= RSE_TC_MIN_BATCH && h->n_rows >= 262144;
 }
 
 // Local top-kprime for nq device-resident queries → packed candidates (device), in two halves: _begin enqueues
@@ -755,18 +628,15 @@ int knn_local_begin(rse_index* h, const float* q_dev, int nq, int kprime, long l
   // ---- tensor-core path in blocks of 256 queries, exact fallback for overflowed queries
   ENSURE(h->tc_status, sizeof(int) * nq);
   int* status = static_cast<int*>(h->tc_status.p);
-  bool use_shadow = h->tc_filter_kind == 2;
-  if (use_shadow) {
+  {
     int rc = ensure_shadow(h);
     if (rc != RSE_OK) return rc;
     if (h->shadow_state < 0) return knn_exact_groups(h, q_dev, sb, nq, kprime, cand_dev);
   }
   for (int b0 = 0; b0 < nq; b0 += kTcBN) {
     const int nqb = std::min(kTcBN, nq - b0);
-    int rc = use_shadow ? knn_tc3_block(h, q_dev + static_cast<int64_t>(b0) * h->dim, sb + b0, nqb, kprime,
-                                        cand_dev + static_cast<int64_t>(b0) * kprime * 3, status + b0)
-                        : knn_tc_block(h, q_dev + static_cast<int64_t>(b0) * h->dim, sb + b0, nqb, kprime,
-                          cand_dev + static_cast<int64_t>(b0) * kprime * 3, status + b0);
+    int rc = knn_tc3_block(h, q_dev + static_cast<int64_t>(b0) * h->dim, sb + b0, nqb, kprime,
+                           cand_dev + static_cast<int64_t>(b0) * kprime * 3, status + b0);
     if (rc != RSE_OK) return rc;
   }
   h->stats.tc_queries += nq;
@@ -824,6 +694,7 @@ int upload_queries(rse_index* h, const float* q_host, int nq) {
   ENSURE(h->q_dev, sizeof(float) * static_cast<size_t>(nq) * h->dim);
   CK(cudaMemcpyAsync(h->q_dev.p, q_host, sizeof(float) * static_cast<size_t>(nq) * h->dim, cudaMemcpyHostToDevice,
                      h->stream));
+  h->stats.h2d_bytes += static_cast<int64_t>(sizeof(float)) * nq * h->dim;
   return RSE_OK;
 }
 
@@ -891,6 +762,10 @@ int rse_create(int32_t device, rse_index** out) {
   }
   h->stream = h->own_stream;
   for (auto& ev : h->ev) cudaEventCreate(&ev);
+  if (cudaMalloc(&h->dev_counters, sizeof(unsigned long long) * 8) == cudaSuccess)
+    cudaMemset(h->dev_counters, 0, sizeof(unsigned long long) * 8);
+  else
+    h->dev_counters = nullptr;
   // diagnostics: RSE_NO_OVERLAP=1 keeps the hybrid step's BM25 on the caller's stream (no second stream)
   if (const char* ev = std::getenv("RSE_NO_OVERLAP")) h->overlap_enabled = !(ev[0] == '1');
   if (const char* ev = std::getenv("RSE_TIMELINE")) h->timeline = ev[0] == '1';
@@ -909,8 +784,8 @@ void rse_destroy(rse_index* h) {
   for (DevBuf* b : {&h->q_dev, &h->sb, &h->sel, &h->hist, &h->selkeys, &h->cand, &h->dist, &h->o_dist, &h->o_pos,
                     &h->o_rowid, &h->o_movie, &h->o_count, &h->b_tokptr, &h->b_terms, &h->b_idf, &h->b_chi, &h->b_clo,
                     &h->b_ccnt, &h->b_score, &h->b_doc, &h->b_count, &h->f_bid, &h->f_bsc, &h->f_bcnt, &h->f_sid,
-                    &h->f_sds, &h->f_scnt, &h->f_oid, &h->f_osc, &h->f_oa, &h->f_ob, &h->f_ocnt, &h->tc_q, &h->tc_thr, &h->tc_isb,
-                    &h->tc_rows, &h->tc_cnt, &h->tc_keys, &h->tc_status, &h->tc_q16, &h->b_shi, &h->b_slo, &h->b_scnt,
+                    &h->f_sds, &h->f_scnt, &h->f_oid, &h->f_osc, &h->f_oa, &h->f_ob, &h->f_ocnt, &h->tc_thr,
+                    &h->tc_rows, &h->tc_cnt, &h->tc_status, &h->tc_q16, &h->b_shi, &h->b_slo, &h->b_scnt,
                     &h->b_status, &h->b_flagged})
     free_buf(*b);
   if (h->pin_status) cudaFreeHost(h->pin_status);
@@ -935,6 +810,7 @@ void rse_destroy(rse_index* h) {
   if (h->stream_b) cudaStreamDestroy(h->stream_b);
   free_ptr(h->doc_ids);
   free_ptr(h->movie_ids);
+  free_ptr(h->dev_counters);
   for (auto& ev : h->ev) if (ev) cudaEventDestroy(ev);
   for (auto& ev : h->scan_ev) cudaEventDestroy(ev);
   if (h->own_stream) cudaStreamDestroy(h->own_stream);
@@ -971,11 +847,8 @@ int rse_set_fma(rse_index* h, int32_t use_fma) {
 
 int rse_set_tc_mode(rse_index* h, int32_t mode) {
   if (!h) return RSE_ERR_INVALID;
-  if (mode < 0 || mode > 6) return fail(h, RSE_ERR_INVALID, "rse_set_tc_mode: mode must be 0..6");
-  // 0 / 2: fp16-shadow kernel (knn_tc3); 3 / 4: TF32, queries resident in TMEM (knn_tc2);
-  // 5 / 6: TF32, queries streamed (knn_tc) — auto / forced respectively
-  h->tc_filter_kind = (mode >= 5) ? 0 : (mode >= 3 ? 1 : 2);
-  h->tc_mode = (mode == 3 || mode == 5) ? 0 : ((mode == 4 || mode == 6) ? 2 : mode);
+  if (mode < 0 || mode > 2) return fail(h, RSE_ERR_INVALID, "rse_set_tc_mode: mode must be 0..2");
+  h->tc_mode = mode;
   return RSE_OK;
 }
 
@@ -1005,6 +878,15 @@ int rse_get_stats(rse_index* h, rse_stats* out) {
     }
     h->scan_ev_used = 0;
   }
+  if (h->dev_counters) {
+    unsigned long long c[3] = {0, 0, 0};
+    CK(cudaStreamSynchronize(h->stream));
+    if (h->stream_b) CK(cudaStreamSynchronize(h->stream_b));
+    CK(cudaMemcpy(c, h->dev_counters, sizeof(c), cudaMemcpyDeviceToHost));
+    h->stats.bm25_fallback_queries = static_cast<int64_t>(c[0]);
+    h->stats.bm25_finalists = static_cast<int64_t>(c[1]);
+    h->stats.bm25_candidates = static_cast<int64_t>(c[2]);
+  }
   *out = h->stats;
   return RSE_OK;
 }
@@ -1015,6 +897,11 @@ int rse_stats_reset(rse_index* h) {
   const int dim = h->stats.emb_dim;
   h->stats = rse_stats{};
   h->scan_ev_used = 0;
+  if (h->dev_counters) {
+    CK(cudaStreamSynchronize(h->stream));
+    if (h->stream_b) CK(cudaStreamSynchronize(h->stream_b));
+    CK(cudaMemset(h->dev_counters, 0, sizeof(unsigned long long) * 8));
+  }
   h->stats.emb_rows = rows; h->stats.emb_dim = dim; h->stats.bm25_postings = post; h->stats.bm25_docs = docs;
   return RSE_OK;
 }
@@ -1110,6 +997,7 @@ int rse_knn(rse_index* h, const float* q_host, int32_t nq, int32_t kprime, float
   if (out_rowid) CK(cudaMemcpyAsync(out_rowid, h->o_rowid.p, sizeof(long long) * n, cudaMemcpyDeviceToHost, h->stream));
   if (out_movie_idx) CK(cudaMemcpyAsync(out_movie_idx, h->o_movie.p, sizeof(int) * n, cudaMemcpyDeviceToHost, h->stream));
   CK(cudaMemcpyAsync(out_count, h->o_count.p, sizeof(int) * nq, cudaMemcpyDeviceToHost, h->stream));
+  h->stats.d2h_bytes += static_cast<int64_t>(n) * 16 + static_cast<int64_t>(nq) * 4;
   if (h->timing) CK(cudaEventRecord(h->ev[3], h->stream));
   CK(cudaStreamSynchronize(h->stream));
   if (h->timing) {
@@ -1148,6 +1036,7 @@ int rse_knn_movies(rse_index* h, const float* q_host, int32_t nq, int32_t k, int
   CK(cudaMemcpyAsync(out_chunk_rowid, h->o_rowid.p, sizeof(long long) * n, cudaMemcpyDeviceToHost, h->stream));
   CK(cudaMemcpyAsync(out_movie_idx, h->o_movie.p, sizeof(int) * n, cudaMemcpyDeviceToHost, h->stream));
   CK(cudaMemcpyAsync(out_count, h->o_count.p, sizeof(int) * nq, cudaMemcpyDeviceToHost, h->stream));
+  h->stats.d2h_bytes += static_cast<int64_t>(n) * 16 + static_cast<int64_t>(nq) * 4;
   if (h->timing) CK(cudaEventRecord(h->ev[3], h->stream));
   CK(cudaStreamSynchronize(h->stream));
   if (h->timing) {
@@ -1290,6 +1179,7 @@ int bm25_stage(rse_index* h, const int32_t* tok_indptr, const int32_t* term_rows
     CK(cudaMemcpyAsync(h->b_idf.p, idf, sizeof(double) * ntok, cudaMemcpyHostToDevice, h->stream));
   }
   CK(cudaEventRecord(h->ev_stage, h->stream));
+  h->stats.h2d_bytes += static_cast<int64_t>(bytes_ptr) + (ntok > 0 ? static_cast<int64_t>(ntok) * 12 : 0);
   return RSE_OK;
 }
 
@@ -1372,6 +1262,7 @@ int bm25_run(rse_index* h, int nq, int k, double k1, double b) {
     ENSURE(h->b_flagged, sizeof(int) * (std::min(nq, chunk) + 1));
     CK(cudaMemsetAsync(h->b_status.p, 0, sizeof(int) * nq, h->stream));
   }
+  h->stats.bm25_queries += nq;
   for (int q0 = 0; q0 < nq; q0 += chunk) {
     const int nc = std::min(chunk, nq - q0);
     // candidate buffers are indexed by absolute q inside the kernels → offset the base pointers
@@ -1395,7 +1286,8 @@ int bm25_run(rse_index* h, int nq, int k, double k1, double b) {
       bm25_fx_finish_kernel<<<nc, kBmThreads, 0, h->stream>>>(
           fin, fcnt, ng, status, h->indptr, h->post16, h->roff, h->nr, static_cast<const int32_t*>(h->b_tokptr.p),
           static_cast<const int32_t*>(h->b_terms.p), static_cast<const double*>(h->b_idf.p), q0, k,
-          static_cast<double*>(h->b_score.p), static_cast<int*>(h->b_doc.p), static_cast<int*>(h->b_count.p));
+          static_cast<double*>(h->b_score.p), static_cast<int*>(h->b_doc.p), static_cast<int*>(h->b_count.p),
+          h->dev_counters);
       LAUNCHED(h);
     } else if (stream) {
       const size_t per_qs = static_cast<size_t>(ng) * std::max(k, 2 * kFxFinalCap);
@@ -1415,7 +1307,7 @@ int bm25_run(rse_index* h, int nq, int k, double k1, double b) {
     int* flagged = nullptr;
     if (stream) {
       flagged = static_cast<int*>(h->b_flagged.p);
-      bm25_flag_compact_kernel<<<1, 256, 0, h->stream>>>(status, q0, nc, flagged);
+      bm25_flag_compact_kernel<<<1, 256, 0, h->stream>>>(status, q0, nc, flagged, h->dev_counters);
       LAUNCHED(h);
     }
     dim3 grid(h->nr, stream ? std::min(nc, 16) : nc);
@@ -1461,6 +1353,7 @@ int rse_bm25(rse_index* h, const int32_t* tok_indptr, const int32_t* term_rows, 
   CK(cudaMemcpyAsync(out_score, h->b_score.p, sizeof(double) * n, cudaMemcpyDeviceToHost, h->stream));
   CK(cudaMemcpyAsync(out_doc_idx, h->b_doc.p, sizeof(int) * n, cudaMemcpyDeviceToHost, h->stream));
   CK(cudaMemcpyAsync(out_count, h->b_count.p, sizeof(int) * nq, cudaMemcpyDeviceToHost, h->stream));
+  h->stats.d2h_bytes += static_cast<int64_t>(n) * 12 + static_cast<int64_t>(nq) * 4;
   if (h->timing) CK(cudaEventRecord(h->ev[3], h->stream));
   CK(cudaStreamSynchronize(h->stream));
   if (h->timing) {
@@ -1479,10 +1372,10 @@ int fuse_launch(rse_index* h, int mode, double param, int tie_mode, int nq, int 
   if (limit < 1 || limit > RSE_MAX_FUSE_LIMIT) return fail(h, RSE_ERR_UNSUPPORTED, "fusion: limit must be in [1, 128]");
   if (tie_mode != RSE_TIE_REFERENCE && tie_mode != RSE_TIE_BY_ID) return fail(h, RSE_ERR_INVALID, "fusion: bad tie_mode");
   const size_t smem = fuse_smem_bytes(limit);
-  static size_t attr_smem = 0;
-  if (smem > 48 * 1024 && smem > attr_smem) {
-    CK(cudaFuncSetAttribute(fuse_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
-    attr_smem = smem;
+  if (smem > 48 * 1024 && !(h->attr_mask & (1u << 15))) {     // per handle: the attribute is per device
+    CK(cudaFuncSetAttribute(fuse_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                            static_cast<int>(fuse_smem_bytes(RSE_MAX_FUSE_LIMIT))));
+    h->attr_mask |= 1u << 15;
   }
   fuse_kernel<<<nq, 32, smem, h->stream>>>(in, nq, limit, mode, param, tie_mode, o_id, o_sc, o_a, o_b, o_cnt);
   LAUNCHED(h);
@@ -1726,6 +1619,7 @@ int rse_hybrid_fetch(rse_index* h, int32_t limit, int64_t* out_id, double* out_s
     h->pin_out_bytes = bytes + bytes / 2;
   }
   CK(cudaMemcpyAsync(h->pin_out, h->f_pack.p, bytes, cudaMemcpyDeviceToHost, h->stream));
+  h->stats.d2h_bytes += static_cast<int64_t>(bytes);
   CK(cudaStreamSynchronize(h->stream));
   tl_print(h);
   std::memcpy(out_id, h->pin_out, 8 * n);
@@ -1815,8 +1709,12 @@ int rse_hybrid_submit(rse_index* h, int32_t mode, double param, int32_t tie_mode
     if (ce == cudaSuccess) ce = cudaStreamWaitEvent(h->stream_d2h, h->ev_fused, 0);
     if (ce == cudaSuccess) ce = cudaMemcpyAsync(sl.pin, h->f_pack.p, bytes, cudaMemcpyDeviceToHost, h->stream_d2h);
     if (ce == cudaSuccess) ce = cudaEventRecord(sl.ev, h->stream_d2h);
+    if (ce == cudaSuccess) h->stats.d2h_bytes += static_cast<int64_t>(bytes);
   }
   swap_in_out();
+  // the staged batch lives in the SLOT's buffers: nothing is staged in the handle's own any more, so a later
+  // rse_hybrid_run / _fetch without a fresh rse_hybrid_stage must fail instead of touching stale pointers
+  h->staged_nq = 0; h->pack_n = 0; h->pack_nq = 0;
   if (rc != RSE_OK) return rc;
   if (ce != cudaSuccess) return fail(h, RSE_ERR_CUDA, std::string("rse_hybrid_submit: ") + cudaGetErrorString(ce));
   sl.deferred = h->run_deferred;
@@ -1852,11 +1750,15 @@ int rse_hybrid_collect(rse_index* h, int64_t ticket, int32_t* out_nq, int32_t* o
       // is complete and parked in its own pinned slot once the stream has drained.
       CK(cudaStreamSynchronize(h->stream));
       ++h->pipeline_reruns;
-      ++h->next_collect;
+      // the ticket stays collectable until the re-run has succeeded (a failed re-run can be retried or drained)
+      const int rc = rse_hybrid(h, sl.mode, sl.param, sl.tie_mode, sl.limit, sl.knn_multiplier, sl.nq, h->pin_q[ticket & 1],
+                                sl.tok_indptr.data(), sl.term_rows.empty() ? nullptr : sl.term_rows.data(), sl.k1, sl.b,
+                                out_id, out_score, out_a, out_b, out_count);
+      h->staged_nq = 0; h->pack_n = 0; h->pack_nq = 0;
+      if (rc != RSE_OK) return rc;
       sl.deferred = false;
-      return rse_hybrid(h, sl.mode, sl.param, sl.tie_mode, sl.limit, sl.knn_multiplier, sl.nq, h->pin_q[ticket & 1],
-                        sl.tok_indptr.data(), sl.term_rows.empty() ? nullptr : sl.term_rows.data(), sl.k1, sl.b,
-                        out_id, out_score, out_a, out_b, out_count);
+      ++h->next_collect;
+      return RSE_OK;
     }
   }
   std::memcpy(out_id, sl.pin, 8 * n);
@@ -1865,6 +1767,21 @@ int rse_hybrid_collect(rse_index* h, int64_t ticket, int32_t* out_nq, int32_t* o
   std::memcpy(out_b, sl.pin + 24 * n, 8 * n);
   std::memcpy(out_count, sl.pin + 32 * n, 4 * static_cast<size_t>(sl.nq));
   ++h->next_collect;
+  return RSE_OK;
+}
+
+int rse_hybrid_drain(rse_index* h, int32_t* out_dropped) {
+  if (!h) return RSE_ERR_INVALID;
+  CK(cudaSetDevice(h->device));
+  int dropped = 0;
+  while (h->next_collect < h->next_ticket) {
+    rse_index::OutSlot& sl = h->out_slot[h->next_collect & 1];
+    if (sl.ev) CK(cudaEventSynchronize(sl.ev));
+    sl.deferred = false;
+    ++h->next_collect;
+    ++dropped;
+  }
+  if (out_dropped) *out_dropped = dropped;
   return RSE_OK;
 }
 

@@ -205,21 +205,28 @@ class HybridSearch:
                       "sem_rank": None if ob[q, j] < 0 else int(ob[q, j])} for j in range(oc[q])] for q in range(nq)]
 
         pending = None                                           # (ticket, nq) of the batch in flight
-        for token_lists, query_vecs in batches:
-            if len(token_lists) == 0:
-                if pending is not None:
-                    yield unpack(self._index.hybrid_collect(pending[0]), pending[1])
-                    pending = None
-                yield []
-                continue
-            tok_indptr, rows = kw._term_rows(token_lists)
-            ticket = self._index.hybrid_submit(0, float(k), limit, query_vecs, tok_indptr, rows,
-                                               knn_multiplier=knn_multiplier, k1=k1, b=b, tie_mode=self.tie_mode)
+        try:
+            for token_lists, query_vecs in batches:
+                if len(token_lists) == 0:
+                    if pending is not None:
+                        done, pending = pending, None
+                        yield unpack(self._index.hybrid_collect(done[0]), done[1])
+                    yield []
+                    continue
+                tok_indptr, rows = kw._term_rows(token_lists)
+                ticket = self._index.hybrid_submit(0, float(k), limit, query_vecs, tok_indptr, rows,
+                                                   knn_multiplier=knn_multiplier, k1=k1, b=b, tie_mode=self.tie_mode)
+                done, pending = pending, (ticket, len(token_lists))
+                if done is not None:
+                    yield unpack(self._index.hybrid_collect(done[0]), done[1])
             if pending is not None:
-                yield unpack(self._index.hybrid_collect(pending[0]), pending[1])
-            pending = (ticket, len(token_lists))
-        if pending is not None:
-            yield unpack(self._index.hybrid_collect(pending[0]), pending[1])
+                done, pending = pending, None
+                yield unpack(self._index.hybrid_collect(done[0]), done[1])
+        finally:
+            # a consumer that stops iterating early (GeneratorExit) or an exception between a submit and its
+            # collect must not leave tickets in flight: the handle is shared per (db, device) and collects in
+            # submission order, so a stale ticket would wedge every later stream call
+            self._index.hybrid_drain()
 
     # ---------------- cleanup (hybrid_search.py:382-384) ---------------- #
     def close(self) -> None:

@@ -27,7 +27,7 @@ def test_library_exports_every_declared_symbol():
     for name in declared:
         assert hasattr(L, name), f"{name} declared in rse.h but not exported by librse.so"
     assert declared == set(_lib.EXPORTED_SYMBOLS), declared ^ set(_lib.EXPORTED_SYMBOLS)
-    assert L.rse_abi_version() == 1
+    assert L.rse_abi_version() == 2
 
 
 def test_no_cpu_fallback_without_gpu():
@@ -295,6 +295,11 @@ def test_rrf_search_stream_keeps_two_batches_in_flight_and_the_order(tmp_path):
             oa = np.tile(np.arange(limit, dtype=np.float64), (nq, 1)); oa[:, -1] = -1.0
             ob = -np.ones((nq, limit))
             return oid, osc, oa, ob, np.full(nq, limit - 1, np.int32)
+        def hybrid_drain(self):
+            n = len(self.outstanding)
+            self.outstanding.clear()
+            self.log.append(("drain", n))
+            return n
 
     class Arr:
         term_row = {"a": 0, "b": 1}
@@ -314,12 +319,29 @@ def test_rrf_search_stream_keeps_two_batches_in_flight_and_the_order(tmp_path):
         sizes = [3, 1, 0, 2, 4]
         batches = [([["a", "zz"]] * n, np.zeros((n, 8), np.float32)) for n in sizes]
         out = list(hs.rrf_search_stream(iter(batches), k=60, limit=4))
+        log_full = list(fake.log)
+        # a consumer that stops early, or a failing submit, must not leave a ticket in flight on the
+        # shared handle — the generator drains on exit and a second stream works
+        gen = hs.rrf_search_stream(iter(batches), k=60, limit=4)
+        first = next(gen)
+        assert len(first) == 3 and len(fake.outstanding) == 1            # batch 1 is in flight behind batch 0
+        gen.close()
+        assert not fake.outstanding and fake.log[-1] == ("drain", 1)
+        def boom():
+            yield batches[0]
+            yield batches[1]
+            raise RuntimeError("tokenizer failed")
+        with pytest.raises(RuntimeError, match="tokenizer failed"):
+            list(hs.rrf_search_stream(boom(), k=60, limit=4))
+        assert not fake.outstanding
+        again = list(hs.rrf_search_stream(iter(batches[:2]), k=60, limit=4))
+        assert [len(o) for o in again] == sizes[:2] and not fake.outstanding
     finally:
         del runtime._handles[key]
     assert [len(o) for o in out] == sizes
     assert fake.max_outstanding == 2 and not fake.outstanding
-    assert fake.log == ["ids", ("submit", 0), ("submit", 1), ("collect", 0), ("collect", 1),      # empty batch drains
-                        ("submit", 2), ("submit", 3), ("collect", 2), ("collect", 3)]
+    assert log_full == ["ids", ("submit", 0), ("submit", 1), ("collect", 0), ("collect", 1),      # empty batch drains
+                        ("submit", 2), ("submit", 3), ("collect", 2), ("collect", 3), ("drain", 0)]
     # batch i carries ticket i's ids, three hits per query (count = limit - 1), last rank None-able fields mapped
     assert out[0][0][0] == {"id": 0, "score": 1.0, "bm25_rank": 0, "sem_rank": None}
     assert [h["id"] for h in out[3][1]] == [200, 201, 202] and [h["id"] for h in out[4][0]] == [300, 301, 302]
