@@ -155,6 +155,7 @@ class Index:
             self._h = c_void_p()
             raise RseError(rc, msg.decode() if msg else "rse_create failed")
         self.device = int(device)
+        self.n_rows, self.dim, self.n_docs = 0, 0, 0
         self._keepalive = []
         self._tickets = {}
 

@@ -34,7 +34,7 @@ class HybridSearch:
         self.device = device
         self.tie_mode = {"reference": _lib.TIE_REFERENCE, "id": _lib.TIE_BY_ID}[tie_mode]
         kw_extra = {k: v for k, v in retriever_kwargs.items() if k in ("tokenizer",)}
-        sem_extra = {k: v for k, v in retriever_kwargs.items() if k in ("encoder",)}
+        sem_extra = {k: v for k, v in retriever_kwargs.items() if k in ("encoder", "fallback_build")}
         if KeywordSearch.__module__.startswith(__package__):
             kw_extra["device"] = device
         if SemanticSearch.__module__.startswith(__package__):
@@ -45,6 +45,31 @@ class HybridSearch:
                                        overlap=overlap, force=force, **sem_extra)
         self._index = runtime.acquire(self.db_path, device)      # fusion kernels (+ shared with GPU retrievers)
         self._closed = False
+
+    @classmethod
+    def from_loaded(cls, index: "_lib.Index", term_row: Dict[str, int], doc_ids, movie_ids, *, registry_key,
+                    device: int = 0, tie_mode: str = "reference") -> "HybridSearch":
+        """The batch / stream entry points over a handle whose indexes are ALREADY in HBM (rse_load_bm25 +
+        rse_load_embeddings / rse_attach_embeddings_dev done by the caller): for corpora that never lived in a
+        SQLite file — synthetic benchmarks, a shard of a larger service.  The single-query text methods, which
+        read titles from SQLite, are not available on such an object.  ``registry_key`` names the handle in
+        ``runtime`` (any path-like string unique to it)."""
+        from types import SimpleNamespace
+        self = cls.__new__(cls)
+        self.db_path = Path(registry_key)
+        self.device = device
+        self.tie_mode = {"reference": _lib.TIE_REFERENCE, "id": _lib.TIE_BY_ID}[tie_mode]
+        kw = KeywordSearch.__new__(KeywordSearch)
+        kw._arr = SimpleNamespace(term_row=term_row, doc_ids=np.ascontiguousarray(doc_ids, np.int64))
+        kw._closed = True
+        sem = SemanticSearch.__new__(SemanticSearch)
+        sem._arr = SimpleNamespace(movie_ids=np.ascontiguousarray(movie_ids, np.int64),
+                                   emb=np.zeros((int(index.n_rows), 0), np.float32))
+        sem._closed = True
+        self.keyword, self.semantic, self._index = kw, sem, index
+        runtime.adopt(self.db_path, device, index)
+        self._closed = False
+        return self
 
     # ---------------- wrappers (hybrid_search.py:57-88) ---------------- #
     def _bm25_search(self, query: str, limit: int) -> List[Dict[str, Any]]:
@@ -157,26 +182,56 @@ class HybridSearch:
         return isinstance(self.keyword, KeywordSearch) and isinstance(self.semantic, SemanticSearch) and \
             type(self.keyword).__module__.startswith(__package__) and type(self.semantic).__module__.startswith(__package__)
 
+    def _ensure_id_tables(self):
+        reg = runtime.parts(self.db_path, self.device)
+        if "ids" not in reg:
+            self._index.set_id_tables(self.keyword._arr.doc_ids, self.semantic._arr.movie_ids)
+            reg["ids"] = True
+
     def _hybrid_batch(self, mode, param, token_lists, query_vecs, limit, knn_multiplier, k1, b):
         if not self._gpu_retrievers():
             raise RuntimeError("*_batch needs the GPU KeywordSearch and SemanticSearch of this package")
         kw, sem = self.keyword, self.semantic
-        reg = runtime.parts(self.db_path, self.device)
-        if "ids" not in reg:
-            self._index.set_id_tables(kw._arr.doc_ids, sem._arr.movie_ids)
-            reg["ids"] = True
         tok_indptr, rows = kw._term_rows(token_lists)
+        nq = len(tok_indptr) - 1
+        if sem._arr.emb.shape[0] == 0 or len(kw._arr.doc_ids) == 0:
+            # one side has no index (keyword-only or embeddings-only database): the reference degrades to the
+            # other retriever (tests/test_hybrid_search.py:94-124); same here, still on the device
+            L = int(limit)
+            bid = np.full((nq, L), -1, np.int64); bsc = np.zeros((nq, L)); bc = np.zeros(nq, np.int32)
+            sid = np.full((nq, L), -1, np.int64); sds = np.zeros((nq, L)); sc = np.zeros(nq, np.int32)
+            if len(kw._arr.doc_ids):
+                score, doc, bc = self._index.bm25(tok_indptr, rows, L, k1, b)
+                bid = np.where(doc >= 0, kw._arr.doc_ids[np.clip(doc, 0, None)], -1)
+                bsc = score
+            if sem._arr.emb.shape[0]:
+                dist, _rowid, movie, sc = self._index.knn_movies(query_vecs, L, max(L * knn_multiplier, L))
+                sid = np.where(movie >= 0, sem._arr.movie_ids[np.clip(movie, 0, None)], -1)
+                sds = dist.astype(np.float64)
+            if mode == 0:
+                oid, osc, orb, ors, oc = self._index.fuse_rrf(L, param, bid, bsc, bc, sid, sds, sc, tie_mode=self.tie_mode)
+                return oid, osc, orb.astype(np.float64), ors.astype(np.float64), oc
+            oid, ob, osem, osc, oc = self._index.fuse_weighted(L, param, bid, bsc, bc, sid, sds, sc, tie_mode=self.tie_mode)
+            return oid, osc, ob, osem, oc
+        self._ensure_id_tables()
         return self._index.hybrid(mode, param, limit, query_vecs, tok_indptr, rows, knn_multiplier=knn_multiplier,
                                   k1=k1, b=b, tie_mode=self.tie_mode)
 
-    def rrf_search_batch(self, token_lists: Sequence[Sequence[str]], query_vecs, k=60, limit: int = 10,
-                         knn_multiplier: int = 10, k1: float = 1.5, b: float = 0.75):
-        """[{id, score, bm25_rank, sem_rank}] per query; BM25 + KNN + aggregation + RRF in one device call."""
-        oid, osc, oa, ob, oc = self._hybrid_batch(0, float(k), token_lists, query_vecs, limit, knn_multiplier, k1, b)
-        return [[{"id": int(oid[q, j]), "score": float(osc[q, j]),
-                  "bm25_rank": None if oa[q, j] < 0 else int(oa[q, j]),
-                  "sem_rank": None if ob[q, j] < 0 else int(ob[q, j])} for j in range(oc[q])]
-                for q in range(len(token_lists))]
+    @staticmethod
+    def _unpack_rrf(res, nq):
+        """[{id, score, bm25_rank, sem_rank}] per query from the packed arrays (one bulk ``tolist`` per array:
+        per-element numpy indexing cost 4x the device step for a 256-query batch)."""
+        oid, osc, oa, ob, oc = (x.tolist() for x in res)
+        return [[{"id": i, "score": s, "bm25_rank": None if a < 0 else int(a), "sem_rank": None if b_ < 0 else int(b_)}
+                 for i, s, a, b_, _ in zip(oid[q], osc[q], oa[q], ob[q], range(oc[q]))] for q in range(nq)]
+
+    def rrf_search_batch(self, token_lists, query_vecs, k=60, limit: int = 10, knn_multiplier: int = 10,
+                         k1: float = 1.5, b: float = 0.75, as_arrays: bool = False):
+        """[{id, score, bm25_rank, sem_rank}] per query; BM25 + KNN + aggregation + RRF in one device call.
+        ``as_arrays=True`` returns the packed result instead — (id int64, score, bm25_rank, sem_rank as float64
+        with -1 = None, each [nq, limit]; count int32[nq]) — for callers that do not want Python objects."""
+        res = self._hybrid_batch(0, float(k), token_lists, query_vecs, limit, knn_multiplier, k1, b)
+        return res if as_arrays else self._unpack_rrf(res, len(res[4]))
 
     def weighted_search_batch(self, token_lists: Sequence[Sequence[str]], query_vecs, alpha: float, limit: int = 5,
                               knn_multiplier: int = 10, k1: float = 1.5, b: float = 0.75):
@@ -185,29 +240,27 @@ class HybridSearch:
                   "score": float(osc[q, j])} for j in range(oc[q])] for q in range(len(token_lists))]
 
     def rrf_search_stream(self, batches, k=60, limit: int = 10, knn_multiplier: int = 10, k1: float = 1.5,
-                          b: float = 0.75):
+                          b: float = 0.75, as_arrays: bool = False):
         """Serving loop over an iterable of ``(token_lists, query_vecs)`` batches: yields what ``rrf_search_batch``
         returns for each batch, in order, while the NEXT batch is already enqueued on the device
         (``rse_hybrid_submit`` / ``rse_hybrid_collect``, two batches in flight) — the device never waits for the host
-        to stage inputs or unpack results."""
+        to stage inputs or unpack results.  ``token_lists`` may be the pre-flattened ``(tok_indptr, tokens)`` pair
+        ``KeywordSearch._term_rows`` accepts; ``as_arrays`` as in ``rrf_search_batch``."""
         if not self._gpu_retrievers():
             raise RuntimeError("*_stream needs the GPU KeywordSearch and SemanticSearch of this package")
-        kw, sem = self.keyword, self.semantic
-        reg = runtime.parts(self.db_path, self.device)
-        if "ids" not in reg:
-            self._index.set_id_tables(kw._arr.doc_ids, sem._arr.movie_ids)
-            reg["ids"] = True
+        kw = self.keyword
+        self._ensure_id_tables()
 
         def unpack(res, nq):
-            oid, osc, oa, ob, oc = res
-            return [[{"id": int(oid[q, j]), "score": float(osc[q, j]),
-                      "bm25_rank": None if oa[q, j] < 0 else int(oa[q, j]),
-                      "sem_rank": None if ob[q, j] < 0 else int(ob[q, j])} for j in range(oc[q])] for q in range(nq)]
+            return res if as_arrays else self._unpack_rrf(res, nq)
+
+        def n_queries(tl):
+            return len(tl[0]) - 1 if isinstance(tl, tuple) else len(tl)
 
         pending = None                                           # (ticket, nq) of the batch in flight
         try:
             for token_lists, query_vecs in batches:
-                if len(token_lists) == 0:
+                if n_queries(token_lists) == 0:
                     if pending is not None:
                         done, pending = pending, None
                         yield unpack(self._index.hybrid_collect(done[0]), done[1])
@@ -216,7 +269,7 @@ class HybridSearch:
                 tok_indptr, rows = kw._term_rows(token_lists)
                 ticket = self._index.hybrid_submit(0, float(k), limit, query_vecs, tok_indptr, rows,
                                                    knn_multiplier=knn_multiplier, k1=k1, b=b, tie_mode=self.tie_mode)
-                done, pending = pending, (ticket, len(token_lists))
+                done, pending = pending, (ticket, n_queries(token_lists))
                 if done is not None:
                     yield unpack(self._index.hybrid_collect(done[0]), done[1])
             if pending is not None:

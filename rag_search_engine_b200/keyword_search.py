@@ -104,14 +104,40 @@ class KeywordSearch:
         return cls(docs_path=None, db_path=db_path, **kw)
 
     # ------------------------------------------------------------------ BM25 search
-    def _term_rows(self, token_lists: Sequence[Sequence[str]]):
-        tr = self._arr.term_row
+    def _term_rows(self, token_lists):
+        """Query tokens → (tok_indptr int32[nq+1], term_rows int32[ntok]) for rse_bm25 / rse_hybrid: the CSR row of
+        every token in query order, duplicates kept, -1 for a term the index does not hold
+        (keyword_search.py:205-210).  Accepts a sequence of token lists, or a pre-flattened
+        ``(tok_indptr, tokens)`` pair where ``tokens`` is a numpy array of str — that form is resolved with one
+        ``searchsorted`` over the sorted vocabulary instead of a dict lookup per token."""
+        if isinstance(token_lists, tuple) and len(token_lists) == 2 and isinstance(token_lists[1], np.ndarray):
+            tok_indptr, toks = token_lists
+            tok_indptr = np.ascontiguousarray(tok_indptr, np.int32)
+            if toks.size == 0:
+                return tok_indptr, np.zeros(1, np.int32)
+            vocab, rows_of = self._sorted_vocab()
+            pos = np.searchsorted(vocab, toks)
+            pos[pos >= len(vocab)] = 0
+            hit = vocab[pos] == toks
+            return tok_indptr, np.where(hit, rows_of[pos], -1).astype(np.int32)
+        get = self._arr.term_row.get
+        lens = np.fromiter((len(t) for t in token_lists), np.int64, count=len(token_lists))
         tok_indptr = np.zeros(len(token_lists) + 1, np.int32)
-        rows: List[int] = []
-        for i, toks in enumerate(token_lists):
-            rows.extend(tr.get(t, -1) for t in toks)
-            tok_indptr[i + 1] = len(rows)
-        return tok_indptr, np.array(rows if rows else [0], np.int32)
+        np.cumsum(lens, out=tok_indptr[1:])
+        n = int(tok_indptr[-1])
+        if n == 0:
+            return tok_indptr, np.zeros(1, np.int32)
+        rows = np.fromiter((get(t, -1) for toks in token_lists for t in toks), np.int32, count=n)
+        return tok_indptr, rows
+
+    def _sorted_vocab(self):
+        sv = getattr(self, "_vocab_sorted", None)
+        if sv is None:
+            terms = np.array(list(self._arr.term_row.keys()), dtype=np.str_)
+            rows = np.fromiter(self._arr.term_row.values(), np.int32, count=len(terms))
+            order = np.argsort(terms, kind="stable")
+            sv = self._vocab_sorted = (terms[order], rows[order])
+        return sv
 
     def search_tokens(self, token_lists: Sequence[Sequence[str]], k: int = 10, k1: float = 1.5, b: float = 0.75):
         """Batch entry point on pre-tokenised queries → [(doc_id int64[n], score float64[n])] per query."""

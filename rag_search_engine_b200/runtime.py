@@ -24,6 +24,11 @@ def acquire(db_path, device: int = 0) -> "_lib.Index":
     return ent[0]
 
 
+def adopt(key_path, device: int, index: "_lib.Index") -> None:
+    """Register a handle the caller created and loaded itself (HybridSearch.from_loaded); never closed by release()."""
+    _handles.setdefault((str(Path(key_path).resolve()), int(device)), [index, 1 << 30, {}])
+
+
 def parts(db_path, device: int = 0) -> dict:
     return _handles[(str(Path(db_path).resolve()), int(device))][2]
 

@@ -30,7 +30,7 @@ def _default_encoder():
 class SemanticSearch:
     def __init__(self, docs_path: Path | str | None = None, db_path: Path | str | None = None,
                  max_chunk_size: int = 3, overlap: int = 1, force: bool = False, *, encoder=None,
-                 device: int = 0) -> None:
+                 device: int = 0, fallback_build: bool = False) -> None:
         self.model = encoder if encoder is not None else _default_encoder()
         self.max_chunk_size = max_chunk_size
         self.overlap = overlap
@@ -38,11 +38,13 @@ class SemanticSearch:
         self.db_path.parent.mkdir(parents=True, exist_ok=True)
         self.docs_path = Path(docs_path) if docs_path else None
         self.device = device
+        self.fallback_build = fallback_build
         if self.docs_path is not None:
             self._build(force)
         self.conn = sqlite3.connect(self.db_path)
         self.conn.execute("PRAGMA journal_mode=WAL")
         self.conn.execute("PRAGMA synchronous=NORMAL")
+        store._init_schema(self.conn)                         # a fresh database opens empty, as the reference's does
         self._index = runtime.acquire(self.db_path, device)
         self._closed = False
         self._load()
@@ -62,6 +64,11 @@ class SemanticSearch:
             return
         except ImportError:
             pass
+        if not self.fallback_build:
+            raise RuntimeError("the index build stays on the reference (SQLite + sqlite-vec, north_star) and the "
+                               "reference package is not importable here; pass fallback_build=True to freeze the "
+                               "embeddings into a GPU-ONLY database (vec0 shadow tables without the virtual table: "
+                               "sqlite-vec / the reference cannot open it)")
         if self.model is None:
             raise RuntimeError("SemanticSearch build needs an encoder (sentence-transformers is not installed): "
                                "pass encoder=<object with .encode(texts)>")
@@ -99,6 +106,12 @@ class SemanticSearch:
             arr = store.load_or_export(self.conn, self.db_path, "emb")
             if arr.emb.shape[0] > 0:
                 self._index.load_embeddings(arr.emb, valid=arr.valid, rowid=arr.rowid, movie_idx=arr.movie_idx)
+            else:
+                # no chunk embeddings (keyword-only / fresh database): query_top_k returns [] like the reference;
+                # the handle still needs a dimension for the batch entry points' reshape
+                self._index.dim = int(arr.dim) or (int(self.model.get_sentence_embedding_dimension())
+                                                   if self.model is not None else 384)
+                self._index.n_rows = 0
             reg["emb"] = arr
         self._arr: store.EmbArrays = reg["emb"]
 

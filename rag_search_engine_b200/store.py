@@ -15,7 +15,10 @@ embeddings to disk in the reference's on-disk format where the reference's own b
 """
 from __future__ import annotations
 
+import hashlib
 import json
+import logging
+import os
 import sqlite3
 from dataclasses import dataclass, field
 from pathlib import Path
@@ -28,6 +31,8 @@ from .textutil import Tokenizer, sentence_chunks
 VEC0_BLOCK = 1024
 TITLE_END_TOKEN = "[TITLE_END]"        # keyword_search.py:24
 VEC_TABLE = "chunk_embeddings"         # semantic_search.py:94
+
+logger = logging.getLogger(__name__)
 
 
 # ----------------------------------------------------------------------------- BM25 export
@@ -103,11 +108,15 @@ def _table_exists(conn: sqlite3.Connection, name: str) -> bool:
 
 def export_embeddings(conn: sqlite3.Connection, table: str = VEC_TABLE) -> EmbArrays:
     """Read the vec0 shadow tables in vec0's own scan order (chunk_id ascending, slot ascending)."""
-    if not _table_exists(conn, f"{table}_chunks") or not _table_exists(conn, f"{table}_vector_chunks00"):
-        raise RuntimeError(f"{table}: vec0 shadow tables not found — was the DB built by `rag-search build`?")
     cur = conn.cursor()
-    movie_ids = np.array([r[0] for r in cur.execute("SELECT id FROM movies ORDER BY id")], np.int64)
-    chunk_movie = dict(cur.execute("SELECT id, movie_id FROM chunks").fetchall())
+    movie_ids = (np.array([r[0] for r in cur.execute("SELECT id FROM movies ORDER BY id")], np.int64)
+                 if _table_exists(conn, "movies") else np.zeros(0, np.int64))
+    if not _table_exists(conn, f"{table}_chunks") or not _table_exists(conn, f"{table}_vector_chunks00"):
+        # a keyword-only or fresh database: the reference creates an EMPTY chunk_embeddings table at open time
+        # (semantic_search.py:94-101) and query_top_k returns [] — same here: no rows, no error
+        return EmbArrays(np.zeros((0, 1), np.float32), None, np.zeros(0, np.int64), np.zeros(0, np.int32), movie_ids, 0)
+    chunk_movie = (dict(cur.execute("SELECT id, movie_id FROM chunks").fetchall())
+                   if _table_exists(conn, "chunks") else {})
     blocks = cur.execute(
         f"SELECT c.chunk_id, c.size, c.validity, c.rowids, v.vectors FROM {table}_chunks c "
         f"JOIN {table}_vector_chunks00 v ON v.rowid = c.chunk_id ORDER BY c.chunk_id").fetchall()
@@ -151,21 +160,65 @@ def export_embeddings(conn: sqlite3.Connection, table: str = VEC_TABLE) -> EmbAr
 
 
 # ----------------------------------------------------------------------------- frozen sidecar
-SIDECAR_VERSION = 2
+SIDECAR_VERSION = 3
+
+
+def _md5(b: bytes) -> str:
+    return hashlib.md5(b).hexdigest()
 
 
 def _db_fingerprint(conn: sqlite3.Connection, db_path) -> dict:
     """What the reference's own sync-or-skip checks look at (basesearch_db.py:81-92,
-    keyword_search.py:87-100, semantic_search.py:145-154) plus the file's size and mtime."""
+    keyword_search.py:87-100, semantic_search.py:145-154) plus cheap CONTENT probes: both classes open the
+    database in WAL mode, where an in-place rewrite by another connection (a forced re-embed with the same
+    chunk count, not yet checkpointed) leaves the main file's size and mtime — and possibly the -wal size —
+    unchanged.  So the fingerprint also carries the file header's change counter, the WAL header (its salts
+    change at every WAL restart) and tail (any appended frame changes it), id / length sums, and a digest of
+    the first and last vec0 vector blocks."""
     p = Path(db_path)
     st = p.stat()
     cur = conn.cursor()
     counts = {}
     for t in ("movies", "terms", "postings", "doclen", "chunks", f"{VEC_TABLE}_chunks"):
         counts[t] = cur.execute(f"SELECT COUNT(*) FROM {t}").fetchone()[0] if _table_exists(conn, t) else -1
+    probes = {}
+    if counts["doclen"] > 0:
+        probes["doclen"] = list(cur.execute("SELECT MAX(doc_id), SUM(length) FROM doclen").fetchone())
+    if counts["postings"] > 0:
+        probes["postings"] = list(cur.execute("SELECT MAX(rowid), SUM(length(positions)) FROM postings "
+                                              "WHERE term_id = (SELECT MAX(term_id) FROM postings)").fetchone())
+    if counts["chunks"] > 0:
+        probes["chunks"] = list(cur.execute("SELECT MAX(id), SUM(movie_id) FROM chunks").fetchone())
+    if counts[f"{VEC_TABLE}_chunks"] > 0 and _table_exists(conn, f"{VEC_TABLE}_vector_chunks00"):
+        lo, hi = cur.execute(f"SELECT MIN(rowid), MAX(rowid) FROM {VEC_TABLE}_vector_chunks00").fetchone()
+        dig = []
+        for rid in sorted({lo, hi}):
+            (blob,) = cur.execute(f"SELECT vectors FROM {VEC_TABLE}_vector_chunks00 WHERE rowid = ?", (rid,)).fetchone()
+            dig.append(_md5(bytes(blob)))
+        (val,) = cur.execute(f"SELECT group_concat(hex(validity)) FROM (SELECT validity FROM {VEC_TABLE}_chunks "
+                             f"ORDER BY chunk_id DESC LIMIT 2)").fetchone()
+        probes["vec0"] = dig + [_md5((val or "").encode())]
+    header = b""
+    try:
+        with open(p, "rb") as fh:
+            header = fh.read(100)
+    except OSError:
+        pass
     wal = Path(str(p) + "-wal")
-    return {"version": SIDECAR_VERSION, "size": st.st_size, "mtime_ns": st.st_mtime_ns,
-            "wal_size": wal.stat().st_size if wal.exists() else 0, "counts": counts}
+    wal_sig = ""
+    wal_size = 0
+    if wal.exists():
+        wal_size = wal.stat().st_size
+        try:
+            with open(wal, "rb") as fh:
+                head = fh.read(32)
+                fh.seek(max(0, wal_size - 8192))
+                wal_sig = _md5(head + fh.read())
+        except OSError:
+            pass
+    return {"version": SIDECAR_VERSION, "size": st.st_size, "mtime_ns": st.st_mtime_ns, "wal_size": wal_size,
+            "wal_sig": wal_sig, "change_counter": header[24:28].hex(), "schema_cookie": header[40:44].hex(),
+            "counts": counts, "probes": probes}
 
 
 def sidecar_path(db_path, part: str) -> Path:
@@ -203,23 +256,41 @@ def load_or_export(conn: sqlite3.Connection, db_path, part: str, use_cache: bool
                         raise ValueError("embedding matrix does not belong to this sidecar")
                     return EmbArrays(emb=emb, valid=valid, rowid=z["rowid"], movie_idx=z["movie_idx"],
                                      movie_ids=z["movie_ids"], dim=int(z["dim"]))
-        except Exception:
-            pass                                      # unreadable / stale sidecar → re-export
+                logger.info("sidecar %s is stale (the database changed): re-exporting", sc)
+        except Exception as e:                        # unreadable sidecar → re-export, but say so
+            logger.warning("sidecar %s rejected (%s: %s): re-exporting", sc, type(e).__name__, e)
     arr = exporter(conn)
+
+    def atomic(path: Path, write) -> None:
+        # tmp + os.replace: a concurrent opener sees the old file or the new one, never a half-written one
+        tmp = path.with_name(path.name + f".tmp{os.getpid()}")
+        try:
+            with open(tmp, "wb") as fh:
+                write(fh)
+            os.replace(tmp, path)
+        finally:
+            if tmp.exists():
+                tmp.unlink()
+
     try:
         if part == "bm25":
             terms = np.array([t for t, _ in sorted(arr.term_row.items(), key=lambda kv: kv[1])], dtype=np.str_)
-            np.savez(sc, fingerprint=np.str_(fp), indptr=arr.indptr, doc_idx=arr.doc_idx, tf=arr.tf, df=arr.df, dl=arr.dl,
-                     doc_ids=arr.doc_ids, n_movies=np.int64(arr.n_movies), avgdl=np.float64(arr.avgdl), terms=terms)
+            atomic(sc, lambda fh: np.savez(fh, fingerprint=np.str_(fp), indptr=arr.indptr, doc_idx=arr.doc_idx, tf=arr.tf,
+                                           df=arr.df, dl=arr.dl, doc_ids=arr.doc_ids, n_movies=np.int64(arr.n_movies),
+                                           avgdl=np.float64(arr.avgdl), terms=terms))
         else:
-            # the matrix first, the .npz (which carries the fingerprint) last: it is the commit marker
-            np.save(emb_matrix_path(db_path), np.ascontiguousarray(arr.emb, dtype=np.float32))
-            np.savez(sc, fingerprint=np.str_(fp), emb_shape=np.asarray(arr.emb.shape, np.int64),
-                     has_valid=np.int64(arr.valid is not None),
-                     valid=arr.valid if arr.valid is not None else np.zeros(0, np.uint8), rowid=arr.rowid,
-                     movie_idx=arr.movie_idx, movie_ids=arr.movie_ids, dim=np.int64(arr.dim))
-    except OSError:
-        pass                                          # read-only location: just skip the cache
+            # the matrix first, the .npz (which carries the fingerprint) last: it is the commit marker.  The old
+            # .npz goes first so that no opener can pair the OLD fingerprint with the NEW matrix.
+            if sc.exists():
+                sc.unlink()
+            atomic(emb_matrix_path(db_path), lambda fh: np.save(fh, np.ascontiguousarray(arr.emb, dtype=np.float32)))
+            atomic(sc, lambda fh: np.savez(fh, fingerprint=np.str_(fp), emb_shape=np.asarray(arr.emb.shape, np.int64),
+                                           has_valid=np.int64(arr.valid is not None),
+                                           valid=arr.valid if arr.valid is not None else np.zeros(0, np.uint8),
+                                           rowid=arr.rowid, movie_idx=arr.movie_idx, movie_ids=arr.movie_ids,
+                                           dim=np.int64(arr.dim)))
+    except OSError as e:
+        logger.info("sidecar for %s not written (%s): read-only location?", db_path, e)
     return arr
 
 
@@ -275,8 +346,18 @@ def plan_chunks(movies: Sequence[tuple], max_chunk_size: int, overlap: int):
 
 def write_vec0_shadow(conn: sqlite3.Connection, rowids: np.ndarray, emb: np.ndarray, table: str = VEC_TABLE) -> None:
     """Store vectors exactly where vec0 would after inserting ``rowids`` in order into an empty
-    table: block i // 1024, slot i % 1024 (SURVEY App. A.2 / C)."""
+    table: block i // 1024, slot i % 1024 (SURVEY App. A.2 / C).
+
+    NOT a sqlite-vec writer: only the three shadow tables this package reads are created — there is no
+    ``chunk_embeddings`` virtual-table entry and no ``_info`` table, so the reference (whose
+    ``CREATE VIRTUAL TABLE IF NOT EXISTS`` would collide with the existing shadow tables) cannot open the
+    result.  It exists to freeze synthetic corpora / precomputed embeddings for tests and benches; the file is
+    marked in ``rse_meta`` so tools can tell, and SemanticSearch only uses it for a build when asked
+    explicitly (``fallback_build=True``)."""
     cur = conn.cursor()
+    cur.execute("CREATE TABLE IF NOT EXISTS rse_meta (key TEXT PRIMARY KEY, value TEXT)")
+    cur.execute("INSERT OR REPLACE INTO rse_meta(key, value) VALUES ('vec0_shadow_writer', "
+                "'rag_search_engine_b200.store.write_vec0_shadow: GPU-only database, not openable by sqlite-vec')")
     cur.execute(f"DROP TABLE IF EXISTS {table}_chunks")
     cur.execute(f"DROP TABLE IF EXISTS {table}_vector_chunks00")
     cur.execute(f"DROP TABLE IF EXISTS {table}_rowids")

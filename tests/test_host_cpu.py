@@ -239,7 +239,39 @@ def test_sidecar_cache_round_trip_and_invalidation(tmp_path):
     conn.commit()
     a3 = store.load_or_export(conn, db, "bm25")
     assert a3.n_movies == a.n_movies + 1
+    # an in-place rewrite that keeps every row count (a forced re-embed through ANOTHER connection
+    # in WAL mode: file size and mtime of the main file unchanged) must invalidate the sidecar as well
+    e5 = store.load_or_export(conn, db, "emb")
+    conn.execute("PRAGMA journal_mode=WAL")
+    other = sqlite3.connect(db)
+    other.execute("PRAGMA journal_mode=WAL")
+    (rid, blob) = other.execute("SELECT rowid, vectors FROM chunk_embeddings_vector_chunks00 ORDER BY rowid LIMIT 1").fetchone()
+    vec = np.frombuffer(blob, np.float32).copy()
+    vec[:8] += 1.0
+    other.execute("UPDATE chunk_embeddings_vector_chunks00 SET vectors = ? WHERE rowid = ?", (vec.tobytes(), rid))
+    other.commit()
+    e6 = store.load_or_export(conn, db, "emb")
+    assert not (np.asarray(e6.emb)[0, :8] == np.asarray(e5.emb)[0, :8]).any(), "stale sidecar served after an in-place rewrite"
+    other.close()
+    # no temporary files are left behind by the atomic writes
+    assert not [p for p in Path(db).parent.iterdir() if ".tmp" in p.name]
     conn.close()
+
+
+def test_query_only_open_without_vec0_tables_is_empty_not_an_error(tmp_path):
+    """a keyword-only / fresh database has no vec0 shadow tables; the reference creates an empty
+    chunk_embeddings table at open time and query_top_k returns [] — the exporter returns an empty matrix."""
+    from rag_search_engine_b200 import store
+    from rag_search_engine_b200.textutil import whitespace_tokenizer
+    docs = [{"id": 1, "title": "a b", "description": "c d."}, {"id": 2, "title": "e", "description": "f."}]
+    db = store.write_reference_db(tmp_path / "k.db", docs, whitespace_tokenizer)       # keyword tables only
+    conn = sqlite3.connect(db)
+    e = store.export_embeddings(conn)
+    assert e.emb.shape[0] == 0 and e.dim == 0 and e.movie_ids.tolist() == [1, 2]
+    fresh = sqlite3.connect(tmp_path / "fresh.db")
+    e = store.export_embeddings(fresh)
+    assert e.emb.shape[0] == 0 and len(e.movie_ids) == 0
+    conn.close(); fresh.close()
 
 
 def test_synthetic_corpus_is_deterministic_and_keeps_its_tie_cases():
@@ -345,3 +377,25 @@ def test_rrf_search_stream_keeps_two_batches_in_flight_and_the_order(tmp_path):
     # batch i carries ticket i's ids, three hits per query (count = limit - 1), last rank None-able fields mapped
     assert out[0][0][0] == {"id": 0, "score": 1.0, "bm25_rank": 0, "sem_rank": None}
     assert [h["id"] for h in out[3][1]] == [200, 201, 202] and [h["id"] for h in out[4][0]] == [300, 301, 302]
+
+
+def test_term_rows_list_form_and_flat_array_form_agree():
+    """KeywordSearch._term_rows: dict lookups over token lists and one searchsorted over a flat numpy array of
+    tokens give the same CSR rows (query order, duplicates kept, -1 = unknown term: keyword_search.py:205-210)."""
+    from types import SimpleNamespace
+    from rag_search_engine_b200.keyword_search import KeywordSearch
+    rng = random.Random(5)
+    vocab = [f"w{i}" for i in range(5000)]
+    rng.shuffle(vocab)
+    kw = KeywordSearch.__new__(KeywordSearch)
+    kw._arr = SimpleNamespace(term_row={t: i for i, t in enumerate(vocab)})
+    lists = [[rng.choice(vocab + ["<oov>", "zzz"]) for _ in range(rng.randint(0, 7))] for _ in range(300)]
+    lists[5] = lists[5] + lists[5][:1] * 2                      # duplicates stay
+    ptr, rows = kw._term_rows(lists)
+    want = [kw._arr.term_row.get(t, -1) for l in lists for t in l]
+    assert ptr.tolist() == np.cumsum([0] + [len(l) for l in lists]).tolist() and rows.tolist() == want
+    flat = np.array([t for l in lists for t in l], dtype=np.str_)
+    ptr2, rows2 = kw._term_rows((ptr, flat))
+    assert ptr2.tolist() == ptr.tolist() and rows2.tolist() == want
+    ptr3, rows3 = kw._term_rows([[], []])
+    assert ptr3.tolist() == [0, 0, 0] and len(rows3) == 1
