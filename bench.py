@@ -6,8 +6,8 @@
 
 A "step" = one batch of hybrid queries through the whole hot path
 (BM25 top-10 + exact vec0 KNN top-100 + best-chunk-per-movie + RRF fusion).
-  value : whole-job queries/s with the query batch already resident in HBM
-          (rse_hybrid_stage once, then K × rse_hybrid_run), CUDA events, max over ranks.
+  value : whole-job queries/s with the query batches already resident in HBM (8 distinct batches staged once
+          and parked with rse_hybrid_stash, then K x rse_hybrid_run rotating over them), CUDA events, max over ranks.
   e2e   : the same metric through the host-buffer C-ABI calls: every step uploads its query
           vectors/tokens (host -> pinned -> device) and reads its results back inside the timed
           region.  Headline = the serving loop (rse_hybrid_submit / rse_hybrid_collect, two batches
@@ -69,8 +69,15 @@ def parse_args():
     ap.add_argument("--no-knn1", action="store_true", help="skip the batch-1 KNN micro-measurement")
     ap.add_argument("--workload", default="hybrid600k", choices=["hybrid600k", "bm25_10k", "knn100m"],
                     help="hybrid600k = configs[3] (the metric's configuration, default); bm25_10k = configs[1]; "
-                         "knn100m = configs[4] (12.5 M-row shard per GPU, top-100, NCCL candidate merge)")
-    ap.add_argument("--shard-rows", type=int, default=12_500_000)
+                         "knn100m = configs[4] alone (fixed 100M-row corpus row-sharded over the GPUs, top-100)")
+    ap.add_argument("--shard-rows", type=int, default=0,
+                    help="--workload knn100m only: rows per GPU of a SMALLER corpus for experiments (0 = configs[4] as specified)")
+    ap.add_argument("--corpus", default="isotropic", choices=["isotropic", "clustered", "clustered_dense"],
+                    help="embedding distribution of the main line (the default line also carries short measurements on "
+                         "the two clustered corpora)")
+    ap.add_argument("--no-extras", action="store_true",
+                    help="main line only: skip the weighted / clustered / python-API / small-batch / rowshard / knn100m objects")
+    ap.add_argument("--no-knn100m", action="store_true", help="skip the configs[4] object of the default line")
     ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
                     help="N > 1: weak = --batch queries per GPU per step (global batch = batch x N; every rank scans its "
                          "row shard for all of them, so per-GPU work is constant); strong = the same --batch split over N")
@@ -193,23 +200,56 @@ class ClockSampler:
 
 
 # ----------------------------------------------------------------------------- workload
-def build_workload(args, device: str):
-    """Seeded S-600k corpus + query batch (identical on every rank and in both arms)."""
+NB = 8          # distinct query batches rotated through every timed loop (data-dependent variance stays visible)
+
+
+def sqlite_vec_status() -> str:
+    try:
+        import sqlite_vec  # noqa: F401
+        return "present"
+    except Exception:
+        return "absent"
+
+
+def build_corpus(args, device: str, corpus: str = "isotropic"):
+    from rag_search_engine_b200 import synth
+    if corpus == "isotropic":
+        return synth.synth_embeddings(args.movies, seed=1234, device=device)
+    if corpus == "clustered":      # 2000 "genres", ~2400 chunks each, ~4e2 rows within +-2 eps of the 100-th neighbour
+        return synth.synth_embeddings(args.movies, seed=1234, device=device, distribution="clustered",
+                                      n_centres=max(2, args.movies // 300), spread=0.15)
+    if corpus == "clustered_dense":  # near-duplicate neighbourhoods: ~1e3 rows within +-2 eps of the 100-th neighbour
+        return synth.synth_embeddings(args.movies, seed=1234, device=device, distribution="clustered",
+                                      n_centres=max(2, args.movies // 300), spread=0.06)
+    raise ValueError(corpus)
+
+
+def build_workload(args, device: str, corpus: str = "isotropic", bm=None):
+    """Seeded S-600k corpus + NB query batches (identical on every rank and in both arms)."""
     import torch
     from rag_search_engine_b200 import synth
     t0 = time.time()
-    se = synth.synth_embeddings(args.movies, seed=1234, device=device)
-    bm = synth.synth_bm25(args.movies, args.vocab, seed=1234, device=device)
-    tok_indptr, terms = synth.synth_token_queries(bm, args.batch, seed=99)
-    Q = synth.synth_query_vectors(se.emb, args.batch, seed=99)
+    se = build_corpus(args, device, corpus)
+    if bm is None:
+        bm = synth.synth_bm25(args.movies, args.vocab, seed=1234, device=device)
+    tok_indptr, terms = synth.synth_token_queries(bm, NB * args.batch, seed=99)
+    Q = synth.synth_query_vectors(se.emb, NB * args.batch, seed=99)
     if device != "cpu":
         torch.cuda.synchronize()
     info = {"chunks": int(se.emb.shape[0]), "dim": int(se.emb.shape[1]), "movies": args.movies,
-            "postings": int(len(bm.doc_idx)), "terms": int(len(bm.df)), "build_s": round(time.time() - t0, 1)}
+            "postings": int(len(bm.doc_idx)), "terms": int(len(bm.df)), "build_s": round(time.time() - t0, 1),
+            "corpus": corpus}
     return se, bm, tok_indptr, terms, Q, info
 
 
-def postings_touched(bm, tok_indptr, terms) -> int:
+def batch_slice(tok_indptr, terms, Qn, lo, hi):
+    """Queries lo..hi of the flattened workload as (Q, tok_indptr, term_rows) with a zero-based indptr."""
+    tp = (tok_indptr[lo:hi + 1] - tok_indptr[lo]).astype(np.int32)
+    tr = np.ascontiguousarray(terms[tok_indptr[lo]:tok_indptr[hi]])
+    return Qn[lo:hi], tp, tr
+
+
+def postings_touched(bm, terms) -> int:
     t = terms[terms >= 0]
     return int(bm.df[t].sum())
 
@@ -219,12 +259,14 @@ def config_dict(args, info, world, par="replicate"):
                         "(BM25 top-10 + exact vec0 KNN top-100 + per-movie best chunk + RRF), Gemini disabled",
             "mode": args.mode, "limit": args.limit, "knn_kprime": max(args.limit * 10, args.limit),
             "queries_per_step": args.batch, "queries_per_gpu_per_step": args.batch // max(1, world) if getattr(args, "scaling", "weak") == "weak" else None,
+            "distinct_query_batches": NB, "corpus": info.get("corpus", "isotropic"),
             "movies": info["movies"], "chunks": info["chunks"], "dim": info["dim"],
             "bm25_postings": info["postings"], "bm25_terms": info["terms"],
             "l2": "inputs larger than L2: every step streams the 3.7 GB fp16 shadow of the corpus (one pass per 256 "
                   "queries) and ~1.3 GB of postings against a 126 MB L2; no flush",
+            "sqlite_vec": sqlite_vec_status(),
             "parallelism": ("1 GPU" if world == 1 else
-                            (f"row-shard x{world} + all_gather(top-K') + query-slice BM25/fusion" if par == "rowshard" else
+                            (f"row-shard x{world} + candidate exchange (top-K') + query-slice BM25/fusion" if par == "rowshard" else
                              f"corpus replicated x{world}, query batch split by rank, no data-path collective"))}
 
 
@@ -269,14 +311,13 @@ def run_reference(args, rank, world):
     times = []
     budget_s = 150.0          # the whole arm must end within a few minutes whatever --steps says
     t_start = time.perf_counter()
+    nq_all = NB * args.batch
     for step in range(args.warmup + args.steps):
         if step > args.warmup + 1 and time.perf_counter() - t_start > budget_s:
             break
-        off = (step * sample) % max(1, args.batch - sample + 1)
-        tp = (tok_indptr[off: off + sample + 1] - tok_indptr[off]).astype(np.int32)
-        tr = terms[tok_indptr[off]: tok_indptr[off + sample]]
-        qps, dt, _ = cpu_hybrid_sample(emb_host, movie_of, bm, se.movie_ids, Qh[off: off + sample], tp, tr, args.limit,
-                                       args.mode, sample, cores)
+        off = (step * sample) % max(1, nq_all - sample + 1)
+        Qs, tp, tr = batch_slice(tok_indptr, terms, Qh, off, off + sample)
+        qps, dt, _ = cpu_hybrid_sample(emb_host, movie_of, bm, se.movie_ids, Qs, tp, tr, args.limit, args.mode, sample, cores)
         if step >= args.warmup:
             times.append(dt)
     total = sum(times)
@@ -294,30 +335,269 @@ def run_reference(args, rank, world):
     print(json.dumps(line), flush=True)
 
 
+# ----------------------------------------------------------------------------- one handle, one mode: resident + e2e
+class Timer:
+    def __init__(self, stream, world, device):
+        import torch
+        self.torch, self.stream, self.world, self.device = torch, stream, world, device
+        self.e0, self.e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+
+    def barrier(self):
+        if self.world > 1:
+            import torch.distributed as dist
+            dist.barrier()
+
+    def max_over_ranks(self, x: float) -> float:
+        if self.world > 1:
+            import torch.distributed as dist
+            t = self.torch.tensor([x], dtype=self.torch.float64, device=self.device)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            return float(t.item())
+        return x
+
+
+def measure_hybrid(idx, tm: Timer, batches, mode, param, limit, steps, warmup, *, sample_clocks=None, e2e=True):
+    """batches = NB x (Q pinned numpy [nq, dim], tok_indptr, term_rows) of THIS rank.  Returns the device-timed
+    resident number, the host-buffer numbers (serving loop + blocking call) and the last results per batch."""
+    torch = tm.torch
+    nb = len(batches)
+    nq = batches[0][0].shape[0]
+    # resident: every batch staged once and parked in HBM; a step exchanges the staged batch with its stash slot
+    for b, (Qb, tp, tr) in enumerate(batches):
+        idx.hybrid_stage(Qb, tp, tr)
+        idx.hybrid_stash(b)
+
+    def step(i):
+        idx.hybrid_stash(i % nb)
+        idx.hybrid_run(mode, param, limit)
+        idx.hybrid_stash(i % nb)
+
+    for i in range(max(warmup, 3)):
+        step(i)
+    torch.cuda.synchronize(); tm.barrier()
+    idx.set_timing(True)
+    idx.stats_reset()
+    sampler = None
+    if sample_clocks is not None:
+        sampler = ClockSampler(sample_clocks)
+        sampler.start()
+    torch.cuda.synchronize(); tm.barrier()
+    tm.e0.record(tm.stream)
+    for i in range(steps):
+        step(i)                               # (no inline NVML sampling here: one query costs the host ~25 ms and the
+    tm.e1.record(tm.stream)                   #  device would idle; the sampler thread polls concurrently instead)
+    torch.cuda.synchronize(); tm.barrier()
+    clocks = sampler.stop() if sampler else None
+    ms_local = tm.e0.elapsed_time(tm.e1)
+    st = idx.stats()
+    idx.set_timing(False)
+    out = {"ms": tm.max_over_ranks(ms_local), "ms_local": ms_local, "stats": st, "clocks": clocks, "nq": nq,
+           "survivors": None, "e2e": None, "results": None}
+    if int(st.tc_filter_launches) > 0:
+        try:
+            out["survivors"] = idx.tc_last_survivors(min(nq, 256))
+        except Exception:
+            pass
+    if not e2e:
+        return out
+    # (1) the blocking call, one batch at a time: the device idles while the host stages and collects
+    res = [None] * nb
+    for i in range(2):
+        idx.hybrid(mode, param, limit, *batches[i % nb])
+    torch.cuda.synchronize(); tm.barrier()
+    t0 = time.perf_counter()
+    tm.e0.record(tm.stream)
+    for i in range(steps):
+        res[i % nb] = idx.hybrid(mode, param, limit, *batches[i % nb])
+    tm.e1.record(tm.stream)
+    torch.cuda.synchronize()
+    wall_blocking = tm.max_over_ranks(time.perf_counter() - t0)
+    dev_blocking = tm.e0.elapsed_time(tm.e1) / steps
+    for i in range(steps, nb):                                   # results of every batch for the comparisons below
+        res[i] = idx.hybrid(mode, param, limit, *batches[i])
+    # (2) the serving loop: rse_hybrid_submit / rse_hybrid_collect, two batches in flight — every step still
+    # uploads its own inputs from host buffers and reads its own results back inside the timed region
+    for _ in range(2):                                           # warm both ticket slots (their buffers are allocated lazily)
+        t_prev = idx.hybrid_submit(mode, param, limit, *batches[0])
+        t_next = idx.hybrid_submit(mode, param, limit, *batches[1 % nb])
+        idx.hybrid_collect(t_prev); idx.hybrid_collect(t_next)
+    torch.cuda.synchronize(); tm.barrier()
+    res_p = [None] * nb
+    t0 = time.perf_counter()
+    t_prev = idx.hybrid_submit(mode, param, limit, *batches[0])
+    for i in range(1, steps):
+        t_next = idx.hybrid_submit(mode, param, limit, *batches[i % nb])
+        res_p[(i - 1) % nb] = idx.hybrid_collect(t_prev)
+        t_prev = t_next
+    res_p[(steps - 1) % nb] = idx.hybrid_collect(t_prev)
+    torch.cuda.synchronize()
+    wall = tm.max_over_ranks(time.perf_counter() - t0)
+    same = all(all((a.view(np.uint8) == b.view(np.uint8)).all() for a, b in zip(res[i], res_p[i]))
+               for i in range(nb) if res_p[i] is not None)
+    ntok = int(np.mean([len(b[2]) for b in batches]))
+    h2d = batches[0][0].nbytes + (nq + 1) * 4 + ntok * (4 + 8)
+    d2h = nq * limit * (8 + 8 + 8 + 8) + nq * 4
+    out["e2e"] = {"wall": wall, "wall_blocking": wall_blocking, "dev_blocking": dev_blocking, "same": bool(same),
+                  "h2d": int(h2d), "d2h": int(d2h)}
+    out["results"] = res
+    return out
+
+
+def e2e_dict(m, nq_global, steps, world):
+    e = m["e2e"]
+    return {"value": nq_global * steps / e["wall"], "unit": "queries/s", "h2d_bytes_per_step": e["h2d"] * world,
+            "d2h_bytes_per_step": e["d2h"] * world, "wall_ms_per_step": 1e3 * e["wall"] / steps,
+            "api": "rse_hybrid_submit / rse_hybrid_collect, host buffers, two batches in flight, "
+                   f"{NB} distinct batches in rotation",
+            "same_results_as_blocking_call": e["same"],
+            "blocking_call": {"value": nq_global * steps / e["wall_blocking"], "unit": "queries/s",
+                              "api": "rse_hybrid (one batch at a time)", "device_ms_per_step": e["dev_blocking"],
+                              "wall_ms_per_step": 1e3 * e["wall_blocking"] / steps}}
+
+
+def survivor_stats(surv):
+    if surv is None or len(surv) == 0:
+        return None
+    s = np.sort(np.asarray(surv, np.int64))
+    pick = lambda p: int(s[min(len(s) - 1, int(p * len(s)))])          # noqa: E731
+    return {"p50": pick(0.5), "p90": pick(0.9), "p99": pick(0.99), "max": int(s[-1]), "cap": 8192,
+            "note": "rows per query that passed the tcgen05 filter of the LAST timed batch (exact re-score decides)"}
+
+
+def make_handle(args, local_rank, stream, se, bm, lo, hi, dim):
+    from rag_search_engine_b200 import _lib
+    idx = _lib.Index(local_rank)
+    if args.tc_mode >= 0:
+        idx.set_tc_mode(args.tc_mode)
+    if args.bm25_mode >= 0:
+        idx.set_bm25_mode(args.bm25_mode)
+    idx.set_stream(stream.cuda_stream)
+    shard = se.emb[lo:hi]
+    mo = se.movie_of_chunk[lo:hi].contiguous()
+    idx.attach_embeddings_dev(shard.data_ptr(), hi - lo, dim, movie_idx_ptr=mo.data_ptr(), pos_base=lo,
+                              keepalive=(se, shard, mo))
+    idx.load_bm25(bm.indptr, bm.doc_idx, bm.tf, bm.df, bm.dl, bm.n_movies, bm.avgdl)
+    idx.set_id_tables(se.movie_ids, se.movie_ids)
+    return idx
+
+
+def pinned_batches(torch, Q, tok_indptr, terms, batch, qlo_of, qhi_of):
+    """NB batches; from global batch b this rank takes queries [qlo_of, qhi_of) (the whole batch when N = 1)."""
+    Qh = torch.empty(tuple(Q.shape), dtype=torch.float32, pin_memory=True)
+    Qh.copy_(Q.cpu())
+    Qn = Qh.numpy()
+    out = []
+    for b in range(NB):
+        out.append(batch_slice(tok_indptr, terms, Qn, b * batch + qlo_of, b * batch + qhi_of))
+    return Qn, out
+
+
+def measure_corpus_variant(args, local_rank, device, stream, bm, corpus, steps, tm):
+    """The same hybrid step on a CLUSTERED corpus (VERDICT r01 weak #3): fallback rate, survivor counts, q/s, and
+    the tensor-core path's results against the exact scan on a sample."""
+    import torch
+    se, _, tok_indptr, terms, Q, info = build_workload(args, f"cuda:{local_rank}", corpus=corpus, bm=bm)
+    idx = make_handle(args, local_rank, stream, se, bm, 0, info["chunks"], info["dim"])
+    Qn, batches = pinned_batches(torch, Q, tok_indptr, terms, args.batch, 0, args.batch)
+    m = measure_hybrid(idx, tm, batches, 0, 60.0, args.limit, steps, 3, e2e=False)
+    st = m["stats"]
+    # parity of the filter path on this distribution: K4 (auto) vs the exact scan (tc_mode 1) on 32 queries
+    kp = max(args.limit * 10, args.limit)
+    a = idx.knn_movies(Qn[:32], args.limit, kp)
+    idx.set_tc_mode(1)
+    b = idx.knn_movies(Qn[:32], args.limit, kp)
+    same = all((x.view(np.uint8) == y.view(np.uint8)).all() for x, y in zip(a, b))
+    out = {"corpus": corpus, "value": m["nq"] * steps / (m["ms"] / 1e3), "unit": "queries/s", "ms_per_step": m["ms"] / steps,
+           "steps": steps, "tc_queries": int(st.tc_queries), "tc_fallback_queries": int(st.tc_fallback_queries),
+           "tc_second_chance_queries": int(st.tc_second_chance_queries),
+           "tc_fallback_rate": (int(st.tc_fallback_queries) / int(st.tc_queries)) if int(st.tc_queries) else None,
+           "filter_pass_ms": st.scan_ms_total / max(1, st.scan_launches_timed),
+           "survivors_per_query": survivor_stats(m["survivors"]),
+           "tc_equals_exact_scan_on_32_queries": bool(same), "build_s": info["build_s"]}
+    idx.close()
+    del se
+    torch.cuda.empty_cache()
+    return out
+
+
+def measure_python_api(args, idx, bm, se, Qn, tok_indptr, terms, limit, steps):
+    """e2e through the advertised Python drop-in (VERDICT r01 weak #5): text tokens in, Python result lists out —
+    HybridSearch.rrf_search_stream over the resident handle, including the term lookup and the construction of
+    the result dicts; and the same stream with flat numpy token arrays in / packed numpy arrays out."""
+    from rag_search_engine_b200 import HybridSearch
+    T = len(bm.df)
+    names = np.array([f"t{i}" for i in range(T)], dtype=np.str_)
+    term_row = dict(zip(names.tolist(), range(T)))
+    hs = HybridSearch.from_loaded(idx, term_row, se.movie_ids, se.movie_ids, registry_key=f"bench-{os.getpid()}-{id(idx)}",
+                                  device=idx.device)
+    nb = NB
+    B = args.batch
+    tok_lists, flat = [], []
+    for b in range(nb):
+        Qb, tp, tr = batch_slice(tok_indptr, terms, Qn, b * B, (b + 1) * B)
+        toks = np.where(tr >= 0, names[np.clip(tr, 0, None)], "<oov>")
+        flat.append(((tp, toks), Qb))
+        tl = toks.tolist()
+        tok_lists.append(([tl[tp[i]:tp[i + 1]] for i in range(B)], Qb))
+
+    def run(batches, as_arrays):
+        gen = (batches[i % nb] for i in range(steps))
+        n = 0
+        t0 = time.perf_counter()
+        for out in hs.rrf_search_stream(gen, k=60, limit=limit, as_arrays=as_arrays):
+            n += 1
+        return time.perf_counter() - t0, out
+
+    run(tok_lists, False); run(flat, True)                        # warm (sorted vocabulary, ticket slots)
+    w_dict, last = run(tok_lists, False)
+    w_arr, last_arr = run(flat, True)
+    return {"value": B * steps / w_dict, "unit": "queries/s", "wall_ms_per_step": 1e3 * w_dict / steps,
+            "api": "HybridSearch.rrf_search_stream(token lists, frozen vectors) -> list of result dicts per query "
+                   "(term lookup in a 1M-entry dict + ~2.5k dicts built per batch, on the host, per step)",
+            "arrays": {"value": B * steps / w_arr, "unit": "queries/s", "wall_ms_per_step": 1e3 * w_arr / steps,
+                       "api": "the same stream with (tok_indptr, numpy str tokens) in and as_arrays=True out"},
+            "hits_in_last_batch": int(sum(len(x) for x in last))}
+
+
+def measure_small_batches(idx, Qn, limit):
+    """Where does the tensor-core path take over from the streaming scan?  rse_knn_movies (host buffers) for small
+    batches with the exact scan forced, K4 forced, and the library's automatic choice (VERDICT r01 weak #9)."""
+    kp = max(limit * 10, limit)
+    table = []
+    for nq in (1, 2, 3, 4, 8, 16, 32, 47, 64):
+        row = {"nq": nq}
+        for name, mode in (("scan_ms", 1), ("tc_ms", 2), ("auto_ms", 0)):
+            idx.set_tc_mode(mode)
+            for _ in range(2):
+                idx.knn_movies(Qn[:nq], limit, kp)
+            reps = 5
+            t0 = time.perf_counter()
+            for r in range(reps):
+                idx.knn_movies(Qn[r * nq:(r + 1) * nq], limit, kp)
+            row[name] = round(1e3 * (time.perf_counter() - t0) / reps, 4)
+        table.append(row)
+    idx.set_tc_mode(0)
+    return {"call": "rse_knn_movies, host buffers, S-600k, top-10 of K'=100", "rows": table,
+            "auto_threshold": "nq >= 4 (RSE_TC_MIN_BATCH)"}
+
+
 def measure_rowshard(args, rank, world, local_rank, se, bm, tok_indptr, terms, Q, Qn, info, mode, param, limit, steps):
-    """The same global batch through the ROW-SHARDED path (north_star: local top-K' per shard + one NCCL all_gather
+    """The same global batch through the ROW-SHARDED path (north_star: local top-K' per shard + candidate exchange
     + merge; sharded.py): device-timed steps with the batch resident, max over ranks, checked against one handle."""
     import torch
     import torch.distributed as dist
     from rag_search_engine_b200 import _lib, sharded
     device = torch.device("cuda", local_rank)
-    C, nq = info["chunks"], Qn.shape[0]
+    C = info["chunks"]
+    nq = args.batch
     bounds = sharded.shard_bounds(C, world)
     lo, hi = bounds[rank], bounds[rank + 1]
-    idx = _lib.Index(local_rank)
-    if args.tc_mode >= 0:
-        idx.set_tc_mode(args.tc_mode)
     stream = torch.cuda.current_stream(device)
-    idx.set_stream(stream.cuda_stream)
-    shard = se.emb[lo:hi]
-    mo = se.movie_of_chunk[lo:hi].contiguous()
-    idx.attach_embeddings_dev(shard.data_ptr(), hi - lo, info["dim"], movie_idx_ptr=mo.data_ptr(), pos_base=lo,
-                              keepalive=(se, shard, mo))
-    idx.load_bm25(bm.indptr, bm.doc_idx, bm.tf, bm.df, bm.dl, bm.n_movies, bm.avgdl)
-    idx.set_id_tables(se.movie_ids, se.movie_ids)
-    backend = sharded.LibrseShardBackend(idx, Qn, tok_indptr, terms, device)
+    idx = make_handle(args, local_rank, stream, se, bm, lo, hi, info["dim"])
+    Qb, tp, tr = batch_slice(tok_indptr, terms, Qn, 0, nq)
+    backend = sharded.LibrseShardBackend(idx, Qb, tp, tr, device)
     sh = sharded.ShardedHybrid(backend, nq)
-    Qd = Q.to(device).contiguous()
+    Qd = Q[:nq].to(device).contiguous()
     for _ in range(3):
         sh.step(Qd, mode, param, limit)
     torch.cuda.synchronize(); dist.barrier()
@@ -332,184 +612,76 @@ def measure_rowshard(args, rank, world, local_rank, se, bm, tok_indptr, terms, Q
     ms = float(t.item())
     ok = None
     if rank == 0:
-        chk = _lib.Index(local_rank)
-        chk.set_stream(stream.cuda_stream)
-        mo_full = se.movie_of_chunk.contiguous()
-        chk.attach_embeddings_dev(se.emb.data_ptr(), C, info["dim"], movie_idx_ptr=mo_full.data_ptr(), keepalive=(se, mo_full))
-        chk.load_bm25(bm.indptr, bm.doc_idx, bm.tf, bm.df, bm.dl, bm.n_movies, bm.avgdl)
-        chk.set_id_tables(se.movie_ids, se.movie_ids)
-        oid, osc, oa, ob, oc = chk.hybrid(mode, param, limit, Qn, tok_indptr, terms)
+        chk = make_handle(args, local_rank, stream, se, bm, 0, C, info["dim"])
+        oid, osc, oa, ob, oc = chk.hybrid(mode, param, limit, Qb, tp, tr)
         ok = bool((r.ids.cpu().numpy() == oid).all() and (r.score.cpu().numpy() == osc).all() and
                   (r.count.cpu().numpy() == oc).all())
         chk.close()
     idx.close()
     dist.barrier()
     return {"value": nq * steps / (ms / 1e3), "unit": "queries/s", "ms_per_step": ms / steps, "steps": steps,
-            "queries_per_step": nq, "parallelism": f"row-shard x{world} + all_gather(top-K') + query-slice BM25/fusion",
-            "sharded_matches_single_gpu": ok}
+            "queries_per_step": nq, "parallelism": f"row-shard x{world} + candidate exchange (top-K') + query-slice BM25/fusion",
+            "exchange": sh.exchange_kind, "sharded_matches_single_gpu": ok}
 
 
 # ----------------------------------------------------------------------------- B200 arm
 def run_b200(args, rank, world, local_rank):
     import torch
     import torch.distributed as dist
-    from rag_search_engine_b200 import _lib, sharded
+    from rag_search_engine_b200 import sharded
 
     torch.cuda.set_device(local_rank)
     device = torch.device("cuda", local_rank)
-    per_gpu_batch = args.batch
     if world > 1 and args.scaling == "weak":
-        args.batch = args.batch * world          # global batch; every rank scans its shard for all of it
-    se, bm, tok_indptr, terms, Q, info = build_workload(args, f"cuda:{local_rank}")
+        args.batch = args.batch * world          # global batch; every rank serves its slice of it
+    se, bm, tok_indptr, terms, Q, info = build_workload(args, f"cuda:{local_rank}", corpus=args.corpus)
     C = info["chunks"]
     par = args.parallelism
     if par == "auto":
         fits = C * info["dim"] * 6 < torch.cuda.get_device_properties(device).total_memory / 3
         par = "replicate" if fits else "rowshard"
     rowshard = world > 1 and par == "rowshard"
-    bounds = sharded.shard_bounds(C, world) if rowshard else [0] + [C] * world
-    lo, hi = (bounds[rank], bounds[rank + 1]) if rowshard else (0, C)
-    idx = _lib.Index(local_rank)
-    if args.tc_mode >= 0:
-        idx.set_tc_mode(args.tc_mode)
-    if args.bm25_mode >= 0:
-        idx.set_bm25_mode(args.bm25_mode)
     stream = torch.cuda.current_stream(device)
-    idx.set_stream(stream.cuda_stream)
-    shard = se.emb[lo:hi]
-    mo = se.movie_of_chunk[lo:hi].contiguous()
-    idx.attach_embeddings_dev(shard.data_ptr(), hi - lo, info["dim"], movie_idx_ptr=mo.data_ptr(), pos_base=lo,
-                              keepalive=(se, shard, mo))
-    idx.load_bm25(bm.indptr, bm.doc_idx, bm.tf, bm.df, bm.dl, bm.n_movies, bm.avgdl)
-    idx.set_id_tables(se.movie_ids, se.movie_ids)
+    tm = Timer(stream, world, device)
     mode = 0 if args.mode == "rrf" else 1
     param = 60.0 if mode == 0 else 0.5
     limit, nq = args.limit, args.batch
-    Qh = torch.empty((nq, info["dim"]), dtype=torch.float32, pin_memory=True)
-    Qh.copy_(Q.cpu())
-    Qn = Qh.numpy()
-    # replicate: this rank's slice of the global batch (the whole batch when N = 1)
     qs = sharded.query_slices(nq, world)
     qlo, qhi = (qs[rank], qs[rank + 1]) if (world > 1 and not rowshard) else (0, nq)
-    Qn_loc = Qn[qlo:qhi]
-    tp_loc = (tok_indptr[qlo:qhi + 1] - tok_indptr[qlo]).astype(np.int32)
-    tr_loc = terms[tok_indptr[qlo]:tok_indptr[qhi]]
-    nq_loc = qhi - qlo
-
-    def barrier():
-        if world > 1:
-            dist.barrier()
 
     if rowshard:
-        backend = sharded.LibrseShardBackend(idx, Qn, tok_indptr, terms, device)
-        sh = sharded.ShardedHybrid(backend, nq)
-        Qd = Q.to(device).contiguous()
-        step_fn = lambda: sh.step(Qd, mode, param, limit)        # noqa: E731
-    else:
-        idx.hybrid_stage(Qn_loc, tp_loc, tr_loc)
-        step_fn = lambda: idx.hybrid_run(mode, param, limit)     # noqa: E731
+        line = run_b200_rowshard(args, rank, world, local_rank, se, bm, tok_indptr, terms, Q, info, mode, param, tm)
+        if rank == 0:
+            print(json.dumps(line), flush=True)
+        return
 
-    for _ in range(max(args.warmup, 3)):
-        step_fn()
-    torch.cuda.synchronize(); barrier()
-
-    # ---- timed region: K steps, inputs resident in HBM
-    idx.set_timing(True)
-    idx.stats_reset()
-    sampler = ClockSampler(local_rank)
-    sampler.start()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    torch.cuda.synchronize(); barrier()
-    e0.record(stream)
-    for _ in range(args.steps):
-        step_fn()                             # (no inline NVML sampling here: one query costs the host ~25 ms and the
-    e1.record(stream)                         #  device would idle; the sampler thread polls concurrently instead)
-    torch.cuda.synchronize(); barrier()
-    clocks = sampler.stop()
-    sh_last = step_fn() if rowshard else None
-    torch.cuda.synchronize(); barrier()
-    ms = e0.elapsed_time(e1)
-    st = idx.stats()
-    idx.set_timing(False)
+    idx = make_handle(args, local_rank, stream, se, bm, 0, C, info["dim"])
+    Qn, batches = pinned_batches(torch, Q, tok_indptr, terms, nq, qlo, qhi)
+    m = measure_hybrid(idx, tm, batches, mode, param, limit, args.steps, args.warmup, sample_clocks=local_rank,
+                       e2e=not args.no_e2e)
+    ms, st, clocks = m["ms"], m["stats"], m["clocks"]
     launches = int(st.kernel_launches)
     scan_ms = st.scan_ms_total / max(1, st.scan_launches_timed)
-    scan_share = st.scan_ms_total / ms if ms > 0 else None
-    if world > 1:
-        t = torch.tensor([ms], dtype=torch.float64, device=device)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms = float(t.item())
+    scan_share = st.scan_ms_total / m["ms_local"] if m["ms_local"] > 0 else None
     value = nq * args.steps / (ms / 1e3)
+    e2e = e2e_dict(m, nq, args.steps, world) if m["e2e"] else None
+    res = m["results"]
 
-    # ---- e2e: host buffers through the C-ABI call, copies inside the timed region
-    e2e = None
-    res = None
-    if not args.no_e2e and not rowshard:
-        # every rank: its slice of the batch through the host-buffer call (H2D of queries + tokens, D2H of results)
-        def wall_max(w):
-            if world > 1:
-                t = torch.tensor([w], dtype=torch.float64, device=device)
-                dist.all_reduce(t, op=dist.ReduceOp.MAX)
-                return float(t.item())
-            return w
-        # (1) the blocking call, one batch at a time: the device idles while the host stages and collects
-        for _ in range(2):
-            idx.hybrid(mode, param, limit, Qn_loc, tp_loc, tr_loc)
-        torch.cuda.synchronize(); barrier()
-        t0 = time.perf_counter()
-        e0.record(stream)
-        for _ in range(args.steps):
-            res = idx.hybrid(mode, param, limit, Qn_loc, tp_loc, tr_loc)
-        e1.record(stream)
-        torch.cuda.synchronize()
-        wall_blocking = wall_max(time.perf_counter() - t0)
-        dev_blocking = e0.elapsed_time(e1) / args.steps
-        # (2) the serving loop: rse_hybrid_submit / rse_hybrid_collect, two batches in flight — every step still
-        # uploads its own inputs from host buffers and reads its own results back inside the timed region
-        for _ in range(2):                                       # warm both ticket slots (their buffers are allocated lazily)
-            t_prev = idx.hybrid_submit(mode, param, limit, Qn_loc, tp_loc, tr_loc)
-            t_next = idx.hybrid_submit(mode, param, limit, Qn_loc, tp_loc, tr_loc)
-            idx.hybrid_collect(t_prev); idx.hybrid_collect(t_next)
-        torch.cuda.synchronize(); barrier()
-        t0 = time.perf_counter()
-        t_prev = idx.hybrid_submit(mode, param, limit, Qn_loc, tp_loc, tr_loc)
-        for _ in range(args.steps - 1):
-            t_next = idx.hybrid_submit(mode, param, limit, Qn_loc, tp_loc, tr_loc)
-            res_p = idx.hybrid_collect(t_prev)
-            t_prev = t_next
-        res_p = idx.hybrid_collect(t_prev)
-        torch.cuda.synchronize()
-        wall = wall_max(time.perf_counter() - t0)
-        pipelined_ok = all((a.view(np.uint8) == b.view(np.uint8)).all() for a, b in zip(res, res_p))
-        ntok = int(tok_indptr[-1])
-        h2d = Qn.nbytes + (nq + world) * 4 + ntok * (4 + 8)
-        d2h = nq * limit * (8 + 8 + 8 + 8) + nq * 4
-        e2e = {"value": nq * args.steps / wall, "unit": "queries/s", "h2d_bytes_per_step": int(h2d),
-               "d2h_bytes_per_step": int(d2h), "wall_ms_per_step": 1e3 * wall / args.steps,
-               "api": "rse_hybrid_submit / rse_hybrid_collect, host buffers, two batches in flight",
-               "same_results_as_blocking_call": bool(pipelined_ok),
-               "blocking_call": {"value": nq * args.steps / wall_blocking, "unit": "queries/s",
-                                 "api": "rse_hybrid (one batch at a time)", "device_ms_per_step": dev_blocking,
-                                 "wall_ms_per_step": 1e3 * wall_blocking / args.steps}}
-    elif rowshard and not args.no_e2e:
-        # sharded e2e: stage (H2D of this rank's slice + the batch's query vectors) + step + D2H of the fused batch
-        torch.cuda.synchronize(); barrier()
-        t0 = time.perf_counter()
-        for _ in range(args.steps):
-            backend.stage_slice(sh.lo, sh.hi)
-            Qd2 = Qh.to(device, non_blocking=True)
-            r = sh.step(Qd2, mode, param, limit)
-            _ = r.ids.cpu(), r.score.cpu(), r.count.cpu()
-        torch.cuda.synchronize(); barrier()
-        wall = time.perf_counter() - t0
-        t = torch.tensor([wall], dtype=torch.float64, device=device)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        wall = float(t.item())
-        e2e = {"value": nq * args.steps / wall, "unit": "queries/s", "h2d_bytes_per_step": int(Qn.nbytes),
-               "d2h_bytes_per_step": int(nq * limit * 16 + nq * 4), "wall_ms_per_step": 1e3 * wall / args.steps}
+    # ---- the other fusion mode of configs[3] (weighted alpha = 0.5 next to rrf): same batches, fewer steps
+    other = None
+    if not args.no_extras:
+        omode, oparam, oname = (1, 0.5, "weighted") if mode == 0 else (0, 60.0, "rrf")
+        osteps = min(args.steps, 40)
+        mo_ = measure_hybrid(idx, tm, batches, omode, oparam, limit, osteps, 3, e2e=not args.no_e2e)
+        other = {"mode": oname, "param": oparam, "value": nq * osteps / (mo_["ms"] / 1e3), "unit": "queries/s",
+                 "ms_per_step": mo_["ms"] / osteps, "steps": osteps,
+                 "e2e": e2e_dict(mo_, nq, osteps, world) if mo_["e2e"] else None,
+                 "note": "r01's 55.9 k q/s weighted-mode figure (gpurun_out/b_weighted.log) was an artefact of the "
+                         "bench of that hour, which took an inline NVML sample (~25 ms of host time) every 8 steps "
+                         "inside the device-resident loop; the kernels of the two modes differ only in fuse_kernel"}
 
     # ---- batch-1 KNN (north_star: batch-1 kNN as a fraction of HBM peak): scan<QB=1> alone + whole call
-    knn1 = None
-    knn1k = None
+    knn1 = knn1k = small = pyapi = None
     if world == 1 and not args.no_knn1:
         kp = max(limit * 10, limit)
         for _ in range(3):
@@ -518,14 +690,13 @@ def run_b200(args, rank, world, local_rank):
         reps = 20
         t0 = time.perf_counter()
         for i in range(reps):
-            idx.knn_movies(Qn[i % nq: i % nq + 1], limit, kp)
+            idx.knn_movies(Qn[i: i + 1], limit, kp)
         wall1 = (time.perf_counter() - t0) / reps
         s1 = idx.stats(); idx.set_timing(False)
         sm1 = s1.scan_ms_total / max(1, s1.scan_launches_timed)
         knn1 = {"scan_ms": sm1, "call_ms_host_buffers": 1e3 * wall1, "launches_per_query": s1.kernel_launches / reps}
         # configs[2]: batch-1024 semantic search (KNN top-K' + per-movie best chunk) through the host-buffer call
-        from rag_search_engine_b200 import synth as _synth
-        Q1k = _synth.synth_query_vectors(se.emb, 1024, seed=7).cpu().numpy()
+        Q1k = Qn[:1024]
         for _ in range(2):
             idx.knn_movies(Q1k, limit, kp)
         idx.set_timing(True); idx.stats_reset()
@@ -537,14 +708,13 @@ def run_b200(args, rank, world, local_rank):
         s1k = idx.stats(); idx.set_timing(False)
         f_ms = s1k.scan_ms_total / max(1, s1k.scan_launches_timed)
         knn1k = {"call_ms_host_buffers": 1e3 * wall1k, "queries_per_s": 1024 / wall1k, "filter_pass_ms": f_ms,
-                 "filter_tflops": 2.0 * 384 * (hi - lo) * 256 / (f_ms * 1e-3) / 1e12 if f_ms > 0 else None,
+                 "filter_tflops": 2.0 * 384 * C * 256 / (f_ms * 1e-3) / 1e12 if f_ms > 0 else None,
                  "tc_fallback_queries": int(s1k.tc_fallback_queries)}
+        if not args.no_extras:
+            small = measure_small_batches(idx, Qn, limit)
+            pyapi = measure_python_api(args, idx, bm, se, Qn, tok_indptr, terms, limit, min(args.steps, 40))
 
-    sharded_ok = None
-    replicas_ok = None
-    rowshard_extra = None
-    mismatch = None
-    corpora_identical = None
+    replicas_ok = mismatch = corpora_identical = rowshard_extra = None
     if world > 1:
         # every rank generates the corpus on its own GPU from the same seeds: verify they really are the same bits
         def csum(t):
@@ -556,127 +726,197 @@ def run_b200(args, rank, world, local_rank):
         sigs = [None] * world
         dist.all_gather_object(sigs, sig)
         corpora_identical = all(x == sigs[0] for x in sigs)
-    if world > 1:
-        # rank 0 generated the whole corpus: check the N-GPU result against a single-handle run of the whole batch
-        if rowshard:
-            got = (sh_last.ids.cpu().numpy(), sh_last.score.cpu().numpy(), sh_last.count.cpu().numpy())
-        else:
-            mine = res if res is not None else idx.hybrid(mode, param, limit, Qn_loc, tp_loc, tr_loc)
-            parts = [None] * world
-            dist.all_gather_object(parts, (mine[0], mine[1], mine[4]))
-            got = tuple(np.concatenate([p[i] for p in parts]) for i in range(3))
+        # rank 0 holds the whole corpus: the gathered slices of batch 0 must equal one handle's run of the whole batch
+        mine = res[0] if res is not None else idx.hybrid(mode, param, limit, *batches[0])
+        parts = [None] * world
+        dist.all_gather_object(parts, (mine[0], mine[1], mine[4]))
+        got = tuple(np.concatenate([p[i] for p in parts]) for i in range(3))
         if rank == 0:
-            if rowshard:
-                chk = _lib.Index(local_rank)
-                chk.set_stream(stream.cuda_stream)
-                mo_full = se.movie_of_chunk.contiguous()
-                chk.attach_embeddings_dev(se.emb.data_ptr(), C, info["dim"], movie_idx_ptr=mo_full.data_ptr(),
-                                          keepalive=(se, mo_full))
-                chk.load_bm25(bm.indptr, bm.doc_idx, bm.tf, bm.df, bm.dl, bm.n_movies, bm.avgdl)
-                chk.set_id_tables(se.movie_ids, se.movie_ids)
-            else:
-                chk = idx
-            oid, osc, oa, ob, oc = chk.hybrid(mode, param, limit, Qn, tok_indptr, terms)
-            ok = bool((got[0] == oid).all() and (got[1] == osc).all() and (got[2] == oc).all())
-            if not ok:
+            oid, osc, oa, ob, oc = idx.hybrid(mode, param, limit, *batch_slice(tok_indptr, terms, Qn, 0, nq))
+            replicas_ok = bool((got[0] == oid).all() and (got[1] == osc).all() and (got[2] == oc).all())
+            if not replicas_ok:
                 badq = np.nonzero((got[0] != oid).any(axis=1) | (got[1] != osc).any(axis=1) | (got[2] != oc))[0]
-                mismatch = {"queries": int(len(badq)), "first": [int(x) for x in badq[:8]],
-                            "ids_differ": int((got[0] != oid).any(axis=1).sum()),
-                            "scores_differ": int((got[1] != osc).any(axis=1).sum()),
-                            "example": {"q": int(badq[0]), "got_id": [int(x) for x in got[0][badq[0]]],
-                                        "want_id": [int(x) for x in oid[badq[0]]],
-                                        "got_score": [float(x) for x in got[1][badq[0]]],
-                                        "want_score": [float(x) for x in osc[badq[0]]]}}
-            if rowshard:
-                sharded_ok = ok
-                chk.close()
-            else:
-                replicas_ok = ok
-        if not rowshard and args.parallelism == "auto":
+                mismatch = {"queries": int(len(badq)), "first": [int(x) for x in badq[:8]]}
+        if args.parallelism == "auto" and not args.no_extras:
             rowshard_extra = measure_rowshard(args, rank, world, local_rank, se, bm, tok_indptr, terms, Q, Qn, info, mode,
                                               param, limit, min(args.steps, 30))
-    if world > 1:
         dist.barrier()
+
+    # ---- CPU baseline + clustered corpora (rank 0 of a 1-GPU run), then configs[4]
+    cpu = None
+    clustered = []
+    if world == 1 and not args.no_cpu_baseline:
+        cores = os.cpu_count() or 1
+        sample = min(nq, args.cpu_sample or 2 * cores)
+        emb_host = se.emb.cpu().numpy()
+        movie_of = se.movie_of_chunk.cpu().numpy().astype(np.int64)
+        Qb, tp, tr = batch_slice(tok_indptr, terms, Qn, 0, nq)
+        qps, dt, cpu_out = cpu_hybrid_sample(emb_host, movie_of, bm, se.movie_ids, Qb, tp, tr, limit, args.mode, sample, cores)
+        # the sample doubles as a full-size parity check of the GPU results
+        oid, osc, oa, ob, oc = res[0] if res is not None else idx.hybrid(mode, param, limit, Qb, tp, tr)
+        ok = all([int(x) for x in oid[q, :oc[q]]] == [r["id"] for r in cpu_out[q]] and
+                 [float(x) for x in osc[q, :oc[q]]] == [r["score"] for r in cpu_out[q]] for q in range(sample))
+        # the reference itself is single-threaded (SURVEY §8d): the same port on ONE core, two queries
+        qps1, dt1, _ = cpu_hybrid_sample(emb_host, movie_of, bm, se.movie_ids, Qb, tp, tr, limit, args.mode, 2, 1)
+        cpu = {"value": qps, "unit": "queries/s", "cores": cores, "kind": "port",
+               "one_core": {"value": qps1, "unit": "queries/s", "sample": f"2 queries, {dt1:.1f} s"},
+               "sample": f"{sample} hybrid queries of batch 0 over the full corpus, {dt:.1f} s (OpenMP over queries; "
+                         f"literal vec0 scan per query)", "gpu_matches_cpu_on_sample": bool(ok)}
+        del emb_host
+    ptouched = postings_touched(bm, terms) // NB
+    idx.close()
+    if world == 1 and not args.no_extras and args.corpus == "isotropic":
+        del se
+        torch.cuda.empty_cache()
+        for corpus in ("clustered", "clustered_dense"):
+            clustered.append(measure_corpus_variant(args, local_rank, device, stream, bm, corpus, min(args.steps, 20), tm))
+    knn100m = None
+    if not args.no_extras and not args.no_knn100m:
+        se = None
+        torch.cuda.empty_cache()
+        knn100m = knn100m_measure(args, rank, world, local_rank, steps=min(args.steps, 20), batch=256)
     if rank != 0:
         return
+
     peaks = {}
     pk = ROOT / "MEASURED_PEAKS.json"
     if pk.exists():
         peaks = json.loads(pk.read_text())
     peak = float(peaks.get("hbm_gbs", 6650.0))
-    rows_local = hi - lo
-    qb = 16 if nq >= 9 else (8 if nq >= 5 else (4 if nq >= 3 else nq))
+    nq_loc = qhi - qlo
+    qb = 16 if nq_loc >= 9 else (8 if nq_loc >= 5 else (4 if nq_loc >= 3 else nq_loc))
     tc_used = int(st.tc_filter_launches) > 0
     kname, row_bytes = scan_kernel_desc(args, tc_used, qb)
-    alg_bytes = rows_local * row_bytes
+    alg_bytes = C * row_bytes
     # DRAM bytes per launch of the dominant kernel, from the committed ncu --set full capture (profiles/): only
     # quoted when this run has the shard size that was profiled
     traffic = None
-    tj = ROOT / "profiles" / "r01_dominant_kernel_traffic.json"
-    if tj.exists():
+    for tj in sorted((ROOT / "profiles").glob("r0*_dominant_kernel_traffic.json"), reverse=True):
         t = json.loads(tj.read_text())
-        if t.get("rows") == rows_local and t.get("tc_kind") == (tc_kind(args) if tc_used else "scan"):
+        if t.get("rows") == C and t.get("tc_kind") == (tc_kind(args) if tc_used else "scan"):
             traffic = t.get("dram_bytes_read", 0) + t.get("dram_bytes_write", 0)
+            break
     hbm_achieved = alg_bytes / (scan_ms * 1e-3) / 1e9 if scan_ms > 0 else None
     psrc = "MEASURED_PEAKS.json" if peaks else "fallback"
     if tc_used:
-        # The batched filter pass is bound by the tensor pipe (+ TMEM reads), not by the stream: with the MMAs
-        # removed the same kernel streams the shadow at 7.4 TB/s (0.50 ms), with the TMEM loads removed it takes
-        # 0.65 ms = 1.45 PFLOP/s.  Algorithmic work: 2*384 flop per (row, query) pair.
-        q_per_pass = min(nq if rowshard else nq_loc, 256)
-        flops = 2.0 * 384 * rows_local * q_per_pass
-        tpeak = float(peaks.get("bf16_tflops_sustained", 1400.0))
+        # The batched filter pass is bound by the tensor pipe (+ TMEM reads), not by the stream.
+        # Algorithmic work: 2*384 flop per (row, query) pair.  Peak: the BURST figure when the SM clock sampled
+        # during the timed region sat at its maximum with no power cap (a short run), the SUSTAINED one otherwise.
+        q_per_pass = min(nq_loc, 256)
+        flops = 2.0 * 384 * C * q_per_pass
+        burst = float(peaks.get("bf16_tflops", 1623.4))
+        sustained = float(peaks.get("bf16_tflops_sustained", 1379.6))
+        at_max = bool(clocks and clocks.get("sm_mhz") and clocks.get("sm_max_mhz") and
+                      clocks["sm_mhz"] >= 0.97 * clocks["sm_max_mhz"] and "sw_power_cap" not in (clocks.get("reasons") or []))
+        tpeak = burst if at_max else sustained
         tach = flops / (scan_ms * 1e-3) / 1e12 if scan_ms > 0 else None
         roofline = {"bound": "tensor", "kernel": kname, "achieved": tach, "peak": tpeak, "unit": "TFLOP/s",
                     "frac": (tach / tpeak) if tach else None,
-                    "peak_source": f"{psrc} bf16_tflops_sustained (kernel timed inside the step; f16 and bf16 share the "
-                                   f"tensor rate; burst figure {peaks.get('bf16_tflops')})",
+                    "peak_source": f"{psrc} {'bf16_tflops (burst: SM clock at max, no power cap during the timed region)' if at_max else 'bf16_tflops_sustained (SM clock below max / power-capped during the timed region)'}; "
+                                   f"f16 and bf16 share the tensor rate",
+                    "frac_of_burst_peak": (tach / burst) if tach else None,
+                    "frac_of_sustained_peak": (tach / sustained) if tach else None,
                     "traffic": traffic, "algorithmic_flops_per_launch": flops, "queries_per_pass": q_per_pass,
                     "avg_launch_ms": scan_ms,
                     "hbm": {"achieved": hbm_achieved, "peak": peak, "unit": "GB/s",
                             "frac": (hbm_achieved / peak) if hbm_achieved else None,
                             "algorithmic_bytes_per_launch": alg_bytes, "bytes_per_row": row_bytes},
                     "scan_launches": int(st.scan_launches_timed), "scan_share_of_step": scan_share,
-                    "tc_queries": int(st.tc_queries), "tc_fallback_queries": int(st.tc_fallback_queries)}
+                    "tc_queries": int(st.tc_queries), "tc_fallback_queries": int(st.tc_fallback_queries),
+                    "tc_second_chance_queries": int(st.tc_second_chance_queries),
+                    "survivors_per_query": survivor_stats(m["survivors"])}
     else:
         roofline = {"bound": "hbm", "kernel": kname,
                     "achieved": hbm_achieved, "peak": peak, "unit": "GB/s", "frac": (hbm_achieved / peak) if hbm_achieved else None,
                     "peak_source": f"{psrc} hbm_gbs", "traffic": traffic, "algorithmic_bytes_per_launch": alg_bytes,
                     "avg_launch_ms": scan_ms, "scan_launches": int(st.scan_launches_timed), "scan_share_of_step": scan_share,
                     "tc_queries": int(st.tc_queries), "tc_fallback_queries": int(st.tc_fallback_queries)}
-
     if knn1:
-        g1 = rows_local * ROW_BYTES / (knn1["scan_ms"] * 1e-3) / 1e9
+        g1 = C * ROW_BYTES / (knn1["scan_ms"] * 1e-3) / 1e9
         knn1.update(achieved_gbs=g1, frac_of_measured_peak=g1 / peak, queries_per_s=1e3 / knn1["call_ms_host_buffers"])
     line = {"metric": "hybrid queries/sec", "value": value, "unit": "queries/s", "n_gpus": world, "steps": args.steps,
             "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps, "higher_is_better": True,
             "scaling": (args.scaling if world > 1 else "weak"), "vs_baseline": None,
             "dtype": "f16 tensor-core filter + exact f32 re-score (f64 tail), f64 BM25/fusion", "data": "synthetic",
             "config": config_dict(args, info, world, par), "roofline": roofline, "clocks": clocks, "e2e": e2e,
-            "gpu_launches": launches, "sharded_matches_single_gpu": sharded_ok, "replicas_match_single_gpu": replicas_ok, "mismatch": mismatch,
+            "gpu_launches": launches,
+            "bm25": {"queries": int(st.bm25_queries), "fallback_queries": int(st.bm25_fallback_queries),
+                     "finalists_rescored": int(st.bm25_finalists), "candidates_merged": int(st.bm25_candidates)},
+            "bytes_moved_resident_loop": {"h2d": int(st.h2d_bytes), "d2h": int(st.d2h_bytes)},
+            ("weighted" if mode == 0 else "rrf"): other, "clustered": clustered or None, "e2e_python": pyapi,
+            "knn_small_batches": small, "knn100m": knn100m,
+            "replicas_match_single_gpu": replicas_ok, "mismatch": mismatch,
             "corpora_identical_across_ranks": corpora_identical,
-            "rowshard": rowshard_extra, "knn_batch1": knn1, "knn_batch1024": knn1k, "postings_touched_per_step": postings_touched(bm, tok_indptr, terms)}
-
-    if world == 1 and not args.no_cpu_baseline:
-        cores = os.cpu_count() or 1
-        sample = min(nq, args.cpu_sample or 2 * cores)
-        emb_host = se.emb.cpu().numpy()
-        movie_of = se.movie_of_chunk.cpu().numpy().astype(np.int64)
-        qps, dt, cpu_out = cpu_hybrid_sample(emb_host, movie_of, bm, se.movie_ids, Qn, tok_indptr, terms, limit, args.mode,
-                                             sample, cores)
-        # the sample doubles as a full-size parity check of the GPU results
-        oid, osc, oa, ob, oc = res if e2e and world == 1 else idx.hybrid(mode, param, limit, Qn, tok_indptr, terms)
-        ok = all([int(x) for x in oid[q, :oc[q]]] == [r["id"] for r in cpu_out[q]] and
-                 [float(x) for x in osc[q, :oc[q]]] == [r["score"] for r in cpu_out[q]] for q in range(sample))
-        # the reference itself is single-threaded (SURVEY §8d): the same port on ONE core, two queries
-        qps1, dt1, _ = cpu_hybrid_sample(emb_host, movie_of, bm, se.movie_ids, Qn, tok_indptr, terms, limit, args.mode, 2, 1)
-        line["cpu_baseline"] = {"value": qps, "unit": "queries/s", "cores": cores, "kind": "port",
-                                "one_core": {"value": qps1, "unit": "queries/s", "sample": f"2 queries, {dt1:.1f} s"},
-                                "sample": f"{sample} hybrid queries of the same batch over the full corpus, "
-                                          f"{dt:.1f} s (OpenMP over queries; literal vec0 scan per query)",
-                                "gpu_matches_cpu_on_sample": bool(ok)}
+            "rowshard": rowshard_extra, "knn_batch1": knn1, "knn_batch1024": knn1k, "postings_touched_per_step": ptouched}
+    if cpu:
+        line["cpu_baseline"] = cpu
     print(json.dumps(line), flush=True)
+
+
+def run_b200_rowshard(args, rank, world, local_rank, se, bm, tok_indptr, terms, Q, info, mode, param, tm):
+    """--parallelism rowshard as the MAIN line (a corpus that does not fit one GPU takes this path)."""
+    import torch
+    import torch.distributed as dist
+    from rag_search_engine_b200 import sharded
+    device = torch.device("cuda", local_rank)
+    stream = tm.stream
+    C, nq, limit = info["chunks"], args.batch, args.limit
+    bounds = sharded.shard_bounds(C, world)
+    lo, hi = bounds[rank], bounds[rank + 1]
+    idx = make_handle(args, local_rank, stream, se, bm, lo, hi, info["dim"])
+    Qn = Q.cpu().numpy()
+    Qb, tp, tr = batch_slice(tok_indptr, terms, Qn, 0, nq)
+    backend = sharded.LibrseShardBackend(idx, Qb, tp, tr, device)
+    sh = sharded.ShardedHybrid(backend, nq)
+    Qd = Q[:nq].to(device).contiguous()
+    for _ in range(max(args.warmup, 3)):
+        sh.step(Qd, mode, param, limit)
+    torch.cuda.synchronize(); dist.barrier()
+    idx.set_timing(True); idx.stats_reset()
+    sampler = ClockSampler(local_rank); sampler.start()
+    tm.e0.record(stream)
+    for _ in range(args.steps):
+        r = sh.step(Qd, mode, param, limit)
+    tm.e1.record(stream)
+    torch.cuda.synchronize(); dist.barrier()
+    clocks = sampler.stop()
+    ms = tm.max_over_ranks(tm.e0.elapsed_time(tm.e1))
+    st = idx.stats(); idx.set_timing(False)
+    # e2e: stage (H2D of this rank's slice + the batch's query vectors) + step + D2H of the fused batch
+    Qh = torch.empty((nq, info["dim"]), dtype=torch.float32, pin_memory=True); Qh.copy_(Q[:nq].cpu())
+    torch.cuda.synchronize(); dist.barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        backend.stage_slice(sh.lo, sh.hi)
+        Qd2 = Qh.to(device, non_blocking=True)
+        r2 = sh.step(Qd2, mode, param, limit)
+        _ = r2.ids.cpu(), r2.score.cpu(), r2.count.cpu()
+    torch.cuda.synchronize(); dist.barrier()
+    wall = tm.max_over_ranks(time.perf_counter() - t0)
+    ok = None
+    if rank == 0:
+        chk = make_handle(args, local_rank, stream, se, bm, 0, C, info["dim"])
+        oid, osc, oa, ob, oc = chk.hybrid(mode, param, limit, Qb, tp, tr)
+        ok = bool((r.ids.cpu().numpy() == oid).all() and (r.score.cpu().numpy() == osc).all() and
+                  (r.count.cpu().numpy() == oc).all())
+        chk.close()
+    dist.barrier()
+    scan_ms = st.scan_ms_total / max(1, st.scan_launches_timed)
+    line = {"metric": "hybrid queries/sec", "value": nq * args.steps / (ms / 1e3), "unit": "queries/s", "n_gpus": world,
+            "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps, "higher_is_better": True,
+            "scaling": args.scaling, "vs_baseline": None,
+            "dtype": "f16 tensor-core filter + exact f32 re-score (f64 tail), f64 BM25/fusion", "data": "synthetic",
+            "config": config_dict(args, info, world, "rowshard"),
+            "roofline": {"bound": "tensor", "kernel": scan_kernel_desc(args, True, 16)[0], "avg_launch_ms": scan_ms,
+                         "achieved": 2.0 * 384 * (hi - lo) * min(nq, 256) / (scan_ms * 1e-3) / 1e12 if scan_ms else None,
+                         "unit": "TFLOP/s", "peak": None, "frac": None, "traffic": None,
+                         "tc_queries": int(st.tc_queries), "tc_fallback_queries": int(st.tc_fallback_queries)},
+            "clocks": clocks,
+            "e2e": {"value": nq * args.steps / wall, "unit": "queries/s", "h2d_bytes_per_step": int(Qh.numpy().nbytes),
+                    "d2h_bytes_per_step": int(nq * limit * 16 + nq * 4), "wall_ms_per_step": 1e3 * wall / args.steps},
+            "gpu_launches": int(st.kernel_launches), "exchange": sh.exchange_kind, "sharded_matches_single_gpu": ok}
     idx.close()
+    return line
 
 
 def run_bm25_10k(args, local_rank):
@@ -697,7 +937,7 @@ def run_bm25_10k(args, local_rank):
         sc, dc, cnt = idx.bm25(tok_indptr, terms, 10)
     wall = (time.perf_counter() - t0) / args.steps
     launches = int(idx.stats().kernel_launches)
-    touched = postings_touched(bm, tok_indptr, terms)
+    touched = postings_touched(bm, terms)
     import oracle
     cores = os.cpu_count() or 1
     os.environ["OMP_NUM_THREADS"] = str(cores)
@@ -729,90 +969,147 @@ def run_bm25_10k(args, local_rank):
     idx.close()
 
 
-def run_knn100m(args, rank, world, local_rank):
-    """configs[4]: synthetic 100M x 384 corpus as 12.5 M-row shards (one per GPU), top-100 with the NCCL
-    candidate merge.  Weak scaling: every rank always scans a full shard."""
+
+
+# ----------------------------------------------------------------------------- configs[4]: 100M-chunk corpus
+KNN100M_UNIT = 313 * 1024            # rows per generation unit (a whole number of vec0 blocks); 39 units = 12 499 968 rows
+KNN100M_TOTAL_UNITS = 312            # 99 999 744 rows ("100 M"): 8 shards of 39 units, each aligned to vec0 blocks
+
+
+def knn100m_measure(args, rank, world, local_rank, steps, batch=256, total_units=None):
+    """configs[4] AS SPECIFIED: a FIXED synthetic 100M x 384 fp32 corpus (99 999 744 rows: 312 units of 313 vec0
+    blocks, unit u generated from seed 1234+u whatever N is) sharded by row over N GPUs, top-100, candidate
+    exchange + merge — STRONG scaling over N = 2, 4, 8 (rows per GPU = 100M / N; 256 queries per step in total).
+    One GPU cannot hold 100M rows (153.6 GB fp32 + 76.8 GB fp16 shadow): N = 1 measures an ANCHOR, the first
+    half of the same corpus (= the N = 2 shard, no exchange)."""
     import torch
     import torch.distributed as dist
-    from rag_search_engine_b200 import _lib
+    from rag_search_engine_b200 import _lib, sharded
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
-    rows = (args.shard_rows // 1024) * 1024
-    g = torch.Generator(device=dev).manual_seed(1234 + rank)
+    units_total = total_units or KNN100M_TOTAL_UNITS
+    anchor = world == 1
+    n_shards = 2 if anchor else world
+    if units_total % n_shards:
+        return {"skipped": f"{units_total} units do not split over {n_shards} shards"}
+    upg = units_total // n_shards                       # units per GPU
+    rows = upg * KNN100M_UNIT
+    need = rows * 384 * 6 + rows * 4 * 17 + (2 << 30)
+    free, _total = torch.cuda.mem_get_info(dev)
+    if need > free:
+        return {"skipped": f"needs {need / 2**30:.0f} GiB per GPU, {free / 2**30:.0f} GiB free"}
+    t0 = time.time()
     emb = torch.empty((rows, 384), dtype=torch.float32, device=dev)
-    for s0 in range(0, rows, 1 << 20):
-        e0_ = min(rows, s0 + (1 << 20))
-        x = torch.randn((e0_ - s0, 384), generator=g, device=dev)
-        emb[s0:e0_] = x / x.norm(dim=1, keepdim=True)
+    for u in range(upg):
+        g = torch.Generator(device=dev).manual_seed(1234 + rank * upg + u)
+        x = torch.randn((KNN100M_UNIT, 384), generator=g, device=dev)
+        x /= x.norm(dim=1, keepdim=True)
+        emb[u * KNN100M_UNIT:(u + 1) * KNN100M_UNIT] = x
+        del x
     base = rank * rows
-    movie = (torch.arange(rows, device=dev, dtype=torch.int64) + base).to(torch.int32)
+    movie = ((torch.arange(rows, device=dev, dtype=torch.int64) + base) // 8).to(torch.int32)   # 8 chunks per "movie"
+    torch.cuda.synchronize()
+    build_s = time.time() - t0
     idx = _lib.Index(local_rank)
     if args.tc_mode >= 0:
         idx.set_tc_mode(args.tc_mode)
     stream = torch.cuda.current_stream(dev)
     idx.set_stream(stream.cuda_stream)
     idx.attach_embeddings_dev(emb.data_ptr(), rows, 384, movie_idx_ptr=movie.data_ptr(), pos_base=base, keepalive=(emb, movie))
-    nq, kp = args.batch, 100
+    nq, kp = batch, 100
     gq = torch.Generator(device=dev).manual_seed(99)
     Q = torch.randn((nq, 384), generator=gq, device=dev)
     Q /= Q.norm(dim=1, keepdim=True)
     if rank == 0:
-        Q[: min(8, nq)] = emb[torch.arange(min(8, nq), device=dev) * 1000 + 5]       # known self-hits
+        Q[: min(8, nq)] = emb[torch.arange(min(8, nq), device=dev) * 1000 + 5]       # known self-hits (rows of shard 0)
     if world > 1:
         dist.broadcast(Q, 0)
+    ex = sharded.CandidateExchange(nq, world, rank, dev)
+    ns = ex.hi - ex.lo
     cand = torch.empty((nq, kp, 3), dtype=torch.int64, device=dev)
-    flat = torch.empty((world * nq, kp, 3), dtype=torch.int64, device=dev)
-    od = torch.empty((nq, kp), dtype=torch.float32, device=dev); orow = torch.empty((nq, kp), dtype=torch.int64, device=dev)
-    om = torch.empty((nq, kp), dtype=torch.int32, device=dev); oc = torch.empty((nq,), dtype=torch.int32, device=dev)
+    od = torch.empty((max(ns, 1), kp), dtype=torch.float32, device=dev)
+    orow = torch.empty((max(ns, 1), kp), dtype=torch.int64, device=dev)
+    om = torch.empty((max(ns, 1), kp), dtype=torch.int32, device=dev)
+    oc = torch.empty((max(ns, 1),), dtype=torch.int32, device=dev)
+    flags = torch.zeros((1,), dtype=torch.int32, device=dev)
+    idx.set_defer_flags(True)
 
     def step():
         idx.knn_local_dev(Q.data_ptr(), nq, kp, cand.data_ptr())
-        if world > 1:
-            dist.all_gather_into_tensor(flat, cand)
-            idx.knn_merge_movies_dev(flat.data_ptr(), world, nq, kp, kp, od.data_ptr(), orow.data_ptr(), om.data_ptr(), oc.data_ptr())
-        else:
-            idx.knn_merge_movies_dev(cand.data_ptr(), 1, nq, kp, kp, od.data_ptr(), orow.data_ptr(), om.data_ptr(), oc.data_ptr())
+        idx.knn_flags_dev(flags.data_ptr())                                            # += flagged queries (device)
+        mine = ex.exchange(cand)                                                       # [world, ns, kp, 3]
+        if ns > 0:
+            idx.knn_merge_movies_dev(mine.data_ptr(), world, ns, kp, kp, od.data_ptr(), orow.data_ptr(), om.data_ptr(),
+                                     oc.data_ptr())
 
     for _ in range(max(args.warmup, 3)):
         step()
     torch.cuda.synchronize()
     if world > 1:
         dist.barrier()
+    flags.zero_()
     idx.set_timing(True); idx.stats_reset()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record(stream)
-    for _ in range(args.steps):
+    for _ in range(steps):
         step()
     e1.record(stream)
     torch.cuda.synchronize()
     ms = e0.elapsed_time(e1)
     st = idx.stats()
+    idx.set_timing(False)
+    # results: every rank holds its query slice; a checksum over all slices lets records of different N be compared
+    sig = torch.stack([(orow[:ns].to(torch.float64)).sum(), od[:ns].view(torch.int32).to(torch.float64).sum(),
+                       oc[:ns].to(torch.float64).sum(), flags.to(torch.float64).sum(),
+                       (od[:ns, 0] <= 1e-6).to(torch.float64).sum()]) if ns > 0 else torch.zeros(5, dtype=torch.float64, device=dev)
+    t = torch.tensor([ms], dtype=torch.float64, device=dev)
     if world > 1:
-        t = torch.tensor([ms], dtype=torch.float64, device=dev)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms = float(t.item())
-    if rank != 0:
-        return
-    ok = bool((od[: min(8, nq), 0] <= 1e-6).all().item() and (oc == kp).all().item())
-    peak = 6546.6
+        dist.all_reduce(sig, op=dist.ReduceOp.SUM)
+    ms = float(t.item())
+    sig = sig.cpu().tolist()
+    scan_ms = st.scan_ms_total / max(1, st.scan_launches_timed)
+    idx.close()
+    del emb, movie
+    torch.cuda.empty_cache()
+    peaks = {}
     pk = ROOT / "MEASURED_PEAKS.json"
     if pk.exists():
-        peak = float(json.loads(pk.read_text()).get("hbm_gbs", peak))
-    scan_ms = st.scan_ms_total / max(1, st.scan_launches_timed)
-    kname, row_bytes = scan_kernel_desc(args, int(st.tc_filter_launches) > 0, 16)
-    ach = rows * row_bytes / (scan_ms * 1e-3) / 1e9
-    print(json.dumps({"metric": "kNN top-100 queries/sec x corpus chunks (row-sharded, NCCL candidate merge)",
-                      "value": nq * args.steps / (ms / 1e3) * world * rows, "unit": "query-chunks/s",
-                      "queries_per_s": nq * args.steps / (ms / 1e3), "n_gpus": world, "steps": args.steps,
-                      "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps, "higher_is_better": True,
-                      "scaling": "weak", "vs_baseline": None, "dtype": f"{tc_kind(args)} filter + f32 exact re-score", "data": "synthetic",
-                      "config": {"workload": "configs[4]: synthetic 100M x 384 fp32 (12.5 M-row shard per GPU), top-100",
-                                 "rows_per_gpu": rows, "total_rows": rows * world, "queries_per_step": nq},
-                      "roofline": {"bound": "hbm", "kernel": kname, "algorithmic_bytes_per_launch": rows * row_bytes,
-                                   "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": None,
-                                   "avg_launch_ms": scan_ms},
-                      "self_hits_found_and_full_k": ok, "gpu_launches": int(st.kernel_launches)}), flush=True)
-    idx.close()
+        peaks = json.loads(pk.read_text())
+    total_rows = rows * world
+    qps = nq * steps / (ms / 1e3)
+    tfl = 2.0 * 384 * rows * min(nq, 256) / (scan_ms * 1e-3) / 1e12 if scan_ms > 0 else None
+    return {"workload": ("configs[4]: FIXED synthetic 99 999 744 x 384 fp32 corpus row-sharded over N GPUs, top-100, "
+                         "candidate exchange + merge; strong scaling over N = 2, 4, 8" if not anchor else
+                         "configs[4] ANCHOR: 100M rows do not fit one GPU — the first half of the corpus (the N = 2 shard) "
+                         "on one GPU, no exchange"),
+            "value": qps * total_rows, "unit": "query-chunks/s", "queries_per_s": qps, "ms_per_step": ms / steps, "steps": steps,
+            "n_gpus": world, "scaling": "strong" if not anchor else "anchor", "rows_per_gpu": rows, "total_rows": total_rows,
+            "queries_per_step": nq, "exchange": ex.kind, "build_s": round(build_s, 1),
+            "filter_pass_ms": scan_ms, "filter_tflops_per_gpu": tfl,
+            "filter_frac_of_sustained_peak": (tfl / float(peaks.get("bf16_tflops_sustained", 1379.6))) if tfl else None,
+            "shadow_stream_gbs_per_gpu": rows * ROW_BYTES_SHADOW / (scan_ms * 1e-3) / 1e9 if scan_ms > 0 else None,
+            "flagged_queries_in_timed_steps": int(sig[3]), "self_hits_found": int(sig[4]), "full_k": bool(sig[2] == nq * kp),
+            "result_checksum": {"rowid_sum": sig[0], "dist_bits_sum": sig[1]},
+            "gpu_launches": int(st.kernel_launches)}
+
+
+def run_knn100m(args, rank, world, local_rank):
+    """--workload knn100m: configs[4] alone (see knn100m_measure)."""
+    units = None
+    if args.shard_rows:                                   # a smaller corpus for experiments: units per GPU given
+        units = max(1, args.shard_rows // KNN100M_UNIT) * (2 if world == 1 else world)
+    r = knn100m_measure(args, rank, world, local_rank, args.steps, args.batch, total_units=units)
+    if rank != 0:
+        return
+    line = {"metric": "kNN top-100 queries/sec x corpus chunks (row-sharded, candidate exchange + merge)",
+            "value": r.get("value"), "unit": "query-chunks/s", "n_gpus": world, "steps": args.steps,
+            "warmup": max(args.warmup, 3), "ms_per_step": r.get("ms_per_step"), "higher_is_better": True,
+            "scaling": r.get("scaling"), "vs_baseline": None, "dtype": "f16-shadow filter + f32 exact re-score",
+            "data": "synthetic", "config": {"workload": r.get("workload"), "rows_per_gpu": r.get("rows_per_gpu"),
+                                            "total_rows": r.get("total_rows"), "queries_per_step": r.get("queries_per_step")},
+            "knn100m": r, "gpu_launches": r.get("gpu_launches")}
+    print(json.dumps(line), flush=True)
 
 
 def main():

@@ -45,6 +45,7 @@ extern "C" {
 #define RSE_MAX_FUSE_LIMIT 128
 #define RSE_MAX_QUERY_TOKENS 255
 #define RSE_RRF_NOT_FOUND 99999 /* hybrid_search.py:247 */
+#define RSE_MAX_STASH 16        /* staged batches that can be parked in HBM (rse_hybrid_stash) */
 
 /* tie_mode for the fusion entry points */
 #define RSE_TIE_REFERENCE 0 /* CPython set iteration order of the id union (hybrid_search.py:148,248) */
@@ -124,6 +125,13 @@ int rse_knn_movies(rse_index *h, const float *q_host, int32_t nq, int32_t k, int
  * read its per-query overflow flags. */
 int rse_knn_local_dev(rse_index *h, const float *q_dev, int32_t nq, int32_t kprime,
                       int64_t *cand_dev);
+/* Keep a row-sharded step free of host round trips: with deferral enabled rse_knn_local_dev never
+ * synchronises — a query the tensor-core path could not finish (survivor overflow: a mass tie at the K'-th
+ * distance) keeps key = -1 candidates and is only COUNTED: rse_knn_flags_dev enqueues `*flagged_dev +=
+ * (flagged queries of the last rse_knn_local_dev)` on the handle's stream.  The caller lets that counter travel
+ * with the step's results and repeats a step whose global count is non-zero with deferral off. */
+int rse_set_defer_flags(rse_index *h, int32_t enabled);
+int rse_knn_flags_dev(rse_index *h, int32_t *flagged_dev);
 /* Merge n_lists candidate lists per query (gathered_dev is [n_lists, nq, kprime, 3],
  * the layout all_gather produces), keep the first kprime under the key order, then
  * aggregate per movie like rse_knn_movies.  Outputs are DEVICE buffers [nq, k]. */
@@ -210,6 +218,10 @@ int rse_hybrid_run_merged_dev(rse_index *h, int32_t mode, double param, int32_t 
                               double *out_a_dev, double *out_b_dev, int32_t *out_count_dev);
 int rse_hybrid_fetch(rse_index *h, int32_t limit, int64_t *out_id, double *out_score, double *out_a,
                      double *out_b, int32_t *out_count);
+/* EXCHANGE the staged batch with stash slot `slot` (0 .. RSE_MAX_STASH-1); pointer swaps on the host, no device
+ * work.  stage(A); stash(0); stage(B); stash(1) parks two batches in HBM; a later stash(0) makes A the staged
+ * batch again (and parks whatever was staged).  For callers that rotate over several RESIDENT batches. */
+int rse_hybrid_stash(rse_index *h, int32_t slot);
 /* Pipelined form of rse_hybrid for a serving loop: at most TWO batches in flight per handle.
  *   submit : stage (host buffers -> pinned -> device, asynchronous) + run + an asynchronous copy of
  *            the results into a pinned slot owned by the handle; returns a ticket.  It returns as
@@ -261,6 +273,9 @@ typedef struct rse_stats {
   int64_t d2h_bytes;              /* bytes moved device -> host by the query entry points */
 } rse_stats;
 int rse_get_stats(rse_index *h, rse_stats *out);
+/* Survivor counts of the most recent K4 filter pass (one per query of its 256-query block; a count above the
+ * survivor cap of 8192 means the query overflowed and was re-run).  Synchronises.  n <= 256. */
+int rse_tc_last_survivors(rse_index *h, int32_t *out_counts, int32_t n);
 int rse_stats_reset(rse_index *h);
 /* Enable CUDA-event timing: an event pair around every scan launch (no extra syncs). */
 int rse_set_timing(rse_index *h, int32_t enabled);

@@ -76,6 +76,8 @@ _SIGNATURES = {
     "rse_knn_movies": (ctypes.c_int, [c_void_p, POINTER(c_float), c_int32, c_int32, c_int32, POINTER(c_float),
                                       POINTER(c_int64), POINTER(c_int32), POINTER(c_int32)]),
     "rse_knn_local_dev": (ctypes.c_int, [c_void_p, c_void_p, c_int32, c_int32, c_void_p]),
+    "rse_set_defer_flags": (ctypes.c_int, [c_void_p, c_int32]),
+    "rse_knn_flags_dev": (ctypes.c_int, [c_void_p, c_void_p]),
     "rse_knn_merge_movies_dev": (ctypes.c_int, [c_void_p, c_void_p, c_int32, c_int32, c_int32, c_int32, c_void_p,
                                                 c_void_p, c_void_p, c_void_p]),
     "rse_load_bm25": (ctypes.c_int, [c_void_p, POINTER(c_int64), POINTER(c_uint32), POINTER(c_uint32),
@@ -106,6 +108,8 @@ _SIGNATURES = {
     "rse_hybrid_collect": (ctypes.c_int, [c_void_p, c_int64, POINTER(c_int32), POINTER(c_int32), c_void_p, c_void_p,
                                           c_void_p, c_void_p, c_void_p]),
     "rse_hybrid_drain": (ctypes.c_int, [c_void_p, POINTER(c_int32)]),
+    "rse_hybrid_stash": (ctypes.c_int, [c_void_p, c_int32]),
+    "rse_tc_last_survivors": (ctypes.c_int, [c_void_p, POINTER(c_int32), c_int32]),
     "rse_get_stats": (ctypes.c_int, [c_void_p, POINTER(RseStats)]),
     "rse_stats_reset": (ctypes.c_int, [c_void_p]),
     "rse_set_timing": (ctypes.c_int, [c_void_p, c_int32]),
@@ -258,6 +262,13 @@ class Index:
 
     def knn_local_dev(self, q_ptr: int, nq: int, kprime: int, cand_ptr: int):
         self._check(self._L.rse_knn_local_dev(self._h, c_void_p(q_ptr), int(nq), int(kprime), c_void_p(cand_ptr)))
+
+    def set_defer_flags(self, on: bool):
+        """rse_knn_local_dev without the host round trip for the overflow flags (see include/rse.h)."""
+        self._check(self._L.rse_set_defer_flags(self._h, int(bool(on))))
+
+    def knn_flags_dev(self, flagged_ptr: int):
+        self._check(self._L.rse_knn_flags_dev(self._h, c_void_p(flagged_ptr)))
 
     def knn_merge_movies_dev(self, gathered_ptr: int, n_lists: int, nq: int, k: int, kprime: int, dist_ptr: int,
                              rowid_ptr: int, movie_ptr: int, count_ptr: int):
@@ -421,6 +432,17 @@ class Index:
                                                c_void_p(ob.ctypes.data), c_void_p(oc.ctypes.data)))
         del self._tickets[ticket]
         return oid, osc, oa, ob, oc
+
+    def hybrid_stash(self, slot: int):
+        """Exchange the staged batch with stash slot ``slot`` (several batches resident in HBM)."""
+        self._check(self._L.rse_hybrid_stash(self._h, int(slot)))
+        stash = self.__dict__.setdefault("_stash_nq", {})
+        stash[slot], self._staged_nq = getattr(self, "_staged_nq", 0), stash.get(slot, 0)
+
+    def tc_last_survivors(self, n: int = 256):
+        out = np.zeros(int(n), np.int32)
+        self._check(self._L.rse_tc_last_survivors(self._h, _ptr(out, c_int32), int(n)))
+        return out
 
     def hybrid_drain(self) -> int:
         """Wait for and discard every ticket still in flight; the handle accepts submits again afterwards."""

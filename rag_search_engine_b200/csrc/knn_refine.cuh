@@ -177,4 +177,13 @@ knn_refine_kernel(const float* __restrict__ emb, const float* __restrict__ amag,
   }
 }
 
+// *out += the number of queries whose status flag is set (rse_knn_flags_dev: the count rides along with the
+// results of a row-sharded step instead of a host round trip per step)
+__global__ void knn_flag_count_kernel(const int* __restrict__ status, int n, int* __restrict__ out) {
+  int c = 0;
+  for (int i = threadIdx.x; i < n; i += blockDim.x) c += status[i] != 0 ? 1 : 0;
+  c = __reduce_add_sync(0xFFFFFFFFu, c);
+  if ((threadIdx.x & 31) == 0 && c) atomicAdd(out, c);
+}
+
 }  // namespace rse

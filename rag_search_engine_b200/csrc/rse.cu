@@ -47,10 +47,16 @@ struct rse_index {
   size_t scan_ev_used = 0;
   // staged hybrid query batch (rse_hybrid_stage)
   int staged_nq = 0;
+  // rse_hybrid_stash: staged batches parked in HBM (a bench / server rotating over several resident batches)
+  struct Stash { DevBuf q_dev, b_tokptr, b_terms, b_idf; int nq = 0; } stash[RSE_MAX_STASH];
   // K4 tensor-core path
   int tc_mode = 0;                 // 0 auto, 1 off (exact scan only), 2 force on
   // pending tensor-core batch (knn_local_begin / knn_local_finish)
   bool knn_pending = false;
+  // rse_set_defer_flags: rse_knn_local_dev does not wait for the tensor-core path's overflow flags; they stay on
+  // the device (tc_status) and rse_knn_flags_dev adds their count into a caller-owned device counter
+  bool defer_flags_dev = false;
+  int last_flags_n = 0;
   const float* pend_q = nullptr;
   int pend_nq = 0, pend_kprime = 0;
   long long* pend_cand = nullptr;
@@ -802,6 +808,8 @@ void rse_destroy(rse_index* h) {
   if (h->ev_fused) cudaEventDestroy(h->ev_fused);
   for (int i = 0; i < 2; ++i) { if (h->pin_q[i]) cudaFreeHost(h->pin_q[i]); if (h->ev_q[i]) cudaEventDestroy(h->ev_q[i]); }
   free_buf(h->f_pack);
+  for (auto& st : h->stash)
+    for (DevBuf* d : {&st.q_dev, &st.b_tokptr, &st.b_terms, &st.b_idf}) free_buf(*d);
   if (h->ev_status) cudaEventDestroy(h->ev_status);
   if (h->ev_stage) cudaEventDestroy(h->ev_stage);
   for (cudaEvent_t e : h->tl) if (e) cudaEventDestroy(e);
@@ -964,7 +972,31 @@ int rse_knn_local_dev(rse_index* h, const float* q_dev, int32_t nq, int32_t kpri
   if (!h) return RSE_ERR_INVALID;
   if (!q_dev || !cand_dev || nq < 0) return fail(h, RSE_ERR_INVALID, "rse_knn_local_dev: bad arguments");
   CK(cudaSetDevice(h->device));
-  return knn_local(h, q_dev, nq, kprime, reinterpret_cast<long long*>(cand_dev));
+  h->last_flags_n = 0;
+  if (!h->defer_flags_dev) return knn_local(h, q_dev, nq, kprime, reinterpret_cast<long long*>(cand_dev));
+  int rc = knn_local_begin(h, q_dev, nq, kprime, reinterpret_cast<long long*>(cand_dev));
+  if (rc != RSE_OK) return rc;
+  if (h->knn_pending) {                  // tensor-core path: the flags are in tc_status; nobody waits for them here
+    h->knn_pending = false;
+    h->last_flags_n = nq;
+  }
+  return RSE_OK;
+}
+
+int rse_set_defer_flags(rse_index* h, int32_t enabled) {
+  if (!h) return RSE_ERR_INVALID;
+  h->defer_flags_dev = enabled != 0;
+  return RSE_OK;
+}
+
+int rse_knn_flags_dev(rse_index* h, int32_t* flagged_dev) {
+  if (!h) return RSE_ERR_INVALID;
+  if (!flagged_dev) return fail(h, RSE_ERR_INVALID, "rse_knn_flags_dev: flagged_dev is NULL");
+  if (h->last_flags_n <= 0) return RSE_OK;
+  CK(cudaSetDevice(h->device));
+  knn_flag_count_kernel<<<1, 256, 0, h->stream>>>(static_cast<const int*>(h->tc_status.p), h->last_flags_n, flagged_dev);
+  LAUNCHED(h);
+  return RSE_OK;
 }
 
 int rse_knn(rse_index* h, const float* q_host, int32_t nq, int32_t kprime, float* out_dist, int64_t* out_pos,
@@ -1767,6 +1799,28 @@ int rse_hybrid_collect(rse_index* h, int64_t ticket, int32_t* out_nq, int32_t* o
   std::memcpy(out_b, sl.pin + 24 * n, 8 * n);
   std::memcpy(out_count, sl.pin + 32 * n, 4 * static_cast<size_t>(sl.nq));
   ++h->next_collect;
+  return RSE_OK;
+}
+
+int rse_hybrid_stash(rse_index* h, int32_t slot) {
+  if (!h) return RSE_ERR_INVALID;
+  if (slot < 0 || slot >= RSE_MAX_STASH) return fail(h, RSE_ERR_INVALID, "rse_hybrid_stash: slot out of range");
+  if (h->next_collect < h->next_ticket)
+    return fail(h, RSE_ERR_STATE, "rse_hybrid_stash: tickets in flight (collect or drain them first)");
+  rse_index::Stash& st = h->stash[slot];
+  std::swap(h->q_dev, st.q_dev); std::swap(h->b_tokptr, st.b_tokptr); std::swap(h->b_terms, st.b_terms);
+  std::swap(h->b_idf, st.b_idf); std::swap(h->staged_nq, st.nq);
+  h->pack_n = 0; h->pack_nq = 0;
+  return RSE_OK;
+}
+
+int rse_tc_last_survivors(rse_index* h, int32_t* out_counts, int32_t n) {
+  if (!h) return RSE_ERR_INVALID;
+  if (!out_counts || n < 0 || n > kTcBN) return fail(h, RSE_ERR_INVALID, "rse_tc_last_survivors: bad arguments");
+  if (!h->tc_cnt.p) return fail(h, RSE_ERR_STATE, "rse_tc_last_survivors: the tensor-core path has not run");
+  CK(cudaSetDevice(h->device));
+  CK(cudaStreamSynchronize(h->stream));
+  CK(cudaMemcpy(out_counts, h->tc_cnt.p, sizeof(int32_t) * n, cudaMemcpyDeviceToHost));
   return RSE_OK;
 }
 

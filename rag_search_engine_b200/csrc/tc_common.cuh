@@ -14,7 +14,8 @@ namespace rse {
 constexpr int kTcBN = 256;                                 // queries per tensor-core pass (UMMA M of the CTA pair)
 constexpr float kTcEps = 2.5e-3f;                          // bound on |cos~ - cos| (knn_tc3.cuh header)
 constexpr int kTcCandCap = 8192;                           // survivors kept per query
-constexpr int kTcRefineCap = 2048;                         // rows re-scored exactly per query at most
+constexpr int kTcRefineCap = 4096;                         // rows re-scored exactly per query at most (r01: 2048; a dense
+                                                           // neighbourhood of near-duplicates needs the head-room)
 
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }

@@ -147,9 +147,10 @@ class SemanticSearch:
     # ------------------------------------------------------------------ query
     def query_top_k_vec(self, query_vecs, k: int = 5, knn_multiplier: int = 10) -> List[List[Dict[str, Any]]]:
         """Batch entry point on frozen query vectors [B, dim] → one reference-shaped result list per query."""
-        Q = np.ascontiguousarray(query_vecs, np.float32).reshape(-1, self._arr.dim if self._arr.dim else 1)
-        if self._arr.emb.shape[0] == 0:
+        Q = np.atleast_2d(np.ascontiguousarray(query_vecs, np.float32))
+        if self._arr.emb.shape[0] == 0:                         # no chunk embeddings: [] per query, like the reference
             return [[] for _ in range(Q.shape[0])]
+        Q = Q.reshape(-1, self._arr.dim)
         internal_k = max(k * knn_multiplier, k)                 # semantic_search.py:251
         dist, rowid, movie, cnt = self._index.knn_movies(Q, k, internal_k)
         out = []

@@ -41,7 +41,15 @@ def synth_movie_ids(n_movies: int, seed: int) -> np.ndarray:
 
 def synth_embeddings(n_movies: int, seed: int = 1234, dim: int = 384, mean_desc_chunks: float = 7.0,
                      dup_frac: float = 0.02, neardup_frac: float = 0.005, device: str = "cpu",
-                     chunk_rows: int = 1 << 20) -> SynthEmbeddings:
+                     chunk_rows: int = 1 << 20, distribution: str = "isotropic", n_centres: int = 20_000,
+                     spread: float = 0.6) -> SynthEmbeddings:
+    """``distribution="isotropic"``: L2-normalised N(0, I) rows — the K'-th neighbour of a query sits ~3.8 sigma
+    out in a thin tail (the friendliest case for a threshold filter).  ``"clustered"``: every movie draws one of
+    ``n_centres`` unit centres (its "genre") and each of its chunks is normalise(centre + spread * unit noise) —
+    sentence-embedding corpora are clustered like this, so the neighbourhood of a query is DENSE: the top-K' lie
+    inside a cluster of rows_per_centre rows whose cosines to the query differ by a few 1e-3."""
+    if distribution not in ("isotropic", "clustered"):
+        raise ValueError("distribution must be 'isotropic' or 'clustered'")
     g = torch.Generator(device="cpu").manual_seed(seed)
     n_desc = torch.poisson(torch.full((n_movies,), float(mean_desc_chunks)), generator=g).clamp_(min=1)
     per_movie = (1 + n_desc).to(torch.int64)
@@ -50,10 +58,19 @@ def synth_embeddings(n_movies: int, seed: int = 1234, dim: int = 384, mean_desc_
     dev = torch.device(device)
     emb = torch.empty((C, dim), dtype=torch.float32, device=dev)
     gd = torch.Generator(device=dev).manual_seed(seed + 1)
+    centres = centre_of_chunk = None
+    if distribution == "clustered":
+        centres = torch.randn((n_centres, dim), generator=gd, device=dev, dtype=torch.float32)
+        centres /= centres.norm(dim=1, keepdim=True)
+        centre_of_movie = torch.randint(0, n_centres, (n_movies,), generator=g)
+        centre_of_chunk = torch.repeat_interleave(centre_of_movie, per_movie).to(dev)
     for s in range(0, C, chunk_rows):
         e = min(C, s + chunk_rows)
         x = torch.randn((e - s, dim), generator=gd, device=dev, dtype=torch.float32)
         x /= x.norm(dim=1, keepdim=True)
+        if centres is not None:
+            x = centres[centre_of_chunk[s:e]] + spread * x
+            x /= x.norm(dim=1, keepdim=True)
         emb[s:e] = x
     # exact duplicates and 1-ulp near-duplicates
     n_dup = int(C * dup_frac)

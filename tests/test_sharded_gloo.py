@@ -44,8 +44,15 @@ class OracleBackend:
         self.emb = se.emb.numpy()[lo:hi]; self.movie_of = se.movie_of_chunk.numpy(); self.lo = lo
         self.ids = se.movie_ids; self.bm = bm; self.tok_indptr = tok_indptr; self.terms = terms
 
-    def knn_local(self, q_all, kprime):
+    def knn_local(self, q_all, kprime, flag=None):
         out = np.full((q_all.shape[0], kprime, 3), -1, np.int64)
+        if flag is not None and self.lo > 0 and not getattr(self, "flagged_once", False):
+            # the deferred (no host round trip) form of the LAST shard's first step leaves query 0 unfinished: all
+            # its candidates stay -1 and the count goes up — ShardedHybrid must notice on EVERY rank and repeat
+            # the step through the blocking form
+            self.flagged_once = True
+            flag += 1
+            return torch.from_numpy(out)
         for qi, q in enumerate(q_all.numpy()):
             if len(self.emb) == 0:
                 continue
@@ -103,6 +110,11 @@ def _worker(rank, world, port, out_q):
         be = OracleBackend(se, bm, tok_indptr, terms, bounds[rank], bounds[rank + 1])
         sh = sharded.ShardedHybrid(be, NQ)
         r = sh.step(torch.from_numpy(Q), 0, 60.0, LIMIT)
+        assert sh.flagged_steps == 1, "the flagged first step was not repeated on this rank"
+        r2 = sh.step(torch.from_numpy(Q), 0, 60.0, LIMIT)
+        assert sh.flagged_steps == 1 and int(r2.flagged.item()) == 0
+        assert torch.equal(r.ids, r2.ids) and torch.equal(r.score, r2.score)
+        assert "all_gather" in sh.exchange_kind               # gloo has no all-to-all
         out_q.put((rank, r.ids.numpy().copy(), r.score.numpy().copy(), r.count.numpy().copy()))
     finally:
         dist.destroy_process_group()
