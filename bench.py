@@ -578,7 +578,7 @@ def measure_small_batches(idx, Qn, limit):
         table.append(row)
     idx.set_tc_mode(0)
     return {"call": "rse_knn_movies, host buffers, S-600k, top-10 of K'=100", "rows": table,
-            "auto_threshold": "nq >= 4 (RSE_TC_MIN_BATCH)"}
+            "auto_threshold": "nq >= 2 (RSE_TC_MIN_BATCH)"}
 
 
 def measure_rowshard(args, rank, world, local_rank, se, bm, tok_indptr, terms, Q, Qn, info, mode, param, limit, steps):

@@ -195,7 +195,7 @@ class Index:
         self._check(self._L.rse_set_timing(self._h, int(bool(on))))
 
     def set_tc_mode(self, mode: int):
-        """0 = auto (batches of >= 4 queries on >= 256 k rows), 1 = exact scan only, 2 = tensor-core path
+        """0 = auto (batches of >= 2 queries on >= 256 k rows), 1 = exact scan only, 2 = tensor-core path
         whenever the shape allows it.  Results are identical in every mode."""
         self._check(self._L.rse_set_tc_mode(self._h, int(mode)))
 

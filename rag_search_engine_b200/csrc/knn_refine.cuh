@@ -53,7 +53,9 @@ knn_refine_kernel(const float* __restrict__ emb, const float* __restrict__ amag,
                   const double* __restrict__ sb, const uint2* __restrict__ cand_pairs,
                   const unsigned int* __restrict__ cand_count, int cap, int kprime, uint64_t pos_base,
                   const int64_t* __restrict__ rowid, const int32_t* __restrict__ movie_idx,
-                  long long* __restrict__ cand, int* __restrict__ status, int normalized) {
+                  long long* __restrict__ cand, int* __restrict__ status, int normalized,
+                  const float* __restrict__ thr2, const unsigned int* __restrict__ gate,
+                  unsigned long long* __restrict__ counters) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   uint2* pairs = reinterpret_cast<uint2*>(smem_raw);                       // [cap]
   __shared__ float s_q[kScanD];
@@ -62,6 +64,8 @@ knn_refine_kernel(const float* __restrict__ emb, const float* __restrict__ amag,
   __shared__ unsigned int s_warp[8];
   __shared__ uint32_t s_rows[kTcRefineCap];
   const int qi = blockIdx.x;
+  // second-chance pass: only the queries the second threshold kernel re-armed (thr2 finite), and only if any
+  if (thr2 != nullptr && (*gate == 0u || status[qi] == 0 || !(thr2[qi] < __int_as_float(0x7F800000)))) return;
   const unsigned int cnt = cand_count[qi];
   long long* out = cand + static_cast<int64_t>(qi) * kprime * 3;
   if (cnt > static_cast<unsigned int>(cap)) {                              // survivor overflow
@@ -121,7 +125,10 @@ knn_refine_kernel(const float* __restrict__ emb, const float* __restrict__ amag,
     for (int i = threadIdx.x; i < kprime * 3; i += blockDim.x) out[i] = -1ll;
     return;
   }
-  if (threadIdx.x == 0) status[qi] = 0;
+  if (threadIdx.x == 0) {
+    status[qi] = 0;
+    if (thr2 != nullptr && counters) atomicAdd(&counters[3], 1ull);      // answered by the second-chance pass
+  }
 
   // ---- (b) exact distances, lane-per-row from global memory (the reference's sequential sum)
   unsigned long long* keys = reinterpret_cast<unsigned long long*>(smem_raw);   // pairs are dead
@@ -175,6 +182,24 @@ knn_refine_kernel(const float* __restrict__ emb, const float* __restrict__ amag,
       c[0] = -1ll; c[1] = -1ll; c[2] = -1ll;
     }
   }
+}
+
+// Host fallback of the tensor-core path (rse.cu knn_local_finish): the flagged queries of a batch are gathered into
+// one contiguous group so that ONE exact scan pass serves up to 16 of them (r01 ran one pass per contiguous run
+// of flagged queries — scattered flags cost a 1 ms pass each), and their candidates scattered back afterwards.
+__global__ void knn_gather_queries_kernel(const float* __restrict__ q, const double* __restrict__ sb,
+                                          const int* __restrict__ list, int dim, float* __restrict__ q_out,
+                                          double* __restrict__ sb_out) {
+  const int src = list[blockIdx.x];
+  for (int i = threadIdx.x; i < dim; i += blockDim.x)
+    q_out[static_cast<int64_t>(blockIdx.x) * dim + i] = q[static_cast<int64_t>(src) * dim + i];
+  if (threadIdx.x == 0) sb_out[blockIdx.x] = sb[src];
+}
+__global__ void knn_scatter_cand_kernel(const long long* __restrict__ src, const int* __restrict__ list, int per_query,
+                                        long long* __restrict__ dst) {
+  const int q = list[blockIdx.x];
+  for (int i = threadIdx.x; i < per_query; i += blockDim.x)
+    dst[static_cast<int64_t>(q) * per_query + i] = src[static_cast<int64_t>(blockIdx.x) * per_query + i];
 }
 
 // *out += the number of queries whose status flag is set (rse_knn_flags_dev: the count rides along with the

@@ -51,6 +51,7 @@ struct rse_index {
   struct Stash { DevBuf q_dev, b_tokptr, b_terms, b_idf; int nq = 0; } stash[RSE_MAX_STASH];
   // K4 tensor-core path
   int tc_mode = 0;                 // 0 auto, 1 off (exact scan only), 2 force on
+  bool second_chance = true;       // RSE_NO_SECOND_CHANCE=1 switches the second filter pass off (diagnostics)
   // pending tensor-core batch (knn_local_begin / knn_local_finish)
   bool knn_pending = false;
   // rse_set_defer_flags: rse_knn_local_dev does not wait for the tensor-core path's overflow flags; they stay on
@@ -111,6 +112,7 @@ struct rse_index {
   cudaEvent_t tl[8] = {};
   bool tl_set[8] = {};
   DevBuf tc_thr, tc_rows, tc_cnt, tc_status;
+  DevBuf fb_list, fb_q, fb_sb, fb_cand;       // exact-scan fallback of flagged queries, gathered (knn_local_finish)
   // fp16 normalised shadow of the corpus for knn_tc3 (built lazily at the first tensor-core batch)
   DevBuf tc_shadow, tc_q16;
   int shadow_state = 0;            // 0 = not built, 1 = usable, -1 = corpus has non-finite norms: exact scan only
@@ -374,9 +376,10 @@ int make_tmap_lines(rse_index* h, CUtensorMap* out, const void* base, int64_t li
   return RSE_OK;
 }
 
-// refine + exact re-score + emit for one block of queries whose survivors are in tc_rows / tc_cnt
+// refine + exact re-score + emit for one block of queries whose survivors are in tc_rows / tc_cnt.
+// thr2 / gate != NULL: the second-chance pass (only the queries tc3_second_threshold_kernel re-armed).
 int knn_tc_refine(rse_index* h, const float* q_dev, const double* sb, int nqb, int kprime, long long* cand_dev,
-                  int* status_dev, int normalized) {
+                  int* status_dev, const float* thr2, const unsigned int* gate) {
   if (!(h->attr_mask & (1u << 10))) {
     CK(cudaFuncSetAttribute(knn_refine_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kTcCandCap * 8));
     CK(cudaFuncSetAttribute(knn_refine_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kTcCandCap * 8));
@@ -386,12 +389,12 @@ int knn_tc_refine(rse_index* h, const float* q_dev, const double* sb, int nqb, i
     knn_refine_kernel<true><<<nqb, kSelThreads, kTcCandCap * 8, h->stream>>>(
         h->emb, h->amag, q_dev, sb, static_cast<const uint2*>(h->tc_rows.p),
         static_cast<const unsigned int*>(h->tc_cnt.p), kTcCandCap, kprime, h->pos_base, h->rowid, h->movie_idx,
-        cand_dev, status_dev, normalized);
+        cand_dev, status_dev, 1, thr2, gate, h->dev_counters);
   else
     knn_refine_kernel<false><<<nqb, kSelThreads, kTcCandCap * 8, h->stream>>>(
         h->emb, h->amag, q_dev, sb, static_cast<const uint2*>(h->tc_rows.p),
         static_cast<const unsigned int*>(h->tc_cnt.p), kTcCandCap, kprime, h->pos_base, h->rowid, h->movie_idx,
-        cand_dev, status_dev, normalized);
+        cand_dev, status_dev, 1, thr2, gate, h->dev_counters);
   LAUNCHED(h);
   return RSE_OK;
 }
@@ -510,9 +513,9 @@ int knn_tc3_block(rse_index* h, const float* q_dev, const double* sb, int nqb, i
     if (rc != RSE_OK) return rc;
     h->tmap_q16_ok = true;
   }
-  ENSURE(h->tc_thr, sizeof(float) * kTcBN);
+  ENSURE(h->tc_thr, sizeof(float) * 2 * kTcBN);               // [0, 256): first-pass thresholds, [256, 512): second chance
   ENSURE(h->tc_rows, sizeof(uint2) * static_cast<size_t>(kTcBN) * kTcCandCap);
-  ENSURE(h->tc_cnt, sizeof(unsigned int) * kTcBN);
+  ENSURE(h->tc_cnt, sizeof(unsigned int) * (kTcBN + 4));      // [256]: the second-chance gate
   ENSURE(h->sel, sizeof(SelState) * kTcBN);
 
   const int64_t n_tiles = (h->n_rows + kT3TileRows - 1) / kT3TileRows;
@@ -543,10 +546,10 @@ int knn_tc3_block(rse_index* h, const float* q_dev, const double* sb, int nqb, i
   if (sparse_probe) {
     ld_sel = static_cast<int64_t>(probe_clusters) * 2 * kT3ProbeTop;
     knn_tc3_kernel<2><<<grid_p, kT3Threads, kT3SmemBytes, h->stream>>>(
-        h->tmap_a16, h->tmap_q16, n_probe, tile_stride, nqb, nullptr, dist, ld_sel, nullptr, nullptr, 0);
+        h->tmap_a16, h->tmap_q16, n_probe, tile_stride, nqb, nullptr, dist, ld_sel, nullptr, nullptr, 0, nullptr);
   } else {
     knn_tc3_kernel<0><<<grid_p, kT3Threads, kT3SmemBytes, h->stream>>>(
-        h->tmap_a16, h->tmap_q16, n_probe, tile_stride, nqb, nullptr, dist, ld_probe, nullptr, nullptr, 0);
+        h->tmap_a16, h->tmap_q16, n_probe, tile_stride, nqb, nullptr, dist, ld_probe, nullptr, nullptr, 0, nullptr);
   }
   LAUNCHED(h);
   if (sparse_probe && ld_sel <= kT3SelMax) {
@@ -569,7 +572,7 @@ int knn_tc3_block(rse_index* h, const float* q_dev, const double* sb, int nqb, i
   }
 
   // 2. filter pass over all rows
-  CK(cudaMemsetAsync(h->tc_cnt.p, 0, sizeof(unsigned int) * kTcBN, h->stream));
+  CK(cudaMemsetAsync(h->tc_cnt.p, 0, sizeof(unsigned int) * (kTcBN + 4), h->stream));
   const int grid_f = 2 * static_cast<int>(std::min<int64_t>(max_clusters, n_tiles));
   cudaEvent_t e0 = nullptr, e1 = nullptr;
   if (h->timing && h->scan_ev_used + 2 <= (1u << 16)) {
@@ -583,7 +586,7 @@ int knn_tc3_block(rse_index* h, const float* q_dev, const double* sb, int nqb, i
   tl_mark(h, kTlPrefilter, h->stream);
   knn_tc3_kernel<1><<<grid_f, kT3Threads, kT3SmemBytes, h->stream>>>(
       h->tmap_a16, h->tmap_q16, n_tiles, 1, nqb, thr, nullptr, 0, static_cast<uint2*>(h->tc_rows.p),
-      static_cast<unsigned int*>(h->tc_cnt.p), kTcCandCap);
+      static_cast<unsigned int*>(h->tc_cnt.p), kTcCandCap, nullptr);
   LAUNCHED(h);
   tl_mark(h, kTlFilterEnd, h->stream);
   {
@@ -598,7 +601,29 @@ int knn_tc3_block(rse_index* h, const float* q_dev, const double* sb, int nqb, i
   h->stats.tc_filter_launches++;
 
   // 3. refine on the approximate values, 4. exact re-score + sort + emit (one CTA per query)
-  return knn_tc_refine(h, q_dev, sb, nqb, kprime, cand_dev, status_dev, 1);
+  {
+    int rc = knn_tc_refine(h, q_dev, sb, nqb, kprime, cand_dev, status_dev, nullptr, nullptr);
+    if (rc != RSE_OK) return rc;
+  }
+  if (!h->second_chance) return RSE_OK;
+  // 5. second chance for queries whose survivor list overflowed (a dense neighbourhood): a tight threshold from
+  //    the survivors that were kept, one more filter pass + refine for those queries only.  Enqueued
+  //    unconditionally, gated on the device: three near-empty launches when no query needs it.
+  if (!(h->attr_mask & (1u << 16))) {
+    CK(cudaFuncSetAttribute(tc3_second_threshold_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kTcCandCap * 4));
+    h->attr_mask |= 1u << 16;
+  }
+  float* thr2 = thr + kTcBN;
+  unsigned int* gate = static_cast<unsigned int*>(h->tc_cnt.p) + kTcBN;
+  tc3_second_threshold_kernel<<<kTcBN, 256, kTcCandCap * 4, h->stream>>>(
+      status_dev, static_cast<const uint2*>(h->tc_rows.p), static_cast<unsigned int*>(h->tc_cnt.p), kTcCandCap, nqb,
+      kprime, thr2, gate);
+  LAUNCHED(h);
+  knn_tc3_kernel<1><<<grid_f, kT3Threads, kT3SmemBytes, h->stream>>>(
+      h->tmap_a16, h->tmap_q16, n_tiles, 1, nqb, thr2, nullptr, 0, static_cast<uint2*>(h->tc_rows.p),
+      static_cast<unsigned int*>(h->tc_cnt.p), kTcCandCap, gate);
+  LAUNCHED(h);
+  return knn_tc_refine(h, q_dev, sb, nqb, kprime, cand_dev, status_dev, thr2, gate);
 }
 
 bool tc_eligible(const rse_index* h, int nq, int kprime) {
@@ -669,16 +694,29 @@ int knn_local_finish(rse_index* h) {
   long long* cand_dev = h->pend_cand;
   const double* sb = static_cast<const double*>(h->sb.p);
   const int* st = h->pin_status;
-  for (int q = 0; q < nq;) {
-    if (!st[q]) { ++q; continue; }
-    int e = q;
-    while (e < nq && st[e] && e - q < kScanMaxQB) ++e;          // contiguous run of overflowed queries
-    h->stats.tc_fallback_queries += e - q;
-    int rc = knn_exact_groups(h, q_dev + static_cast<int64_t>(q) * h->dim, sb + q, e - q, kprime,
-                              cand_dev + static_cast<int64_t>(q) * kprime * 3);
-    if (rc != RSE_OK) return rc;
-    q = e;
-  }
+  std::vector<int> flagged;
+  for (int q = 0; q < nq; ++q)
+    if (st[q]) flagged.push_back(q);
+  if (flagged.empty()) return RSE_OK;
+  // the flagged queries (a mass tie at the K'-th distance; second chance already tried) go through the exact scan,
+  // gathered into one contiguous group: one pass serves up to 16 of them wherever they sat in the batch
+  const int nf = static_cast<int>(flagged.size());
+  h->stats.tc_fallback_queries += nf;
+  ENSURE(h->fb_list, sizeof(int) * nf);
+  ENSURE(h->fb_q, sizeof(float) * static_cast<size_t>(nf) * h->dim);
+  ENSURE(h->fb_sb, sizeof(double) * nf);
+  ENSURE(h->fb_cand, sizeof(long long) * static_cast<size_t>(nf) * kprime * 3);
+  CK(cudaMemcpyAsync(h->fb_list.p, flagged.data(), sizeof(int) * nf, cudaMemcpyHostToDevice, h->stream));
+  CK(cudaStreamSynchronize(h->stream));                      // `flagged` is a pageable temporary
+  knn_gather_queries_kernel<<<nf, 128, 0, h->stream>>>(q_dev, sb, static_cast<const int*>(h->fb_list.p), h->dim,
+                                                      static_cast<float*>(h->fb_q.p), static_cast<double*>(h->fb_sb.p));
+  LAUNCHED(h);
+  int rc = knn_exact_groups(h, static_cast<const float*>(h->fb_q.p), static_cast<const double*>(h->fb_sb.p), nf, kprime,
+                            static_cast<long long*>(h->fb_cand.p));
+  if (rc != RSE_OK) return rc;
+  knn_scatter_cand_kernel<<<nf, 128, 0, h->stream>>>(static_cast<const long long*>(h->fb_cand.p),
+                                                    static_cast<const int*>(h->fb_list.p), kprime * 3, cand_dev);
+  LAUNCHED(h);
   return RSE_OK;
 }
 
@@ -775,6 +813,7 @@ int rse_create(int32_t device, rse_index** out) {
   // diagnostics: RSE_NO_OVERLAP=1 keeps the hybrid step's BM25 on the caller's stream (no second stream)
   if (const char* ev = std::getenv("RSE_NO_OVERLAP")) h->overlap_enabled = !(ev[0] == '1');
   if (const char* ev = std::getenv("RSE_TIMELINE")) h->timeline = ev[0] == '1';
+  if (const char* ev = std::getenv("RSE_NO_SECOND_CHANCE")) h->second_chance = !(ev[0] == '1');
   *out = h;
   return RSE_OK;
 }
@@ -791,7 +830,7 @@ void rse_destroy(rse_index* h) {
                     &h->o_rowid, &h->o_movie, &h->o_count, &h->b_tokptr, &h->b_terms, &h->b_idf, &h->b_chi, &h->b_clo,
                     &h->b_ccnt, &h->b_score, &h->b_doc, &h->b_count, &h->f_bid, &h->f_bsc, &h->f_bcnt, &h->f_sid,
                     &h->f_sds, &h->f_scnt, &h->f_oid, &h->f_osc, &h->f_oa, &h->f_ob, &h->f_ocnt, &h->tc_thr,
-                    &h->tc_rows, &h->tc_cnt, &h->tc_status, &h->tc_q16, &h->b_shi, &h->b_slo, &h->b_scnt,
+                    &h->tc_rows, &h->tc_cnt, &h->tc_status, &h->fb_list, &h->fb_q, &h->fb_sb, &h->fb_cand, &h->tc_q16, &h->b_shi, &h->b_slo, &h->b_scnt,
                     &h->b_status, &h->b_flagged})
     free_buf(*b);
   if (h->pin_status) cudaFreeHost(h->pin_status);
@@ -887,13 +926,14 @@ int rse_get_stats(rse_index* h, rse_stats* out) {
     h->scan_ev_used = 0;
   }
   if (h->dev_counters) {
-    unsigned long long c[3] = {0, 0, 0};
+    unsigned long long c[4] = {0, 0, 0, 0};
     CK(cudaStreamSynchronize(h->stream));
     if (h->stream_b) CK(cudaStreamSynchronize(h->stream_b));
     CK(cudaMemcpy(c, h->dev_counters, sizeof(c), cudaMemcpyDeviceToHost));
     h->stats.bm25_fallback_queries = static_cast<int64_t>(c[0]);
     h->stats.bm25_finalists = static_cast<int64_t>(c[1]);
     h->stats.bm25_candidates = static_cast<int64_t>(c[2]);
+    h->stats.tc_second_chance_queries = static_cast<int64_t>(c[3]);
   }
   *out = h->stats;
   return RSE_OK;

@@ -111,8 +111,8 @@ def test_stats_counters(small_world):
 
 
 def test_small_batches_take_the_tensor_core_path_and_match_the_exact_scan():
-    """rse.h RSE_TC_MIN_BATCH = 4: on a corpus of >= 256 k rows a 4-query batch goes through K4 (r01: 48), 3 do not;
-    results are identical to the exact scan either way."""
+    """rse.h RSE_TC_MIN_BATCH = 2: on a corpus of >= 256 k rows a 2-query batch goes through K4 (r01: 48), a single
+    query takes the streaming scan; results are identical to the exact scan either way."""
     from rag_search_engine_b200 import _lib
     rng = np.random.default_rng(41)
     n = 262_144 + 1000
@@ -123,17 +123,17 @@ def test_small_batches_take_the_tensor_core_path_and_match_the_exact_scan():
     try:
         idx.load_embeddings(emb)
         idx.stats_reset()
-        a3 = idx.knn(Q[:3], 100)
+        a3 = idx.knn(Q[:1], 100)
         assert idx.stats().tc_queries == 0
-        a4 = idx.knn(Q[:4], 100)
+        a4 = idx.knn(Q[:2], 100)
         a8 = idx.knn(Q, 100)
         st = idx.stats()
-        assert st.tc_queries == 12 and st.tc_fallback_queries == 0
+        assert st.tc_queries == 10 and st.tc_fallback_queries == 0
         surv = idx.tc_last_survivors(8)
         assert (surv >= 100).all() and (surv <= 8192).all()
         idx.set_tc_mode(1)
         e8 = idx.knn(Q, 100)
-        assert same(a8, e8) and same([x[:3] for x in a8], a3) and same([x[:4] for x in a8], a4)
+        assert same(a8, e8) and same([x[:1] for x in a8], a3) and same([x[:2] for x in a8], a4)
         od, orow = oracle.vec0_knn(emb, Q[0], 100, literal=False)
         assert a8[1][0].tolist() == orow.tolist() and a8[0][0].view(np.uint32).tolist() == od.view(np.uint32).tolist()
     finally:
