@@ -595,8 +595,7 @@ def measure_rowshard(args, rank, world, local_rank, se, bm, tok_indptr, terms, Q
     stream = torch.cuda.current_stream(device)
     idx = make_handle(args, local_rank, stream, se, bm, lo, hi, info["dim"])
     Qb, tp, tr = batch_slice(tok_indptr, terms, Qn, 0, nq)
-    backend = sharded.LibrseShardBackend(idx, Qb, tp, tr, device)
-    sh = sharded.ShardedHybrid(backend, nq)
+    sh = sharded.NcclShardedHybrid(idx, Qb, tp, tr, device, nq)
     Qd = Q[:nq].to(device).contiguous()
     for _ in range(3):
         sh.step(Qd, mode, param, limit)
@@ -604,8 +603,9 @@ def measure_rowshard(args, rank, world, local_rank, se, bm, tok_indptr, terms, Q
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record(stream)
     for _ in range(steps):
-        r = sh.step(Qd, mode, param, limit)
+        r = sh.step(Qd, mode, param, limit, check=False)       # no host round trip inside the timed steps ...
     e1.record(stream)
+    flagged_last = int(r.flagged.item())                       # ... the last step's flag count is checked here
     torch.cuda.synchronize(); dist.barrier()
     t = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=device)
     dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -621,7 +621,7 @@ def measure_rowshard(args, rank, world, local_rank, se, bm, tok_indptr, terms, Q
     dist.barrier()
     return {"value": nq * steps / (ms / 1e3), "unit": "queries/s", "ms_per_step": ms / steps, "steps": steps,
             "queries_per_step": nq, "parallelism": f"row-shard x{world} + candidate exchange (top-K') + query-slice BM25/fusion",
-            "exchange": sh.exchange_kind, "sharded_matches_single_gpu": ok}
+            "exchange": sh.exchange_kind, "flagged_queries_last_step": flagged_last, "sharded_matches_single_gpu": ok}
 
 
 # ----------------------------------------------------------------------------- B200 arm
@@ -866,8 +866,7 @@ def run_b200_rowshard(args, rank, world, local_rank, se, bm, tok_indptr, terms, 
     idx = make_handle(args, local_rank, stream, se, bm, lo, hi, info["dim"])
     Qn = Q.cpu().numpy()
     Qb, tp, tr = batch_slice(tok_indptr, terms, Qn, 0, nq)
-    backend = sharded.LibrseShardBackend(idx, Qb, tp, tr, device)
-    sh = sharded.ShardedHybrid(backend, nq)
+    sh = sharded.NcclShardedHybrid(idx, Qb, tp, tr, device, nq)
     Qd = Q[:nq].to(device).contiguous()
     for _ in range(max(args.warmup, 3)):
         sh.step(Qd, mode, param, limit)
@@ -876,7 +875,7 @@ def run_b200_rowshard(args, rank, world, local_rank, se, bm, tok_indptr, terms, 
     sampler = ClockSampler(local_rank); sampler.start()
     tm.e0.record(stream)
     for _ in range(args.steps):
-        r = sh.step(Qd, mode, param, limit)
+        r = sh.step(Qd, mode, param, limit, check=False)
     tm.e1.record(stream)
     torch.cuda.synchronize(); dist.barrier()
     clocks = sampler.stop()
@@ -887,7 +886,7 @@ def run_b200_rowshard(args, rank, world, local_rank, se, bm, tok_indptr, terms, 
     torch.cuda.synchronize(); dist.barrier()
     t0 = time.perf_counter()
     for _ in range(args.steps):
-        backend.stage_slice(sh.lo, sh.hi)
+        sh.stage_slice()
         Qd2 = Qh.to(device, non_blocking=True)
         r2 = sh.step(Qd2, mode, param, limit)
         _ = r2.ids.cpu(), r2.score.cpu(), r2.count.cpu()
@@ -1024,8 +1023,15 @@ def knn100m_measure(args, rank, world, local_rank, steps, batch=256, total_units
         Q[: min(8, nq)] = emb[torch.arange(min(8, nq), device=dev) * 1000 + 5]       # known self-hits (rows of shard 0)
     if world > 1:
         dist.broadcast(Q, 0)
-    ex = sharded.CandidateExchange(nq, world, rank, dev)
-    ns = ex.hi - ex.lo
+    qsl = sharded.query_slices(nq, world)
+    ns = qsl[rank + 1] - qsl[rank]
+    exchange_kind = "none (1 rank)"
+    if world > 1:                                         # the handle owns the NCCL communicator (include/rse.h)
+        ids = [idx.comm_unique_id() if rank == 0 else None]
+        dist.broadcast_object_list(ids, src=0)
+        idx.comm_init(ids[0], world, rank)
+        n_ranks, _r, ver = idx.comm_info()
+        exchange_kind = f"library-owned NCCL {ver}: grouped ncclSend/ncclRecv all-to-all by query slice ({n_ranks} ranks)"
     cand = torch.empty((nq, kp, 3), dtype=torch.int64, device=dev)
     od = torch.empty((max(ns, 1), kp), dtype=torch.float32, device=dev)
     orow = torch.empty((max(ns, 1), kp), dtype=torch.int64, device=dev)
@@ -1035,12 +1041,13 @@ def knn100m_measure(args, rank, world, local_rank, steps, batch=256, total_units
     idx.set_defer_flags(True)
 
     def step():
+        if world > 1:      # local top-K' of all queries -> all-to-all -> merge + aggregation of this rank's slice, one call
+            idx.knn_sharded_dev(Q.data_ptr(), nq, kp, kp, od.data_ptr(), orow.data_ptr(), om.data_ptr(), oc.data_ptr(),
+                                flags.data_ptr())
+            return
         idx.knn_local_dev(Q.data_ptr(), nq, kp, cand.data_ptr())
         idx.knn_flags_dev(flags.data_ptr())                                            # += flagged queries (device)
-        mine = ex.exchange(cand)                                                       # [world, ns, kp, 3]
-        if ns > 0:
-            idx.knn_merge_movies_dev(mine.data_ptr(), world, ns, kp, kp, od.data_ptr(), orow.data_ptr(), om.data_ptr(),
-                                     oc.data_ptr())
+        idx.knn_merge_movies_dev(cand.data_ptr(), 1, nq, kp, kp, od.data_ptr(), orow.data_ptr(), om.data_ptr(), oc.data_ptr())
 
     for _ in range(max(args.warmup, 3)):
         step()
@@ -1085,7 +1092,7 @@ def knn100m_measure(args, rank, world, local_rank, steps, batch=256, total_units
                          "on one GPU, no exchange"),
             "value": qps * total_rows, "unit": "query-chunks/s", "queries_per_s": qps, "ms_per_step": ms / steps, "steps": steps,
             "n_gpus": world, "scaling": "strong" if not anchor else "anchor", "rows_per_gpu": rows, "total_rows": total_rows,
-            "queries_per_step": nq, "exchange": ex.kind, "build_s": round(build_s, 1),
+            "queries_per_step": nq, "exchange": exchange_kind, "build_s": round(build_s, 1),
             "filter_pass_ms": scan_ms, "filter_tflops_per_gpu": tfl,
             "filter_frac_of_sustained_peak": (tfl / float(peaks.get("bf16_tflops_sustained", 1379.6))) if tfl else None,
             "shadow_stream_gbs_per_gpu": rows * ROW_BYTES_SHADOW / (scan_ms * 1e-3) / 1e9 if scan_ms > 0 else None,

@@ -250,6 +250,43 @@ int rse_hybrid_collect(rse_index *h, int64_t ticket, int32_t *out_nq, int32_t *o
  * submit and its collect): afterwards the handle accepts submits again.  out_dropped (optional) = how many. */
 int rse_hybrid_drain(rse_index *h, int32_t *out_dropped);
 
+/* ------------------------------------------------------------------ multi-GPU: row shards over one box
+ * One process per GPU, one handle per process; the HANDLE owns the NCCL communicator (NCCL is bound at run time:
+ * libnccl.so.2, or $RSE_NCCL_LIB).  The chunk-embedding matrix is cut by row into contiguous shards aligned to
+ * vec0 blocks (rse_load_embeddings / rse_attach_embeddings_dev with pos_base = the shard's first global position);
+ * the BM25 index is replicated; rank r owns the contiguous query slice [r*nq/N ...) of every batch (the split of
+ * sharded.query_slices).  The reference has no counterpart (single process, semantic_search.py:254-261 scans one
+ * table); results equal those of one handle holding the whole corpus.
+ *   rse_comm_unique_id : rank 0 creates the 128-byte id and hands it to the other ranks by any means
+ *                        (torch.distributed broadcast, a file, an environment variable);
+ *   rse_comm_init      : every rank, collectively (ncclCommInitRank on the handle's device). */
+#define RSE_COMM_ID_BYTES 128
+int rse_comm_unique_id(uint8_t *out_id);
+int rse_comm_init(rse_index *h, const uint8_t *id_bytes, int32_t n_ranks, int32_t rank);
+int rse_comm_destroy(rse_index *h);
+int rse_comm_info(rse_index *h, int32_t *n_ranks, int32_t *rank, int32_t *nccl_version);
+/* The exchange step alone: cand_dev [nq, kprime, 3] (this shard's local top-K' of ALL queries, rse_knn_local_dev)
+ * -> mine_dev [n_ranks, ns, kprime, 3] (every shard's candidates for THIS rank's ns queries): an all-to-all by
+ * query slice (grouped ncclSend / ncclRecv) on the handle's stream. */
+int rse_comm_exchange_candidates_dev(rse_index *h, const int64_t *cand_dev, int32_t nq, int32_t kprime,
+                                     int64_t *mine_dev);
+int rse_comm_allgather_dev(rse_index *h, const void *send_dev, void *recv_dev, int64_t bytes_per_rank);
+/* configs[4]: sharded KNN + per-movie aggregation in one call — local top-K' of all nq_all queries on this
+ * shard, candidate exchange, merge + aggregation of this rank's query slice.  Outputs [ns, k] DEVICE buffers.
+ * flagged_dev (optional, int32 on the device): never wait for the host; *flagged_dev += the queries this shard
+ * could not finish (see rse_set_defer_flags).  NULL: blocking and always exact.  Collective: every rank calls. */
+int rse_knn_sharded_dev(rse_index *h, const float *q_all_dev, int32_t nq_all, int32_t k, int32_t kprime,
+                        float *out_dist_dev, int64_t *out_chunk_rowid_dev, int32_t *out_movie_idx_dev,
+                        int32_t *out_count_dev, int32_t *flagged_dev);
+/* The hybrid step, row-sharded: the staged batch (rse_hybrid_stage) is THIS rank's query slice (its tokens; the
+ * staged vectors are not used), q_all_dev holds the vectors of the whole batch.  KNN local top-K' of all queries
+ * (the slice's BM25 runs underneath the filter pass) -> exchange -> merge + aggregation + fusion of the slice.
+ * Outputs [ns, limit] DEVICE buffers; flagged_dev as above.  Collective. */
+int rse_hybrid_sharded_run_dev(rse_index *h, int32_t mode, double param, int32_t tie_mode, int32_t limit,
+                               int32_t knn_multiplier, double k1, double b, const float *q_all_dev, int32_t nq_all,
+                               int64_t *out_id_dev, double *out_score_dev, double *out_a_dev, double *out_b_dev,
+                               int32_t *out_count_dev, int32_t *flagged_dev);
+
 /* ------------------------------------------------------------------ introspection
  * Counters since the last rse_stats_reset: kernels launched by this library,
  * device ms of the last call per stage (CUDA events on the handle's stream). */

@@ -110,6 +110,17 @@ _SIGNATURES = {
     "rse_hybrid_drain": (ctypes.c_int, [c_void_p, POINTER(c_int32)]),
     "rse_hybrid_stash": (ctypes.c_int, [c_void_p, c_int32]),
     "rse_tc_last_survivors": (ctypes.c_int, [c_void_p, POINTER(c_int32), c_int32]),
+    "rse_comm_unique_id": (ctypes.c_int, [c_void_p]),
+    "rse_comm_init": (ctypes.c_int, [c_void_p, c_void_p, c_int32, c_int32]),
+    "rse_comm_destroy": (ctypes.c_int, [c_void_p]),
+    "rse_comm_info": (ctypes.c_int, [c_void_p, POINTER(c_int32), POINTER(c_int32), POINTER(c_int32)]),
+    "rse_comm_exchange_candidates_dev": (ctypes.c_int, [c_void_p, c_void_p, c_int32, c_int32, c_void_p]),
+    "rse_comm_allgather_dev": (ctypes.c_int, [c_void_p, c_void_p, c_void_p, c_int64]),
+    "rse_knn_sharded_dev": (ctypes.c_int, [c_void_p, c_void_p, c_int32, c_int32, c_int32, c_void_p, c_void_p, c_void_p,
+                                           c_void_p, c_void_p]),
+    "rse_hybrid_sharded_run_dev": (ctypes.c_int, [c_void_p, c_int32, c_double, c_int32, c_int32, c_int32, c_double,
+                                                  c_double, c_void_p, c_int32, c_void_p, c_void_p, c_void_p, c_void_p,
+                                                  c_void_p, c_void_p]),
     "rse_get_stats": (ctypes.c_int, [c_void_p, POINTER(RseStats)]),
     "rse_stats_reset": (ctypes.c_int, [c_void_p]),
     "rse_set_timing": (ctypes.c_int, [c_void_p, c_int32]),
@@ -450,6 +461,56 @@ class Index:
         self._check(self._L.rse_hybrid_drain(self._h, ctypes.byref(n)))
         self._tickets.clear()
         return int(n.value)
+
+    # ------------------------------------------------------------------ multi-GPU (library-owned NCCL communicator)
+    @staticmethod
+    def comm_unique_id() -> bytes:
+        """128-byte NCCL id; rank 0 creates it and hands it to the other ranks (any transport)."""
+        L = load_library()
+        buf = ctypes.create_string_buffer(128)
+        rc = L.rse_comm_unique_id(buf)
+        if rc != RSE_OK:
+            msg = L.rse_last_error(None)
+            raise RseError(rc, msg.decode() if msg else "rse_comm_unique_id failed")
+        return bytes(buf.raw)
+
+    def comm_init(self, id_bytes: bytes, n_ranks: int, rank: int):
+        if len(id_bytes) != 128:
+            raise ValueError("the NCCL unique id is 128 bytes")
+        buf = ctypes.create_string_buffer(id_bytes, 128)
+        self._check(self._L.rse_comm_init(self._h, buf, int(n_ranks), int(rank)))
+        self.comm_ranks, self.comm_rank = int(n_ranks), int(rank)
+
+    def comm_destroy(self):
+        self._check(self._L.rse_comm_destroy(self._h))
+
+    def comm_info(self):
+        n, r, v = c_int32(0), c_int32(0), c_int32(0)
+        self._check(self._L.rse_comm_info(self._h, ctypes.byref(n), ctypes.byref(r), ctypes.byref(v)))
+        return int(n.value), int(r.value), int(v.value)
+
+    def comm_exchange_candidates_dev(self, cand_ptr: int, nq: int, kprime: int, mine_ptr: int):
+        self._check(self._L.rse_comm_exchange_candidates_dev(self._h, c_void_p(cand_ptr), int(nq), int(kprime),
+                                                             c_void_p(mine_ptr)))
+
+    def comm_allgather_dev(self, send_ptr: int, recv_ptr: int, bytes_per_rank: int):
+        self._check(self._L.rse_comm_allgather_dev(self._h, c_void_p(send_ptr), c_void_p(recv_ptr), int(bytes_per_rank)))
+
+    def knn_sharded_dev(self, q_all_ptr: int, nq_all: int, k: int, kprime: int, dist_ptr: int, rowid_ptr: int,
+                        movie_ptr: int, count_ptr: int, flagged_ptr: int = 0):
+        self._check(self._L.rse_knn_sharded_dev(self._h, c_void_p(q_all_ptr), int(nq_all), int(k), int(kprime),
+                                                c_void_p(dist_ptr), c_void_p(rowid_ptr), c_void_p(movie_ptr),
+                                                c_void_p(count_ptr), c_void_p(flagged_ptr or 0)))
+
+    def hybrid_sharded_run_dev(self, mode: int, param: float, limit: int, q_all_ptr: int, nq_all: int, out_id_ptr: int,
+                               out_score_ptr: int, out_a_ptr: int, out_b_ptr: int, out_count_ptr: int,
+                               flagged_ptr: int = 0, knn_multiplier: int = 10, k1: float = 1.5, b: float = 0.75,
+                               tie_mode: int = TIE_REFERENCE):
+        self._check(self._L.rse_hybrid_sharded_run_dev(self._h, int(mode), float(param), int(tie_mode), int(limit),
+                                                       int(knn_multiplier), float(k1), float(b), c_void_p(q_all_ptr),
+                                                       int(nq_all), c_void_p(out_id_ptr), c_void_p(out_score_ptr),
+                                                       c_void_p(out_a_ptr), c_void_p(out_b_ptr), c_void_p(out_count_ptr),
+                                                       c_void_p(flagged_ptr or 0)))
 
     def hybrid_run_merged_dev(self, mode: int, param: float, limit: int, gathered_ptr: int, n_lists: int,
                               out_id_ptr: int, out_score_ptr: int, out_a_ptr: int, out_b_ptr: int, out_count_ptr: int,

@@ -13,6 +13,7 @@
 #include <vector>
 
 #include "bm25.cuh"
+#include "comm.h"
 #include "common.cuh"
 #include "fusion.cuh"
 #include "knn_scan.cuh"
@@ -162,6 +163,11 @@ struct rse_index {
 
   // cudaFuncSetAttribute is per device: remember per HANDLE which kernels were configured (a process-wide static
   // flag would leave the second device of a multi-GPU process unconfigured)
+  // ---- row-sharded multi-GPU path: the handle owns the communicator (comm.h)
+  ncclComm_t comm = nullptr;
+  int comm_ranks = 1, comm_rank = 0;
+  DevBuf sh_cand, sh_mine;
+
   uint32_t attr_mask = 0;
   rse_stats stats{};
   // device-side counters read back by rse_get_stats: [0] BM25 queries handed to the general kernel, [1] BM25
@@ -858,6 +864,8 @@ void rse_destroy(rse_index* h) {
   free_ptr(h->doc_ids);
   free_ptr(h->movie_ids);
   free_ptr(h->dev_counters);
+  if (h->comm) { if (NcclApi* n = nccl_api()) n->CommDestroy(h->comm); h->comm = nullptr; }
+  free_buf(h->sh_cand); free_buf(h->sh_mine);
   for (auto& ev : h->ev) if (ev) cudaEventDestroy(ev);
   for (auto& ev : h->scan_ev) cudaEventDestroy(ev);
   if (h->own_stream) cudaStreamDestroy(h->own_stream);
@@ -1840,6 +1848,209 @@ int rse_hybrid_collect(rse_index* h, int64_t ticket, int32_t* out_nq, int32_t* o
   std::memcpy(out_count, sl.pin + 32 * n, 4 * static_cast<size_t>(sl.nq));
   ++h->next_collect;
   return RSE_OK;
+}
+
+// ------------------------------------------------------------------ multi-GPU (library-owned NCCL communicator)
+#define NCK(call)                                                                                     \
+  do {                                                                                                \
+    ncclResult_t r__ = (call);                                                                        \
+    if (r__ != ncclSuccess)                                                                           \
+      return fail(h, RSE_ERR_CUDA, std::string(#call) + ": " + nccl_api()->GetErrorString(r__));      \
+  } while (0)
+
+int rse_comm_unique_id(uint8_t* out_id) {
+  rse_index* h = nullptr;
+  if (!out_id) return fail(h, RSE_ERR_INVALID, "rse_comm_unique_id: out_id is NULL");
+  NcclApi* n = nccl_api();
+  if (!n) return fail(h, RSE_ERR_UNSUPPORTED, "NCCL unavailable (set RSE_NCCL_LIB to libnccl.so.2)");
+  ncclUniqueId id;
+  NCK(n->GetUniqueId(&id));
+  static_assert(sizeof(id) == RSE_COMM_ID_BYTES, "ncclUniqueId size");
+  std::memcpy(out_id, &id, sizeof(id));
+  return RSE_OK;
+}
+
+int rse_comm_init(rse_index* h, const uint8_t* id_bytes, int32_t n_ranks, int32_t rank) {
+  if (!h) return RSE_ERR_INVALID;
+  if (!id_bytes || n_ranks < 1 || rank < 0 || rank >= n_ranks) return fail(h, RSE_ERR_INVALID, "rse_comm_init: bad arguments");
+  NcclApi* n = nccl_api();
+  if (!n) return fail(h, RSE_ERR_UNSUPPORTED, "NCCL unavailable (set RSE_NCCL_LIB to libnccl.so.2)");
+  CK(cudaSetDevice(h->device));
+  if (h->comm) { n->CommDestroy(h->comm); h->comm = nullptr; }
+  ncclUniqueId id;
+  std::memcpy(&id, id_bytes, sizeof(id));
+  NCK(n->CommInitRank(&h->comm, n_ranks, id, rank));
+  h->comm_ranks = n_ranks; h->comm_rank = rank;
+  return RSE_OK;
+}
+
+int rse_comm_destroy(rse_index* h) {
+  if (!h) return RSE_ERR_INVALID;
+  if (h->comm) {
+    CK(cudaSetDevice(h->device));
+    CK(cudaStreamSynchronize(h->stream));
+    NCK(nccl_api()->CommDestroy(h->comm));
+    h->comm = nullptr;
+  }
+  h->comm_ranks = 1; h->comm_rank = 0;
+  return RSE_OK;
+}
+
+int rse_comm_info(rse_index* h, int32_t* n_ranks, int32_t* rank, int32_t* nccl_version) {
+  if (!h) return RSE_ERR_INVALID;
+  if (n_ranks) *n_ranks = h->comm ? h->comm_ranks : 0;
+  if (rank) *rank = h->comm ? h->comm_rank : 0;
+  if (nccl_version) {
+    *nccl_version = 0;
+    if (NcclApi* n = nccl_api()) { int v = 0; if (n->GetVersion(&v) == ncclSuccess) *nccl_version = v; }
+  }
+  return RSE_OK;
+}
+
+namespace {
+
+// all-to-all by query slice: rank r receives, from every shard, the candidates of ITS queries.
+// cand [nq, kprime, 3] (this shard, all queries) -> mine [n_ranks, ns, kprime, 3]
+int comm_exchange(rse_index* h, const long long* cand, int nq, int kprime, long long* mine) {
+  if (!h->comm) return fail(h, RSE_ERR_STATE, "no communicator: call rse_comm_init first");
+  NcclApi* n = nccl_api();
+  const int R = h->comm_ranks, me = h->comm_rank;
+  const size_t per = static_cast<size_t>(kprime) * 3;
+  const int ns = query_slice(nq, R, me + 1) - query_slice(nq, R, me);
+  NCK(n->GroupStart());
+  for (int r = 0; r < R; ++r) {
+    const int lo = query_slice(nq, R, r), hi = query_slice(nq, R, r + 1);
+    if (hi > lo) NCK(n->Send(cand + static_cast<size_t>(lo) * per, static_cast<size_t>(hi - lo) * per, ncclInt64, r, h->comm, h->stream));
+    if (ns > 0) NCK(n->Recv(mine + static_cast<size_t>(r) * ns * per, static_cast<size_t>(ns) * per, ncclInt64, r, h->comm, h->stream));
+  }
+  NCK(n->GroupEnd());
+  return RSE_OK;
+}
+
+}  // namespace
+
+int rse_comm_exchange_candidates_dev(rse_index* h, const int64_t* cand_dev, int32_t nq, int32_t kprime, int64_t* mine_dev) {
+  if (!h) return RSE_ERR_INVALID;
+  if (!cand_dev || !mine_dev || nq < 1 || kprime < 1) return fail(h, RSE_ERR_INVALID, "rse_comm_exchange_candidates_dev: bad arguments");
+  CK(cudaSetDevice(h->device));
+  return comm_exchange(h, reinterpret_cast<const long long*>(cand_dev), nq, kprime, reinterpret_cast<long long*>(mine_dev));
+}
+
+int rse_comm_allgather_dev(rse_index* h, const void* send_dev, void* recv_dev, int64_t bytes_per_rank) {
+  if (!h) return RSE_ERR_INVALID;
+  if (!send_dev || !recv_dev || bytes_per_rank < 0) return fail(h, RSE_ERR_INVALID, "rse_comm_allgather_dev: bad arguments");
+  if (!h->comm) return fail(h, RSE_ERR_STATE, "no communicator: call rse_comm_init first");
+  CK(cudaSetDevice(h->device));
+  NCK(nccl_api()->AllGather(send_dev, recv_dev, static_cast<size_t>(bytes_per_rank), ncclUint8, h->comm, h->stream));
+  return RSE_OK;
+}
+
+namespace {
+
+// local top-K' of ALL queries on this shard (+ deferred flag count or blocking exact fallback) + exchange:
+// leaves [n_ranks, ns, kprime, 3] in h->sh_mine.  Optionally starts the slice's BM25 underneath the filter pass.
+int sharded_knn_exchange(rse_index* h, const float* q_all_dev, int nq_all, int kprime, int32_t* flagged_dev, bool with_bm25,
+                         int limit, double k1, double b, bool* bm25_overlapped) {
+  if (!h->comm) return fail(h, RSE_ERR_STATE, "no communicator: call rse_comm_init first");
+  const int R = h->comm_ranks, me = h->comm_rank;
+  const int ns = query_slice(nq_all, R, me + 1) - query_slice(nq_all, R, me);
+  const size_t per = static_cast<size_t>(kprime) * 3;
+  ENSURE(h->sh_cand, sizeof(long long) * static_cast<size_t>(nq_all) * per);
+  ENSURE(h->sh_mine, sizeof(long long) * static_cast<size_t>(R) * std::max(ns, 1) * per);
+  *bm25_overlapped = false;
+  if (with_bm25 && ns > 0) {
+    h->bm25_overlap_pending = h->overlap_enabled;
+    h->ov_nq = ns; h->ov_limit = limit; h->ov_k1 = k1; h->ov_b = b;
+  }
+  int rc = knn_local_begin(h, q_all_dev, nq_all, kprime, static_cast<long long*>(h->sh_cand.p));
+  if (rc != RSE_OK) { h->bm25_overlap_pending = false; return rc; }
+  if (with_bm25 && ns > 0) {
+    *bm25_overlapped = h->overlap_enabled && !h->bm25_overlap_pending;     // the filter launch consumed the request
+    h->bm25_overlap_pending = false;
+    if (!*bm25_overlapped) {
+      rc = bm25_run(h, ns, limit, k1, b);
+      if (rc != RSE_OK) return rc;
+    }
+  }
+  if (h->knn_pending && flagged_dev) {                       // no host round trip: count the unfinished queries
+    h->knn_pending = false;
+    knn_flag_count_kernel<<<1, 256, 0, h->stream>>>(static_cast<const int*>(h->tc_status.p), nq_all, flagged_dev);
+    LAUNCHED(h);
+  } else {
+    rc = knn_local_finish(h);                                // blocking, exact (flagged queries -> exact scan)
+    if (rc != RSE_OK) return rc;
+  }
+  return comm_exchange(h, static_cast<const long long*>(h->sh_cand.p), nq_all, kprime, static_cast<long long*>(h->sh_mine.p));
+}
+
+}  // namespace
+
+int rse_knn_sharded_dev(rse_index* h, const float* q_all_dev, int32_t nq_all, int32_t k, int32_t kprime, float* out_dist_dev,
+                        int64_t* out_chunk_rowid_dev, int32_t* out_movie_idx_dev, int32_t* out_count_dev,
+                        int32_t* flagged_dev) {
+  if (!h) return RSE_ERR_INVALID;
+  if (!q_all_dev || nq_all < 1 || k < 1 || kprime < 1) return fail(h, RSE_ERR_INVALID, "rse_knn_sharded_dev: bad arguments");
+  if (!h->emb || !h->movie_idx) return fail(h, RSE_ERR_STATE, "rse_knn_sharded_dev: needs embeddings with movie_idx");
+  CK(cudaSetDevice(h->device));
+  bool ov = false;
+  int rc = sharded_knn_exchange(h, q_all_dev, nq_all, kprime, flagged_dev, false, 0, 0.0, 0.0, &ov);
+  if (rc != RSE_OK) return rc;
+  const int ns = query_slice(nq_all, h->comm_ranks, h->comm_rank + 1) - query_slice(nq_all, h->comm_ranks, h->comm_rank);
+  if (ns == 0) return RSE_OK;
+  if (!out_dist_dev || !out_chunk_rowid_dev || !out_movie_idx_dev || !out_count_dev)
+    return fail(h, RSE_ERR_INVALID, "rse_knn_sharded_dev: output buffers are NULL");
+  return rse_knn_merge_movies_dev(h, static_cast<const int64_t*>(h->sh_mine.p), h->comm_ranks, ns, k, kprime, out_dist_dev,
+                                  out_chunk_rowid_dev, out_movie_idx_dev, out_count_dev);
+}
+
+int rse_hybrid_sharded_run_dev(rse_index* h, int32_t mode, double param, int32_t tie_mode, int32_t limit,
+                               int32_t knn_multiplier, double k1, double b, const float* q_all_dev, int32_t nq_all,
+                               int64_t* out_id_dev, double* out_score_dev, double* out_a_dev, double* out_b_dev,
+                               int32_t* out_count_dev, int32_t* flagged_dev) {
+  if (!h) return RSE_ERR_INVALID;
+  if (!q_all_dev || nq_all < 1) return fail(h, RSE_ERR_INVALID, "rse_hybrid_sharded_run_dev: bad arguments");
+  if (!h->comm) return fail(h, RSE_ERR_STATE, "no communicator: call rse_comm_init first");
+  if (mode != 0 && mode != 1) return fail(h, RSE_ERR_INVALID, "rse_hybrid: mode must be 0 (rrf) or 1 (weighted)");
+  if (limit < 1 || limit > RSE_MAX_FUSE_LIMIT) return fail(h, RSE_ERR_UNSUPPORTED, "rse_hybrid: limit must be in [1, 128]");
+  if (knn_multiplier < 0) return fail(h, RSE_ERR_INVALID, "rse_hybrid: knn_multiplier < 0");
+  if (!h->emb || !h->movie_idx || !h->indptr || !h->doc_ids || !h->movie_ids)
+    return fail(h, RSE_ERR_STATE, "rse_hybrid: needs embeddings (with movie_idx), a BM25 index and id tables");
+  const int R = h->comm_ranks, me = h->comm_rank;
+  const int ns = query_slice(nq_all, R, me + 1) - query_slice(nq_all, R, me);
+  if (h->staged_nq != ns)
+    return fail(h, RSE_ERR_STATE, "rse_hybrid_sharded_run_dev: the staged batch must be this rank's query slice (tokens)");
+  const int kprime = std::max(limit * knn_multiplier, limit);
+  if (kprime > RSE_MAX_KPRIME) return fail(h, RSE_ERR_UNSUPPORTED, "rse_hybrid: limit*knn_multiplier exceeds 4096");
+  CK(cudaSetDevice(h->device));
+  bool overlapped = false;
+  int rc = sharded_knn_exchange(h, q_all_dev, nq_all, kprime, flagged_dev, true, limit, k1, b, &overlapped);
+  if (rc != RSE_OK) return rc;
+  if (ns == 0) return RSE_OK;
+  if (!out_id_dev || !out_score_dev || !out_a_dev || !out_b_dev || !out_count_dev)
+    return fail(h, RSE_ERR_INVALID, "rse_hybrid_sharded_run_dev: output buffers are NULL");
+  const int n2 = next_pow2(R * kprime);
+  const size_t smem = static_cast<size_t>(n2) * 12;
+  if (smem > 200 * 1024) return fail(h, RSE_ERR_UNSUPPORTED, "rse_hybrid_sharded_run_dev: n_ranks*kprime too large for the merge kernel");
+  if (smem > 48 * 1024) CK(cudaFuncSetAttribute(knn_merge_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+  const size_t n = static_cast<size_t>(ns) * limit;
+  ENSURE(h->cand, sizeof(long long) * static_cast<size_t>(ns) * kprime * 3);
+  ENSURE(h->o_dist, sizeof(float) * n);
+  ENSURE(h->o_rowid, sizeof(long long) * n);
+  ENSURE(h->o_movie, sizeof(int) * n);
+  ENSURE(h->o_count, sizeof(int) * ns);
+  knn_merge_kernel<<<ns, kSelThreads, smem, h->stream>>>(static_cast<const long long*>(h->sh_mine.p), R, ns, kprime, n2,
+                                                         static_cast<long long*>(h->cand.p));
+  LAUNCHED(h);
+  rc = aggregate(h, static_cast<const long long*>(h->cand.p), ns, limit, kprime, static_cast<float*>(h->o_dist.p),
+                 static_cast<long long*>(h->o_rowid.p), static_cast<int*>(h->o_movie.p), static_cast<int*>(h->o_count.p));
+  if (rc != RSE_OK) return rc;
+  if (overlapped) CK(cudaStreamWaitEvent(h->stream, h->ev_bm25_done, 0));
+  FuseIn in{nullptr, static_cast<const double*>(h->b_score.p), static_cast<const int*>(h->b_count.p), nullptr,
+            static_cast<const float*>(h->o_dist.p), static_cast<const int*>(h->o_count.p), nullptr};
+  in.bm25_idx = static_cast<const int*>(h->b_doc.p); in.bm25_table = h->doc_ids; in.bm25_table_n = h->n_doc_ids;
+  in.sem_idx = static_cast<const int*>(h->o_movie.p); in.sem_table = h->movie_ids; in.sem_table_n = h->n_movie_ids;
+  return fuse_launch(h, mode, param, tie_mode, ns, limit, in, reinterpret_cast<long long*>(out_id_dev), out_score_dev,
+                     out_a_dev, out_b_dev, out_count_dev);
 }
 
 int rse_hybrid_stash(rse_index* h, int32_t slot) {

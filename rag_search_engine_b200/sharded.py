@@ -243,3 +243,85 @@ class LibrseShardBackend:
                                          oid.data_ptr(), osc.data_ptr(), oa.data_ptr(), ob.data_ptr(), oc.data_ptr(),
                                          knn_multiplier=knn_multiplier, k1=self.k1, b=self.b, tie_mode=self.tie_mode)
         return oid, osc, oa, ob, oc
+
+
+class NcclShardedHybrid:
+    """The same step with the collective owned by the LIBRARY (include/rse.h "multi-GPU"): the handle holds the NCCL
+    communicator, ``rse_hybrid_sharded_run_dev`` does local top-K' -> all-to-all -> merge -> fusion in one call and
+    ``rse_comm_allgather_dev`` assembles the batch on every rank — a binder that only has the C ABI gets the same
+    multi-GPU path.  Python only distributes the 128-byte communicator id (``torch.distributed`` here; any
+    transport works).  Same result object and the same repeat-when-flagged rule as ``ShardedHybrid``."""
+
+    def __init__(self, index, q_host, tok_indptr, term_rows, device: torch.device, nq: int, k1: float = 1.5,
+                 b: float = 0.75, tie_mode: int = 0, group=None):
+        import numpy as np
+        self.index, self.device, self.nq = index, device, nq
+        self.k1, self.b, self.tie_mode = k1, b, tie_mode
+        self.world = dist.get_world_size(group) if dist.is_initialized() else 1
+        self.rank = dist.get_rank(group) if dist.is_initialized() else 0
+        self.slices = query_slices(nq, self.world)
+        self.lo, self.hi = self.slices[self.rank], self.slices[self.rank + 1]
+        self.max_slice = max(self.slices[r + 1] - self.slices[r] for r in range(self.world))
+        self.q_host = np.ascontiguousarray(q_host, np.float32)
+        self.tok_indptr = np.ascontiguousarray(tok_indptr, np.int32)
+        self.term_rows = np.ascontiguousarray(term_rows, np.int32)
+        self.flagged_steps = 0
+        index.set_stream(torch.cuda.current_stream(device).cuda_stream)
+        ids = [index.comm_unique_id() if self.rank == 0 else None]
+        if self.world > 1:
+            dist.broadcast_object_list(ids, src=0, group=group)
+        index.comm_init(ids[0], self.world, self.rank)
+        n_ranks, _rank, version = index.comm_info()
+        self.exchange_kind = f"library-owned NCCL {version}: grouped ncclSend/ncclRecv all-to-all by query slice ({n_ranks} ranks)"
+        self.stage_slice()
+
+    def stage_slice(self):
+        import numpy as np
+        if self.hi <= self.lo:
+            return
+        t0, t1 = int(self.tok_indptr[self.lo]), int(self.tok_indptr[self.hi])
+        ptr = (self.tok_indptr[self.lo:self.hi + 1] - t0).astype(np.int32)
+        self.index.hybrid_stage(self.q_host[self.lo:self.hi], ptr, self.term_rows[t0:t1])
+
+    def _buffers(self, limit: int):
+        if getattr(self, "_buf_key", None) != limit:
+            pad, dev = self.max_slice, self.device
+            self._pack = torch.zeros((5, pad + 1, limit), dtype=torch.float64, device=dev)
+            self._allp = torch.empty((self.world * 5, pad + 1, limit), dtype=torch.float64, device=dev)
+            self._cnt = torch.zeros((pad,), dtype=torch.int32, device=dev)
+            self._flag = torch.zeros((1,), dtype=torch.int32, device=dev)
+            self._buf_key = limit
+        return self._pack, self._allp, self._cnt, self._flag
+
+    def step(self, q_all: torch.Tensor, mode: int, param: float, limit: int, knn_multiplier: int = 10,
+             check: bool = True) -> HybridBatchResult:
+        res = self._step(q_all, mode, param, limit, knn_multiplier, defer=True)
+        if check and int(res.flagged.item()) > 0:
+            self.flagged_steps += 1
+            res = self._step(q_all, mode, param, limit, knn_multiplier, defer=False)
+        return res
+
+    def _step(self, q_all, mode, param, limit, knn_multiplier, defer: bool) -> HybridBatchResult:
+        pack, allp, cnt, flag = self._buffers(limit)
+        ns = self.hi - self.lo
+        flag.zero_()
+        self.index.hybrid_sharded_run_dev(mode, param, limit, q_all.data_ptr(), q_all.shape[0],
+                                          pack[0].data_ptr(), pack[1].data_ptr(), pack[2].data_ptr(), pack[3].data_ptr(),
+                                          cnt.data_ptr(), flag.data_ptr() if defer else 0,
+                                          knn_multiplier=knn_multiplier, k1=self.k1, b=self.b, tie_mode=self.tie_mode)
+        if ns > 0:
+            pack[4, :ns, 0] = cnt[:ns].to(torch.float64)
+        pack[4, self.max_slice, 0] = flag[0].to(torch.float64)
+        if self.world > 1:
+            self.index.comm_allgather_dev(pack.data_ptr(), allp.data_ptr(), pack.numel() * 8)
+        else:
+            allp.copy_(pack)
+        allv = allp.view(self.world, 5, self.max_slice + 1, limit)
+        flagged = allv[:, 4, self.max_slice, 0].sum().to(torch.int64)
+        body = allv[:, :, : self.max_slice]
+        if self.nq % self.world == 0:
+            full = body.permute(1, 0, 2, 3).reshape(5, self.nq, limit)
+        else:
+            full = torch.cat([body[r, :, : self.slices[r + 1] - self.slices[r]] for r in range(self.world)], 1)
+        return HybridBatchResult(full[0].contiguous().view(torch.int64), full[1], full[2], full[3],
+                                 full[4, :, 0].to(torch.int32), flagged)

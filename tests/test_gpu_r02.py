@@ -265,3 +265,44 @@ def test_keyword_only_database_opens_and_degrades_like_the_reference(tmp_path):
             assert all(h["sem_rank"] is None and h["bm25_rank"] == j for j, h in enumerate(res[q]))
     finally:
         hs.close()
+
+
+def test_library_owned_nccl_comm_single_rank(small_world):
+    """include/rse.h "multi-GPU": the handle owns the NCCL communicator.  With one rank the sharded entry points
+    (local top-K' -> all-to-all (self) -> merge -> aggregation / fusion) must equal the single-handle calls; the
+    N-rank form is checked against one handle by bench.py --gpus N (sharded_matches_single_gpu)."""
+    import torch
+    idx, se, bm, batches = small_world
+    Q, tp, tr = batches[1]
+    nq = Q.shape[0]
+    idx.comm_init(idx.comm_unique_id(), 1, 0)
+    try:
+        n_ranks, rank, ver = idx.comm_info()
+        assert (n_ranks, rank) == (1, 0) and ver >= 20000
+        qd = torch.as_tensor(Q, device="cuda")
+        od = torch.empty((nq, 10), dtype=torch.float32, device="cuda")
+        orow = torch.empty((nq, 10), dtype=torch.int64, device="cuda")
+        om = torch.empty((nq, 10), dtype=torch.int32, device="cuda")
+        oc = torch.empty((nq,), dtype=torch.int32, device="cuda")
+        flag = torch.zeros((1,), dtype=torch.int32, device="cuda")
+        for fl in (flag.data_ptr(), 0):
+            idx.knn_sharded_dev(qd.data_ptr(), nq, 10, 100, od.data_ptr(), orow.data_ptr(), om.data_ptr(), oc.data_ptr(), fl)
+            idx.synchronize()
+            wd, wrow, wm, wc = idx.knn_movies(Q, 10, 100)
+            assert (oc.cpu().numpy() == wc).all() and (orow.cpu().numpy() == wrow).all()
+            assert (od.cpu().numpy().view(np.uint32) == wd.view(np.uint32)).all() and (om.cpu().numpy() == wm).all()
+        assert int(flag.item()) == 0
+        want = idx.hybrid(0, 60.0, 10, Q, tp, tr)
+        idx.hybrid_stage(Q, tp, tr)
+        oid = torch.empty((nq, 10), dtype=torch.int64, device="cuda")
+        osc = torch.empty((nq, 10), dtype=torch.float64, device="cuda")
+        oa = torch.empty((nq, 10), dtype=torch.float64, device="cuda")
+        ob = torch.empty((nq, 10), dtype=torch.float64, device="cuda")
+        ocn = torch.empty((nq,), dtype=torch.int32, device="cuda")
+        idx.hybrid_sharded_run_dev(0, 60.0, 10, qd.data_ptr(), nq, oid.data_ptr(), osc.data_ptr(), oa.data_ptr(),
+                                   ob.data_ptr(), ocn.data_ptr(), flag.data_ptr())
+        idx.synchronize()
+        got = (oid.cpu().numpy(), osc.cpu().numpy(), oa.cpu().numpy(), ob.cpu().numpy(), ocn.cpu().numpy())
+        assert same(got, want)
+    finally:
+        idx.comm_destroy()
