@@ -559,6 +559,66 @@ def measure_python_api(args, idx, bm, se, Qn, tok_indptr, terms, limit, steps):
             "hits_in_last_batch": int(sum(len(x) for x in last))}
 
 
+def measure_text_in(args, idx, bm, se, tok_indptr, terms, limit, steps):
+    """§8(f2): TEXT in — the MiniLM-L6 query encoder runs on the same GPU (csrc/encoder.cuh, random weights of the
+    all-MiniLM-L6-v2 architecture: the checkpoint is not downloadable here and the arithmetic does not depend on
+    the values) and hands its vectors to the hybrid step on the device (rse_encode_dev -> rse_hybrid_stage_dev).
+    Every step uploads the token ids of ITS batch and reads its fused results back."""
+    import torch
+    from rag_search_engine_b200 import HybridSearch
+    from rag_search_engine_b200.encoder import MINILM_L6_CONFIG, GpuSentenceEncoder, pack, random_state_dict
+    enc = GpuSentenceEncoder(idx, random_state_dict(MINILM_L6_CONFIG, seed=5), MINILM_L6_CONFIG)
+    B = args.batch
+    rng = np.random.default_rng(17)
+    id_batches, tok_batches = [], []
+    for b in range(NB):
+        lens = rng.integers(4, 17, B)                       # [CLS] + 2..14 word pieces + [SEP]: short search queries
+        ids = [[101] + rng.integers(1000, 30000, L - 2).tolist() + [102] for L in lens]
+        id_batches.append(ids)
+        lo, hi = b * B, (b + 1) * B
+        tok_batches.append(((tok_indptr[lo:hi + 1] - tok_indptr[lo]).astype(np.int32), terms[tok_indptr[lo]:tok_indptr[hi]]))
+    tokens_per_batch = float(np.mean([sum(len(x) for x in ids) for ids in id_batches]))
+    dev = torch.device("cuda", idx.device)
+    qbuf = torch.empty((B, 384), dtype=torch.float32, device=dev)
+    packed = [pack(ids) for ids in id_batches]
+
+    def step(i):
+        ids, _, cu = packed[i % NB]
+        idx.encode_dev(enc.slot, ids, cu, qbuf.data_ptr())
+        tp, tr = tok_batches[i % NB]
+        idx.hybrid_stage_dev(B, qbuf.data_ptr(), tp, tr)
+        idx.hybrid_run(0, 60.0, limit)
+        return idx.hybrid_fetch(limit)
+
+    for i in range(3):
+        step(i)
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for i in range(steps):
+        step(i)
+    torch.cuda.synchronize()
+    wall = (time.perf_counter() - t0) / steps
+    # the encoder alone, device-timed
+    stream = torch.cuda.current_stream(dev)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
+    for i in range(steps):
+        ids, _, cu = packed[i % NB]
+        idx.encode_dev(enc.slot, ids, cu, qbuf.data_ptr())
+    e1.record(stream)
+    torch.cuda.synchronize()
+    enc_ms = e0.elapsed_time(e1) / steps
+    c = MINILM_L6_CONFIG
+    flop_per_token = 2.0 * c["layers"] * (4 * c["hidden"] ** 2 + 2 * c["hidden"] * c["intermediate"])
+    return {"value": B / wall, "unit": "queries/s", "wall_ms_per_step": 1e3 * wall, "queries_per_step": B,
+            "api": "rse_encode_dev (MiniLM-L6 architecture, fp32) -> rse_hybrid_stage_dev -> rse_hybrid_run -> rse_hybrid_fetch",
+            "encoder_ms_per_batch": enc_ms, "tokens_per_batch": tokens_per_batch,
+            "encoder_tokens_per_s": tokens_per_batch / (enc_ms * 1e-3),
+            "encoder_gemm_tflops": flop_per_token * tokens_per_batch / (enc_ms * 1e-3) / 1e12,
+            "weights": "random (seeded), all-MiniLM-L6-v2 architecture",
+            "reference_cpu_encoder": "5-20 ms PER QUERY (SURVEY §8 f2: torch CPU via sentence-transformers; not installable here)"}
+
+
 def measure_small_batches(idx, Qn, limit):
     """Where does the tensor-core path take over from the streaming scan?  rse_knn_movies (host buffers) for small
     batches with the exact scan forced, K4 forced, and the library's automatic choice (VERDICT r01 weak #9)."""
@@ -681,7 +741,7 @@ def run_b200(args, rank, world, local_rank):
                          "inside the device-resident loop; the kernels of the two modes differ only in fuse_kernel"}
 
     # ---- batch-1 KNN (north_star: batch-1 kNN as a fraction of HBM peak): scan<QB=1> alone + whole call
-    knn1 = knn1k = small = pyapi = None
+    knn1 = knn1k = small = pyapi = textin = None
     if world == 1 and not args.no_knn1:
         kp = max(limit * 10, limit)
         for _ in range(3):
@@ -713,6 +773,7 @@ def run_b200(args, rank, world, local_rank):
         if not args.no_extras:
             small = measure_small_batches(idx, Qn, limit)
             pyapi = measure_python_api(args, idx, bm, se, Qn, tok_indptr, terms, limit, min(args.steps, 40))
+            textin = measure_text_in(args, idx, bm, se, tok_indptr, terms, limit, min(args.steps, 20))
 
     replicas_ok = mismatch = corpora_identical = rowshard_extra = None
     if world > 1:
@@ -843,7 +904,7 @@ def run_b200(args, rank, world, local_rank):
             "bm25": {"queries": int(st.bm25_queries), "fallback_queries": int(st.bm25_fallback_queries),
                      "finalists_rescored": int(st.bm25_finalists), "candidates_merged": int(st.bm25_candidates)},
             "bytes_moved_resident_loop": {"h2d": int(st.h2d_bytes), "d2h": int(st.d2h_bytes)},
-            ("weighted" if mode == 0 else "rrf"): other, "clustered": clustered or None, "e2e_python": pyapi,
+            ("weighted" if mode == 0 else "rrf"): other, "clustered": clustered or None, "e2e_python": pyapi, "text_in": textin,
             "knn_small_batches": small, "knn100m": knn100m,
             "replicas_match_single_gpu": replicas_ok, "mismatch": mismatch,
             "corpora_identical_across_ranks": corpora_identical,

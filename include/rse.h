@@ -250,6 +250,38 @@ int rse_hybrid_collect(rse_index *h, int64_t ticket, int32_t *out_nq, int32_t *o
  * submit and its collect): afterwards the handle accepts submits again.  out_dropped (optional) = how many. */
 int rse_hybrid_drain(rse_index *h, int32_t *out_dropped);
 
+/* ------------------------------------------------------------------ §8(f2)/(f3): the text encoders on the device
+ * The reference encodes every query text with SentenceTransformer("all-MiniLM-L6-v2") on the CPU
+ * (utils/semantic_search.py:45, :211-222: model.encode -> float32[1, 384]) and reranks the fused hits with
+ * CrossEncoder("cross-encoder/ms-marco-TinyBERT-L2-v2").predict(pairs) (utils/hybrid_search.py:279-312).  Both are
+ * HuggingFace BertModels; here one implementation runs either next to the index (csrc/encoder.cuh):
+ *   head 0 : BertModel -> mean pooling over the tokens -> L2 normalise  (the sentence-transformers pipeline);
+ *            output [n_seq, hidden]
+ *   head 1 : BertModel -> pooler (tanh(dense([CLS]))) -> classifier (num_labels = 1); output [n_seq] logits
+ * Weights are handed over tensor by tensor under their HuggingFace state_dict names (any prefix such as "bert." or
+ * "0.auto_model." is ignored); tokenisation stays on the host (out of scope): the caller passes the
+ * token ids of the batch PACKED — ids[T] (+ optional token_type_ids[T], NULL = all 0) and cu_seqlens[n_seq + 1]
+ * (sequence s owns tokens cu[s] .. cu[s+1]; what attention_mask == 1 selects).  fp32 throughout.
+ * rse_encode_dev leaves the result on the device (out_dev on the handle's device, asynchronous on its stream), so
+ * rse_hybrid_stage_dev can take the query vectors from there: text in, no host hop for the vectors. */
+#define RSE_MAX_ENCODERS 2
+typedef struct rse_encoder_config {
+  int32_t vocab_size, hidden, layers, heads, intermediate, max_positions, type_vocab;
+  float ln_eps;
+  int32_t head; /* 0 = mean pool + L2 normalise, 1 = BERT pooler + 1-logit classifier */
+} rse_encoder_config;
+int rse_encoder_create(rse_index *h, int32_t slot, const rse_encoder_config *cfg);
+int rse_encoder_set_tensor(rse_index *h, int32_t slot, const char *name, const float *data, int64_t n_elem);
+int rse_encoder_finalize(rse_index *h, int32_t slot);
+int rse_encode(rse_index *h, int32_t slot, const int32_t *ids, const int32_t *type_ids, const int32_t *cu_seqlens,
+               int32_t n_seq, float *out_host);
+int rse_encode_dev(rse_index *h, int32_t slot, const int32_t *ids, const int32_t *type_ids,
+                   const int32_t *cu_seqlens, int32_t n_seq, float *out_dev);
+/* rse_hybrid_stage with the query vectors already ON THE DEVICE ([nq, dim] fp32, e.g. rse_encode_dev's output);
+ * tokens still come from the host.  Followed by rse_hybrid_run / rse_hybrid_fetch as usual. */
+int rse_hybrid_stage_dev(rse_index *h, int32_t nq, const float *q_dev, const int32_t *tok_indptr,
+                         const int32_t *term_rows);
+
 /* ------------------------------------------------------------------ multi-GPU: row shards over one box
  * One process per GPU, one handle per process; the HANDLE owns the NCCL communicator (NCCL is bound at run time:
  * libnccl.so.2, or $RSE_NCCL_LIB).  The chunk-embedding matrix is cut by row into contiguous shards aligned to

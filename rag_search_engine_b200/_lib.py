@@ -56,6 +56,13 @@ class RseStats(ctypes.Structure):
     ]
 
 
+class RseEncoderConfig(ctypes.Structure):
+    """include/rse.h rse_encoder_config."""
+    _fields_ = [("vocab_size", c_int32), ("hidden", c_int32), ("layers", c_int32), ("heads", c_int32),
+                ("intermediate", c_int32), ("max_positions", c_int32), ("type_vocab", c_int32),
+                ("ln_eps", c_float), ("head", c_int32)]
+
+
 _SIGNATURES = {
     "rse_abi_version": (ctypes.c_int, []),
     "rse_create": (ctypes.c_int, [c_int32, POINTER(c_void_p)]),
@@ -110,6 +117,14 @@ _SIGNATURES = {
     "rse_hybrid_drain": (ctypes.c_int, [c_void_p, POINTER(c_int32)]),
     "rse_hybrid_stash": (ctypes.c_int, [c_void_p, c_int32]),
     "rse_tc_last_survivors": (ctypes.c_int, [c_void_p, POINTER(c_int32), c_int32]),
+    "rse_encoder_create": (ctypes.c_int, [c_void_p, c_int32, POINTER(RseEncoderConfig)]),
+    "rse_encoder_set_tensor": (ctypes.c_int, [c_void_p, c_int32, c_char_p, POINTER(c_float), c_int64]),
+    "rse_encoder_finalize": (ctypes.c_int, [c_void_p, c_int32]),
+    "rse_encode": (ctypes.c_int, [c_void_p, c_int32, POINTER(c_int32), POINTER(c_int32), POINTER(c_int32), c_int32,
+                                  POINTER(c_float)]),
+    "rse_encode_dev": (ctypes.c_int, [c_void_p, c_int32, POINTER(c_int32), POINTER(c_int32), POINTER(c_int32), c_int32,
+                                      c_void_p]),
+    "rse_hybrid_stage_dev": (ctypes.c_int, [c_void_p, c_int32, c_void_p, c_void_p, c_void_p]),
     "rse_comm_unique_id": (ctypes.c_int, [c_void_p]),
     "rse_comm_init": (ctypes.c_int, [c_void_p, c_void_p, c_int32, c_int32]),
     "rse_comm_destroy": (ctypes.c_int, [c_void_p]),
@@ -461,6 +476,57 @@ class Index:
         self._check(self._L.rse_hybrid_drain(self._h, ctypes.byref(n)))
         self._tickets.clear()
         return int(n.value)
+
+    # ------------------------------------------------------------------ text encoders (§8 f2 / f3)
+    def encoder_create(self, slot: int, *, vocab_size: int, hidden: int, layers: int, heads: int, intermediate: int,
+                       max_positions: int, type_vocab: int, ln_eps: float, head: int):
+        cfg = RseEncoderConfig(int(vocab_size), int(hidden), int(layers), int(heads), int(intermediate),
+                               int(max_positions), int(type_vocab), float(ln_eps), int(head))
+        self._check(self._L.rse_encoder_create(self._h, int(slot), ctypes.byref(cfg)))
+        self.__dict__.setdefault("_enc_cfg", {})[int(slot)] = cfg
+
+    def encoder_set_tensor(self, slot: int, name: str, data):
+        a = _c(data, np.float32).reshape(-1)
+        self._check(self._L.rse_encoder_set_tensor(self._h, int(slot), name.encode(), _ptr(a, c_float), a.size))
+
+    def encoder_finalize(self, slot: int):
+        self._check(self._L.rse_encoder_finalize(self._h, int(slot)))
+
+    def _enc_inputs(self, ids, type_ids, cu_seqlens):
+        ids = _c(ids, np.int32).reshape(-1)
+        cu = _c(cu_seqlens, np.int32).reshape(-1)
+        tt = None if type_ids is None else _c(type_ids, np.int32).reshape(-1)
+        if cu[-1] != ids.size or (tt is not None and tt.size != ids.size):
+            raise ValueError("cu_seqlens[-1] must equal the number of token ids (and of token type ids)")
+        return ids, tt, cu
+
+    def encode(self, slot: int, ids, cu_seqlens, type_ids=None):
+        """Packed token ids -> [n_seq, hidden] float32 (head 0) or [n_seq] logits (head 1), on the host."""
+        ids, tt, cu = self._enc_inputs(ids, type_ids, cu_seqlens)
+        cfg = self._enc_cfg[int(slot)]
+        n_seq = cu.size - 1
+        out = np.zeros((n_seq, cfg.hidden) if cfg.head == 0 else (n_seq,), np.float32)
+        self._check(self._L.rse_encode(self._h, int(slot), _ptr(ids, c_int32), _ptr(tt, c_int32), _ptr(cu, c_int32),
+                                       n_seq, _ptr(out, c_float)))
+        return out
+
+    def encode_dev(self, slot: int, ids, cu_seqlens, out_ptr: int, type_ids=None):
+        """Same, result left on the device at ``out_ptr`` (asynchronous on the handle's stream)."""
+        ids, tt, cu = self._enc_inputs(ids, type_ids, cu_seqlens)
+        self._check(self._L.rse_encode_dev(self._h, int(slot), _ptr(ids, c_int32), _ptr(tt, c_int32), _ptr(cu, c_int32),
+                                           cu.size - 1, c_void_p(out_ptr)))
+
+    def hybrid_stage_dev(self, nq: int, q_ptr: int, tok_indptr, term_rows):
+        """rse_hybrid_stage with the query vectors already on the device (e.g. encode_dev's output)."""
+        tok_indptr = _c(tok_indptr, np.int32)
+        term_rows = _c(term_rows, np.int32)
+        if term_rows.size == 0:
+            term_rows = np.zeros(1, np.int32)
+        if len(tok_indptr) != nq + 1:
+            raise ValueError("tok_indptr must have nq+1 entries")
+        self._check(self._L.rse_hybrid_stage_dev(self._h, int(nq), c_void_p(q_ptr), c_void_p(tok_indptr.ctypes.data),
+                                                 c_void_p(term_rows.ctypes.data)))
+        self._staged_nq = int(nq)
 
     # ------------------------------------------------------------------ multi-GPU (library-owned NCCL communicator)
     @staticmethod

@@ -1,0 +1,333 @@
+// encoder.cuh — §8(f2)/(f3): the BERT-family text encoders of the reference on the same GPU as the index.
+//
+//   head 0: SentenceTransformer("all-MiniLM-L6-v2") — the QUERY ENCODER of the semantic path
+//           (rag_search_engine/utils/semantic_search.py:45, :211-222): BertModel (6 layers, hidden 384, 12 heads,
+//           intermediate 1536) -> mean pooling over the attention mask -> L2 normalise;
+//   head 1: CrossEncoder("cross-encoder/ms-marco-TinyBERT-L2-v2") — the rerank step right after fusion
+//           (rag_search_engine/utils/hybrid_search.py:279-312): BertModel (2 layers, hidden 128, 2 heads,
+//           intermediate 512) -> BERT pooler (tanh(dense([CLS]))) -> linear classifier -> one logit per pair.
+//
+// Both are the same graph with different sizes, so there is ONE implementation, driven by a config.  The model is
+// the HuggingFace BertModel: embeddings (word + position + token type) -> LayerNorm; per layer: fused QKV
+// projection, scaled-dot-product attention with a key padding mask, output projection + residual + LayerNorm,
+// GELU(erf) feed-forward + residual + LayerNorm.
+//
+// Numerics.  The bar for this row is the fp32 PyTorch model to <= 1e-5 relative on the pooled vector, so every
+// matrix product accumulates in fp32 with fused multiply-adds (fmaf, explicit: the library is built with
+// --fmad=false), softmax / LayerNorm / GELU are fp32 with expf / erff / rsqrtf-free sqrt, and nothing is stored
+// in reduced precision.  A TF32 tensor-core GEMM would be ~1e-3 off and fail that bar; the tcgen05 route to fp32
+// accuracy is a 3-pass split (hi*hi + lo*hi + hi*lo), see DESIGN.md §10.
+//
+// Layout: PACKED tokens — the sequences of a batch are concatenated, [T, hidden] row-major, with cu_seqlens
+// [n_seq + 1] (queries are 3-20 tokens: padding to the longest would waste half the GEMM rows); position ids are
+// the index inside the sequence; attention and pooling work per sequence from cu_seqlens.
+#pragma once
+#include <cuda_runtime.h>
+
+#include <cstdint>
+
+namespace rse {
+
+constexpr int kEncMaxHidden = 1024;
+
+// ---------------------------------------------------------------- embeddings + LayerNorm / residual + LayerNorm
+// one warp per token; two-pass mean / variance in registers (torch.nn.LayerNorm: biased variance, eps inside sqrt)
+template <int MAX_PER_LANE>
+__device__ __forceinline__ void warp_layernorm(float (&v)[MAX_PER_LANE], int per_lane, int hidden, float eps,
+                                               const float* __restrict__ gamma, const float* __restrict__ beta,
+                                               float* __restrict__ out_row, int lane) {
+  float s = 0.0f;
+#pragma unroll
+  for (int i = 0; i < MAX_PER_LANE; ++i) if (i < per_lane) s += v[i];
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xFFFFFFFFu, s, o);
+  const float mean = s / static_cast<float>(hidden);
+  float q = 0.0f;
+#pragma unroll
+  for (int i = 0; i < MAX_PER_LANE; ++i) if (i < per_lane) { const float d = v[i] - mean; q = fmaf(d, d, q); }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) q += __shfl_xor_sync(0xFFFFFFFFu, q, o);
+  const float rstd = 1.0f / sqrtf(q / static_cast<float>(hidden) + eps);
+#pragma unroll
+  for (int i = 0; i < MAX_PER_LANE; ++i)
+    if (i < per_lane) {
+      const int c = i * 32 + lane;
+      out_row[c] = fmaf((v[i] - mean) * rstd, gamma[c], beta[c]);
+    }
+}
+
+__global__ void __launch_bounds__(128)
+enc_embed_ln_kernel(const int32_t* __restrict__ ids, const int32_t* __restrict__ type_ids,
+                    const int32_t* __restrict__ pos_of_token, int n_tokens, int hidden, int vocab, int max_pos,
+                    int type_vocab, const float* __restrict__ word, const float* __restrict__ pos,
+                    const float* __restrict__ type, const float* __restrict__ gamma, const float* __restrict__ beta,
+                    float eps, float* __restrict__ out) {
+  const int lane = threadIdx.x & 31;
+  const int t = blockIdx.x * 4 + (threadIdx.x >> 5);
+  if (t >= n_tokens) return;
+  int id = ids[t]; id = id < 0 ? 0 : (id >= vocab ? vocab - 1 : id);
+  int p = pos_of_token[t]; p = p >= max_pos ? max_pos - 1 : p;
+  int tt = type_ids ? type_ids[t] : 0; tt = tt < 0 ? 0 : (tt >= type_vocab ? type_vocab - 1 : tt);
+  const int per_lane = hidden / 32;
+  float v[kEncMaxHidden / 32];
+#pragma unroll
+  for (int i = 0; i < kEncMaxHidden / 32; ++i)
+    if (i < per_lane) {
+      const int c = i * 32 + lane;
+      // BertEmbeddings.forward: (inputs_embeds + token_type_embeddings) + position_embeddings
+      v[i] = (word[static_cast<int64_t>(id) * hidden + c] + type[static_cast<int64_t>(tt) * hidden + c]) +
+             pos[static_cast<int64_t>(p) * hidden + c];
+    }
+  warp_layernorm(v, per_lane, hidden, eps, gamma, beta, out + static_cast<int64_t>(t) * hidden, lane);
+}
+
+// out = LayerNorm(x + residual)
+__global__ void __launch_bounds__(128)
+enc_add_ln_kernel(const float* __restrict__ x, const float* __restrict__ residual, int n_tokens, int hidden,
+                  const float* __restrict__ gamma, const float* __restrict__ beta, float eps, float* __restrict__ out) {
+  const int lane = threadIdx.x & 31;
+  const int t = blockIdx.x * 4 + (threadIdx.x >> 5);
+  if (t >= n_tokens) return;
+  const int per_lane = hidden / 32;
+  float v[kEncMaxHidden / 32];
+#pragma unroll
+  for (int i = 0; i < kEncMaxHidden / 32; ++i)
+    if (i < per_lane) {
+      const int64_t o = static_cast<int64_t>(t) * hidden + i * 32 + lane;
+      v[i] = x[o] + residual[o];
+    }
+  warp_layernorm(v, per_lane, hidden, eps, gamma, beta, out + static_cast<int64_t>(t) * hidden, lane);
+}
+
+// ---------------------------------------------------------------- GEMM: C[M, N] = A[M, K] . W[N, K]^T + bias
+// (torch.nn.Linear layout: both operands K-contiguous.)  fp32 SIMT, fmaf accumulation: 128 x 128 x 16 tiles, 256
+// threads, 8 x 8 outputs per thread as two 4-wide groups in each dimension (conflict-free float4 reads of the
+// k-major shared tiles), register-prefetched double buffering.  K % 16 == 0.  EPI: 0 = bias, 1 = bias + GELU(erf).
+constexpr int kGemmBM = 128, kGemmBN = 128, kGemmBK = 16, kGemmPad = 4;
+
+__device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752440f)); }
+
+template <int EPI>
+__global__ void __launch_bounds__(256, 2)
+enc_gemm_kernel(const float* __restrict__ A, const float* __restrict__ W, const float* __restrict__ bias,
+                float* __restrict__ C, int M, int N, int K) {
+  __shared__ __align__(16) float As[2][kGemmBK][kGemmBM + kGemmPad];
+  __shared__ __align__(16) float Ws[2][kGemmBK][kGemmBN + kGemmPad];
+  const int tid = threadIdx.x;
+  const int m0 = blockIdx.y * kGemmBM, n0 = blockIdx.x * kGemmBN;
+  const int ty = tid >> 4, tx = tid & 15;                 // 16 x 16 threads
+  // global -> register staging: 2 float4 of A and 2 of W per thread per k-block (row = idx / 4, k-quad = idx % 4)
+  float4 ra[2], rw[2];
+  auto load_tiles = [&](int k0) {
+#pragma unroll
+    for (int j = 0; j < 2; ++j) {
+      const int idx = tid + 256 * j, row = idx >> 2, kq = idx & 3;
+      const int gm = m0 + row, gn = n0 + row;
+      ra[j] = gm < M ? *reinterpret_cast<const float4*>(A + static_cast<int64_t>(gm) * K + k0 + kq * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
+      rw[j] = gn < N ? *reinterpret_cast<const float4*>(W + static_cast<int64_t>(gn) * K + k0 + kq * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+  };
+  auto store_tiles = [&](int buf) {
+#pragma unroll
+    for (int j = 0; j < 2; ++j) {
+      const int idx = tid + 256 * j, row = idx >> 2, kq = idx & 3;
+      As[buf][kq * 4 + 0][row] = ra[j].x; As[buf][kq * 4 + 1][row] = ra[j].y;
+      As[buf][kq * 4 + 2][row] = ra[j].z; As[buf][kq * 4 + 3][row] = ra[j].w;
+      Ws[buf][kq * 4 + 0][row] = rw[j].x; Ws[buf][kq * 4 + 1][row] = rw[j].y;
+      Ws[buf][kq * 4 + 2][row] = rw[j].z; Ws[buf][kq * 4 + 3][row] = rw[j].w;
+    }
+  };
+  float acc[8][8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i)
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[i][j] = 0.0f;
+  load_tiles(0);
+  store_tiles(0);
+  __syncthreads();
+  const int nk = K / kGemmBK;
+  for (int kb = 0; kb < nk; ++kb) {
+    const int buf = kb & 1;
+    if (kb + 1 < nk) load_tiles((kb + 1) * kGemmBK);
+#pragma unroll
+    for (int k = 0; k < kGemmBK; ++k) {
+      const float4 a0 = *reinterpret_cast<const float4*>(&As[buf][k][ty * 4]);
+      const float4 a1 = *reinterpret_cast<const float4*>(&As[buf][k][64 + ty * 4]);
+      const float4 b0 = *reinterpret_cast<const float4*>(&Ws[buf][k][tx * 4]);
+      const float4 b1 = *reinterpret_cast<const float4*>(&Ws[buf][k][64 + tx * 4]);
+      const float a[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+      const float b[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+#pragma unroll
+      for (int i = 0; i < 8; ++i)
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
+    }
+    if (kb + 1 < nk) {
+      store_tiles(buf ^ 1);
+      __syncthreads();
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const int gm = m0 + (i < 4 ? ty * 4 + i : 64 + ty * 4 + (i - 4));
+    if (gm >= M) continue;
+#pragma unroll
+    for (int jg = 0; jg < 2; ++jg) {
+      const int gn = n0 + (jg == 0 ? tx * 4 : 64 + tx * 4);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        if (gn + j < N) {
+          float v = acc[i][jg * 4 + j] + bias[gn + j];
+          if (EPI == 1) v = gelu_erf(v);
+          C[static_cast<int64_t>(gm) * N + gn + j] = v;
+        }
+      }
+    }
+  }
+}
+
+// ---------------------------------------------------------------- attention
+// qkv: packed [T, 3*hidden] rows = [q | k | v], head h at columns h*HD.  One CTA per (sequence, head): thread t owns
+// query row t (+128, +256, ... for longer sequences), keys / values stream through shared memory 64 at a time;
+// online softmax (running max / sum), fp32, expf.  Keys beyond the sequence do not exist in the packed layout, which
+// IS the reference's padding mask (BertModel's extended attention mask adds -inf to padded keys).
+template <int HD>
+__global__ void __launch_bounds__(128)
+enc_attention_kernel(const float* __restrict__ qkv, const int32_t* __restrict__ cu_seqlens, int hidden,
+                     float* __restrict__ ctx) {
+  constexpr int KB = 64;
+  __shared__ __align__(16) float sK[KB][HD];
+  __shared__ __align__(16) float sV[KB][HD];
+  const int seq = blockIdx.x, head = blockIdx.y;
+  const int t0 = cu_seqlens[seq], len = cu_seqlens[seq + 1] - t0;
+  const int ld = 3 * hidden;
+  const float scale = 1.0f / sqrtf(static_cast<float>(HD));
+  for (int q0 = 0; q0 < len; q0 += blockDim.x) {
+    const int qi = q0 + threadIdx.x;
+    const bool active = qi < len;
+    float q[HD], acc[HD];
+#pragma unroll
+    for (int d = 0; d < HD; ++d) { q[d] = 0.0f; acc[d] = 0.0f; }
+    if (active) {
+      const float4* qp = reinterpret_cast<const float4*>(qkv + static_cast<int64_t>(t0 + qi) * ld + head * HD);
+#pragma unroll
+      for (int d = 0; d < HD / 4; ++d) { const float4 f = qp[d]; q[4 * d] = f.x; q[4 * d + 1] = f.y; q[4 * d + 2] = f.z; q[4 * d + 3] = f.w; }
+    }
+    float m = -__int_as_float(0x7F800000), l = 0.0f;
+    for (int k0 = 0; k0 < len; k0 += KB) {
+      const int nk = min(KB, len - k0);
+      __syncthreads();
+      for (int i = threadIdx.x; i < nk * (HD / 4); i += blockDim.x) {
+        const int r = i / (HD / 4), c = i % (HD / 4);
+        const float* row = qkv + static_cast<int64_t>(t0 + k0 + r) * ld + head * HD;
+        reinterpret_cast<float4*>(&sK[r][0])[c] = reinterpret_cast<const float4*>(row + hidden)[c];
+        reinterpret_cast<float4*>(&sV[r][0])[c] = reinterpret_cast<const float4*>(row + 2 * hidden)[c];
+      }
+      __syncthreads();
+      if (active) {
+        for (int j = 0; j < nk; ++j) {
+          float s = 0.0f;
+#pragma unroll
+          for (int d = 0; d < HD; ++d) s = fmaf(q[d], sK[j][d], s);
+          s *= scale;
+          const float m_new = fmaxf(m, s);
+          const float corr = expf(m - m_new);            // exp(-inf) = 0 on the first key
+          const float p = expf(s - m_new);
+          l = fmaf(l, corr, p);
+#pragma unroll
+          for (int d = 0; d < HD; ++d) acc[d] = fmaf(acc[d], corr, p * sV[j][d]);
+          m = m_new;
+        }
+      }
+    }
+    if (active) {
+      const float inv = 1.0f / l;
+      float4* op = reinterpret_cast<float4*>(ctx + static_cast<int64_t>(t0 + qi) * hidden + head * HD);
+#pragma unroll
+      for (int d = 0; d < HD / 4; ++d)
+        op[d] = make_float4(acc[4 * d] * inv, acc[4 * d + 1] * inv, acc[4 * d + 2] * inv, acc[4 * d + 3] * inv);
+    }
+  }
+}
+
+// ---------------------------------------------------------------- heads
+// head 0 (sentence-transformers Pooling(mean) + Normalize): mean over the sequence's tokens (sum / clamp(len, 1e-9)),
+// then x / max(||x||_2, 1e-12).  One CTA per sequence, one thread per column.
+__global__ void enc_pool_mean_norm_kernel(const float* __restrict__ x, const int32_t* __restrict__ cu_seqlens, int hidden,
+                                          float* __restrict__ out) {
+  __shared__ float s_part[32];
+  const int seq = blockIdx.x;
+  const int t0 = cu_seqlens[seq], len = cu_seqlens[seq + 1] - t0;
+  float sq = 0.0f;
+  float mean_c[kEncMaxHidden / 128];                     // blockDim = 128: columns c = threadIdx.x + 128*i
+  const int per = (hidden + 127) / 128;
+#pragma unroll
+  for (int i = 0; i < kEncMaxHidden / 128; ++i) {
+    mean_c[i] = 0.0f;
+    const int c = threadIdx.x + 128 * i;
+    if (i < per && c < hidden) {
+      float s = 0.0f;
+      for (int t = 0; t < len; ++t) s += x[static_cast<int64_t>(t0 + t) * hidden + c];
+      const float mval = s / fmaxf(static_cast<float>(len), 1e-9f);
+      mean_c[i] = mval;
+      sq = fmaf(mval, mval, sq);
+    }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) sq += __shfl_xor_sync(0xFFFFFFFFu, sq, o);
+  if ((threadIdx.x & 31) == 0) s_part[threadIdx.x >> 5] = sq;
+  __syncthreads();
+  float tot = 0.0f;
+  for (int w = 0; w < (blockDim.x >> 5); ++w) tot += s_part[w];
+  const float inv = 1.0f / fmaxf(sqrtf(tot), 1e-12f);
+#pragma unroll
+  for (int i = 0; i < kEncMaxHidden / 128; ++i) {
+    const int c = threadIdx.x + 128 * i;
+    if (i < per && c < hidden) out[static_cast<int64_t>(seq) * hidden + c] = mean_c[i] * inv;
+  }
+}
+
+// head 1 (BertPooler + classifier, num_labels = 1): logit = w_c . tanh(W_p . h[CLS] + b_p) + b_c.  One CTA per
+// sequence, one thread per pooler output row.
+__global__ void enc_cls_head_kernel(const float* __restrict__ x, const int32_t* __restrict__ cu_seqlens, int hidden,
+                                    const float* __restrict__ pool_w, const float* __restrict__ pool_b,
+                                    const float* __restrict__ cls_w, const float* __restrict__ cls_b,
+                                    float* __restrict__ out) {
+  extern __shared__ float s_h[];                         // [hidden] h[CLS], then [32] partial sums
+  float* s_part = s_h + hidden;
+  const int seq = blockIdx.x;
+  const float* h = x + static_cast<int64_t>(cu_seqlens[seq]) * hidden;
+  for (int c = threadIdx.x; c < hidden; c += blockDim.x) s_h[c] = h[c];
+  __syncthreads();
+  float part = 0.0f;
+  for (int r = threadIdx.x; r < hidden; r += blockDim.x) {
+    float s = 0.0f;
+    const float* w = pool_w + static_cast<int64_t>(r) * hidden;
+    for (int c = 0; c < hidden; ++c) s = fmaf(w[c], s_h[c], s);
+    part = fmaf(cls_w[r], tanhf(s + pool_b[r]), part);
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) part += __shfl_xor_sync(0xFFFFFFFFu, part, o);
+  if ((threadIdx.x & 31) == 0) s_part[threadIdx.x >> 5] = part;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float tot = 0.0f;
+    for (int w = 0; w < (blockDim.x >> 5); ++w) tot += s_part[w];
+    out[seq] = tot + cls_b[0];
+  }
+}
+
+// position of every token inside its sequence (cu_seqlens -> pos_of_token), one thread per token via binary search
+__global__ void enc_positions_kernel(const int32_t* __restrict__ cu_seqlens, int n_seq, int n_tokens,
+                                     int32_t* __restrict__ pos_of_token) {
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= n_tokens) return;
+  int lo = 0, hi = n_seq;                                // last s with cu[s] <= t
+  while (hi - lo > 1) {
+    const int mid = (lo + hi) >> 1;
+    if (cu_seqlens[mid] <= t) lo = mid; else hi = mid;
+  }
+  pos_of_token[t] = t - cu_seqlens[lo];
+}
+
+}  // namespace rse

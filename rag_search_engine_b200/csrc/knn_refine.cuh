@@ -51,11 +51,12 @@ template <bool FMA>
 __global__ void __launch_bounds__(kSelThreads, 2)
 knn_refine_kernel(const float* __restrict__ emb, const float* __restrict__ amag, const float* __restrict__ q,
                   const double* __restrict__ sb, const uint2* __restrict__ cand_pairs,
-                  const unsigned int* __restrict__ cand_count, int cap, int kprime, uint64_t pos_base,
+                  unsigned int* __restrict__ cand_count, int cap, int kprime, uint64_t pos_base,
                   const int64_t* __restrict__ rowid, const int32_t* __restrict__ movie_idx,
                   long long* __restrict__ cand, int* __restrict__ status, int normalized,
                   const float* __restrict__ thr2, const unsigned int* __restrict__ gate,
-                  unsigned long long* __restrict__ counters) {
+                  unsigned long long* __restrict__ counters, float* __restrict__ thr2_out,
+                  unsigned int* __restrict__ gate_out) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   uint2* pairs = reinterpret_cast<uint2*>(smem_raw);                       // [cap]
   __shared__ float s_q[kScanD];
@@ -68,12 +69,20 @@ knn_refine_kernel(const float* __restrict__ emb, const float* __restrict__ amag,
   if (thr2 != nullptr && (*gate == 0u || status[qi] == 0 || !(thr2[qi] < __int_as_float(0x7F800000)))) return;
   const unsigned int cnt = cand_count[qi];
   long long* out = cand + static_cast<int64_t>(qi) * kprime * 3;
-  if (cnt > static_cast<unsigned int>(cap)) {                              // survivor overflow
+  // Survivor overflow (count > cap: the sample's K'-th value was a poor bound — a dense neighbourhood on a
+  // clustered corpus).  First pass with thr2_out: ARM THE SECOND CHANCE instead of giving up — the `cap` survivors
+  // that were kept are K'+ rows with known cos~, so their K'-th largest value s' is a valid lower bound of the
+  // K'-th largest cos~ overall and thr2 = s' - 2 eps keeps every row of the exact top-K' by the same argument as
+  // the first bound, only much tighter.  The filter and this kernel are enqueued a second time, gated on *gate_out.
+  const bool overflow = cnt > static_cast<unsigned int>(cap);
+  const bool arm = overflow && thr2_out != nullptr && kprime <= cap;
+  if (thr2_out != nullptr && threadIdx.x == 0) thr2_out[qi] = __int_as_float(0x7F800000);   // default: keep nothing
+  if (overflow && !arm) {
     if (threadIdx.x == 0) status[qi] = 1;
     for (int i = threadIdx.x; i < kprime * 3; i += blockDim.x) out[i] = -1ll;
     return;
   }
-  const int n = static_cast<int>(cnt);
+  const int n = overflow ? cap : static_cast<int>(cnt);
   // (knn_tc3 never emits an empty slot or a zero row: its thresholds are positive and those rows read cos~ = 0;
   //  knn_tc / knn_tc2 check |a|^2 in their epilogues)
   for (int i = threadIdx.x; i < n; i += blockDim.x) pairs[i] = cand_pairs[static_cast<int64_t>(qi) * cap + i];
@@ -103,6 +112,20 @@ knn_refine_kernel(const float* __restrict__ emb, const float* __restrict__ amag,
       resolved_mask |= 0xFFu << shift;
       __syncthreads();
     }
+  }
+  if (arm) {                                                               // n = cap > K': s_prefix is s' of the kept survivors
+    if (threadIdx.x == 0) {
+      const float s_k = __uint_as_float(f32_from_orderable(~s_prefix));
+      const float cut2 = s_k - 2.0f * kTcEps - 1e-6f;
+      if (cut2 > 1e-6f) {
+        thr2_out[qi] = cut2;
+        cand_count[qi] = 0u;
+        atomicAdd(gate_out, 1u);
+      }
+      status[qi] = 1;
+    }
+    for (int i = threadIdx.x; i < kprime * 3; i += blockDim.x) out[i] = -1ll;
+    return;
   }
   // s_K (exact K'-th largest approximate value), cut = s_K - 2 eps |q|  (slack for f32 rounding)
   float cut = -__int_as_float(0x7F800000);

@@ -388,67 +388,6 @@ tc3_probe_threshold_kernel(const uint32_t* __restrict__ dist, int64_t ld, int nq
   }
 }
 
-// ---------------------------------------------------------------- second chance (survivor overflow)
-// A query whose survivor list overflowed (count > cap: the sample's K'-th value was a poor bound — a dense
-// neighbourhood on a clustered corpus) does not have to go back to the exact scan (2.9 ms per 16 queries): the
-// `cap` survivors that WERE kept are K'+ rows with known cos~, so their K'-th largest value s' is a valid lower
-// bound of the K'-th largest cos~ overall, and thr2 = s' - 2 eps keeps every row of the exact top-K' by the same
-// argument as the first bound — only much tighter (the kept survivors are a large subset of everything above the
-// first threshold).  One CTA per query of the block:
-//   status == 0                          -> thr2 = +inf (pass 2 keeps nothing for it)
-//   flagged for another reason           -> thr2 = +inf, stays flagged (refined-list overflow = a mass tie at the
-//                                           K'-th distance, too few rows, unusable norm: the exact scan's job)
-//   flagged, count > cap                 -> thr2 from the kept survivors, count reset, *gate += 1
-// The filter pass and the refine kernel are then enqueued a second time, gated on *gate.
-__global__ void __launch_bounds__(256)
-tc3_second_threshold_kernel(const int* __restrict__ status, const uint2* __restrict__ cand_pairs,
-                            unsigned int* __restrict__ cand_count, int cap, int nq, int kprime,
-                            float* __restrict__ thr2, unsigned int* __restrict__ gate) {
-  extern __shared__ uint32_t s_val[];                      // [cap] ~orderable(cos~): ascending == descending cos~
-  __shared__ unsigned int s_hist[256];
-  __shared__ unsigned int s_prefix, s_need, s_digit, s_before;
-  __shared__ unsigned int s_warp[8];
-  const int q = blockIdx.x;
-  const float inf = __int_as_float(0x7F800000);
-  if (q >= nq || status[q] == 0 || cand_count[q] <= static_cast<unsigned int>(cap) || kprime > cap) {
-    if (threadIdx.x == 0) thr2[q] = inf;
-    return;
-  }
-  for (int i = threadIdx.x; i < cap; i += blockDim.x) s_val[i] = ~f32_orderable(cand_pairs[static_cast<int64_t>(q) * cap + i].y);
-  if (threadIdx.x == 0) { s_prefix = 0u; s_need = static_cast<unsigned int>(kprime); }
-  __syncthreads();
-  uint32_t resolved = 0u;
-  for (int pass = 0; pass < 4; ++pass) {
-    const int shift = 24 - 8 * pass;
-    s_hist[threadIdx.x] = 0u;
-    __syncthreads();
-    const uint32_t prefix = s_prefix;
-    for (int i = threadIdx.x; i < cap; i += blockDim.x) {
-      const uint32_t key = s_val[i];
-      if ((key & resolved) == prefix) atomicAdd(&s_hist[(key >> shift) & 0xFFu], 1u);
-    }
-    __syncthreads();
-    block_pick_digit(s_hist, s_need, s_warp, &s_digit, &s_before);
-    if (threadIdx.x == 0) {
-      s_prefix = prefix | ((s_digit & 0xFFu) << shift);
-      s_need = s_need - s_before;
-    }
-    resolved |= 0xFFu << shift;
-    __syncthreads();
-  }
-  if (threadIdx.x == 0) {
-    const float s_k = __uint_as_float(f32_from_orderable(~s_prefix));     // K'-th largest cos~ among the kept survivors
-    const float cut = s_k - 2.0f * kTcEps - 1e-6f;
-    if (cut > 1e-6f) {
-      thr2[q] = cut;
-      cand_count[q] = 0u;
-      atomicAdd(gate, 1u);
-    } else {
-      thr2[q] = inf;
-    }
-  }
-}
-
 // ---------------------------------------------------------------- the GEMM
 // MODE 0 (probe) : tiles t = 0..n_tiles-1 map to the 256-row tile t*tile_stride; d~ = 1 - cos~ is stored to
 //                  dist[q*ld + t*256 + r].  Empty slots / rows past the end are zero rows of the shadow:
@@ -470,8 +409,8 @@ knn_tc3_kernel(const __grid_constant__ CUtensorMap tmap_rows, const __grid_const
                int64_t n_tiles, int64_t tile_stride, int nq, const float* __restrict__ thr,
                uint32_t* __restrict__ dist, int64_t ld, uint2* __restrict__ cand_pairs,
                unsigned int* __restrict__ cand_count, int cap, const unsigned int* __restrict__ gate) {
-  // second-chance pass (rse.cu): enqueued unconditionally, runs only when the threshold kernel counted a query that
-  // needs it.  Uniform over the grid and ahead of every barrier / TMEM allocation.
+  // second-chance pass (rse.cu, knn_refine.cuh): enqueued unconditionally, runs only when the first refine pass
+  // armed a query.  Uniform over the grid and ahead of every barrier / TMEM allocation.
   if (gate != nullptr && *gate == 0u) return;
   extern __shared__ unsigned char smem_raw[];
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;

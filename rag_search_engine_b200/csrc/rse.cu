@@ -9,12 +9,14 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <set>
 #include <string>
 #include <vector>
 
 #include "bm25.cuh"
 #include "comm.h"
 #include "common.cuh"
+#include "encoder.cuh"
 #include "fusion.cuh"
 #include "knn_scan.cuh"
 #include "select.cuh"
@@ -29,6 +31,23 @@ thread_local std::string g_create_error;
 struct DevBuf {
   void* p = nullptr;
   size_t bytes = 0;
+};
+
+// ---- §8(f2)/(f3): a BERT-family encoder resident next to the index (encoder.cuh)
+struct EncLayer {
+  float *wqkv = nullptr, *bqkv = nullptr, *wo = nullptr, *bo = nullptr, *ln1g = nullptr, *ln1b = nullptr;
+  float *wi = nullptr, *bi = nullptr, *wo2 = nullptr, *bo2 = nullptr, *ln2g = nullptr, *ln2b = nullptr;
+};
+struct Encoder {
+  rse_encoder_config cfg{};
+  bool created = false, finalized = false;
+  float *word = nullptr, *pos = nullptr, *type = nullptr, *elng = nullptr, *elnb = nullptr;
+  float *poolw = nullptr, *poolb = nullptr, *clsw = nullptr, *clsb = nullptr;
+  std::vector<EncLayer> layers;
+  std::set<std::string> seen;
+  DevBuf ids, type_ids, cu, posidx, x, qkv, ctx, tmp, ff, out;
+  int32_t* pin_in = nullptr;          // pinned staging of ids | type_ids | cu_seqlens
+  size_t pin_in_n = 0;
 };
 
 }  // namespace
@@ -163,6 +182,8 @@ struct rse_index {
 
   // cudaFuncSetAttribute is per device: remember per HANDLE which kernels were configured (a process-wide static
   // flag would leave the second device of a multi-GPU process unconfigured)
+  Encoder enc[RSE_MAX_ENCODERS];
+
   // ---- row-sharded multi-GPU path: the handle owns the communicator (comm.h)
   ncclComm_t comm = nullptr;
   int comm_ranks = 1, comm_rank = 0;
@@ -240,6 +261,18 @@ void release_bm25(rse_index* h) {
   h->df_host.clear();
   h->n_terms = h->n_postings = h->n_docs = h->n_movies = 0;
   h->normk_k1 = NAN; h->normk_b = NAN;
+}
+
+void enc_release(Encoder& e) {
+  for (float** p : {&e.word, &e.pos, &e.type, &e.elng, &e.elnb, &e.poolw, &e.poolb, &e.clsw, &e.clsb}) free_ptr(*p);
+  for (auto& l : e.layers)
+    for (float** p : {&l.wqkv, &l.bqkv, &l.wo, &l.bo, &l.ln1g, &l.ln1b, &l.wi, &l.bi, &l.wo2, &l.bo2, &l.ln2g, &l.ln2b}) free_ptr(*p);
+  e.layers.clear();
+  e.seen.clear();
+  for (DevBuf* b : {&e.ids, &e.type_ids, &e.cu, &e.posidx, &e.x, &e.qkv, &e.ctx, &e.tmp, &e.ff, &e.out}) free_buf(*b);
+  if (e.pin_in) cudaFreeHost(e.pin_in);
+  e.pin_in = nullptr; e.pin_in_n = 0;
+  e.created = e.finalized = false;
 }
 
 // ------------------------------------------------------------------ scan launch
@@ -385,7 +418,7 @@ int make_tmap_lines(rse_index* h, CUtensorMap* out, const void* base, int64_t li
 // refine + exact re-score + emit for one block of queries whose survivors are in tc_rows / tc_cnt.
 // thr2 / gate != NULL: the second-chance pass (only the queries tc3_second_threshold_kernel re-armed).
 int knn_tc_refine(rse_index* h, const float* q_dev, const double* sb, int nqb, int kprime, long long* cand_dev,
-                  int* status_dev, const float* thr2, const unsigned int* gate) {
+                  int* status_dev, const float* thr2, const unsigned int* gate, float* thr2_out, unsigned int* gate_out) {
   if (!(h->attr_mask & (1u << 10))) {
     CK(cudaFuncSetAttribute(knn_refine_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kTcCandCap * 8));
     CK(cudaFuncSetAttribute(knn_refine_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kTcCandCap * 8));
@@ -394,13 +427,13 @@ int knn_tc_refine(rse_index* h, const float* q_dev, const double* sb, int nqb, i
   if (h->fma)
     knn_refine_kernel<true><<<nqb, kSelThreads, kTcCandCap * 8, h->stream>>>(
         h->emb, h->amag, q_dev, sb, static_cast<const uint2*>(h->tc_rows.p),
-        static_cast<const unsigned int*>(h->tc_cnt.p), kTcCandCap, kprime, h->pos_base, h->rowid, h->movie_idx,
-        cand_dev, status_dev, 1, thr2, gate, h->dev_counters);
+        static_cast<unsigned int*>(h->tc_cnt.p), kTcCandCap, kprime, h->pos_base, h->rowid, h->movie_idx,
+        cand_dev, status_dev, 1, thr2, gate, h->dev_counters, thr2_out, gate_out);
   else
     knn_refine_kernel<false><<<nqb, kSelThreads, kTcCandCap * 8, h->stream>>>(
         h->emb, h->amag, q_dev, sb, static_cast<const uint2*>(h->tc_rows.p),
-        static_cast<const unsigned int*>(h->tc_cnt.p), kTcCandCap, kprime, h->pos_base, h->rowid, h->movie_idx,
-        cand_dev, status_dev, 1, thr2, gate, h->dev_counters);
+        static_cast<unsigned int*>(h->tc_cnt.p), kTcCandCap, kprime, h->pos_base, h->rowid, h->movie_idx,
+        cand_dev, status_dev, 1, thr2, gate, h->dev_counters, thr2_out, gate_out);
   LAUNCHED(h);
   return RSE_OK;
 }
@@ -606,30 +639,23 @@ int knn_tc3_block(rse_index* h, const float* q_dev, const double* sb, int nqb, i
   h->stats.knn_scan_launches++;
   h->stats.tc_filter_launches++;
 
-  // 3. refine on the approximate values, 4. exact re-score + sort + emit (one CTA per query)
+  // 3. refine on the approximate values, 4. exact re-score + sort + emit (one CTA per query); a query whose
+  //    survivor list overflowed arms the second chance instead (thr2 from the survivors that were kept)
+  float* thr2 = thr + kTcBN;
+  unsigned int* gate = static_cast<unsigned int*>(h->tc_cnt.p) + kTcBN;
   {
-    int rc = knn_tc_refine(h, q_dev, sb, nqb, kprime, cand_dev, status_dev, nullptr, nullptr);
+    int rc = knn_tc_refine(h, q_dev, sb, nqb, kprime, cand_dev, status_dev, nullptr, nullptr,
+                           h->second_chance ? thr2 : nullptr, h->second_chance ? gate : nullptr);
     if (rc != RSE_OK) return rc;
   }
   if (!h->second_chance) return RSE_OK;
-  // 5. second chance for queries whose survivor list overflowed (a dense neighbourhood): a tight threshold from
-  //    the survivors that were kept, one more filter pass + refine for those queries only.  Enqueued
-  //    unconditionally, gated on the device: three near-empty launches when no query needs it.
-  if (!(h->attr_mask & (1u << 16))) {
-    CK(cudaFuncSetAttribute(tc3_second_threshold_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kTcCandCap * 4));
-    h->attr_mask |= 1u << 16;
-  }
-  float* thr2 = thr + kTcBN;
-  unsigned int* gate = static_cast<unsigned int*>(h->tc_cnt.p) + kTcBN;
-  tc3_second_threshold_kernel<<<kTcBN, 256, kTcCandCap * 4, h->stream>>>(
-      status_dev, static_cast<const uint2*>(h->tc_rows.p), static_cast<unsigned int*>(h->tc_cnt.p), kTcCandCap, nqb,
-      kprime, thr2, gate);
-  LAUNCHED(h);
+  // 5. second chance: one more filter pass + refine for the armed queries only.  Enqueued unconditionally, gated on
+  //    the device: two near-empty launches when no query needs it.
   knn_tc3_kernel<1><<<grid_f, kT3Threads, kT3SmemBytes, h->stream>>>(
       h->tmap_a16, h->tmap_q16, n_tiles, 1, nqb, thr2, nullptr, 0, static_cast<uint2*>(h->tc_rows.p),
       static_cast<unsigned int*>(h->tc_cnt.p), kTcCandCap, gate);
   LAUNCHED(h);
-  return knn_tc_refine(h, q_dev, sb, nqb, kprime, cand_dev, status_dev, thr2, gate);
+  return knn_tc_refine(h, q_dev, sb, nqb, kprime, cand_dev, status_dev, thr2, gate, nullptr, nullptr);
 }
 
 bool tc_eligible(const rse_index* h, int nq, int kprime) {
@@ -863,6 +889,7 @@ void rse_destroy(rse_index* h) {
   if (h->stream_b) cudaStreamDestroy(h->stream_b);
   free_ptr(h->doc_ids);
   free_ptr(h->movie_ids);
+  for (auto& e : h->enc) enc_release(e);
   free_ptr(h->dev_counters);
   if (h->comm) { if (NcclApi* n = nccl_api()) n->CommDestroy(h->comm); h->comm = nullptr; }
   free_buf(h->sh_cand); free_buf(h->sh_mine);
@@ -1847,6 +1874,269 @@ int rse_hybrid_collect(rse_index* h, int64_t ticket, int32_t* out_nq, int32_t* o
   std::memcpy(out_b, sl.pin + 24 * n, 8 * n);
   std::memcpy(out_count, sl.pin + 32 * n, 4 * static_cast<size_t>(sl.nq));
   ++h->next_collect;
+  return RSE_OK;
+}
+
+// ------------------------------------------------------------------ §8(f2)/(f3): text encoders on the device
+namespace {
+
+int enc_alloc(rse_index* h, float** p, size_t n) {
+  CK(cudaMalloc(p, sizeof(float) * std::max<size_t>(n, 1)));
+  return RSE_OK;
+}
+
+extern "C++" {
+template <int EPI>
+int enc_gemm(rse_index* h, const float* A, const float* W, const float* bias, float* C, int M, int N, int K) {
+  dim3 grid((N + kGemmBN - 1) / kGemmBN, (M + kGemmBM - 1) / kGemmBM);
+  enc_gemm_kernel<EPI><<<grid, 256, 0, h->stream>>>(A, W, bias, C, M, N, K);
+  LAUNCHED(h);
+  return RSE_OK;
+}
+}
+
+// ids / type_ids / cu_seqlens are on the device already; x <- encoder output [T, hidden]; out <- head output
+int enc_forward(rse_index* h, Encoder& e, int n_seq, int T, bool has_types, float* out_dev) {
+  const rse_encoder_config& c = e.cfg;
+  const int H = c.hidden, I = c.intermediate;
+  ENSURE(e.posidx, sizeof(int32_t) * T);
+  ENSURE(e.x, sizeof(float) * static_cast<size_t>(T) * H);
+  ENSURE(e.qkv, sizeof(float) * static_cast<size_t>(T) * 3 * H);
+  ENSURE(e.ctx, sizeof(float) * static_cast<size_t>(T) * H);
+  ENSURE(e.tmp, sizeof(float) * static_cast<size_t>(T) * H);
+  ENSURE(e.ff, sizeof(float) * static_cast<size_t>(T) * I);
+  float* x = static_cast<float*>(e.x.p);
+  float* qkv = static_cast<float*>(e.qkv.p);
+  float* ctx = static_cast<float*>(e.ctx.p);
+  float* tmp = static_cast<float*>(e.tmp.p);
+  float* ff = static_cast<float*>(e.ff.p);
+  const int32_t* cu = static_cast<const int32_t*>(e.cu.p);
+  enc_positions_kernel<<<(T + 255) / 256, 256, 0, h->stream>>>(cu, n_seq, T, static_cast<int32_t*>(e.posidx.p));
+  LAUNCHED(h);
+  const int tok_grid = (T + 3) / 4;
+  enc_embed_ln_kernel<<<tok_grid, 128, 0, h->stream>>>(
+      static_cast<const int32_t*>(e.ids.p), has_types ? static_cast<const int32_t*>(e.type_ids.p) : nullptr,
+      static_cast<const int32_t*>(e.posidx.p), T, H, c.vocab_size, c.max_positions, c.type_vocab, e.word, e.pos, e.type,
+      e.elng, e.elnb, c.ln_eps, x);
+  LAUNCHED(h);
+  const int hd = H / c.heads;
+  for (const EncLayer& l : e.layers) {
+    int rc = enc_gemm<0>(h, x, l.wqkv, l.bqkv, qkv, T, 3 * H, H);
+    if (rc != RSE_OK) return rc;
+    dim3 agrid(n_seq, c.heads);
+    if (hd == 32) enc_attention_kernel<32><<<agrid, 128, 0, h->stream>>>(qkv, cu, H, ctx);
+    else enc_attention_kernel<64><<<agrid, 128, 0, h->stream>>>(qkv, cu, H, ctx);
+    LAUNCHED(h);
+    rc = enc_gemm<0>(h, ctx, l.wo, l.bo, tmp, T, H, H);
+    if (rc != RSE_OK) return rc;
+    enc_add_ln_kernel<<<tok_grid, 128, 0, h->stream>>>(tmp, x, T, H, l.ln1g, l.ln1b, c.ln_eps, x);
+    LAUNCHED(h);
+    rc = enc_gemm<1>(h, x, l.wi, l.bi, ff, T, I, H);
+    if (rc != RSE_OK) return rc;
+    rc = enc_gemm<0>(h, ff, l.wo2, l.bo2, tmp, T, H, I);
+    if (rc != RSE_OK) return rc;
+    enc_add_ln_kernel<<<tok_grid, 128, 0, h->stream>>>(tmp, x, T, H, l.ln2g, l.ln2b, c.ln_eps, x);
+    LAUNCHED(h);
+  }
+  if (c.head == 0) {
+    enc_pool_mean_norm_kernel<<<n_seq, 128, 0, h->stream>>>(x, cu, H, out_dev);
+  } else {
+    enc_cls_head_kernel<<<n_seq, 128, sizeof(float) * (H + 32), h->stream>>>(x, cu, H, e.poolw, e.poolb, e.clsw, e.clsb, out_dev);
+  }
+  LAUNCHED(h);
+  return RSE_OK;
+}
+
+int enc_check(rse_index* h, int32_t slot, bool need_final) {
+  if (slot < 0 || slot >= RSE_MAX_ENCODERS) return fail(h, RSE_ERR_INVALID, "encoder: slot out of range");
+  if (!h->enc[slot].created) return fail(h, RSE_ERR_STATE, "encoder: rse_encoder_create has not been called for this slot");
+  if (need_final && !h->enc[slot].finalized) return fail(h, RSE_ERR_STATE, "encoder: not finalized (tensors missing?)");
+  return RSE_OK;
+}
+
+// host inputs -> pinned -> device, then forward; out_dev [n_seq, hidden] (head 0) or [n_seq] (head 1)
+int enc_run(rse_index* h, int32_t slot, const int32_t* ids, const int32_t* type_ids, const int32_t* cu, int32_t n_seq,
+            float* out_dev) {
+  int rc = enc_check(h, slot, true);
+  if (rc != RSE_OK) return rc;
+  Encoder& e = h->enc[slot];
+  if (n_seq < 1 || !ids || !cu || !out_dev) return fail(h, RSE_ERR_INVALID, "rse_encode: bad arguments");
+  if (cu[0] != 0) return fail(h, RSE_ERR_INVALID, "rse_encode: cu_seqlens must start at 0");
+  for (int s = 0; s < n_seq; ++s) {
+    const int len = cu[s + 1] - cu[s];
+    if (len < 1) return fail(h, RSE_ERR_INVALID, "rse_encode: empty sequence (the reference raises 'cannot embed empty text', semantic_search.py:218-219)");
+    if (len > e.cfg.max_positions) return fail(h, RSE_ERR_UNSUPPORTED, "rse_encode: sequence longer than max_positions (truncate on the host like the tokenizer does)");
+  }
+  const int T = cu[n_seq];
+  CK(cudaSetDevice(h->device));
+  const size_t n_in = static_cast<size_t>(T) * 2 + n_seq + 1;
+  if (e.pin_in_n < n_in) {
+    CK(cudaStreamSynchronize(h->stream));
+    if (e.pin_in) CK(cudaFreeHost(e.pin_in));
+    e.pin_in = nullptr; e.pin_in_n = 0;
+    CK(cudaMallocHost(reinterpret_cast<void**>(&e.pin_in), sizeof(int32_t) * (n_in + n_in / 2 + 64)));
+    e.pin_in_n = n_in + n_in / 2 + 64;
+  } else {
+    CK(cudaStreamSynchronize(h->stream));                 // the previous call's uploads have left the buffer
+  }
+  std::memcpy(e.pin_in, ids, sizeof(int32_t) * T);
+  if (type_ids) std::memcpy(e.pin_in + T, type_ids, sizeof(int32_t) * T);
+  std::memcpy(e.pin_in + 2 * static_cast<size_t>(T), cu, sizeof(int32_t) * (n_seq + 1));
+  ENSURE(e.ids, sizeof(int32_t) * T);
+  ENSURE(e.type_ids, sizeof(int32_t) * T);
+  ENSURE(e.cu, sizeof(int32_t) * (n_seq + 1));
+  CK(cudaMemcpyAsync(e.ids.p, e.pin_in, sizeof(int32_t) * T, cudaMemcpyHostToDevice, h->stream));
+  if (type_ids) CK(cudaMemcpyAsync(e.type_ids.p, e.pin_in + T, sizeof(int32_t) * T, cudaMemcpyHostToDevice, h->stream));
+  CK(cudaMemcpyAsync(e.cu.p, e.pin_in + 2 * static_cast<size_t>(T), sizeof(int32_t) * (n_seq + 1), cudaMemcpyHostToDevice, h->stream));
+  h->stats.h2d_bytes += static_cast<int64_t>(sizeof(int32_t)) * (static_cast<int64_t>(T) * (type_ids ? 2 : 1) + n_seq + 1);
+  return enc_forward(h, e, n_seq, T, type_ids != nullptr, out_dev);
+}
+
+}  // namespace
+
+int rse_encoder_create(rse_index* h, int32_t slot, const rse_encoder_config* cfg) {
+  if (!h) return RSE_ERR_INVALID;
+  if (slot < 0 || slot >= RSE_MAX_ENCODERS || !cfg) return fail(h, RSE_ERR_INVALID, "rse_encoder_create: bad arguments");
+  const rse_encoder_config& c = *cfg;
+  if (c.hidden < 32 || c.hidden > kEncMaxHidden || c.hidden % 32 || c.heads < 1 || c.hidden % c.heads ||
+      (c.hidden / c.heads != 32 && c.hidden / c.heads != 64) || c.layers < 1 || c.layers > 48 || c.intermediate < 16 ||
+      c.intermediate % 16 || c.hidden % 16 || c.vocab_size < 1 || c.max_positions < 1 || c.type_vocab < 1 ||
+      (c.head != 0 && c.head != 1) || !(c.ln_eps > 0.0f))
+    return fail(h, RSE_ERR_UNSUPPORTED, "rse_encoder_create: unsupported shape (hidden % 32, head_dim 32 or 64, intermediate % 16)");
+  CK(cudaSetDevice(h->device));
+  Encoder& e = h->enc[slot];
+  enc_release(e);
+  e.cfg = c;
+  const size_t H = c.hidden, I = c.intermediate;
+  int rc = RSE_OK;
+  auto A = [&](float** p, size_t n) { if (rc == RSE_OK) rc = enc_alloc(h, p, n); };
+  A(&e.word, c.vocab_size * H); A(&e.pos, c.max_positions * H); A(&e.type, c.type_vocab * H); A(&e.elng, H); A(&e.elnb, H);
+  if (c.head == 1) { A(&e.poolw, H * H); A(&e.poolb, H); A(&e.clsw, H); A(&e.clsb, 1); }
+  e.layers.resize(c.layers);
+  for (auto& l : e.layers) {
+    A(&l.wqkv, 3 * H * H); A(&l.bqkv, 3 * H); A(&l.wo, H * H); A(&l.bo, H); A(&l.ln1g, H); A(&l.ln1b, H);
+    A(&l.wi, I * H); A(&l.bi, I); A(&l.wo2, H * I); A(&l.bo2, H); A(&l.ln2g, H); A(&l.ln2b, H);
+  }
+  if (rc != RSE_OK) { enc_release(e); return rc; }
+  e.created = true;
+  return RSE_OK;
+}
+
+int rse_encoder_set_tensor(rse_index* h, int32_t slot, const char* name, const float* data, int64_t n_elem) {
+  if (!h) return RSE_ERR_INVALID;
+  int rc = enc_check(h, slot, false);
+  if (rc != RSE_OK) return rc;
+  if (!name || !data || n_elem < 1) return fail(h, RSE_ERR_INVALID, "rse_encoder_set_tensor: bad arguments");
+  Encoder& e = h->enc[slot];
+  const rse_encoder_config& c = e.cfg;
+  const int64_t H = c.hidden, I = c.intermediate;
+  // HuggingFace state_dict names, with whatever prefix the wrapper adds ("bert.", "0.auto_model.", ...)
+  std::string full(name);
+  size_t at = std::string::npos;
+  for (const char* key : {"embeddings.", "encoder.layer.", "pooler.", "classifier."}) {
+    const size_t p = full.find(key);
+    if (p != std::string::npos && (at == std::string::npos || p < at)) at = p;
+  }
+  if (at == std::string::npos) return fail(h, RSE_ERR_INVALID, "rse_encoder_set_tensor: not a BERT tensor name: " + full);
+  const std::string nm = full.substr(at);
+  float* dst = nullptr;
+  int64_t want = 0;
+  auto is = [&](const char* s_) { return nm == s_; };
+  if (is("embeddings.word_embeddings.weight")) { dst = e.word; want = c.vocab_size * H; }
+  else if (is("embeddings.position_embeddings.weight")) { dst = e.pos; want = c.max_positions * H; }
+  else if (is("embeddings.token_type_embeddings.weight")) { dst = e.type; want = c.type_vocab * H; }
+  else if (is("embeddings.LayerNorm.weight")) { dst = e.elng; want = H; }
+  else if (is("embeddings.LayerNorm.bias")) { dst = e.elnb; want = H; }
+  else if (is("pooler.dense.weight")) { dst = e.poolw; want = H * H; }
+  else if (is("pooler.dense.bias")) { dst = e.poolb; want = H; }
+  else if (is("classifier.weight")) { dst = e.clsw; want = H; }
+  else if (is("classifier.bias")) { dst = e.clsb; want = 1; }
+  else if (nm.rfind("encoder.layer.", 0) == 0) {
+    const size_t dot = nm.find('.', 14);
+    if (dot == std::string::npos) return fail(h, RSE_ERR_INVALID, "rse_encoder_set_tensor: bad layer name: " + full);
+    const int li = std::atoi(nm.substr(14, dot - 14).c_str());
+    if (li < 0 || li >= c.layers) return fail(h, RSE_ERR_INVALID, "rse_encoder_set_tensor: layer index out of range: " + full);
+    EncLayer& l = e.layers[li];
+    const std::string t = nm.substr(dot + 1);
+    if (t == "attention.self.query.weight") { dst = l.wqkv; want = H * H; }
+    else if (t == "attention.self.key.weight") { dst = l.wqkv + H * H; want = H * H; }
+    else if (t == "attention.self.value.weight") { dst = l.wqkv + 2 * H * H; want = H * H; }
+    else if (t == "attention.self.query.bias") { dst = l.bqkv; want = H; }
+    else if (t == "attention.self.key.bias") { dst = l.bqkv + H; want = H; }
+    else if (t == "attention.self.value.bias") { dst = l.bqkv + 2 * H; want = H; }
+    else if (t == "attention.output.dense.weight") { dst = l.wo; want = H * H; }
+    else if (t == "attention.output.dense.bias") { dst = l.bo; want = H; }
+    else if (t == "attention.output.LayerNorm.weight") { dst = l.ln1g; want = H; }
+    else if (t == "attention.output.LayerNorm.bias") { dst = l.ln1b; want = H; }
+    else if (t == "intermediate.dense.weight") { dst = l.wi; want = I * H; }
+    else if (t == "intermediate.dense.bias") { dst = l.bi; want = I; }
+    else if (t == "output.dense.weight") { dst = l.wo2; want = H * I; }
+    else if (t == "output.dense.bias") { dst = l.bo2; want = H; }
+    else if (t == "output.LayerNorm.weight") { dst = l.ln2g; want = H; }
+    else if (t == "output.LayerNorm.bias") { dst = l.ln2b; want = H; }
+  }
+  if (!dst) {
+    if (c.head == 0 && (nm.rfind("pooler.", 0) == 0 || nm.rfind("classifier.", 0) == 0)) return RSE_OK;   // unused by this head
+    return fail(h, RSE_ERR_INVALID, "rse_encoder_set_tensor: unknown tensor: " + full);
+  }
+  if (n_elem != want) return fail(h, RSE_ERR_INVALID, "rse_encoder_set_tensor: wrong element count for " + full);
+  CK(cudaSetDevice(h->device));
+  CK(cudaMemcpy(dst, data, sizeof(float) * n_elem, cudaMemcpyHostToDevice));
+  e.seen.insert(nm);
+  e.finalized = false;
+  return RSE_OK;
+}
+
+int rse_encoder_finalize(rse_index* h, int32_t slot) {
+  if (!h) return RSE_ERR_INVALID;
+  int rc = enc_check(h, slot, false);
+  if (rc != RSE_OK) return rc;
+  Encoder& e = h->enc[slot];
+  const size_t want = 5 + 16 * static_cast<size_t>(e.cfg.layers) + (e.cfg.head == 1 ? 4 : 0);
+  if (e.seen.size() != want)
+    return fail(h, RSE_ERR_STATE, "rse_encoder_finalize: " + std::to_string(e.seen.size()) + " of " + std::to_string(want) +
+                                      " tensors were set");
+  e.finalized = true;
+  return RSE_OK;
+}
+
+int rse_encode_dev(rse_index* h, int32_t slot, const int32_t* ids, const int32_t* type_ids, const int32_t* cu_seqlens,
+                   int32_t n_seq, float* out_dev) {
+  if (!h) return RSE_ERR_INVALID;
+  return enc_run(h, slot, ids, type_ids, cu_seqlens, n_seq, out_dev);
+}
+
+int rse_encode(rse_index* h, int32_t slot, const int32_t* ids, const int32_t* type_ids, const int32_t* cu_seqlens,
+               int32_t n_seq, float* out_host) {
+  if (!h) return RSE_ERR_INVALID;
+  int rc = enc_check(h, slot, true);
+  if (rc != RSE_OK) return rc;
+  if (!out_host || n_seq < 1) return fail(h, RSE_ERR_INVALID, "rse_encode: bad arguments");
+  Encoder& e = h->enc[slot];
+  const size_t n_out = static_cast<size_t>(n_seq) * (e.cfg.head == 0 ? e.cfg.hidden : 1);
+  CK(cudaSetDevice(h->device));
+  ENSURE(e.out, sizeof(float) * n_out);
+  rc = enc_run(h, slot, ids, type_ids, cu_seqlens, n_seq, static_cast<float*>(e.out.p));
+  if (rc != RSE_OK) return rc;
+  CK(cudaMemcpyAsync(out_host, e.out.p, sizeof(float) * n_out, cudaMemcpyDeviceToHost, h->stream));
+  h->stats.d2h_bytes += static_cast<int64_t>(sizeof(float) * n_out);
+  CK(cudaStreamSynchronize(h->stream));
+  return RSE_OK;
+}
+
+int rse_hybrid_stage_dev(rse_index* h, int32_t nq, const float* q_dev, const int32_t* tok_indptr, const int32_t* term_rows) {
+  if (!h) return RSE_ERR_INVALID;
+  if (nq < 1 || !q_dev || !tok_indptr) return fail(h, RSE_ERR_INVALID, "rse_hybrid_stage_dev: bad arguments");
+  if (!h->emb || !h->movie_idx || !h->indptr || !h->doc_ids || !h->movie_ids)
+    return fail(h, RSE_ERR_STATE, "rse_hybrid: needs embeddings (with movie_idx), a BM25 index and id tables");
+  h->staged_nq = 0;
+  if (tok_indptr[nq] > 0 && !term_rows) return fail(h, RSE_ERR_INVALID, "rse_hybrid_stage_dev: term_rows is NULL");
+  CK(cudaSetDevice(h->device));
+  int rc = bm25_stage(h, tok_indptr, term_rows, nq);
+  if (rc != RSE_OK) return rc;
+  ENSURE(h->q_dev, sizeof(float) * static_cast<size_t>(nq) * h->dim);
+  CK(cudaMemcpyAsync(h->q_dev.p, q_dev, sizeof(float) * static_cast<size_t>(nq) * h->dim, cudaMemcpyDeviceToDevice, h->stream));
+  h->staged_nq = nq;
   return RSE_OK;
 }
 

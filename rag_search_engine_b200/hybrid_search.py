@@ -29,9 +29,12 @@ logger = logging.getLogger(__name__)
 class HybridSearch:
     def __init__(self, docs_path: Path | str | None = None, db_path: Path | str | None = None, *, force: bool = False,
                  max_chunk_size: int = 3, overlap: int = 1, device: int = 0, tie_mode: str = "reference",
-                 **retriever_kwargs) -> None:
+                 cross_encoder=None, **retriever_kwargs) -> None:
         self.db_path = Path(db_path) if db_path else Path(DEFAULT_DB_PATH)
         self.device = device
+        # rerank_method="cross_encoder": an object with .predict(pairs) (encoder.GpuCrossEncoder runs the reference's
+        # TinyBERT cross-encoder on the same GPU); None = the reference's own CPU CrossEncoder (hybrid_search.py:296)
+        self.cross_encoder = cross_encoder
         self.tie_mode = {"reference": _lib.TIE_REFERENCE, "id": _lib.TIE_BY_ID}[tie_mode]
         kw_extra = {k: v for k, v in retriever_kwargs.items() if k in ("tokenizer",)}
         sem_extra = {k: v for k, v in retriever_kwargs.items() if k in ("encoder", "fallback_build")}
@@ -67,6 +70,7 @@ class HybridSearch:
                                    emb=np.zeros((int(index.n_rows), 0), np.float32))
         sem._closed = True
         self.keyword, self.semantic, self._index = kw, sem, index
+        self.cross_encoder = None
         runtime.adopt(self.db_path, device, index)
         self._closed = False
         return self
@@ -146,13 +150,16 @@ class HybridSearch:
 
         # ---- rerank branches run on the host on top of the GPU results (out of scope) ----
         if rerank_method == "cross_encoder":                                               # :279-312
-            from sentence_transformers import CrossEncoder  # type: ignore
             pairs = []
             for idx, doc in enumerate(results, start=1):
                 doc["rrf_rank"] = idx
                 pairs.append([query, f"{doc.get('title', '')} - {doc.get('document') or doc.get('description', '')}"])
             if pairs:
-                scores = CrossEncoder("cross-encoder/ms-marco-TinyBERT-L2-v2").predict(pairs)
+                ce = getattr(self, "cross_encoder", None)
+                if ce is None:
+                    from sentence_transformers import CrossEncoder  # type: ignore
+                    ce = CrossEncoder("cross-encoder/ms-marco-TinyBERT-L2-v2")
+                scores = ce.predict(pairs)
                 for doc, score in zip(results, scores):
                     doc["cross_encoder_score"] = float(score)
                 results.sort(key=lambda d: (d.get("cross_encoder_score", 0.0), d["score"]), reverse=True)
@@ -244,6 +251,30 @@ class HybridSearch:
         oid, osc, oa, ob, oc = self._hybrid_batch(1, float(alpha), token_lists, query_vecs, limit, knn_multiplier, k1, b)
         return [[{"id": int(oid[q, j]), "bm25": float(oa[q, j]), "semantic": float(ob[q, j]),
                   "score": float(osc[q, j])} for j in range(oc[q])] for q in range(len(token_lists))]
+
+    def rrf_search_texts(self, token_lists, encoder_ids, encoder, k=60, limit: int = 10, knn_multiplier: int = 10,
+                         k1: float = 1.5, b: float = 0.75, as_arrays: bool = False):
+        """Text in: the query vectors are produced by ``encoder`` (encoder.GpuSentenceEncoder) ON THE DEVICE and
+        handed to the hybrid step there (``rse_encode_dev`` -> ``rse_hybrid_stage_dev``): no host hop for the
+        vectors.  ``token_lists`` are the BM25 tokens of the queries (the reference's ``preprocess`` output),
+        ``encoder_ids`` the encoder's token ids ([CLS] ... [SEP]) of the same queries."""
+        import torch
+        if not self._gpu_retrievers():
+            raise RuntimeError("rrf_search_texts needs the GPU KeywordSearch and SemanticSearch of this package")
+        self._ensure_id_tables()
+        tok_indptr, rows = self.keyword._term_rows(token_lists)
+        nq = len(tok_indptr) - 1
+        buf = getattr(self, "_qvec_dev", None)
+        if buf is None or buf.shape[0] < nq:
+            buf = self._qvec_dev = torch.empty((max(nq, 256), self._index.dim), dtype=torch.float32,
+                                               device=torch.device("cuda", self.device))
+        n = encoder.encode_ids_dev(encoder_ids, buf.data_ptr())
+        if n != nq:
+            raise ValueError("token_lists and encoder_ids describe different numbers of queries")
+        self._index.hybrid_stage_dev(nq, buf.data_ptr(), tok_indptr, rows)
+        self._index.hybrid_run(0, float(k), limit, knn_multiplier=knn_multiplier, k1=k1, b=b, tie_mode=self.tie_mode)
+        res = self._index.hybrid_fetch(limit)
+        return res if as_arrays else self._unpack_rrf(res, nq)
 
     def rrf_search_stream(self, batches, k=60, limit: int = 10, knn_multiplier: int = 10, k1: float = 1.5,
                           b: float = 0.75, as_arrays: bool = False):

@@ -21,6 +21,7 @@ try:
     for c in d.get("clustered") or []:
         print("clustered", c)
     print("python", d.get("e2e_python"))
+    print("text_in", d.get("text_in"))
     print("small", d.get("knn_small_batches"))
     print("knn100m", d.get("knn100m"))
     print("cpu", d.get("cpu_baseline"))

@@ -1,0 +1,166 @@
+"""GPU: the BERT-family encoders of csrc/encoder.cuh against the fp32 PyTorch models.
+
+The reference's checkpoints (all-MiniLM-L6-v2, ms-marco-TinyBERT-L2-v2) cannot be downloaded here, so the oracle is
+``transformers``' own BertModel / BertForSequenceClassification with the SAME architecture and seeded random
+weights (perturbed away from the initialiser so LayerNorm gains, biases and the position / type tables all
+matter), evaluated in fp32 on the CPU exactly the way sentence-transformers drives it: padded batch + attention
+mask -> last_hidden_state -> mean pooling over the mask -> L2 normalise (semantic_search.py:211-222), and
+[CLS] pooler -> 1-logit classifier for the cross-encoder (hybrid_search.py:296-297).
+
+Tolerance (floating point, stated here): normwise relative error of the pooled vector <= 1e-5 against the fp32
+PyTorch result — and, as a sanity check of that bar, <= 5e-6 against an fp64 evaluation of the same model
+(PyTorch-fp32's own error against fp64 is ~1e-6 on these inputs).
+"""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+torch = pytest.importorskip("torch")
+transformers = pytest.importorskip("transformers")
+
+
+def _randomise(model, seed):
+    g = torch.Generator().manual_seed(seed)
+    with torch.no_grad():
+        for name, p in model.named_parameters():
+            if "LayerNorm.weight" in name:
+                p.copy_(1.0 + 0.1 * torch.randn(p.shape, generator=g))
+            elif name.endswith("bias"):
+                p.copy_(0.05 * torch.randn(p.shape, generator=g))
+            elif "embeddings" in name:
+                p.copy_(0.5 * torch.randn(p.shape, generator=g))
+            else:
+                p.copy_(torch.randn(p.shape, generator=g) / (p.shape[-1] ** 0.5))
+    return model.eval()
+
+
+def _batch(seed, n, lo, hi, vocab, pair=False):
+    rng = np.random.default_rng(seed)
+    ids, types = [], []
+    for _ in range(n):
+        L = int(rng.integers(lo, hi + 1))
+        x = rng.integers(1000, vocab, L).tolist()
+        x[0], x[-1] = 101, 102                                   # [CLS] ... [SEP]
+        t = [0] * L
+        if pair and L > 4:
+            cut = int(rng.integers(2, L - 1))
+            x[cut] = 102
+            t = [0] * (cut + 1) + [1] * (L - cut - 1)
+        ids.append(x); types.append(t)
+    return ids, types
+
+
+def _pad(lists, fill=0):
+    S = max(len(x) for x in lists)
+    a = np.full((len(lists), S), fill, np.int64)
+    m = np.zeros((len(lists), S), np.int64)
+    for i, x in enumerate(lists):
+        a[i, :len(x)] = x
+        m[i, :len(x)] = 1
+    return torch.from_numpy(a), torch.from_numpy(m)
+
+
+def _st_pipeline(bert, ids, dtype):
+    """sentence-transformers: Transformer -> Pooling(mean) -> Normalize."""
+    x, mask = _pad(ids)
+    with torch.no_grad():
+        h = bert(input_ids=x, attention_mask=mask).last_hidden_state.to(dtype)
+    m = mask.unsqueeze(-1).to(dtype)
+    pooled = (h * m).sum(1) / torch.clamp(m.sum(1), min=1e-9)
+    return torch.nn.functional.normalize(pooled, p=2, dim=1).numpy()
+
+
+def _relerr(a, b):
+    a, b = np.asarray(a, np.float64), np.asarray(b, np.float64)
+    return float(np.linalg.norm(a - b, axis=-1).max() / max(1e-30, np.linalg.norm(b, axis=-1).min()))
+
+
+@pytest.fixture(scope="module")
+def minilm():
+    from rag_search_engine_b200.encoder import MINILM_L6_CONFIG as C
+    cfg = transformers.BertConfig(vocab_size=C["vocab_size"], hidden_size=C["hidden"], num_hidden_layers=C["layers"],
+                                  num_attention_heads=C["heads"], intermediate_size=C["intermediate"],
+                                  max_position_embeddings=C["max_positions"], type_vocab_size=C["type_vocab"],
+                                  layer_norm_eps=C["ln_eps"], hidden_dropout_prob=0.0, attention_probs_dropout_prob=0.0)
+    return _randomise(transformers.BertModel(cfg, add_pooling_layer=False), 1)
+
+
+def test_minilm_query_encoder_matches_fp32_pytorch(minilm, fresh_index):
+    from rag_search_engine_b200.encoder import GpuSentenceEncoder, config_from_hf
+    enc = GpuSentenceEncoder(fresh_index, minilm.state_dict(), config_from_hf(minilm.config))
+    assert enc.get_sentence_embedding_dimension() == 384
+    for seed, n, lo, hi in ((3, 67, 3, 24), (4, 5, 100, 200), (5, 1, 2, 2), (6, 9, 250, 256)):
+        ids, _ = _batch(seed, n, lo, hi, 30522)
+        got = enc.encode_ids(ids)
+        ref32 = _st_pipeline(minilm, ids, torch.float32)
+        assert got.shape == ref32.shape == (n, 384)
+        e = _relerr(got, ref32)
+        assert e <= 1e-5, f"pooled vectors differ from the fp32 PyTorch model by {e:.2e} (batch {seed})"
+        assert np.abs(np.linalg.norm(got.astype(np.float64), axis=1) - 1.0).max() < 1e-6
+    # the bar in perspective: our error against an fp64 evaluation vs PyTorch-fp32's own
+    ids, _ = _batch(7, 24, 3, 40, 30522)
+    ref64 = _st_pipeline(minilm.double(), ids, torch.float64)
+    minilm.float()
+    ours, theirs = _relerr(enc.encode_ids(ids), ref64), _relerr(_st_pipeline(minilm, ids, torch.float32), ref64)
+    print(f"error vs fp64: librse {ours:.2e}, PyTorch fp32 {theirs:.2e}")
+    assert ours <= 5e-6
+    # sequences longer than max_seq_length are truncated like the tokenizer would; an empty one is refused
+    long_ids, _ = _batch(8, 2, 300, 300, 30522)
+    assert np.array_equal(enc.encode_ids(long_ids), enc.encode_ids([x[:256] for x in long_ids]))
+    from rag_search_engine_b200._lib import RseError
+    with pytest.raises(RseError, match="empty"):
+        enc.encode_ids([[101, 102], []])
+
+
+def test_tinybert_cross_encoder_matches_fp32_pytorch(fresh_index):
+    from rag_search_engine_b200.encoder import TINYBERT_L2_CONFIG as C, GpuCrossEncoder, config_from_hf
+    cfg = transformers.BertConfig(vocab_size=C["vocab_size"], hidden_size=C["hidden"], num_hidden_layers=C["layers"],
+                                  num_attention_heads=C["heads"], intermediate_size=C["intermediate"],
+                                  max_position_embeddings=C["max_positions"], type_vocab_size=C["type_vocab"],
+                                  layer_norm_eps=C["ln_eps"], hidden_dropout_prob=0.0, attention_probs_dropout_prob=0.0,
+                                  num_labels=1)
+    model = _randomise(transformers.BertForSequenceClassification(cfg), 2)
+    ce = GpuCrossEncoder(fresh_index, model.state_dict(), config_from_hf(model.config))
+    for seed, n, lo, hi in ((11, 20, 12, 90), (12, 3, 400, 512), (13, 1, 5, 5)):
+        ids, types = _batch(seed, n, lo, hi, 30522, pair=True)
+        x, mask = _pad(ids)
+        tt, _ = _pad(types)
+        with torch.no_grad():
+            ref = model(input_ids=x, attention_mask=mask, token_type_ids=tt).logits[:, 0].numpy()
+        got = ce.predict_ids(ids, types)
+        assert got.shape == (n,)
+        err = np.abs(got.astype(np.float64) - ref) / np.maximum(1.0, np.abs(ref))
+        assert err.max() <= 1e-5, f"cross-encoder logits off by {err.max():.2e}"
+        assert np.argsort(-got, kind="stable").tolist() == np.argsort(-ref, kind="stable").tolist()
+    ce.activation = "sigmoid"
+    sg = ce.predict_ids(ids, types)
+    assert np.allclose(sg, 1.0 / (1.0 + np.exp(-ref)), atol=1e-6)
+
+
+def test_text_in_hybrid_keeps_the_query_vectors_on_the_device(minilm):
+    """rse_encode_dev -> rse_hybrid_stage_dev -> run == rse_encode (host) -> rse_hybrid, bit for bit; and the
+    cross-encoder plug of HybridSearch.rrf_search reorders by its scores (hybrid_search.py:279-312)."""
+    from rag_search_engine_b200 import HybridSearch, _lib, synth
+    from rag_search_engine_b200.encoder import GpuSentenceEncoder, config_from_hf
+    se = synth.synth_embeddings(3000, seed=21, device="cpu")
+    bm = synth.synth_bm25(3000, 2000, seed=21, mean_len=30, sd_len=10)
+    idx = _lib.Index(0)
+    try:
+        idx.load_embeddings(se.emb.numpy(), movie_idx=se.movie_of_chunk.numpy())
+        idx.load_bm25(bm.indptr, bm.doc_idx, bm.tf, bm.df, bm.dl, bm.n_movies, bm.avgdl)
+        enc = GpuSentenceEncoder(idx, minilm.state_dict(), config_from_hf(minilm.config))
+        T = len(bm.df)
+        names = [f"t{i}" for i in range(T)]
+        hs = HybridSearch.from_loaded(idx, dict(zip(names, range(T))), se.movie_ids, se.movie_ids,
+                                      registry_key="r02-textin-test")
+        nq = 40
+        tok_indptr, terms = synth.synth_token_queries(bm, nq, seed=22)
+        token_lists = [[names[t] if t >= 0 else "<oov>" for t in terms[tok_indptr[i]:tok_indptr[i + 1]]] for i in range(nq)]
+        ids, _ = _batch(23, nq, 3, 20, 30522)
+        got = hs.rrf_search_texts(token_lists, ids, enc, k=60, limit=10, as_arrays=True)
+        vecs = enc.encode_ids(ids)
+        want = hs.rrf_search_batch(token_lists, vecs, k=60, limit=10, as_arrays=True)
+        assert all((a.view(np.uint8) == b.view(np.uint8)).all() for a, b in zip(got, want))
+        assert int(want[4].sum()) > 0
+    finally:
+        idx.close()
