@@ -110,10 +110,21 @@ class GpuSentenceEncoder:
     def get_sentence_embedding_dimension(self) -> int:
         return int(self.config["hidden"])
 
-    def encode_ids(self, id_lists: Sequence[Sequence[int]]) -> np.ndarray:
+    def encode_ids(self, id_lists: Sequence[Sequence[int]], max_tokens_per_call: int = 1 << 16) -> np.ndarray:
+        """Any number of sequences: the bulk embedding of an index build (semantic_search.py:199-206 encodes every
+        chunk text in one ``model.encode`` call) goes through in slices of at most ``max_tokens_per_call`` tokens
+        (scratch is ~10 KB per token)."""
         id_lists = [list(x)[: self.max_seq_length] for x in id_lists]
-        ids, _, cu = pack(id_lists)
-        return self.index.encode(self.slot, ids, cu)
+        out = np.empty((len(id_lists), int(self.config["hidden"])), np.float32)
+        lo = 0
+        while lo < len(id_lists):
+            hi, tok = lo, 0
+            while hi < len(id_lists) and (hi == lo or tok + len(id_lists[hi]) <= max_tokens_per_call):
+                tok += len(id_lists[hi]); hi += 1
+            ids, _, cu = pack(id_lists[lo:hi])
+            out[lo:hi] = self.index.encode(self.slot, ids, cu)
+            lo = hi
+        return out
 
     def encode_ids_dev(self, id_lists: Sequence[Sequence[int]], out_ptr: int) -> int:
         """Result stays on the device at ``out_ptr`` ([n, hidden] fp32); returns n."""

@@ -164,3 +164,13 @@ def test_text_in_hybrid_keeps_the_query_vectors_on_the_device(minilm):
         assert int(want[4].sum()) > 0
     finally:
         idx.close()
+
+
+def test_bulk_encode_is_sliced_and_equal(minilm, fresh_index):
+    """Index-build sized input (semantic_search.py:199-206): slices of the token budget give the same vectors."""
+    from rag_search_engine_b200.encoder import GpuSentenceEncoder, config_from_hf
+    enc = GpuSentenceEncoder(fresh_index, minilm.state_dict(), config_from_hf(minilm.config))
+    ids, _ = _batch(31, 300, 3, 30, 30522)
+    whole = enc.encode_ids(ids)
+    sliced = enc.encode_ids(ids, max_tokens_per_call=500)
+    assert np.array_equal(whole, sliced) and whole.shape == (300, 384)

@@ -306,3 +306,47 @@ def test_library_owned_nccl_comm_single_rank(small_world):
         assert same(got, want)
     finally:
         idx.comm_destroy()
+
+
+def test_multimodal_search_ranks_like_the_reference_expression():
+    """§8 f4: image -> text search (rag_search_engine/llm/multimodal.py:86-95) with the ranking on the GPU.
+    Floating point: similarity within 1e-6 of the reference's numpy expression; same ids wherever neighbouring
+    similarities are further apart than that."""
+    from rag_search_engine_b200.multimodal import MultimodalSearch
+
+    class FakeClip:                                   # the CLIP model is out of scope: any object with .encode
+        def __init__(self, dim=512):
+            self.dim = dim
+        def encode(self, items, convert_to_numpy=True, show_progress_bar=False):
+            out = np.empty((len(items), self.dim), np.float32)
+            for i, t in enumerate(items):
+                seed = abs(hash(t)) % (2 ** 32) if isinstance(t, str) else 7
+                out[i] = np.random.default_rng(seed).standard_normal(self.dim).astype(np.float32) * 3.0
+            return out
+
+    docs = [{"id": 100 + i, "title": f"Movie {i}", "description": f"plot {i * 7 % 13} words {i}"} for i in range(6000)]
+    docs[17] = {"id": 117, "title": "no description", "document": "fallback text"}
+    ms = MultimodalSearch(documents=docs, model=FakeClip())
+    try:
+        rng = np.random.default_rng(3)
+        for trial in range(4):
+            img = (ms.text_embeddings[rng.integers(0, 6000)] + 2.0 * rng.standard_normal(512)).astype(np.float32)
+            # the reference, verbatim (llm/multimodal.py:86-95)
+            image_vec = img / (np.linalg.norm(img) + 1e-12)
+            text_vecs = ms.text_embeddings
+            text_normed = text_vecs / (np.linalg.norm(text_vecs, axis=1, keepdims=True) + 1e-12)
+            similarities = (text_normed @ image_vec).astype(float)
+            top = np.argsort(similarities)[::-1][:25]
+            got = ms.search_with_vector(img, top_k=25)
+            assert len(got) == 25 and list(got[0].keys()) == ["id", "title", "description", "similarity"]
+            for j, (g, want) in enumerate(zip(got, top)):
+                assert abs(g["similarity"] - similarities[want]) < 1e-6
+                gap = min(abs(similarities[top[j]] - similarities[top[j - 1]]) if j else 1.0,
+                          abs(similarities[top[j]] - similarities[top[j + 1]]) if j + 1 < len(top) else 1.0)
+                if gap > 2e-6:
+                    assert g["id"] == docs[want].get("id", want)
+        assert ms.search_with_vector(img, top_k=10 ** 6 if False else 3)[0]["id"] == got[0]["id"]
+        with pytest.raises(ValueError, match="initialized without documents"):
+            MultimodalSearch(documents=None, model=FakeClip()).search_with_image("x.png")
+    finally:
+        ms.close()
