@@ -273,6 +273,10 @@ typedef struct rse_encoder_config {
 int rse_encoder_create(rse_index *h, int32_t slot, const rse_encoder_config *cfg);
 int rse_encoder_set_tensor(rse_index *h, int32_t slot, const char *name, const float *data, int64_t n_elem);
 int rse_encoder_finalize(rse_index *h, int32_t slot);
+/* Which GEMM the encoder's linear layers run on (results agree to ~1e-6 relative; both meet the 1e-5 bar):
+ * 0 = tcgen05 kind::tf32 tensor cores with a 3-pass hi/lo split of both operands (fp32-class accuracy; default
+ * when every GEMM dimension is a multiple of 128), 1 = fp32 SIMT (fmaf). */
+int rse_encoder_set_mode(rse_index *h, int32_t slot, int32_t mode);
 int rse_encode(rse_index *h, int32_t slot, const int32_t *ids, const int32_t *type_ids, const int32_t *cu_seqlens,
                int32_t n_seq, float *out_host);
 int rse_encode_dev(rse_index *h, int32_t slot, const int32_t *ids, const int32_t *type_ids,

@@ -120,6 +120,7 @@ _SIGNATURES = {
     "rse_encoder_create": (ctypes.c_int, [c_void_p, c_int32, POINTER(RseEncoderConfig)]),
     "rse_encoder_set_tensor": (ctypes.c_int, [c_void_p, c_int32, c_char_p, POINTER(c_float), c_int64]),
     "rse_encoder_finalize": (ctypes.c_int, [c_void_p, c_int32]),
+    "rse_encoder_set_mode": (ctypes.c_int, [c_void_p, c_int32, c_int32]),
     "rse_encode": (ctypes.c_int, [c_void_p, c_int32, POINTER(c_int32), POINTER(c_int32), POINTER(c_int32), c_int32,
                                   POINTER(c_float)]),
     "rse_encode_dev": (ctypes.c_int, [c_void_p, c_int32, POINTER(c_int32), POINTER(c_int32), POINTER(c_int32), c_int32,
@@ -491,6 +492,10 @@ class Index:
 
     def encoder_finalize(self, slot: int):
         self._check(self._L.rse_encoder_finalize(self._h, int(slot)))
+
+    def encoder_set_mode(self, slot: int, mode: int):
+        """0 = tcgen05 3xTF32 GEMMs (default), 1 = fp32 SIMT GEMMs."""
+        self._check(self._L.rse_encoder_set_mode(self._h, int(slot), int(mode)))
 
     def _enc_inputs(self, ids, type_ids, cu_seqlens):
         ids = _c(ids, np.int32).reshape(-1)

@@ -26,16 +26,30 @@
 
 #include <cstdint>
 
+#include "tc_common.cuh"
+
 namespace rse {
 
 constexpr int kEncMaxHidden = 1024;
+
+// tf32 split of an fp32 value (see the tensor-core GEMM at the end of this file): hi = tf32(x), lo = tf32(x - hi)
+__device__ __forceinline__ float tf32_rna(float x) {
+  uint32_t r;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
+  return __uint_as_float(r);
+}
+__device__ __forceinline__ void tf32_split(float x, float& hi, float& lo) {
+  hi = tf32_rna(x);
+  lo = tf32_rna(x - hi);                                        // x - hi is exact in fp32
+}
 
 // ---------------------------------------------------------------- embeddings + LayerNorm / residual + LayerNorm
 // one warp per token; two-pass mean / variance in registers (torch.nn.LayerNorm: biased variance, eps inside sqrt)
 template <int MAX_PER_LANE>
 __device__ __forceinline__ void warp_layernorm(float (&v)[MAX_PER_LANE], int per_lane, int hidden, float eps,
                                                const float* __restrict__ gamma, const float* __restrict__ beta,
-                                               float* __restrict__ out_row, int lane) {
+                                               float* __restrict__ out_row, int lane,
+                                               float* __restrict__ hi_row = nullptr, float* __restrict__ lo_row = nullptr) {
   float s = 0.0f;
 #pragma unroll
   for (int i = 0; i < MAX_PER_LANE; ++i) if (i < per_lane) s += v[i];
@@ -52,7 +66,9 @@ __device__ __forceinline__ void warp_layernorm(float (&v)[MAX_PER_LANE], int per
   for (int i = 0; i < MAX_PER_LANE; ++i)
     if (i < per_lane) {
       const int c = i * 32 + lane;
-      out_row[c] = fmaf((v[i] - mean) * rstd, gamma[c], beta[c]);
+      const float y = fmaf((v[i] - mean) * rstd, gamma[c], beta[c]);
+      out_row[c] = y;
+      if (hi_row) { float h, l; tf32_split(y, h, l); hi_row[c] = h; lo_row[c] = l; }
     }
 }
 
@@ -61,7 +77,7 @@ enc_embed_ln_kernel(const int32_t* __restrict__ ids, const int32_t* __restrict__
                     const int32_t* __restrict__ pos_of_token, int n_tokens, int hidden, int vocab, int max_pos,
                     int type_vocab, const float* __restrict__ word, const float* __restrict__ pos,
                     const float* __restrict__ type, const float* __restrict__ gamma, const float* __restrict__ beta,
-                    float eps, float* __restrict__ out) {
+                    float eps, float* __restrict__ out, float* __restrict__ out_hi, float* __restrict__ out_lo) {
   const int lane = threadIdx.x & 31;
   const int t = blockIdx.x * 4 + (threadIdx.x >> 5);
   if (t >= n_tokens) return;
@@ -78,13 +94,16 @@ enc_embed_ln_kernel(const int32_t* __restrict__ ids, const int32_t* __restrict__
       v[i] = (word[static_cast<int64_t>(id) * hidden + c] + type[static_cast<int64_t>(tt) * hidden + c]) +
              pos[static_cast<int64_t>(p) * hidden + c];
     }
-  warp_layernorm(v, per_lane, hidden, eps, gamma, beta, out + static_cast<int64_t>(t) * hidden, lane);
+  const int64_t ro = static_cast<int64_t>(t) * hidden;
+  warp_layernorm(v, per_lane, hidden, eps, gamma, beta, out + ro, lane, out_hi ? out_hi + ro : nullptr,
+                 out_hi ? out_lo + ro : nullptr);
 }
 
 // out = LayerNorm(x + residual)
 __global__ void __launch_bounds__(128)
 enc_add_ln_kernel(const float* __restrict__ x, const float* __restrict__ residual, int n_tokens, int hidden,
-                  const float* __restrict__ gamma, const float* __restrict__ beta, float eps, float* __restrict__ out) {
+                  const float* __restrict__ gamma, const float* __restrict__ beta, float eps, float* __restrict__ out,
+                  float* __restrict__ out_hi, float* __restrict__ out_lo) {
   const int lane = threadIdx.x & 31;
   const int t = blockIdx.x * 4 + (threadIdx.x >> 5);
   if (t >= n_tokens) return;
@@ -96,7 +115,9 @@ enc_add_ln_kernel(const float* __restrict__ x, const float* __restrict__ residua
       const int64_t o = static_cast<int64_t>(t) * hidden + i * 32 + lane;
       v[i] = x[o] + residual[o];
     }
-  warp_layernorm(v, per_lane, hidden, eps, gamma, beta, out + static_cast<int64_t>(t) * hidden, lane);
+  const int64_t ro = static_cast<int64_t>(t) * hidden;
+  warp_layernorm(v, per_lane, hidden, eps, gamma, beta, out + ro, lane, out_hi ? out_hi + ro : nullptr,
+                 out_hi ? out_lo + ro : nullptr);
 }
 
 // ---------------------------------------------------------------- GEMM: C[M, N] = A[M, K] . W[N, K]^T + bias
@@ -194,7 +215,7 @@ enc_gemm_kernel(const float* __restrict__ A, const float* __restrict__ W, const 
 template <int HD>
 __global__ void __launch_bounds__(128)
 enc_attention_kernel(const float* __restrict__ qkv, const int32_t* __restrict__ cu_seqlens, int hidden,
-                     float* __restrict__ ctx) {
+                     float* __restrict__ ctx, float* __restrict__ ctx_lo) {   // ctx_lo != NULL: ctx <- hi, ctx_lo <- lo
   constexpr int KB = 64;
   __shared__ __align__(16) float sK[KB][HD];
   __shared__ __align__(16) float sV[KB][HD];
@@ -242,10 +263,22 @@ enc_attention_kernel(const float* __restrict__ qkv, const int32_t* __restrict__ 
     }
     if (active) {
       const float inv = 1.0f / l;
-      float4* op = reinterpret_cast<float4*>(ctx + static_cast<int64_t>(t0 + qi) * hidden + head * HD);
+      const int64_t off = static_cast<int64_t>(t0 + qi) * hidden + head * HD;
+      float4* op = reinterpret_cast<float4*>(ctx + off);
+      float4* ol = ctx_lo ? reinterpret_cast<float4*>(ctx_lo + off) : nullptr;
 #pragma unroll
-      for (int d = 0; d < HD / 4; ++d)
-        op[d] = make_float4(acc[4 * d] * inv, acc[4 * d + 1] * inv, acc[4 * d + 2] * inv, acc[4 * d + 3] * inv);
+      for (int d = 0; d < HD / 4; ++d) {
+        float y[4] = {acc[4 * d] * inv, acc[4 * d + 1] * inv, acc[4 * d + 2] * inv, acc[4 * d + 3] * inv};
+        if (ol) {
+          float h[4], l[4];
+#pragma unroll
+          for (int e = 0; e < 4; ++e) tf32_split(y[e], h[e], l[e]);
+          op[d] = make_float4(h[0], h[1], h[2], h[3]);
+          ol[d] = make_float4(l[0], l[1], l[2], l[3]);
+        } else {
+          op[d] = make_float4(y[0], y[1], y[2], y[3]);
+        }
+      }
     }
   }
 }
@@ -328,6 +361,173 @@ __global__ void enc_positions_kernel(const int32_t* __restrict__ cu_seqlens, int
     if (cu_seqlens[mid] <= t) lo = mid; else hi = mid;
   }
   pos_of_token[t] = t - cu_seqlens[lo];
+}
+
+// ================================================================ tensor-core GEMM with fp32 accuracy (3 x TF32)
+// The SIMT GEMM above is exact-ish but runs at ~19 TFLOP/s (r02 bench: 2.8 ms for a 256-query batch).  The
+// tensor cores have no fp32 mode; kind::tf32 keeps 10 mantissa bits of each operand, which alone is ~1e-3 off and
+// fails the 1e-5 bar.  The classic remedy: split every operand into hi = tf32(x) and lo = tf32(x - hi) and
+// accumulate  hi*hi + lo*hi + hi*lo  in the fp32 TMEM accumulator — the dropped lo*lo term is 2^-22 relative, the
+// truncation of lo another 2^-21: fp32-class accuracy at a third of the TF32 rate (still > 10x the SIMT kernel).
+//   * weights are split once at load (enc_split_kernel), activations by the kernel that produces them
+//     (LayerNorm / attention / GELU epilogue write hi and lo next to or instead of the fp32 value);
+//   * one 128 x 128 output tile per CTA (cta_group::1): warp 0 = TMA producer (3-stage ring, per stage four
+//     128 x 32-float boxes: A_hi, A_lo, W_hi, W_lo, SWIZZLE_128B), warp 1 = single-thread tcgen05.mma issuer
+//     (12 MMAs of 128x128x8 per k-block: 4 k-steps x 3 products), warps 2-5 = epilogue (tcgen05.ld 32x32b, one
+//     TMEM lane = one token row per thread): bias (+ GELU + split) and 128-byte row stores.
+constexpr int kEgBM = 128, kEgBN = 128, kEgBK = 32, kEgStages = 3;
+constexpr int kEgBox = kEgBM * kEgBK * 4;                       // 16,384 B: one operand box
+constexpr int kEgStageBytes = 4 * kEgBox;                       // 65,536
+constexpr int kEgThreads = 192;
+constexpr int kEgSmemBytes = kEgStages * kEgStageBytes + 16 * 8 + 16 + 1024;
+// kind::tf32: D = f32 (bit 4), A = B = tf32 (format 2), both K-major, N = 128, M = 128
+constexpr uint32_t kEgIdesc = (1u << 4) | (2u << 7) | (2u << 10) | ((kEgBN >> 3) << 17) | ((kEgBM >> 4) << 24);
+
+__global__ void enc_split_kernel(const float* __restrict__ x, int64_t n, float* __restrict__ hi, float* __restrict__ lo) {
+  const int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  float h, l;
+  tf32_split(x[i], h, l);
+  hi[i] = h; lo[i] = l;
+}
+
+__device__ __forceinline__ void eg_tma_load_2d(void* smem_dst, const CUtensorMap* tmap, int c0, int c1, uint64_t* bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::
+          "r"(smem_u32(smem_dst)),
+      "l"(tmap), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void eg_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void eg_mma_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "setp.ne.b32 p, %4, 0;\n"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n"
+      "}\n" ::"r"(tmem_d),
+      "l"(adesc), "l"(bdesc), "r"(kEgIdesc), "r"(accumulate)
+      : "memory");
+}
+
+// EPI 0: C = acc + bias (fp32).  EPI 1: g = GELU(acc + bias) -> C_hi / C_lo (the operand of the next GEMM).
+template <int EPI>
+__global__ void __launch_bounds__(kEgThreads, 1)
+enc_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a_hi, const __grid_constant__ CUtensorMap tmap_a_lo,
+                   const __grid_constant__ CUtensorMap tmap_w_hi, const __grid_constant__ CUtensorMap tmap_w_lo,
+                   const float* __restrict__ bias, float* __restrict__ C, float* __restrict__ C_lo, int M, int N, int K) {
+  extern __shared__ unsigned char smem_raw[];
+  const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  unsigned char* smem = smem_raw + (base - smem_u32(smem_raw));
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kEgStages * kEgStageBytes);
+  uint64_t* full = bars;                       // [stages]
+  uint64_t* empty = bars + kEgStages;          // [stages]
+  uint64_t* tfull = bars + 2 * kEgStages;      // [1]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * kEgStages + 1);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int m0 = blockIdx.y * kEgBM, n0 = blockIdx.x * kEgBN;
+  const int nkb = K / kEgBK;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < kEgStages; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
+    mbar_init(tfull, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 0) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(128u) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      asm volatile("prefetch.tensormap [%0];" ::"l"(&tmap_a_hi) : "memory");
+      asm volatile("prefetch.tensormap [%0];" ::"l"(&tmap_a_lo) : "memory");
+      asm volatile("prefetch.tensormap [%0];" ::"l"(&tmap_w_hi) : "memory");
+      asm volatile("prefetch.tensormap [%0];" ::"l"(&tmap_w_lo) : "memory");
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int kb = 0; kb < nkb; ++kb) {
+        mbar_wait(&empty[stage], phase ^ 1u);
+        mbar_arrive_expect_tx(&full[stage], kEgStageBytes);
+        unsigned char* st = smem + stage * kEgStageBytes;
+        eg_tma_load_2d(st, &tmap_a_hi, kb * kEgBK, m0, &full[stage]);            // rows past M are zero-filled
+        eg_tma_load_2d(st + kEgBox, &tmap_a_lo, kb * kEgBK, m0, &full[stage]);
+        eg_tma_load_2d(st + 2 * kEgBox, &tmap_w_hi, kb * kEgBK, n0, &full[stage]);
+        eg_tma_load_2d(st + 3 * kEgBox, &tmap_w_lo, kb * kEgBK, n0, &full[stage]);
+        if (++stage == kEgStages) { stage = 0; phase ^= 1u; }
+      }
+    }
+    __syncwarp();
+  } else if (warp == 1) {
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int kb = 0; kb < nkb; ++kb) {
+        mbar_wait(&full[stage], phase);
+        tc_fence_after();
+        const uint32_t st = base + stage * kEgStageBytes;
+        const uint64_t a_hi = tc_smem_desc(st), a_lo = tc_smem_desc(st + kEgBox);
+        const uint64_t w_hi = tc_smem_desc(st + 2 * kEgBox), w_lo = tc_smem_desc(st + 3 * kEgBox);
+#pragma unroll
+        for (int k = 0; k < kEgBK / 8; ++k) {
+          const uint64_t o = static_cast<uint64_t>(2 * k);      // 8 tf32 = 32 B inside the swizzle atom
+          // small terms first, the dominant hi*hi product last
+          eg_mma_tf32(tmem_base, a_lo + o, w_hi + o, (kb | k) != 0 ? 1u : 0u);
+          eg_mma_tf32(tmem_base, a_hi + o, w_lo + o, 1u);
+          eg_mma_tf32(tmem_base, a_hi + o, w_hi + o, 1u);
+        }
+        eg_commit(&empty[stage]);
+        if (++stage == kEgStages) { stage = 0; phase ^= 1u; }
+      }
+      eg_commit(tfull);
+    }
+    __syncwarp();
+  } else {
+    const int quarter = warp & 3;                               // TMEM lanes [32*quarter, +32) belong to this warp
+    const int row = m0 + quarter * 32 + lane;
+    mbar_wait(tfull, 0u);
+    tc_fence_after();
+    const uint32_t taddr0 = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16);
+#pragma unroll 1
+    for (int c0 = 0; c0 < kEgBN; c0 += 32) {
+      uint32_t v[32];
+      tc_ld32(taddr0 + static_cast<uint32_t>(c0), v);
+      if (row < M) {
+        const int col = n0 + c0;
+        float* dst = C + static_cast<int64_t>(row) * N + col;
+        float* dst_lo = (EPI == 1) ? C_lo + static_cast<int64_t>(row) * N + col : nullptr;
+#pragma unroll
+        for (int j = 0; j < 32; j += 4) {
+          float o[4], l[4];
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            float x = __uint_as_float(v[j + e]) + (col + j + e < N ? __ldg(bias + col + j + e) : 0.0f);
+            if (EPI == 1) { x = gelu_erf(x); tf32_split(x, o[e], l[e]); } else { o[e] = x; }
+          }
+          if (col + j + 3 < N) {
+            *reinterpret_cast<float4*>(dst + j) = make_float4(o[0], o[1], o[2], o[3]);
+            if (EPI == 1) *reinterpret_cast<float4*>(dst_lo + j) = make_float4(l[0], l[1], l[2], l[3]);
+          } else {
+#pragma unroll
+            for (int e = 0; e < 4; ++e)
+              if (col + j + e < N) { dst[j + e] = o[e]; if (EPI == 1) dst_lo[j + e] = l[e]; }
+          }
+        }
+      }
+    }
+    tc_fence_before();
+  }
+  __syncthreads();
+  if (warp == 0) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(128u) : "memory");
+  }
 }
 
 }  // namespace rse

@@ -97,13 +97,22 @@ def test_minilm_query_encoder_matches_fp32_pytorch(minilm, fresh_index):
         e = _relerr(got, ref32)
         assert e <= 1e-5, f"pooled vectors differ from the fp32 PyTorch model by {e:.2e} (batch {seed})"
         assert np.abs(np.linalg.norm(got.astype(np.float64), axis=1) - 1.0).max() < 1e-6
-    # the bar in perspective: our error against an fp64 evaluation vs PyTorch-fp32's own
+    # the bar in perspective: our error against an fp64 evaluation vs PyTorch-fp32's own — for BOTH GEMM paths
+    # (0 = tcgen05 kind::tf32 with the 3-pass hi/lo split, the default; 1 = fp32 SIMT)
     ids, _ = _batch(7, 24, 3, 40, 30522)
     ref64 = _st_pipeline(minilm.double(), ids, torch.float64)
     minilm.float()
-    ours, theirs = _relerr(enc.encode_ids(ids), ref64), _relerr(_st_pipeline(minilm, ids, torch.float32), ref64)
-    print(f"error vs fp64: librse {ours:.2e}, PyTorch fp32 {theirs:.2e}")
-    assert ours <= 5e-6
+    theirs = _relerr(_st_pipeline(minilm, ids, torch.float32), ref64)
+    got = {}
+    for mode, name in ((0, "tcgen05 3xTF32"), (1, "fp32 SIMT")):
+        fresh_index.encoder_set_mode(enc.slot, mode)
+        got[mode] = enc.encode_ids(ids)
+        ours = _relerr(got[mode], ref64)
+        print(f"error vs fp64: librse {name} {ours:.2e}, PyTorch fp32 {theirs:.2e}")
+        assert ours <= 5e-6
+        assert _relerr(got[mode], _st_pipeline(minilm, ids, torch.float32)) <= 1e-5
+    assert _relerr(got[0], got[1]) <= 5e-6
+    fresh_index.encoder_set_mode(enc.slot, 0)
     # sequences longer than max_seq_length are truncated like the tokenizer would; an empty one is refused
     long_ids, _ = _batch(8, 2, 300, 300, 30522)
     assert np.array_equal(enc.encode_ids(long_ids), enc.encode_ids([x[:256] for x in long_ids]))
