@@ -366,19 +366,28 @@ __global__ void enc_positions_kernel(const int32_t* __restrict__ cu_seqlens, int
 // ================================================================ tensor-core GEMM with fp32 accuracy (3 x TF32)
 // The SIMT GEMM above is exact-ish but runs at ~19 TFLOP/s (r02 bench: 2.8 ms for a 256-query batch).  The
 // tensor cores have no fp32 mode; kind::tf32 keeps 10 mantissa bits of each operand, which alone is ~1e-3 off and
-// fails the 1e-5 bar.  The classic remedy: split every operand into hi = tf32(x) and lo = tf32(x - hi) and
-// accumulate  hi*hi + lo*hi + hi*lo  in the fp32 TMEM accumulator — the dropped lo*lo term is 2^-22 relative, the
-// truncation of lo another 2^-21: fp32-class accuracy at a third of the TF32 rate (still > 10x the SIMT kernel).
+// fails the 1e-5 bar.  The remedy (Ootomo & Yokota, "Recovering single precision accuracy from Tensor Cores"):
+//   (1) split every operand into hi = tf32(x) and lo = tf32(x - hi) and compute hi*hi + lo*hi + hi*lo (the dropped
+//       lo*lo term is 2^-22 relative);
+//   (2) do NOT accumulate everything in the tensor core: its fp32 accumulator is updated with truncation, a
+//       one-sided error that grows LINEARLY with the number of accumulation steps — the first version of this
+//       kernel (all 3*K/8 MMAs of a tile into one TMEM accumulator) was 2.2e-5 off the PyTorch fp32 model after 6
+//       layers, 20x worse than the SIMT kernel (9e-7).  So the dominant hi*hi products are accumulated in TMEM only
+//       over K-CHUNKS of 128 (16 MMAs), each chunk from zero into one of two chunk buffers, and the epilogue warps
+//       add the chunk sums into fp32 REGISTER accumulators (round-to-nearest, CUDA cores) while the next chunk is
+//       being computed; the two correction products, 2^-11 smaller, accumulate in a third TMEM buffer over the
+//       whole K (their truncation error is below 2^-30 relative).
 //   * weights are split once at load (enc_split_kernel), activations by the kernel that produces them
 //     (LayerNorm / attention / GELU epilogue write hi and lo next to or instead of the fp32 value);
 //   * one 128 x 128 output tile per CTA (cta_group::1): warp 0 = TMA producer (3-stage ring, per stage four
 //     128 x 32-float boxes: A_hi, A_lo, W_hi, W_lo, SWIZZLE_128B), warp 1 = single-thread tcgen05.mma issuer
 //     (12 MMAs of 128x128x8 per k-block: 4 k-steps x 3 products), warps 2-5 = epilogue (tcgen05.ld 32x32b, one
-//     TMEM lane = one token row per thread): bias (+ GELU + split) and 128-byte row stores.
+//     TMEM lane = one token row per thread, 128 accumulators in registers): bias (+ GELU + split), 128-byte stores.
 constexpr int kEgBM = 128, kEgBN = 128, kEgBK = 32, kEgStages = 3;
 constexpr int kEgBox = kEgBM * kEgBK * 4;                       // 16,384 B: one operand box
 constexpr int kEgStageBytes = 4 * kEgBox;                       // 65,536
 constexpr int kEgThreads = 192;
+constexpr int kEgChunkKB = 4;                                   // k-blocks per hi*hi accumulation chunk (K = 128)
 constexpr int kEgSmemBytes = kEgStages * kEgStageBytes + 16 * 8 + 16 + 1024;
 // kind::tf32: D = f32 (bit 4), A = B = tf32 (format 2), both K-major, N = 128, M = 128
 constexpr uint32_t kEgIdesc = (1u << 4) | (2u << 7) | (2u << 10) | ((kEgBN >> 3) << 17) | ((kEgBM >> 4) << 24);
@@ -424,25 +433,29 @@ enc_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a_hi, const __grid_c
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kEgStages * kEgStageBytes);
   uint64_t* full = bars;                       // [stages]
   uint64_t* empty = bars + kEgStages;          // [stages]
-  uint64_t* tfull = bars + 2 * kEgStages;      // [1]
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * kEgStages + 1);
+  uint64_t* cfull = bars + 2 * kEgStages;      // [2] hi*hi chunk buffer complete
+  uint64_t* cempty = bars + 2 * kEgStages + 2; // [2] the four epilogue warps drained it
+  uint64_t* sfull = bars + 2 * kEgStages + 4;  // [1] correction accumulator complete (= every MMA retired)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * kEgStages + 5);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int m0 = blockIdx.y * kEgBM, n0 = blockIdx.x * kEgBN;
   const int nkb = K / kEgBK;
+  const int nchunks = nkb / kEgChunkKB;        // K % 128 == 0 (checked on the host)
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < kEgStages; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
-    mbar_init(tfull, 1);
+    for (int b = 0; b < 2; ++b) { mbar_init(&cfull[b], 1); mbar_init(&cempty[b], 4); }
+    mbar_init(sfull, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 0) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(128u) : "memory");
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512u) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
-  const uint32_t tmem_base = *tmem_slot;
+  const uint32_t tmem_base = *tmem_slot;       // columns [0,128): corrections, [128,256) / [256,384): hi*hi chunks
 
   if (warp == 0) {
     if (lane == 0) {
@@ -468,36 +481,60 @@ enc_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a_hi, const __grid_c
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
-      for (int kb = 0; kb < nkb; ++kb) {
-        mbar_wait(&full[stage], phase);
+      for (int c = 0; c < nchunks; ++c) {
+        const uint32_t buf = c & 1, use = c >> 1;
+        mbar_wait(&cempty[buf], (use & 1u) ^ 1u);               // the epilogue has read this chunk buffer's last sums
         tc_fence_after();
-        const uint32_t st = base + stage * kEgStageBytes;
-        const uint64_t a_hi = tc_smem_desc(st), a_lo = tc_smem_desc(st + kEgBox);
-        const uint64_t w_hi = tc_smem_desc(st + 2 * kEgBox), w_lo = tc_smem_desc(st + 3 * kEgBox);
+        const uint32_t d_main = tmem_base + 128u * (1u + buf);
+        for (int kc = 0; kc < kEgChunkKB; ++kc) {
+          mbar_wait(&full[stage], phase);
+          tc_fence_after();
+          const uint32_t st = base + stage * kEgStageBytes;
+          const uint64_t a_hi = tc_smem_desc(st), a_lo = tc_smem_desc(st + kEgBox);
+          const uint64_t w_hi = tc_smem_desc(st + 2 * kEgBox), w_lo = tc_smem_desc(st + 3 * kEgBox);
 #pragma unroll
-        for (int k = 0; k < kEgBK / 8; ++k) {
-          const uint64_t o = static_cast<uint64_t>(2 * k);      // 8 tf32 = 32 B inside the swizzle atom
-          // small terms first, the dominant hi*hi product last
-          eg_mma_tf32(tmem_base, a_lo + o, w_hi + o, (kb | k) != 0 ? 1u : 0u);
-          eg_mma_tf32(tmem_base, a_hi + o, w_lo + o, 1u);
-          eg_mma_tf32(tmem_base, a_hi + o, w_hi + o, 1u);
+          for (int k = 0; k < kEgBK / 8; ++k) {
+            const uint64_t o = static_cast<uint64_t>(2 * k);    // 8 tf32 = 32 B inside the swizzle atom
+            eg_mma_tf32(tmem_base, a_lo + o, w_hi + o, (c | kc | k) != 0 ? 1u : 0u);
+            eg_mma_tf32(tmem_base, a_hi + o, w_lo + o, 1u);
+            eg_mma_tf32(d_main, a_hi + o, w_hi + o, (kc | k) != 0 ? 1u : 0u);
+          }
+          eg_commit(&empty[stage]);
+          if (++stage == kEgStages) { stage = 0; phase ^= 1u; }
         }
-        eg_commit(&empty[stage]);
-        if (++stage == kEgStages) { stage = 0; phase ^= 1u; }
+        eg_commit(&cfull[buf]);
       }
-      eg_commit(tfull);
+      eg_commit(sfull);
     }
     __syncwarp();
   } else {
     const int quarter = warp & 3;                               // TMEM lanes [32*quarter, +32) belong to this warp
     const int row = m0 + quarter * 32 + lane;
-    mbar_wait(tfull, 0u);
+    const uint32_t lane_addr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16);
+    float acc[kEgBN];
+#pragma unroll
+    for (int j = 0; j < kEgBN; ++j) acc[j] = 0.0f;
+    for (int c = 0; c < nchunks; ++c) {
+      const uint32_t buf = c & 1, use = c >> 1;
+      mbar_wait(&cfull[buf], use & 1u);
+      tc_fence_after();
+#pragma unroll
+      for (int c0 = 0; c0 < kEgBN; c0 += 32) {
+        uint32_t v[32];
+        tc_ld32(lane_addr + 128u * (1u + buf) + static_cast<uint32_t>(c0), v);
+#pragma unroll
+        for (int j = 0; j < 32; ++j) acc[c0 + j] += __uint_as_float(v[j]);      // fp32 add, round to nearest
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&cempty[buf]);
+    }
+    mbar_wait(sfull, 0u);
     tc_fence_after();
-    const uint32_t taddr0 = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16);
-#pragma unroll 1
+#pragma unroll
     for (int c0 = 0; c0 < kEgBN; c0 += 32) {
       uint32_t v[32];
-      tc_ld32(taddr0 + static_cast<uint32_t>(c0), v);
+      tc_ld32(lane_addr + static_cast<uint32_t>(c0), v);
       if (row < M) {
         const int col = n0 + c0;
         float* dst = C + static_cast<int64_t>(row) * N + col;
@@ -507,7 +544,7 @@ enc_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a_hi, const __grid_c
           float o[4], l[4];
 #pragma unroll
           for (int e = 0; e < 4; ++e) {
-            float x = __uint_as_float(v[j + e]) + (col + j + e < N ? __ldg(bias + col + j + e) : 0.0f);
+            float x = (acc[c0 + j + e] + __uint_as_float(v[j + e])) + (col + j + e < N ? __ldg(bias + col + j + e) : 0.0f);
             if (EPI == 1) { x = gelu_erf(x); tf32_split(x, o[e], l[e]); } else { o[e] = x; }
           }
           if (col + j + 3 < N) {
@@ -526,7 +563,7 @@ enc_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a_hi, const __grid_c
   __syncthreads();
   if (warp == 0) {
     tc_fence_after();
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(128u) : "memory");
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
   }
 }
 

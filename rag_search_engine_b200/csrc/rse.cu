@@ -2166,7 +2166,7 @@ int rse_encoder_finalize(rse_index* h, int32_t slot) {
                                       " tensors were set");
   // tf32 hi / lo halves of the weight matrices for the tensor-core GEMMs (every GEMM dimension must tile)
   const int64_t H = e.cfg.hidden, I = e.cfg.intermediate;
-  e.tc_ok = (H % kEgBN == 0) && (I % kEgBN == 0) && (H % kEgBK == 0) && (I % kEgBK == 0);
+  e.tc_ok = (H % kEgBN == 0) && (I % kEgBN == 0) && (H % (kEgBK * kEgChunkKB) == 0) && (I % (kEgBK * kEgChunkKB) == 0);
   if (e.tc_ok) {
     CK(cudaSetDevice(h->device));
     for (EncLayer& l : e.layers) {
