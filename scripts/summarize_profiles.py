@@ -82,7 +82,7 @@ def full(tag, rep):
                 i = hdr.index(m)
                 return float(row[i].replace(",", "")) * {"Gbyte": 1e9, "Mbyte": 1e6, "Kbyte": 1e3, "byte": 1}.get(units[i], 1)
             grid = row[hdr.index("Grid Size")] if "Grid Size" in hdr else ""
-            (ROOT / "profiles" / "r01_dominant_kernel_traffic.json").write_text(json.dumps({
+            (ROOT / "profiles" / f"{tag}_dominant_kernel_traffic.json").write_text(json.dumps({
                 "kernel": "knn_tc3_kernel<1> (filter)", "tc_kind": "f16-shadow", "rows": 4799462, "source": Path(rep).name,
                 "dram_bytes_read": val("dram__bytes_read.sum"), "dram_bytes_write": val("dram__bytes_write.sum"),
                 "gpu_time_ms_under_ncu": float(row[hdr.index("gpu__time_duration.sum")].replace(",", "")) *
