@@ -1007,9 +1007,40 @@ int rse_load_embeddings(rse_index* h, const float* emb_host, int64_t n_rows, int
   release_embeddings(h);
   const size_t bytes = sizeof(float) * static_cast<size_t>(std::max<int64_t>(n_rows, 1)) * dim;
   CK(cudaMalloc(&h->emb_owned, bytes));
-  if (n_rows > 0)
-    CK(cudaMemcpyAsync(h->emb_owned, emb_host, sizeof(float) * static_cast<size_t>(n_rows) * dim,
-                       cudaMemcpyHostToDevice, h->stream));
+  if (n_rows > 0) {
+    // The matrix usually arrives as a memory-mapped sidecar (store.load_or_export): gigabytes of PAGEABLE memory,
+    // possibly not yet in the page cache.  One cudaMemcpy of that stages through the driver's small bounce
+    // buffer and serialises page-in and transfer; here the host side is cut into 32 MB pieces that are copied
+    // into two pinned buffers alternately (the memcpy faults the next pages in) while the previous piece is on
+    // its way to the device.
+    const size_t total = sizeof(float) * static_cast<size_t>(n_rows) * dim;
+    const size_t piece = size_t(32) << 20;
+    if (total <= 2 * piece) {
+      CK(cudaMemcpyAsync(h->emb_owned, emb_host, total, cudaMemcpyHostToDevice, h->stream));
+    } else {
+      char* pin[2] = {nullptr, nullptr};
+      cudaEvent_t ev[2] = {nullptr, nullptr};
+      cudaError_t ce = cudaSuccess;
+      for (int i = 0; i < 2 && ce == cudaSuccess; ++i) {
+        ce = cudaMallocHost(reinterpret_cast<void**>(&pin[i]), piece);
+        if (ce == cudaSuccess) ce = cudaEventCreateWithFlags(&ev[i], cudaEventDisableTiming);
+      }
+      const char* src = reinterpret_cast<const char*>(emb_host);
+      char* dst = reinterpret_cast<char*>(h->emb_owned);
+      int b = 0;
+      for (size_t off = 0; off < total && ce == cudaSuccess; off += piece, b ^= 1) {
+        const size_t n = std::min(piece, total - off);
+        ce = cudaEventSynchronize(ev[b]);                       // this buffer's previous piece has left
+        if (ce != cudaSuccess) break;
+        std::memcpy(pin[b], src + off, n);
+        ce = cudaMemcpyAsync(dst + off, pin[b], n, cudaMemcpyHostToDevice, h->stream);
+        if (ce == cudaSuccess) ce = cudaEventRecord(ev[b], h->stream);
+      }
+      if (ce == cudaSuccess) ce = cudaStreamSynchronize(h->stream);
+      for (int i = 0; i < 2; ++i) { if (pin[i]) cudaFreeHost(pin[i]); if (ev[i]) cudaEventDestroy(ev[i]); }
+      if (ce != cudaSuccess) return fail(h, RSE_ERR_CUDA, std::string("rse_load_embeddings (chunked upload): ") + cudaGetErrorString(ce));
+    }
+  }
   h->emb = h->emb_owned;
   h->n_rows = n_rows; h->dim = dim; h->pos_base = static_cast<uint64_t>(pos_base);
   uint8_t* valid_dev = nullptr;
