@@ -3,7 +3,7 @@
 TEST INFRASTRUCTURE ONLY.  Only ``tests/``, ``__graft_entry__.smoke()`` and
 ``bench.py``'s ``cpu_baseline`` / ``--impl reference`` legs may import this
 package, and there only as the checker or the timed CPU baseline.  Nothing
-under ``rag_search_engine_b200/`` imports it (``tests/test_no_oracle_in_product.py``
+under ``rag_search_engine_b200/`` imports it (``tests/test_host_cpu.py::test_product_never_touches_the_oracle``
 enforces that).
 
 Parity status:

@@ -7,7 +7,10 @@ Layout
   keyword_search.py, semantic_search.py, hybrid_search.py
                    drop-in mirrors of the reference classes (same names, signatures, dicts)
   store.py         load-time exporter from the reference's SQLite file (+ writer of that format)
-  sharded.py       row-sharded multi-GPU plumbing (torch.distributed)
+  encoder.py       GpuSentenceEncoder / GpuCrossEncoder: the reference's MiniLM query encoder and TinyBERT
+                   cross-encoder on the device (csrc/encoder.cuh)
+  multimodal.py    MultimodalSearch mirror: CLIP image -> text ranking on the device
+  sharded.py       row-sharded multi-GPU drivers (library-owned NCCL communicator; torch.distributed for tests)
   synth.py         seeded synthetic corpora of the movies_600k shape
   cli.py           the reference CLI with these classes injected
 

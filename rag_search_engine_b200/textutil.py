@@ -4,7 +4,7 @@ These are NOT accelerated (chunk-text reconstruction and token
 on the host); they exist so the mirror classes return the same dict payloads as the
 reference.  Behaviour follows rag_search_engine/utils/utils.py:126-179 (``chunk`` /
 ``semantic_chunk``) and is checked against the reference's functions in
-tests/test_host_api.py when the reference checkout is present.
+tests/test_host_cpu.py when the reference checkout is present.
 """
 from __future__ import annotations
 
