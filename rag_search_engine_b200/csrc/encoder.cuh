@@ -383,14 +383,16 @@ __global__ void enc_positions_kernel(const int32_t* __restrict__ cu_seqlens, int
 //     128 x 32-float boxes: A_hi, A_lo, W_hi, W_lo, SWIZZLE_128B), warp 1 = single-thread tcgen05.mma issuer
 //     (12 MMAs of 128x128x8 per k-block: 4 k-steps x 3 products), warps 2-5 = epilogue (tcgen05.ld 32x32b, one
 //     TMEM lane = one token row per thread, 128 accumulators in registers): bias (+ GELU + split), 128-byte stores.
+// Output tile 128 x BN, BN = 128 or 64: the narrow tile is for GEMMs whose 128-wide tiling would leave most SMs idle
+// (MiniLM's N = 384 projections on a 2.5 k-token batch: 60 tiles for 148 SMs; 120 with BN = 64).
 constexpr int kEgBM = 128, kEgBN = 128, kEgBK = 32, kEgStages = 3;
-constexpr int kEgBox = kEgBM * kEgBK * 4;                       // 16,384 B: one operand box
-constexpr int kEgStageBytes = 4 * kEgBox;                       // 65,536
+constexpr int kEgBox = kEgBM * kEgBK * 4;                       // 16,384 B: one 128-row operand box
 constexpr int kEgThreads = 192;
 constexpr int kEgChunkKB = 4;                                   // k-blocks per hi*hi accumulation chunk (K = 128)
-constexpr int kEgSmemBytes = kEgStages * kEgStageBytes + 16 * 8 + 16 + 1024;
-// kind::tf32: D = f32 (bit 4), A = B = tf32 (format 2), both K-major, N = 128, M = 128
-constexpr uint32_t kEgIdesc = (1u << 4) | (2u << 7) | (2u << 10) | ((kEgBN >> 3) << 17) | ((kEgBM >> 4) << 24);
+__host__ __device__ constexpr int eg_stage_bytes(int bn) { return 2 * kEgBox + 2 * bn * kEgBK * 4; }
+__host__ __device__ constexpr int eg_smem_bytes(int bn) { return kEgStages * eg_stage_bytes(bn) + 16 * 8 + 16 + 1024; }
+// kind::tf32: D = f32 (bit 4), A = B = tf32 (format 2), both K-major, N = BN, M = 128
+__host__ __device__ constexpr uint32_t eg_idesc(int bn) { return (1u << 4) | (2u << 7) | (2u << 10) | ((static_cast<uint32_t>(bn) >> 3) << 17) | ((kEgBM >> 4) << 24); }
 
 __global__ void enc_split_kernel(const float* __restrict__ x, int64_t n, float* __restrict__ hi, float* __restrict__ lo) {
   const int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
@@ -410,19 +412,19 @@ __device__ __forceinline__ void eg_tma_load_2d(void* smem_dst, const CUtensorMap
 __device__ __forceinline__ void eg_commit(uint64_t* bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
-__device__ __forceinline__ void eg_mma_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t accumulate) {
+__device__ __forceinline__ void eg_mma_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
   asm volatile(
       "{\n"
       ".reg .pred p;\n"
       "setp.ne.b32 p, %4, 0;\n"
       "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n"
       "}\n" ::"r"(tmem_d),
-      "l"(adesc), "l"(bdesc), "r"(kEgIdesc), "r"(accumulate)
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
       : "memory");
 }
 
 // EPI 0: C = acc + bias (fp32).  EPI 1: g = GELU(acc + bias) -> C_hi / C_lo (the operand of the next GEMM).
-template <int EPI>
+template <int EPI, int BN>
 __global__ void __launch_bounds__(kEgThreads, 1)
 enc_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a_hi, const __grid_constant__ CUtensorMap tmap_a_lo,
                    const __grid_constant__ CUtensorMap tmap_w_hi, const __grid_constant__ CUtensorMap tmap_w_lo,
@@ -430,7 +432,11 @@ enc_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a_hi, const __grid_c
   extern __shared__ unsigned char smem_raw[];
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   unsigned char* smem = smem_raw + (base - smem_u32(smem_raw));
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kEgStages * kEgStageBytes);
+  constexpr int kStageBytes = eg_stage_bytes(BN);
+  constexpr int kWBox = BN * kEgBK * 4;
+  constexpr uint32_t kIdesc = eg_idesc(BN);
+  constexpr uint32_t kTmemCols = BN == 128 ? 512u : 256u;       // 3 x BN columns, rounded up to a power of two
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kEgStages * kStageBytes);
   uint64_t* full = bars;                       // [stages]
   uint64_t* empty = bars + kEgStages;          // [stages]
   uint64_t* cfull = bars + 2 * kEgStages;      // [2] hi*hi chunk buffer complete
@@ -438,7 +444,7 @@ enc_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a_hi, const __grid_c
   uint64_t* sfull = bars + 2 * kEgStages + 4;  // [1] correction accumulator complete (= every MMA retired)
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * kEgStages + 5);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int m0 = blockIdx.y * kEgBM, n0 = blockIdx.x * kEgBN;
+  const int m0 = blockIdx.y * kEgBM, n0 = blockIdx.x * BN;
   const int nkb = K / kEgBK;
   const int nchunks = nkb / kEgChunkKB;        // K % 128 == 0 (checked on the host)
 
@@ -449,13 +455,13 @@ enc_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a_hi, const __grid_c
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 0) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512u) : "memory");
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(kTmemCols) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
-  const uint32_t tmem_base = *tmem_slot;       // columns [0,128): corrections, [128,256) / [256,384): hi*hi chunks
+  const uint32_t tmem_base = *tmem_slot;       // columns [0,BN): corrections, [BN,2BN) / [2BN,3BN): hi*hi chunks
 
   if (warp == 0) {
     if (lane == 0) {
@@ -467,12 +473,12 @@ enc_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a_hi, const __grid_c
       uint32_t phase = 0;
       for (int kb = 0; kb < nkb; ++kb) {
         mbar_wait(&empty[stage], phase ^ 1u);
-        mbar_arrive_expect_tx(&full[stage], kEgStageBytes);
-        unsigned char* st = smem + stage * kEgStageBytes;
+        mbar_arrive_expect_tx(&full[stage], kStageBytes);
+        unsigned char* st = smem + stage * kStageBytes;
         eg_tma_load_2d(st, &tmap_a_hi, kb * kEgBK, m0, &full[stage]);            // rows past M are zero-filled
         eg_tma_load_2d(st + kEgBox, &tmap_a_lo, kb * kEgBK, m0, &full[stage]);
         eg_tma_load_2d(st + 2 * kEgBox, &tmap_w_hi, kb * kEgBK, n0, &full[stage]);
-        eg_tma_load_2d(st + 3 * kEgBox, &tmap_w_lo, kb * kEgBK, n0, &full[stage]);
+        eg_tma_load_2d(st + 2 * kEgBox + kWBox, &tmap_w_lo, kb * kEgBK, n0, &full[stage]);
         if (++stage == kEgStages) { stage = 0; phase ^= 1u; }
       }
     }
@@ -485,19 +491,19 @@ enc_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a_hi, const __grid_c
         const uint32_t buf = c & 1, use = c >> 1;
         mbar_wait(&cempty[buf], (use & 1u) ^ 1u);               // the epilogue has read this chunk buffer's last sums
         tc_fence_after();
-        const uint32_t d_main = tmem_base + 128u * (1u + buf);
+        const uint32_t d_main = tmem_base + static_cast<uint32_t>(BN) * (1u + buf);
         for (int kc = 0; kc < kEgChunkKB; ++kc) {
           mbar_wait(&full[stage], phase);
           tc_fence_after();
-          const uint32_t st = base + stage * kEgStageBytes;
+          const uint32_t st = base + stage * kStageBytes;
           const uint64_t a_hi = tc_smem_desc(st), a_lo = tc_smem_desc(st + kEgBox);
-          const uint64_t w_hi = tc_smem_desc(st + 2 * kEgBox), w_lo = tc_smem_desc(st + 3 * kEgBox);
+          const uint64_t w_hi = tc_smem_desc(st + 2 * kEgBox), w_lo = tc_smem_desc(st + 2 * kEgBox + kWBox);
 #pragma unroll
           for (int k = 0; k < kEgBK / 8; ++k) {
             const uint64_t o = static_cast<uint64_t>(2 * k);    // 8 tf32 = 32 B inside the swizzle atom
-            eg_mma_tf32(tmem_base, a_lo + o, w_hi + o, (c | kc | k) != 0 ? 1u : 0u);
-            eg_mma_tf32(tmem_base, a_hi + o, w_lo + o, 1u);
-            eg_mma_tf32(d_main, a_hi + o, w_hi + o, (kc | k) != 0 ? 1u : 0u);
+            eg_mma_tf32(tmem_base, a_lo + o, w_hi + o, kIdesc, (c | kc | k) != 0 ? 1u : 0u);
+            eg_mma_tf32(tmem_base, a_hi + o, w_lo + o, kIdesc, 1u);
+            eg_mma_tf32(d_main, a_hi + o, w_hi + o, kIdesc, (kc | k) != 0 ? 1u : 0u);
           }
           eg_commit(&empty[stage]);
           if (++stage == kEgStages) { stage = 0; phase ^= 1u; }
@@ -511,17 +517,17 @@ enc_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a_hi, const __grid_c
     const int quarter = warp & 3;                               // TMEM lanes [32*quarter, +32) belong to this warp
     const int row = m0 + quarter * 32 + lane;
     const uint32_t lane_addr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16);
-    float acc[kEgBN];
+    float acc[BN];
 #pragma unroll
-    for (int j = 0; j < kEgBN; ++j) acc[j] = 0.0f;
+    for (int j = 0; j < BN; ++j) acc[j] = 0.0f;
     for (int c = 0; c < nchunks; ++c) {
       const uint32_t buf = c & 1, use = c >> 1;
       mbar_wait(&cfull[buf], use & 1u);
       tc_fence_after();
 #pragma unroll
-      for (int c0 = 0; c0 < kEgBN; c0 += 32) {
+      for (int c0 = 0; c0 < BN; c0 += 32) {
         uint32_t v[32];
-        tc_ld32(lane_addr + 128u * (1u + buf) + static_cast<uint32_t>(c0), v);
+        tc_ld32(lane_addr + static_cast<uint32_t>(BN) * (1u + buf) + static_cast<uint32_t>(c0), v);
 #pragma unroll
         for (int j = 0; j < 32; ++j) acc[c0 + j] += __uint_as_float(v[j]);      // fp32 add, round to nearest
       }
@@ -532,7 +538,7 @@ enc_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a_hi, const __grid_c
     mbar_wait(sfull, 0u);
     tc_fence_after();
 #pragma unroll
-    for (int c0 = 0; c0 < kEgBN; c0 += 32) {
+    for (int c0 = 0; c0 < BN; c0 += 32) {
       uint32_t v[32];
       tc_ld32(lane_addr + static_cast<uint32_t>(c0), v);
       if (row < M) {
@@ -563,7 +569,7 @@ enc_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a_hi, const __grid_c
   __syncthreads();
   if (warp == 0) {
     tc_fence_after();
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(kTmemCols) : "memory");
   }
 }
 

@@ -79,6 +79,7 @@ struct rse_index {
   // K4 tensor-core path
   int tc_mode = 0;                 // 0 auto, 1 off (exact scan only), 2 force on
   bool second_chance = true;       // RSE_NO_SECOND_CHANCE=1 switches the second filter pass off (diagnostics)
+  int survivor_div = 3;            // probe sample density: expected first-pass survivors ~ cap / survivor_div (RSE_TC_SURVIVOR_DIV)
   // pending tensor-core batch (knn_local_begin / knn_local_finish)
   bool knn_pending = false;
   // rse_set_defer_flags: rse_knn_local_dev does not wait for the tensor-core path's overflow flags; they stay on
@@ -571,7 +572,7 @@ int knn_tc3_block(rse_index* h, const float* q_dev, const double* sb, int nqb, i
   // Probe sample: every tile_stride-th 256-row tile.  Expected survivors per query ≈ K' * tile_stride
   // (+ the 2*eps band), so the stride is as large as a third of the survivor cap allows, while the
   // sample keeps at least 64 tiles (and 8 K' rows) so its K'-th value is a meaningful bound.
-  int64_t tile_stride = std::max<int64_t>(1, std::min<int64_t>(kTcCandCap / (3ll * kprime), n_tiles / 64));
+  int64_t tile_stride = std::max<int64_t>(1, std::min<int64_t>(kTcCandCap / (static_cast<int64_t>(h->survivor_div) * kprime), n_tiles / 64));
   int64_t n_probe = (n_tiles + tile_stride - 1) / tile_stride;
   while (n_probe * kT3TileRows < 8ll * kprime && tile_stride > 1) { tile_stride /= 2; n_probe = (n_tiles + tile_stride - 1) / tile_stride; }
   const int64_t ld_probe = n_probe * kT3TileRows;
@@ -855,6 +856,7 @@ int rse_create(int32_t device, rse_index** out) {
   if (const char* ev = std::getenv("RSE_NO_OVERLAP")) h->overlap_enabled = !(ev[0] == '1');
   if (const char* ev = std::getenv("RSE_TIMELINE")) h->timeline = ev[0] == '1';
   if (const char* ev = std::getenv("RSE_NO_SECOND_CHANCE")) h->second_chance = !(ev[0] == '1');
+  if (const char* ev = std::getenv("RSE_TC_SURVIVOR_DIV")) { const int v = std::atoi(ev); if (v >= 1 && v <= 64) h->survivor_div = v; }
   *out = h;
   return RSE_OK;
 }
@@ -1936,7 +1938,7 @@ int enc_gemm(rse_index* h, const float* A, const float* W, const float* bias, fl
 }
 
 // [rows][K] row-major fp32 matrix, box = 32 floats (one 128-byte swizzle atom) x 128 rows
-int make_tmap_f32(rse_index* h, CUtensorMap* out, const float* base, int64_t rows, int64_t K) {
+int make_tmap_f32(rse_index* h, CUtensorMap* out, const float* base, int64_t rows, int64_t K, int box_rows) {
   static PFN_tmapEncodeTiled fn = nullptr;
   if (!fn) {
     void* p = nullptr;
@@ -1947,7 +1949,7 @@ int make_tmap_f32(rse_index* h, CUtensorMap* out, const float* base, int64_t row
   }
   const cuuint64_t gdim[2] = {static_cast<cuuint64_t>(K), static_cast<cuuint64_t>(rows)};
   const cuuint64_t gstr[1] = {static_cast<cuuint64_t>(K) * 4};
-  const cuuint32_t box[2] = {kEgBK, kEgBM};
+  const cuuint32_t box[2] = {kEgBK, static_cast<cuuint32_t>(box_rows)};
   const cuuint32_t estr[2] = {1, 1};
   CUresult r = fn(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(base), gdim, gstr, box, estr,
                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
@@ -1962,18 +1964,26 @@ template <int EPI>
 int enc_gemm_tc(rse_index* h, const float* A_hi, const float* A_lo, const float* W_hi, const float* W_lo, const float* bias,
                 float* C, float* C_lo, int M, int N, int K) {
   if (!(h->attr_mask & (1u << 17))) {
-    CK(cudaFuncSetAttribute(enc_gemm_tc_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, kEgSmemBytes));
-    CK(cudaFuncSetAttribute(enc_gemm_tc_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, kEgSmemBytes));
+    CK(cudaFuncSetAttribute(enc_gemm_tc_kernel<0, 128>, cudaFuncAttributeMaxDynamicSharedMemorySize, eg_smem_bytes(128)));
+    CK(cudaFuncSetAttribute(enc_gemm_tc_kernel<1, 128>, cudaFuncAttributeMaxDynamicSharedMemorySize, eg_smem_bytes(128)));
+    CK(cudaFuncSetAttribute(enc_gemm_tc_kernel<0, 64>, cudaFuncAttributeMaxDynamicSharedMemorySize, eg_smem_bytes(64)));
+    CK(cudaFuncSetAttribute(enc_gemm_tc_kernel<1, 64>, cudaFuncAttributeMaxDynamicSharedMemorySize, eg_smem_bytes(64)));
     h->attr_mask |= 1u << 17;
   }
+  // 128-wide tiles unless they would leave most of the SMs without one: then 64-wide (twice the CTAs)
+  const int m_tiles = (M + kEgBM - 1) / kEgBM;
+  const int bn = (m_tiles * (N / 128) >= h->sm_count || N % 64 != 0) ? 128 : 64;
   CUtensorMap ta_h, ta_l, tw_h, tw_l;
-  int rc = make_tmap_f32(h, &ta_h, A_hi, M, K);
-  if (rc == RSE_OK) rc = make_tmap_f32(h, &ta_l, A_lo, M, K);
-  if (rc == RSE_OK) rc = make_tmap_f32(h, &tw_h, W_hi, N, K);
-  if (rc == RSE_OK) rc = make_tmap_f32(h, &tw_l, W_lo, N, K);
+  int rc = make_tmap_f32(h, &ta_h, A_hi, M, K, kEgBM);
+  if (rc == RSE_OK) rc = make_tmap_f32(h, &ta_l, A_lo, M, K, kEgBM);
+  if (rc == RSE_OK) rc = make_tmap_f32(h, &tw_h, W_hi, N, K, bn);
+  if (rc == RSE_OK) rc = make_tmap_f32(h, &tw_l, W_lo, N, K, bn);
   if (rc != RSE_OK) return rc;
-  dim3 grid((N + kEgBN - 1) / kEgBN, (M + kEgBM - 1) / kEgBM);
-  enc_gemm_tc_kernel<EPI><<<grid, kEgThreads, kEgSmemBytes, h->stream>>>(ta_h, ta_l, tw_h, tw_l, bias, C, C_lo, M, N, K);
+  dim3 grid((N + bn - 1) / bn, m_tiles);
+  if (bn == 128)
+    enc_gemm_tc_kernel<EPI, 128><<<grid, kEgThreads, eg_smem_bytes(128), h->stream>>>(ta_h, ta_l, tw_h, tw_l, bias, C, C_lo, M, N, K);
+  else
+    enc_gemm_tc_kernel<EPI, 64><<<grid, kEgThreads, eg_smem_bytes(64), h->stream>>>(ta_h, ta_l, tw_h, tw_l, bias, C, C_lo, M, N, K);
   LAUNCHED(h);
   return RSE_OK;
 }

@@ -183,3 +183,69 @@ def test_bulk_encode_is_sliced_and_equal(minilm, fresh_index):
     whole = enc.encode_ids(ids)
     sliced = enc.encode_ids(ids, max_tokens_per_call=500)
     assert np.array_equal(whole, sliced) and whole.shape == (300, 384)
+
+
+def _word_ids(text, lo=1000, span=29000):
+    import zlib
+    return [101] + [lo + zlib.crc32(w.encode()) % span for w in text.lower().split()] + [102]
+
+
+def test_mirrors_take_the_gpu_encoders_through_the_reference_seams(minilm, tmp_path):
+    """The reference calls ``self.model.encode(texts)`` (semantic_search.py:221) and
+    ``CrossEncoder(...).predict(pairs)`` then sorts by (cross_encoder_score, score) (hybrid_search.py:296-309):
+    SemanticSearch(encoder=GpuSentenceEncoder) and HybridSearch(cross_encoder=GpuCrossEncoder) go through exactly
+    those seams, with the models on the GPU."""
+    from rag_search_engine_b200 import HybridSearch, runtime, store
+    from rag_search_engine_b200.encoder import TINYBERT_L2_CONFIG as C, GpuCrossEncoder, GpuSentenceEncoder, config_from_hf
+    from rag_search_engine_b200.textutil import whitespace_tokenizer
+    rng = np.random.default_rng(5)
+    words = [f"w{i}" for i in range(60)]
+    docs = [{"id": 7 + 3 * i, "title": " ".join(rng.choice(words, 2)).title(),
+             "description": " ".join(rng.choice(words, 12)) + ". " + " ".join(rng.choice(words, 9)) + "."} for i in range(120)]
+    db = tmp_path / "enc.db"
+    idx = runtime.acquire(db, 0)                       # the handle the mirrors will share
+    try:
+        enc = GpuSentenceEncoder(idx, minilm.state_dict(), config_from_hf(minilm.config),
+                                 tokenizer=lambda texts: [_word_ids(t) for t in texts])
+        store.write_reference_db(db, docs, whitespace_tokenizer, embed=enc.encode)        # chunk embeddings by the GPU encoder
+        cfg = transformers.BertConfig(vocab_size=C["vocab_size"], hidden_size=C["hidden"], num_hidden_layers=C["layers"],
+                                      num_attention_heads=C["heads"], intermediate_size=C["intermediate"],
+                                      max_position_embeddings=C["max_positions"], type_vocab_size=C["type_vocab"],
+                                      layer_norm_eps=C["ln_eps"], num_labels=1)
+        ce_model = _randomise(transformers.BertForSequenceClassification(cfg), 9)
+
+        def pair_tok(pairs):
+            ids, tts = [], []
+            for q, d in pairs:
+                a, b = _word_ids(q), _word_ids(d)[1:]
+                ids.append(a + b); tts.append([0] * len(a) + [1] * len(b))
+            return ids, tts
+        ce = GpuCrossEncoder(idx, ce_model.state_dict(), config_from_hf(ce_model.config), pair_tokenizer=pair_tok)
+        hs = HybridSearch(docs_path=None, db_path=db, tokenizer=whitespace_tokenizer, encoder=enc, cross_encoder=ce)
+        try:
+            q = "w3 w17 w5"
+            sem = hs.semantic.query_top_k(q, k=5)
+            assert len(sem) == 5 and sem == sorted(sem, key=lambda h: h["distance"])
+            # the query vector the mirror used == the encoder's own output (and a unit vector)
+            v = hs.semantic.generate_embedding(q)
+            assert v.shape == (1, 384) and abs(float(np.linalg.norm(v[0])) - 1.0) < 1e-6
+            base = hs.rrf_search(q, k=60, limit=8)
+            rr = hs.rrf_search(q, k=60, limit=8, rerank_method="cross_encoder")
+            assert sorted(d["id"] for d in rr) == sorted(d["id"] for d in base)
+            # the reference's own ordering rule, with the fp32 PyTorch cross-encoder as the oracle for the scores
+            pairs = [[q, f"{d.get('title', '')} - {d.get('description', '')}"] for d in base]
+            ids, tts = pair_tok(pairs)
+            x, mask = _pad(ids)
+            tt, _ = _pad(tts)
+            with torch.no_grad():
+                ref = ce_model(input_ids=x, attention_mask=mask, token_type_ids=tt).logits[:, 0].numpy()
+            by_id = {d["id"]: s for d, s in zip(base, ref)}
+            for d in rr:
+                assert abs(d["cross_encoder_score"] - by_id[d["id"]]) <= 1e-5 * max(1.0, abs(by_id[d["id"]]))
+            want = sorted(base, key=lambda d: (by_id[d["id"]], d["score"]), reverse=True)
+            assert [d["id"] for d in rr] == [d["id"] for d in want]
+            assert [d["rrf_rank"] for d in sorted(rr, key=lambda d: d["rrf_rank"])] == list(range(1, len(rr) + 1))
+        finally:
+            hs.close()
+    finally:
+        runtime.release(db, 0)
