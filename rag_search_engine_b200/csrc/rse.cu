@@ -79,7 +79,9 @@ struct rse_index {
   // K4 tensor-core path
   int tc_mode = 0;                 // 0 auto, 1 off (exact scan only), 2 force on
   bool second_chance = true;       // RSE_NO_SECOND_CHANCE=1 switches the second filter pass off (diagnostics)
-  int survivor_div = 3;            // probe sample density: expected first-pass survivors ~ cap / survivor_div (RSE_TC_SURVIVOR_DIV)
+  int survivor_div = 5;            // probe sample density: expected first-pass survivors ~ cap / survivor_div (RSE_TC_SURVIVOR_DIV).
+                                   // r02 sweep, ms per 256-query step, isotropic / clustered / dense-clustered S-600k:
+                                   // 3: 1.155 / 1.460 / 2.336   5: 1.146 / 1.223 / 1.785   8: 1.174 / 1.240 / 1.454
   // pending tensor-core batch (knn_local_begin / knn_local_finish)
   bool knn_pending = false;
   // rse_set_defer_flags: rse_knn_local_dev does not wait for the tensor-core path's overflow flags; they stay on

@@ -229,22 +229,28 @@ def test_mirrors_take_the_gpu_encoders_through_the_reference_seams(minilm, tmp_p
             # the query vector the mirror used == the encoder's own output (and a unit vector)
             v = hs.semantic.generate_embedding(q)
             assert v.shape == (1, 384) and abs(float(np.linalg.norm(v[0])) - 1.0) < 1e-6
-            base = hs.rrf_search(q, k=60, limit=8)
+            seen = []
+            orig_predict = ce.predict
+            ce.predict = lambda pairs, **kw: (seen.append([list(p) for p in pairs]), orig_predict(pairs, **kw))[1]
             rr = hs.rrf_search(q, k=60, limit=8, rerank_method="cross_encoder")
-            assert sorted(d["id"] for d in rr) == sorted(d["id"] for d in base)
-            # the reference's own ordering rule, with the fp32 PyTorch cross-encoder as the oracle for the scores
-            pairs = [[q, f"{d.get('title', '')} - {d.get('description', '')}"] for d in base]
+            ce.predict = orig_predict
+            # the reranker saw the WHOLE fused union (the reference truncates after reranking, :312), in RRF order
+            pairs = seen[0]
+            assert len(rr) == 8 and 8 <= len(pairs) <= 16 and all(p[0] == q for p in pairs)
+            text_to_id = {f"{d['title']} - {d['description']}": d["id"] for d in docs}
+            pair_ids = [text_to_id[p[1]] for p in pairs]
+            # the fp32 PyTorch cross-encoder is the oracle for the scores; the reference's rule orders them (:304-309)
             ids, tts = pair_tok(pairs)
             x, mask = _pad(ids)
             tt, _ = _pad(tts)
             with torch.no_grad():
                 ref = ce_model(input_ids=x, attention_mask=mask, token_type_ids=tt).logits[:, 0].numpy()
-            by_id = {d["id"]: s for d, s in zip(base, ref)}
+            by_id = dict(zip(pair_ids, ref))
             for d in rr:
                 assert abs(d["cross_encoder_score"] - by_id[d["id"]]) <= 1e-5 * max(1.0, abs(by_id[d["id"]]))
-            want = sorted(base, key=lambda d: (by_id[d["id"]], d["score"]), reverse=True)
-            assert [d["id"] for d in rr] == [d["id"] for d in want]
-            assert [d["rrf_rank"] for d in sorted(rr, key=lambda d: d["rrf_rank"])] == list(range(1, len(rr) + 1))
+            want = [pair_ids[i] for i in np.argsort(-ref, kind="stable")[:8]]
+            assert [d["id"] for d in rr] == want
+            assert all(d["rrf_rank"] == pair_ids.index(d["id"]) + 1 for d in rr)
         finally:
             hs.close()
     finally:
