@@ -66,7 +66,7 @@ knn_refine_kernel(const float* __restrict__ emb, const float* __restrict__ amag,
   __shared__ uint32_t s_rows[kTcRefineCap];
   const int qi = blockIdx.x;
   // second-chance pass: only the queries the second threshold kernel re-armed (thr2 finite), and only if any
-  if (thr2 != nullptr && (*gate == 0u || status[qi] == 0 || !(thr2[qi] < __int_as_float(0x7F800000)))) return;
+  if (thr2 != nullptr && (gate[qi >> 8] == 0u || status[qi] == 0 || !(thr2[qi] < __int_as_float(0x7F800000)))) return;
   const unsigned int cnt = cand_count[qi];
   long long* out = cand + static_cast<int64_t>(qi) * kprime * 3;
   // Survivor overflow (count > cap: the sample's K'-th value was a poor bound — a dense neighbourhood on a
@@ -120,7 +120,7 @@ knn_refine_kernel(const float* __restrict__ emb, const float* __restrict__ amag,
       if (cut2 > 1e-6f) {
         thr2_out[qi] = cut2;
         cand_count[qi] = 0u;
-        atomicAdd(gate_out, 1u);
+        atomicAdd(&gate_out[qi >> 8], 1u);                      // one gate per 256-query block
       }
       status[qi] = 1;
     }

@@ -348,7 +348,7 @@ tc3_probe_threshold_kernel(const uint32_t* __restrict__ dist, int64_t ld, int nq
   __shared__ unsigned int s_hist[256];
   __shared__ unsigned int s_prefix, s_need, s_fail, s_digit, s_before;
   __shared__ unsigned int s_warp[8];
-  const int q = blockIdx.x;
+  const int q = blockIdx.x;                        // grid = the padded query count (a multiple of 256)
   const float inf = __int_as_float(0x7F800000);
   if (q >= nq || !(sb[q] > 0.0 && sb[q] < 1e300)) {
     if (threadIdx.x == 0) thr[q] = inf;
@@ -402,16 +402,27 @@ tc3_probe_threshold_kernel(const uint32_t* __restrict__ dist, int64_t ld, int nq
 //                  batch and its three radix-select passes cost 0.19 ms; this one writes 1.2 MB.
 // MODE 1 (filter): all tiles; survivors appended to cand_pairs[q*cap + slot] = {local row, cos~}.  thr > 0
 //                  for every query (or +inf), so zero rows never survive.
+// QUERY BLOCKS (r02): one launch serves n_qblocks blocks of 256 queries — q16 / thr / dist / cand_* are indexed by
+//                  the global query qb*256 + q.  The CTA pair loops over the blocks: the producer reloads the
+//                  resident queries once the MMAs of the previous block have retired (qfree, a multicast commit),
+//                  the tile ring, the two accumulator buffers and their phases simply run on.  (r01 launched the
+//                  whole probe / threshold / filter / refine chain once per block from a host loop: a 2048-query
+//                  step on a shard was 40 launches, each paying launch latency, TMEM allocation and the pipeline
+//                  fill of a 0.1 ms pass.)  MODE 0 is only used with one block.
+// gate (MODE 1, second-chance pass): gate[qb] == 0 -> block qb is skipped by every role; all zero -> the kernel
+//                  returns before any barrier / TMEM allocation (enqueued unconditionally, rse.cu).
 // grid = 2 * n_clusters (<= 148), cluster = 2.
 template <int MODE>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kT3Threads, 1)
 knn_tc3_kernel(const __grid_constant__ CUtensorMap tmap_rows, const __grid_constant__ CUtensorMap tmap_q,
-               int64_t n_tiles, int64_t tile_stride, int nq, const float* __restrict__ thr,
+               int64_t n_tiles, int64_t tile_stride, int nq, int n_qblocks, const float* __restrict__ thr,
                uint32_t* __restrict__ dist, int64_t ld, uint2* __restrict__ cand_pairs,
                unsigned int* __restrict__ cand_count, int cap, const unsigned int* __restrict__ gate) {
-  // second-chance pass (rse.cu, knn_refine.cuh): enqueued unconditionally, runs only when the first refine pass
-  // armed a query.  Uniform over the grid and ahead of every barrier / TMEM allocation.
-  if (gate != nullptr && *gate == 0u) return;
+  if (gate != nullptr) {
+    bool any = false;
+    for (int b = 0; b < n_qblocks; ++b) any |= gate[b] != 0u;
+    if (!any) return;                              // uniform over the grid
+  }
   extern __shared__ unsigned char smem_raw[];
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   unsigned char* smem = smem_raw + (base - smem_u32(smem_raw));
@@ -423,7 +434,8 @@ knn_tc3_kernel(const __grid_constant__ CUtensorMap tmap_rows, const __grid_const
   uint64_t* tfull = bars + 2 * kT3Stages;         // [2] both CTAs: accumulator buffer complete
   uint64_t* tempty = bars + 2 * kT3Stages + 2;    // [2] leader: both CTAs' epilogues drained the buffer
   uint64_t* qfull = bars + 2 * kT3Stages + 4;     // [1] leader: both CTAs' query halves landed
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * kT3Stages + 5);
+  uint64_t* qfree = bars + 2 * kT3Stages + 5;     // [1] both CTAs: the MMAs that read the resident queries retired
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * kT3Stages + 6);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -437,6 +449,7 @@ knn_tc3_kernel(const __grid_constant__ CUtensorMap tmap_rows, const __grid_const
     for (int s = 0; s < kT3Stages; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
     for (int b = 0; b < 2; ++b) { mbar_init(&tfull[b], 1); mbar_init(&tempty[b], 2 * kT3EpiWarps); }
     mbar_init(qfull, 1);
+    mbar_init(qfree, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) {
@@ -456,27 +469,34 @@ knn_tc3_kernel(const __grid_constant__ CUtensorMap tmap_rows, const __grid_const
     if (lane == 0) {
       asm volatile("prefetch.tensormap [%0];" ::"l"(&tmap_rows) : "memory");
       asm volatile("prefetch.tensormap [%0];" ::"l"(&tmap_q) : "memory");
-      // my 128 queries, once
-      if (leader) mbar_arrive_expect_tx(qfull, 2 * kT3QBytes);
       const uint32_t lq = map_to_rank(qfull, 0u);
-#pragma unroll
-      for (int kb = 0; kb < kT3KBlocks; ++kb)
-        tma_load_2d_2sm(smem + kb * kT3StageBytes, &tmap_q, kb * kT3BK, static_cast<int>(rank) * kT3HalfRows, lq);
       int stage = 0;
       uint32_t phase = 0;
+      uint32_t nb = 0;                             // query blocks processed so far (skipped ones do not count)
       // (An L2 prefetch 6-18 stages ahead of the fill — cp.async.bulk.prefetch.tensor — changed nothing:
       // with every MMA but one per stage removed the same ring streams at 7.4 TB/s; the pass is bound by
       // the tensor pipe + TMEM reads, not by the fill.  r01 experiments)
       const int64_t my_tiles = (n_tiles - cluster_id + n_clusters - 1) / n_clusters;
       const int64_t my_stages = my_tiles * kT3KBlocks;
-      for (int64_t g = 0; g < my_stages; ++g) {
-        // my 128 rows of the tile = 6 contiguous 16 KB blocks of the tiled shadow (one per k-block)
-        const int64_t t = cluster_id + (g / kT3KBlocks) * n_clusters;
-        const int line = static_cast<int>(((t * tile_stride * 2 + rank) * kT3KBlocks + g % kT3KBlocks) * kT3HalfRows);
-        mbar_wait(&empty[stage], phase ^ 1u);
-        if (leader) mbar_arrive_expect_tx(&full[stage], 2 * kT3StageBytes);
-        tma_load_2d_2sm(ring + stage * kT3StageBytes, &tmap_rows, 0, line, map_to_rank(&full[stage], 0u));
-        if (++stage == kT3Stages) { stage = 0; phase ^= 1u; }
+      for (int qb = 0; qb < n_qblocks; ++qb) {
+        if (gate != nullptr && gate[qb] == 0u) continue;
+        // my 128 queries of this block (the previous block's MMAs must have retired: they read this memory)
+        if (nb > 0) mbar_wait(qfree, (nb - 1u) & 1u);
+        if (leader) mbar_arrive_expect_tx(qfull, 2 * kT3QBytes);
+#pragma unroll
+        for (int kb = 0; kb < kT3KBlocks; ++kb)
+          tma_load_2d_2sm(smem + kb * kT3StageBytes, &tmap_q, kb * kT3BK,
+                          qb * kTcBN + static_cast<int>(rank) * kT3HalfRows, lq);
+        for (int64_t g = 0; g < my_stages; ++g) {
+          // my 128 rows of the tile = 6 contiguous 16 KB blocks of the tiled shadow (one per k-block)
+          const int64_t t = cluster_id + (g / kT3KBlocks) * n_clusters;
+          const int line = static_cast<int>(((t * tile_stride * 2 + rank) * kT3KBlocks + g % kT3KBlocks) * kT3HalfRows);
+          mbar_wait(&empty[stage], phase ^ 1u);
+          if (leader) mbar_arrive_expect_tx(&full[stage], 2 * kT3StageBytes);
+          tma_load_2d_2sm(ring + stage * kT3StageBytes, &tmap_rows, 0, line, map_to_rank(&full[stage], 0u));
+          if (++stage == kT3Stages) { stage = 0; phase ^= 1u; }
+        }
+        ++nb;
       }
     }
     __syncwarp();                                  // reconverge before the aligned cluster barrier below
@@ -485,29 +505,34 @@ knn_tc3_kernel(const __grid_constant__ CUtensorMap tmap_rows, const __grid_const
     if (lane == 0 && leader) {
       int stage = 0;
       uint32_t phase = 0;
-      uint32_t it = 0;
-      mbar_wait(qfull, 0u);
-      tc_fence_after();
-      for (int64_t t = cluster_id; t < n_tiles; t += n_clusters, ++it) {
-        const uint32_t buf = it & 1u, use = it >> 1;
-        mbar_wait(&tempty[buf], (use & 1u) ^ 1u);  // both epilogues drained this buffer
+      uint32_t it = 0, nb = 0;
+      for (int qb = 0; qb < n_qblocks; ++qb) {
+        if (gate != nullptr && gate[qb] == 0u) continue;
+        mbar_wait(qfull, nb & 1u);
         tc_fence_after();
-        const uint32_t d_addr = tmem_base + buf * kT3TileRows;
-        for (int kb = 0; kb < kT3KBlocks; ++kb) {
-          mbar_wait(&full[stage], phase);
+        for (int64_t t = cluster_id; t < n_tiles; t += n_clusters, ++it) {
+          const uint32_t buf = it & 1u, use = it >> 1;
+          mbar_wait(&tempty[buf], (use & 1u) ^ 1u);  // both epilogues drained this buffer
           tc_fence_after();
-          const uint64_t adesc = tc_smem_desc(base + kb * kT3StageBytes);                      // queries
-          const uint64_t bdesc = tc_smem_desc(base + kT3QBytes + stage * kT3StageBytes);       // rows
+          const uint32_t d_addr = tmem_base + buf * kT3TileRows;
+          for (int kb = 0; kb < kT3KBlocks; ++kb) {
+            mbar_wait(&full[stage], phase);
+            tc_fence_after();
+            const uint64_t adesc = tc_smem_desc(base + kb * kT3StageBytes);                      // queries
+            const uint64_t bdesc = tc_smem_desc(base + kT3QBytes + stage * kT3StageBytes);       // rows
 #pragma unroll
-          for (int k = 0; k < kT3BK / 16; ++k) {
-            // advance 16 halves = 32 B inside the swizzle atom: +2 in the (>>4) start-address field
-            tc3_mma_f16(d_addr, adesc + static_cast<uint64_t>(2 * k), bdesc + static_cast<uint64_t>(2 * k), kT3Idesc,
-                        (kb | k) != 0 ? 1u : 0u);
+            for (int k = 0; k < kT3BK / 16; ++k) {
+              // advance 16 halves = 32 B inside the swizzle atom: +2 in the (>>4) start-address field
+              tc3_mma_f16(d_addr, adesc + static_cast<uint64_t>(2 * k), bdesc + static_cast<uint64_t>(2 * k), kT3Idesc,
+                          (kb | k) != 0 ? 1u : 0u);
+            }
+            tc2_commit_mc(&empty[stage]);            // both CTAs may refill this stage
+            if (++stage == kT3Stages) { stage = 0; phase ^= 1u; }
           }
-          tc2_commit_mc(&empty[stage]);            // both CTAs may refill this stage
-          if (++stage == kT3Stages) { stage = 0; phase ^= 1u; }
+          tc2_commit_mc(&tfull[buf]);                // accumulator complete in both CTAs
         }
-        tc2_commit_mc(&tfull[buf]);                // accumulator complete in both CTAs
+        tc2_commit_mc(qfree);                        // every MMA that reads this block's queries has been issued: the
+        ++nb;                                        // barrier flips in both CTAs when they retire
       }
     }
     __syncwarp();
@@ -516,17 +541,20 @@ knn_tc3_kernel(const __grid_constant__ CUtensorMap tmap_rows, const __grid_const
     const int ew = warp - 2;                       // 0..7
     const int quarter = warp & 3;                  // TMEM lanes [32*quarter, +32) belong to this warp
     const int col_half = ew >> 2;                  // which 128 columns (rows of the tile)
-    const int qi = static_cast<int>(rank) * kT3HalfRows + quarter * 32 + lane;
-    const float my_thr = (MODE == 1) ? __ldg(thr + qi) : 0.0f;
+    const int qi0 = static_cast<int>(rank) * kT3HalfRows + quarter * 32 + lane;   // my query inside a block
     uint32_t* qrow = s_queue + ew * 3 * kT3QueueCap;
     uint32_t* qcount = s_queue + kT3EpiWarps * 3 * kT3QueueCap + ew;
     T3Queue qu;
     qu.row = qrow; qu.val = qrow + kT3QueueCap; qu.qid = qrow + 2 * kT3QueueCap; qu.count = qcount;
+    uint32_t it = 0;
+    for (int qb = 0; qb < n_qblocks; ++qb) {
+    if (gate != nullptr && gate[qb] == 0u) continue;
+    const int qi = qb * kTcBN + qi0;               // global query
+    const float my_thr = (MODE == 1) ? __ldg(thr + qi) : 0.0f;
     const T3Sink sink{qrow, qcount, static_cast<uint32_t>(qi), cand_pairs, cand_count, cap};
     float top[kT3ProbeTop];
 #pragma unroll
     for (int i = 0; i < kT3ProbeTop; ++i) top[i] = -3.0f;                    // below any cosine
-    uint32_t it = 0;
     for (int64_t t = cluster_id; t < n_tiles; t += n_clusters, ++it) {
       const uint32_t buf = it & 1u, use = it >> 1;
       mbar_wait(&tfull[buf], use & 1u);
@@ -603,6 +631,7 @@ knn_tc3_kernel(const __grid_constant__ CUtensorMap tmap_rows, const __grid_const
       for (int i = 0; i < kT3ProbeTop; ++i)
         o[i] = top[i] > -2.0f ? __float_as_uint(1.0f - top[i]) : 0x7FFFFFFFu;
     }
+    }                                              // query blocks
   }
 
   tc_fence_before();

@@ -72,6 +72,7 @@ struct rse_index {
   // synchronising; resolved lazily in rse_get_stats (after the caller's sync).
   std::vector<cudaEvent_t> scan_ev;   // 2 per timed launch
   size_t scan_ev_used = 0;
+  std::vector<int> scan_ev_passes;    // K4: how many 256-query passes each timed filter launch covered (else 1)
   // staged hybrid query batch (rse_hybrid_stage)
   int staged_nq = 0;
   // rse_hybrid_stash: staged batches parked in HBM (a bench / server rotating over several resident batches)
@@ -149,6 +150,8 @@ struct rse_index {
   CUtensorMap tmap_a16{};          // [n_rows][384] f16, box {64, 128}, SWIZZLE_128B
   CUtensorMap tmap_q16{};          // [256][384] f16, box {64, 128}
   bool tmap_q16_ok = false;
+  int tmap_q16_rows = 0;
+  const void* tmap_q16_base = nullptr;
 
   // ---- a1: embeddings (vec0 physical layout)
   const float* emb = nullptr;
@@ -354,6 +357,7 @@ int knn_exact_groups(rse_index* h, const float* q_dev, const double* sb, int nq,
       e0 = h->scan_ev[h->scan_ev_used];
       e1 = h->scan_ev[h->scan_ev_used + 1];
       h->scan_ev_used += 2;
+      h->scan_ev_passes.push_back(1);
       CK(cudaEventRecord(e0, h->stream));
     }
     int rc = h->fma ? launch_scan<true>(h, q_dev + static_cast<int64_t>(g0) * h->dim, sb + g0, ng, dist)
@@ -546,8 +550,12 @@ int enqueue_bm25_overlapped(rse_index* h, cudaEvent_t after) {
   return RSE_OK;
 }
 
-// ---- K4 over the fp16 shadow (knn_tc3.cuh) for one block of ≤ 256 queries
-int knn_tc3_block(rse_index* h, const float* q_dev, const double* sb, int nqb, int kprime, long long* cand_dev,
+// ---- K4 over the fp16 shadow (knn_tc3.cuh) for a GROUP of up to kTcGroupBlocks blocks of 256 queries: one launch
+// per stage (query prep, probe, thresholds, filter, refine, gated second filter + refine) whatever the number of
+// blocks — r01 ran the whole chain once per block from a host loop.
+constexpr int kTcGroupBlocks = 8;                 // 2048 queries per group: 134 MB of survivor lists
+
+int knn_tc3_group(rse_index* h, const float* q_dev, const double* sb, int nqg, int kprime, long long* cand_dev,
                   int* status_dev) {
   if (!(h->attr_mask & (1u << 11))) {
     CK(cudaFuncSetAttribute(knn_tc3_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, kT3SmemBytes));
@@ -558,72 +566,81 @@ int knn_tc3_block(rse_index* h, const float* q_dev, const double* sb, int nqb, i
     CK(cudaFuncSetAttribute(knn_tc3_kernel<1>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
     h->attr_mask |= 1u << 11;
   }
-  ENSURE(h->tc_q16, sizeof(__half) * kTcBN * kScanD);
-  if (!h->tmap_q16_ok) {
-    int rc = make_tmap_any(h, &h->tmap_q16, h->tc_q16.p, kTcBN, kT3HalfRows, 2);
-    if (rc != RSE_OK) return rc;
-    h->tmap_q16_ok = true;
-  }
-  ENSURE(h->tc_thr, sizeof(float) * 2 * kTcBN);               // [0, 256): first-pass thresholds, [256, 512): second chance
-  ENSURE(h->tc_rows, sizeof(uint2) * static_cast<size_t>(kTcBN) * kTcCandCap);
-  ENSURE(h->tc_cnt, sizeof(unsigned int) * (kTcBN + 4));      // [256]: the second-chance gate
-  ENSURE(h->sel, sizeof(SelState) * kTcBN);
-
   const int64_t n_tiles = (h->n_rows + kT3TileRows - 1) / kT3TileRows;
   const int max_clusters = std::max(1, h->sm_count / 2);
   // Probe sample: every tile_stride-th 256-row tile.  Expected survivors per query ≈ K' * tile_stride
-  // (+ the 2*eps band), so the stride is as large as a third of the survivor cap allows, while the
+  // (+ the 2*eps band), so the stride is as large as a fifth (survivor_div) of the survivor cap allows, while the
   // sample keeps at least 64 tiles (and 8 K' rows) so its K'-th value is a meaningful bound.
   int64_t tile_stride = std::max<int64_t>(1, std::min<int64_t>(kTcCandCap / (static_cast<int64_t>(h->survivor_div) * kprime), n_tiles / 64));
   int64_t n_probe = (n_tiles + tile_stride - 1) / tile_stride;
   while (n_probe * kT3TileRows < 8ll * kprime && tile_stride > 1) { tile_stride /= 2; n_probe = (n_tiles + tile_stride - 1) / tile_stride; }
   const int64_t ld_probe = n_probe * kT3TileRows;
+  const int probe_clusters = static_cast<int>(std::min<int64_t>(max_clusters, n_probe));
+  const int grid_p = 2 * probe_clusters;
+  const bool sparse_probe = kprime <= 256 && static_cast<int64_t>(probe_clusters) * 2 * kT3ProbeTop >= 4ll * kprime &&
+                            static_cast<int64_t>(probe_clusters) * 2 * kT3ProbeTop <= kT3SelMax;
+  // the dense probe (K' > 256, tiny corpora) keeps its per-query sample matrix and radix select: one block at a time
+  if (!sparse_probe && nqg > kTcBN) {
+    for (int b0 = 0; b0 < nqg; b0 += kTcBN) {
+      const int nqb = std::min(kTcBN, nqg - b0);
+      int rc = knn_tc3_group(h, q_dev + static_cast<int64_t>(b0) * h->dim, sb + b0, nqb, kprime,
+                             cand_dev + static_cast<int64_t>(b0) * kprime * 3, status_dev + b0);
+      if (rc != RSE_OK) return rc;
+    }
+    return RSE_OK;
+  }
+  const int nblk = (nqg + kTcBN - 1) / kTcBN;
+  const int nq_pad = nblk * kTcBN;
+  ENSURE(h->tc_q16, sizeof(__half) * static_cast<size_t>(nq_pad) * kScanD);
+  if (!h->tmap_q16_ok || h->tmap_q16_rows != nq_pad || h->tmap_q16_base != h->tc_q16.p) {
+    int rc = make_tmap_any(h, &h->tmap_q16, h->tc_q16.p, nq_pad, kT3HalfRows, 2);
+    if (rc != RSE_OK) return rc;
+    h->tmap_q16_ok = true; h->tmap_q16_rows = nq_pad; h->tmap_q16_base = h->tc_q16.p;
+  }
+  ENSURE(h->tc_thr, sizeof(float) * 2 * nq_pad);              // [0, nq_pad): first-pass thresholds, then the second chance's
+  ENSURE(h->tc_rows, sizeof(uint2) * static_cast<size_t>(nq_pad) * kTcCandCap);
+  ENSURE(h->tc_cnt, sizeof(unsigned int) * (nq_pad + kTcGroupBlocks + 4));   // [nq_pad ...): one second-chance gate per block
+  ENSURE(h->sel, sizeof(SelState) * kTcBN);
+  int64_t ld_sel = sparse_probe ? static_cast<int64_t>(probe_clusters) * 2 * kT3ProbeTop : ld_probe;
   ENSURE(h->dist, std::max(sizeof(float) * static_cast<size_t>(kScanMaxQB) * h->dist_ld,
-                           sizeof(uint32_t) * static_cast<size_t>(nqb) * ld_probe));
+                           sizeof(uint32_t) * static_cast<size_t>(nq_pad) * ld_sel));
   uint32_t* dist = static_cast<uint32_t*>(h->dist.p);
   SelState* sel = static_cast<SelState*>(h->sel.p);
   unsigned int* hist = static_cast<unsigned int*>(h->hist.p);
   __half* q16 = static_cast<__half*>(h->tc_q16.p);
   float* thr = static_cast<float*>(h->tc_thr.p);
 
-  tc3_query_prep_kernel<<<kTcBN, kScanD / 4, 0, h->stream>>>(q_dev, sb, nqb, q16);
+  tc3_query_prep_kernel<<<nq_pad, kScanD / 4, 0, h->stream>>>(q_dev, sb, nqg, q16);
   LAUNCHED(h);
 
   // 1. probe: approximate distances of a strided sample of tiles → K'-th smallest per query
-  const int probe_clusters = static_cast<int>(std::min<int64_t>(max_clusters, n_probe));
-  const int grid_p = 2 * probe_clusters;
-  const bool sparse_probe = kprime <= 256 && static_cast<int64_t>(probe_clusters) * 2 * kT3ProbeTop >= 4ll * kprime;
-  int64_t ld_sel = ld_probe;
   if (sparse_probe) {
-    ld_sel = static_cast<int64_t>(probe_clusters) * 2 * kT3ProbeTop;
     knn_tc3_kernel<2><<<grid_p, kT3Threads, kT3SmemBytes, h->stream>>>(
-        h->tmap_a16, h->tmap_q16, n_probe, tile_stride, nqb, nullptr, dist, ld_sel, nullptr, nullptr, 0, nullptr);
-  } else {
-    knn_tc3_kernel<0><<<grid_p, kT3Threads, kT3SmemBytes, h->stream>>>(
-        h->tmap_a16, h->tmap_q16, n_probe, tile_stride, nqb, nullptr, dist, ld_probe, nullptr, nullptr, 0, nullptr);
-  }
-  LAUNCHED(h);
-  if (sparse_probe && ld_sel <= kT3SelMax) {
-    tc3_probe_threshold_kernel<<<kTcBN, 256, 0, h->stream>>>(dist, ld_sel, nqb, kprime, sb, thr);
+        h->tmap_a16, h->tmap_q16, n_probe, tile_stride, nqg, nblk, nullptr, dist, ld_sel, nullptr, nullptr, 0, nullptr);
+    LAUNCHED(h);
+    tc3_probe_threshold_kernel<<<nq_pad, 256, 0, h->stream>>>(dist, ld_sel, nqg, kprime, sb, thr);
     LAUNCHED(h);
   } else {
-    select_init_kernel<<<(nqb + 127) / 128, 128, 0, h->stream>>>(sel, nqb, static_cast<unsigned int>(kprime));
+    knn_tc3_kernel<0><<<grid_p, kT3Threads, kT3SmemBytes, h->stream>>>(
+        h->tmap_a16, h->tmap_q16, n_probe, tile_stride, nqg, 1, nullptr, dist, ld_probe, nullptr, nullptr, 0, nullptr);
+    LAUNCHED(h);
+    select_init_kernel<<<(nqg + 127) / 128, 128, 0, h->stream>>>(sel, nqg, static_cast<unsigned int>(kprime));
     LAUNCHED(h);
     int blocks = static_cast<int>(std::min<int64_t>((ld_sel + 4095) / 4096, h->sm_count));
     if (blocks < 1) blocks = 1;
-    dim3 grid(blocks, nqb);
+    dim3 grid(blocks, nqg);
     static const int shifts[3] = {53, 42, 32};
     static const int widths[3] = {11, 11, 10};
     for (int p = 0; p < 3; ++p) {
       select_pass_kernel<<<grid, kSelThreads, 0, h->stream>>>(dist, ld_sel, ld_sel, 0ull, sel, hist, shifts[p], widths[p]);
       LAUNCHED(h);
     }
-    tc3_threshold_kernel<<<2, 128, 0, h->stream>>>(sel, sb, nqb, thr);
+    tc3_threshold_kernel<<<2, 128, 0, h->stream>>>(sel, sb, nqg, thr);
     LAUNCHED(h);
   }
 
-  // 2. filter pass over all rows
-  CK(cudaMemsetAsync(h->tc_cnt.p, 0, sizeof(unsigned int) * (kTcBN + 4), h->stream));
+  // 2. filter pass over all rows (nblk passes in one launch)
+  CK(cudaMemsetAsync(h->tc_cnt.p, 0, sizeof(unsigned int) * (nq_pad + kTcGroupBlocks + 4), h->stream));
   const int grid_f = 2 * static_cast<int>(std::min<int64_t>(max_clusters, n_tiles));
   cudaEvent_t e0 = nullptr, e1 = nullptr;
   if (h->timing && h->scan_ev_used + 2 <= (1u << 16)) {
@@ -636,7 +653,7 @@ int knn_tc3_block(rse_index* h, const float* q_dev, const double* sb, int nqb, i
   }
   tl_mark(h, kTlPrefilter, h->stream);
   knn_tc3_kernel<1><<<grid_f, kT3Threads, kT3SmemBytes, h->stream>>>(
-      h->tmap_a16, h->tmap_q16, n_tiles, 1, nqb, thr, nullptr, 0, static_cast<uint2*>(h->tc_rows.p),
+      h->tmap_a16, h->tmap_q16, n_tiles, 1, nqg, nblk, thr, nullptr, 0, static_cast<uint2*>(h->tc_rows.p),
       static_cast<unsigned int*>(h->tc_cnt.p), kTcCandCap, nullptr);
   LAUNCHED(h);
   tl_mark(h, kTlFilterEnd, h->stream);
@@ -647,27 +664,28 @@ int knn_tc3_block(rse_index* h, const float* q_dev, const double* sb, int nqb, i
   if (e0) {
     int rc = scan_event(h, &e1);
     if (rc != RSE_OK) return rc;
+    h->scan_ev_passes.push_back(nblk);                        // this event pair covers nblk 256-query passes
   }
   h->stats.knn_scan_launches++;
-  h->stats.tc_filter_launches++;
+  h->stats.tc_filter_launches += nblk;
 
   // 3. refine on the approximate values, 4. exact re-score + sort + emit (one CTA per query); a query whose
   //    survivor list overflowed arms the second chance instead (thr2 from the survivors that were kept)
-  float* thr2 = thr + kTcBN;
-  unsigned int* gate = static_cast<unsigned int*>(h->tc_cnt.p) + kTcBN;
+  float* thr2 = thr + nq_pad;
+  unsigned int* gate = static_cast<unsigned int*>(h->tc_cnt.p) + nq_pad;
   {
-    int rc = knn_tc_refine(h, q_dev, sb, nqb, kprime, cand_dev, status_dev, nullptr, nullptr,
+    int rc = knn_tc_refine(h, q_dev, sb, nqg, kprime, cand_dev, status_dev, nullptr, nullptr,
                            h->second_chance ? thr2 : nullptr, h->second_chance ? gate : nullptr);
     if (rc != RSE_OK) return rc;
   }
   if (!h->second_chance) return RSE_OK;
-  // 5. second chance: one more filter pass + refine for the armed queries only.  Enqueued unconditionally, gated on
-  //    the device: two near-empty launches when no query needs it.
+  // 5. second chance: one more filter pass + refine for the armed queries only (blocks without one are skipped).
+  //    Enqueued unconditionally, gated on the device: two near-empty launches when no query needs it.
   knn_tc3_kernel<1><<<grid_f, kT3Threads, kT3SmemBytes, h->stream>>>(
-      h->tmap_a16, h->tmap_q16, n_tiles, 1, nqb, thr2, nullptr, 0, static_cast<uint2*>(h->tc_rows.p),
+      h->tmap_a16, h->tmap_q16, n_tiles, 1, nqg, nblk, thr2, nullptr, 0, static_cast<uint2*>(h->tc_rows.p),
       static_cast<unsigned int*>(h->tc_cnt.p), kTcCandCap, gate);
   LAUNCHED(h);
-  return knn_tc_refine(h, q_dev, sb, nqb, kprime, cand_dev, status_dev, thr2, gate, nullptr, nullptr);
+  return knn_tc_refine(h, q_dev, sb, nqg, kprime, cand_dev, status_dev, thr2, gate, nullptr, nullptr);
 }
 
 bool tc_eligible(const rse_index* h, int nq, int kprime) {
@@ -708,9 +726,9 @@ int knn_local_begin(rse_index* h, const float* q_dev, int nq, int kprime, long l
     if (rc != RSE_OK) return rc;
     if (h->shadow_state < 0) return knn_exact_groups(h, q_dev, sb, nq, kprime, cand_dev);
   }
-  for (int b0 = 0; b0 < nq; b0 += kTcBN) {
-    const int nqb = std::min(kTcBN, nq - b0);
-    int rc = knn_tc3_block(h, q_dev + static_cast<int64_t>(b0) * h->dim, sb + b0, nqb, kprime,
+  for (int b0 = 0; b0 < nq; b0 += kTcGroupBlocks * kTcBN) {
+    const int nqg = std::min(kTcGroupBlocks * kTcBN, nq - b0);
+    int rc = knn_tc3_group(h, q_dev + static_cast<int64_t>(b0) * h->dim, sb + b0, nqg, kprime,
                            cand_dev + static_cast<int64_t>(b0) * kprime * 3, status + b0);
     if (rc != RSE_OK) return rc;
   }
@@ -969,9 +987,11 @@ int rse_get_stats(rse_index* h, rse_stats* out) {
       float ms = 0.f;
       CK(cudaEventElapsedTime(&ms, h->scan_ev[i], h->scan_ev[i + 1]));
       h->stats.scan_ms_total += ms;
-      h->stats.scan_launches_timed++;
+      // a multi-block K4 launch counts as that many passes, so scan_ms_total / scan_launches_timed stays "per pass"
+      h->stats.scan_launches_timed += (i / 2 < h->scan_ev_passes.size()) ? h->scan_ev_passes[i / 2] : 1;
     }
     h->scan_ev_used = 0;
+    h->scan_ev_passes.clear();
   }
   if (h->dev_counters) {
     unsigned long long c[4] = {0, 0, 0, 0};
@@ -993,6 +1013,7 @@ int rse_stats_reset(rse_index* h) {
   const int dim = h->stats.emb_dim;
   h->stats = rse_stats{};
   h->scan_ev_used = 0;
+  h->scan_ev_passes.clear();
   if (h->dev_counters) {
     CK(cudaStreamSynchronize(h->stream));
     if (h->stream_b) CK(cudaStreamSynchronize(h->stream_b));
