@@ -377,16 +377,12 @@ __global__ void enc_positions_kernel(const int32_t* __restrict__ cu_seqlens, int
 //       add the chunk sums into fp32 REGISTER accumulators (round-to-nearest, CUDA cores) while the next chunk is
 //       being computed; the two correction products, 2^-11 smaller, accumulate in a third TMEM buffer over the
 //       whole K (their truncation error is below 2^-30 relative).
-//   * the split happens IN SHARED MEMORY: TMA brings the plain fp32 boxes (A: 128 x 32 floats, W: BN x 32,
-//     SWIZZLE_128B) and warps 2-5 rewrite each in place as hi and write lo to a second buffer — an elementwise
-//     transform, so the swizzled layout does not matter — then fence.proxy.async + mbarrier hand the stage to the
-//     MMA thread.  (The first version kept hi and lo copies of weights and activations in global memory and loaded
-//     four boxes per k-block: the GEMMs were L2-bound at 64 KB per k-block per CTA, ~7 TB/s over the grid.)
-//   * one 128 x BN output tile per CTA (cta_group::1): warp 0 = TMA producer (3-stage ring), warp 1 = single-thread
-//     tcgen05.mma issuer (12 MMAs of 128xBNx8 per k-block: 4 k-steps x 3 products), warps 2-5 = splitter +
-//     epilogue (tcgen05.ld 32x32b, one TMEM lane = one token row per thread, BN accumulators in registers; the
-//     chunk sums are added two k-blocks behind the split so the MMAs always have split stages queued): bias
-//     (+ GELU), 128-byte row stores.
+//   * weights are split once at load (enc_split_kernel), activations by the kernel that produces them
+//     (LayerNorm / attention / GELU epilogue write hi and lo next to or instead of the fp32 value);
+//   * one 128 x 128 output tile per CTA (cta_group::1): warp 0 = TMA producer (3-stage ring, per stage four
+//     128 x 32-float boxes: A_hi, A_lo, W_hi, W_lo, SWIZZLE_128B), warp 1 = single-thread tcgen05.mma issuer
+//     (12 MMAs of 128x128x8 per k-block: 4 k-steps x 3 products), warps 2-5 = epilogue (tcgen05.ld 32x32b, one
+//     TMEM lane = one token row per thread, 128 accumulators in registers): bias (+ GELU + split), 128-byte stores.
 // Output tile 128 x BN, BN = 128 or 64: the narrow tile is for GEMMs whose 128-wide tiling would leave most SMs idle
 // (MiniLM's N = 384 projections on a 2.5 k-token batch: 60 tiles for 148 SMs; 120 with BN = 64).
 constexpr int kEgBM = 128, kEgBN = 128, kEgBK = 32, kEgStages = 3;
@@ -394,9 +390,17 @@ constexpr int kEgBox = kEgBM * kEgBK * 4;                       // 16,384 B: one
 constexpr int kEgThreads = 192;
 constexpr int kEgChunkKB = 4;                                   // k-blocks per hi*hi accumulation chunk (K = 128)
 __host__ __device__ constexpr int eg_stage_bytes(int bn) { return 2 * kEgBox + 2 * bn * kEgBK * 4; }
-__host__ __device__ constexpr int eg_smem_bytes(int bn) { return kEgStages * eg_stage_bytes(bn) + 24 * 8 + 16 + 1024; }
+__host__ __device__ constexpr int eg_smem_bytes(int bn) { return kEgStages * eg_stage_bytes(bn) + 16 * 8 + 16 + 1024; }
 // kind::tf32: D = f32 (bit 4), A = B = tf32 (format 2), both K-major, N = BN, M = 128
 __host__ __device__ constexpr uint32_t eg_idesc(int bn) { return (1u << 4) | (2u << 7) | (2u << 10) | ((static_cast<uint32_t>(bn) >> 3) << 17) | ((kEgBM >> 4) << 24); }
+
+__global__ void enc_split_kernel(const float* __restrict__ x, int64_t n, float* __restrict__ hi, float* __restrict__ lo) {
+  const int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  float h, l;
+  tf32_split(x[i], h, l);
+  hi[i] = h; lo[i] = l;
+}
 
 __device__ __forceinline__ void eg_tma_load_2d(void* smem_dst, const CUtensorMap* tmap, int c0, int c1, uint64_t* bar) {
   asm volatile(
@@ -419,34 +423,33 @@ __device__ __forceinline__ void eg_mma_tf32(uint32_t tmem_d, uint64_t adesc, uin
       : "memory");
 }
 
-// EPI 0: C = acc + bias.  EPI 1: C = GELU(acc + bias).
+// EPI 0: C = acc + bias (fp32).  EPI 1: g = GELU(acc + bias) -> C_hi / C_lo (the operand of the next GEMM).
 template <int EPI, int BN>
 __global__ void __launch_bounds__(kEgThreads, 1)
-enc_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_w,
-                   const float* __restrict__ bias, float* __restrict__ C, int M, int N, int K) {
+enc_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a_hi, const __grid_constant__ CUtensorMap tmap_a_lo,
+                   const __grid_constant__ CUtensorMap tmap_w_hi, const __grid_constant__ CUtensorMap tmap_w_lo,
+                   const float* __restrict__ bias, float* __restrict__ C, float* __restrict__ C_lo, int M, int N, int K) {
   extern __shared__ unsigned char smem_raw[];
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   unsigned char* smem = smem_raw + (base - smem_u32(smem_raw));
-  constexpr int kStageBytes = eg_stage_bytes(BN);               // [A hi (raw lands here) | A lo | W hi (raw) | W lo]
+  constexpr int kStageBytes = eg_stage_bytes(BN);
   constexpr int kWBox = BN * kEgBK * 4;
   constexpr uint32_t kIdesc = eg_idesc(BN);
   constexpr uint32_t kTmemCols = BN == 128 ? 512u : 256u;       // 3 x BN columns, rounded up to a power of two
-  constexpr int kSplitLead = 2;                                 // chunk sums are added this many k-blocks behind the split
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kEgStages * kStageBytes);
-  uint64_t* raw = bars;                        // [stages] TMA landed the fp32 boxes
-  uint64_t* full = bars + kEgStages;           // [stages] the four splitter warps wrote hi / lo
-  uint64_t* empty = bars + 2 * kEgStages;      // [stages] the MMAs reading the stage retired
-  uint64_t* cfull = bars + 3 * kEgStages;      // [2] hi*hi chunk buffer complete
-  uint64_t* cempty = bars + 3 * kEgStages + 2; // [2] the four epilogue warps drained it
-  uint64_t* sfull = bars + 3 * kEgStages + 4;  // [1] correction accumulator complete (= every MMA retired)
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 3 * kEgStages + 5);
+  uint64_t* full = bars;                       // [stages]
+  uint64_t* empty = bars + kEgStages;          // [stages]
+  uint64_t* cfull = bars + 2 * kEgStages;      // [2] hi*hi chunk buffer complete
+  uint64_t* cempty = bars + 2 * kEgStages + 2; // [2] the four epilogue warps drained it
+  uint64_t* sfull = bars + 2 * kEgStages + 4;  // [1] correction accumulator complete (= every MMA retired)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * kEgStages + 5);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int m0 = blockIdx.y * kEgBM, n0 = blockIdx.x * BN;
   const int nkb = K / kEgBK;
   const int nchunks = nkb / kEgChunkKB;        // K % 128 == 0 (checked on the host)
 
   if (threadIdx.x == 0) {
-    for (int s = 0; s < kEgStages; ++s) { mbar_init(&raw[s], 1); mbar_init(&full[s], 4); mbar_init(&empty[s], 1); }
+    for (int s = 0; s < kEgStages; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
     for (int b = 0; b < 2; ++b) { mbar_init(&cfull[b], 1); mbar_init(&cempty[b], 4); }
     mbar_init(sfull, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -462,16 +465,20 @@ enc_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
 
   if (warp == 0) {
     if (lane == 0) {
-      asm volatile("prefetch.tensormap [%0];" ::"l"(&tmap_a) : "memory");
-      asm volatile("prefetch.tensormap [%0];" ::"l"(&tmap_w) : "memory");
+      asm volatile("prefetch.tensormap [%0];" ::"l"(&tmap_a_hi) : "memory");
+      asm volatile("prefetch.tensormap [%0];" ::"l"(&tmap_a_lo) : "memory");
+      asm volatile("prefetch.tensormap [%0];" ::"l"(&tmap_w_hi) : "memory");
+      asm volatile("prefetch.tensormap [%0];" ::"l"(&tmap_w_lo) : "memory");
       int stage = 0;
       uint32_t phase = 0;
       for (int kb = 0; kb < nkb; ++kb) {
         mbar_wait(&empty[stage], phase ^ 1u);
-        mbar_arrive_expect_tx(&raw[stage], kEgBox + kWBox);
+        mbar_arrive_expect_tx(&full[stage], kStageBytes);
         unsigned char* st = smem + stage * kStageBytes;
-        eg_tma_load_2d(st, &tmap_a, kb * kEgBK, m0, &raw[stage]);                // rows past M are zero-filled
-        eg_tma_load_2d(st + 2 * kEgBox, &tmap_w, kb * kEgBK, n0, &raw[stage]);
+        eg_tma_load_2d(st, &tmap_a_hi, kb * kEgBK, m0, &full[stage]);            // rows past M are zero-filled
+        eg_tma_load_2d(st + kEgBox, &tmap_a_lo, kb * kEgBK, m0, &full[stage]);
+        eg_tma_load_2d(st + 2 * kEgBox, &tmap_w_hi, kb * kEgBK, n0, &full[stage]);
+        eg_tma_load_2d(st + 2 * kEgBox + kWBox, &tmap_w_lo, kb * kEgBK, n0, &full[stage]);
         if (++stage == kEgStages) { stage = 0; phase ^= 1u; }
       }
     }
@@ -486,7 +493,7 @@ enc_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
         tc_fence_after();
         const uint32_t d_main = tmem_base + static_cast<uint32_t>(BN) * (1u + buf);
         for (int kc = 0; kc < kEgChunkKB; ++kc) {
-          mbar_wait(&full[stage], phase);                       // hi / lo written (generic proxy) and fenced
+          mbar_wait(&full[stage], phase);
           tc_fence_after();
           const uint32_t st = base + stage * kStageBytes;
           const uint64_t a_hi = tc_smem_desc(st), a_lo = tc_smem_desc(st + kEgBox);
@@ -508,13 +515,12 @@ enc_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
     __syncwarp();
   } else {
     const int quarter = warp & 3;                               // TMEM lanes [32*quarter, +32) belong to this warp
-    const int te = threadIdx.x - 64;                            // 0..127 among the splitter / epilogue threads
     const int row = m0 + quarter * 32 + lane;
     const uint32_t lane_addr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16);
     float acc[BN];
 #pragma unroll
     for (int j = 0; j < BN; ++j) acc[j] = 0.0f;
-    auto add_chunk = [&](int c) {
+    for (int c = 0; c < nchunks; ++c) {
       const uint32_t buf = c & 1, use = c >> 1;
       mbar_wait(&cfull[buf], use & 1u);
       tc_fence_after();
@@ -528,40 +534,7 @@ enc_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&cempty[buf]);
-    };
-    int stage = 0, chunks_done = 0;
-    uint32_t phase = 0;
-    for (int kb = 0; kb < nkb; ++kb) {
-      // ---- split this stage's fp32 boxes into tf32 hi (in place) and lo
-      mbar_wait(&raw[stage], phase);
-      float4* a_hi = reinterpret_cast<float4*>(smem + stage * kStageBytes);
-      float4* a_lo = a_hi + kEgBox / 16;
-      float4* w_hi = a_hi + 2 * (kEgBox / 16);
-      float4* w_lo = w_hi + kWBox / 16;
-#pragma unroll
-      for (int j = 0; j < kEgBox / 16 / 128; ++j) {
-        const int i = te + 128 * j;
-        const float4 x = a_hi[i];
-        float4 h, l;
-        tf32_split(x.x, h.x, l.x); tf32_split(x.y, h.y, l.y); tf32_split(x.z, h.z, l.z); tf32_split(x.w, h.w, l.w);
-        a_hi[i] = h; a_lo[i] = l;
-      }
-#pragma unroll
-      for (int j = 0; j < kWBox / 16 / 128; ++j) {
-        const int i = te + 128 * j;
-        const float4 x = w_hi[i];
-        float4 h, l;
-        tf32_split(x.x, h.x, l.x); tf32_split(x.y, h.y, l.y); tf32_split(x.z, h.z, l.z); tf32_split(x.w, h.w, l.w);
-        w_hi[i] = h; w_lo[i] = l;
-      }
-      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");     // generic-proxy writes -> visible to tcgen05.mma
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&full[stage]);
-      if (++stage == kEgStages) { stage = 0; phase ^= 1u; }
-      // ---- chunk sums, kSplitLead k-blocks behind: every split the chunk's MMAs need is long done
-      if (kb >= kSplitLead && ((kb - kSplitLead) % kEgChunkKB) == kEgChunkKB - 1) { add_chunk((kb - kSplitLead) / kEgChunkKB); ++chunks_done; }
     }
-    for (int c = chunks_done; c < nchunks; ++c) add_chunk(c);
     mbar_wait(sfull, 0u);
     tc_fence_after();
 #pragma unroll
@@ -571,20 +544,22 @@ enc_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
       if (row < M) {
         const int col = n0 + c0;
         float* dst = C + static_cast<int64_t>(row) * N + col;
+        float* dst_lo = (EPI == 1) ? C_lo + static_cast<int64_t>(row) * N + col : nullptr;
 #pragma unroll
         for (int j = 0; j < 32; j += 4) {
-          float o[4];
+          float o[4], l[4];
 #pragma unroll
           for (int e = 0; e < 4; ++e) {
             float x = (acc[c0 + j + e] + __uint_as_float(v[j + e])) + (col + j + e < N ? __ldg(bias + col + j + e) : 0.0f);
-            o[e] = (EPI == 1) ? gelu_erf(x) : x;
+            if (EPI == 1) { x = gelu_erf(x); tf32_split(x, o[e], l[e]); } else { o[e] = x; }
           }
           if (col + j + 3 < N) {
             *reinterpret_cast<float4*>(dst + j) = make_float4(o[0], o[1], o[2], o[3]);
+            if (EPI == 1) *reinterpret_cast<float4*>(dst_lo + j) = make_float4(l[0], l[1], l[2], l[3]);
           } else {
 #pragma unroll
             for (int e = 0; e < 4; ++e)
-              if (col + j + e < N) dst[j + e] = o[e];
+              if (col + j + e < N) { dst[j + e] = o[e]; if (EPI == 1) dst_lo[j + e] = l[e]; }
           }
         }
       }

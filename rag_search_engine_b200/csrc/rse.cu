@@ -37,6 +37,9 @@ struct DevBuf {
 struct EncLayer {
   float *wqkv = nullptr, *bqkv = nullptr, *wo = nullptr, *bo = nullptr, *ln1g = nullptr, *ln1b = nullptr;
   float *wi = nullptr, *bi = nullptr, *wo2 = nullptr, *bo2 = nullptr, *ln2g = nullptr, *ln2b = nullptr;
+  // tf32 hi / lo halves of the four weight matrices (the tensor-core GEMM, encoder.cuh), written by finalize
+  float *wqkv_h = nullptr, *wqkv_l = nullptr, *wo_h = nullptr, *wo_l = nullptr;
+  float *wi_h = nullptr, *wi_l = nullptr, *wo2_h = nullptr, *wo2_l = nullptr;
 };
 struct Encoder {
   rse_encoder_config cfg{};
@@ -46,6 +49,7 @@ struct Encoder {
   std::vector<EncLayer> layers;
   std::set<std::string> seen;
   DevBuf ids, type_ids, cu, posidx, x, qkv, ctx, tmp, ff, out;
+  DevBuf x_h, x_l, ctx_l, ff_l;       // hi / lo activations of the tensor-core path (ctx / ff hold the hi halves there)
   int mode = 0;                       // 0 = tcgen05 3xTF32 GEMMs (when every GEMM dimension is a multiple of 128 / 32),
                                       // 1 = fp32 SIMT GEMMs
   bool tc_ok = false;
@@ -275,10 +279,12 @@ void release_bm25(rse_index* h) {
 void enc_release(Encoder& e) {
   for (float** p : {&e.word, &e.pos, &e.type, &e.elng, &e.elnb, &e.poolw, &e.poolb, &e.clsw, &e.clsb}) free_ptr(*p);
   for (auto& l : e.layers)
-    for (float** p : {&l.wqkv, &l.bqkv, &l.wo, &l.bo, &l.ln1g, &l.ln1b, &l.wi, &l.bi, &l.wo2, &l.bo2, &l.ln2g, &l.ln2b}) free_ptr(*p);
+    for (float** p : {&l.wqkv, &l.bqkv, &l.wo, &l.bo, &l.ln1g, &l.ln1b, &l.wi, &l.bi, &l.wo2, &l.bo2, &l.ln2g, &l.ln2b,
+                      &l.wqkv_h, &l.wqkv_l, &l.wo_h, &l.wo_l, &l.wi_h, &l.wi_l, &l.wo2_h, &l.wo2_l}) free_ptr(*p);
   e.layers.clear();
   e.seen.clear();
-  for (DevBuf* b : {&e.ids, &e.type_ids, &e.cu, &e.posidx, &e.x, &e.qkv, &e.ctx, &e.tmp, &e.ff, &e.out}) free_buf(*b);
+  for (DevBuf* b : {&e.ids, &e.type_ids, &e.cu, &e.posidx, &e.x, &e.qkv, &e.ctx, &e.tmp, &e.ff, &e.out, &e.x_h, &e.x_l,
+                    &e.ctx_l, &e.ff_l}) free_buf(*b);
   if (e.pin_in) cudaFreeHost(e.pin_in);
   e.pin_in = nullptr; e.pin_in_n = 0;
   e.created = e.finalized = false;
@@ -1975,11 +1981,11 @@ int make_tmap_f32(rse_index* h, CUtensorMap* out, const float* base, int64_t row
   return RSE_OK;
 }
 
-// tensor-core GEMM: C[M, N] = A[M, K] . W[N, K]^T + bias (EPI 1: GELU), fp32 operands split into tf32 hi / lo in
-// shared memory (encoder.cuh)
+// tensor-core GEMM: C[M, N] = (A_hi + A_lo)[M, K] . (W_hi + W_lo)[N, K]^T + bias; EPI 1: GELU -> C (hi), C_lo
 extern "C++" {
 template <int EPI>
-int enc_gemm_tc(rse_index* h, const float* A, const float* W, const float* bias, float* C, int M, int N, int K) {
+int enc_gemm_tc(rse_index* h, const float* A_hi, const float* A_lo, const float* W_hi, const float* W_lo, const float* bias,
+                float* C, float* C_lo, int M, int N, int K) {
   if (!(h->attr_mask & (1u << 17))) {
     CK(cudaFuncSetAttribute(enc_gemm_tc_kernel<0, 128>, cudaFuncAttributeMaxDynamicSharedMemorySize, eg_smem_bytes(128)));
     CK(cudaFuncSetAttribute(enc_gemm_tc_kernel<1, 128>, cudaFuncAttributeMaxDynamicSharedMemorySize, eg_smem_bytes(128)));
@@ -1990,15 +1996,17 @@ int enc_gemm_tc(rse_index* h, const float* A, const float* W, const float* bias,
   // 128-wide tiles unless they would leave most of the SMs without one: then 64-wide (twice the CTAs)
   const int m_tiles = (M + kEgBM - 1) / kEgBM;
   const int bn = (m_tiles * (N / 128) >= h->sm_count || N % 64 != 0) ? 128 : 64;
-  CUtensorMap ta, tw;
-  int rc = make_tmap_f32(h, &ta, A, M, K, kEgBM);
-  if (rc == RSE_OK) rc = make_tmap_f32(h, &tw, W, N, K, bn);
+  CUtensorMap ta_h, ta_l, tw_h, tw_l;
+  int rc = make_tmap_f32(h, &ta_h, A_hi, M, K, kEgBM);
+  if (rc == RSE_OK) rc = make_tmap_f32(h, &ta_l, A_lo, M, K, kEgBM);
+  if (rc == RSE_OK) rc = make_tmap_f32(h, &tw_h, W_hi, N, K, bn);
+  if (rc == RSE_OK) rc = make_tmap_f32(h, &tw_l, W_lo, N, K, bn);
   if (rc != RSE_OK) return rc;
   dim3 grid((N + bn - 1) / bn, m_tiles);
   if (bn == 128)
-    enc_gemm_tc_kernel<EPI, 128><<<grid, kEgThreads, eg_smem_bytes(128), h->stream>>>(ta, tw, bias, C, M, N, K);
+    enc_gemm_tc_kernel<EPI, 128><<<grid, kEgThreads, eg_smem_bytes(128), h->stream>>>(ta_h, ta_l, tw_h, tw_l, bias, C, C_lo, M, N, K);
   else
-    enc_gemm_tc_kernel<EPI, 64><<<grid, kEgThreads, eg_smem_bytes(64), h->stream>>>(ta, tw, bias, C, M, N, K);
+    enc_gemm_tc_kernel<EPI, 64><<<grid, kEgThreads, eg_smem_bytes(64), h->stream>>>(ta_h, ta_l, tw_h, tw_l, bias, C, C_lo, M, N, K);
   LAUNCHED(h);
   return RSE_OK;
 }
@@ -2015,11 +2023,21 @@ int enc_forward(rse_index* h, Encoder& e, int n_seq, int T, bool has_types, floa
   ENSURE(e.ctx, sizeof(float) * static_cast<size_t>(T) * H);
   ENSURE(e.tmp, sizeof(float) * static_cast<size_t>(T) * H);
   ENSURE(e.ff, sizeof(float) * static_cast<size_t>(T) * I);
+  if (tc) {
+    ENSURE(e.x_h, sizeof(float) * static_cast<size_t>(T) * H);
+    ENSURE(e.x_l, sizeof(float) * static_cast<size_t>(T) * H);
+    ENSURE(e.ctx_l, sizeof(float) * static_cast<size_t>(T) * H);
+    ENSURE(e.ff_l, sizeof(float) * static_cast<size_t>(T) * I);
+  }
   float* x = static_cast<float*>(e.x.p);
   float* qkv = static_cast<float*>(e.qkv.p);
   float* ctx = static_cast<float*>(e.ctx.p);
   float* tmp = static_cast<float*>(e.tmp.p);
   float* ff = static_cast<float*>(e.ff.p);
+  float* x_h = tc ? static_cast<float*>(e.x_h.p) : nullptr;
+  float* x_l = tc ? static_cast<float*>(e.x_l.p) : nullptr;
+  float* ctx_l = tc ? static_cast<float*>(e.ctx_l.p) : nullptr;
+  float* ff_l = tc ? static_cast<float*>(e.ff_l.p) : nullptr;
   const int32_t* cu = static_cast<const int32_t*>(e.cu.p);
   enc_positions_kernel<<<(T + 255) / 256, 256, 0, h->stream>>>(cu, n_seq, T, static_cast<int32_t*>(e.posidx.p));
   LAUNCHED(h);
@@ -2027,25 +2045,29 @@ int enc_forward(rse_index* h, Encoder& e, int n_seq, int T, bool has_types, floa
   enc_embed_ln_kernel<<<tok_grid, 128, 0, h->stream>>>(
       static_cast<const int32_t*>(e.ids.p), has_types ? static_cast<const int32_t*>(e.type_ids.p) : nullptr,
       static_cast<const int32_t*>(e.posidx.p), T, H, c.vocab_size, c.max_positions, c.type_vocab, e.word, e.pos, e.type,
-      e.elng, e.elnb, c.ln_eps, x, nullptr, nullptr);
+      e.elng, e.elnb, c.ln_eps, x, x_h, x_l);
   LAUNCHED(h);
   const int hd = H / c.heads;
   for (const EncLayer& l : e.layers) {
-    int rc = tc ? enc_gemm_tc<0>(h, x, l.wqkv, l.bqkv, qkv, T, 3 * H, H) : enc_gemm<0>(h, x, l.wqkv, l.bqkv, qkv, T, 3 * H, H);
+    int rc = tc ? enc_gemm_tc<0>(h, x_h, x_l, l.wqkv_h, l.wqkv_l, l.bqkv, qkv, nullptr, T, 3 * H, H)
+                : enc_gemm<0>(h, x, l.wqkv, l.bqkv, qkv, T, 3 * H, H);
     if (rc != RSE_OK) return rc;
     dim3 agrid(n_seq, c.heads);
-    if (hd == 32) enc_attention_kernel<32><<<agrid, 128, 0, h->stream>>>(qkv, cu, H, ctx, nullptr);
-    else enc_attention_kernel<64><<<agrid, 128, 0, h->stream>>>(qkv, cu, H, ctx, nullptr);
+    if (hd == 32) enc_attention_kernel<32><<<agrid, 128, 0, h->stream>>>(qkv, cu, H, ctx, ctx_l);
+    else enc_attention_kernel<64><<<agrid, 128, 0, h->stream>>>(qkv, cu, H, ctx, ctx_l);
     LAUNCHED(h);
-    rc = tc ? enc_gemm_tc<0>(h, ctx, l.wo, l.bo, tmp, T, H, H) : enc_gemm<0>(h, ctx, l.wo, l.bo, tmp, T, H, H);
+    rc = tc ? enc_gemm_tc<0>(h, ctx, ctx_l, l.wo_h, l.wo_l, l.bo, tmp, nullptr, T, H, H)
+            : enc_gemm<0>(h, ctx, l.wo, l.bo, tmp, T, H, H);
     if (rc != RSE_OK) return rc;
-    enc_add_ln_kernel<<<tok_grid, 128, 0, h->stream>>>(tmp, x, T, H, l.ln1g, l.ln1b, c.ln_eps, x, nullptr, nullptr);
+    enc_add_ln_kernel<<<tok_grid, 128, 0, h->stream>>>(tmp, x, T, H, l.ln1g, l.ln1b, c.ln_eps, x, x_h, x_l);
     LAUNCHED(h);
-    rc = tc ? enc_gemm_tc<1>(h, x, l.wi, l.bi, ff, T, I, H) : enc_gemm<1>(h, x, l.wi, l.bi, ff, T, I, H);
+    rc = tc ? enc_gemm_tc<1>(h, x_h, x_l, l.wi_h, l.wi_l, l.bi, ff, ff_l, T, I, H)
+            : enc_gemm<1>(h, x, l.wi, l.bi, ff, T, I, H);
     if (rc != RSE_OK) return rc;
-    rc = tc ? enc_gemm_tc<0>(h, ff, l.wo2, l.bo2, tmp, T, H, I) : enc_gemm<0>(h, ff, l.wo2, l.bo2, tmp, T, H, I);
+    rc = tc ? enc_gemm_tc<0>(h, ff, ff_l, l.wo2_h, l.wo2_l, l.bo2, tmp, nullptr, T, H, I)
+            : enc_gemm<0>(h, ff, l.wo2, l.bo2, tmp, T, H, I);
     if (rc != RSE_OK) return rc;
-    enc_add_ln_kernel<<<tok_grid, 128, 0, h->stream>>>(tmp, x, T, H, l.ln2g, l.ln2b, c.ln_eps, x, nullptr, nullptr);
+    enc_add_ln_kernel<<<tok_grid, 128, 0, h->stream>>>(tmp, x, T, H, l.ln2g, l.ln2b, c.ln_eps, x, x_h, x_l);
     LAUNCHED(h);
   }
   if (c.head == 0) {
@@ -2206,9 +2228,24 @@ int rse_encoder_finalize(rse_index* h, int32_t slot) {
   if (e.seen.size() != want)
     return fail(h, RSE_ERR_STATE, "rse_encoder_finalize: " + std::to_string(e.seen.size()) + " of " + std::to_string(want) +
                                       " tensors were set");
-  // the tensor-core GEMMs need every GEMM dimension to tile (else the SIMT path serves the model)
+  // tf32 hi / lo halves of the weight matrices for the tensor-core GEMMs (every GEMM dimension must tile)
   const int64_t H = e.cfg.hidden, I = e.cfg.intermediate;
   e.tc_ok = (H % kEgBN == 0) && (I % kEgBN == 0) && (H % (kEgBK * kEgChunkKB) == 0) && (I % (kEgBK * kEgChunkKB) == 0);
+  if (e.tc_ok) {
+    CK(cudaSetDevice(h->device));
+    for (EncLayer& l : e.layers) {
+      struct { const float* w; float** hi; float** lo; int64_t n; } parts[4] = {
+          {l.wqkv, &l.wqkv_h, &l.wqkv_l, 3 * H * H}, {l.wo, &l.wo_h, &l.wo_l, H * H},
+          {l.wi, &l.wi_h, &l.wi_l, I * H}, {l.wo2, &l.wo2_h, &l.wo2_l, H * I}};
+      for (auto& p : parts) {
+        if (!*p.hi) { rc = enc_alloc(h, p.hi, p.n); if (rc != RSE_OK) return rc; }
+        if (!*p.lo) { rc = enc_alloc(h, p.lo, p.n); if (rc != RSE_OK) return rc; }
+        enc_split_kernel<<<static_cast<unsigned int>((p.n + 255) / 256), 256, 0, h->stream>>>(p.w, p.n, *p.hi, *p.lo);
+        LAUNCHED(h);
+      }
+    }
+    CK(cudaStreamSynchronize(h->stream));
+  }
   e.finalized = true;
   return RSE_OK;
 }
