@@ -378,7 +378,11 @@ __global__ void enc_positions_kernel(const int32_t* __restrict__ cu_seqlens, int
 //       being computed; the two correction products, 2^-11 smaller, accumulate in a third TMEM buffer over the
 //       whole K (their truncation error is below 2^-30 relative).
 //   * weights are split once at load (enc_split_kernel), activations by the kernel that produces them
-//     (LayerNorm / attention / GELU epilogue write hi and lo next to or instead of the fp32 value);
+//     (LayerNorm / attention / GELU epilogue write hi and lo next to or instead of the fp32 value).  (Tried in r02:
+//     loading the plain fp32 boxes and splitting them IN SHARED MEMORY with the epilogue warps — half the operand
+//     traffic, no hi/lo copies — was 10 % SLOWER, 1.22 vs 1.11 ms per 256-query batch: the tile is bound by the
+//     latency of a 3-stage ring per CTA and by wave quantisation, not by L2 bandwidth, and the split adds a hop
+//     to every stage.)
 //   * one 128 x 128 output tile per CTA (cta_group::1): warp 0 = TMA producer (3-stage ring, per stage four
 //     128 x 32-float boxes: A_hi, A_lo, W_hi, W_lo, SWIZZLE_128B), warp 1 = single-thread tcgen05.mma issuer
 //     (12 MMAs of 128x128x8 per k-block: 4 k-steps x 3 products), warps 2-5 = epilogue (tcgen05.ld 32x32b, one

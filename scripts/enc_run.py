@@ -14,7 +14,11 @@ if len(sys.argv) > 1:
     idx.encoder_set_mode(enc.slot, int(sys.argv[1]))
 rng = np.random.default_rng(1)
 ids = [[101] + rng.integers(1000, 30000, int(L) - 2).tolist() + [102] for L in rng.integers(4, 17, 256)]
+import time
 for _ in range(3):
     out = enc.encode_ids(ids)
-print(out.shape, float(np.linalg.norm(out[0])))
+t0 = time.perf_counter()
+for _ in range(20):
+    out = enc.encode_ids(ids)
+print(out.shape, float(np.linalg.norm(out[0])), f"{(time.perf_counter() - t0) / 20 * 1e3:.3f} ms per encode call (host buffers, 256 queries)")
 idx.close()
