@@ -389,12 +389,16 @@ __global__ void enc_positions_kernel(const int32_t* __restrict__ cu_seqlens, int
 //     TMEM lane = one token row per thread, 128 accumulators in registers): bias (+ GELU + split), 128-byte stores.
 // Output tile 128 x BN, BN = 128 or 64: the narrow tile is for GEMMs whose 128-wide tiling would leave most SMs idle
 // (MiniLM's N = 384 projections on a 2.5 k-token batch: 60 tiles for 148 SMs; 120 with BN = 64).
-constexpr int kEgBM = 128, kEgBN = 128, kEgBK = 32, kEgStages = 3;
+constexpr int kEgBM = 128, kEgBN = 128, kEgBK = 32;
+// ring depth: 3 stages of 64 KB for the 128-wide tile (one CTA per SM); 2 stages of 48 KB for the 64-wide tile, which
+// then fits TWICE on an SM (96 KB of shared memory, 256 TMEM columns, 132 registers x 192 threads each): four
+// stages in flight per SM and one CTA's prologue / epilogue under the other's main loop
+__host__ __device__ constexpr int eg_stages(int bn) { return bn == 128 ? 3 : 2; }
 constexpr int kEgBox = kEgBM * kEgBK * 4;                       // 16,384 B: one 128-row operand box
 constexpr int kEgThreads = 192;
 constexpr int kEgChunkKB = 4;                                   // k-blocks per hi*hi accumulation chunk (K = 128)
 __host__ __device__ constexpr int eg_stage_bytes(int bn) { return 2 * kEgBox + 2 * bn * kEgBK * 4; }
-__host__ __device__ constexpr int eg_smem_bytes(int bn) { return kEgStages * eg_stage_bytes(bn) + 16 * 8 + 16 + 1024; }
+__host__ __device__ constexpr int eg_smem_bytes(int bn) { return eg_stages(bn) * eg_stage_bytes(bn) + 16 * 8 + 16 + 1024; }
 // kind::tf32: D = f32 (bit 4), A = B = tf32 (format 2), both K-major, N = BN, M = 128
 __host__ __device__ constexpr uint32_t eg_idesc(int bn) { return (1u << 4) | (2u << 7) | (2u << 10) | ((static_cast<uint32_t>(bn) >> 3) << 17) | ((kEgBM >> 4) << 24); }
 
@@ -429,7 +433,7 @@ __device__ __forceinline__ void eg_mma_tf32(uint32_t tmem_d, uint64_t adesc, uin
 
 // EPI 0: C = acc + bias (fp32).  EPI 1: g = GELU(acc + bias) -> C_hi / C_lo (the operand of the next GEMM).
 template <int EPI, int BN>
-__global__ void __launch_bounds__(kEgThreads, 1)
+__global__ void __launch_bounds__(kEgThreads, BN == 128 ? 1 : 2)
 enc_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a_hi, const __grid_constant__ CUtensorMap tmap_a_lo,
                    const __grid_constant__ CUtensorMap tmap_w_hi, const __grid_constant__ CUtensorMap tmap_w_lo,
                    const float* __restrict__ bias, float* __restrict__ C, float* __restrict__ C_lo, int M, int N, int K) {
@@ -437,6 +441,7 @@ enc_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a_hi, const __grid_c
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   unsigned char* smem = smem_raw + (base - smem_u32(smem_raw));
   constexpr int kStageBytes = eg_stage_bytes(BN);
+  constexpr int kEgStages = eg_stages(BN);
   constexpr int kWBox = BN * kEgBK * 4;
   constexpr uint32_t kIdesc = eg_idesc(BN);
   constexpr uint32_t kTmemCols = BN == 128 ? 512u : 256u;       // 3 x BN columns, rounded up to a power of two

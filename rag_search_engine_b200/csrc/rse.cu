@@ -80,6 +80,7 @@ struct rse_index {
   // K4 tensor-core path
   int tc_mode = 0;                 // 0 auto, 1 off (exact scan only), 2 force on
   bool second_chance = true;       // RSE_NO_SECOND_CHANCE=1 switches the second filter pass off (diagnostics)
+  int enc_bn_override = 0;         // RSE_ENC_BN=64|128 forces the encoder GEMM tile width (diagnostics)
   int survivor_div = 5;            // probe sample density: expected first-pass survivors ~ cap / survivor_div (RSE_TC_SURVIVOR_DIV).
                                    // r02 sweep, ms per 256-query step, isotropic / clustered / dense-clustered S-600k:
                                    // 3: 1.155 / 1.460 / 2.336   5: 1.146 / 1.223 / 1.785   8: 1.174 / 1.240 / 1.454
@@ -876,6 +877,7 @@ int rse_create(int32_t device, rse_index** out) {
   if (const char* ev = std::getenv("RSE_NO_OVERLAP")) h->overlap_enabled = !(ev[0] == '1');
   if (const char* ev = std::getenv("RSE_TIMELINE")) h->timeline = ev[0] == '1';
   if (const char* ev = std::getenv("RSE_NO_SECOND_CHANCE")) h->second_chance = !(ev[0] == '1');
+  if (const char* ev = std::getenv("RSE_ENC_BN")) { const int v = std::atoi(ev); if (v == 64 || v == 128) h->enc_bn_override = v; }
   if (const char* ev = std::getenv("RSE_TC_SURVIVOR_DIV")) { const int v = std::atoi(ev); if (v >= 1 && v <= 64) h->survivor_div = v; }
   *out = h;
   return RSE_OK;
@@ -1995,7 +1997,9 @@ int enc_gemm_tc(rse_index* h, const float* A_hi, const float* A_lo, const float*
   }
   // 128-wide tiles unless they would leave most of the SMs without one: then 64-wide (twice the CTAs)
   const int m_tiles = (M + kEgBM - 1) / kEgBM;
-  const int bn = (m_tiles * (N / 128) >= h->sm_count || N % 64 != 0) ? 128 : 64;
+  int bn = (m_tiles * (N / 128) >= h->sm_count || N % 64 != 0) ? 128 : 64;
+  if (h->enc_bn_override == 64 && N % 64 == 0) bn = 64;
+  if (h->enc_bn_override == 128) bn = 128;
   CUtensorMap ta_h, ta_l, tw_h, tw_l;
   int rc = make_tmap_f32(h, &ta_h, A_hi, M, K, kEgBM);
   if (rc == RSE_OK) rc = make_tmap_f32(h, &ta_l, A_lo, M, K, kEgBM);
