@@ -1995,10 +1995,11 @@ int enc_gemm_tc(rse_index* h, const float* A_hi, const float* A_lo, const float*
     CK(cudaFuncSetAttribute(enc_gemm_tc_kernel<1, 64>, cudaFuncAttributeMaxDynamicSharedMemorySize, eg_smem_bytes(64)));
     h->attr_mask |= 1u << 17;
   }
-  // 128-wide tiles unless they would leave most of the SMs without one: then 64-wide (twice the CTAs)
+  // 64-wide tiles, two CTAs per SM (r02, 256 queries / 2.5 k tokens, ms per host-buffer encode call: 64-wide
+  // everywhere 1.35, 128-wide everywhere 1.46, 128-wide unless that leaves SMs idle 1.49): the kernel is bound by
+  // the latency of its operand ring and by wave quantisation, so more, smaller tiles in flight win
   const int m_tiles = (M + kEgBM - 1) / kEgBM;
-  int bn = (m_tiles * (N / 128) >= h->sm_count || N % 64 != 0) ? 128 : 64;
-  if (h->enc_bn_override == 64 && N % 64 == 0) bn = 64;
+  int bn = (N % 64 == 0) ? 64 : 128;
   if (h->enc_bn_override == 128) bn = 128;
   CUtensorMap ta_h, ta_l, tw_h, tw_l;
   int rc = make_tmap_f32(h, &ta_h, A_hi, M, K, kEgBM);
