@@ -350,3 +350,16 @@ def test_multimodal_search_ranks_like_the_reference_expression():
             MultimodalSearch(documents=None, model=FakeClip()).search_with_image("x.png")
     finally:
         ms.close()
+
+
+def test_sharded_entry_points_need_a_communicator(small_world):
+    import torch
+    from rag_search_engine_b200._lib import RseError
+    idx, se, bm, batches = small_world
+    Q, tp, tr = batches[0]
+    qd = torch.as_tensor(Q, device="cuda")
+    out = torch.empty((Q.shape[0], 10), dtype=torch.float64, device="cuda")
+    with pytest.raises(RseError, match="communicator"):
+        idx.knn_sharded_dev(qd.data_ptr(), Q.shape[0], 10, 100, out.data_ptr(), out.data_ptr(), out.data_ptr(), out.data_ptr())
+    n_ranks, rank, ver = idx.comm_info()
+    assert n_ranks == 0
