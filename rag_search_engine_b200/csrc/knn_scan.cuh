@@ -277,30 +277,67 @@ knn_scan384_kernel(const float* __restrict__ emb, const float* __restrict__ amag
   }
 }
 
-// ---------------------------------------------------------------- K1 generic path (any dim)
-// Same arithmetic, lane-per-row straight from global memory.  Used for
-// dim != 384 (e.g. the reference's own unit test uses dim = 4,
-// tests/test_semantic_search.py:34-44); not a performance path.
+// Any other embedding width (the reference's own unit test uses dim = 4, tests/test_semantic_search.py:34-44; a
+// different sentence-transformers model is 768 wide; the CLIP text embeddings of llm/multimodal.py are 512 wide).
+// Same arithmetic as the 384 kernel — one SEQUENTIAL fp32 accumulator per (row, query), unfused unless FMA — so the
+// rows are staged through shared memory: a warp loads 32 rows x 64 floats with coalesced 128-byte reads into a
+// [32][65] tile (stride 65: lane-per-row reads are conflict-free), then every lane walks its own row's 64 values
+// in order for up to 16 queries; the accumulators stay in registers across the chunks.  (r01's version read
+// global memory lane-per-row — 32 different 2 KB-strided rows per load instruction — and reached ~3 % of the HBM
+// bandwidth; it was "not a performance path" until the image search of §8 f4 started using it.)
+constexpr int kGenChunk = 64;
+constexpr int kGenWarps = 4;
 template <bool FMA>
-__global__ void knn_scan_generic_kernel(const float* __restrict__ emb, const float* __restrict__ amag,
-                                        int64_t n_rows, int dim, const float* __restrict__ q,
-                                        const double* __restrict__ sb, int nq, float* __restrict__ dist,
-                                        int64_t ld) {
-  int64_t row = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+__global__ void __launch_bounds__(kGenWarps * 32)
+knn_scan_generic_kernel(const float* __restrict__ emb, const float* __restrict__ amag,
+                        int64_t n_rows, int dim, const float* __restrict__ q,
+                        const double* __restrict__ sb, int nq, float* __restrict__ dist,
+                        int64_t ld) {
+  __shared__ float s_tile[kGenWarps][32][kGenChunk + 1];
+  __shared__ float s_q[kScanMaxQB][kGenChunk];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int64_t row0 = (static_cast<int64_t>(blockIdx.x) * kGenWarps + warp) * 32;
+  const int64_t row = row0 + lane;
+  float acc[kScanMaxQB];
+#pragma unroll
+  for (int j = 0; j < kScanMaxQB; ++j) acc[j] = 0.0f;
+  for (int c0 = 0; c0 < dim; c0 += kGenChunk) {
+    const int nc = min(kGenChunk, dim - c0);
+    __syncthreads();                                           // the previous chunk's queries / tile are consumed
+    for (int i = threadIdx.x; i < nq * kGenChunk; i += blockDim.x) {
+      const int j = i / kGenChunk, k = i % kGenChunk;
+      s_q[j][k] = k < nc ? __ldg(q + static_cast<int64_t>(j) * dim + c0 + k) : 0.0f;
+    }
+#pragma unroll 4
+    for (int r = 0; r < 32; ++r) {
+      const int64_t gr = row0 + r;
+      const float* src = emb + gr * dim + c0;
+      float v0 = 0.0f, v1 = 0.0f;
+      if (gr < n_rows) {
+        if (lane < nc) v0 = __ldg(src + lane);
+        if (lane + 32 < nc) v1 = __ldg(src + lane + 32);
+      }
+      s_tile[warp][r][lane] = v0;
+      s_tile[warp][r][lane + 32] = v1;
+    }
+    __syncthreads();
+    const float* mine = s_tile[warp][lane];
+    for (int k = 0; k < nc; ++k) {
+      const float a = mine[k];
+#pragma unroll
+      for (int j = 0; j < kScanMaxQB; ++j)
+        if (j < nq) acc[j] = mac<FMA>(acc[j], a, s_q[j][k]);
+    }
+  }
   if (row >= n_rows) return;
   const float am = amag[row];
-  const float* a = emb + row * dim;
-  for (int j = 0; j < nq; ++j) {
-    float v;
-    if (am < 0.0f) {
-      v = __uint_as_float(0x7FFFFFFFu);
-    } else {
-      const float* b = q + static_cast<int64_t>(j) * dim;
-      float acc = 0.0f;
-      for (int i = 0; i < dim; ++i) acc = mac<FMA>(acc, a[i], __ldg(b + i));
-      v = cosine_tail(acc, sqrt(static_cast<double>(am)), sb[j]);
+#pragma unroll
+  for (int j = 0; j < kScanMaxQB; ++j) {
+    if (j < nq) {
+      float v = __uint_as_float(0x7FFFFFFFu);
+      if (!(am < 0.0f)) v = cosine_tail(acc[j], sqrt(static_cast<double>(am)), sb[j]);
+      dist[j * ld + row] = v;
     }
-    dist[j * ld + row] = v;
   }
 }
 

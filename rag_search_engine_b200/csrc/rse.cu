@@ -321,7 +321,7 @@ int launch_scan(rse_index* h, const float* q, const double* sb, int nq, float* d
     if (nq <= 8) return launch_scan384<8, FMA>(h, q, sb, nq, dist);
     return launch_scan384<16, FMA>(h, q, sb, nq, dist);
   }
-  const int threads = 128;
+  const int threads = kGenWarps * 32;
   const int grid = static_cast<int>((h->n_rows + threads - 1) / threads);
   knn_scan_generic_kernel<FMA><<<grid, threads, 0, h->stream>>>(h->emb, h->amag, h->n_rows, h->dim, q, sb, nq,
                                                                 dist, h->dist_ld);

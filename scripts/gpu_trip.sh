@@ -22,6 +22,7 @@ try:
         print("clustered", c)
     print("python", d.get("e2e_python"))
     print("text_in", d.get("text_in"))
+    print("image_search", d.get("image_search"))
     print("small", d.get("knn_small_batches"))
     print("knn100m", d.get("knn100m"))
     print("cpu", d.get("cpu_baseline"))

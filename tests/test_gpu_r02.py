@@ -363,3 +363,22 @@ def test_sharded_entry_points_need_a_communicator(small_world):
         idx.knn_sharded_dev(qd.data_ptr(), Q.shape[0], 10, 100, out.data_ptr(), out.data_ptr(), out.data_ptr(), out.data_ptr())
     n_ranks, rank, ver = idx.comm_info()
     assert n_ranks == 0
+
+
+def test_torch_distributed_sharded_driver_single_rank(small_world):
+    """sharded.ShardedHybrid + LibrseShardBackend (the torch.distributed form of the row-sharded step; the gloo test
+    drives it with an oracle backend) on one rank must equal the single-handle call."""
+    import torch
+    from rag_search_engine_b200 import sharded
+    idx, se, bm, batches = small_world
+    Q, tp, tr = batches[2]
+    dev = torch.device("cuda", 0)
+    be = sharded.LibrseShardBackend(idx, Q, tp, tr, dev)
+    sh = sharded.ShardedHybrid(be, Q.shape[0])
+    r = sh.step(torch.as_tensor(Q, device=dev), 0, 60.0, 10)
+    idx.synchronize()
+    idx.use_own_stream()
+    want = idx.hybrid(0, 60.0, 10, Q, tp, tr)
+    assert int(r.flagged.item()) == 0
+    assert (r.ids.cpu().numpy() == want[0]).all() and (r.score.cpu().numpy() == want[1]).all()
+    assert (r.count.cpu().numpy() == want[4]).all()
