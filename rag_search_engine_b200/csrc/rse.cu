@@ -53,8 +53,12 @@ struct Encoder {
   int mode = 0;                       // 0 = tcgen05 3xTF32 GEMMs (when every GEMM dimension is a multiple of 128 / 32),
                                       // 1 = fp32 SIMT GEMMs
   bool tc_ok = false;
-  int32_t* pin_in = nullptr;          // pinned staging of ids | type_ids | cu_seqlens
-  size_t pin_in_n = 0;
+  // pinned staging of ids | type_ids | cu_seqlens: two buffers used alternately, each guarded by an event, so a call
+  // never waits for the device unless the upload two calls ago is still in flight
+  int32_t* pin_in[2] = {nullptr, nullptr};
+  size_t pin_in_n[2] = {0, 0};
+  cudaEvent_t pin_ev[2] = {nullptr, nullptr};
+  int pin_next = 0;
 };
 
 }  // namespace
@@ -286,8 +290,11 @@ void enc_release(Encoder& e) {
   e.seen.clear();
   for (DevBuf* b : {&e.ids, &e.type_ids, &e.cu, &e.posidx, &e.x, &e.qkv, &e.ctx, &e.tmp, &e.ff, &e.out, &e.x_h, &e.x_l,
                     &e.ctx_l, &e.ff_l}) free_buf(*b);
-  if (e.pin_in) cudaFreeHost(e.pin_in);
-  e.pin_in = nullptr; e.pin_in_n = 0;
+  for (int i = 0; i < 2; ++i) {
+    if (e.pin_in[i]) cudaFreeHost(e.pin_in[i]);
+    if (e.pin_ev[i]) cudaEventDestroy(e.pin_ev[i]);
+    e.pin_in[i] = nullptr; e.pin_in_n[i] = 0; e.pin_ev[i] = nullptr;
+  }
   e.created = e.finalized = false;
 }
 
@@ -2107,24 +2114,27 @@ int enc_run(rse_index* h, int32_t slot, const int32_t* ids, const int32_t* type_
   const int T = cu[n_seq];
   CK(cudaSetDevice(h->device));
   const size_t n_in = static_cast<size_t>(T) * 2 + n_seq + 1;
-  if (e.pin_in_n < n_in) {
-    CK(cudaStreamSynchronize(h->stream));
-    if (e.pin_in) CK(cudaFreeHost(e.pin_in));
-    e.pin_in = nullptr; e.pin_in_n = 0;
-    CK(cudaMallocHost(reinterpret_cast<void**>(&e.pin_in), sizeof(int32_t) * (n_in + n_in / 2 + 64)));
-    e.pin_in_n = n_in + n_in / 2 + 64;
-  } else {
-    CK(cudaStreamSynchronize(h->stream));                 // the previous call's uploads have left the buffer
+  const int pb = e.pin_next;
+  e.pin_next ^= 1;
+  if (!e.pin_ev[pb]) CK(cudaEventCreateWithFlags(&e.pin_ev[pb], cudaEventDisableTiming));
+  else CK(cudaEventSynchronize(e.pin_ev[pb]));            // the uploads out of this buffer (two calls ago) have finished
+  if (e.pin_in_n[pb] < n_in) {
+    if (e.pin_in[pb]) CK(cudaFreeHost(e.pin_in[pb]));
+    e.pin_in[pb] = nullptr; e.pin_in_n[pb] = 0;
+    CK(cudaMallocHost(reinterpret_cast<void**>(&e.pin_in[pb]), sizeof(int32_t) * (n_in + n_in / 2 + 64)));
+    e.pin_in_n[pb] = n_in + n_in / 2 + 64;
   }
-  std::memcpy(e.pin_in, ids, sizeof(int32_t) * T);
-  if (type_ids) std::memcpy(e.pin_in + T, type_ids, sizeof(int32_t) * T);
-  std::memcpy(e.pin_in + 2 * static_cast<size_t>(T), cu, sizeof(int32_t) * (n_seq + 1));
+  int32_t* pin = e.pin_in[pb];
+  std::memcpy(pin, ids, sizeof(int32_t) * T);
+  if (type_ids) std::memcpy(pin + T, type_ids, sizeof(int32_t) * T);
+  std::memcpy(pin + 2 * static_cast<size_t>(T), cu, sizeof(int32_t) * (n_seq + 1));
   ENSURE(e.ids, sizeof(int32_t) * T);
   ENSURE(e.type_ids, sizeof(int32_t) * T);
   ENSURE(e.cu, sizeof(int32_t) * (n_seq + 1));
-  CK(cudaMemcpyAsync(e.ids.p, e.pin_in, sizeof(int32_t) * T, cudaMemcpyHostToDevice, h->stream));
-  if (type_ids) CK(cudaMemcpyAsync(e.type_ids.p, e.pin_in + T, sizeof(int32_t) * T, cudaMemcpyHostToDevice, h->stream));
-  CK(cudaMemcpyAsync(e.cu.p, e.pin_in + 2 * static_cast<size_t>(T), sizeof(int32_t) * (n_seq + 1), cudaMemcpyHostToDevice, h->stream));
+  CK(cudaMemcpyAsync(e.ids.p, pin, sizeof(int32_t) * T, cudaMemcpyHostToDevice, h->stream));
+  if (type_ids) CK(cudaMemcpyAsync(e.type_ids.p, pin + T, sizeof(int32_t) * T, cudaMemcpyHostToDevice, h->stream));
+  CK(cudaMemcpyAsync(e.cu.p, pin + 2 * static_cast<size_t>(T), sizeof(int32_t) * (n_seq + 1), cudaMemcpyHostToDevice, h->stream));
+  CK(cudaEventRecord(e.pin_ev[pb], h->stream));
   h->stats.h2d_bytes += static_cast<int64_t>(sizeof(int32_t)) * (static_cast<int64_t>(T) * (type_ids ? 2 : 1) + n_seq + 1);
   return enc_forward(h, e, n_seq, T, type_ids != nullptr, out_dev);
 }
