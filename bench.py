@@ -501,11 +501,12 @@ def measure_corpus_variant(args, local_rank, device, stream, bm, corpus, steps, 
     Qn, batches = pinned_batches(torch, Q, tok_indptr, terms, args.batch, 0, args.batch)
     m = measure_hybrid(idx, tm, batches, 0, 60.0, args.limit, steps, 3, e2e=False)
     st = m["stats"]
-    # parity of the filter path on this distribution: K4 (auto) vs the exact scan (tc_mode 1) on 32 queries
+    # parity of the filter path on this distribution: K4 (auto) vs the exact scan (tc_mode 1) on a whole batch
     kp = max(args.limit * 10, args.limit)
-    a = idx.knn_movies(Qn[:32], args.limit, kp)
+    nchk = min(256, args.batch)
+    a = idx.knn(Qn[:nchk], kp)
     idx.set_tc_mode(1)
-    b = idx.knn_movies(Qn[:32], args.limit, kp)
+    b = idx.knn(Qn[:nchk], kp)
     same = all((x.view(np.uint8) == y.view(np.uint8)).all() for x, y in zip(a, b))
     out = {"corpus": corpus, "value": m["nq"] * steps / (m["ms"] / 1e3), "unit": "queries/s", "ms_per_step": m["ms"] / steps,
            "steps": steps, "tc_queries": int(st.tc_queries), "tc_fallback_queries": int(st.tc_fallback_queries),
@@ -513,7 +514,8 @@ def measure_corpus_variant(args, local_rank, device, stream, bm, corpus, steps, 
            "tc_fallback_rate": (int(st.tc_fallback_queries) / int(st.tc_queries)) if int(st.tc_queries) else None,
            "filter_pass_ms": st.scan_ms_total / max(1, st.scan_launches_timed),
            "survivors_per_query": survivor_stats(m["survivors"]),
-           "tc_equals_exact_scan_on_32_queries": bool(same), "build_s": info["build_s"]}
+           "tc_equals_exact_scan": {"queries": nchk, "kprime": kp, "identical_rows_order_and_distances": bool(same)},
+           "build_s": info["build_s"]}
     idx.close()
     del se
     torch.cuda.empty_cache()
@@ -823,6 +825,17 @@ def run_b200(args, rank, world, local_rank):
                          "bench of that hour, which took an inline NVML sample (~25 ms of host time) every 8 steps "
                          "inside the device-resident loop; the kernels of the two modes differ only in fuse_kernel"}
 
+    # ---- full-size parity of the tensor-core path: the whole of batch 0 through K4 and through the exact scan
+    tc_same = None
+    if world == 1 and not args.no_extras:
+        kp_ = max(limit * 10, limit)
+        a_ = idx.knn(Qn[:min(256, nq)], kp_)
+        idx.set_tc_mode(1)
+        b_ = idx.knn(Qn[:min(256, nq)], kp_)
+        idx.set_tc_mode(args.tc_mode if args.tc_mode >= 0 else 0)
+        tc_same = {"queries": min(256, nq), "kprime": kp_,
+                   "identical_rows_order_and_distances": bool(all((x.view(np.uint8) == y.view(np.uint8)).all() for x, y in zip(a_, b_)))}
+
     # ---- batch-1 KNN (north_star: batch-1 kNN as a fraction of HBM peak): scan<QB=1> alone + whole call
     knn1 = knn1k = small = pyapi = textin = None
     if world == 1 and not args.no_knn1:
@@ -976,7 +989,7 @@ def run_b200(args, rank, world, local_rank):
                     "scan_launches": int(st.scan_launches_timed), "scan_share_of_step": scan_share,
                     "tc_queries": int(st.tc_queries), "tc_fallback_queries": int(st.tc_fallback_queries),
                     "tc_second_chance_queries": int(st.tc_second_chance_queries),
-                    "survivors_per_query": survivor_stats(m["survivors"])}
+                    "survivors_per_query": survivor_stats(m["survivors"]), "tc_equals_exact_scan": tc_same}
     else:
         roofline = {"bound": "hbm", "kernel": kname,
                     "achieved": hbm_achieved, "peak": peak, "unit": "GB/s", "frac": (hbm_achieved / peak) if hbm_achieved else None,
