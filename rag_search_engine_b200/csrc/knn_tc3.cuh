@@ -394,7 +394,7 @@ tc3_probe_threshold_kernel(const uint32_t* __restrict__ dist, int64_t ld, int nq
 //                  they read d~ = 1, which can only matter when tau_s >= 1 - 2 eps — and then the query is
 //                  handed to the exact scan anyway (tc3_threshold_kernel).
 // MODE 2 (probe, K' <= 256): same tiles as MODE 0, but nothing dense is stored: every epilogue thread keeps the
-//                  8 largest cos~ of the (query, rows) pairs it sees in registers and writes them at the end —
+//                  8 largest of the per-32-row-group maxima of cos~ it sees in registers and writes them at the end —
 //                  dist[q*ld + (cluster*2 + half)*8 + i], ld = n_clusters*16.  The K'-th smallest d~ of that
 //                  union is the K'-th smallest of a SUBSET of the sample: still an upper bound of the K'-th
 //                  exact distance (+eps), and equal to the dense answer unless one thread holds more than 8 of
@@ -586,18 +586,17 @@ knn_tc3_kernel(const __grid_constant__ CUtensorMap tmap_rows, const __grid_const
         for (int c = 0; c < 4; ++c) {
           uint32_t v[32];
           tc_ld32(taddr0 + static_cast<uint32_t>(32 * c), v);
-          if (t3_max32(v) > top[kT3ProbeTop - 1]) {
+          // only the MAXIMUM of the 32 rows is offered to the list (r02): any subset of sample rows gives a valid
+          // bound, the sample's best K' rows almost never share one of the ~9 k 32-row groups a query sees, and the
+          // element-wise version ran its 32-step insertion loop for nearly every group (some lane of the warp always
+          // had a candidate): 640 instructions per group, the probe's epilogue as slow as its MMAs
+          const float x = t3_max32(v);
+          if (x > top[kT3ProbeTop - 1]) {
+            top[kT3ProbeTop - 1] = x;
 #pragma unroll
-            for (int j = 0; j < 32; ++j) {
-              const float x = __uint_as_float(v[j]);
-              if (x > top[kT3ProbeTop - 1]) {
-                top[kT3ProbeTop - 1] = x;
-#pragma unroll
-                for (int i = kT3ProbeTop - 1; i > 0; --i) {
-                  const float hi = fmaxf(top[i - 1], top[i]), lo = fminf(top[i - 1], top[i]);
-                  top[i - 1] = hi; top[i] = lo;
-                }
-              }
+            for (int i = kT3ProbeTop - 1; i > 0; --i) {
+              const float hi = fmaxf(top[i - 1], top[i]), lo = fminf(top[i - 1], top[i]);
+              top[i - 1] = hi; top[i] = lo;
             }
           }
         }
