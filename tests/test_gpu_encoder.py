@@ -255,3 +255,75 @@ def test_mirrors_take_the_gpu_encoders_through_the_reference_seams(minilm, tmp_p
             hs.close()
     finally:
         runtime.release(db, 0)
+
+
+def test_encoder_abi_error_paths(fresh_index):
+    """Status codes instead of undefined behaviour: wrong tensor sizes / names, missing tensors, use before
+    finalize, unsupported shapes, over-long sequences."""
+    from rag_search_engine_b200._lib import RseError
+    from rag_search_engine_b200.encoder import random_state_dict
+    idx = fresh_index
+    cfg = dict(vocab_size=500, hidden=128, layers=1, heads=2, intermediate=512, max_positions=16, type_vocab=2, ln_eps=1e-12)
+    with pytest.raises(RseError, match="create"):
+        idx._check(idx._L.rse_encoder_finalize(idx._h, 0))
+    with pytest.raises(RseError, match="unsupported"):
+        idx.encoder_create(0, head=0, **{**cfg, "hidden": 100})
+    with pytest.raises(RseError, match="slot"):
+        idx.encoder_create(5, head=0, **cfg)
+    idx.encoder_create(0, head=0, **cfg)
+    sd = random_state_dict(cfg, seed=1)
+    with pytest.raises(RseError, match="element count"):
+        idx.encoder_set_tensor(0, "embeddings.LayerNorm.weight", np.zeros(64, np.float32))
+    with pytest.raises(RseError, match="unknown tensor|not a BERT"):
+        idx.encoder_set_tensor(0, "encoder.layer.0.attention.self.nope.weight", np.zeros(4, np.float32))
+    with pytest.raises(RseError, match="layer index"):
+        idx.encoder_set_tensor(0, "encoder.layer.3.output.dense.bias", np.zeros(128, np.float32))
+    names = list(sd)
+    for n in names[:-1]:
+        idx.encoder_set_tensor(0, "0.auto_model." + n, sd[n])             # a wrapper prefix is ignored
+    with pytest.raises(RseError, match="tensors were set"):
+        idx.encoder_finalize(0)
+    with pytest.raises(RseError, match="not finalized"):
+        idx.encode(0, np.array([101, 102], np.int32), np.array([0, 2], np.int32))
+    idx.encoder_set_tensor(0, names[-1], sd[names[-1]])
+    idx.encoder_finalize(0)
+    out = idx.encode(0, np.array([101, 7, 102, 101, 102], np.int32), np.array([0, 3, 5], np.int32))
+    assert out.shape == (2, 128) and np.isfinite(out).all()
+    with pytest.raises(RseError, match="max_positions"):
+        idx.encode(0, np.arange(20, dtype=np.int32), np.array([0, 20], np.int32))
+    with pytest.raises(ValueError):
+        idx.encode(0, np.arange(5, dtype=np.int32), np.array([0, 4], np.int32))          # cu_seqlens does not cover the ids
+
+
+def test_fallback_build_is_explicit_and_marked(minilm, tmp_path):
+    """Index build stays on the reference (north_star).  Without the reference package the mirror refuses to build
+    unless asked (fallback_build=True), and the database it then writes says that sqlite-vec cannot open it."""
+    import json
+    import sqlite3
+    from rag_search_engine_b200 import SemanticSearch, runtime
+    from rag_search_engine_b200.encoder import GpuSentenceEncoder, config_from_hf
+    try:
+        import rag_search_engine.utils.semantic_search  # noqa: F401
+        pytest.skip("the reference package is importable here: its own build is used")
+    except ImportError:
+        pass
+    docs = {"movies": [{"id": 11 + i, "title": f"T{i} w{i % 5}", "description": f"w{i} w{i + 1}. w{i % 7} again."} for i in range(40)]}
+    p = tmp_path / "movies.json"
+    p.write_text(json.dumps(docs))
+    db = tmp_path / "fb.db"
+    idx = runtime.acquire(db, 0)
+    try:
+        enc = GpuSentenceEncoder(idx, minilm.state_dict(), config_from_hf(minilm.config),
+                                 tokenizer=lambda texts: [_word_ids(t) for t in texts])
+        with pytest.raises(RuntimeError, match="fallback_build=True"):
+            SemanticSearch(docs_path=p, db_path=db, encoder=enc)
+        ss = SemanticSearch(docs_path=p, db_path=db, encoder=enc, fallback_build=True)     # bulk embed on the GPU encoder
+        try:
+            hits = ss.query_top_k("w3 w4", k=3)
+            assert len(hits) == 3 and all(h["chunk"] for h in hits)
+            (note,) = sqlite3.connect(db).execute("SELECT value FROM rse_meta WHERE key='vec0_shadow_writer'").fetchone()
+            assert "not openable by sqlite-vec" in note
+        finally:
+            ss.close()
+    finally:
+        runtime.release(db, 0)
