@@ -268,7 +268,7 @@ def test_encoder_abi_error_paths(fresh_index):
         idx._check(idx._L.rse_encoder_finalize(idx._h, 0))
     with pytest.raises(RseError, match="unsupported"):
         idx.encoder_create(0, head=0, **{**cfg, "hidden": 100})
-    with pytest.raises(RseError, match="slot"):
+    with pytest.raises(RseError, match="bad arguments"):
         idx.encoder_create(5, head=0, **cfg)
     idx.encoder_create(0, head=0, **cfg)
     sd = random_state_dict(cfg, seed=1)
