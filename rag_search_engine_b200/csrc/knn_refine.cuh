@@ -153,7 +153,10 @@ knn_refine_kernel(const float* __restrict__ emb, const float* __restrict__ amag,
     if (thr2 != nullptr && counters) atomicAdd(&counters[3], 1ull);      // answered by the second-chance pass
   }
 
-  // ---- (b) exact distances, lane-per-row from global memory (the reference's sequential sum)
+  // ---- (b) exact distances, lane-per-row from global memory (the reference's sequential sum).  The products are
+  //      independent of the running sum, so 24 float4 loads are in flight per thread before the first add (r02 ncu:
+  //      with 8 in flight this loop held 34 % of the kernel's stall samples — twelve dependent round trips to HBM
+  //      per row — and the barrier-per-stage bitonic sort below another 30 %)
   unsigned long long* keys = reinterpret_cast<unsigned long long*>(smem_raw);   // pairs are dead
   __syncthreads();
   int m2 = 2;
@@ -165,29 +168,49 @@ knn_refine_kernel(const float* __restrict__ emb, const float* __restrict__ amag,
       const uint32_t row = s_rows[i];
       const float4* rp = reinterpret_cast<const float4*>(emb + static_cast<int64_t>(row) * kScanD);
       float acc = 0.0f;
-#pragma unroll 8
-      for (int c = 0; c < kScanD / 4; ++c) {
-        const float4 a = __ldg(rp + c);
-        acc = mac<FMA>(acc, a.x, s_q[4 * c + 0]);
-        acc = mac<FMA>(acc, a.y, s_q[4 * c + 1]);
-        acc = mac<FMA>(acc, a.z, s_q[4 * c + 2]);
-        acc = mac<FMA>(acc, a.w, s_q[4 * c + 3]);
+#pragma unroll 1
+      for (int c0 = 0; c0 < kScanD / 4; c0 += 24) {
+        float4 a[24];
+#pragma unroll
+        for (int c = 0; c < 24; ++c) a[c] = __ldg(rp + c0 + c);
+#pragma unroll
+        for (int c = 0; c < 24; ++c) {
+          acc = mac<FMA>(acc, a[c].x, s_q[4 * (c0 + c) + 0]);
+          acc = mac<FMA>(acc, a[c].y, s_q[4 * (c0 + c) + 1]);
+          acc = mac<FMA>(acc, a[c].z, s_q[4 * (c0 + c) + 2]);
+          acc = mac<FMA>(acc, a[c].w, s_q[4 * (c0 + c) + 3]);
+        }
       }
       const float d = cosine_tail(acc, sqrt(static_cast<double>(__ldg(amag + row))), sbq);
       key = knn_key(f32_orderable(__float_as_uint(d)), pos_base + static_cast<uint64_t>(row));
     }
     keys[i] = key;
   }
-  // ---- (c) keys-only bitonic sort, emit the first K'
-  for (int size = 2; size <= m2; size <<= 1) {
-    for (int stride = size >> 1; stride > 0; stride >>= 1) {
-      __syncthreads();
-      for (int t = threadIdx.x; t < (m2 >> 1); t += blockDim.x) {
-        const int lo = 2 * t - (t & (stride - 1));
-        const int hi = lo + stride;
-        const bool up = ((lo & size) == 0);
-        const unsigned long long a = keys[lo], b = keys[hi];
-        if ((a > b) == up) { keys[lo] = b; keys[hi] = a; }
+  // ---- (c) sort the keys (all distinct: the position is part of the key), emit the first K'
+  const unsigned long long* sorted = keys;
+  if (m <= 512u) {
+    // rank counting: every key is compared with all the others straight from shared memory (broadcast reads), no
+    // barrier per stage — K' plus a thin band is a few hundred keys
+    unsigned long long* dst = keys + kTcRefineCap;                  // the upper half of the 64 KB region
+    __syncthreads();
+    for (int i = threadIdx.x; i < static_cast<int>(m); i += blockDim.x) {
+      const unsigned long long me = keys[i];
+      int rank = 0;
+      for (int j = 0; j < static_cast<int>(m); ++j) rank += keys[j] < me ? 1 : 0;
+      dst[rank] = me;
+    }
+    sorted = dst;
+  } else {
+    for (int size = 2; size <= m2; size <<= 1) {
+      for (int stride = size >> 1; stride > 0; stride >>= 1) {
+        __syncthreads();
+        for (int t = threadIdx.x; t < (m2 >> 1); t += blockDim.x) {
+          const int lo = 2 * t - (t & (stride - 1));
+          const int hi = lo + stride;
+          const bool up = ((lo & size) == 0);
+          const unsigned long long a = keys[lo], b = keys[hi];
+          if ((a > b) == up) { keys[lo] = b; keys[hi] = a; }
+        }
       }
     }
   }
@@ -195,7 +218,7 @@ knn_refine_kernel(const float* __restrict__ emb, const float* __restrict__ amag,
   for (int i = threadIdx.x; i < kprime; i += blockDim.x) {
     long long* c = out + static_cast<int64_t>(i) * 3;
     if (i < static_cast<int>(m)) {
-      const uint64_t key = keys[i];
+      const uint64_t key = sorted[i];
       const uint64_t pos = knn_key_pos(key);
       const int64_t local = static_cast<int64_t>(pos - pos_base);
       c[0] = static_cast<long long>(key);
