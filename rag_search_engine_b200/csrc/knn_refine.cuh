@@ -21,7 +21,8 @@ namespace rse {
 // list overflowed, or fewer than K' rows survived (a corpus/query the bound does not cover: fewer
 // than K' valid rows, zero or non-finite query norm).  `normalized`: the survivor values are cos~
 // (knn_tc3, unit-norm operands) instead of dot~/|a| (knn_tc / knn_tc2), so the band is not scaled by |q|.
-// smem: cap * 8 bytes (pairs) — reused for the exact keys.
+// smem: kRefineSmemBytes = 80 KB (the pairs, cap * 8 <= 64 KB; later the row staging area, or the keys of the slow
+// path) + 8 KB (keys of the fast path).
 // 256 threads, 256 histogram bins (one per thread): the digit d with  sum(hist[0..d-1]) < need <= sum(hist[0..d]).
 // The thread that owns d writes *out_digit = d and *out_before = sum(hist[0..d-1]); *out_digit stays 256 when
 // the histogram holds fewer than `need` entries.  s_warp: 8 words of scratch.  Ends with a barrier.
@@ -47,6 +48,78 @@ __device__ __forceinline__ void block_pick_digit(const unsigned int* s_hist, uns
 }
 
 
+// 16-byte asynchronous copy global -> shared, L2 only (the staged rows are read once)
+__device__ __forceinline__ void cp_async16_cg(uint32_t smem_dst, const void* gmem_src) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_dst), "l"(gmem_src) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+constexpr int kRefineFastKeys = 512;                                  // the staged path sorts up to this many keys
+constexpr int kRefineChunkFloats = 32;                                // one 128-byte line per row per stage
+constexpr int kRefineStageBytes = 32 * kRefineChunkFloats * 4;        // 32 rows of a warp: 4 KB
+constexpr int kRefineStagingBytes = 20 * kRefineStageBytes;           // 80 KB: the pairs (cap * 8 = 64 KB), later 20 stages
+constexpr int kRefineSmemBytes = kRefineStagingBytes + 2 * kRefineFastKeys * 8;   // + keys and rank-sorted keys
+static_assert(kTcCandCap * 8 <= kRefineStagingBytes, "the survivor pairs must fit the staging region");
+
+// The exact dot product of the warp's 32 rows (lane l owns row `myrow` of lane l) with the query in s_q, rows STAGED
+// through shared memory: each 128-byte line of a row arrives as one coalesced request (8 lanes x 16 B, cp.async, L2
+// only) instead of 32 lanes pulling 16 B each from 32 different rows (r02 timeline: lane-per-row loads made this phase
+// 42 of the kernel's 64 us on the isotropic corpus — 39 k random rows per launch at 1.4 TB/s; staged: 13 us with two
+// stages).  Lane l then walks ITS row in order from shared memory (the reference's sequential sum); float4 j of row r
+// sits at slot j ^ (r & 7), so the 8 lanes of a quarter-warp hit 8 different 16-byte bank groups.  STAGES - 1 lines
+// are in flight while one is summed.
+template <bool FMA, int STAGES>
+__device__ __forceinline__ float staged_row_dot(const float* __restrict__ emb, uint32_t myrow, const float* s_q,
+                                                unsigned char* wbuf, int lane) {
+  constexpr int kChunks = kScanD / kRefineChunkFloats;                     // 12
+  const uint32_t wbuf_s = smem_u32(wbuf);
+  auto issue = [&](int k) {
+    if (k < kChunks) {
+#pragma unroll
+      for (int it = 0; it < 8; ++it) {
+        const int r = 4 * it + (lane >> 3);
+        const uint32_t row = __shfl_sync(0xFFFFFFFFu, myrow, r);
+        cp_async16_cg(wbuf_s + (k % STAGES) * kRefineStageBytes + r * 128 + (((lane & 7) ^ (r & 7)) << 4),
+                      emb + static_cast<int64_t>(row) * kScanD + k * kRefineChunkFloats + (lane & 7) * 4);
+      }
+    }
+    cp_async_commit();                                                     // (an empty group past the last line)
+  };
+#pragma unroll
+  for (int k = 0; k < STAGES - 1; ++k) issue(k);
+  float acc = 0.0f;
+#pragma unroll 1
+  for (int k = 0; k < kChunks; ++k) {
+    issue(k + STAGES - 1);
+    cp_async_wait<STAGES - 1>();
+    __syncwarp();
+    const unsigned char* rb = wbuf + (k % STAGES) * kRefineStageBytes + lane * 128;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const float4 a = *reinterpret_cast<const float4*>(rb + ((j ^ (lane & 7)) << 4));
+      const float4 qv = *reinterpret_cast<const float4*>(s_q + k * kRefineChunkFloats + 4 * j);
+      acc = mac<FMA>(acc, a.x, qv.x);
+      acc = mac<FMA>(acc, a.y, qv.y);
+      acc = mac<FMA>(acc, a.z, qv.z);
+      acc = mac<FMA>(acc, a.w, qv.w);
+    }
+    __syncwarp();                                                          // the stage is free for line k + STAGES
+  }
+  cp_async_wait<0>();
+  return acc;
+}
+
+#ifdef RSE_REFINE_TIMING
+__device__ unsigned long long g_refine_ns[8 * 4096];
+#define RT_STAMP(k) do { if (threadIdx.x == 0 && blockIdx.x < 4096) { unsigned long long t_; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_)); g_refine_ns[blockIdx.x * 8 + (k)] = t_; } } while (0)
+#define RT_SYNC() __syncthreads()
+#else
+#define RT_STAMP(k)
+#define RT_SYNC()
+#endif
+
 template <bool FMA>
 __global__ void __launch_bounds__(kSelThreads, 2)
 knn_refine_kernel(const float* __restrict__ emb, const float* __restrict__ amag, const float* __restrict__ q,
@@ -63,8 +136,10 @@ knn_refine_kernel(const float* __restrict__ emb, const float* __restrict__ amag,
   __shared__ unsigned int s_hist[256];
   __shared__ unsigned int s_prefix, s_need, s_m, s_digit, s_before;
   __shared__ unsigned int s_warp[8];
+  __shared__ uint32_t s_and[kSelThreads / 32], s_or[kSelThreads / 32];
   __shared__ uint32_t s_rows[kTcRefineCap];
   const int qi = blockIdx.x;
+  if (thr2 == nullptr) RT_STAMP(0);
   // second-chance pass: only the queries the second threshold kernel re-armed (thr2 finite), and only if any
   if (thr2 != nullptr && (gate[qi >> 8] == 0u || status[qi] == 0 || !(thr2[qi] < __int_as_float(0x7F800000)))) return;
   const unsigned int cnt = cand_count[qi];
@@ -85,17 +160,50 @@ knn_refine_kernel(const float* __restrict__ emb, const float* __restrict__ amag,
   const int n = overflow ? cap : static_cast<int>(cnt);
   // (knn_tc3 never emits an empty slot or a zero row: its thresholds are positive and those rows read cos~ = 0;
   //  knn_tc / knn_tc2 check |a|^2 in their epilogues)
-  for (int i = threadIdx.x; i < n; i += blockDim.x) pairs[i] = cand_pairs[static_cast<int64_t>(qi) * cap + i];
+  // the bits every survivor's key shares (AND == OR) need no histogram pass: cos~ of the survivors sits in a narrow
+  // range above the threshold, so the sign/exponent byte is constant and the first radix pass — 2300 shared-memory
+  // atomics on ONE bin — is skipped
+  uint32_t k_and = 0xFFFFFFFFu, k_or = 0u;
+  // (eight loads in flight per thread: a load -> store loop is one HBM round trip per 256 pairs, 6 us of the kernel)
+  for (int i0 = threadIdx.x; i0 < n; i0 += 8 * kSelThreads) {
+    uint2 pr[8];
+#pragma unroll
+    for (int u = 0; u < 8; ++u)
+      if (i0 + u * kSelThreads < n) pr[u] = cand_pairs[static_cast<int64_t>(qi) * cap + i0 + u * kSelThreads];
+#pragma unroll
+    for (int u = 0; u < 8; ++u)
+      if (i0 + u * kSelThreads < n) {
+        pairs[i0 + u * kSelThreads] = pr[u];
+        const uint32_t key = ~f32_orderable(pr[u].y);
+        k_and &= key; k_or |= key;
+      }
+  }
   for (int i = threadIdx.x; i < kScanD; i += blockDim.x) s_q[i] = q[static_cast<int64_t>(qi) * kScanD + i];
+  k_and = __reduce_and_sync(0xFFFFFFFFu, k_and);
+  k_or = __reduce_or_sync(0xFFFFFFFFu, k_or);
+  if ((threadIdx.x & 31) == 0) { s_and[threadIdx.x >> 5] = k_and; s_or[threadIdx.x >> 5] = k_or; }
   if (threadIdx.x == 0) { s_prefix = 0u; s_need = static_cast<unsigned int>(kprime < n ? kprime : n); s_m = 0u; }
   __syncthreads();
+#pragma unroll
+  for (int w = 0; w < kSelThreads / 32; ++w) { k_and &= s_and[w]; k_or |= s_or[w]; }
+  const uint32_t same_bits = ~(k_and ^ k_or);                             // 1 = the bit is identical in every key
+  RT_STAMP(1);
 
   // ---- (a) K'-th largest approximate value: MSD radix select (4 x 8 bits) on ~orderable(s)
   //      (descending s == ascending ~orderable)
   uint32_t resolved_mask = 0u;
   if (n > kprime) {
-    for (int pass = 0; pass < 4; ++pass) {
+    // Three passes resolve the top 24 bits of the K'-th key; the low byte is left at its largest value, i.e. s_K is
+    // UNDER-estimated by at most 2^-15 of its magnitude (4e-6 against the 5e-3 band): the cut only moves down, the
+    // kept set stays a superset of the exact top-K' (the same holds for the second-chance bound s' below).
+    for (int pass = 0; pass < 3; ++pass) {
       const int shift = 24 - 8 * pass;
+      if (((same_bits >> shift) & 0xFFu) == 0xFFu) {                       // block-uniform: every key has this byte
+        if (threadIdx.x == 0) s_prefix = s_prefix | (k_and & (0xFFu << shift));
+        resolved_mask |= 0xFFu << shift;
+        __syncthreads();
+        continue;
+      }
       for (int i = threadIdx.x; i < 256; i += blockDim.x) s_hist[i] = 0u;
       __syncthreads();
       const uint32_t prefix = s_prefix;
@@ -113,6 +221,11 @@ knn_refine_kernel(const float* __restrict__ emb, const float* __restrict__ amag,
       __syncthreads();
     }
   }
+  if (n > kprime) {
+    if (threadIdx.x == 0) s_prefix = s_prefix | 0xFFu;
+    __syncthreads();
+  }
+  RT_STAMP(2);
   if (arm) {                                                               // n = cap > K': s_prefix is s' of the kept survivors
     if (threadIdx.x == 0) {
       const float s_k = __uint_as_float(f32_from_orderable(~s_prefix));
@@ -143,6 +256,7 @@ knn_refine_kernel(const float* __restrict__ emb, const float* __restrict__ amag,
   }
   __syncthreads();
   const unsigned int m = s_m;
+  RT_STAMP(3);
   if (m > kTcRefineCap || m < static_cast<unsigned int>(kprime)) {         // refined list overflow (mass ties) / too few rows
     if (threadIdx.x == 0) status[qi] = 1;
     for (int i = threadIdx.x; i < kprime * 3; i += blockDim.x) out[i] = -1ll;
@@ -153,45 +267,70 @@ knn_refine_kernel(const float* __restrict__ emb, const float* __restrict__ amag,
     if (thr2 != nullptr && counters) atomicAdd(&counters[3], 1ull);      // answered by the second-chance pass
   }
 
-  // ---- (b) exact distances, lane-per-row from global memory (the reference's sequential sum).  The products are
-  //      independent of the running sum, so 24 float4 loads are in flight per thread before the first add (r02 ncu:
-  //      with 8 in flight this loop held 34 % of the kernel's stall samples — twelve dependent round trips to HBM
-  //      per row — and the barrier-per-stage bitonic sort below another 30 %)
-  unsigned long long* keys = reinterpret_cast<unsigned long long*>(smem_raw);   // pairs are dead
-  __syncthreads();
+  // ---- (b) exact distances: one lane per row, the reference's sequential fp32 sum
+  const double sbq = sb[qi];
+  const bool fast = m <= static_cast<unsigned int>(kRefineFastKeys);
+  // fast path keys live AFTER the pairs region, which becomes the staging area; the slow path (a refined list above
+  // 512 rows: mass ties, second-chance leftovers) keeps the r01 layout — keys over the dead pairs, lane-per-row loads
+  unsigned long long* keys = fast ? reinterpret_cast<unsigned long long*>(smem_raw + kRefineStagingBytes)
+                                  : reinterpret_cast<unsigned long long*>(smem_raw);
+  __syncthreads();                                                         // pairs are dead
   int m2 = 2;
   while (m2 < static_cast<int>(m)) m2 <<= 1;
-  const double sbq = sb[qi];
-  for (int i = threadIdx.x; i < m2; i += blockDim.x) {
-    unsigned long long key = ~0ull;
-    if (i < static_cast<int>(m)) {
-      const uint32_t row = s_rows[i];
-      const float4* rp = reinterpret_cast<const float4*>(emb + static_cast<int64_t>(row) * kScanD);
-      float acc = 0.0f;
-#pragma unroll 1
-      for (int c0 = 0; c0 < kScanD / 4; c0 += 24) {
-        float4 a[24];
-#pragma unroll
-        for (int c = 0; c < 24; ++c) a[c] = __ldg(rp + c0 + c);
-#pragma unroll
-        for (int c = 0; c < 24; ++c) {
-          acc = mac<FMA>(acc, a[c].x, s_q[4 * (c0 + c) + 0]);
-          acc = mac<FMA>(acc, a[c].y, s_q[4 * (c0 + c) + 1]);
-          acc = mac<FMA>(acc, a[c].z, s_q[4 * (c0 + c) + 2]);
-          acc = mac<FMA>(acc, a[c].w, s_q[4 * (c0 + c) + 3]);
-        }
+  if (fast) {
+    // 20 stages of 4 KB are shared out among the warps that own rows: 4 per warp up to 160 rows (the usual K' + band),
+    // 3 up to 192, 2 beyond
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int n_active = m >= static_cast<unsigned int>(kSelThreads) ? kSelThreads / 32 : static_cast<int>((m + 31u) >> 5);
+    const int per_warp = (kRefineStagingBytes / kRefineStageBytes) / n_active;
+    const int stages = per_warp >= 4 ? 4 : per_warp;                       // 8 warps -> 2
+    unsigned char* wbuf = smem_raw + warp * stages * kRefineStageBytes;
+    for (int base = warp * 32; base < static_cast<int>(m); base += kSelThreads) {
+      const int i = base + lane;
+      const uint32_t myrow = s_rows[i < static_cast<int>(m) ? i : static_cast<int>(m) - 1];
+      float acc;
+      if (stages == 4) acc = staged_row_dot<FMA, 4>(emb, myrow, s_q, wbuf, lane);
+      else if (stages == 3) acc = staged_row_dot<FMA, 3>(emb, myrow, s_q, wbuf, lane);
+      else acc = staged_row_dot<FMA, 2>(emb, myrow, s_q, wbuf, lane);
+      if (i < static_cast<int>(m)) {
+        const float d = cosine_tail(acc, sqrt(static_cast<double>(__ldg(amag + myrow))), sbq);
+        keys[i] = knn_key(f32_orderable(__float_as_uint(d)), pos_base + static_cast<uint64_t>(myrow));
       }
-      const float d = cosine_tail(acc, sqrt(static_cast<double>(__ldg(amag + row))), sbq);
-      key = knn_key(f32_orderable(__float_as_uint(d)), pos_base + static_cast<uint64_t>(row));
     }
-    keys[i] = key;
+  } else {
+    for (int i = threadIdx.x; i < m2; i += blockDim.x) {
+      unsigned long long key = ~0ull;
+      if (i < static_cast<int>(m)) {
+        const uint32_t row = s_rows[i];
+        const float4* rp = reinterpret_cast<const float4*>(emb + static_cast<int64_t>(row) * kScanD);
+        float acc = 0.0f;
+#pragma unroll 1
+        for (int c0 = 0; c0 < kScanD / 4; c0 += 24) {
+          float4 a[24];
+#pragma unroll
+          for (int c = 0; c < 24; ++c) a[c] = __ldg(rp + c0 + c);
+#pragma unroll
+          for (int c = 0; c < 24; ++c) {
+            acc = mac<FMA>(acc, a[c].x, s_q[4 * (c0 + c) + 0]);
+            acc = mac<FMA>(acc, a[c].y, s_q[4 * (c0 + c) + 1]);
+            acc = mac<FMA>(acc, a[c].z, s_q[4 * (c0 + c) + 2]);
+            acc = mac<FMA>(acc, a[c].w, s_q[4 * (c0 + c) + 3]);
+          }
+        }
+        const float d = cosine_tail(acc, sqrt(static_cast<double>(__ldg(amag + row))), sbq);
+        key = knn_key(f32_orderable(__float_as_uint(d)), pos_base + static_cast<uint64_t>(row));
+      }
+      keys[i] = key;
+    }
   }
+  RT_SYNC();
+  RT_STAMP(4);
   // ---- (c) sort the keys (all distinct: the position is part of the key), emit the first K'
   const unsigned long long* sorted = keys;
-  if (m <= 512u) {
+  if (fast) {
     // rank counting: every key is compared with all the others straight from shared memory (broadcast reads), no
     // barrier per stage — K' plus a thin band is a few hundred keys
-    unsigned long long* dst = keys + kTcRefineCap;                  // the upper half of the 64 KB region
+    unsigned long long* dst = keys + kRefineFastKeys;
     __syncthreads();
     for (int i = threadIdx.x; i < static_cast<int>(m); i += blockDim.x) {
       const unsigned long long me = keys[i];
@@ -215,6 +354,7 @@ knn_refine_kernel(const float* __restrict__ emb, const float* __restrict__ amag,
     }
   }
   __syncthreads();
+  RT_STAMP(5);
   for (int i = threadIdx.x; i < kprime; i += blockDim.x) {
     long long* c = out + static_cast<int64_t>(i) * 3;
     if (i < static_cast<int>(m)) {
@@ -228,6 +368,11 @@ knn_refine_kernel(const float* __restrict__ emb, const float* __restrict__ amag,
       c[0] = -1ll; c[1] = -1ll; c[2] = -1ll;
     }
   }
+  RT_SYNC();
+  RT_STAMP(6);
+#ifdef RSE_REFINE_TIMING
+  if (threadIdx.x == 0 && blockIdx.x < 4096) g_refine_ns[blockIdx.x * 8 + 7] = m;
+#endif
 }
 
 // Host fallback of the tensor-core path (rse.cu knn_local_finish): the flagged queries of a batch are gathered into

@@ -444,17 +444,17 @@ int make_tmap_lines(rse_index* h, CUtensorMap* out, const void* base, int64_t li
 int knn_tc_refine(rse_index* h, const float* q_dev, const double* sb, int nqb, int kprime, long long* cand_dev,
                   int* status_dev, const float* thr2, const unsigned int* gate, float* thr2_out, unsigned int* gate_out) {
   if (!(h->attr_mask & (1u << 10))) {
-    CK(cudaFuncSetAttribute(knn_refine_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kTcCandCap * 8));
-    CK(cudaFuncSetAttribute(knn_refine_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kTcCandCap * 8));
+    CK(cudaFuncSetAttribute(knn_refine_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kRefineSmemBytes));
+    CK(cudaFuncSetAttribute(knn_refine_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kRefineSmemBytes));
     h->attr_mask |= 1u << 10;
   }
   if (h->fma)
-    knn_refine_kernel<true><<<nqb, kSelThreads, kTcCandCap * 8, h->stream>>>(
+    knn_refine_kernel<true><<<nqb, kSelThreads, kRefineSmemBytes, h->stream>>>(
         h->emb, h->amag, q_dev, sb, static_cast<const uint2*>(h->tc_rows.p),
         static_cast<unsigned int*>(h->tc_cnt.p), kTcCandCap, kprime, h->pos_base, h->rowid, h->movie_idx,
         cand_dev, status_dev, 1, thr2, gate, h->dev_counters, thr2_out, gate_out);
   else
-    knn_refine_kernel<false><<<nqb, kSelThreads, kTcCandCap * 8, h->stream>>>(
+    knn_refine_kernel<false><<<nqb, kSelThreads, kRefineSmemBytes, h->stream>>>(
         h->emb, h->amag, q_dev, sb, static_cast<const uint2*>(h->tc_rows.p),
         static_cast<unsigned int*>(h->tc_cnt.p), kTcCandCap, kprime, h->pos_base, h->rowid, h->movie_idx,
         cand_dev, status_dev, 1, thr2, gate, h->dev_counters, thr2_out, gate_out);
@@ -2553,5 +2553,12 @@ int rse_hybrid_drain(rse_index* h, int32_t* out_dropped) {
   if (out_dropped) *out_dropped = dropped;
   return RSE_OK;
 }
+
+#ifdef RSE_REFINE_TIMING
+// debug build only (-DRSE_REFINE_TIMING): per-CTA globaltimer stamps of the last knn_refine_kernel launch
+int rse_debug_refine_ns(unsigned long long* out, int n_words) {
+  return cudaMemcpyFromSymbol(out, rse::g_refine_ns, sizeof(unsigned long long) * n_words) == cudaSuccess ? 0 : -2;
+}
+#endif
 
 }  // extern "C"
