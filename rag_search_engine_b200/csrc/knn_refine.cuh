@@ -129,7 +129,7 @@ knn_refine_kernel(const float* __restrict__ emb, const float* __restrict__ amag,
                   long long* __restrict__ cand, int* __restrict__ status, int normalized,
                   const float* __restrict__ thr2, const unsigned int* __restrict__ gate,
                   unsigned long long* __restrict__ counters, float* __restrict__ thr2_out,
-                  unsigned int* __restrict__ gate_out) {
+                  unsigned int* __restrict__ gate_out, const float* __restrict__ tverify) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   uint2* pairs = reinterpret_cast<uint2*>(smem_raw);                       // [cap]
   __shared__ float s_q[kScanD];
@@ -192,7 +192,8 @@ knn_refine_kernel(const float* __restrict__ emb, const float* __restrict__ amag,
   // ---- (a) K'-th largest approximate value: MSD radix select (4 x 8 bits) on ~orderable(s)
   //      (descending s == ascending ~orderable)
   uint32_t resolved_mask = 0u;
-  if (n > kprime) {
+  const bool select = n > kprime || (tverify != nullptr && n == kprime);   // (the verified path needs s_K even then)
+  if (select) {
     // Three passes resolve the top 24 bits of the K'-th key; the low byte is left at its largest value, i.e. s_K is
     // UNDER-estimated by at most 2^-15 of its magnitude (4e-6 against the 5e-3 band): the cut only moves down, the
     // kept set stays a superset of the exact top-K' (the same holds for the second-chance bound s' below).
@@ -221,12 +222,20 @@ knn_refine_kernel(const float* __restrict__ emb, const float* __restrict__ amag,
       __syncthreads();
     }
   }
-  if (n > kprime) {
+  if (select) {
     if (threadIdx.x == 0) s_prefix = s_prefix | 0xFFu;
     __syncthreads();
   }
   RT_STAMP(2);
-  if (arm) {                                                               // n = cap > K': s_prefix is s' of the kept survivors
+  // Sample path (tverify): the filter's cut came from the probe's j-th best sample value T, j << K' — tight, but
+  // only valid if at least K' rows reach T, i.e. if s_K >= T (then every row of the exact top-K', cos~ >= s_K - 2 eps,
+  // passed the filter's cut T - 2 eps - 1e-6; the 1e-7 absorbs the rounding of T = 1 - (1 - cos~)).  s_K here is a
+  // lower bound of the true value (low byte unresolved), so the test is conservative.  When it fails, s_K IS still
+  // the K'-th largest cos~ overall (everything above the filter's cut is in the list), so the second chance runs
+  // with the exact bound s_K - 2 eps.
+  const bool reverify = !overflow && select && tverify != nullptr && thr2_out != nullptr &&
+                        !(__uint_as_float(f32_from_orderable(~s_prefix)) >= tverify[qi] - 1e-7f);
+  if (arm || reverify) {                                                   // (arm: n = cap > K', s_prefix is s' of the kept survivors)
     if (threadIdx.x == 0) {
       const float s_k = __uint_as_float(f32_from_orderable(~s_prefix));
       const float cut2 = s_k - 2.0f * kTcEps - 1e-6f;
@@ -242,7 +251,7 @@ knn_refine_kernel(const float* __restrict__ emb, const float* __restrict__ amag,
   }
   // s_K (exact K'-th largest approximate value), cut = s_K - 2 eps |q|  (slack for f32 rounding)
   float cut = -__int_as_float(0x7F800000);
-  if (n > kprime) {
+  if (select) {
     const float s_k = __uint_as_float(f32_from_orderable(~s_prefix));
     const float qn = normalized ? 1.0f : static_cast<float>(sb[qi]);
     cut = s_k - (2.0f * kTcEps + 1e-6f) * qn - 1e-30f;

@@ -338,6 +338,47 @@ tc3_shadow_kernel(const float* __restrict__ emb, const float* __restrict__ amag,
   }
 }
 
+// The probe's SAMPLE (r02): sample row i is one row of the group [i*stride, (i+1)*stride) of corpus rows, at a
+// hashed offset that depends on i only — a stratified sample, independent of the data, stored as its own small
+// shadow in the same tiled layout (n_rows / stride rows, zero-padded to whole tiles).  Because the choice is
+// independent of the data, the number X of sample rows among ANY K' rows (the exact top-K' of a query) is a sum of
+// independent Bernoulli draws with mean K'/stride, whose upper tail is bounded by Binomial(K', 1/stride)
+// (Hoeffding 1956).  rse.cu turns that into the probe's order statistic; the result is VERIFIED in the refine
+// kernel, so the tail only costs a second filter pass, never a wrong answer.
+__device__ __forceinline__ int64_t t3_sample_source(int64_t i, int stride, int64_t n_rows) {
+  uint32_t x = static_cast<uint32_t>(i) * 0x9E3779B1u;
+  x ^= x >> 15; x *= 0x85EBCA77u; x ^= x >> 13; x *= 0xC2B2AE3Du; x ^= x >> 16;
+  const int64_t g = i * stride;
+  const int64_t gs = n_rows - g < stride ? n_rows - g : stride;
+  return g + static_cast<int64_t>(x % static_cast<uint32_t>(gs));
+}
+__global__ void __launch_bounds__(256)
+tc3_sample_kernel(const float* __restrict__ emb, const float* __restrict__ amag, int64_t n_rows, int stride,
+                  int64_t n_sample, __half* __restrict__ sample) {
+  const int lane = threadIdx.x & 31;
+  const int64_t warp0 = (static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
+  const int64_t n_warps = (static_cast<int64_t>(gridDim.x) * blockDim.x) >> 5;
+  for (int64_t i = warp0; i < n_sample; i += n_warps) {
+    const int64_t r = t3_sample_source(i, stride, n_rows);
+    const float am = __ldg(amag + r);
+    float inv = 0.0f;                                                    // empty slots stay zero rows
+    if (am > 0.0f && am < __int_as_float(0x7F800000)) inv = static_cast<float>(1.0 / sqrt(static_cast<double>(am)));
+    const float4* src = reinterpret_cast<const float4*>(emb + r * kScanD);
+#pragma unroll
+    for (int j = 0; j < kScanD / 128; ++j) {
+      const int f4 = j * 32 + lane;
+      const float4 f = __ldg(src + f4);
+      const __half2 lo = __floats2half2_rn(__fmul_rn(f.x, inv), __fmul_rn(f.y, inv));
+      const __half2 hi = __floats2half2_rn(__fmul_rn(f.z, inv), __fmul_rn(f.w, inv));
+      uint2 o;
+      o.x = *reinterpret_cast<const uint32_t*>(&lo);
+      o.y = *reinterpret_cast<const uint32_t*>(&hi);
+      const int kb = f4 >> 4, within = f4 & 15;
+      reinterpret_cast<uint2*>(sample + t3_shadow_offset(i, kb))[within] = o;
+    }
+  }
+}
+
 // q16[q] = fp16_rn(q / ||q||) for q < nq (||q|| = sb[q], the K1 factor), zero rows for the padding and
 // for queries whose norm is zero / non-finite (those get thr = +inf and are re-run exactly).
 __global__ void __launch_bounds__(96)
@@ -386,7 +427,7 @@ __global__ void tc3_threshold_kernel(const SelState* __restrict__ st, const doub
 constexpr int kT3SelMax = 2048;
 __global__ void __launch_bounds__(256)
 tc3_probe_threshold_kernel(const uint32_t* __restrict__ dist, int64_t ld, int nq, int kprime,
-                           const double* __restrict__ sb, float* __restrict__ thr) {
+                           const double* __restrict__ sb, float* __restrict__ thr, float* __restrict__ tver) {
   __shared__ uint32_t s_key[kT3SelMax];
   __shared__ unsigned int s_hist[256];
   __shared__ unsigned int s_prefix, s_need, s_fail, s_digit, s_before;
@@ -394,7 +435,7 @@ tc3_probe_threshold_kernel(const uint32_t* __restrict__ dist, int64_t ld, int nq
   const int q = blockIdx.x;                        // grid = the padded query count (a multiple of 256)
   const float inf = __int_as_float(0x7F800000);
   if (q >= nq || !(sb[q] > 0.0 && sb[q] < 1e300)) {
-    if (threadIdx.x == 0) thr[q] = inf;
+    if (threadIdx.x == 0) { thr[q] = inf; if (tver) tver[q] = inf; }
     return;
   }
   const int n = static_cast<int>(ld);
@@ -426,6 +467,11 @@ tc3_probe_threshold_kernel(const uint32_t* __restrict__ dist, int64_t ld, int nq
       const float tau = __uint_as_float(f32_from_orderable(s_prefix));   // K'-th smallest d~ (NaN if it is a sentinel)
       const float cut = 1.0f - tau - 2.0f * kTcEps - 1e-6f;
       if (cut > 1e-6f) t = cut;
+      // the un-banded bound the refine kernel verifies (sample path: kprime here is the probe's order statistic j,
+      // and "the K'-th largest cos~ of the survivors >= 1 - tau" is what makes the cut valid)
+      if (tver) tver[q] = cut > 1e-6f ? 1.0f - tau : inf;
+    } else if (tver) {
+      tver[q] = inf;
     }
     thr[q] = t;
   }

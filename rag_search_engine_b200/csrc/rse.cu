@@ -151,6 +151,14 @@ struct rse_index {
   DevBuf fb_list, fb_q, fb_sb, fb_cand;       // exact-scan fallback of flagged queries, gathered (knn_local_finish)
   // fp16 normalised shadow of the corpus for knn_tc3 (built lazily at the first tensor-core batch)
   DevBuf tc_shadow, tc_q16;
+  // the probe's stratified row sample (knn_tc3.cuh tc3_sample_kernel): one row of every sample_stride, own small shadow
+  DevBuf tc_sample;
+  CUtensorMap tmap_s16{};
+  int64_t sample_tiles = 0;        // 0 = no sample (small corpus, RSE_TC_SAMPLE=0): the probe strides over the main shadow
+  int sample_stride = 32;          // RSE_TC_SAMPLE_STRIDE
+  int probe_rank = 0;              // RSE_TC_PROBE_RANK: force the probe's order statistic j (tests: 1 = always too tight)
+  bool use_sample = true;          // RSE_TC_SAMPLE=0 switches the sample path off
+  int sample_min_tiles = 64;       // RSE_TC_SAMPLE_MIN_TILES (tests lower it to exercise the path on small corpora)
   int shadow_state = 0;            // 0 = not built, 1 = usable, -1 = corpus has non-finite norms: exact scan only
   CUtensorMap tmap_a16{};          // [n_rows][384] f16, box {64, 128}, SWIZZLE_128B
   CUtensorMap tmap_q16{};          // [256][384] f16, box {64, 128}
@@ -270,6 +278,8 @@ void release_embeddings(rse_index* h) {
   free_ptr(h->movie_idx);
   h->n_rows = 0; h->dim = 0;
   free_buf(h->tc_shadow);
+  free_buf(h->tc_sample);
+  h->sample_tiles = 0;
   h->shadow_state = 0;
 }
 
@@ -442,7 +452,8 @@ int make_tmap_lines(rse_index* h, CUtensorMap* out, const void* base, int64_t li
 // refine + exact re-score + emit for one block of queries whose survivors are in tc_rows / tc_cnt.
 // thr2 / gate != NULL: the second-chance pass (only the queries tc3_second_threshold_kernel re-armed).
 int knn_tc_refine(rse_index* h, const float* q_dev, const double* sb, int nqb, int kprime, long long* cand_dev,
-                  int* status_dev, const float* thr2, const unsigned int* gate, float* thr2_out, unsigned int* gate_out) {
+                  int* status_dev, const float* thr2, const unsigned int* gate, float* thr2_out, unsigned int* gate_out,
+                  const float* tverify) {
   if (!(h->attr_mask & (1u << 10))) {
     CK(cudaFuncSetAttribute(knn_refine_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kRefineSmemBytes));
     CK(cudaFuncSetAttribute(knn_refine_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kRefineSmemBytes));
@@ -452,12 +463,12 @@ int knn_tc_refine(rse_index* h, const float* q_dev, const double* sb, int nqb, i
     knn_refine_kernel<true><<<nqb, kSelThreads, kRefineSmemBytes, h->stream>>>(
         h->emb, h->amag, q_dev, sb, static_cast<const uint2*>(h->tc_rows.p),
         static_cast<unsigned int*>(h->tc_cnt.p), kTcCandCap, kprime, h->pos_base, h->rowid, h->movie_idx,
-        cand_dev, status_dev, 1, thr2, gate, h->dev_counters, thr2_out, gate_out);
+        cand_dev, status_dev, 1, thr2, gate, h->dev_counters, thr2_out, gate_out, tverify);
   else
     knn_refine_kernel<false><<<nqb, kSelThreads, kRefineSmemBytes, h->stream>>>(
         h->emb, h->amag, q_dev, sb, static_cast<const uint2*>(h->tc_rows.p),
         static_cast<unsigned int*>(h->tc_cnt.p), kTcCandCap, kprime, h->pos_base, h->rowid, h->movie_idx,
-        cand_dev, status_dev, 1, thr2, gate, h->dev_counters, thr2_out, gate_out);
+        cand_dev, status_dev, 1, thr2, gate, h->dev_counters, thr2_out, gate_out, tverify);
   LAUNCHED(h);
   return RSE_OK;
 }
@@ -505,8 +516,42 @@ int ensure_shadow(rse_index* h) {
   // the tiled shadow as a 2-D array of 128-byte lines: [n_pad * 6 lines][64 halves], box = 128 lines = one stage
   int rc = make_tmap_lines(h, &h->tmap_a16, h->tc_shadow.p, n_pad * kT3KBlocks, kT3HalfRows);
   if (rc != RSE_OK) return rc;
+  // the probe's sample: worth its own matrix once it fills every cluster with a few tiles (>= 64 tiles = 512 k rows
+  // at stride 32); smaller corpora keep the strided-tile probe over the main shadow
+  h->sample_tiles = 0;
+  const int64_t n_sample = (h->n_rows + h->sample_stride - 1) / h->sample_stride;
+  if (h->use_sample && n_sample >= static_cast<int64_t>(h->sample_min_tiles) * kT3TileRows) {
+    const int64_t s_pad = (n_sample + kT3TileRows - 1) / kT3TileRows * kT3TileRows;
+    const size_t s_bytes = sizeof(__half) * static_cast<size_t>(s_pad) * kScanD;
+    ENSURE(h->tc_sample, s_bytes);
+    const size_t s_tail0 = sizeof(__half) * static_cast<size_t>(s_pad - kT3TileRows) * kScanD;
+    CK(cudaMemsetAsync(static_cast<char*>(h->tc_sample.p) + s_tail0, 0, s_bytes - s_tail0, h->stream));
+    tc3_sample_kernel<<<grid, 256, 0, h->stream>>>(h->emb, h->amag, h->n_rows, h->sample_stride, n_sample,
+                                                   static_cast<__half*>(h->tc_sample.p));
+    LAUNCHED(h);
+    rc = make_tmap_lines(h, &h->tmap_s16, h->tc_sample.p, s_pad * kT3KBlocks, kT3HalfRows);
+    if (rc != RSE_OK) return rc;
+    h->sample_tiles = s_pad / kT3TileRows;
+  }
   h->shadow_state = 1;
   return RSE_OK;
+}
+
+// The probe's order statistic on the sample path: the smallest j with P(Binomial(K', 1/stride) >= j) <= 1e-7.  The
+// sample's j-th best value exceeds the true K'-th best only if at least j of the (at most K' - 1) rows above it were
+// drawn; the draw is independent of the data (tc3_sample_kernel), so that probability is bounded by the binomial tail
+// whatever the corpus looks like.  j <= K' (the sample's K'-th best is always a valid bound).
+int sample_probe_rank(int kprime, int stride) {
+  const double p = 1.0 / stride, q = 1.0 - p;
+  // tail(j) = sum_{i >= j} C(K', i) p^i q^(K'-i); walk the pmf up from i = 0
+  double pmf = std::pow(q, kprime), cdf = 0.0;
+  for (int j = 0; j < kprime; ++j) {
+    // here pmf = P(X = j), cdf = P(X < j)
+    if (1.0 - cdf <= 1e-7) return std::max(1, j);
+    cdf += pmf;
+    pmf *= static_cast<double>(kprime - j) / (j + 1) * p / q;
+  }
+  return kprime;
 }
 
 extern "C" int bm25_run_fwd(rse_index* h, int nq, int k, double k1, double b);   // = bm25_run (defined further down)
@@ -582,11 +627,26 @@ int knn_tc3_group(rse_index* h, const float* q_dev, const double* sb, int nqg, i
   int64_t tile_stride = std::max<int64_t>(1, std::min<int64_t>(kTcCandCap / (static_cast<int64_t>(h->survivor_div) * kprime), n_tiles / 64));
   int64_t n_probe = (n_tiles + tile_stride - 1) / tile_stride;
   while (n_probe * kT3TileRows < 8ll * kprime && tile_stride > 1) { tile_stride /= 2; n_probe = (n_tiles + tile_stride - 1) / tile_stride; }
+  // Sample path (r02): the probe runs over the stratified row sample instead of a strided subset of tiles, and the
+  // threshold is the sample's j-th best value, j = sample_probe_rank << K' — a few hundred survivors per query
+  // instead of K' * tile_stride; the refine kernel verifies the bound and re-arms the second chance when it was too
+  // tight (1e-7 per query by construction), so it needs the second chance enabled.
+  int kth = kprime;
+  bool sampled = false;
+  if (h->sample_tiles > 0 && h->second_chance && kprime <= 256) {
+    const int clusters_s = static_cast<int>(std::min<int64_t>(max_clusters, h->sample_tiles));
+    const int j = h->probe_rank > 0 ? std::min(h->probe_rank, kprime) : sample_probe_rank(kprime, h->sample_stride);
+    if (static_cast<int64_t>(clusters_s) * 2 * kT3ProbeTop >= 8ll * j &&
+        static_cast<int64_t>(clusters_s) * 2 * kT3ProbeTop <= kT3SelMax) {
+      sampled = true; kth = j; tile_stride = 1; n_probe = h->sample_tiles;
+    }
+  }
   const int64_t ld_probe = n_probe * kT3TileRows;
   const int probe_clusters = static_cast<int>(std::min<int64_t>(max_clusters, n_probe));
   const int grid_p = 2 * probe_clusters;
-  const bool sparse_probe = kprime <= 256 && static_cast<int64_t>(probe_clusters) * 2 * kT3ProbeTop >= 4ll * kprime &&
-                            static_cast<int64_t>(probe_clusters) * 2 * kT3ProbeTop <= kT3SelMax;
+  const bool sparse_probe = sampled ||
+                            (kprime <= 256 && static_cast<int64_t>(probe_clusters) * 2 * kT3ProbeTop >= 4ll * kprime &&
+                             static_cast<int64_t>(probe_clusters) * 2 * kT3ProbeTop <= kT3SelMax);
   // the dense probe (K' > 256, tiny corpora) keeps its per-query sample matrix and radix select: one block at a time
   if (!sparse_probe && nqg > kTcBN) {
     for (int b0 = 0; b0 < nqg; b0 += kTcBN) {
@@ -605,7 +665,7 @@ int knn_tc3_group(rse_index* h, const float* q_dev, const double* sb, int nqg, i
     if (rc != RSE_OK) return rc;
     h->tmap_q16_ok = true; h->tmap_q16_rows = nq_pad; h->tmap_q16_base = h->tc_q16.p;
   }
-  ENSURE(h->tc_thr, sizeof(float) * 2 * nq_pad);              // [0, nq_pad): first-pass thresholds, then the second chance's
+  ENSURE(h->tc_thr, sizeof(float) * 3 * nq_pad);              // first-pass cuts, the second chance's, the bounds to verify
   ENSURE(h->tc_rows, sizeof(uint2) * static_cast<size_t>(nq_pad) * kTcCandCap);
   ENSURE(h->tc_cnt, sizeof(unsigned int) * (nq_pad + kTcGroupBlocks + 4));   // [nq_pad ...): one second-chance gate per block
   ENSURE(h->sel, sizeof(SelState) * kTcBN);
@@ -624,9 +684,11 @@ int knn_tc3_group(rse_index* h, const float* q_dev, const double* sb, int nqg, i
   // 1. probe: approximate distances of a strided sample of tiles → K'-th smallest per query
   if (sparse_probe) {
     knn_tc3_kernel<2><<<grid_p, kT3Threads, kT3SmemBytes, h->stream>>>(
-        h->tmap_a16, h->tmap_q16, n_probe, tile_stride, nqg, nblk, nullptr, dist, ld_sel, nullptr, nullptr, 0, nullptr);
+        sampled ? h->tmap_s16 : h->tmap_a16, h->tmap_q16, n_probe, tile_stride, nqg, nblk, nullptr, dist, ld_sel, nullptr,
+        nullptr, 0, nullptr);
     LAUNCHED(h);
-    tc3_probe_threshold_kernel<<<nq_pad, 256, 0, h->stream>>>(dist, ld_sel, nqg, kprime, sb, thr);
+    tc3_probe_threshold_kernel<<<nq_pad, 256, 0, h->stream>>>(dist, ld_sel, nqg, kth, sb, thr,
+                                                              sampled ? thr + 2 * nq_pad : nullptr);
     LAUNCHED(h);
   } else {
     knn_tc3_kernel<0><<<grid_p, kT3Threads, kT3SmemBytes, h->stream>>>(
@@ -683,7 +745,8 @@ int knn_tc3_group(rse_index* h, const float* q_dev, const double* sb, int nqg, i
   unsigned int* gate = static_cast<unsigned int*>(h->tc_cnt.p) + nq_pad;
   {
     int rc = knn_tc_refine(h, q_dev, sb, nqg, kprime, cand_dev, status_dev, nullptr, nullptr,
-                           h->second_chance ? thr2 : nullptr, h->second_chance ? gate : nullptr);
+                           h->second_chance ? thr2 : nullptr, h->second_chance ? gate : nullptr,
+                           sampled ? thr + 2 * nq_pad : nullptr);
     if (rc != RSE_OK) return rc;
   }
   if (!h->second_chance) return RSE_OK;
@@ -693,7 +756,7 @@ int knn_tc3_group(rse_index* h, const float* q_dev, const double* sb, int nqg, i
       h->tmap_a16, h->tmap_q16, n_tiles, 1, nqg, nblk, thr2, nullptr, 0, static_cast<uint2*>(h->tc_rows.p),
       static_cast<unsigned int*>(h->tc_cnt.p), kTcCandCap, gate);
   LAUNCHED(h);
-  return knn_tc_refine(h, q_dev, sb, nqg, kprime, cand_dev, status_dev, thr2, gate, nullptr, nullptr);
+  return knn_tc_refine(h, q_dev, sb, nqg, kprime, cand_dev, status_dev, thr2, gate, nullptr, nullptr, nullptr);
 }
 
 bool tc_eligible(const rse_index* h, int nq, int kprime) {
@@ -885,6 +948,10 @@ int rse_create(int32_t device, rse_index** out) {
   if (const char* ev = std::getenv("RSE_TIMELINE")) h->timeline = ev[0] == '1';
   if (const char* ev = std::getenv("RSE_NO_SECOND_CHANCE")) h->second_chance = !(ev[0] == '1');
   if (const char* ev = std::getenv("RSE_ENC_BN")) { const int v = std::atoi(ev); if (v == 64 || v == 128) h->enc_bn_override = v; }
+  if (const char* ev = std::getenv("RSE_TC_SAMPLE")) h->use_sample = !(ev[0] == '0');
+  if (const char* ev = std::getenv("RSE_TC_SAMPLE_STRIDE")) { const int v = std::atoi(ev); if (v >= 2 && v <= 256) h->sample_stride = v; }
+  if (const char* ev = std::getenv("RSE_TC_SAMPLE_MIN_TILES")) { const int v = std::atoi(ev); if (v >= 1) h->sample_min_tiles = v; }
+  if (const char* ev = std::getenv("RSE_TC_PROBE_RANK")) { const int v = std::atoi(ev); if (v >= 1) h->probe_rank = v; }
   if (const char* ev = std::getenv("RSE_TC_SURVIVOR_DIV")) { const int v = std::atoi(ev); if (v >= 1 && v <= 64) h->survivor_div = v; }
   *out = h;
   return RSE_OK;

@@ -16,6 +16,7 @@ slice of the same seeds in the `-m gpu` suite; a longer run's log is kept under 
 from __future__ import annotations
 
 import argparse
+import os
 import sys
 import time
 from pathlib import Path
@@ -96,10 +97,29 @@ def fuzz_knn(seed, lib, oracle):
     fma = bool(rng.random() < 0.15)
     k = int(rng.integers(1, min(kprime, 128) + 1))
     desc = f"knn seed={seed} n={n} dim={dim} nq={nq} k'={kprime} k={k} {kind} holes={holes} rowid={rowid is not None} base={base} fma={fma}"
+    # the probe's row sample (knn_tc3.cuh): as shipped it needs >= 512 k rows — lower the bar on some cases, and on
+    # some force the probe's order statistic so low that the verified bound fails and the second chance must repair it
+    knobs = {}
+    pick = rng.random()
+    if pick < 0.5:
+        knobs = {"RSE_TC_SAMPLE_MIN_TILES": "1", "RSE_TC_SAMPLE_STRIDE": str(int(rng.choice([4, 8, 16, 32])))}
+        if pick < 0.2:
+            knobs["RSE_TC_PROBE_RANK"] = str(int(rng.choice([1, 2, 5])))
+    desc += f" knobs={knobs}" if knobs else ""
     res = {}
     used_tc = False
     for mode in (1, 2):
-        idx = lib.Index(0)
+        old = {name: os.environ.get(name) for name in knobs}
+        if mode == 2:
+            os.environ.update(knobs)
+        try:
+            idx = lib.Index(0)
+        finally:
+            for name, val in old.items():
+                if val is None:
+                    os.environ.pop(name, None)
+                else:
+                    os.environ[name] = val
         try:
             idx.set_tc_mode(mode)
             idx.set_fma(fma)

@@ -1,8 +1,8 @@
 #!/bin/bash
 set -u
 mkdir -p gpurun_out
-timeout 600 python -m pytest tests/test_gpu_parity.py tests/test_gpu_r02.py -m gpu -x -q > gpurun_out/pytest_div.log 2>&1; echo "pytest rc=$?"; tail -2 gpurun_out/pytest_div.log
-for D in 5 8 12; do
+
+for D in ${DIVS:-5 8 12}; do
   RSE_TC_SURVIVOR_DIV=$D timeout 600 python bench.py --steps 20 --warmup 5 --no-cpu-baseline --no-knn100m --no-e2e > gpurun_out/bench_div$D.json 2> gpurun_out/bench_div$D.err
   echo "div=$D rc=$?"
   python - <<PY

@@ -382,3 +382,63 @@ def test_torch_distributed_sharded_driver_single_rank(small_world):
     assert int(r.flagged.item()) == 0
     assert (r.ids.cpu().numpy() == want[0]).all() and (r.score.cpu().numpy() == want[1]).all()
     assert (r.count.cpu().numpy() == want[4]).all()
+
+
+# ----------------------------------------------------------------------------- the probe's row sample (verified bound)
+class _env:
+    """librse reads its RSE_* knobs when a handle is created."""
+    def __init__(self, **kw):
+        self.kw = {k: str(v) for k, v in kw.items()}
+
+    def __enter__(self):
+        import os
+        self.old = {k: os.environ.get(k) for k in self.kw}
+        os.environ.update(self.kw)
+
+    def __exit__(self, *a):
+        import os
+        for k, v in self.old.items():
+            if v is None:
+                os.environ.pop(k, None)
+            else:
+                os.environ[k] = v
+
+
+@pytest.mark.parametrize("distribution,knobs,expect_second", [
+    ("isotropic", dict(RSE_TC_SAMPLE_MIN_TILES=1, RSE_TC_SAMPLE_STRIDE=8), False),     # the sample path as shipped
+    ("clustered", dict(RSE_TC_SAMPLE_MIN_TILES=1, RSE_TC_SAMPLE_STRIDE=8), False),
+    ("isotropic", dict(RSE_TC_SAMPLE_MIN_TILES=1, RSE_TC_SAMPLE_STRIDE=8, RSE_TC_PROBE_RANK=1), True),   # bound always far too tight
+    ("isotropic", dict(RSE_TC_SAMPLE_MIN_TILES=1, RSE_TC_SAMPLE_STRIDE=8, RSE_TC_PROBE_RANK=12), True),  # too tight half the time
+    ("clustered", dict(RSE_TC_SAMPLE_MIN_TILES=1, RSE_TC_SAMPLE_STRIDE=8, RSE_TC_PROBE_RANK=12), True),
+    ("clustered", dict(RSE_TC_SAMPLE_MIN_TILES=1, RSE_TC_SAMPLE_STRIDE=16, RSE_TC_PROBE_RANK=2), True),
+])
+def test_sampled_probe_bound_is_verified_and_results_stay_exact(distribution, knobs, expect_second):
+    """The probe's threshold on the sample path is the j-th best value of a stratified row sample, j << K': tight, and
+    valid only with high probability — the refine kernel verifies it (s_K >= T) and re-arms the second filter pass with
+    the exact bound when it fails (fewer than K' survivors: the exact scan).  Forcing a small j makes the bound fail for
+    many queries: the answers must not change."""
+    from rag_search_engine_b200 import _lib, synth
+    se = synth.synth_embeddings(9_000, seed=21, device="cpu", distribution=distribution)     # ~72 k rows
+    emb = se.emb.numpy()
+    nq = 300                                                                                  # two query blocks
+    Q = synth.synth_query_vectors(se.emb, nq, seed=22).numpy()
+    out = {}
+    for mode in (1, 2):
+        with _env(**(knobs if mode == 2 else {})):
+            idx = _lib.Index(0)
+        try:
+            idx.set_tc_mode(mode)
+            idx.load_embeddings(emb, movie_idx=se.movie_of_chunk.numpy())
+            out[mode] = idx.knn(Q, 100) + idx.knn_movies(Q, 10, 100) + idx.knn(Q[:40], 10)
+            st = idx.stats()
+            if mode == 2:
+                assert st.tc_queries == 2 * nq + 40
+                print(f"{distribution} {knobs}: second chance {st.tc_second_chance_queries}, fallback {st.tc_fallback_queries} "
+                      f"of {st.tc_queries}; survivors p50 {int(np.median(idx.tc_last_survivors(40)))}")
+                if expect_second:
+                    assert st.tc_second_chance_queries + st.tc_fallback_queries > nq // 4
+                else:
+                    assert st.tc_second_chance_queries + st.tc_fallback_queries <= 3
+        finally:
+            idx.close()
+    assert same(out[1], out[2])
