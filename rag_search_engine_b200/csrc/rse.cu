@@ -155,10 +155,10 @@ struct rse_index {
   DevBuf tc_sample;
   CUtensorMap tmap_s16{};
   int64_t sample_tiles = 0;        // 0 = no sample (small corpus, RSE_TC_SAMPLE=0): the probe strides over the main shadow
-  int sample_stride = 32;          // RSE_TC_SAMPLE_STRIDE
+  int sample_stride = 64;          // RSE_TC_SAMPLE_STRIDE (r02 sweep on S-600k: 16 -> 1.137, 32 -> 1.106, 64 -> 1.091 ms per step)
   int probe_rank = 0;              // RSE_TC_PROBE_RANK: force the probe's order statistic j (tests: 1 = always too tight)
   bool use_sample = true;          // RSE_TC_SAMPLE=0 switches the sample path off
-  int sample_min_tiles = 64;       // RSE_TC_SAMPLE_MIN_TILES (tests lower it to exercise the path on small corpora)
+  int sample_min_tiles = 16;       // RSE_TC_SAMPLE_MIN_TILES: 262 k rows at stride 64 (tests lower it for small corpora)
   int shadow_state = 0;            // 0 = not built, 1 = usable, -1 = corpus has non-finite norms: exact scan only
   CUtensorMap tmap_a16{};          // [n_rows][384] f16, box {64, 128}, SWIZZLE_128B
   CUtensorMap tmap_q16{};          // [256][384] f16, box {64, 128}
@@ -516,8 +516,8 @@ int ensure_shadow(rse_index* h) {
   // the tiled shadow as a 2-D array of 128-byte lines: [n_pad * 6 lines][64 halves], box = 128 lines = one stage
   int rc = make_tmap_lines(h, &h->tmap_a16, h->tc_shadow.p, n_pad * kT3KBlocks, kT3HalfRows);
   if (rc != RSE_OK) return rc;
-  // the probe's sample: worth its own matrix once it fills every cluster with a few tiles (>= 64 tiles = 512 k rows
-  // at stride 32); smaller corpora keep the strided-tile probe over the main shadow
+  // the probe's sample: its own small matrix from sample_min_tiles tiles on (262 k corpus rows, the automatic K4
+  // threshold); smaller corpora keep the strided-tile probe over the main shadow
   h->sample_tiles = 0;
   const int64_t n_sample = (h->n_rows + h->sample_stride - 1) / h->sample_stride;
   if (h->use_sample && n_sample >= static_cast<int64_t>(h->sample_min_tiles) * kT3TileRows) {
