@@ -347,6 +347,15 @@ class Timer:
             import torch.distributed as dist
             dist.barrier()
 
+    def gather_ranks(self, x: float):
+        """x of every rank (diagnostics: which rank the max-over-ranks time belongs to)."""
+        if self.world > 1:
+            import torch.distributed as dist
+            t = self.torch.zeros(self.world, dtype=self.torch.float64, device=self.device)
+            dist.all_gather_into_tensor(t, self.torch.tensor([x], dtype=self.torch.float64, device=self.device))
+            return [float(v) for v in t.cpu().tolist()]
+        return [x]
+
     def max_over_ranks(self, x: float) -> float:
         if self.world > 1:
             import torch.distributed as dist
@@ -392,7 +401,7 @@ def measure_hybrid(idx, tm: Timer, batches, mode, param, limit, steps, warmup, *
     st = idx.stats()
     idx.set_timing(False)
     out = {"ms": tm.max_over_ranks(ms_local), "ms_local": ms_local, "stats": st, "clocks": clocks, "nq": nq,
-           "survivors": None, "e2e": None, "results": None}
+           "survivors": None, "e2e": None, "results": None, "ms_ranks": tm.gather_ranks(ms_local)}
     if int(st.tc_filter_launches) > 0:
         try:
             out["survivors"] = idx.tc_last_survivors(min(nq, 256))
@@ -1001,6 +1010,7 @@ def run_b200(args, rank, world, local_rank):
         knn1.update(achieved_gbs=g1, frac_of_measured_peak=g1 / peak, queries_per_s=1e3 / knn1["call_ms_host_buffers"])
     line = {"metric": "hybrid queries/sec", "value": value, "unit": "queries/s", "n_gpus": world, "steps": args.steps,
             "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps, "higher_is_better": True,
+            "ms_per_step_ranks": [round(v / args.steps, 4) for v in m["ms_ranks"]],
             "scaling": (args.scaling if world > 1 else "weak"), "vs_baseline": None,
             "dtype": "f16 tensor-core filter + exact f32 re-score (f64 tail), f64 BM25/fusion", "data": "synthetic",
             "config": config_dict(args, info, world, par), "roofline": roofline, "clocks": clocks, "e2e": e2e,
