@@ -405,6 +405,7 @@ struct __align__(16) Post16 {
   double w;        // tf*(k1+1) / (tf + normk[doc])
 };
 
+constexpr int kBsWideThreads = 896;               // bm25_fx_kernel underneath the filter (see there)
 constexpr int kBsThreads = 512;                   // 16 warps x 3 CTAs per SM: the kernel is issue-latency-bound, TLP is what it needs
 constexpr int kBsPerTrip = 2;                     // postings per thread per trip
 constexpr int kBsDocsPerThread = kBmRange / kBsThreads;   // 14
@@ -693,13 +694,23 @@ __host__ __device__ constexpr int fx_smem_bytes(int rpg) {
 
 // fin: [nq][ng][kFxFinalCap] {fixed-point sum, doc}; fin_cnt: [nq][ng]
 // 4 CTAs per SM = 32 registers per thread: that is also what lets ONE of these CTAs sit beside the tensor-core
-// filter's CTA (120 registers x 320 threads) in a hybrid step — at 40 registers the pair overflows a scheduler's
-// 16 K registers and BM25 silently waits for the filter to finish.
-__global__ void __launch_bounds__(kBsThreads, 4)
-bm25_fx_kernel(const int64_t* __restrict__ indptr, const uint2* __restrict__ post8, const uint32_t* __restrict__ roff,
-               int nr, const int32_t* __restrict__ tok_indptr, const int32_t* __restrict__ term_rows,
-               const double* __restrict__ tok_idf, double scale, int q0, int k, int rpg, int ng,
-               uint2* __restrict__ fin, int* __restrict__ fin_cnt, int* __restrict__ status) {
+// filter's CTA in a hybrid step — at 40 registers the pair overflows a scheduler's 16 K registers and BM25 silently
+// waits for the filter to finish.  THREADS = 512 is the stand-alone shape (4 CTAs per SM); THREADS = kBsWideThreads
+// is the shape of the CTA that runs UNDERNEATH the filter: the filter's 10 warps put 3 on two of the four
+// schedulers (3 x 32 x 96 registers = 9216 of 16384), which leaves room for exactly 7 warps of 32 registers per
+// scheduler — 28 warps instead of 16.  (A 768-thread shape does NOT fit: its launch bound lets ptxas take 39
+// registers.)  r02 measurements, all on one box: stand-alone the kernel is thread-parallelism-bound (4 / 3 / 2 / 1
+// CTAs per SM: 0.31 / 0.34 / 0.42 / 0.69 ms, scripts/bm25_occupancy.py), but beside the filter it runs at ~14 % of
+// the stand-alone rate whatever its shape — 28 warps instead of 16 finish 8 us earlier (step 1.078 -> 1.070 ms), and
+// a 55-register variant with four posting loads in flight per lane was slower overall (1.13 ms: only two of those
+// fit an SM once the filter is gone).  What it competes for there is the memory system: the filter streams the
+// shadow at 4.9 TB/s of the 6.5 the HBM gives.
+template <int THREADS, int DEPTH>
+__device__ __forceinline__ void
+bm25_fx_body(const int64_t* __restrict__ indptr, const uint2* __restrict__ post8, const uint32_t* __restrict__ roff,
+             int nr, const int32_t* __restrict__ tok_indptr, const int32_t* __restrict__ term_rows,
+             const double* __restrict__ tok_idf, double scale, int q0, int k, int rpg, int ng,
+             uint2* __restrict__ fin, int* __restrict__ fin_cnt, int* __restrict__ status) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   uint32_t* acc = reinterpret_cast<uint32_t*>(smem_raw);                               // [kBmRange] fixed-point sums
   uint32_t* s_off = acc + kBmRange;                                                    // [kBsMaxTok][rpg + 1]
@@ -774,7 +785,7 @@ bm25_fx_kernel(const int64_t* __restrict__ indptr, const uint2* __restrict__ pos
     __syncthreads();
   };
 
-  constexpr unsigned int kW = kBsThreads / 32;
+  constexpr unsigned int kW = THREADS / 32;
   constexpr int kVec = kBmRange / 4;                      // accumulators as uint4
   for (int r = r0; r < r1; ++r) {
     const int jr = r - r0;
@@ -829,15 +840,20 @@ bm25_fx_kernel(const int64_t* __restrict__ indptr, const uint2* __restrict__ pos
       if (e.z != 0xFFFFFFFFu) atomicAdd(&acc[e.z - doc_base], __double2uint_rn(__dmul_rn(idfx, __uint2double_rn(e.w))));
     };
     {
-      // two loads in flight per lane, buffers alternate by name
-      uint4 e0, e1;
-      double f0, f1;
+      // DEPTH loads in flight per lane (a ring of named buffers: every index below is a compile-time constant)
+      uint4 e[DEPTH];
+      double f[DEPTH];
       unsigned int it = warp;
-      item_load(it, e0, f0);
+#pragma unroll
+      for (int d = 0; d < DEPTH - 1; ++d) item_load(it + d * kW, e[d], f[d]);
       while (it < n_items) {
-        item_load(it + kW, e1, f1); item_apply(e0, f0); it += kW;
-        if (it >= n_items) break;
-        item_load(it + kW, e0, f0); item_apply(e1, f1); it += kW;
+#pragma unroll
+        for (int d = 0; d < DEPTH; ++d) {
+          item_load(it + (DEPTH - 1) * kW, e[(d + DEPTH - 1) % DEPTH], f[(d + DEPTH - 1) % DEPTH]);
+          item_apply(e[d], f[d]);
+          it += kW;
+          if (it >= n_items) break;
+        }
       }
     }
     __syncthreads();                                      // the range's sums are complete
@@ -847,11 +863,11 @@ bm25_fx_kernel(const int64_t* __restrict__ indptr, const uint2* __restrict__ pos
       // theta = (k-th largest of the warps' best thread maxima) - margin: maxima of distinct threads are distinct
       // documents, so k of them at or above it bound the k-th best exact score from below
       unsigned int mine = 0u;
-      for (int v = threadIdx.x; v < kVec; v += kBsThreads) {
+      for (int v = threadIdx.x; v < kVec; v += THREADS) {
         const uint4 x = a4[v];
         mine = max(mine, max(max(x.x, x.y), max(x.z, x.w)));
       }
-      const int m = (k + kBsThreads / 32 - 1) / (kBsThreads / 32);        // 1 or 2
+      const int m = (k + THREADS / 32 - 1) / (THREADS / 32);        // 1 or 2
       unsigned int* s_top = reinterpret_cast<unsigned int*>(cand_alt);
       for (int round = 0; round < m; ++round) {
         unsigned int wm = mine;
@@ -862,7 +878,7 @@ bm25_fx_kernel(const int64_t* __restrict__ indptr, const uint2* __restrict__ pos
       }
       if (threadIdx.x == 0) s_tw = 0u;
       __syncthreads();
-      const int nv = (kBsThreads / 32) * m;                                // 16 or 32
+      const int nv = (THREADS / 32) * m;                                // 16 or 32
       if (static_cast<int>(threadIdx.x) < nv) {
         const unsigned int me = s_top[threadIdx.x];
         int r2 = 0;
@@ -879,7 +895,7 @@ bm25_fx_kernel(const int64_t* __restrict__ indptr, const uint2* __restrict__ pos
     // scan + clear: collect the documents at or above theta (theta = 0: every touched document)
     {
       const unsigned int bar = theta ? theta : 1u;
-      for (int v = threadIdx.x; v < kVec; v += kBsThreads) {
+      for (int v = threadIdx.x; v < kVec; v += THREADS) {
         const uint4 x = a4[v];
         if ((x.x | x.y | x.z | x.w) == 0u) continue;
         a4[v] = make_uint4(0u, 0u, 0u, 0u);
@@ -913,6 +929,14 @@ bm25_fx_kernel(const int64_t* __restrict__ indptr, const uint2* __restrict__ pos
   if (threadIdx.x == 0) fin_cnt[cbase] = static_cast<int>(n);
 }
 
+template <int THREADS>
+__global__ void __launch_bounds__(THREADS, (THREADS <= 512 ? 4 : 2))
+bm25_fx_kernel(const int64_t* __restrict__ indptr, const uint2* __restrict__ post8, const uint32_t* __restrict__ roff,
+               int nr, const int32_t* __restrict__ tok_indptr, const int32_t* __restrict__ term_rows,
+               const double* __restrict__ tok_idf, double scale, int q0, int k, int rpg, int ng,
+               uint2* __restrict__ fin, int* __restrict__ fin_cnt, int* __restrict__ status) {
+  bm25_fx_body<THREADS, 2>(indptr, post8, roff, nr, tok_indptr, term_rows, tok_idf, scale, q0, k, rpg, ng, fin, fin_cnt, status);
+}
 // K7'': one CTA per query bm25_fx_kernel finished (see the header above).
 __global__ void __launch_bounds__(kBmThreads)
 bm25_fx_finish_kernel(const uint2* __restrict__ fin, const int* __restrict__ fin_cnt, int ng, int* __restrict__ status,

@@ -698,12 +698,10 @@ knn_tc3_kernel(const __grid_constant__ CUtensorMap tmap_rows, const __grid_const
         const uint32_t row_base = static_cast<uint32_t>(t * kT3TileRows + col_half * 128);
         bool pushed = false;                       // rare per lane: ≈ K'·stride + band survivors per query per pass
 #pragma unroll 1
-        for (int hcol = 0; hcol < 128; hcol += 64) {     // 64 columns at a time: 120 registers instead of 168, same speed
-          uint32_t v[64];
-          tc_ld64(taddr0 + static_cast<uint32_t>(hcol), v);
-#pragma unroll
-          for (int c = 0; c < 2; ++c)
-            pushed |= t3_scan32(v + 32 * c, my_thr, row_base + static_cast<uint32_t>(hcol + 32 * c), sink);
+        for (int hcol = 0; hcol < 128; hcol += 32) {     // 32 columns per tcgen05.ld: 90 registers (64: 118, 128: 168), same
+          uint32_t v[32];                                // speed — and 96 allocated registers are what lets a 28-warp BM25
+          tc_ld32(taddr0 + static_cast<uint32_t>(hcol), v);   // CTA share the SM (bm25.cuh, bm25_fx_kernel)
+          pushed |= t3_scan32(v, my_thr, row_base + static_cast<uint32_t>(hcol), sink);
         }
         if (__any_sync(0xFFFFFFFFu, pushed)) {
           __syncwarp();

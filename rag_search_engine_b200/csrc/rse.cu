@@ -142,6 +142,8 @@ struct rse_index {
   int ov_nq = 0, ov_limit = 0;
   double ov_k1 = 0.0, ov_b = 0.0;
   bool overlap_enabled = true;
+  int bm25_pad = 0;                // RSE_BM25_PAD: extra dynamic shared memory per BM25 CTA (occupancy experiments)
+  bool bm25_wide = true;           // RSE_BM25_WIDE=0: the 512-thread BM25 CTA underneath the filter as well
   // RSE_TIMELINE=1: timed events at the stage boundaries of a hybrid step on both streams, printed (ms since the
   // step's first event) to stderr by rse_hybrid_fetch — a development aid, off by default
   bool timeline = false;
@@ -944,6 +946,8 @@ int rse_create(int32_t device, rse_index** out) {
   else
     h->dev_counters = nullptr;
   // diagnostics: RSE_NO_OVERLAP=1 keeps the hybrid step's BM25 on the caller's stream (no second stream)
+  if (const char* ev = std::getenv("RSE_BM25_PAD")) h->bm25_pad = std::max(0, std::atoi(ev));
+  if (const char* ev = std::getenv("RSE_BM25_WIDE")) h->bm25_wide = !(ev[0] == '0');
   if (const char* ev = std::getenv("RSE_NO_OVERLAP")) h->overlap_enabled = !(ev[0] == '1');
   if (const char* ev = std::getenv("RSE_TIMELINE")) h->timeline = ev[0] == '1';
   if (const char* ev = std::getenv("RSE_NO_SECOND_CHANCE")) h->second_chance = !(ev[0] == '1');
@@ -1367,8 +1371,10 @@ int rse_load_bm25(rse_index* h, const int64_t* indptr, const uint32_t* doc_idx, 
   if (!(h->attr_mask & (1u << 14))) {
     CK(cudaFuncSetAttribute(bm25_score_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kBmRange * 9));
     CK(cudaFuncSetAttribute(bm25_stream_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bs_smem_bytes()));
-    CK(cudaFuncSetAttribute(bm25_fx_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, fx_smem_bytes(kBsMaxRpg)));
-    CK(cudaFuncSetAttribute(bm25_fx_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+    CK(cudaFuncSetAttribute(bm25_fx_kernel<kBsThreads>, cudaFuncAttributeMaxDynamicSharedMemorySize, fx_smem_bytes(kBsMaxRpg) + h->bm25_pad));
+    CK(cudaFuncSetAttribute(bm25_fx_kernel<kBsThreads>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+    CK(cudaFuncSetAttribute(bm25_fx_kernel<kBsWideThreads>, cudaFuncAttributeMaxDynamicSharedMemorySize, fx_smem_bytes(kBsMaxRpg)));
+    CK(cudaFuncSetAttribute(bm25_fx_kernel<kBsWideThreads>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
     h->attr_mask |= 1u << 14;
   }
   return RSE_OK;
@@ -1526,10 +1532,17 @@ int bm25_run(rse_index* h, int nq, int k, double k1, double b) {
       int* fcnt = static_cast<int*>(h->b_scnt.p) - static_cast<int64_t>(q0) * ng;
       status = static_cast<int*>(h->b_status.p);
       dim3 sgrid(ng, nc);
-      bm25_fx_kernel<<<sgrid, kBsThreads, fx_smem_bytes(rpg), h->stream>>>(
-          h->indptr, h->post8, h->roff, h->nr, static_cast<const int32_t*>(h->b_tokptr.p),
-          static_cast<const int32_t*>(h->b_terms.p), static_cast<const double*>(h->b_idf.p), fx_scale / h->wq_scale, q0, k,
-          rpg, ng, fin, fcnt, status);
+      // underneath the tensor-core filter (hybrid step, second stream): the wide CTA (bm25.cuh)
+      if (h->bm25_wide && h->stream_b && h->stream == h->stream_b)
+        bm25_fx_kernel<kBsWideThreads><<<sgrid, kBsWideThreads, fx_smem_bytes(rpg), h->stream>>>(
+            h->indptr, h->post8, h->roff, h->nr, static_cast<const int32_t*>(h->b_tokptr.p),
+            static_cast<const int32_t*>(h->b_terms.p), static_cast<const double*>(h->b_idf.p), fx_scale / h->wq_scale, q0, k,
+            rpg, ng, fin, fcnt, status);
+      else
+        bm25_fx_kernel<kBsThreads><<<sgrid, kBsThreads, fx_smem_bytes(rpg) + h->bm25_pad, h->stream>>>(
+            h->indptr, h->post8, h->roff, h->nr, static_cast<const int32_t*>(h->b_tokptr.p),
+            static_cast<const int32_t*>(h->b_terms.p), static_cast<const double*>(h->b_idf.p), fx_scale / h->wq_scale, q0, k,
+            rpg, ng, fin, fcnt, status);
       LAUNCHED(h);
       bm25_fx_finish_kernel<<<nc, kBmThreads, 0, h->stream>>>(
           fin, fcnt, ng, status, h->indptr, h->post16, h->roff, h->nr, static_cast<const int32_t*>(h->b_tokptr.p),

@@ -310,8 +310,10 @@ def test_library_owned_nccl_comm_single_rank(small_world):
 
 def test_multimodal_search_ranks_like_the_reference_expression():
     """§8 f4: image -> text search (rag_search_engine/llm/multimodal.py:86-95) with the ranking on the GPU.
-    Floating point: similarity within 1e-6 of the reference's numpy expression; same ids wherever neighbouring
-    similarities are further apart than that."""
+    Floating point: similarity within 4e-6 of the reference's numpy expression (fp32 dot products of 512 terms in a
+    different summation order: BLAS blocks, the scan sums sequentially); same ids wherever neighbouring similarities
+    are further apart than that."""
+    import zlib
     from rag_search_engine_b200.multimodal import MultimodalSearch
 
     class FakeClip:                                   # the CLIP model is out of scope: any object with .encode
@@ -320,7 +322,7 @@ def test_multimodal_search_ranks_like_the_reference_expression():
         def encode(self, items, convert_to_numpy=True, show_progress_bar=False):
             out = np.empty((len(items), self.dim), np.float32)
             for i, t in enumerate(items):
-                seed = abs(hash(t)) % (2 ** 32) if isinstance(t, str) else 7
+                seed = zlib.crc32(t.encode()) if isinstance(t, str) else 7          # (str hashes differ per process)
                 out[i] = np.random.default_rng(seed).standard_normal(self.dim).astype(np.float32) * 3.0
             return out
 
@@ -340,10 +342,10 @@ def test_multimodal_search_ranks_like_the_reference_expression():
             got = ms.search_with_vector(img, top_k=25)
             assert len(got) == 25 and list(got[0].keys()) == ["id", "title", "description", "similarity"]
             for j, (g, want) in enumerate(zip(got, top)):
-                assert abs(g["similarity"] - similarities[want]) < 1e-6
+                assert abs(g["similarity"] - similarities[want]) < 4e-6
                 gap = min(abs(similarities[top[j]] - similarities[top[j - 1]]) if j else 1.0,
                           abs(similarities[top[j]] - similarities[top[j + 1]]) if j + 1 < len(top) else 1.0)
-                if gap > 2e-6:
+                if gap > 8e-6:
                     assert g["id"] == docs[want].get("id", want)
         assert ms.search_with_vector(img, top_k=10 ** 6 if False else 3)[0]["id"] == got[0]["id"]
         with pytest.raises(ValueError, match="initialized without documents"):
