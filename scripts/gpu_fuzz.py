@@ -195,8 +195,24 @@ def fuzz_hybrid(seed, lib, oracle):
     mode = int(rng.integers(0, 2))
     param = float(rng.choice([60.0, 1.0, 7.5])) if mode == 0 else float(rng.choice([0.5, 0.0, 1.0, 0.3]))
     desc = f"hybrid seed={seed} movies={n_movies} {dist_kind} nq={nq} limit={limit} mult={mult} mode={'rrf' if mode == 0 else 'weighted'} param={param}"
-    idx = lib.Index(0)
+    # half of the cases force the tensor-core path (the automatic choice needs 262 k rows): BM25 then runs on the second
+    # stream underneath the filter, in its 896-thread shape
+    force_tc = bool(rng.random() < 0.5)
+    desc += f" tc={'forced' if force_tc else 'auto'}"
+    knobs = {"RSE_TC_SAMPLE_MIN_TILES": "1", "RSE_TC_SAMPLE_STRIDE": "8"} if force_tc and rng.random() < 0.5 else {}
+    old_env = {name: os.environ.get(name) for name in knobs}
+    os.environ.update(knobs)
     try:
+        idx = lib.Index(0)
+    finally:
+        for name, val in old_env.items():
+            if val is None:
+                os.environ.pop(name, None)
+            else:
+                os.environ[name] = val
+    try:
+        if force_tc:
+            idx.set_tc_mode(2)
         idx.load_embeddings(emb, movie_idx=movie_of)
         idx.load_bm25(bm.indptr, bm.doc_idx, bm.tf, bm.df, bm.dl, bm.n_movies, bm.avgdl)
         idx.set_id_tables(ids, ids)
