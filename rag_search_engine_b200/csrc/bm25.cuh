@@ -711,6 +711,11 @@ bm25_fx_body(const int64_t* __restrict__ indptr, const uint2* __restrict__ post8
              int nr, const int32_t* __restrict__ tok_indptr, const int32_t* __restrict__ term_rows,
              const double* __restrict__ tok_idf, double scale, int q0, int k, int rpg, int ng,
              uint2* __restrict__ fin, int* __restrict__ fin_cnt, int* __restrict__ status) {
+  // rpg < 0 (host: RSE_BM25_QFAST): the grid is (queries, groups) instead of (groups, queries) — the CTAs that are
+  // resident together then work on the SAME ranges for different queries, so the slices of the hot posting lists
+  // they share are read within microseconds of each other
+  const bool qfast = rpg < 0;
+  if (qfast) rpg = -rpg;
   extern __shared__ __align__(16) unsigned char smem_raw[];
   uint32_t* acc = reinterpret_cast<uint32_t*>(smem_raw);                               // [kBmRange] fixed-point sums
   uint32_t* s_off = acc + kBmRange;                                                    // [kBsMaxTok][rpg + 1]
@@ -723,8 +728,8 @@ bm25_fx_body(const int64_t* __restrict__ indptr, const uint2* __restrict__ post8
   __shared__ unsigned int s_ncand, s_nkept;
   __shared__ unsigned int s_min, s_tw;
 
-  const int g = blockIdx.x;
-  const int q = q0 + blockIdx.y;
+  const int g = qfast ? blockIdx.y : blockIdx.x;
+  const int q = q0 + (qfast ? blockIdx.x : blockIdx.y);
   const int t0 = tok_indptr[q], ntok = tok_indptr[q + 1] - t0;
   const int64_t cbase = static_cast<int64_t>(q) * ng + g;
   if (ntok > kBsMaxTok) {                                 // uniform: the whole query goes to the general kernel

@@ -142,6 +142,7 @@ struct rse_index {
   int ov_nq = 0, ov_limit = 0;
   double ov_k1 = 0.0, ov_b = 0.0;
   bool overlap_enabled = true;
+  bool bm25_qfast = true;          // RSE_BM25_QFAST=0: group-major CTA order (r01)
   int bm25_pad = 0;                // RSE_BM25_PAD: extra dynamic shared memory per BM25 CTA (occupancy experiments)
   bool bm25_wide = true;           // RSE_BM25_WIDE=0: the 512-thread BM25 CTA underneath the filter as well
   // RSE_TIMELINE=1: timed events at the stage boundaries of a hybrid step on both streams, printed (ms since the
@@ -946,6 +947,7 @@ int rse_create(int32_t device, rse_index** out) {
   else
     h->dev_counters = nullptr;
   // diagnostics: RSE_NO_OVERLAP=1 keeps the hybrid step's BM25 on the caller's stream (no second stream)
+  if (const char* ev = std::getenv("RSE_BM25_QFAST")) h->bm25_qfast = !(ev[0] == '0');
   if (const char* ev = std::getenv("RSE_BM25_PAD")) h->bm25_pad = std::max(0, std::atoi(ev));
   if (const char* ev = std::getenv("RSE_BM25_WIDE")) h->bm25_wide = !(ev[0] == '0');
   if (const char* ev = std::getenv("RSE_NO_OVERLAP")) h->overlap_enabled = !(ev[0] == '1');
@@ -1531,18 +1533,19 @@ int bm25_run(rse_index* h, int nq, int k, double k1, double b) {
       uint2* fin = static_cast<uint2*>(h->b_shi.p) - static_cast<int64_t>(q0) * ng * kFxFinalCap;
       int* fcnt = static_cast<int*>(h->b_scnt.p) - static_cast<int64_t>(q0) * ng;
       status = static_cast<int*>(h->b_status.p);
-      dim3 sgrid(ng, nc);
+      dim3 sgrid(h->bm25_qfast ? nc : ng, h->bm25_qfast ? ng : nc);
+      const int rpg_arg = h->bm25_qfast ? -rpg : rpg;
       // underneath the tensor-core filter (hybrid step, second stream): the wide CTA (bm25.cuh)
       if (h->bm25_wide && h->stream_b && h->stream == h->stream_b)
         bm25_fx_kernel<kBsWideThreads><<<sgrid, kBsWideThreads, fx_smem_bytes(rpg), h->stream>>>(
             h->indptr, h->post8, h->roff, h->nr, static_cast<const int32_t*>(h->b_tokptr.p),
             static_cast<const int32_t*>(h->b_terms.p), static_cast<const double*>(h->b_idf.p), fx_scale / h->wq_scale, q0, k,
-            rpg, ng, fin, fcnt, status);
+            rpg_arg, ng, fin, fcnt, status);
       else
         bm25_fx_kernel<kBsThreads><<<sgrid, kBsThreads, fx_smem_bytes(rpg) + h->bm25_pad, h->stream>>>(
             h->indptr, h->post8, h->roff, h->nr, static_cast<const int32_t*>(h->b_tokptr.p),
             static_cast<const int32_t*>(h->b_terms.p), static_cast<const double*>(h->b_idf.p), fx_scale / h->wq_scale, q0, k,
-            rpg, ng, fin, fcnt, status);
+            rpg_arg, ng, fin, fcnt, status);
       LAUNCHED(h);
       bm25_fx_finish_kernel<<<nc, kBmThreads, 0, h->stream>>>(
           fin, fcnt, ng, status, h->indptr, h->post16, h->roff, h->nr, static_cast<const int32_t*>(h->b_tokptr.p),
