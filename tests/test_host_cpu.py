@@ -399,3 +399,31 @@ def test_term_rows_list_form_and_flat_array_form_agree():
     assert ptr2.tolist() == ptr.tolist() and rows2.tolist() == want
     ptr3, rows3 = kw._term_rows([[], []])
     assert ptr3.tolist() == [0, 0, 0] and len(rows3) == 1
+
+
+def test_gpu_fuzz_generators_run_without_a_gpu():
+    """scripts/gpu_fuzz.py draws its cases on the host; a stub handle stops each case where the GPU would take over,
+    so the generators (and the script's imports) are exercised by the CPU suite as well."""
+    import importlib.util
+    from pathlib import Path
+    import oracle
+    spec = importlib.util.spec_from_file_location("gpu_fuzz", Path(__file__).resolve().parents[1] / "scripts" / "gpu_fuzz.py")
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+
+    class Reached(Exception):
+        pass
+
+    class StubLib:
+        class Index:
+            def __init__(self, device):
+                raise Reached()
+
+    reached = 0
+    for seed in range(4):
+        for kind in ("knn", "bm25", "hybrid"):
+            try:
+                mod.KINDS[kind](seed, StubLib, oracle)
+            except Reached:
+                reached += 1
+    assert reached == 12
