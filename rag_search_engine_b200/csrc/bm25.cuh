@@ -709,7 +709,7 @@ template <int THREADS, int DEPTH>
 __device__ __forceinline__ void
 bm25_fx_body(const int64_t* __restrict__ indptr, const uint2* __restrict__ post8, const uint32_t* __restrict__ roff,
              int nr, const int32_t* __restrict__ tok_indptr, const int32_t* __restrict__ term_rows,
-             const double* __restrict__ tok_idf, double scale, int q0, int k, int rpg, int ng,
+             const double* __restrict__ tok_idf, double scale, int q0, int k, int rpg, int ng, int g0,
              uint2* __restrict__ fin, int* __restrict__ fin_cnt, int* __restrict__ status) {
   // rpg < 0 (host: RSE_BM25_QFAST): the grid is (queries, groups) instead of (groups, queries) — the CTAs that are
   // resident together then work on the SAME ranges for different queries, so the slices of the hot posting lists
@@ -728,7 +728,7 @@ bm25_fx_body(const int64_t* __restrict__ indptr, const uint2* __restrict__ post8
   __shared__ unsigned int s_ncand, s_nkept;
   __shared__ unsigned int s_min, s_tw;
 
-  const int g = qfast ? blockIdx.y : blockIdx.x;
+  const int g = g0 + (qfast ? blockIdx.y : blockIdx.x);    // g0: first group of this launch (rse.cu splits the groups)
   const int q = q0 + (qfast ? blockIdx.x : blockIdx.y);
   const int t0 = tok_indptr[q], ntok = tok_indptr[q + 1] - t0;
   const int64_t cbase = static_cast<int64_t>(q) * ng + g;
@@ -938,9 +938,9 @@ template <int THREADS>
 __global__ void __launch_bounds__(THREADS, (THREADS <= 512 ? 4 : 2))
 bm25_fx_kernel(const int64_t* __restrict__ indptr, const uint2* __restrict__ post8, const uint32_t* __restrict__ roff,
                int nr, const int32_t* __restrict__ tok_indptr, const int32_t* __restrict__ term_rows,
-               const double* __restrict__ tok_idf, double scale, int q0, int k, int rpg, int ng,
+               const double* __restrict__ tok_idf, double scale, int q0, int k, int rpg, int ng, int g0,
                uint2* __restrict__ fin, int* __restrict__ fin_cnt, int* __restrict__ status) {
-  bm25_fx_body<THREADS, 2>(indptr, post8, roff, nr, tok_indptr, term_rows, tok_idf, scale, q0, k, rpg, ng, fin, fin_cnt, status);
+  bm25_fx_body<THREADS, 2>(indptr, post8, roff, nr, tok_indptr, term_rows, tok_idf, scale, q0, k, rpg, ng, g0, fin, fin_cnt, status);
 }
 // K7'': one CTA per query bm25_fx_kernel finished (see the header above).
 __global__ void __launch_bounds__(kBmThreads)

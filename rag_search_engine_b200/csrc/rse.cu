@@ -144,6 +144,8 @@ struct rse_index {
   bool overlap_enabled = true;
   bool bm25_qfast = true;          // RSE_BM25_QFAST=0: group-major CTA order (r01)
   int bm25_pad = 0;                // RSE_BM25_PAD: extra dynamic shared memory per BM25 CTA (occupancy experiments)
+  int bm25_wide_pct = 100;         // RSE_BM25_WIDE_PCT: share of the range groups launched in the wide shape (r02: 25 / 40 /
+                                   // 60 / 100 % -> 1.064 / 1.071 / 1.087 / 1.050 ms per step: a second launch waits for the first)
   bool bm25_wide = true;           // RSE_BM25_WIDE=0: the 512-thread BM25 CTA underneath the filter as well
   // RSE_TIMELINE=1: timed events at the stage boundaries of a hybrid step on both streams, printed (ms since the
   // step's first event) to stderr by rse_hybrid_fetch — a development aid, off by default
@@ -949,6 +951,7 @@ int rse_create(int32_t device, rse_index** out) {
   // diagnostics: RSE_NO_OVERLAP=1 keeps the hybrid step's BM25 on the caller's stream (no second stream)
   if (const char* ev = std::getenv("RSE_BM25_QFAST")) h->bm25_qfast = !(ev[0] == '0');
   if (const char* ev = std::getenv("RSE_BM25_PAD")) h->bm25_pad = std::max(0, std::atoi(ev));
+  if (const char* ev = std::getenv("RSE_BM25_WIDE_PCT")) { const int v = std::atoi(ev); if (v >= 0 && v <= 100) h->bm25_wide_pct = v; }
   if (const char* ev = std::getenv("RSE_BM25_WIDE")) h->bm25_wide = !(ev[0] == '0');
   if (const char* ev = std::getenv("RSE_NO_OVERLAP")) h->overlap_enabled = !(ev[0] == '1');
   if (const char* ev = std::getenv("RSE_TIMELINE")) h->timeline = ev[0] == '1';
@@ -1533,20 +1536,28 @@ int bm25_run(rse_index* h, int nq, int k, double k1, double b) {
       uint2* fin = static_cast<uint2*>(h->b_shi.p) - static_cast<int64_t>(q0) * ng * kFxFinalCap;
       int* fcnt = static_cast<int*>(h->b_scnt.p) - static_cast<int64_t>(q0) * ng;
       status = static_cast<int*>(h->b_status.p);
-      dim3 sgrid(h->bm25_qfast ? nc : ng, h->bm25_qfast ? ng : nc);
       const int rpg_arg = h->bm25_qfast ? -rpg : rpg;
-      // underneath the tensor-core filter (hybrid step, second stream): the wide CTA (bm25.cuh)
-      if (h->bm25_wide && h->stream_b && h->stream == h->stream_b)
-        bm25_fx_kernel<kBsWideThreads><<<sgrid, kBsWideThreads, fx_smem_bytes(rpg), h->stream>>>(
+      // underneath the tensor-core filter (hybrid step, second stream): wide CTAs (bm25.cuh: 28 warps beside the
+      // filter's CTA).  Alone the 512-thread shape is the faster one (4 CTAs per SM: 284 against 318 us), so the
+      // groups CAN be split between the two shapes — measured, the split loses (see bm25_wide_pct)
+      const bool under_filter = h->bm25_wide && h->bm25_qfast && h->stream_b && h->stream == h->stream_b;
+      const int g_wide = under_filter ? std::min(ng, std::max(1, (ng * h->bm25_wide_pct + 50) / 100)) : 0;
+      if (g_wide > 0) {
+        bm25_fx_kernel<kBsWideThreads><<<dim3(nc, g_wide), kBsWideThreads, fx_smem_bytes(rpg), h->stream>>>(
             h->indptr, h->post8, h->roff, h->nr, static_cast<const int32_t*>(h->b_tokptr.p),
             static_cast<const int32_t*>(h->b_terms.p), static_cast<const double*>(h->b_idf.p), fx_scale / h->wq_scale, q0, k,
-            rpg_arg, ng, fin, fcnt, status);
-      else
-        bm25_fx_kernel<kBsThreads><<<sgrid, kBsThreads, fx_smem_bytes(rpg) + h->bm25_pad, h->stream>>>(
+            rpg_arg, ng, 0, fin, fcnt, status);
+        LAUNCHED(h);
+      }
+      if (g_wide < ng) {
+        const int g_rest = ng - g_wide;
+        bm25_fx_kernel<kBsThreads><<<h->bm25_qfast ? dim3(nc, g_rest) : dim3(ng, nc), kBsThreads,
+                                     fx_smem_bytes(rpg) + h->bm25_pad, h->stream>>>(
             h->indptr, h->post8, h->roff, h->nr, static_cast<const int32_t*>(h->b_tokptr.p),
             static_cast<const int32_t*>(h->b_terms.p), static_cast<const double*>(h->b_idf.p), fx_scale / h->wq_scale, q0, k,
-            rpg_arg, ng, fin, fcnt, status);
-      LAUNCHED(h);
+            rpg_arg, ng, g_wide, fin, fcnt, status);
+        LAUNCHED(h);
+      }
       bm25_fx_finish_kernel<<<nc, kBmThreads, 0, h->stream>>>(
           fin, fcnt, ng, status, h->indptr, h->post16, h->roff, h->nr, static_cast<const int32_t*>(h->b_tokptr.p),
           static_cast<const int32_t*>(h->b_terms.p), static_cast<const double*>(h->b_idf.p), q0, k,
