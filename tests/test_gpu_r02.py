@@ -112,7 +112,7 @@ def test_stats_counters(small_world):
 
 def test_small_batches_take_the_tensor_core_path_and_match_the_exact_scan():
     """rse.h RSE_TC_MIN_BATCH = 2: on a corpus of >= 256 k rows a 2-query batch goes through K4 (r01: 48), a single
-    query takes the streaming scan; results are identical to the exact scan either way."""
+    query takes the streaming scan until a batch has built the shadow; results are identical to the exact scan either way."""
     from rag_search_engine_b200 import _lib
     rng = np.random.default_rng(41)
     n = 262_144 + 1000
@@ -131,6 +131,8 @@ def test_small_batches_take_the_tensor_core_path_and_match_the_exact_scan():
         assert st.tc_queries == 10 and st.tc_fallback_queries == 0
         surv = idx.tc_last_survivors(8)
         assert (surv >= 100).all() and (surv <= 8192).all()
+        a3b = idx.knn(Q[:1], 100)                     # the shadow exists now: a single query takes K4 as well
+        assert idx.stats().tc_queries == 11 and same(a3, a3b)
         idx.set_tc_mode(1)
         e8 = idx.knn(Q, 100)
         assert same(a8, e8) and same([x[:1] for x in a8], a3) and same([x[:2] for x in a8], a4)
