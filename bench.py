@@ -650,7 +650,7 @@ def measure_text_in(args, idx, bm, se, tok_indptr, terms, limit, steps):
 def measure_cold_open(emb_host, local_rank):
     """§8(f1): how long does a query-only open take?  The frozen sidecar's embedding matrix (a raw .npy next to the
     database, store.emb_matrix_path) is memory-mapped and handed to rse_load_embeddings, which streams it to HBM
-    through two pinned 32 MB buffers.  Measured with the file just written (page cache warm)."""
+    through two pinned 64 MB buffers (staging copy on a few threads).  Measured with the file just written (page cache warm)."""
     import shutil
     import tempfile
     from rag_search_engine_b200 import _lib
@@ -670,7 +670,7 @@ def measure_cold_open(emb_host, local_rank):
         del m
         f.unlink()
         return {"seconds": dt, "gbytes": emb_host.nbytes / 1e9, "gb_per_s": emb_host.nbytes / dt / 1e9,
-                "what": "np.load(mmap) of the sidecar matrix + rse_load_embeddings (2 x 32 MB pinned buffers, row norms "
+                "what": "np.load(mmap) of the sidecar matrix + rse_load_embeddings (2 x 64 MB pinned buffers filled by min(16, cores) threads, row norms "
                         "included), page cache warm"}
     except Exception as e:                               # a bench extra must not take the line down
         return {"skipped": f"{type(e).__name__}: {e}"}
