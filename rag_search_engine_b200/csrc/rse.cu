@@ -142,6 +142,7 @@ struct rse_index {
   bool bm25_overlap_pending = false;
   int ov_nq = 0, ov_limit = 0;
   double ov_k1 = 0.0, ov_b = 0.0;
+  bool wide_scan = true;           // RSE_WIDE_SCAN=0: the r01 chunk-loop kernel for widths other than 384
   bool overlap_enabled = true;
   bool bm25_qfast = true;          // RSE_BM25_QFAST=0: group-major CTA order (r01)
   int bm25_pad = 0;                // RSE_BM25_PAD: extra dynamic shared memory per BM25 CTA (occupancy experiments)
@@ -222,6 +223,7 @@ struct rse_index {
   DevBuf sh_cand, sh_mine;
 
   uint32_t attr_mask = 0;
+  uint32_t attr_mask_wide = 0;     // knn_scan_wide_kernel instantiations
   rse_stats stats{};
   // device-side counters read back by rse_get_stats: [0] BM25 queries handed to the general kernel, [1] BM25
   // finalists re-scored exactly, [2] BM25 candidates merged by the finish kernel
@@ -335,6 +337,26 @@ int launch_scan384(rse_index* h, const float* q, const double* sb, int nq, float
   return RSE_OK;
 }
 
+template <int QB, bool FMA>
+int launch_scan_wide(rse_index* h, const float* q, const double* sb, int nq, float* dist) {
+  const int smem = wide_smem_bytes(QB, h->dim);
+  // (the opt-in is per function and per device; the size depends on dim, so it is simply raised to the cap once)
+  constexpr uint32_t bit = 1u << ((QB == 1 ? 0 : QB == 2 ? 1 : QB == 4 ? 2 : QB == 8 ? 3 : 4) + (FMA ? 5 : 0));
+  if (!(h->attr_mask_wide & bit)) {
+    CK(cudaFuncSetAttribute(knn_scan_wide_kernel<QB, FMA>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    h->attr_mask_wide |= bit;
+  }
+  const int64_t n_tiles = (h->n_rows + 31) / 32;
+  const int per_sm = std::max(1, std::min(4, (220 * 1024) / (smem + 1024)));
+  int grid = static_cast<int>(std::min<int64_t>(static_cast<int64_t>(h->sm_count) * per_sm, (n_tiles + kWideWarps - 1) / kWideWarps));
+  if (grid < 1) grid = 1;
+  knn_scan_wide_kernel<QB, FMA><<<grid, kWideWarps * 32, smem, h->stream>>>(h->emb, h->amag, h->n_rows, h->dim, q, sb, nq,
+                                                                           dist, h->dist_ld);
+  LAUNCHED(h);
+  h->stats.knn_scan_launches++;
+  return RSE_OK;
+}
+
 template <bool FMA>
 int launch_scan(rse_index* h, const float* q, const double* sb, int nq, float* dist) {
   if (h->dim == kScanD) {
@@ -343,6 +365,14 @@ int launch_scan(rse_index* h, const float* q, const double* sb, int nq, float* d
     if (nq <= 4) return launch_scan384<4, FMA>(h, q, sb, nq, dist);
     if (nq <= 8) return launch_scan384<8, FMA>(h, q, sb, nq, dist);
     return launch_scan384<16, FMA>(h, q, sb, nq, dist);
+  }
+  // any width that keeps the rows 16-byte aligned: the staged kernel (queries must fit beside the stages)
+  if (h->dim % 4 == 0 && h->wide_scan && wide_smem_bytes(16, h->dim) <= 200 * 1024) {
+    if (nq <= 1) return launch_scan_wide<1, FMA>(h, q, sb, nq, dist);
+    if (nq <= 2) return launch_scan_wide<2, FMA>(h, q, sb, nq, dist);
+    if (nq <= 4) return launch_scan_wide<4, FMA>(h, q, sb, nq, dist);
+    if (nq <= 8) return launch_scan_wide<8, FMA>(h, q, sb, nq, dist);
+    return launch_scan_wide<16, FMA>(h, q, sb, nq, dist);
   }
   const int threads = kGenWarps * 32;
   const int grid = static_cast<int>((h->n_rows + threads - 1) / threads);
@@ -956,6 +986,7 @@ int rse_create(int32_t device, rse_index** out) {
   if (const char* ev = std::getenv("RSE_BM25_PAD")) h->bm25_pad = std::max(0, std::atoi(ev));
   if (const char* ev = std::getenv("RSE_BM25_WIDE_PCT")) { const int v = std::atoi(ev); if (v >= 0 && v <= 100) h->bm25_wide_pct = v; }
   if (const char* ev = std::getenv("RSE_BM25_WIDE")) h->bm25_wide = !(ev[0] == '0');
+  if (const char* ev = std::getenv("RSE_WIDE_SCAN")) h->wide_scan = !(ev[0] == '0');
   if (const char* ev = std::getenv("RSE_NO_OVERLAP")) h->overlap_enabled = !(ev[0] == '1');
   if (const char* ev = std::getenv("RSE_TIMELINE")) h->timeline = ev[0] == '1';
   if (const char* ev = std::getenv("RSE_NO_SECOND_CHANCE")) h->second_chance = !(ev[0] == '1');
