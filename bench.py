@@ -634,7 +634,12 @@ def measure_text_in(args, idx, bm, se, tok_indptr, terms, limit, steps):
     bulk_ms = e0.elapsed_time(e1) / 3
     c = MINILM_L6_CONFIG
     flop_per_token = 2.0 * c["layers"] * (4 * c["hidden"] ** 2 + 2 * c["hidden"] * c["intermediate"])
-    return {"value": B / wall, "unit": "queries/s", "wall_ms_per_step": 1e3 * wall, "queries_per_step": B,
+    rerank = None
+    try:
+        rerank = measure_rerank(idx, limit)
+    except Exception as e:                               # a bench extra must not take the line down
+        rerank = {"error": repr(e)[:200]}
+    return {"rerank": rerank, "value": B / wall, "unit": "queries/s", "wall_ms_per_step": 1e3 * wall, "queries_per_step": B,
             "api": "rse_encode_dev (MiniLM-L6 architecture, fp32) -> rse_hybrid_stage_dev -> rse_hybrid_run -> rse_hybrid_fetch",
             "encoder_ms_per_batch": enc_ms, "tokens_per_batch": tokens_per_batch,
             "encoder_tokens_per_s": tokens_per_batch / (enc_ms * 1e-3),
@@ -645,6 +650,40 @@ def measure_text_in(args, idx, bm, se, tok_indptr, terms, limit, steps):
                            "note": "index-build shaped input: 2048 chunk texts of 24-64 word pieces per call"},
             "weights": "random (seeded), all-MiniLM-L6-v2 architecture",
             "reference_cpu_encoder": "5-20 ms PER QUERY (SURVEY §8 f2: torch CPU via sentence-transformers; not installable here)"}
+
+
+def measure_rerank(idx, limit):
+    """§8(f3): the cross-encoder rerank of hybrid_search.py:279-312 — CrossEncoder.predict over the (query, document)
+    pairs of the fused union (<= 2 * limit per query) — on the device: the TinyBERT-L2 architecture of
+    cross-encoder/ms-marco-TinyBERT-L2-v2 with seeded random weights, pairs of an 8-token query and a 100-200 token
+    document.  One query's pairs per call (the reference's call shape), and 64 queries' pairs in one call."""
+    from rag_search_engine_b200.encoder import TINYBERT_L2_CONFIG, GpuCrossEncoder, random_state_dict
+    ce = GpuCrossEncoder(idx, random_state_dict(TINYBERT_L2_CONFIG, seed=9, head=1), TINYBERT_L2_CONFIG)
+    rng = np.random.default_rng(23)
+
+    def pairs(n):
+        ids, tts = [], []
+        for _ in range(n):
+            qn, dn = 8, int(rng.integers(100, 201))
+            # numpy rows, as a tokenizer called with return_tensors="np" hands them over (Python int lists cost the
+            # host ~50 ns per token in pack(): 10 ms for the 200 k tokens of the 64-query call)
+            ids.append(np.concatenate(([101], rng.integers(1000, 30000, qn), [102], rng.integers(1000, 30000, dn), [102])).astype(np.int32))
+            tts.append(np.concatenate((np.zeros(qn + 2, np.int32), np.ones(dn + 1, np.int32))))
+        return ids, tts
+    out = {}
+    for name, n_pairs, reps in (("one_query", 2 * limit, 20), ("batch_of_64_queries", 64 * 2 * limit, 5)):
+        ids, tts = pairs(n_pairs)
+        for _ in range(2):
+            ce.predict_ids(ids, tts)
+        t0 = time.perf_counter()
+        for _ in range(reps):
+            sc = ce.predict_ids(ids, tts)
+        dt = (time.perf_counter() - t0) / reps
+        out[name] = {"pairs": n_pairs, "tokens": int(sum(len(x) for x in ids)), "call_ms": 1e3 * dt, "pairs_per_s": n_pairs / dt,
+                     "finite": bool(np.isfinite(sc).all())}
+    out["api"] = "GpuCrossEncoder.predict_ids -> rse_encode (packed tokens, pooler + classifier head), host buffers in and out"
+    out["weights"] = "random (seeded), ms-marco-TinyBERT-L2-v2 architecture"
+    return out
 
 
 def measure_cold_open(emb_host, local_rank):

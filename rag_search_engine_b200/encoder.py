@@ -17,6 +17,8 @@ from __future__ import annotations
 
 from typing import Callable, Dict, List, Optional, Sequence
 
+import itertools
+
 import numpy as np
 
 MINILM_L6_CONFIG = dict(vocab_size=30522, hidden=384, layers=6, heads=12, intermediate=1536, max_positions=512,
@@ -76,13 +78,19 @@ def random_state_dict(config: dict, seed: int = 0, head: int = 0) -> Dict[str, n
 
 def pack(id_lists: Sequence[Sequence[int]], type_lists: Optional[Sequence[Sequence[int]]] = None):
     """Token-id lists -> (ids int32[T], type_ids int32[T] | None, cu_seqlens int32[n + 1])."""
-    lens = np.fromiter((len(x) for x in id_lists), np.int64, count=len(id_lists))
+    lens = np.fromiter(map(len, id_lists), np.int64, count=len(id_lists))
     cu = np.zeros(len(id_lists) + 1, np.int32)
     np.cumsum(lens, out=cu[1:])
-    ids = np.fromiter((t for x in id_lists for t in x), np.int32, count=int(cu[-1]))
-    tt = None
-    if type_lists is not None:
-        tt = np.fromiter((t for x in type_lists for t in x), np.int32, count=int(cu[-1]))
+    total = int(cu[-1])
+
+    def flat(lists):
+        # itertools.chain keeps the walk over the tokens in C (a generator expression costs ~50 ns per token: 10 ms for
+        # the 200 k tokens of a 64-query rerank batch)
+        if total and all(isinstance(x, np.ndarray) for x in lists):
+            return np.concatenate(lists).astype(np.int32, copy=False)
+        return np.fromiter(itertools.chain.from_iterable(lists), np.int32, count=total)
+    ids = flat(id_lists)
+    tt = flat(type_lists) if type_lists is not None else None
     return ids, tt, cu
 
 
@@ -170,8 +178,9 @@ class GpuCrossEncoder:
         return cls(index, sd, config_from_hf(model.config), tok, slot=slot, max_length=ml)
 
     def predict_ids(self, id_lists, type_lists) -> np.ndarray:
-        id_lists = [list(x)[: self.max_length] for x in id_lists]
-        type_lists = [list(x)[: self.max_length] for x in type_lists]
+        ml = self.max_length                                   # (copy only what has to be cut)
+        id_lists = [x if len(x) <= ml else x[:ml] for x in id_lists]
+        type_lists = [x if len(x) <= ml else x[:ml] for x in type_lists]
         ids, tt, cu = pack(id_lists, type_lists)
         out = self.index.encode(self.slot, ids, cu, type_ids=tt)
         if self.activation == "sigmoid":

@@ -23,6 +23,7 @@ try:
     print("python", d.get("e2e_python"))
     print("text_in", d.get("text_in"))
     print("image_search", d.get("image_search"))
+    print("rerank", (d.get("text_in") or {}).get("rerank"))
     print("small", d.get("knn_small_batches"))
     print("knn100m", d.get("knn100m"))
     print("cpu", d.get("cpu_baseline"))
