@@ -208,12 +208,12 @@ enc_gemm_kernel(const float* __restrict__ A, const float* __restrict__ W, const 
 }
 
 // ---------------------------------------------------------------- attention
-// qkv: packed [T, 3*hidden] rows = [q | k | v], head h at columns h*HD.  One CTA per (sequence, head): thread t owns
-// query row t (+128, +256, ... for longer sequences), keys / values stream through shared memory 64 at a time;
+// qkv: packed [T, 3*hidden] rows = [q | k | v], head h at columns h*HD.  One CTA per (sequence, head) of 32..256 threads (the
+// longest sequence of the batch, rse.cu): thread t owns query row t (+blockDim, ... for longer sequences), keys / values stream through shared memory 64 at a time;
 // online softmax (running max / sum), fp32, expf.  Keys beyond the sequence do not exist in the packed layout, which
 // IS the reference's padding mask (BertModel's extended attention mask adds -inf to padded keys).
 template <int HD>
-__global__ void __launch_bounds__(128)
+__global__ void __launch_bounds__(256)
 enc_attention_kernel(const float* __restrict__ qkv, const int32_t* __restrict__ cu_seqlens, int hidden,
                      float* __restrict__ ctx, float* __restrict__ ctx_lo) {   // ctx_lo != NULL: ctx <- hi, ctx_lo <- lo
   constexpr int KB = 64;

@@ -60,6 +60,7 @@ struct Encoder {
   size_t pin_in_n[2] = {0, 0};
   cudaEvent_t pin_ev[2] = {nullptr, nullptr};
   int pin_next = 0;
+  int max_len = 128;                  // longest sequence of the batch being encoded (sizes the attention CTA)
 };
 
 }  // namespace
@@ -2210,8 +2211,13 @@ int enc_forward(rse_index* h, Encoder& e, int n_seq, int T, bool has_types, floa
                 : enc_gemm<0>(h, x, l.wqkv, l.bqkv, qkv, T, 3 * H, H);
     if (rc != RSE_OK) return rc;
     dim3 agrid(n_seq, c.heads);
-    if (hd == 32) enc_attention_kernel<32><<<agrid, 128, 0, h->stream>>>(qkv, cu, H, ctx, ctx_l);
-    else enc_attention_kernel<64><<<agrid, 128, 0, h->stream>>>(qkv, cu, H, ctx, ctx_l);
+    // one thread per query row: a CTA as wide as the longest sequence of the batch (32 .. 256 threads) — search
+    // queries of 4-16 tokens used to idle 7 of 8 lanes of a 128-thread CTA, 160-token rerank pairs took two rounds
+    // (above 128 threads only when the grid leaves SMs idle anyway: 216 registers x 256 threads is one CTA per SM)
+    const int acap = static_cast<int64_t>(n_seq) * c.heads < 2ll * h->sm_count ? 256 : 128;
+    const int athreads = std::min(acap, std::max(32, (e.max_len + 31) / 32 * 32));
+    if (hd == 32) enc_attention_kernel<32><<<agrid, athreads, 0, h->stream>>>(qkv, cu, H, ctx, ctx_l);
+    else enc_attention_kernel<64><<<agrid, athreads, 0, h->stream>>>(qkv, cu, H, ctx, ctx_l);
     LAUNCHED(h);
     rc = tc ? enc_gemm_tc<0>(h, ctx, ctx_l, l.wo_h, l.wo_l, l.bo, tmp, nullptr, T, H, H)
             : enc_gemm<0>(h, ctx, l.wo, l.bo, tmp, T, H, H);
@@ -2251,8 +2257,10 @@ int enc_run(rse_index* h, int32_t slot, const int32_t* ids, const int32_t* type_
   Encoder& e = h->enc[slot];
   if (n_seq < 1 || !ids || !cu || !out_dev) return fail(h, RSE_ERR_INVALID, "rse_encode: bad arguments");
   if (cu[0] != 0) return fail(h, RSE_ERR_INVALID, "rse_encode: cu_seqlens must start at 0");
+  int max_len = 1;
   for (int s = 0; s < n_seq; ++s) {
     const int len = cu[s + 1] - cu[s];
+    max_len = std::max(max_len, len);
     if (len < 1) return fail(h, RSE_ERR_INVALID, "rse_encode: empty sequence (the reference raises 'cannot embed empty text', semantic_search.py:218-219)");
     if (len > e.cfg.max_positions) return fail(h, RSE_ERR_UNSUPPORTED, "rse_encode: sequence longer than max_positions (truncate on the host like the tokenizer does)");
   }
@@ -2281,6 +2289,7 @@ int enc_run(rse_index* h, int32_t slot, const int32_t* ids, const int32_t* type_
   CK(cudaMemcpyAsync(e.cu.p, pin + 2 * static_cast<size_t>(T), sizeof(int32_t) * (n_seq + 1), cudaMemcpyHostToDevice, h->stream));
   CK(cudaEventRecord(e.pin_ev[pb], h->stream));
   h->stats.h2d_bytes += static_cast<int64_t>(sizeof(int32_t)) * (static_cast<int64_t>(T) * (type_ids ? 2 : 1) + n_seq + 1);
+  e.max_len = max_len;
   return enc_forward(h, e, n_seq, T, type_ids != nullptr, out_dev);
 }
 
