@@ -353,6 +353,10 @@ int rse_get_stats(rse_index *h, rse_stats *out);
 /* Survivor counts of the most recent K4 filter pass (one per query of its 256-query block; a count above the
  * survivor cap of 8192 means the query overflowed and was re-run).  Synchronises.  n <= 256. */
 int rse_tc_last_survivors(rse_index *h, int32_t *out_counts, int32_t n);
+/* The order statistic j of the K4 probe's row sample (DESIGN.md §5 "The probe's sample"): the smallest j with
+ * P(Binomial(kprime, 1 / stride) >= j) <= 1e-7, capped at kprime.  Pure host arithmetic — exported so that the claim
+ * can be checked against an independent binomial tail (tests/test_host_cpu.py). */
+int rse_tc_probe_rank(int32_t kprime, int32_t stride);
 int rse_stats_reset(rse_index *h);
 /* Enable CUDA-event timing: an event pair around every scan launch (no extra syncs). */
 int rse_set_timing(rse_index *h, int32_t enabled);

@@ -117,6 +117,7 @@ _SIGNATURES = {
     "rse_hybrid_drain": (ctypes.c_int, [c_void_p, POINTER(c_int32)]),
     "rse_hybrid_stash": (ctypes.c_int, [c_void_p, c_int32]),
     "rse_tc_last_survivors": (ctypes.c_int, [c_void_p, POINTER(c_int32), c_int32]),
+    "rse_tc_probe_rank": (ctypes.c_int, [c_int32, c_int32]),
     "rse_encoder_create": (ctypes.c_int, [c_void_p, c_int32, POINTER(RseEncoderConfig)]),
     "rse_encoder_set_tensor": (ctypes.c_int, [c_void_p, c_int32, c_char_p, POINTER(c_float), c_int64]),
     "rse_encoder_finalize": (ctypes.c_int, [c_void_p, c_int32]),

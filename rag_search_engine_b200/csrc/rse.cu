@@ -2683,6 +2683,11 @@ int rse_hybrid_stash(rse_index* h, int32_t slot) {
   return RSE_OK;
 }
 
+int rse_tc_probe_rank(int32_t kprime, int32_t stride) {
+  if (kprime < 1 || stride < 2) return kprime < 1 ? 0 : kprime;
+  return sample_probe_rank(kprime, stride);
+}
+
 int rse_tc_last_survivors(rse_index* h, int32_t* out_counts, int32_t n) {
   if (!h) return RSE_ERR_INVALID;
   if (!out_counts || n < 0 || n > kTcBN) return fail(h, RSE_ERR_INVALID, "rse_tc_last_survivors: bad arguments");

@@ -427,3 +427,22 @@ def test_gpu_fuzz_generators_run_without_a_gpu():
             except Reached:
                 reached += 1
     assert reached == 12
+
+
+def test_probe_rank_is_the_binomial_tail_quantile():
+    """the K4 probe takes the j-th best value of a 1-in-`stride` row sample as its bound, j = the smallest
+    rank whose binomial tail P(Bin(K', 1/stride) >= j) is at most 1e-7 (the bound is verified on the device anyway;
+    the tail is only how often a second filter pass is paid)."""
+    from scipy.stats import binom
+    from rag_search_engine_b200 import _lib
+    L = _lib.load_library()
+    for stride in (4, 8, 16, 32, 64, 128):
+        for kprime in (1, 2, 5, 10, 50, 100, 256):
+            j = L.rse_tc_probe_rank(kprime, stride)
+            assert 1 <= j <= kprime
+            if j < kprime:
+                assert binom.sf(j - 1, kprime, 1.0 / stride) <= 1e-7 * (1 + 1e-6)
+                assert j == 1 or binom.sf(j - 2, kprime, 1.0 / stride) > 1e-7 * (1 - 1e-6)
+            else:
+                assert kprime == 1 or binom.sf(kprime - 2, kprime, 1.0 / stride) > 1e-7 * (1 - 1e-6)
+    assert L.rse_tc_probe_rank(100, 64) == 12 and L.rse_tc_probe_rank(100, 32) == 16
