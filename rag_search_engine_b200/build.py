@@ -7,6 +7,7 @@ box with the gpurun snapshot.
 """
 from __future__ import annotations
 
+import os
 import subprocess
 import sys
 from pathlib import Path
@@ -36,7 +37,9 @@ def needs_build() -> bool:
 def build(force: bool = False, verbose: bool = False) -> Path:
     if not force and not needs_build():
         return LIB
-    cmd = ["nvcc", *NVCC_FLAGS, "-o", str(LIB), *map(str, SOURCES)]
+    # RSE_EXTRA_NVCC_FLAGS: e.g. -DRSE_REFINE_TIMING for the per-phase stamps scripts/refine_timing.py reads
+    extra = os.environ.get("RSE_EXTRA_NVCC_FLAGS", "").split()
+    cmd = ["nvcc", *NVCC_FLAGS, *extra, "-o", str(LIB), *map(str, SOURCES)]
     proc = subprocess.run(cmd, capture_output=True, text=True)
     # the log is tracked (register / spill counts per kernel are evidence); drop the lines that differ on every build
     log = "\n".join(l for l in (proc.stdout + proc.stderr).splitlines() if "Compile time" not in l) + "\n"
