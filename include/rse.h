@@ -93,7 +93,7 @@ int rse_set_fma(rse_index *h, int32_t use_fma);
  * streaming scan): 0 = auto (batches of >= RSE_TC_MIN_BATCH queries on >= 256 k rows, dim 384), 1 = never,
  * 2 = whenever the shape allows it.  The probe/filter GEMM runs over an fp16 normalised shadow of the corpus
  * (knn_tc3.cuh; built once at the first batch that needs it, +768 B per row of device memory).  Measured on
- * S-600k (bench.py knn_small_batches, r02): the K4 chain costs 0.82-0.92 ms per call for 1..64 queries, the exact
+ * S-600k (bench.py knn_small_batches, r02): the K4 chain costs 0.75-0.82 ms per call for 1..64 queries, the exact
  * scan 1.21 / 1.41 / 1.65 / 1.72 / 2.32 / 3.98 ms for 1 / 2 / 3 / 4 / 8 / 16 — K4 wins from the first query on.  A
  * single query takes the exact streaming scan (north_star: batch-1 = the HBM-bound kernel; no shadow needed) until
  * a batch has built the shadow, and K4 from then on; mode 2 sends it through K4 from the start. */

@@ -52,10 +52,11 @@ constexpr int kT3KBlocks = kScanD / kT3BK;                // 6
 constexpr int kT3StageBytes = kT3HalfRows * kT3BK * 2;    // 16,384
 constexpr int kT3Stages = 4;                              // 64 KB of rows in flight per SM.  3..7 stages measure the same
                                                           // (0.81-0.85 ms, r01): the pass is not fill-bound, and the
-                                                          // smaller footprint (178 KB, 120 registers) leaves room for ONE
-                                                          // BM25 CTA per SM to run underneath it (rse.cu, hybrid step).
-                                                          // Room for two (3 stages, 96 registers) was worse: the filter
-                                                          // slowed from 0.86 to 0.99 ms and the step from 1.28 to 1.40 ms
+                                                          // smaller footprint (178 KB; 90 registers since the epilogue
+                                                          // reads 32 columns at a time) leaves room for ONE BM25 CTA per SM
+                                                          // to run underneath it (rse.cu, hybrid step; 896 threads, r02).
+                                                          // Room for two (3 stages, r01) was worse: the filter slowed
+                                                          // from 0.86 to 0.99 ms and the step from 1.28 to 1.40 ms
 constexpr int kT3ProbeTop = 8;                            // MODE 2: sample values kept per thread
 constexpr int kT3QueueCap = 128;                          // per-warp survivor queue (entries of 12 B)
 constexpr int kT3QueueFlush = 32;                         // flushed to global memory once this full
