@@ -40,7 +40,8 @@ def inject_ties(rng, emb, n_dup):
 # ----------------------------------------------------------------------------- KNN
 @pytest.mark.parametrize("n,dim,kprime,nq", [(5000, 384, 100, 5), (40000, 384, 100, 9), (3000, 384, 1, 3),
                                               (1500, 384, 1500, 2), (4100, 384, 4096, 1), (2500, 48, 50, 4),
-                                              (37, 4, 10, 3), (1025, 384, 100, 8), (31, 384, 5, 1)])
+                                              (37, 4, 10, 3), (1025, 384, 100, 8), (31, 384, 5, 1),
+                                              (3000, 512, 20, 7), (2000, 768, 10, 16), (1200, 100, 15, 3)])   # any-width scan
 def test_knn_matches_oracle_bit_exact(fresh_index, n, dim, kprime, nq):
     rng = np.random.default_rng(n + dim + kprime)
     emb = inject_ties(rng, unit_rows(rng, n, dim), n // 20)
