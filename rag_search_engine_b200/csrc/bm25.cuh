@@ -418,8 +418,10 @@ constexpr unsigned int kBsRangeCap = 256;         // documents that may cross th
 constexpr int kBsFinalCap = 64;                   // finalists (k + ties) ranked exactly
 
 // out8 (optional): the 8-byte stream bm25_fx_kernel reads, {doc, round(w * wq_scale)} — see the K6'' header
+// out4 (optional): the 4-byte stream, (doc % kBmRange) | round(w * wq4_scale) << 13 — see bm25_fx_body<.., P4 = true>
 __global__ void bm25_weight_kernel(const uint2* __restrict__ post, const double* __restrict__ normk, int64_t n,
-                                   double k1p1, Post16* __restrict__ out, uint2* __restrict__ out8, double wq_scale) {
+                                   double k1p1, Post16* __restrict__ out, uint2* __restrict__ out8, double wq_scale,
+                                   uint32_t* __restrict__ out4, double wq4_scale) {
   const int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
   if (i >= n) return;
   const uint2 e = post[i];
@@ -429,6 +431,11 @@ __global__ void bm25_weight_kernel(const uint2* __restrict__ post, const double*
   o.w = __ddiv_rn(__dmul_rn(tfd, k1p1), __dadd_rn(tfd, normk[e.x]));
   out[i] = o;
   if (out8) out8[i] = make_uint2(e.x, __double2uint_rn(__dmul_rn(o.w, wq_scale)));
+  if (out4) {
+    unsigned int wq = __double2uint_rn(__dmul_rn(o.w, wq4_scale));
+    if (wq > 0x7FFFFu) wq = 0x7FFFFu;                      // (k1+1) * wq4_scale <= 2^19: only a weight at the very top clamps
+    out4[i] = (e.x % static_cast<uint32_t>(kBmRange)) | (wq << 13);
+  }
 }
 
 constexpr int bs_smem_bytes() {
@@ -705,7 +712,14 @@ __host__ __device__ constexpr int fx_smem_bytes(int rpg) {
 // a 55-register variant with four posting loads in flight per lane was slower overall (1.13 ms: only two of those
 // fit an SM once the filter is gone).  What it competes for there is the memory system: the filter streams the
 // shadow at 4.9 TB/s of the 6.5 the HBM gives.
-template <int THREADS, int DEPTH>
+// P4 (r02): the posting stream is 4 BYTES per posting — 13 bits of document offset inside its range (the range is
+// known from the slice being read) and a 19-bit weight, wq = round(w * wq4_scale), (k1+1) * wq4_scale <= 2^19.  Half
+// the bytes (the kernel shares the HBM with the tensor-core filter in a hybrid step) and 128 postings per warp item
+// instead of 64, so the per-item token lookup is paid half as often.  The price is precision: a weight is known to
+// +-1 unit of wq (0.5 from its rounding, the clamp at the top), i.e. +-idfx units of the sum, so the margin everything
+// is decided with grows from the constant kFxMargin to 2 * sum_t (idfx_t + 0.5) + 8 units PER QUERY (~1e-3 in score
+// units for a 16-token query with the default k1) — a few more finalists for the exact finish kernel, same results.
+template <int THREADS, int DEPTH, bool P4>
 __device__ __forceinline__ void
 bm25_fx_body(const int64_t* __restrict__ indptr, const uint2* __restrict__ post8, const uint32_t* __restrict__ roff,
              int nr, const int32_t* __restrict__ tok_indptr, const int32_t* __restrict__ term_rows,
@@ -726,7 +740,7 @@ bm25_fx_body(const int64_t* __restrict__ indptr, const uint2* __restrict__ post8
   __shared__ double s_idfx[kBsMaxTok];                                                 // idf * scale / wq_scale (exact: powers of two)
   __shared__ int s_term[kBsMaxTok];
   __shared__ unsigned int s_ncand, s_nkept;
-  __shared__ unsigned int s_min, s_tw;
+  __shared__ unsigned int s_min, s_tw, s_margin;
 
   const int g = g0 + (qfast ? blockIdx.y : blockIdx.x);    // g0: first group of this launch (rse.cu splits the groups)
   const int q = q0 + (qfast ? blockIdx.x : blockIdx.y);
@@ -756,6 +770,16 @@ bm25_fx_body(const int64_t* __restrict__ indptr, const uint2* __restrict__ post8
     uint4* a4 = reinterpret_cast<uint4*>(acc);
     for (int i = threadIdx.x; i < kBmRange / 4; i += blockDim.x) a4[i] = make_uint4(0u, 0u, 0u, 0u);
   }
+  if (threadIdx.x == 0) {                         // the margin lives in shared memory: the kernel has no register to spare
+    unsigned int mg = kFxMargin;
+    if (P4) {
+      double m = 0.0;
+      for (int t = 0; t < ntok; ++t) m += s_idfx[t] + 0.5;
+      const unsigned int mq = 2u * static_cast<unsigned int>(ceil(m)) + 8u;
+      if (mq > mg) mg = mq;
+    }
+    s_margin = mg;
+  }
   __syncthreads();
 
   uint2* cand = s_cand0;
@@ -772,7 +796,7 @@ bm25_fx_body(const int64_t* __restrict__ indptr, const uint2* __restrict__ post8
     __syncthreads();
     if (threadIdx.x < n) {
       const uint2 me = cand[threadIdx.x];
-      const unsigned int bar = me.x + kFxMargin;
+      const unsigned int bar = me.x + s_margin;
       unsigned int greater = 0u;
       for (unsigned int j = 0; j < n; ++j) greater += cand[j].x > bar ? 1u : 0u;
       if (greater < static_cast<unsigned int>(k)) {
@@ -783,7 +807,7 @@ bm25_fx_body(const int64_t* __restrict__ indptr, const uint2* __restrict__ post8
     __syncthreads();
     uint2* tmp = cand; cand = cand_alt; cand_alt = tmp;
     const unsigned int mn = s_min;
-    theta = mn > kFxMargin ? mn - kFxMargin : 1u;
+    theta = mn > s_margin ? mn - s_margin : 1u;
     established = true;
     __syncthreads();
     if (threadIdx.x == 0) s_ncand = s_nkept;
@@ -803,7 +827,8 @@ bm25_fx_body(const int64_t* __restrict__ indptr, const uint2* __restrict__ post8
       const uint32_t a = s_off[lane * ostride + jr];
       sn = s_off[lane * ostride + jr + 1] - a;
       sb = s_base[lane] + a;
-      c = sn ? (sn + static_cast<unsigned int>(sb & 1) + 63u) >> 6 : 0u;      // pairs start at an even posting index
+      if (P4) c = sn ? (sn + static_cast<unsigned int>(sb & 3) + 127u) >> 7 : 0u;   // quads start at a multiple of 4
+      else c = sn ? (sn + static_cast<unsigned int>(sb & 1) + 63u) >> 6 : 0u;        // pairs start at an even posting index
     }
     unsigned int incl = c;
 #pragma unroll
@@ -820,7 +845,8 @@ bm25_fx_body(const int64_t* __restrict__ indptr, const uint2* __restrict__ post8
     const int sb_hi = static_cast<int>(static_cast<unsigned long long>(sb) >> 32);
 
     auto item_load = [&](unsigned int item, uint4& e, double& idfx) {
-      e = make_uint4(0xFFFFFFFFu, 0u, 0xFFFFFFFFu, 0u);   // {doc, wq, doc, wq}; doc = ~0: nothing to add
+      e = P4 ? make_uint4(0u, 0u, 0u, 0u)                 // P4: a zero word adds nothing
+             : make_uint4(0xFFFFFFFFu, 0u, 0xFFFFFFFFu, 0u);   // {doc, wq, doc, wq}; doc = ~0: nothing to add
       idfx = 0.0;
       if (item >= n_items) return;                        // warp-uniform
       // token of the item: the highest lane holding items whose first item is <= item
@@ -830,9 +856,24 @@ bm25_fx_body(const int64_t* __restrict__ indptr, const uint2* __restrict__ post8
       const long long tsb = static_cast<long long>(
           (static_cast<unsigned long long>(static_cast<unsigned int>(__shfl_sync(0xFFFFFFFFu, sb_hi, t))) << 32) |
           static_cast<unsigned int>(__shfl_sync(0xFFFFFFFFu, sb_lo, t)));
-      const long long se = tsb + __shfl_sync(0xFFFFFFFFu, sn, t);
-      const long long j0 = (tsb & ~1LL) + chunk * 64u + 2u * lane;
+      const unsigned int tsn = __shfl_sync(0xFFFFFFFFu, sn, t);
       idfx = s_idfx[t];
+      if (P4) {
+        // four packed postings per lane; a word of 0 (weight 0) adds nothing, so that is also the "not mine" mark
+        // (positions relative to the slice start, 32-bit: the kernel has no register to spare)
+        const int len = static_cast<int>(tsn);
+        const int rel = static_cast<int>(chunk * 128u + 4u * lane) - static_cast<int>(tsb & 3);   // of e.x; >= -3
+        if (rel + 3 >= 0 && rel < len) {                  // the quad overlaps the slice (the stream is padded by one quad)
+          e = __ldg(reinterpret_cast<const uint4*>(reinterpret_cast<const uint32_t*>(post8) + (tsb + rel)));
+          if (rel < 0) e.x = 0u;
+          if (rel + 1 < 0 || rel + 1 >= len) e.y = 0u;
+          if (rel + 2 < 0 || rel + 2 >= len) e.z = 0u;
+          if (rel + 3 >= len) e.w = 0u;
+        }
+        return;
+      }
+      const long long se = tsb + tsn;
+      const long long j0 = (tsb & ~1LL) + chunk * 64u + 2u * lane;
       if (j0 + 1 >= tsb && j0 < se) {                     // the pair overlaps the slice (the stream is padded by one pair)
         e = __ldg(reinterpret_cast<const uint4*>(post8 + j0));
         if (j0 < tsb) e.x = 0xFFFFFFFFu;
@@ -841,6 +882,13 @@ bm25_fx_body(const int64_t* __restrict__ indptr, const uint2* __restrict__ post8
     };
     auto item_apply = [&](const uint4& e, double idfx) {
       // sums only grow and nothing reads them before the barrier: plain reductions, no returned value to wait for
+      if (P4) {
+        const uint32_t w4[4] = {e.x, e.y, e.z, e.w};
+#pragma unroll
+        for (int u = 0; u < 4; ++u)
+          if (w4[u] >> 13) atomicAdd(&acc[w4[u] & 0x1FFFu], __double2uint_rn(__dmul_rn(idfx, __uint2double_rn(w4[u] >> 13))));
+        return;
+      }
       if (e.x != 0xFFFFFFFFu) atomicAdd(&acc[e.x - doc_base], __double2uint_rn(__dmul_rn(idfx, __uint2double_rn(e.y))));
       if (e.z != 0xFFFFFFFFu) atomicAdd(&acc[e.z - doc_base], __double2uint_rn(__dmul_rn(idfx, __uint2double_rn(e.w))));
     };
@@ -895,7 +943,7 @@ bm25_fx_body(const int64_t* __restrict__ indptr, const uint2* __restrict__ post8
       }
       __syncthreads();
       const unsigned int tb = s_tw;
-      if (tb != 0u) { theta = tb > kFxMargin ? tb - kFxMargin : 1u; established = true; }
+      if (tb != 0u) { theta = tb > s_margin ? tb - s_margin : 1u; established = true; }
     }
     // scan + clear: collect the documents at or above theta (theta = 0: every touched document)
     {
@@ -934,13 +982,13 @@ bm25_fx_body(const int64_t* __restrict__ indptr, const uint2* __restrict__ post8
   if (threadIdx.x == 0) fin_cnt[cbase] = static_cast<int>(n);
 }
 
-template <int THREADS>
+template <int THREADS, bool P4>
 __global__ void __launch_bounds__(THREADS, (THREADS <= 512 ? 4 : 2))
 bm25_fx_kernel(const int64_t* __restrict__ indptr, const uint2* __restrict__ post8, const uint32_t* __restrict__ roff,
                int nr, const int32_t* __restrict__ tok_indptr, const int32_t* __restrict__ term_rows,
                const double* __restrict__ tok_idf, double scale, int q0, int k, int rpg, int ng, int g0,
                uint2* __restrict__ fin, int* __restrict__ fin_cnt, int* __restrict__ status) {
-  bm25_fx_body<THREADS, 2>(indptr, post8, roff, nr, tok_indptr, term_rows, tok_idf, scale, q0, k, rpg, ng, g0, fin, fin_cnt, status);
+  bm25_fx_body<THREADS, 2, P4>(indptr, post8, roff, nr, tok_indptr, term_rows, tok_idf, scale, q0, k, rpg, ng, g0, fin, fin_cnt, status);
 }
 // K7'': one CTA per query bm25_fx_kernel finished (see the header above).
 __global__ void __launch_bounds__(kBmThreads)
@@ -949,7 +997,7 @@ bm25_fx_finish_kernel(const uint2* __restrict__ fin, const int* __restrict__ fin
                       const uint32_t* __restrict__ roff, int nr, const int32_t* __restrict__ tok_indptr,
                       const int32_t* __restrict__ term_rows, const double* __restrict__ tok_idf, int q0, int k,
                       double* __restrict__ out_score, int* __restrict__ out_doc, int* __restrict__ out_count,
-                      unsigned long long* __restrict__ counters) {
+                      unsigned long long* __restrict__ counters, double idfx_scale) {   // idfx_scale > 0: 4-byte postings
   __shared__ uint2 s_c[kBsMaxGroups * kFxFinalCap];       // 12 KB: the groups' candidates {sum, doc}
   __shared__ double s_w[kFxRescoreCap][kBsMaxTok];        // 12 KB: weight of (document, token), 0 = not in the list
   __shared__ uint32_t s_doc[kFxRescoreCap];
@@ -958,6 +1006,13 @@ bm25_fx_finish_kernel(const uint2* __restrict__ fin, const int* __restrict__ fin
   const int q = q0 + blockIdx.x;
   if (status[q] != 0) return;                             // the general path owns this query
   const int t0 = tok_indptr[q], ntok = tok_indptr[q + 1] - t0;
+  unsigned int margin = kFxMargin;                        // the same per-query margin bm25_fx_body decided with
+  if (idfx_scale > 0.0) {
+    double m = 0.0;
+    for (int t = 0; t < ntok; ++t) m += tok_idf[t0 + t] * idfx_scale + 0.5;
+    const unsigned int mq = 2u * static_cast<unsigned int>(ceil(m)) + 8u;
+    if (mq > margin) margin = mq;
+  }
   if (threadIdx.x == 0) { s_n = 0u; s_m = 0u; }
   __syncthreads();
   for (int g = 0; g < ng; ++g) {
@@ -970,7 +1025,7 @@ bm25_fx_finish_kernel(const uint2* __restrict__ fin, const int* __restrict__ fin
   // documents that fewer than k others beat beyond the margin: the exact top-k is among them
   for (unsigned int e = threadIdx.x; e < n; e += blockDim.x) {
     const uint2 me = s_c[e];
-    const unsigned int bar = me.x + kFxMargin;
+    const unsigned int bar = me.x + margin;
     unsigned int greater = 0u;
     for (unsigned int j = 0; j < n; ++j) greater += s_c[j].x > bar ? 1u : 0u;
     if (greater < static_cast<unsigned int>(k)) {

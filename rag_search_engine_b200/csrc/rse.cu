@@ -201,6 +201,9 @@ struct rse_index {
   Post16* post16 = nullptr;        // {doc, tf, w}: postings with the (k1, b)-dependent weight precomputed (bm25_stream_kernel)
   uint2* post8 = nullptr;          // {doc, round(w * wq_scale)}: the 8-byte stream of bm25_fx_kernel (padded by one pair)
   double wq_scale = 0.0;
+  uint32_t* post4 = nullptr;       // (doc % range) | round(w * wq4_scale) << 13: the 4-byte stream (padded by one quad)
+  double wq4_scale = 0.0;
+  bool bm25_p4 = true;             // RSE_BM25_P4=0: bm25_fx_kernel reads the 8-byte stream (r02 first half)
   double w_k1 = NAN, w_b = NAN;
   DevBuf b_shi, b_slo, b_scnt, b_status, b_flagged;
   int bm25_mode = 0;               // 0 = fixed-point streaming kernel (default), 1 = exact-order streaming kernel, 2 = general kernel only
@@ -293,7 +296,7 @@ void release_embeddings(rse_index* h) {
 }
 
 void release_bm25(rse_index* h) {
-  free_ptr(h->indptr); free_ptr(h->post); free_ptr(h->dl); free_ptr(h->roff); free_ptr(h->normk); free_ptr(h->post16); free_ptr(h->post8);
+  free_ptr(h->indptr); free_ptr(h->post); free_ptr(h->dl); free_ptr(h->roff); free_ptr(h->normk); free_ptr(h->post16); free_ptr(h->post8); free_ptr(h->post4);
   h->w_k1 = NAN; h->w_b = NAN;
   h->df_host.clear();
   h->n_terms = h->n_postings = h->n_docs = h->n_movies = 0;
@@ -983,6 +986,7 @@ int rse_create(int32_t device, rse_index** out) {
   else
     h->dev_counters = nullptr;
   // diagnostics: RSE_NO_OVERLAP=1 keeps the hybrid step's BM25 on the caller's stream (no second stream)
+  if (const char* ev = std::getenv("RSE_BM25_P4")) h->bm25_p4 = !(ev[0] == '0');
   if (const char* ev = std::getenv("RSE_BM25_QFAST")) h->bm25_qfast = !(ev[0] == '0');
   if (const char* ev = std::getenv("RSE_BM25_PAD")) h->bm25_pad = std::max(0, std::atoi(ev));
   if (const char* ev = std::getenv("RSE_BM25_WIDE_PCT")) { const int v = std::atoi(ev); if (v >= 0 && v <= 100) h->bm25_wide_pct = v; }
@@ -1428,10 +1432,14 @@ int rse_load_bm25(rse_index* h, const int64_t* indptr, const uint32_t* doc_idx, 
   if (!(h->attr_mask & (1u << 14))) {
     CK(cudaFuncSetAttribute(bm25_score_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kBmRange * 9));
     CK(cudaFuncSetAttribute(bm25_stream_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bs_smem_bytes()));
-    CK(cudaFuncSetAttribute(bm25_fx_kernel<kBsThreads>, cudaFuncAttributeMaxDynamicSharedMemorySize, fx_smem_bytes(kBsMaxRpg) + h->bm25_pad));
-    CK(cudaFuncSetAttribute(bm25_fx_kernel<kBsThreads>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
-    CK(cudaFuncSetAttribute(bm25_fx_kernel<kBsWideThreads>, cudaFuncAttributeMaxDynamicSharedMemorySize, fx_smem_bytes(kBsMaxRpg)));
-    CK(cudaFuncSetAttribute(bm25_fx_kernel<kBsWideThreads>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+    CK(cudaFuncSetAttribute(bm25_fx_kernel<kBsThreads, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, fx_smem_bytes(kBsMaxRpg) + h->bm25_pad));
+    CK(cudaFuncSetAttribute(bm25_fx_kernel<kBsThreads, false>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+    CK(cudaFuncSetAttribute(bm25_fx_kernel<kBsWideThreads, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, fx_smem_bytes(kBsMaxRpg)));
+    CK(cudaFuncSetAttribute(bm25_fx_kernel<kBsWideThreads, false>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+    CK(cudaFuncSetAttribute(bm25_fx_kernel<kBsThreads, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, fx_smem_bytes(kBsMaxRpg) + h->bm25_pad));
+    CK(cudaFuncSetAttribute(bm25_fx_kernel<kBsThreads, true>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+    CK(cudaFuncSetAttribute(bm25_fx_kernel<kBsWideThreads, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, fx_smem_bytes(kBsMaxRpg)));
+    CK(cudaFuncSetAttribute(bm25_fx_kernel<kBsWideThreads, true>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
     h->attr_mask |= 1u << 14;
   }
   return RSE_OK;
@@ -1539,10 +1547,16 @@ int bm25_run(rse_index* h, int nq, int k, double k1, double b) {
         const double m = std::frexp(k1p1, &e);                 // k1p1 = m * 2^e, 0.5 <= m < 1
         h->wq_scale = std::ldexp(1.0, m == 0.5 ? 32 - e : 31 - e);
         if (!h->post8) CK(cudaMalloc(&h->post8, sizeof(uint2) * (static_cast<size_t>(h->n_postings) + 2)));
+        h->wq4_scale = 0.0;
+        if (h->bm25_p4) {                                      // largest power of two with (k1 + 1) * wq4_scale <= 2^19
+          h->wq4_scale = std::ldexp(1.0, m == 0.5 ? 20 - e : 19 - e);
+          if (!h->post4) CK(cudaMalloc(&h->post4, sizeof(uint32_t) * (static_cast<size_t>(h->n_postings) + 8)));
+        }
       }
       const int threads = 256;
       bm25_weight_kernel<<<static_cast<unsigned int>((h->n_postings + threads - 1) / threads), threads, 0, h->stream>>>(
-          h->post, h->normk, h->n_postings, k1p1, h->post16, h->wq_scale > 0.0 ? h->post8 : nullptr, h->wq_scale);
+          h->post, h->normk, h->n_postings, k1p1, h->post16, h->wq_scale > 0.0 ? h->post8 : nullptr, h->wq_scale,
+          h->wq4_scale > 0.0 ? h->post4 : nullptr, h->wq4_scale);
       LAUNCHED(h);
       h->w_k1 = k1; h->w_b = b;
     }
@@ -1594,27 +1608,32 @@ int bm25_run(rse_index* h, int nq, int k, double k1, double b) {
       // groups CAN be split between the two shapes — measured, the split loses (see bm25_wide_pct)
       const bool under_filter = h->bm25_wide && h->bm25_qfast && h->stream_b && h->stream == h->stream_b;
       const int g_wide = under_filter ? std::min(ng, std::max(1, (ng * h->bm25_wide_pct + 50) / 100)) : 0;
+      const bool p4 = h->bm25_p4 && h->wq4_scale > 0.0 && h->post4;
+      const uint2* stream8 = p4 ? reinterpret_cast<const uint2*>(h->post4) : h->post8;   // P4 reads it as uint32
+      const double idfx_scale = fx_scale / (p4 ? h->wq4_scale : h->wq_scale);
+      auto launch_fx = [&](auto kernel, dim3 grid, int threads, size_t smem, int g0) {
+        kernel<<<grid, threads, smem, h->stream>>>(
+            h->indptr, stream8, h->roff, h->nr, static_cast<const int32_t*>(h->b_tokptr.p),
+            static_cast<const int32_t*>(h->b_terms.p), static_cast<const double*>(h->b_idf.p), idfx_scale, q0, k,
+            rpg_arg, ng, g0, fin, fcnt, status);
+      };
       if (g_wide > 0) {
-        bm25_fx_kernel<kBsWideThreads><<<dim3(nc, g_wide), kBsWideThreads, fx_smem_bytes(rpg), h->stream>>>(
-            h->indptr, h->post8, h->roff, h->nr, static_cast<const int32_t*>(h->b_tokptr.p),
-            static_cast<const int32_t*>(h->b_terms.p), static_cast<const double*>(h->b_idf.p), fx_scale / h->wq_scale, q0, k,
-            rpg_arg, ng, 0, fin, fcnt, status);
+        if (p4) launch_fx(bm25_fx_kernel<kBsWideThreads, true>, dim3(nc, g_wide), kBsWideThreads, fx_smem_bytes(rpg), 0);
+        else launch_fx(bm25_fx_kernel<kBsWideThreads, false>, dim3(nc, g_wide), kBsWideThreads, fx_smem_bytes(rpg), 0);
         LAUNCHED(h);
       }
       if (g_wide < ng) {
         const int g_rest = ng - g_wide;
-        bm25_fx_kernel<kBsThreads><<<h->bm25_qfast ? dim3(nc, g_rest) : dim3(ng, nc), kBsThreads,
-                                     fx_smem_bytes(rpg) + h->bm25_pad, h->stream>>>(
-            h->indptr, h->post8, h->roff, h->nr, static_cast<const int32_t*>(h->b_tokptr.p),
-            static_cast<const int32_t*>(h->b_terms.p), static_cast<const double*>(h->b_idf.p), fx_scale / h->wq_scale, q0, k,
-            rpg_arg, ng, g_wide, fin, fcnt, status);
+        const dim3 grid = h->bm25_qfast ? dim3(nc, g_rest) : dim3(ng, nc);
+        if (p4) launch_fx(bm25_fx_kernel<kBsThreads, true>, grid, kBsThreads, fx_smem_bytes(rpg) + h->bm25_pad, g_wide);
+        else launch_fx(bm25_fx_kernel<kBsThreads, false>, grid, kBsThreads, fx_smem_bytes(rpg) + h->bm25_pad, g_wide);
         LAUNCHED(h);
       }
       bm25_fx_finish_kernel<<<nc, kBmThreads, 0, h->stream>>>(
           fin, fcnt, ng, status, h->indptr, h->post16, h->roff, h->nr, static_cast<const int32_t*>(h->b_tokptr.p),
           static_cast<const int32_t*>(h->b_terms.p), static_cast<const double*>(h->b_idf.p), q0, k,
           static_cast<double*>(h->b_score.p), static_cast<int*>(h->b_doc.p), static_cast<int*>(h->b_count.p),
-          h->dev_counters);
+          h->dev_counters, p4 ? idfx_scale : 0.0);
       LAUNCHED(h);
     } else if (stream) {
       const size_t per_qs = static_cast<size_t>(ng) * std::max(k, 2 * kFxFinalCap);
