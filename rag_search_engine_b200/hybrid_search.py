@@ -250,7 +250,7 @@ class HybridSearch:
                               knn_multiplier: int = 10, k1: float = 1.5, b: float = 0.75):
         oid, osc, oa, ob, oc = self._hybrid_batch(1, float(alpha), token_lists, query_vecs, limit, knn_multiplier, k1, b)
         return [[{"id": int(oid[q, j]), "bm25": float(oa[q, j]), "semantic": float(ob[q, j]),
-                  "score": float(osc[q, j])} for j in range(oc[q])] for q in range(len(token_lists))]
+                  "score": float(osc[q, j])} for j in range(oc[q])] for q in range(len(oc))]
 
     def rrf_search_texts(self, token_lists, encoder_ids, encoder, k=60, limit: int = 10, knn_multiplier: int = 10,
                          k1: float = 1.5, b: float = 0.75, as_arrays: bool = False):

@@ -60,19 +60,36 @@ def export_bm25(conn: sqlite3.Connection) -> Bm25Arrays:
     term_ids = np.array([t[0] for t in terms], np.int64)
     term_row = {t[1]: i for i, t in enumerate(terms)}
     T = len(terms)
-    # postings in (term_id, doc_id) order = the autoindex order the reference reads them in (:214-218)
+    # postings in (term_id, doc_id) order = the autoindex order the reference reads them in (:214-218).  One result
+    # row per TERM (group_concat over the (term_id, doc_id) autoindex), parsed in bulk: a Python tuple per posting
+    # costs ~1.3 us in sqlite3's row loop alone — minutes at 54 M postings — against ~0.5 us this way.  Term-id
+    # slices bound the size of the concatenated strings.
     t_list: List[np.ndarray] = []
     d_list: List[np.ndarray] = []
     f_list: List[np.ndarray] = []
-    cur.execute("SELECT term_id, doc_id, json_array_length(positions) FROM postings ORDER BY term_id, doc_id")
-    while True:
-        chunk = cur.fetchmany(1 << 18)
-        if not chunk:
-            break
-        a = np.array(chunk, np.int64).reshape(-1, 3)
-        t_list.append(a[:, 0]); d_list.append(a[:, 1]); f_list.append(a[:, 2])
+    (n_post,) = cur.execute("SELECT COUNT(*) FROM postings").fetchone()
+    if n_post:
+        t_lo, t_hi = cur.execute("SELECT MIN(term_id), MAX(term_id) FROM postings").fetchone()
+        n_slices = max(1, -(-n_post // (1 << 22)))
+        step = max(1, -(-(t_hi - t_lo + 1) // n_slices))
+        for lo in range(t_lo, t_hi + 1, step):
+            grp = cur.execute("SELECT term_id, COUNT(*), group_concat(doc_id), group_concat(json_array_length(positions)) "
+                              "FROM postings WHERE term_id >= ? AND term_id < ? GROUP BY term_id", (lo, lo + step)).fetchall()
+            if not grp:
+                continue
+            cnt = np.array([g[1] for g in grp], np.int64)
+            t_list.append(np.repeat(np.array([g[0] for g in grp], np.int64), cnt))
+            d_list.append(np.fromstring(",".join(g[2] for g in grp), dtype=np.int64, sep=","))
+            f_list.append(np.fromstring(",".join(g[3] for g in grp), dtype=np.int64, sep=","))
+            if len(d_list[-1]) != cnt.sum() or len(f_list[-1]) != cnt.sum():
+                raise RuntimeError("postings export: group_concat row count mismatch")
     if t_list:
         pt = np.concatenate(t_list); pd = np.concatenate(d_list); pf = np.concatenate(f_list)
+        # SQL does not promise an order inside a group (in practice the autoindex gives doc_id ascending): check, and
+        # sort when it is not the reference's read order
+        if len(pt) > 1 and not (((pt[1:] > pt[:-1]) | ((pt[1:] == pt[:-1]) & (pd[1:] > pd[:-1]))).all()):
+            order = np.lexsort((pd, pt))
+            pt, pd, pf = pt[order], pd[order], pf[order]
     else:
         pt = pd = pf = np.zeros(0, np.int64)
     trow = np.searchsorted(term_ids, pt)
@@ -115,14 +132,21 @@ def export_embeddings(conn: sqlite3.Connection, table: str = VEC_TABLE) -> EmbAr
         # a keyword-only or fresh database: the reference creates an EMPTY chunk_embeddings table at open time
         # (semantic_search.py:94-101) and query_top_k returns [] — same here: no rows, no error
         return EmbArrays(np.zeros((0, 1), np.float32), None, np.zeros(0, np.int64), np.zeros(0, np.int32), movie_ids, 0)
-    chunk_movie = (dict(cur.execute("SELECT id, movie_id FROM chunks").fetchall())
-                   if _table_exists(conn, "chunks") else {})
-    blocks = cur.execute(
-        f"SELECT c.chunk_id, c.size, c.validity, c.rowids, v.vectors FROM {table}_chunks c "
-        f"JOIN {table}_vector_chunks00 v ON v.rowid = c.chunk_id ORDER BY c.chunk_id").fetchall()
-    embs, valids, rowids = [], [], []
+    empty = EmbArrays(np.zeros((0, 1), np.float32), None, np.zeros(0, np.int64), np.zeros(0, np.int32), movie_ids, 0)
+    (n_blocks,) = cur.execute(f"SELECT COUNT(*) FROM {table}_chunks c JOIN {table}_vector_chunks00 v "
+                              f"ON v.rowid = c.chunk_id").fetchone()
+    if n_blocks == 0:
+        return empty
+    # one pass over the blobs straight into the final arrays (sized from the block count; blocks without live rows
+    # are skipped and trimmed off below): peak memory is the matrix itself, not the matrix plus a list of its blobs
+    emb = None
+    valid = np.zeros(n_blocks * VEC0_BLOCK, np.uint8)
+    rowid = np.zeros(n_blocks * VEC0_BLOCK, np.int64)
     dim = None
-    for _cid, size, validity, rowid_blob, vectors in blocks:
+    n = 0
+    for _cid, size, validity, rowid_blob, vectors in cur.execute(
+            f"SELECT c.chunk_id, c.size, c.validity, c.rowids, v.vectors FROM {table}_chunks c "
+            f"JOIN {table}_vector_chunks00 v ON v.rowid = c.chunk_id ORDER BY c.chunk_id"):
         if size != VEC0_BLOCK:
             raise RuntimeError(f"vec0 chunk_size {size} != 1024 (the reference never sets chunk_size)")
         v = np.unpackbits(np.frombuffer(validity, np.uint8), bitorder="little")[:size]
@@ -132,29 +156,34 @@ def export_embeddings(conn: sqlite3.Connection, table: str = VEC_TABLE) -> EmbAr
         d = vec.size // size
         if dim is None:
             dim = d
+            emb = np.empty((n_blocks * VEC0_BLOCK, dim), np.float32)
         elif d != dim:
             raise RuntimeError("inconsistent vector dimension across vec0 blocks")
-        embs.append(vec.reshape(size, d))
-        valids.append(v.astype(np.uint8))
-        rowids.append(np.frombuffer(rowid_blob, np.int64)[:size])
-    if not embs:
-        return EmbArrays(np.zeros((0, 1), np.float32), None, np.zeros(0, np.int64), np.zeros(0, np.int32), movie_ids, 0)
-    emb = np.ascontiguousarray(np.concatenate(embs, 0))
-    valid = np.concatenate(valids)
-    rowid = np.concatenate(rowids).astype(np.int64)
+        emb[n:n + size] = vec.reshape(size, d)
+        valid[n:n + size] = v
+        rowid[n:n + size] = np.frombuffer(rowid_blob, np.int64)[:size]
+        n += size
+    if emb is None:
+        return empty
     # trailing empty slots of the last block carry no information
-    last = int(np.nonzero(valid)[0][-1]) + 1
+    last = int(np.nonzero(valid[:n])[0][-1]) + 1
     emb, valid, rowid = emb[:last], valid[:last], rowid[:last]
-    mv = np.array([chunk_movie.get(int(r), None) if ok else None for r, ok in zip(rowid, valid)], object)
-    movie_idx = np.full(len(rowid), -1, np.int32)
-    have = np.array([m is not None for m in mv])
-    if have.any():
-        mids = np.array([int(m) for m in mv[have]], np.int64)
-        pos = np.searchsorted(movie_ids, mids)
-        ok = pos < len(movie_ids)
-        ok[ok] &= movie_ids[pos[ok]] == mids[ok]
-        tmp = np.where(ok, pos, -1).astype(np.int32)
-        movie_idx[np.nonzero(have)[0]] = tmp
+    # the two JOINs of semantic_search.py:262-279 as sorted-array lookups: chunks.id -> movie_id -> dense movie
+    # index; a live row without a chunks row, or whose movie is gone, keeps -1 (it still occupies its place in
+    # the KNN's top-K' and is dropped afterwards, as the inner JOINs drop it)
+    movie_idx = np.full(last, -1, np.int32)
+    if _table_exists(conn, "chunks"):
+        cm = np.array(cur.execute("SELECT id, movie_id FROM chunks ORDER BY id").fetchall(), np.int64).reshape(-1, 2)
+        if len(cm) and len(movie_ids):
+            live = np.nonzero(valid)[0]
+            cpos = np.searchsorted(cm[:, 0], rowid[live])
+            ok = cpos < len(cm)
+            ok[ok] &= cm[cpos[ok], 0] == rowid[live][ok]
+            mids = cm[cpos[ok], 1]
+            mpos = np.searchsorted(movie_ids, mids)
+            okm = mpos < len(movie_ids)
+            okm[okm] &= movie_ids[mpos[okm]] == mids[okm]
+            movie_idx[live[ok]] = np.where(okm, mpos, -1).astype(np.int32)
     return EmbArrays(emb=emb, valid=None if valid.all() else valid, rowid=rowid, movie_idx=movie_idx,
                      movie_ids=movie_ids, dim=int(dim))
 

@@ -197,6 +197,24 @@ def test_export_embeddings_physical_layout(tmp_path):
     arr2 = store.export_embeddings(conn)
     assert arr2.valid is not None and arr2.valid[5] == 0 and arr2.valid[77] == 0 and arr2.valid.sum() == n_chunks - 2
     assert arr2.movie_idx[9] == -1 and arr2.movie_idx[5] == -1
+    # a chunk whose MOVIE is gone is dropped by the second JOIN (semantic_search.py:275-276); the other rows keep
+    # their dense movie index into the shrunken movies table
+    gone = movie_of[20]
+    conn.execute("DELETE FROM movies WHERE id = ?", (gone,))
+    conn.commit()
+    arr3 = store.export_embeddings(conn)
+    for i in range(n_chunks):
+        want = -1 if (i in (5, 77, 9) or movie_of[i] == gone) else movie_of[i]
+        got = -1 if arr3.movie_idx[i] < 0 else int(arr3.movie_ids[arr3.movie_idx[i]])
+        assert got == want, i
+    # a block with no live row at all is skipped: the rows of the later blocks move up by 1024 physical slots
+    dead = np.zeros(1024, np.uint8)
+    conn.execute("UPDATE chunk_embeddings_chunks SET validity = ? WHERE chunk_id = 1",
+                 (np.packbits(dead, bitorder="little").tobytes(),))
+    conn.commit()
+    arr4 = store.export_embeddings(conn)
+    assert arr4.emb.shape[0] == n_chunks - 1024 and (arr4.rowid == np.arange(1024, n_chunks)).all()
+    assert (arr4.emb == arr.emb[1024:]).all() and (arr4.movie_idx == arr3.movie_idx[1024:]).all()
     conn.close()
 
 
