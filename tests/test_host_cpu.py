@@ -397,6 +397,62 @@ def test_rrf_search_stream_keeps_two_batches_in_flight_and_the_order(tmp_path):
     assert [h["id"] for h in out[3][1]] == [200, 201, 202] and [h["id"] for h in out[4][0]] == [300, 301, 302]
 
 
+def test_batch_entry_points_accept_both_token_forms(tmp_path):
+    """rrf_search_batch / weighted_search_batch over a fake handle: token lists and the pre-flattened
+    (tok_indptr, tokens) pair reach the handle as the same CSR and unpack to one result list PER QUERY (the flat
+    form is a 2-tuple: its length is not the number of queries)."""
+    from pathlib import Path
+    from rag_search_engine_b200 import hybrid_search as hsm, runtime
+    from rag_search_engine_b200.keyword_search import KeywordSearch
+    from rag_search_engine_b200.semantic_search import SemanticSearch
+
+    class FakeIndex:
+        calls = []
+        def set_id_tables(self, a, b):
+            pass
+        def hybrid(self, mode, param, limit, Q, tok_indptr, rows, **kw):
+            nq = len(tok_indptr) - 1
+            self.calls.append((mode, param, tok_indptr.tolist(), rows.tolist()))
+            oid = np.arange(nq * limit, dtype=np.int64).reshape(nq, limit)
+            osc = np.tile(1.0 / (1 + np.arange(limit)), (nq, 1))
+            a = np.tile(np.arange(limit, dtype=np.float64), (nq, 1))
+            b = -np.ones((nq, limit)) if mode == 0 else a / 2
+            return oid, osc, a, b, np.arange(nq, dtype=np.int32) % (limit + 1)
+
+    class Arr:
+        term_row = {"a": 0, "b": 1, "c": 2}
+        doc_ids = np.arange(3, dtype=np.int64)
+        movie_ids = np.arange(3, dtype=np.int64)
+        emb = np.zeros((4, 8), np.float32)
+
+    db = tmp_path / "y.db"
+    db.touch()
+    hs = hsm.HybridSearch.__new__(hsm.HybridSearch)
+    kw = KeywordSearch.__new__(KeywordSearch); kw._arr = Arr()
+    sem = SemanticSearch.__new__(SemanticSearch); sem._arr = Arr()
+    fake = FakeIndex()
+    hs.keyword, hs.semantic, hs._index, hs.db_path, hs.device, hs.tie_mode = kw, sem, fake, Path(db), 0, 0
+    key = (str(Path(db).resolve()), 0)
+    runtime._handles[key] = [fake, 1, {}]
+    try:
+        lists = [["a", "zz"], ["c"], [], ["b", "b", "a"], ["a"]]
+        flat = (np.cumsum([0] + [len(l) for l in lists]).astype(np.int32),
+                np.array([t for l in lists for t in l], dtype=np.str_))
+        Q = np.zeros((len(lists), 8), np.float32)
+        r1 = hs.rrf_search_batch(lists, Q, k=60, limit=4)
+        r2 = hs.rrf_search_batch(flat, Q, k=60, limit=4)
+        w1 = hs.weighted_search_batch(lists, Q, alpha=0.5, limit=4)
+        w2 = hs.weighted_search_batch(flat, Q, alpha=0.5, limit=4)
+    finally:
+        del runtime._handles[key]
+    assert fake.calls[0] == fake.calls[1] == (0, 60.0, [0, 2, 3, 3, 6, 7], [0, -1, 2, 1, 1, 0, 0])
+    assert fake.calls[2] == fake.calls[3] == (1, 0.5, [0, 2, 3, 3, 6, 7], [0, -1, 2, 1, 1, 0, 0])
+    assert r1 == r2 and w1 == w2
+    assert [len(x) for x in r1] == [0, 1, 2, 3, 4] == [len(x) for x in w1]
+    assert r1[1][0] == {"id": 4, "score": 1.0, "bm25_rank": 0, "sem_rank": None}
+    assert w1[4][3] == {"id": 19, "bm25": 3.0, "semantic": 1.5, "score": 0.25}
+
+
 def test_term_rows_list_form_and_flat_array_form_agree():
     """KeywordSearch._term_rows: dict lookups over token lists and one searchsorted over a flat numpy array of
     tokens give the same CSR rows (query order, duplicates kept, -1 = unknown term: keyword_search.py:205-210)."""
