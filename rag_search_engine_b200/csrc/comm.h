@@ -6,6 +6,7 @@
 #include <dlfcn.h>
 #include <nccl.h>   // types only (ncclComm_t, ncclUniqueId, ncclDataType_t); no symbol is linked
 
+#include <mutex>
 #include <string>
 
 namespace rse {
@@ -28,6 +29,8 @@ struct NcclApi {
 // Process-wide, loaded on first use.  `path` (optional, or $RSE_NCCL_LIB) overrides the soname lookup.
 inline NcclApi* nccl_api(const char* path = nullptr) {
   static NcclApi api;
+  static std::mutex mu;                       // two handles may ask for the communicator API at the same time
+  std::lock_guard<std::mutex> lock(mu);
   if (api.lib) return &api;
   const char* env = std::getenv("RSE_NCCL_LIB");
   const char* names[3] = {path, env, "libnccl.so.2"};
@@ -35,7 +38,8 @@ inline NcclApi* nccl_api(const char* path = nullptr) {
     if (!n || !*n) continue;
     api.lib = dlopen(n, RTLD_NOW | RTLD_GLOBAL);
     if (api.lib) break;
-    api.error = dlerror() ? dlerror() : "dlopen failed";
+    const char* why = dlerror();               // (dlerror() clears the message: a second call returns NULL)
+    api.error = why ? why : "dlopen failed";
   }
   if (!api.lib) {
     if (api.error.empty()) api.error = "libnccl.so.2 not found";
