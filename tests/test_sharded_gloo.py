@@ -1,4 +1,4 @@
-"""CPU, world_size 2, gloo: the N>1 host plumbing of rag_search_engine_b200.sharded (shard bounds,
+"""CPU, world_size 2 and 3, gloo: the N>1 host plumbing of rag_search_engine_b200.sharded (shard bounds,
 query slices, the candidate all_gather layout, per-slice merge+fuse, result assembly) with an
 oracle-backed stand-in for the per-rank librse calls.  The same ShardedHybrid object drives the
 real backend on the GPUs (bench.py --gpus N; tests/test_gpu_parity.py emulates the shards on one GPU)."""
@@ -121,8 +121,8 @@ def _worker(rank, world, port, out_q):
 
 
 @pytest.mark.timeout(300)
-def test_sharded_hybrid_two_ranks_gloo_equals_single_process():
-    world = 2
+@pytest.mark.parametrize("world", [2, 3])                # 7 queries: slices 4 + 3 and 3 + 2 + 2; 3 shards of unequal size
+def test_sharded_hybrid_gloo_equals_single_process(world):
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
     port = _free_port()
