@@ -78,11 +78,25 @@ class KeywordSearch:
 
     def _load(self) -> None:
         reg = runtime.parts(self.db_path, self.device)
-        if "bm25" not in reg:
-            arr = store.load_or_export(self.conn, self.db_path, "bm25")
+        full = store._db_fingerprint(self.conn, self.db_path)
+        fp = store.part_fingerprint(full, "bm25")
+        if "bm25" not in reg or reg.get("bm25_fp") != fp:
+            # first open of this database in the process — or the keyword tables changed under a live handle (a
+            # rebuild in place): export again and replace the device copy; every object on the handle reads its
+            # arrays through the registry (``_arr``), so they all move to the new index together
+            arr = store.load_or_export(self.conn, self.db_path, "bm25", fingerprint=full)
             self._index.load_bm25(arr.indptr, arr.doc_idx, arr.tf, arr.df, arr.dl, arr.n_movies, arr.avgdl)
-            reg["bm25"] = arr
-        self._arr: store.Bm25Arrays = reg["bm25"]
+            reg["bm25"], reg["bm25_fp"] = arr, fp
+            reg.pop("ids", None)                              # the fused path's id tables follow the arrays
+
+    @property
+    def _arr(self) -> store.Bm25Arrays:
+        own = self.__dict__.get("_arr_own")                  # set directly by from_loaded / tests
+        return own if own is not None else runtime.parts(self.db_path, self.device)["bm25"]
+
+    @_arr.setter
+    def _arr(self, value) -> None:
+        self.__dict__["_arr_own"] = value
 
     # ------------------------------------------------------------------ helpers mirrored from BaseSearchDB
     def count_movies(self) -> int:                            # basesearch_db.py:95-99
@@ -131,13 +145,14 @@ class KeywordSearch:
         return tok_indptr, rows
 
     def _sorted_vocab(self):
+        term_row = self._arr.term_row
         sv = getattr(self, "_vocab_sorted", None)
-        if sv is None:
-            terms = np.array(list(self._arr.term_row.keys()), dtype=np.str_)
-            rows = np.fromiter(self._arr.term_row.values(), np.int32, count=len(terms))
+        if sv is None or sv[0] is not term_row:              # (rebuilt when the arrays were replaced)
+            terms = np.array(list(term_row.keys()), dtype=np.str_)
+            rows = np.fromiter(term_row.values(), np.int32, count=len(terms))
             order = np.argsort(terms, kind="stable")
-            sv = self._vocab_sorted = (terms[order], rows[order])
-        return sv
+            sv = self._vocab_sorted = (term_row, terms[order], rows[order])
+        return sv[1], sv[2]
 
     def search_tokens(self, token_lists: Sequence[Sequence[str]], k: int = 10, k1: float = 1.5, b: float = 0.75):
         """Batch entry point on pre-tokenised queries → [(doc_id int64[n], score float64[n])] per query."""

@@ -102,8 +102,10 @@ class SemanticSearch:
 
     def _load(self) -> None:
         reg = runtime.parts(self.db_path, self.device)
-        if "emb" not in reg:
-            arr = store.load_or_export(self.conn, self.db_path, "emb")
+        full = store._db_fingerprint(self.conn, self.db_path)
+        fp = store.part_fingerprint(full, "emb")
+        if "emb" not in reg or reg.get("emb_fp") != fp:          # first open, or re-embedded under a live handle
+            arr = store.load_or_export(self.conn, self.db_path, "emb", fingerprint=full)
             if arr.emb.shape[0] > 0:
                 self._index.load_embeddings(arr.emb, valid=arr.valid, rowid=arr.rowid, movie_idx=arr.movie_idx)
             else:
@@ -112,8 +114,17 @@ class SemanticSearch:
                 self._index.dim = int(arr.dim) or (int(self.model.get_sentence_embedding_dimension())
                                                    if self.model is not None else 384)
                 self._index.n_rows = 0
-            reg["emb"] = arr
-        self._arr: store.EmbArrays = reg["emb"]
+            reg["emb"], reg["emb_fp"] = arr, fp
+            reg.pop("ids", None)
+
+    @property
+    def _arr(self) -> store.EmbArrays:
+        own = self.__dict__.get("_arr_own")                      # set directly by from_loaded / tests
+        return own if own is not None else runtime.parts(self.db_path, self.device)["emb"]
+
+    @_arr.setter
+    def _arr(self, value) -> None:
+        self.__dict__["_arr_own"] = value
 
     # ------------------------------------------------------------------ BaseSearchDB helpers
     def count_movies(self) -> int:

@@ -211,6 +211,8 @@ def _db_fingerprint(conn: sqlite3.Connection, db_path) -> dict:
     for t in ("movies", "terms", "postings", "doclen", "chunks", f"{VEC_TABLE}_chunks"):
         counts[t] = cur.execute(f"SELECT COUNT(*) FROM {t}").fetchone()[0] if _table_exists(conn, t) else -1
     probes = {}
+    if counts["movies"] > 0:
+        probes["movies"] = list(cur.execute("SELECT MAX(id), SUM(id) FROM movies").fetchone())
     if counts["doclen"] > 0:
         probes["doclen"] = list(cur.execute("SELECT MAX(doc_id), SUM(length) FROM doclen").fetchone())
     if counts["postings"] > 0:
@@ -250,6 +252,20 @@ def _db_fingerprint(conn: sqlite3.Connection, db_path) -> dict:
             "counts": counts, "probes": probes}
 
 
+def part_fingerprint(full: dict, part: str) -> str:
+    """What a LIVE handle's copy of ``part`` ('bm25' | 'emb') depends on: the row counts and content probes of
+    that part's tables out of ``_db_fingerprint`` (the other part's build — HybridSearch builds the keyword tables,
+    opens them, then builds the vectors — must not look like a change; file size / mtime / WAL state therefore
+    stay out).  The mirrors compare it at every open: a database rebuilt in place while this process still holds
+    its handle is re-exported and re-uploaded instead of being searched through the stale copy (the reference
+    re-reads SQLite on every query and cannot go stale)."""
+    tables = {"bm25": ("movies", "terms", "postings", "doclen"),
+              "emb": ("movies", "chunks", f"{VEC_TABLE}_chunks")}[part]
+    probes = {"bm25": ("movies", "doclen", "postings"), "emb": ("movies", "chunks", "vec0")}[part]
+    return json.dumps({"counts": {t: full["counts"].get(t) for t in tables},
+                       "probes": {k: full["probes"].get(k) for k in probes}}, sort_keys=True)
+
+
 def sidecar_path(db_path, part: str) -> Path:
     return Path(str(db_path) + f".rse-{part}.npz")
 
@@ -261,14 +277,15 @@ def emb_matrix_path(db_path) -> Path:
     return Path(str(db_path) + ".rse-emb.f32.npy")
 
 
-def load_or_export(conn: sqlite3.Connection, db_path, part: str, use_cache: bool = True):
+def load_or_export(conn: sqlite3.Connection, db_path, part: str, use_cache: bool = True, fingerprint: dict | None = None):
     """part = 'bm25' | 'emb'.  Exports once and keeps an .npz next to the database (plus, for 'emb', the
     matrix as a memory-mappable .npy); a later open whose fingerprint matches loads the arrays without
-    touching the big tables."""
+    touching the big tables.  ``fingerprint`` = a ``_db_fingerprint`` the caller has just taken (it counts the
+    big tables: once per open is enough)."""
     exporter = {"bm25": export_bm25, "emb": export_embeddings}[part]
     if not use_cache:
         return exporter(conn)
-    fp = json.dumps(_db_fingerprint(conn, db_path), sort_keys=True)
+    fp = json.dumps(fingerprint if fingerprint is not None else _db_fingerprint(conn, db_path), sort_keys=True)
     sc = sidecar_path(db_path, part)
     if sc.exists():
         try:

@@ -453,6 +453,59 @@ def test_batch_entry_points_accept_both_token_forms(tmp_path):
     assert w1[4][3] == {"id": 19, "bm25": 3.0, "semantic": 1.5, "score": 0.25}
 
 
+def test_rebuild_in_place_under_a_live_handle_is_reloaded(tmp_path, monkeypatch):
+    """The (database, device) handle registry must not serve a stale index: a database rebuilt in place while an
+    object of this process still holds the handle is re-exported and re-uploaded at the next open, every live
+    object then reads the NEW arrays, and an unchanged database is not uploaded twice (the other part's build —
+    vectors after keyword tables — is not a change of the keyword part)."""
+    from rag_search_engine_b200 import _lib, runtime, store
+    from rag_search_engine_b200.keyword_search import KeywordSearch
+    from rag_search_engine_b200.semantic_search import SemanticSearch
+    from rag_search_engine_b200.textutil import whitespace_tokenizer
+
+    class FakeIndex:
+        def __init__(self, device=0):
+            self.bm25_loads, self.emb_loads, self.closed = [], [], False
+        def load_bm25(self, indptr, doc_idx, tf, df, dl, n_movies, avgdl):
+            self.bm25_loads.append((int(n_movies), int(len(doc_idx))))
+        def load_embeddings(self, emb, valid=None, rowid=None, movie_idx=None):
+            self.emb_loads.append(tuple(emb.shape)); self.dim, self.n_rows = emb.shape[1], emb.shape[0]
+        def close(self):
+            self.closed = True
+
+    class Enc:
+        def get_sentence_embedding_dimension(self):
+            return 8
+
+    monkeypatch.setattr(_lib, "Index", FakeIndex)
+    docs, _, _ = _docs(5, 40)
+    rng = np.random.default_rng(0)
+    embed = lambda texts: rng.standard_normal((len(texts), 8)).astype(np.float32)      # noqa: E731
+    db = store.write_reference_db(tmp_path / "r.db", docs, whitespace_tokenizer, embed=embed)
+    kw1 = KeywordSearch(None, db, tokenizer=whitespace_tokenizer)
+    sem1 = SemanticSearch(None, db, encoder=Enc())
+    fake = kw1._index
+    assert sem1._index is fake and len(fake.bm25_loads) == 1 and len(fake.emb_loads) == 1
+    kw2 = KeywordSearch(None, db, tokenizer=whitespace_tokenizer)                       # unchanged: no second upload
+    assert len(fake.bm25_loads) == 1 and kw2._arr is kw1._arr
+    # rebuild in place with more documents while kw1 / kw2 / sem1 are alive
+    docs2, _, _ = _docs(6, 55)
+    store.write_reference_db(db, docs2, whitespace_tokenizer, embed=embed)
+    kw3 = KeywordSearch(None, db, tokenizer=whitespace_tokenizer)
+    assert kw3._index is fake and len(fake.bm25_loads) == 2 and fake.bm25_loads[-1][0] == 55
+    assert kw1._arr is kw3._arr and kw1._arr.n_movies == 55                            # live objects follow
+    ptr, rows = kw1._term_rows((np.array([0, 1], np.int32), np.array([next(iter(kw3._arr.term_row))], np.str_)))
+    assert rows.tolist() == [kw3._arr.term_row[next(iter(kw3._arr.term_row))]]          # sorted vocabulary rebuilt
+    assert len(fake.emb_loads) == 1                                                     # not reopened yet
+    sem2 = SemanticSearch(None, db, encoder=Enc())
+    assert len(fake.emb_loads) == 2 and sem1._arr is sem2._arr
+    assert sem1._arr.emb.shape[0] == sqlite3.connect(db).execute("SELECT COUNT(*) FROM chunks").fetchone()[0]
+    for o in (kw1, kw2, kw3, sem1, sem2):
+        assert not fake.closed
+        o.close()
+    assert fake.closed and not runtime._handles
+
+
 def test_term_rows_list_form_and_flat_array_form_agree():
     """KeywordSearch._term_rows: dict lookups over token lists and one searchsorted over a flat numpy array of
     tokens give the same CSR rows (query order, duplicates kept, -1 = unknown term: keyword_search.py:205-210)."""
