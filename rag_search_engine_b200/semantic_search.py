@@ -164,21 +164,38 @@ class SemanticSearch:
         Q = Q.reshape(-1, self._arr.dim)
         internal_k = max(k * knn_multiplier, k)                 # semantic_search.py:251
         dist, rowid, movie, cnt = self._index.knn_movies(Q, k, internal_k)
+        # the two JOINs of semantic_search.py:262-279 for the <= k final hits of every query: ONE lookup per table
+        # for the whole batch (a point query per hit costs more than the device call from ~100 hits on)
+        movie_ids = self._arr.movie_ids
+        live = np.arange(rowid.shape[1])[None, :] < np.asarray(cnt)[:, None]
+        chunk_meta = self._fetch("SELECT id, chunk_index, max_chunk_size, overlap FROM chunks WHERE id IN ({})",
+                                 np.unique(rowid[live]))
+        movie_meta = self._fetch("SELECT id, title, description FROM movies WHERE id IN ({})",
+                                 np.unique(movie_ids[movie[live]]))
         out = []
-        cur = self.conn.cursor()
         for q in range(Q.shape[0]):
             hits = []
             for j in range(cnt[q]):
                 cid = int(rowid[q, j])
-                movie_id = int(self._arr.movie_ids[movie[q, j]])
-                ci, mcs, ov = cur.execute("SELECT chunk_index, max_chunk_size, overlap FROM chunks WHERE id = ?",
-                                          (cid,)).fetchone()
-                title, desc = cur.execute("SELECT title, description FROM movies WHERE id = ?", (movie_id,)).fetchone()
+                movie_id = int(movie_ids[movie[q, j]])
+                ci, mcs, ov = chunk_meta[cid]
+                title, desc = movie_meta[movie_id]
                 hits.append({"chunk_id": cid, "distance": float(dist[q, j]),
                              "chunk": chunk_text(title, desc, int(ci), int(mcs), int(ov)),
                              "movie_id": movie_id, "title": title, "description": desc})
             out.append(hits)
         return out
+
+    def _fetch(self, sql: str, ids) -> Dict[int, tuple]:
+        """{id: rest of the row} for ``ids`` (int64 array), in slices below SQLite's bound-variable limit."""
+        got: Dict[int, tuple] = {}
+        cur = self.conn.cursor()
+        ids = [int(i) for i in ids]
+        for lo in range(0, len(ids), 900):
+            part = ids[lo:lo + 900]
+            for row in cur.execute(sql.format(",".join("?" * len(part))), part):
+                got[row[0]] = row[1:]
+        return got
 
     def query_top_k(self, query_text: str, k: int = 5, knn_multiplier: int = 10) -> List[Dict[str, Any]]:
         """semantic_search.py:225-340."""

@@ -506,6 +506,61 @@ def test_rebuild_in_place_under_a_live_handle_is_reloaded(tmp_path, monkeypatch)
     assert fake.closed and not runtime._handles
 
 
+def test_query_top_k_vec_builds_reference_shaped_hits_from_batched_lookups(tmp_path, monkeypatch):
+    """SemanticSearch.query_top_k_vec over a fake handle: the chunk / movie metadata of a whole batch comes from one
+    lookup per table, and every hit is the reference's dict (keys, key order, reconstructed chunk text:
+    semantic_search.py:321-340)."""
+    from rag_search_engine_b200 import _lib, store
+    from rag_search_engine_b200.semantic_search import SemanticSearch
+    from rag_search_engine_b200.textutil import chunk_text, whitespace_tokenizer
+
+    picks = {0: [7, 0, 33], 1: [], 2: [33, 12]}                  # query -> chunk rows returned by the "device"
+
+    class FakeIndex:
+        def __init__(self, device=0):
+            pass
+        def load_embeddings(self, emb, valid=None, rowid=None, movie_idx=None):
+            self.rowid, self.movie_idx, self.dim, self.n_rows = rowid, movie_idx, emb.shape[1], emb.shape[0]
+        def knn_movies(self, Q, k, kprime):
+            nq = Q.shape[0]
+            dist = np.zeros((nq, k), np.float32); row = np.full((nq, k), -1, np.int64)
+            mov = np.full((nq, k), -1, np.int32); cnt = np.zeros(nq, np.int32)
+            for q, rows in picks.items():
+                for j, r in enumerate(rows):
+                    dist[q, j], row[q, j], mov[q, j] = 0.125 * (j + 1), self.rowid[r], self.movie_idx[r]
+                cnt[q] = len(rows)
+            return dist, row, mov, cnt
+        def close(self):
+            pass
+
+    class Enc:
+        def get_sentence_embedding_dimension(self):
+            return 8
+
+    monkeypatch.setattr(_lib, "Index", FakeIndex)
+    docs, _, _ = _docs(9, 30)
+    rng = np.random.default_rng(1)
+    db = store.write_reference_db(tmp_path / "q.db", docs, whitespace_tokenizer,
+                                  embed=lambda t: rng.standard_normal((len(t), 8)).astype(np.float32))
+    ss = SemanticSearch(None, db, encoder=Enc())
+    try:
+        out = ss.query_top_k_vec(np.zeros((3, 8), np.float32), k=4)
+        conn = sqlite3.connect(db)
+        assert [len(h) for h in out] == [3, 0, 2]
+        for q, rows in picks.items():
+            for j, r in enumerate(rows):
+                mid, ci, mcs, ov = conn.execute("SELECT movie_id, chunk_index, max_chunk_size, overlap FROM chunks "
+                                                "WHERE id = ?", (r,)).fetchone()
+                title, desc = conn.execute("SELECT title, description FROM movies WHERE id = ?", (mid,)).fetchone()
+                hit = out[q][j]
+                assert list(hit) == ["chunk_id", "distance", "chunk", "movie_id", "title", "description"]
+                assert hit == {"chunk_id": r, "distance": 0.125 * (j + 1), "chunk": chunk_text(title, desc, ci, mcs, ov),
+                               "movie_id": mid, "title": title, "description": desc}
+        conn.close()
+    finally:
+        ss.close()
+
+
 def test_term_rows_list_form_and_flat_array_form_agree():
     """KeywordSearch._term_rows: dict lookups over token lists and one searchsorted over a flat numpy array of
     tokens give the same CSR rows (query order, duplicates kept, -1 = unknown term: keyword_search.py:205-210)."""
