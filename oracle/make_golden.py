@@ -11,6 +11,9 @@ What it pins:
                        (hybrid_search.py:91-180,183-272,379) driven through the reference's own
                        plugin seam (dummy retrievers monkeypatched on the module, exactly as
                        tests/test_hybrid_search.py:73-76 does), including structural ties.
+  * knn_kat.json     — vec0 KNN known answers (duplicates across block boundaries, mass ties, holes)
+                       from the pure-Python second restatement ``pyref.vec0_knn`` (sqlite-vec is not
+                       installable here: this fixture pins oracle.c against pyref, not against sqlite-vec).
 Floats are stored with float.hex() so the fixtures are bit-exact.
 """
 from __future__ import annotations
@@ -170,7 +173,54 @@ def fusion_golden():
     print("fusion_ref.json:", len(cases), "cases")
 
 
+# ----------------------------------------------------------------------------- vec0 KNN known answers
+def knn_kat_inputs(case: dict):
+    """(emb f32[n, dim], valid bool[n], queries f32[nq, dim]) of a fixture case, rebuilt from its seed — the fixture
+    stores the seed and the ANSWERS, not the matrix."""
+    import numpy as np
+    rng = np.random.default_rng(case["seed"])
+    n, dim = case["n"], case["dim"]
+    emb = rng.standard_normal((n, dim)).astype(np.float32)
+    emb *= rng.uniform(0.5, 2.0, (n, 1)).astype(np.float32)           # norms are recomputed per pair
+    emb = (np.round(emb * 4) / 4).astype(np.float32) if case["coarse"] else emb   # coarse grid: exact distance ties
+    for a, b in case["dups"]:
+        emb[b] = emb[a]
+    valid = np.ones(n, bool)
+    valid[case["holes"]] = False
+    Q = rng.standard_normal((case["nq"], dim)).astype(np.float32)
+    for j, r in enumerate(case["query_rows"]):
+        Q[j] = emb[r] * np.float32(1.5)
+    return emb, valid, Q
+
+
+def knn_golden():
+    """tests/golden/knn_kat.json — SURVEY §8c (3): vec0 KNN known answers with duplicate rows on both sides of
+    1024-row block boundaries, mass ties (coarse grid), deleted slots and k above a block's size, computed by the
+    pure-Python restatement (pyref.vec0_knn); tests/test_oracle_golden.py checks oracle.c — the checker of every GPU
+    parity test — against them."""
+    from oracle import pyref
+    cases = []
+    specs = [dict(seed=21, n=2100, dim=8, coarse=False, nq=5, query_rows=[1023, 5], holes=[3, 1024, 2099],
+                  dups=[[1023, 1024], [1023, 2047], [5, 900], [5, 2050], [2047, 2048]], ks=[1, 10, 100]),
+             dict(seed=22, n=1500, dim=4, coarse=True, nq=4, query_rows=[7], holes=[0, 7, 1499],
+                  dups=[[7, 8], [7, 1030], [100, 1023]], ks=[3, 64, 1100])]
+    for sp in specs:
+        emb, valid, Q = knn_kat_inputs(sp)
+        answers = []
+        for k in sp["ks"]:
+            for qi in range(len(Q)):
+                res = pyref.vec0_knn(emb, Q[qi], k, valid=valid)
+                answers.append({"k": k, "q": qi, "rows": [r for r, _ in res],
+                                "dist": [float(d).hex() for _, d in res]})
+        cases.append({**{kk: v for kk, v in sp.items() if kk != "ks"}, "answers": answers})
+    (GOLDEN / "knn_kat.json").write_text(json.dumps({"cases": cases}, separators=(",", ":")))
+    print("knn_kat.json:", sum(len(c["answers"]) for c in cases), "answers")
+
+
 if __name__ == "__main__":
+    import sys
     GOLDEN.mkdir(parents=True, exist_ok=True)
-    bm25_golden()
-    fusion_golden()
+    if "--knn-only" not in sys.argv:
+        bm25_golden()
+        fusion_golden()
+    knn_golden()

@@ -134,3 +134,59 @@ def set_union_order(a: Sequence[int], b: Sequence[int]) -> List[int]:
     da = {int(x): None for x in a}
     db = {int(x): None for x in b}
     return list(set(da.keys()) | set(db.keys()))
+
+
+# ----------------------------------------------------------------------------- vec0 KNN (second restatement)
+def vec0_knn(emb, q, k: int, valid=None, chunk_size: int = 1024) -> List[Tuple[int, float]]:
+    """``embedding MATCH :q AND k = :k`` on a vec0 table (semantic_search.py:254-261), restated a SECOND time,
+    independently of oracle.c and in the slowest possible way, so that the committed fixture
+    (tests/golden/knn_kat.json) pins the C restatement against an accidental change: numpy float32 SCALARS for the
+    three sequential accumulators of sqlite-vec's ``distance_cosine_float`` (v0.1.x; a = stored row, b = query),
+    Python floats (doubles) for the tail ``1 - dot / (sqrt(aMag) * sqrt(bMag))`` narrowed to f32; per 1024-row
+    block ``min_idx`` (repeated arg-min with ``<=`` while the slot ascends: among equal distances the HIGHEST slot
+    goes first) over the valid slots; ``merge_sorted_lists`` where the running list wins ties (earlier blocks
+    first).  ``emb`` is in physical order (row r = block r // 1024, slot r % 1024); ``valid`` marks live slots.
+    Returns [(row, distance)] in emit order.  Small inputs only (Python loops).  "Parity unpinned" like oracle.c:
+    sqlite-vec itself is not installable here (tests/test_sqlite_vec_crosscheck.py pins both the day it is)."""
+    import numpy as np
+    f32 = np.float32
+    n, dim = len(emb), len(q)
+    run: List[Tuple[int, float]] = []
+    for b0 in range(0, n, chunk_size):
+        slots = list(range(b0, min(n, b0 + chunk_size)))
+        dist: Dict[int, float] = {}
+        for r in slots:
+            if valid is not None and not valid[r]:
+                continue
+            dot = amag = bmag = f32(0.0)
+            a = emb[r]
+            for i in range(dim):
+                dot = f32(dot + f32(f32(a[i]) * f32(q[i])))
+                amag = f32(amag + f32(f32(a[i]) * f32(a[i])))
+                bmag = f32(bmag + f32(f32(q[i]) * f32(q[i])))
+            dist[r] = float(f32(1.0 - float(dot) / (math.sqrt(float(amag)) * math.sqrt(float(bmag)))))
+        taken: set = set()
+        top: List[int] = []
+        for _ in range(min(k, chunk_size)):
+            cand = [r for r in slots if r in dist and r not in taken]
+            if not cand:
+                break
+            mi = cand[0]
+            for r in slots:                                   # ascending slot, `<=`: the last equal one wins
+                if r in dist and r not in taken and dist[r] <= dist[mi]:
+                    mi = r
+            top.append(mi)
+            taken.add(mi)
+        merged: List[Tuple[int, float]] = []
+        pa = pb = 0
+        while len(merged) < k and (pa < len(run) or pb < len(top)):
+            if pa >= len(run):
+                merged.append((top[pb], dist[top[pb]])); pb += 1
+            elif pb >= len(top):
+                merged.append(run[pa]); pa += 1
+            elif run[pa][1] <= dist[top[pb]]:                 # the running list wins ties
+                merged.append(run[pa]); pa += 1
+            else:
+                merged.append((top[pb], dist[top[pb]])); pb += 1
+        run = merged
+    return run

@@ -128,6 +128,43 @@ def test_vec0_literal_scan_equals_key_order():
     assert r.tolist() == [1023, 100, 7, 2047, 1024]   # block 0 slots desc, then block 1 slots desc
 
 
+def test_vec0_knn_known_answers_fixture():
+    """tests/golden/knn_kat.json: answers of the pure-Python second restatement
+    (oracle/pyref.py::vec0_knn) — duplicates on both sides of block boundaries, mass ties on a coarse grid,
+    deleted slots, k above the block size — against oracle.c, rows / emit order / distance bits, through both of
+    its forms (literal block scan and closed-form key order)."""
+    from oracle.make_golden import knn_kat_inputs
+    fx = json.loads((GOLDEN / "knn_kat.json").read_text())
+    n_checked = 0
+    for case in fx["cases"]:
+        emb, valid, Q = knn_kat_inputs(case)
+        pos = np.nonzero(valid)[0].astype(np.int64)
+        live = np.ascontiguousarray(emb[valid])
+        for a in case["answers"]:
+            want_d = np.array([float.fromhex(h) for h in a["dist"]], np.float32)
+            for literal in (True, False):
+                d, r = oracle.vec0_knn(live, Q[a["q"]], a["k"], pos=pos, literal=literal)
+                assert pos[r].tolist() == a["rows"], (case["seed"], a["k"], a["q"], literal)
+                assert d.view(np.uint32).tolist() == want_d.view(np.uint32).tolist()
+            n_checked += 1
+        # the fixture really holds the hard cases: a duplicate pair split by a block boundary, emitted block-first
+        first = next(a for a in case["answers"] if a["q"] == 0 and a["k"] >= 3)
+        assert len(set(first["dist"][:2])) == 1 and first["rows"][0] // 1024 <= first["rows"][1] // 1024
+    assert n_checked == 27
+
+
+def test_pyref_vec0_knn_still_generates_the_fixture():
+    """The committed answers are what oracle/pyref.py::vec0_knn computes today (one small slice re-derived here:
+    the fixture cannot drift from the script that made it)."""
+    from oracle.make_golden import knn_kat_inputs
+    fx = json.loads((GOLDEN / "knn_kat.json").read_text())
+    case = fx["cases"][1]
+    emb, valid, Q = knn_kat_inputs(case)
+    for a in [x for x in case["answers"] if x["k"] <= 64][:4]:
+        res = pyref.vec0_knn(emb, Q[a["q"]], a["k"], valid=valid)
+        assert [r for r, _ in res] == a["rows"] and [float(d).hex() for _, d in res] == a["dist"]
+
+
 def test_vec0_distance_is_sequential_fp32():
     rng = np.random.default_rng(6)
     a = rng.standard_normal(384).astype(np.float32)
