@@ -31,6 +31,7 @@ from .textutil import Tokenizer, sentence_chunks
 VEC0_BLOCK = 1024
 TITLE_END_TOKEN = "[TITLE_END]"        # keyword_search.py:24
 VEC_TABLE = "chunk_embeddings"         # semantic_search.py:94
+EXPORT_SLICE_POSTINGS = 1 << 22        # export_bm25 reads the postings table in slices of about this many rows
 
 logger = logging.getLogger(__name__)
 
@@ -62,25 +63,32 @@ def export_bm25(conn: sqlite3.Connection) -> Bm25Arrays:
     T = len(terms)
     # postings in (term_id, doc_id) order = the autoindex order the reference reads them in (:214-218).  One result
     # row per TERM (group_concat over the (term_id, doc_id) autoindex), parsed in bulk: a Python tuple per posting
-    # costs ~1.3 us in sqlite3's row loop alone — minutes at 54 M postings — against ~0.5 us this way.  Term-id
-    # slices bound the size of the concatenated strings.
+    # costs ~1.3 us in sqlite3's row loop alone — minutes at 54 M postings — against ~0.5 us this way.
     t_list: List[np.ndarray] = []
     d_list: List[np.ndarray] = []
     f_list: List[np.ndarray] = []
-    (n_post,) = cur.execute("SELECT COUNT(*) FROM postings").fetchone()
-    if n_post:
-        t_lo, t_hi = cur.execute("SELECT MIN(term_id), MAX(term_id) FROM postings").fetchone()
-        n_slices = max(1, -(-n_post // (1 << 22)))
-        step = max(1, -(-(t_hi - t_lo + 1) // n_slices))
-        for lo in range(t_lo, t_hi + 1, step):
-            grp = cur.execute("SELECT term_id, COUNT(*), group_concat(doc_id), group_concat(json_array_length(positions)) "
-                              "FROM postings WHERE term_id >= ? AND term_id < ? GROUP BY term_id", (lo, lo + step)).fetchall()
-            if not grp:
+    # slices of ~4 M postings, cut on the per-term counts (term ids are handed out by first appearance, so the low
+    # ids hold most of a Zipfian index: equal-width id ranges would put nearly everything into the first slice)
+    per_term = np.array(cur.execute("SELECT term_id, COUNT(*) FROM postings GROUP BY term_id ORDER BY term_id").fetchall(),
+                        np.int64).reshape(-1, 2)
+    if len(per_term):
+        csum = np.cumsum(per_term[:, 1])
+        cuts = np.searchsorted(csum, np.arange(EXPORT_SLICE_POSTINGS, int(csum[-1]), EXPORT_SLICE_POSTINGS), side="left") + 1
+        starts = np.concatenate([[0], cuts]).astype(np.int64)
+        ends = np.concatenate([cuts, [len(per_term)]]).astype(np.int64)
+        for a, b in zip(starts.tolist(), ends.tolist()):
+            if a >= b:
                 continue
-            cnt = np.array([g[1] for g in grp], np.int64)
-            t_list.append(np.repeat(np.array([g[0] for g in grp], np.int64), cnt))
-            d_list.append(np.fromstring(",".join(g[2] for g in grp), dtype=np.int64, sep=","))
-            f_list.append(np.fromstring(",".join(g[3] for g in grp), dtype=np.int64, sep=","))
+            lo, hi = int(per_term[a, 0]), int(per_term[b - 1, 0])
+            grp = cur.execute("SELECT term_id, group_concat(doc_id), group_concat(json_array_length(positions)) "
+                              "FROM postings WHERE term_id >= ? AND term_id <= ? GROUP BY term_id ORDER BY term_id",
+                              (lo, hi)).fetchall()
+            cnt = per_term[a:b, 1]
+            if [g[0] for g in grp] != per_term[a:b, 0].tolist():
+                raise RuntimeError("postings export: the table changed while it was being read")
+            t_list.append(np.repeat(per_term[a:b, 0], cnt))
+            d_list.append(np.fromstring(",".join(g[1] for g in grp), dtype=np.int64, sep=","))
+            f_list.append(np.fromstring(",".join(g[2] for g in grp), dtype=np.int64, sep=","))
             if len(d_list[-1]) != cnt.sum() or len(f_list[-1]) != cnt.sum():
                 raise RuntimeError("postings export: group_concat row count mismatch")
     if t_list:

@@ -122,7 +122,7 @@ def _docs(seed=3, n=60):
     return docs, words, weights
 
 
-def test_export_bm25_round_trip_matches_reference_layout(tmp_path):
+def test_export_bm25_round_trip_matches_reference_layout(tmp_path, monkeypatch):
     from rag_search_engine_b200 import store
     from rag_search_engine_b200.textutil import whitespace_tokenizer
     docs, _, _ = _docs()
@@ -138,6 +138,13 @@ def test_export_bm25_round_trip_matches_reference_layout(tmp_path):
         a = slice(arr.indptr[r], arr.indptr[r + 1]); b = slice(csr["indptr"][row], csr["indptr"][row + 1])
         assert (arr.doc_idx[a] == csr["doc"][b]).all() and (arr.tf[a] == csr["tf"][b]).all()
         assert arr.df[r] == csr["df"][row]
+    # the table is read in slices cut on cumulative per-term counts: tiny slices (many cuts, single-term slices,
+    # a term larger than a slice) give the same arrays
+    monkeypatch.setattr(store, "EXPORT_SLICE_POSTINGS", 7)
+    arr_s = store.export_bm25(conn)
+    for f in ("indptr", "doc_idx", "tf", "df", "dl", "doc_ids"):
+        assert (getattr(arr_s, f) == getattr(arr, f)).all(), f
+    monkeypatch.undo()
     # a posting whose doc has no doclen row is counted in df (:222) but dropped from the CSR (:235-236)
     tid = conn.execute("SELECT id FROM terms LIMIT 1").fetchone()[0]
     conn.execute("INSERT INTO postings(term_id, doc_id, positions) VALUES (?, ?, ?)", (tid, 10**9, "[0, 1]"))
